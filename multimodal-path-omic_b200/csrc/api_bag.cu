@@ -1,0 +1,236 @@
+// extern "C" surface for the bag stage (declared in include/mpo_b200.h) + small auxiliary kernels.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include "../../include/mpo_b200.h"
+#include "mpo_ptx.cuh"
+#include "mpo_common.cuh"
+#include "launchers.h"
+
+namespace mpo {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail) {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+int check_cuda(cudaError_t e, const char* where) {
+  if (e == cudaSuccess) return MPO_OK;
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return MPO_E_CUDA;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
+  }
+  return n;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D row-major bf16 tensor [rows][cols]; box = box_cols x box_rows, 128-byte swizzle (box_cols * 2 B == 128 B)
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols,
+                      uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(MPO_E_CUDA, "%s", "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return MPO_E_CUDA;
+  }
+  return MPO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t i4 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i4 + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(src + i4);
+    const float4 b = *reinterpret_cast<const float4*>(src + i4 + 4);
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(dst + i4) = o;
+  } else {
+    for (int64_t i = i4; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
+// one block per tile: amap[i][row] = exp(scores[i][row] - lse[slide][i])
+__global__ void attn_map_kernel(const TileInfo* __restrict__ tile_info, const float* __restrict__ scores,
+                                const float* __restrict__ lse, float* __restrict__ amap, int total_rows) {
+  const TileInfo ti = tile_info[blockIdx.x];
+  const int r = threadIdx.x;
+  if (r >= ti.nvalid) return;
+#pragma unroll
+  for (int i = 0; i < kQ; ++i) {
+    const size_t o = static_cast<size_t>(i) * total_rows + ti.row0 + r;
+    amap[o] = __expf(scores[o] - lse[ti.slide * kQ + i]);
+  }
+}
+
+// lse_in [S][6], pooled_in [S][6][256] -> combined
+__global__ void lse_combine_kernel(const float* __restrict__ lse_in, const float* __restrict__ pooled_in, int S,
+                                   float* __restrict__ lse_out, float* __restrict__ pooled_out) {
+  const int i = blockIdx.x, d = threadIdx.x;
+  float M = -INFINITY;
+  for (int s = 0; s < S; ++s) M = fmaxf(M, lse_in[s * kQ + i]);
+  float L = 0.f, acc = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const float w = __expf(lse_in[s * kQ + i] - M);
+    L += w;
+    acc = fmaf(pooled_in[(static_cast<size_t>(s) * kQ + i) * kD + d], w, acc);
+  }
+  pooled_out[i * kD + d] = acc / L;
+  if (d == 0) lse_out[i] = M + __logf(L);
+}
+
+}  // namespace mpo
+
+using namespace mpo;
+
+extern "C" {
+
+const char* mpo_last_error(void) { return g_err; }
+int mpo_version(void) { return 100; }
+
+int mpo_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && (!src || !dst))) return fail(MPO_E_ARG, "%s", "mpo_cast_bf16: null pointer");
+  if (n == 0) return MPO_OK;
+  const int64_t groups = (n + 7) / 8;
+  const int threads = 256;
+  const int64_t blocks = (groups + threads - 1) / threads;
+  cast_bf16_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), n);
+  return check_cuda(cudaGetLastError(), "mpo_cast_bf16");
+}
+
+static int check_bag(const mpo_bag* bag, const char* who) {
+  if (!bag) return fail(MPO_E_ARG, "%s: bag is NULL", who);
+  if (bag->num_slides < 0 || bag->num_tiles < 0 || bag->total_rows < 0) return fail(MPO_E_ARG, "%s: negative size", who);
+  if (bag->total_rows > 0 && (!bag->x || !bag->tile_info || !bag->tile_prefix))
+    return fail(MPO_E_ARG, "%s: bag pointers are NULL", who);
+  if ((reinterpret_cast<uintptr_t>(bag->x) & 15) != 0) return fail(MPO_E_ARG, "%s: bag must be 16-byte aligned", who);
+  if (num_sms() <= 0) return fail(MPO_E_CUDA, "%s: no CUDA device (this library has no CPU fallback)", who);
+  return MPO_OK;
+}
+
+int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, const float* qk, float* scores,
+                float* part_ml, float* part_pool, float* pooled, float* lse, void* h_saved, uint32_t seed,
+                float drop_p, void* stream) {
+  int rc = check_bag(bag, "mpo_bag_fwd");
+  if (rc) return rc;
+  if (bag->total_rows == 0 || bag->num_tiles == 0) return MPO_OK;
+  if (!w_h_bf16 || !bias_h || !qk || !scores || !part_ml || !part_pool || !pooled || !lse)
+    return fail(MPO_E_ARG, "%s", "mpo_bag_fwd: null pointer");
+  if (drop_p < 0.f || drop_p >= 1.f) return fail(MPO_E_ARG, "%s", "mpo_bag_fwd: drop_p must be in [0,1)");
+  CUtensorMap tm_x, tm_w;
+  rc = make_tmap_bf16_2d(&tm_x, bag->x, static_cast<uint64_t>(bag->total_rows), kDIn, kBK, kTileM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tm_w, w_h_bf16, kD, kDIn, kBK, kD);
+  if (rc) return rc;
+  BagFwdParams p;
+  p.tile_info = reinterpret_cast<const TileInfo*>(bag->tile_info);
+  p.num_tiles = bag->num_tiles;
+  p.total_rows = static_cast<int>(bag->total_rows);
+  p.bias = bias_h;
+  p.qk = qk;
+  p.scores = scores;
+  p.part_ml = part_ml;
+  p.part_pool = part_pool;
+  p.h_out = static_cast<__nv_bfloat16*>(h_saved);
+  p.seed = seed;
+  p.drop_thr = static_cast<uint32_t>(drop_p * 256.f + 0.5f);
+  p.drop_scale = p.drop_thr ? 256.f / static_cast<float>(256 - p.drop_thr) : 1.f;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = check_cuda(launch_bag_fwd(tm_x, tm_w, p, num_sms(), st), "bag_fwd_kernel");
+  if (rc) return rc;
+  return check_cuda(launch_bag_merge(bag->tile_prefix, part_ml, part_pool, pooled, lse, bag->num_slides, st),
+                    "bag_merge_kernel");
+}
+
+int mpo_attn_map(const mpo_bag* bag, const float* scores, const float* lse, float* amap, void* stream) {
+  int rc = check_bag(bag, "mpo_attn_map");
+  if (rc) return rc;
+  if (bag->num_tiles == 0) return MPO_OK;
+  if (!scores || !lse || !amap) return fail(MPO_E_ARG, "%s", "mpo_attn_map: null pointer");
+  attn_map_kernel<<<bag->num_tiles, kTileM, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const TileInfo*>(bag->tile_info), scores, lse, amap, static_cast<int>(bag->total_rows));
+  return check_cuda(cudaGetLastError(), "attn_map_kernel");
+}
+
+int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, const float* lse, const float* pooled,
+                const float* dpooled, const float* qk, void* dz_ws, float* part_dqk, float* part_db, float* dqk,
+                float* grad_w_h, float* grad_b_h, float drop_p, void* stream) {
+  int rc = check_bag(bag, "mpo_bag_bwd");
+  if (rc) return rc;
+  if (bag->total_rows == 0 || bag->num_tiles == 0) return MPO_OK;
+  if (!h_saved || !scores || !lse || !pooled || !dpooled || !qk || !dz_ws || !part_dqk || !part_db || !dqk ||
+      !grad_w_h || !grad_b_h)
+    return fail(MPO_E_ARG, "%s", "mpo_bag_bwd: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BagBwdDzParams p;
+  p.tile_info = reinterpret_cast<const TileInfo*>(bag->tile_info);
+  p.num_tiles = bag->num_tiles;
+  p.total_rows = static_cast<int>(bag->total_rows);
+  p.h = static_cast<const __nv_bfloat16*>(h_saved);
+  p.scores = scores;
+  p.lse = lse;
+  p.pooled = pooled;
+  p.dpooled = dpooled;
+  p.qk = qk;
+  p.dz = static_cast<__nv_bfloat16*>(dz_ws);
+  p.part_dqk = part_dqk;
+  p.part_db = part_db;
+  const uint32_t thr = static_cast<uint32_t>(drop_p * 256.f + 0.5f);
+  p.keep_scale = thr ? 256.f / static_cast<float>(256 - thr) : 1.f;
+  rc = check_cuda(launch_bag_bwd_dz(p, st), "bag_bwd_dz_kernel");
+  if (rc) return rc;
+  rc = check_cuda(launch_bag_bwd_reduce(bag->tile_prefix, part_dqk, part_db, dqk, grad_b_h, bag->num_slides,
+                                        bag->num_tiles, st),
+                  "bag_bwd_reduce_kernel");
+  if (rc) return rc;
+  CUtensorMap tm_dz, tm_x;
+  rc = make_tmap_bf16_2d(&tm_dz, dz_ws, static_cast<uint64_t>(bag->total_rows), kD, 64, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tm_x, bag->x, static_cast<uint64_t>(bag->total_rows), kDIn, 64, 64);
+  if (rc) return rc;
+  return check_cuda(launch_bag_bwd_dw(tm_dz, tm_x, grad_w_h, static_cast<int>(bag->total_rows), num_sms(), st),
+                    "bag_bwd_dw_kernel");
+}
+
+int mpo_lse_combine(const float* lse_in, const float* pooled_in, int32_t nshards, float* lse_out, float* pooled_out,
+                    void* stream) {
+  if (nshards <= 0 || !lse_in || !pooled_in || !lse_out || !pooled_out)
+    return fail(MPO_E_ARG, "%s", "mpo_lse_combine: bad arguments");
+  lse_combine_kernel<<<kQ, kD, 0, static_cast<cudaStream_t>(stream)>>>(lse_in, pooled_in, nshards, lse_out, pooled_out);
+  return check_cuda(cudaGetLastError(), "lse_combine_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,373 @@
+// Bag-pass forward for MCAT (reference: models/mcat/mcat.py:87 `H_bag = self.H(wsi)` and :97 co-attention).
+//
+// One persistent CTA per SM streams 128-patch tiles of the packed bf16 bag:
+//   TMA (warp 0)  : X tile [128 x 1024] and W_H [256 x 1024] in 64-wide K blocks, 128B-swizzled, 3-stage ring
+//   MMA (warp 1)  : tcgen05.mma M=128 N=256 K=16, fp32 accumulators in TMEM, two accumulator stages
+//   epilogue (8 w): TMEM -> registers; +bias, ReLU, (dropout); six folded-query dots per patch (fp32);
+//                   H tile staged once in shared memory as bf16; tile-local softmax statistics;
+//                   pooled[6,256] += p^T H from the staged tile; per-tile (m, l, pooled) partial written.
+// The K/V projections of the reference's nn.MultiheadAttention are folded away exactly:
+//   score_in = h_n . (W_k^T q_i)/sqrt(d)   (the b_k term is constant over n and cancels in the softmax)
+//   out_i    = W_v (sum_n a_in h_n) + b_v  (done in the tail on the pooled vector)
+// A second kernel merges the per-tile partials by log-sum-exp per slide.
+#include "mpo_ptx.cuh"
+#include "mpo_common.cuh"
+
+namespace mpo {
+
+constexpr int kStages = 3;
+constexpr int kABytes = kTileM * kBK * 2;            // 16 KB
+constexpr int kBBytes = kD * kBK * 2;                // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;       // 48 KB
+constexpr int kStagingBytes = kTileM * kD * 2;       // 64 KB  bf16 H tile, K-major SW128 (4 blocks of 128x64)
+constexpr int kEpiThreads = 256;
+constexpr int kFwdThreads = 64 + kEpiThreads;
+
+struct FwdSmem {
+  // offsets from the 1024-aligned base
+  static constexpr int stages = 0;
+  static constexpr int staging = kStages * kStageBytes;                 // 147456
+  static constexpr int qk = staging + kStagingBytes;                    // fp32 [6][256]
+  static constexpr int bias = qk + kQ * kD * 4;                         // fp32 [256]
+  static constexpr int P = bias + kD * 4;                               // fp32 [128][8]
+  static constexpr int spart = P + kTileM * 8 * 4;                      // fp32 [128][8]
+  static constexpr int wred = spart + kTileM * 8 * 4;                   // fp32 [2][4][8]
+  static constexpr int bars = wred + 2 * 4 * 8 * 4;                     // mbarriers
+  static constexpr int tmem_slot = bars + 16 * 8;
+  static constexpr int total = tmem_slot + 16;
+};
+constexpr int kFwdSmemBytes = FwdSmem::total + 1024;  // + slack for manual 1024 B alignment
+
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
+bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+               const BagFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::bars);
+  uint64_t* full_bar = bars;                 // [kStages]
+  uint64_t* empty_bar = bars + kStages;      // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FwdSmem::tmem_slot);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kEpiThreads / 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      const uint64_t pol_stream = policy_evict_first();   // the bag is read once per pass
+      const uint64_t pol_keep = policy_evict_last();      // W_H is re-read by every tile: keep it in L2
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int row0 = p.tile_info[t].row0;
+        for (int kb = 0; kb < kKBlocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + FwdSmem::stages + stage * kStageBytes;
+          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          tma_load_2d(sa, &tm_x, &full_bar[stage], kb * kBK, row0, pol_stream);
+          tma_load_2d(sa + kABytes, &tm_w, &full_bar[stage], kb * kBK, 0, pol_keep);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, kD, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);   // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kD;
+        for (int kb = 0; kb < kKBlocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + FwdSmem::stages + stage * kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);        // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps (2..9)
+    const int et = threadIdx.x - 64;           // 0..255
+    const int qd = warp & 3;                   // TMEM lane quadrant this warp may access
+    const int ch = (warp - 2) >> 2;            // column half handled in phase 1
+    const int r = qd * 32 + lane;              // tile row (patch) owned in phase 1
+    float* qk_s = reinterpret_cast<float*>(smem + FwdSmem::qk);
+    float* bias_s = reinterpret_cast<float*>(smem + FwdSmem::bias);
+    float* P_s = reinterpret_cast<float*>(smem + FwdSmem::P);
+    float* spart_s = reinterpret_cast<float*>(smem + FwdSmem::spart);
+    float* wmax_s = reinterpret_cast<float*>(smem + FwdSmem::wred);
+    float* wsum_s = wmax_s + 4 * 8;
+    uint8_t* staging = smem + FwdSmem::staging;
+    float* red_s = reinterpret_cast<float*>(staging);   // aliases the staged tile after phase 2
+
+    bias_s[et] = p.bias[et];
+    int cur_slide = -1;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const TileInfo ti = p.tile_info[t];
+      if (ti.slide != cur_slide) {
+        cur_slide = ti.slide;
+        const float* src = p.qk + static_cast<size_t>(ti.slide) * kQ * kD;
+#pragma unroll
+        for (int j = 0; j < kQ; ++j) qk_s[et + j * 256] = src[et + j * 256];
+      }
+      named_bar_sync(1, kEpiThreads);   // qk/bias visible; previous tile's reduction buffer is free
+
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+
+      // ---- phase 1: accumulator -> h (fp32) -> score partials, bf16 tile in shared memory
+      float s[kQ];
+#pragma unroll
+      for (int i = 0; i < kQ; ++i) s[i] = 0.f;
+      const uint32_t grow = static_cast<uint32_t>(ti.row0 + r);
+#pragma unroll 1
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int col0 = ch * 128 + c4 * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + as * kD + col0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float h[8];
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col0 + j);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col0 + j + 4);
+          h[0] = __uint_as_float(v[j + 0]) + b0.x;
+          h[1] = __uint_as_float(v[j + 1]) + b0.y;
+          h[2] = __uint_as_float(v[j + 2]) + b0.z;
+          h[3] = __uint_as_float(v[j + 3]) + b0.w;
+          h[4] = __uint_as_float(v[j + 4]) + b1.x;
+          h[5] = __uint_as_float(v[j + 5]) + b1.y;
+          h[6] = __uint_as_float(v[j + 6]) + b1.z;
+          h[7] = __uint_as_float(v[j + 7]) + b1.w;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) h[e] = fmaxf(h[e], 0.f);
+          if (p.drop_thr != 0) {
+            // one 32-bit draw covers four consecutive features of this patch row
+            const uint32_t base = (grow * kD + col0 + j) >> 2;
+            const uint32_t r0 = rng_u32(p.seed, 0u, base);
+            const uint32_t r1 = rng_u32(p.seed, 0u, base + 1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              h[e] = (((r0 >> (8 * e)) & 0xFFu) < p.drop_thr) ? 0.f : h[e] * p.drop_scale;
+              h[4 + e] = (((r1 >> (8 * e)) & 0xFFu) < p.drop_thr) ? 0.f : h[4 + e] * p.drop_scale;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) {
+            const float4 q0 = *reinterpret_cast<const float4*>(qk_s + i * kD + col0 + j);
+            const float4 q1 = *reinterpret_cast<const float4*>(qk_s + i * kD + col0 + j + 4);
+            s[i] = fmaf(h[0], q0.x, s[i]);
+            s[i] = fmaf(h[1], q0.y, s[i]);
+            s[i] = fmaf(h[2], q0.z, s[i]);
+            s[i] = fmaf(h[3], q0.w, s[i]);
+            s[i] = fmaf(h[4], q1.x, s[i]);
+            s[i] = fmaf(h[5], q1.y, s[i]);
+            s[i] = fmaf(h[6], q1.z, s[i]);
+            s[i] = fmaf(h[7], q1.w, s[i]);
+          }
+          uint4 pk;
+          pk.x = pack_bf16x2(h[0], h[1]);
+          pk.y = pack_bf16x2(h[2], h[3]);
+          pk.z = pack_bf16x2(h[4], h[5]);
+          pk.w = pack_bf16x2(h[6], h[7]);
+          const int j16 = (col0 + j) >> 3;           // 16-byte chunk index within the 512 B row
+          const int cb = j16 >> 3, jj = j16 & 7;     // 64-feature block, chunk within the 128 B swizzle row
+          *reinterpret_cast<uint4*>(staging + cb * (kTileM * 128) + r * 128 + ((jj ^ (r & 7)) << 4)) = pk;
+        }
+      }
+      // accumulator stage fully read: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+
+      if (ch == 1) {
+        *reinterpret_cast<float4*>(spart_s + r * 8) = make_float4(s[0], s[1], s[2], s[3]);
+        *reinterpret_cast<float2*>(spart_s + r * 8 + 4) = make_float2(s[4], s[5]);
+      }
+      named_bar_sync(1, kEpiThreads);
+
+      // ---- tile-local softmax statistics (threads of column half 0 own one patch row each)
+      const bool valid = r < ti.nvalid;
+      if (ch == 0) {
+        const float4 o0 = *reinterpret_cast<const float4*>(spart_s + r * 8);
+        const float2 o1 = *reinterpret_cast<const float2*>(spart_s + r * 8 + 4);
+        s[0] += o0.x; s[1] += o0.y; s[2] += o0.z; s[3] += o0.w; s[4] += o1.x; s[5] += o1.y;
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
+          if (valid) p.scores[static_cast<size_t>(i) * p.total_rows + ti.row0 + r] = s[i];
+          float m = valid ? s[i] : -INFINITY;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          if (lane == 0) wmax_s[qd * 8 + i] = m;
+        }
+      }
+      named_bar_sync(1, kEpiThreads);
+      if (ch == 0) {
+        float pr[8];
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
+          const float m = fmaxf(fmaxf(wmax_s[i], wmax_s[8 + i]), fmaxf(wmax_s[16 + i], wmax_s[24 + i]));
+          pr[i] = valid ? __expf(s[i] - m) : 0.f;
+          float l = pr[i];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+          if (lane == 0) wsum_s[qd * 8 + i] = l;
+          if (et == 0) p.part_ml[static_cast<size_t>(t) * 12 + i] = m;   // et==0 is warp 2 lane 0 (ch 0)
+        }
+        pr[6] = 0.f; pr[7] = 0.f;
+        *reinterpret_cast<float4*>(P_s + r * 8) = make_float4(pr[0], pr[1], pr[2], pr[3]);
+        *reinterpret_cast<float4*>(P_s + r * 8 + 4) = make_float4(pr[4], pr[5], pr[6], pr[7]);
+      }
+      named_bar_sync(1, kEpiThreads);
+      if (et < kQ) {
+        p.part_ml[static_cast<size_t>(t) * 12 + 6 + et] =
+            wsum_s[et] + wsum_s[8 + et] + wsum_s[16 + et] + wsum_s[24 + et];
+      }
+
+      // ---- phase 2: pooled[i][d] += sum_n p[n][i] * h[n][d] from the staged bf16 tile
+      const int fg = et & 63;    // four features 4fg..4fg+3
+      const int pg = et >> 6;    // 32 patch rows pg*32..pg*32+31
+      float acc[kQ][4];
+#pragma unroll
+      for (int i = 0; i < kQ; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+      {
+        const int j16 = fg >> 1, cb = j16 >> 3, jj = j16 & 7;
+        const uint8_t* colbase = staging + cb * (kTileM * 128) + (fg & 1) * 8;
+        __nv_bfloat16* hout = p.h_out;
+#pragma unroll 4
+        for (int nn = 0; nn < 32; ++nn) {
+          const int n = pg * 32 + nn;
+          const uint2 hv = *reinterpret_cast<const uint2*>(colbase + n * 128 + ((jj ^ (n & 7)) << 4));
+          const float4 p0 = *reinterpret_cast<const float4*>(P_s + n * 8);
+          const float2 p1 = *reinterpret_cast<const float2*>(P_s + n * 8 + 4);
+          const float h0 = bf16lo_to_f32(hv.x), h1 = bf16hi_to_f32(hv.x);
+          const float h2 = bf16lo_to_f32(hv.y), h3 = bf16hi_to_f32(hv.y);
+          const float pw[kQ] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y};
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) {
+            acc[i][0] = fmaf(pw[i], h0, acc[i][0]);
+            acc[i][1] = fmaf(pw[i], h1, acc[i][1]);
+            acc[i][2] = fmaf(pw[i], h2, acc[i][2]);
+            acc[i][3] = fmaf(pw[i], h3, acc[i][3]);
+          }
+          if (hout != nullptr && n < ti.nvalid) {
+            *reinterpret_cast<uint2*>(hout + static_cast<size_t>(ti.row0 + n) * kD + fg * 4) = hv;
+          }
+        }
+      }
+      named_bar_sync(1, kEpiThreads);    // every read of the staged tile is done -> reuse it for the reduction
+#pragma unroll
+      for (int i = 0; i < kQ; ++i) {
+        *reinterpret_cast<float4*>(red_s + pg * (kQ * kD) + i * kD + fg * 4) =
+            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      }
+      named_bar_sync(1, kEpiThreads);
+      float* dst = p.part_pool + static_cast<size_t>(t) * (kQ * kD);
+#pragma unroll
+      for (int j = 0; j < kQ; ++j) {
+        const int e = et + j * 256;
+        dst[e] = red_s[e] + red_s[kQ * kD + e] + red_s[2 * kQ * kD + e] + red_s[3 * kQ * kD + e];
+      }
+      // the barrier at the top of the next iteration orders these reads before the next phase-1 writes
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSE merge of per-tile partials -> pooled[B][6][256] (normalised) and lse[B][6]
+// (the same combine is reused across GPUs for a patch-range-sharded bag, see lse_combine in bag_aux.cu)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bag_merge_kernel(const int* __restrict__ tile_prefix,   // [B+1] first tile of each slide
+                 const float* __restrict__ part_ml, const float* __restrict__ part_pool,
+                 float* __restrict__ pooled, float* __restrict__ lse) {
+  const int b = blockIdx.x, i = blockIdx.y, d = threadIdx.x;
+  const int t0 = tile_prefix[b], t1 = tile_prefix[b + 1];
+  float M = -INFINITY;
+  for (int t = t0; t < t1; ++t) M = fmaxf(M, part_ml[static_cast<size_t>(t) * 12 + i]);
+  float L = 0.f, acc = 0.f;
+  for (int t = t0; t < t1; ++t) {
+    const float w = __expf(part_ml[static_cast<size_t>(t) * 12 + i] - M);
+    L = fmaf(part_ml[static_cast<size_t>(t) * 12 + 6 + i], w, L);
+    acc = fmaf(part_pool[(static_cast<size_t>(t) * kQ + i) * kD + d], w, acc);
+  }
+  pooled[(static_cast<size_t>(b) * kQ + i) * kD + d] = acc / L;
+  if (d == 0) lse[b * kQ + i] = M + __logf(L);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers (C++ side; the extern "C" surface is in api.cu)
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const BagFwdParams& prm, int num_sms,
+                           cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(bag_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (prm.num_tiles <= 0) return cudaSuccess;
+  const int grid = prm.num_tiles < num_sms ? prm.num_tiles : num_sms;
+  bag_fwd_kernel<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(tm_x, tm_w, prm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, const float* part_pool, float* pooled,
+                             float* lse, int B, cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  bag_merge_kernel<<<dim3(B, kQ), 256, 0, stream>>>(tile_prefix, part_ml, part_pool, pooled, lse);
+  return cudaGetLastError();
+}
+
+}  // namespace mpo

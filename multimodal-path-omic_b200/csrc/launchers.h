@@ -1,0 +1,24 @@
+// C++-side launch functions shared between the kernel translation units and the extern "C" surface.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "mpo_common.cuh"
+
+namespace mpo {
+
+extern thread_local char g_err[512];
+int fail(int code, const char* fmt, const char* detail);
+int check_cuda(cudaError_t e, const char* where);
+int num_sms();
+
+cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const BagFwdParams& prm, int num_sms,
+                           cudaStream_t stream);
+cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, const float* part_pool, float* pooled,
+                             float* lse, int B, cudaStream_t stream);
+cudaError_t launch_bag_bwd_dz(const BagBwdDzParams& prm, cudaStream_t stream);
+cudaError_t launch_bag_bwd_reduce(const int* tile_prefix, const float* part_dqk, const float* part_db, float* dqk,
+                                  float* grad_bias, int B, int num_tiles, cudaStream_t stream);
+cudaError_t launch_bag_bwd_dw(const CUtensorMap& tm_dz, const CUtensorMap& tm_x, float* grad_w, int total_rows,
+                              int num_sms, cudaStream_t stream);
+
+}  // namespace mpo

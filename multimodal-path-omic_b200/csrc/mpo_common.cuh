@@ -1,0 +1,55 @@
+// Shared constants and parameter blocks of the slide hot path (medium model: 1024 -> 256, 6 omic queries).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+namespace mpo {
+
+constexpr int kDIn = 1024;    // patch feature width          (reference: models/mcat/mcat.py:25)
+constexpr int kD = 256;       // model width, medium           (reference: models/mcat/mcat.py:18-19)
+constexpr int kQ = 6;         // omic signature queries
+constexpr int kTileM = 128;   // patches per bag tile (one UMMA M)
+constexpr int kBK = 64;       // K elements per pipeline stage (128 B of bf16 = one swizzle row)
+constexpr int kKBlocks = kDIn / kBK;
+
+// one entry per 128-patch tile of the packed bag
+struct TileInfo {
+  int slide;     // slide index in the batch
+  int row0;      // first packed-bag row of the tile
+  int nvalid;    // rows of this tile that belong to `slide` (1..128)
+  int tile_in_slide;
+};
+
+struct BagFwdParams {
+  const TileInfo* tile_info;   // [num_tiles]
+  int num_tiles;
+  int total_rows;
+  const float* bias;           // [256]                       H.0.bias
+  const float* qk;             // [B][6][256]                 folded queries (W_k^T q_i / 16)
+  float* scores;               // [6][total_rows]             raw scores (pre-softmax)
+  float* part_ml;              // [num_tiles][12]             tile max (6) and tile sum of exp (6)
+  float* part_pool;            // [num_tiles][6][256]         sum_n exp(s - m_tile) h_n
+  __nv_bfloat16* h_out;        // [total_rows][256] or null   saved activations for the backward pass
+  uint32_t seed;               // dropout stream (train mode)
+  uint32_t drop_thr;           // drop an element when its 8 random bits < drop_thr (0 = eval)
+  float drop_scale;            // 1 / keep probability
+};
+
+struct BagBwdDzParams {
+  const TileInfo* tile_info;
+  int num_tiles;
+  int total_rows;
+  const __nv_bfloat16* h;      // [total_rows][256] saved by the forward pass
+  const float* scores;         // [6][total_rows]
+  const float* lse;            // [B][6]
+  const float* pooled;         // [B][6][256]
+  const float* dpooled;        // [B][6][256]
+  const float* qk;             // [B][6][256]
+  __nv_bfloat16* dz;           // [total_rows][256]
+  float* part_dqk;             // [num_tiles][6][256]
+  float* part_db;              // [num_tiles][256]
+  float keep_scale;            // 1/(1-p) in train mode, 1 in eval
+};
+
+}  // namespace mpo
