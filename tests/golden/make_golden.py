@@ -1,0 +1,109 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference modules (needs /root/reference).
+
+Run from the repository root in the build container:   python tests/golden/make_golden.py
+The reference cannot travel to the GPU box, these small fixtures do.  Weights and inputs are not stored: both
+come from multimodal-path-omic_b200/synth.py (numpy PCG64), which tests re-run to rebuild the identical case.
+Stored per case: hazards, S, Y, risk, attention maps, NLL and CES losses, and a digest (norm, random projection,
+16 samples) of every parameter gradient of the NLL loss, from the reference's own autograd in eval() mode.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+CASES = [
+    # name,             model,     fusion,     N,    seed, sharpen
+    ("mcat_concat_300", "mcat", "concat", 300, 1, 1.0),
+    ("mcat_concat_sharp_517", "mcat", "concat", 517, 2, 8.0),
+    ("mcat_concat_4096", "mcat", "concat", 4096, 3, 4.0),
+    ("mcat_concat_2", "mcat", "concat", 2, 4, 1.0),
+    ("mcat_concat_128", "mcat", "concat", 128, 5, 8.0),
+    ("mcat_bilinear_200", "mcat", "bilinear", 200, 6, 4.0),
+    ("nacagat_concat_300", "nacagat", "concat", 300, 7, 1.0),
+    ("nacagat_concat_sharp_517", "nacagat", "concat", 517, 8, 8.0),
+    ("nacagat_bilinear_200", "nacagat", "bilinear", 200, 9, 4.0),
+    ("nacagat_concat_4096", "nacagat", "concat", 4096, 10, 4.0),
+]
+
+
+def import_reference():
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))      # models/utils.py:1 imports it, unused on this path
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from models.mcat.mcat import MultimodalCoAttentionTransformer
+    from models.nacagat.nacagat import NarrowContextualAttentionGateTransformer
+    from models.loss import NegativeLogLikelihoodSurvivalLoss, CrossEntropySurvivalLoss
+    return (MultimodalCoAttentionTransformer, NarrowContextualAttentionGateTransformer,
+            NegativeLogLikelihoodSurvivalLoss, CrossEntropySurvivalLoss)
+
+
+def main():
+    from importlib import import_module
+    synth = import_module("multimodal-path-omic_b200.synth")
+    MCAT, NACAGAT, NLL, CES = import_reference()
+    torch.set_num_threads(8)
+    outdir = os.path.dirname(os.path.abspath(__file__))
+    for name, model, fusion, n, seed, sharpen in CASES:
+        cls = MCAT if model == "mcat" else NACAGAT
+        torch.manual_seed(seed)
+        net = cls(omic_sizes=list(synth.OMIC_SIZES), fusion=fusion)
+        shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        state = synth.make_state(shapes, seed, model=model, sharpen=sharpen)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()})
+        net.eval()
+        bag, omics, label, censor = synth.make_slide(seed, n)
+        wsi = torch.from_numpy(bag)
+        om = [torch.from_numpy(o) for o in omics]
+        Y_t = torch.tensor([[label]], dtype=torch.int64)
+        c_t = torch.tensor([censor])
+        if model == "mcat":
+            hazards, S, Y, att = net(wsi=wsi, omics=om, inference=True)
+        else:
+            hazards, S, Y, att = net(wsi=wsi, omics=om)
+        loss_nll = NLL()(hazards, S, Y_t, c_t)
+        loss_ces = CES()(hazards, S, Y_t, c=c_t)
+        net.zero_grad()
+        loss_nll.backward()
+        rec = dict(
+            hazards=hazards.detach().numpy(), S=S.detach().numpy(), Y=Y.detach().numpy(),
+            risk=(-torch.sum(S, dim=1)).detach().numpy(),
+            coattn=att["coattn"].detach().numpy(), path=att["path"].detach().numpy(),
+            omic=att["omic"].detach().numpy(),
+            loss_nll=np.float64(loss_nll.item()), loss_ces=np.float64(loss_ces.item()),
+            meta=np.array([n, seed, label, censor, sharpen], dtype=np.float64),
+        )
+        names = []
+        for k, p_ in net.named_parameters():
+            g = p_.grad.detach().numpy() if p_.grad is not None else np.zeros(tuple(p_.shape), np.float32)
+            rec["gd/" + k] = synth.grad_digest(k, g)
+            names.append(k)
+        rec["param_names"] = np.array(names)
+        rec["param_shapes"] = np.array([str(shapes[k]) for k in names])
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), **rec)
+        print(f"{name}: hazards={rec['hazards'].round(5).tolist()} loss_nll={rec['loss_nll']:.6f} "
+              f"coattn max={rec['coattn'].max():.3e} min={rec['coattn'].min():.3e}")
+
+    # loss known answers: the reference's own test vectors (models/loss.py:108-121) plus the SURVEY 8c probes
+    hz = torch.tensor([0.51, 0.52, 0.49, 0.48]).reshape(1, 4)
+    S = torch.tensor([0.5, 0.4, 0.2, 0.1]).reshape(1, 4)
+    rows = []
+    for y in range(4):
+        for c in (0.0, 1.0):
+            if y + 1 > 4:
+                continue
+            ln = NLL()(hz, S, torch.tensor([y]), torch.tensor([c])).item() if y < 4 else float("nan")
+            lc = CES()(hz, S, torch.tensor([y]), torch.tensor([c])).item()
+            rows.append([y, c, ln, lc])
+    np.savez_compressed(os.path.join(outdir, "loss_known_answers.npz"), hazards=hz.numpy(), S=S.numpy(),
+                        table=np.array(rows, dtype=np.float64))
+    print("loss table:\n", np.array(rows))
+
+
+if __name__ == "__main__":
+    main()

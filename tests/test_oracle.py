@@ -1,0 +1,88 @@
+"""The oracle (oracle/mpo_oracle.py) against the reference: golden fixtures generated from the unmodified
+reference modules (tests/golden/make_golden.py) and the reference's own known-answer loss test."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_DIR, digest_errors, golden_cases, load_case
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import mpo_oracle as orc  # noqa: E402
+
+OUT_TOL = 2e-4     # reference runs in fp32, the oracle in fp64
+GRAD_TOL = 1e-3    # norm-relative, with the noise floor of helpers.digest_errors
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_oracle_matches_reference_fixture(name):
+    c = load_case(name)
+    out = orc.model_forward_backward(c["state"], c["bag"], c["omics"], c["label"], c["censor"], model=c["model"],
+                                     fusion=c["fusion"], loss="nll")
+    g = c["gold"]
+    for k in ("hazards", "S", "Y", "risk", "coattn", "path", "omic"):
+        ref = g[k]
+        err = np.max(np.abs(out[k] - ref) / (np.abs(ref) + 1e-9))
+        assert err < OUT_TOL, (k, err)
+    assert abs(out["loss"] - float(g["loss_nll"])) < 1e-5
+    ces = orc.model_forward_backward(c["state"], c["bag"], c["omics"], c["label"], c["censor"], model=c["model"],
+                                     fusion=c["fusion"], loss="ces", want_grads=False)
+    assert abs(ces["loss"] - float(g["loss_ces"])) < 1e-5
+    worst, details = digest_errors(c, out["grads"])
+    assert worst < GRAD_TOL, sorted(details, key=lambda d: -d[2])[:3]
+    assert set(out["grads"].keys()) == set(c["param_names"])
+
+
+def test_reference_known_answer_ces_loss():
+    # models/loss.py:108-121: exact float equality in the reference's own test
+    hz = np.array([[0.51, 0.52, 0.49, 0.48]], np.float32)
+    S = np.array([[0.5, 0.4, 0.2, 0.1]], np.float32)
+    l0, _, _ = orc.ces_surv_loss(hz, S, [0], [0.0])
+    l1, _, _ = orc.ces_surv_loss(hz, S, [0], [1.0])
+    assert np.float32(l0) == np.float32(0.6782951951026917)
+    assert np.float32(l1) == np.float32(0.1732867956161499)
+
+
+def test_loss_table_from_reference():
+    z = np.load(os.path.join(GOLDEN_DIR, "loss_known_answers.npz"))
+    for y, c, nll, ces in z["table"]:
+        ln, _, _ = orc.nll_surv_loss(z["hazards"], z["S"], [int(y)], [c])
+        lc, _, _ = orc.ces_surv_loss(z["hazards"], z["S"], [int(y)], [c])
+        assert abs(ln - nll) < 1e-6 and abs(lc - ces) < 1e-6
+
+
+def test_loss_gradients_finite_difference():
+    rng = np.random.default_rng(0)
+    for fn in (orc.nll_surv_loss, orc.ces_surv_loss):
+        for y in range(4):
+            for c in (0.0, 1.0):
+                hz = rng.uniform(0.2, 0.8, size=(1, 4))
+                S = np.cumprod(1 - hz, axis=1)
+                _, dhz, dS = fn(hz, S, [y], [c])
+                for arr, d in ((hz, dhz), (S, dS)):
+                    for j in range(4):
+                        a = arr.copy(); a[0, j] += 1e-6
+                        b = arr.copy(); b[0, j] -= 1e-6
+                        lp = fn(a if arr is hz else hz, a if arr is S else S, [y], [c])[0]
+                        lm = fn(b if arr is hz else hz, b if arr is S else S, [y], [c])[0]
+                        assert abs((lp - lm) / 2e-6 - d[0, j]) < 1e-5
+
+
+def test_folded_bag_stage_equals_unfolded_attention():
+    # folding W_k into the query and W_v behind the pooled vector is exact
+    c = load_case("mcat_concat_sharp_517")
+    P = {k: np.asarray(v, np.float64) for k, v in c["state"].items()}
+    X = np.asarray(c["bag"], np.float64)
+    H = orc.bag_proj_fwd(P, X)
+    G, _ = orc.snn_fwd(P, c["omics"])
+    out, A, _ = orc.mcat_coattn_fwd(P, G, H)
+    E = 256
+    Win, b_in = P["co_attention.in_proj_weight"], P["co_attention.in_proj_bias"]
+    q = G @ Win[:E].T + b_in[:E]
+    qk = (q @ Win[E:2 * E]) / 16.0
+    _, s, lse, pooled = orc.folded_bag_stage(P["H.0.weight"], P["H.0.bias"], qk, X)
+    A2 = np.exp(s - lse[:, None])
+    out2 = (pooled @ Win[2 * E:].T + b_in[2 * E:]) @ P["co_attention.out_proj.weight"].T + P["co_attention.out_proj.bias"]
+    assert np.max(np.abs(A - A2)) < 1e-12
+    assert np.max(np.abs(out - out2)) < 1e-10
