@@ -84,6 +84,106 @@ int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, co
 int mpo_lse_combine(const float* lse_in, const float* pooled_in, int32_t nshards, float* lse_out, float* pooled_out,
                     void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Slide tail: everything that runs on the 6 omic tokens per slide, batched over the B slides of a step.
+ * Parameters are plain fp32 device arrays in torch's own layouts (the nn.Parameter storage of the drop-in
+ * modules), so reference checkpoints load unchanged.  g* are the gradient buffers (may be NULL
+ * for inference); gradients are accumulated.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct mpo_lin { const float* w; const float* b; float* gw; float* gb; } mpo_lin;      /* nn.Linear / nn.Bilinear */
+typedef struct mpo_norm { const float* g; const float* b; float* gg; float* gb; } mpo_norm;    /* nn.LayerNorm(256)       */
+
+typedef struct mpo_encoder_layer {      /* nn.TransformerEncoderLayer(256, nhead 8, ff 512, relu, post-norm): mcat.py:51-53 */
+  mpo_lin in_proj;                      /* [768,256]  self_attn.in_proj_{weight,bias} */
+  mpo_lin out_proj;                     /* [256,256]  self_attn.out_proj              */
+  mpo_lin linear1;                      /* [512,256] */
+  mpo_lin linear2;                      /* [256,512] */
+  mpo_norm norm1, norm2;
+} mpo_encoder_layer;
+
+typedef struct mpo_pool_head {          /* AttentionNetGated (blocks.py:13-48) + rho (mcat.py:57) */
+  mpo_lin att_a, att_b;                 /* [256,256] each (Tanh / Sigmoid branches)   */
+  mpo_lin att_c;                        /* [1,256]   */
+  mpo_lin rho;                          /* [256,256] + ReLU */
+} mpo_pool_head;
+
+typedef struct mpo_cag {                /* ContextualAttentionGate(dim 256, hidden 256): blocks.py:232-253 */
+  mpo_lin fc1, fc2, fc3, fc_c;          /* [256,256] each, ELU */
+  mpo_norm G, E;
+} mpo_cag;
+
+typedef struct mpo_bilinear {           /* BilinearFusion(256,256, hidden 32, mm 64, out 256): fusion.py:44-113 */
+  mpo_lin h1, z1, o1, h2, z2, o2;       /* h [32,256]; z nn.Bilinear w [32,256,256] b [32]; o [32,32] */
+  mpo_lin fc1;                          /* [64,1089] */
+  mpo_lin fc2;                          /* [256,130] */
+} mpo_bilinear;
+
+#define MPO_VARIANT_MCAT 0
+#define MPO_VARIANT_NACAGAT 1
+#define MPO_FUSION_CONCAT 0
+#define MPO_FUSION_BILINEAR 1
+#define MPO_LOSS_NLL 0
+#define MPO_LOSS_CES 1
+
+typedef struct mpo_model {
+  int32_t variant;                      /* MPO_VARIANT_*  */
+  int32_t fusion;                       /* MPO_FUSION_*   */
+  int32_t n_classes;                    /* survival bins (4) */
+  int32_t omic_dims[MPO_Q];             /* input width of each SNN encoder */
+  mpo_lin H;                            /* [256,1024] H.0 (fp32 master; kernels stream its bf16 copy) */
+  mpo_lin snn[MPO_Q][2];                /* G.i.0.0 [256,d_i] and G.i.1.0 [256,256], ELU (mcat.py:32-45) */
+  mpo_lin coattn_in;                    /* co_attention.in_proj [768,256] (q | k | v blocks) */
+  mpo_lin coattn_out;                   /* co_attention.out_proj [256,256] */
+  mpo_cag cag;                          /* NaCAGaT only */
+  mpo_encoder_layer path_tr[2], omic_tr[2];
+  mpo_pool_head path_pool, omic_pool;
+  mpo_lin fusion0, fusion2;             /* ConcatFusion [256,512], [256,256] (fusion.py:7-19) */
+  mpo_bilinear bil;                     /* fusion == bilinear */
+  mpo_lin classifier;                   /* [n_classes,256] */
+} mpo_model;
+
+/* One step's token-side inputs/outputs.  omics[i] is fp32 [B][omic_dims[i]]. */
+typedef struct mpo_tail_io {
+  int32_t num_slides;
+  const float* omics[MPO_Q];
+  float* ws;                            /* fp32 workspace of mpo_tail_ws_floats() elements */
+  /* bag-stage interface */
+  float* qp;                            /* out of pre_fwd : [B][6][256] projected queries q = W_q g + b_q */
+  float* qk;                            /* out of pre_fwd : [B][6][256] folded queries W_k^T q / 16   */
+  float* kc;                            /* out of pre_fwd : [B][6] key-bias score term b_k.q/16 (NaCAGaT; else NULL) */
+  const float* pooled;                  /* in  to post_fwd: [B][6][256] from mpo_bag_fwd             */
+  float* dpooled;                       /* out of post_bwd: [B][6][256]                               */
+  const float* dqk;                     /* in  to pre_bwd : [B][6][256] from mpo_bag_bwd             */
+  const float* dkc;                     /* in  to pre_bwd : [B][6]      (NaCAGaT; else NULL)          */
+  const float* dtq;                     /* in  to pre_bwd : [B][6][256] gradient w.r.t. tanh(q) (NaCAGaT; else NULL) */
+  /* model outputs (mcat.py:126-142) */
+  float* hazards; float* S; float* Y;   /* [B][n_classes] each                                        */
+  float* att_path; float* att_omic;     /* [B][6] raw pooling logits (attention_scores['path'/'omic']) */
+} mpo_tail_io;
+
+/* ABI self-check for bindings: sizeof(mpo_bag) (which = 0), sizeof(mpo_model) (1), sizeof(mpo_tail_io) (2) */
+int64_t mpo_sizeof(int32_t which);
+/* workspace size in floats for a batch of B slides */
+int64_t mpo_tail_ws_floats(const mpo_model* m, int32_t B);
+/* debugging/test aid: offset (in floats) and length of a named intermediate inside the workspace; -1 if unknown */
+int64_t mpo_tail_ws_lookup(const mpo_model* m, int32_t B, const char* name, int64_t* length);
+
+/* mcat.py:90-92 (SNN encoders -> G_bag), the query in-projection of mcat.py:97 and the key fold qk = W_k^T q / 16 */
+int mpo_tail_pre_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream);
+/* mcat.py:97 (value/out projection of the pooled vectors), :101-138 (encoders, pooling, fusion, survival head) */
+int mpo_tail_post_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream);
+/* models/loss.py:31-43 (NLL, kind 0) and :5-28 (CES, kind 1): loss [B], dhaz/dS [B][n_classes] scaled by grad_scale */
+int mpo_surv_loss(int32_t kind, const float* hazards, const float* S, const int64_t* label, const float* censor,
+                  float alpha, float eps, float grad_scale, float* loss, float* dhaz, float* dS, int32_t B,
+                  int32_t n_classes, void* stream);
+/* autograd of post_fwd given d(hazards), d(S), d(Y) (each [B][n_classes], any may be NULL): parameter gradients,
+ * io->dpooled, and the token-side gradients kept in the workspace for pre_bwd */
+int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dhaz, const float* dS, const float* dY,
+                      void* stream);
+/* autograd of pre_fwd: consumes io->dqk and the workspace gradients, finishes co_attention.in_proj and SNN grads */
+int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,53 @@ class MpoBag(ctypes.Structure):
     ]
 
 
+class MpoLin(ctypes.Structure):
+    _fields_ = [("w", c_void_p), ("b", c_void_p), ("gw", c_void_p), ("gb", c_void_p)]
+
+
+class MpoNorm(ctypes.Structure):
+    _fields_ = [("g", c_void_p), ("b", c_void_p), ("gg", c_void_p), ("gb", c_void_p)]
+
+
+class MpoEncoderLayer(ctypes.Structure):
+    _fields_ = [("in_proj", MpoLin), ("out_proj", MpoLin), ("linear1", MpoLin), ("linear2", MpoLin),
+                ("norm1", MpoNorm), ("norm2", MpoNorm)]
+
+
+class MpoPoolHead(ctypes.Structure):
+    _fields_ = [("att_a", MpoLin), ("att_b", MpoLin), ("att_c", MpoLin), ("rho", MpoLin)]
+
+
+class MpoCag(ctypes.Structure):
+    _fields_ = [("fc1", MpoLin), ("fc2", MpoLin), ("fc3", MpoLin), ("fc_c", MpoLin), ("G", MpoNorm), ("E", MpoNorm)]
+
+
+class MpoBilinear(ctypes.Structure):
+    _fields_ = [("h1", MpoLin), ("z1", MpoLin), ("o1", MpoLin), ("h2", MpoLin), ("z2", MpoLin), ("o2", MpoLin),
+                ("fc1", MpoLin), ("fc2", MpoLin)]
+
+
+class MpoModel(ctypes.Structure):
+    """struct mpo_model (include/mpo_b200.h)."""
+    _fields_ = [
+        ("variant", c_i32), ("fusion", c_i32), ("n_classes", c_i32), ("omic_dims", c_i32 * 6),
+        ("H", MpoLin), ("snn", (MpoLin * 2) * 6), ("coattn_in", MpoLin), ("coattn_out", MpoLin), ("cag", MpoCag),
+        ("path_tr", MpoEncoderLayer * 2), ("omic_tr", MpoEncoderLayer * 2),
+        ("path_pool", MpoPoolHead), ("omic_pool", MpoPoolHead),
+        ("fusion0", MpoLin), ("fusion2", MpoLin), ("bil", MpoBilinear), ("classifier", MpoLin),
+    ]
+
+
+class MpoTailIo(ctypes.Structure):
+    """struct mpo_tail_io (include/mpo_b200.h)."""
+    _fields_ = [
+        ("num_slides", c_i32), ("omics", c_void_p * 6), ("ws", c_void_p),
+        ("qp", c_void_p), ("qk", c_void_p), ("kc", c_void_p), ("pooled", c_void_p), ("dpooled", c_void_p),
+        ("dqk", c_void_p), ("dkc", c_void_p), ("dtq", c_void_p),
+        ("hazards", c_void_p), ("S", c_void_p), ("Y", c_void_p), ("att_path", c_void_p), ("att_omic", c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -61,7 +108,15 @@ SIGNATURES = {
     "mpo_bag_bwd": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p],
     "mpo_lse_combine": [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p],
+    "mpo_tail_pre_fwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],
+    "mpo_tail_post_fwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],
+    "mpo_surv_loss": [c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p,
+                      c_void_p, c_i32, c_i32, c_void_p],
+    "mpo_tail_post_bwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p, c_void_p, c_void_p, c_void_p],
+    "mpo_tail_pre_bwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],
 }
+# functions with a non-int return type
+OTHER_EXPORTS = ["mpo_tail_ws_floats", "mpo_tail_ws_lookup", "mpo_sizeof"]
 
 
 def _declare(L):
@@ -69,11 +124,21 @@ def _declare(L):
         fn = getattr(L, name)
         fn.restype = c_int
         fn.argtypes = argtypes
+    L.mpo_tail_ws_floats.restype = c_i64
+    L.mpo_tail_ws_floats.argtypes = [ctypes.POINTER(MpoModel), c_i32]
+    L.mpo_sizeof.restype = c_i64
+    L.mpo_sizeof.argtypes = [c_i32]
+    for which, st in enumerate((MpoBag, MpoModel, MpoTailIo)):
+        if L.mpo_sizeof(which) != ctypes.sizeof(st):
+            raise RuntimeError("ABI mismatch: %s is %d bytes in libmpo_b200.so but %d in the ctypes binding"
+                               % (st.__name__, L.mpo_sizeof(which), ctypes.sizeof(st)))
+    L.mpo_tail_ws_lookup.restype = c_i64
+    L.mpo_tail_ws_lookup.argtypes = [ctypes.POINTER(MpoModel), c_i32, ctypes.c_char_p, ctypes.POINTER(c_i64)]
 
 
 def exported_symbols():
     """Names include/mpo_b200.h declares (used by the CPU-side ABI test)."""
-    return ["mpo_last_error", "mpo_version"] + list(SIGNATURES.keys())
+    return ["mpo_last_error", "mpo_version"] + list(SIGNATURES.keys()) + OTHER_EXPORTS
 
 
 def call(name, *args):

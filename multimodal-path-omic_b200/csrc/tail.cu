@@ -1,0 +1,562 @@
+// Orchestration of the slide tail (declared in include/mpo_b200.h): a fixed sequence of the small kernels in
+// tail_kernels.cuh, batched over the B slides of a step, all on the caller's stream.  Mirrors, stage by stage,
+// what the reference modules compute on the 6 omic tokens (file:line given at each stage).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/mpo_b200.h"
+#include "launchers.h"
+#include "tail_kernels.cuh"
+
+namespace mpo {
+namespace {
+
+constexpr int E = 256;       // model width
+constexpr int FF = 512;      // transformer feed-forward width
+constexpr int BH = 32;       // bilinear hidden
+constexpr int BMM = 64;      // bilinear mm_hidden
+
+// ---------------------------------------------------------------------------------------------- workspace layout
+struct Layout {
+  std::vector<std::pair<std::string, std::pair<long long, long long>>> items;
+  long long total = 0;
+  long long add(const char* name, long long len) {
+    const long long off = total;
+    items.push_back({name, {off, len}});
+    total += (len + 63) / 64 * 64;   // keep every buffer 256-byte aligned
+    return off;
+  }
+};
+
+struct EncBuf { long long qkv, probs, ctx, sa, y1, xh1, rs1, f, f2, y2, xh2, rs2; };
+struct PoolBuf { long long a, b, w, hp, h; };
+
+struct Ws {
+  long long snn_h[MPO_Q], G, v, hc;
+  long long cag_f1, cag_f2, cag_f3, cag_s, cag_u, cag_Gg, cag_Gxh, cag_Grs, cag_w, cag_Ee, cag_Exh, cag_Ers, cag_m, cag_C;
+  EncBuf enc[4];      // path.0, path.1, omic.0, omic.1
+  PoolBuf pool[2];    // path, omic
+  long long cat, z1, z2;                                   // concat fusion
+  long long bh[2], bU[2], bg[2], bgh[2], bo[2], kp, cat130, bf2;   // bilinear fusion
+  long long logits;
+  // gradients / scratch
+  long long dlogits, dh, dcat, dz1, dz2, dhp[2], dxa, dxb, dtok[2], s768, s512, s256a, s256b, s256c, dG, dqp;
+  long long bV, bdkp, bdcat130, bdo[2], bdgh[2], bdh[2], bdz[2], bdx[2];
+  Layout lay;
+};
+
+void build_layout(const mpo_model* m, int B, Ws& w) {
+  const long long R = 6LL * B;
+  Layout& L = w.lay;
+  char nm[64];
+  for (int i = 0; i < MPO_Q; ++i) { snprintf(nm, sizeof nm, "snn_h%d", i); w.snn_h[i] = L.add(nm, (long long)B * E); }
+  w.G = L.add("G", R * E);
+  w.v = L.add("v", R * E);
+  w.hc = L.add("hc", R * E);
+  if (m->variant == MPO_VARIANT_NACAGAT) {
+    w.cag_f1 = L.add("cag_f1", R * E); w.cag_f2 = L.add("cag_f2", R * E); w.cag_f3 = L.add("cag_f3", R * E);
+    w.cag_s = L.add("cag_s", R * E); w.cag_u = L.add("cag_u", R * E); w.cag_Gg = L.add("cag_Gg", R * E);
+    w.cag_Gxh = L.add("cag_Gxh", R * E); w.cag_Grs = L.add("cag_Grs", R);
+    w.cag_w = L.add("cag_w", R * E); w.cag_Ee = L.add("cag_Ee", R * E); w.cag_Exh = L.add("cag_Exh", R * E);
+    w.cag_Ers = L.add("cag_Ers", R); w.cag_m = L.add("cag_m", R * E); w.cag_C = L.add("cag_C", R * E);
+  }
+  const char* en[4] = {"path0", "path1", "omic0", "omic1"};
+  for (int e = 0; e < 4; ++e) {
+    EncBuf& b = w.enc[e];
+    auto A = [&](const char* s, long long n) { snprintf(nm, sizeof nm, "%s_%s", en[e], s); return L.add(nm, n); };
+    b.qkv = A("qkv", R * 3 * E); b.probs = A("probs", (long long)B * 8 * 36); b.ctx = A("ctx", R * E);
+    b.sa = A("sa", R * E); b.y1 = A("y1", R * E); b.xh1 = A("xh1", R * E); b.rs1 = A("rs1", R);
+    b.f = A("f", R * FF); b.f2 = A("f2", R * E); b.y2 = A("y2", R * E); b.xh2 = A("xh2", R * E); b.rs2 = A("rs2", R);
+  }
+  const char* pn[2] = {"pathpool", "omicpool"};
+  for (int p = 0; p < 2; ++p) {
+    PoolBuf& b = w.pool[p];
+    auto A = [&](const char* s, long long n) { snprintf(nm, sizeof nm, "%s_%s", pn[p], s); return L.add(nm, n); };
+    b.a = A("a", R * E); b.b = A("b", R * E); b.w = A("w", (long long)B * 6); b.hp = A("hp", (long long)B * E);
+    b.h = A("h", (long long)B * E);
+  }
+  if (m->fusion == MPO_FUSION_CONCAT) {
+    w.cat = L.add("cat", (long long)B * 2 * E); w.z1 = L.add("z1", (long long)B * E); w.z2 = L.add("z2", (long long)B * E);
+  } else {
+    for (int s = 0; s < 2; ++s) {
+      auto A = [&](const char* t, long long n) { snprintf(nm, sizeof nm, "bil%d_%s", s + 1, t); return L.add(nm, n); };
+      w.bh[s] = A("h", (long long)B * BH); w.bU[s] = A("U", (long long)B * BH * E); w.bg[s] = A("g", (long long)B * BH);
+      w.bgh[s] = A("gh", (long long)B * BH); w.bo[s] = A("o", (long long)B * BH);
+      w.bdo[s] = A("do", (long long)B * BH); w.bdgh[s] = A("dgh", (long long)B * BH); w.bdh[s] = A("dh", (long long)B * BH);
+      w.bdz[s] = A("dz", (long long)B * BH); w.bdx[s] = A("dx", (long long)B * E);
+    }
+    w.kp = L.add("kp", (long long)B * 1089); w.cat130 = L.add("cat130", (long long)B * 130);
+    w.bf2 = L.add("bf2", (long long)B * E);
+    w.bV = L.add("bV", (long long)B * BH * E); w.bdkp = L.add("bdkp", (long long)B * 1089);
+    w.bdcat130 = L.add("bdcat130", (long long)B * 130);
+  }
+  w.logits = L.add("logits", (long long)B * m->n_classes);
+  w.dlogits = L.add("dlogits", (long long)B * m->n_classes);
+  w.dh = L.add("dh", (long long)B * E);
+  w.dcat = L.add("dcat", (long long)B * 2 * E); w.dz1 = L.add("dz1", (long long)B * E); w.dz2 = L.add("dz2", (long long)B * E);
+  w.dhp[0] = L.add("dhp_path", (long long)B * E); w.dhp[1] = L.add("dhp_omic", (long long)B * E);
+  w.dxa = L.add("dxa", R * E); w.dxb = L.add("dxb", R * E);
+  w.dtok[0] = L.add("dtok_path", R * E); w.dtok[1] = L.add("dtok_omic", R * E);
+  w.s768 = L.add("s768", R * 3 * E); w.s512 = L.add("s512", R * FF);
+  w.s256a = L.add("s256a", R * E); w.s256b = L.add("s256b", R * E); w.s256c = L.add("s256c", R * E);
+  w.dG = L.add("dG", R * E); w.dqp = L.add("dqp", R * E);
+}
+
+// ---------------------------------------------------------------------------------------------- op helpers
+struct Ctx {
+  cudaStream_t st;
+  cudaError_t err = cudaSuccess;
+  const char* where = "";
+  void chk(cudaError_t e, const char* w) { if (err == cudaSuccess && e != cudaSuccess) { err = e; where = w; } }
+};
+
+inline unsigned nblk(long long n, int t = 256) { return static_cast<unsigned>((n + t - 1) / t); }
+
+mpo_lin sub(const mpo_lin& L, int row0, int in) {   // rows [row0, ...) of a packed projection
+  mpo_lin s;
+  s.w = L.w + (long long)row0 * in;
+  s.b = L.b ? L.b + row0 : nullptr;
+  s.gw = L.gw ? L.gw + (long long)row0 * in : nullptr;
+  s.gb = L.gb ? L.gb + row0 : nullptr;
+  return s;
+}
+
+// y[rows,out] = act(x[rows,in] W^T + b)
+void lin_fwd(Ctx& c, const float* x, long long ldx, const mpo_lin& L, int out, int in, float* y, long long ldy, int rows,
+             int act) {
+  GemmArgs g{x, ldx, 1, L.w, 1, in, y, ldy, L.b, rows, out, in, 1.f, 0, act};
+  c.chk(launch_gemm(g, c.st), "lin_fwd");
+}
+// dz [rows,out] is the gradient at the pre-activation.  dx (=|+=) dz W ; gw += dz^T x ; gb += colsum(dz)
+void lin_bwd(Ctx& c, const float* dz, long long lddz, const float* x, long long ldx, const mpo_lin& L, int out, int in,
+             float* dx, long long lddx, int rows, bool acc_dx) {
+  if (dx != nullptr) {
+    GemmArgs g{dz, lddz, 1, L.w, in, 1, dx, lddx, nullptr, rows, in, out, 1.f, acc_dx ? 1 : 0, ACT_NONE};
+    c.chk(launch_gemm(g, c.st), "lin_bwd.dgrad");
+  }
+  if (L.gw != nullptr) {
+    GemmArgs g{dz, 1, lddz, x, ldx, 1, L.gw, in, nullptr, out, in, rows, 1.f, 1, ACT_NONE};
+    c.chk(launch_gemm(g, c.st), "lin_bwd.wgrad");
+  }
+  if (L.gb != nullptr) {
+    colsum_kernel<<<nblk(out, 128), 128, 0, c.st>>>(dz, lddz, nullptr, 0, L.gb, rows, out);
+    c.chk(cudaGetLastError(), "lin_bwd.bgrad");
+  }
+}
+void act_bwd(Ctx& c, const float* dy, long long lddy, const float* y, long long ldy, float* dz, long long lddz, int rows,
+             int cols, int act) {
+  act_bwd_kernel<<<nblk((long long)rows * cols), 256, 0, c.st>>>(dy, lddy, y, ldy, dz, lddz, rows, cols, act);
+  c.chk(cudaGetLastError(), "act_bwd");
+}
+void add(Ctx& c, const float* a, const float* b, float* out, long long n) {
+  add_kernel<<<nblk(n), 256, 0, c.st>>>(a, b, out, n);
+  c.chk(cudaGetLastError(), "add");
+}
+void mul(Ctx& c, const float* a, const float* b, float* out, long long n) {
+  mul_kernel<<<nblk(n), 256, 0, c.st>>>(a, b, out, n);
+  c.chk(cudaGetLastError(), "mul");
+}
+void act(Ctx& c, const float* x, float* y, long long n, int a) {
+  act_kernel<<<nblk(n), 256, 0, c.st>>>(x, y, n, a);
+  c.chk(cudaGetLastError(), "act");
+}
+void ln_fwd(Ctx& c, const float* a, const float* b, const mpo_norm& N, float* y, float* xh, float* rs, int rows) {
+  layernorm_fwd_kernel<<<nblk(rows, 8), 256, 0, c.st>>>(a, b, N.g, N.b, y, xh, rs, rows);
+  c.chk(cudaGetLastError(), "ln_fwd");
+}
+void ln_bwd(Ctx& c, const float* dy, const mpo_norm& N, const float* xh, const float* rs, float* dx, int rows) {
+  layernorm_bwd_kernel<<<nblk(rows, 8), 256, 0, c.st>>>(dy, N.g, xh, rs, dx, rows);
+  c.chk(cudaGetLastError(), "ln_bwd");
+  if (N.gg != nullptr) {
+    colsum_kernel<<<nblk(E, 128), 128, 0, c.st>>>(dy, E, xh, E, N.gg, rows, E);
+    colsum_kernel<<<nblk(E, 128), 128, 0, c.st>>>(dy, E, nullptr, 0, N.gb, rows, E);
+    c.chk(cudaGetLastError(), "ln_bwd.params");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- encoder layer
+// reference: nn.TransformerEncoderLayer (post-norm) as built at models/mcat/mcat.py:51-53
+void enc_fwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, float* ws, const float* x, int B) {
+  const int R = 6 * B;
+  lin_fwd(c, x, E, P.in_proj, 3 * E, E, ws + b.qkv, 3 * E, R, ACT_NONE);
+  mha6_fwd_kernel<<<nblk((long long)B * 8, 8), 256, 0, c.st>>>(ws + b.qkv, ws + b.probs, ws + b.ctx, B);
+  c.chk(cudaGetLastError(), "mha6_fwd");
+  lin_fwd(c, ws + b.ctx, E, P.out_proj, E, E, ws + b.sa, E, R, ACT_NONE);
+  ln_fwd(c, x, ws + b.sa, P.norm1, ws + b.y1, ws + b.xh1, ws + b.rs1, R);
+  lin_fwd(c, ws + b.y1, E, P.linear1, FF, E, ws + b.f, FF, R, ACT_RELU);
+  lin_fwd(c, ws + b.f, FF, P.linear2, E, FF, ws + b.f2, E, R, ACT_NONE);
+  ln_fwd(c, ws + b.y1, ws + b.f2, P.norm2, ws + b.y2, ws + b.xh2, ws + b.rs2, R);
+}
+// dy2 -> dx (written to dx_out).  Uses scratch s768/s512/s256a/s256b.
+void enc_bwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, const Ws& w, float* ws, const float* x,
+             const float* dy2, float* dx_out, int B) {
+  const int R = 6 * B;
+  float* dr2 = ws + w.s256a;       // gradient of (y1 + f2)
+  ln_bwd(c, dy2, P.norm2, ws + b.xh2, ws + b.rs2, dr2, R);
+  float* df = ws + w.s512;
+  {   // linear2: dz = dr2
+    GemmArgs g{dr2, E, 1, P.linear2.w, FF, 1, df, FF, nullptr, R, FF, E, 1.f, 0, ACT_NONE};
+    c.chk(launch_gemm(g, c.st), "enc.lin2.dgrad");
+    lin_bwd(c, dr2, E, ws + b.f, FF, P.linear2, E, FF, nullptr, 0, R, false);
+  }
+  act_bwd(c, df, FF, ws + b.f, FF, df, FF, R, FF, ACT_RELU);
+  float* dy1 = ws + w.s256b;
+  lin_bwd(c, df, FF, ws + b.y1, E, P.linear1, FF, E, dy1, E, R, false);
+  add(c, dy1, dr2, dy1, (long long)R * E);
+  float* dr1 = ws + w.s256a;       // gradient of (x + sa); dr2 no longer needed
+  ln_bwd(c, dy1, P.norm1, ws + b.xh1, ws + b.rs1, dr1, R);
+  float* dctx = ws + w.s256b;
+  lin_bwd(c, dr1, E, ws + b.ctx, E, P.out_proj, E, E, dctx, E, R, false);
+  float* dqkv = ws + w.s768;
+  mha6_bwd_kernel<<<nblk((long long)B * 8, 8), 256, 0, c.st>>>(ws + b.qkv, ws + b.probs, dctx, dqkv, B);
+  c.chk(cudaGetLastError(), "mha6_bwd");
+  lin_bwd(c, dqkv, 3 * E, x, E, P.in_proj, 3 * E, E, dx_out, E, R, false);
+  add(c, dx_out, dr1, dx_out, (long long)R * E);
+}
+
+// ---------------------------------------------------------------------------------------------- pooling + rho
+// reference: models/blocks.py:42-48, models/mcat/mcat.py:105-109
+void pool_fwd(Ctx& c, const mpo_pool_head& P, const PoolBuf& b, float* ws, const float* x, float* att_logits, int B) {
+  const int R = 6 * B;
+  lin_fwd(c, x, E, P.att_a, E, E, ws + b.a, E, R, ACT_TANH);
+  lin_fwd(c, x, E, P.att_b, E, E, ws + b.b, E, R, ACT_SIGMOID);
+  pool_fwd_kernel<<<B, 256, 0, c.st>>>(x, ws + b.a, ws + b.b, P.att_c.w, P.att_c.b, att_logits, ws + b.w, ws + b.hp);
+  c.chk(cudaGetLastError(), "pool_fwd");
+  lin_fwd(c, ws + b.hp, E, P.rho, E, E, ws + b.h, E, B, ACT_RELU);
+}
+// dh [B,256] (gradient of rho's output) -> dx_out [R,256]
+void pool_bwd(Ctx& c, const mpo_pool_head& P, const PoolBuf& b, const Ws& w, float* ws, const float* x, const float* dh,
+              float* dhp, float* dx_out, int B) {
+  const int R = 6 * B;
+  float* dzr = ws + w.dz1;   // reuse a [B,256] scratch
+  act_bwd(c, dh, E, ws + b.h, E, dzr, E, B, E, ACT_RELU);
+  lin_bwd(c, dzr, E, ws + b.hp, E, P.rho, E, E, dhp, E, B, false);
+  pool_bwd_kernel<<<B, 256, 0, c.st>>>(x, ws + b.a, ws + b.b, P.att_c.w, ws + b.w, dhp, dx_out, ws + w.dxa, ws + w.dxb,
+                                       P.att_c.gw, P.att_c.gb);
+  c.chk(cudaGetLastError(), "pool_bwd");
+  lin_bwd(c, ws + w.dxa, E, x, E, P.att_a, E, E, dx_out, E, R, true);
+  lin_bwd(c, ws + w.dxb, E, x, E, P.att_b, E, E, dx_out, E, R, true);
+}
+
+// ---------------------------------------------------------------------------------------------- CAG (NaCAGaT)
+// reference: models/blocks.py:247-253   C = fc_c( LN(ELU(fc1 Q + fc2 Qh)) * LN(ELU(fc3 Qh)) ), every fc = Linear+ELU
+void cag_fwd(Ctx& c, const mpo_cag& P, const Ws& w, float* ws, const float* Q, const float* Qh, int R) {
+  lin_fwd(c, Q, E, P.fc1, E, E, ws + w.cag_f1, E, R, ACT_ELU);
+  lin_fwd(c, Qh, E, P.fc2, E, E, ws + w.cag_f2, E, R, ACT_ELU);
+  lin_fwd(c, Qh, E, P.fc3, E, E, ws + w.cag_f3, E, R, ACT_ELU);
+  add(c, ws + w.cag_f1, ws + w.cag_f2, ws + w.cag_s, (long long)R * E);
+  act(c, ws + w.cag_s, ws + w.cag_u, (long long)R * E, ACT_ELU);
+  ln_fwd(c, ws + w.cag_u, nullptr, P.G, ws + w.cag_Gg, ws + w.cag_Gxh, ws + w.cag_Grs, R);
+  act(c, ws + w.cag_f3, ws + w.cag_w, (long long)R * E, ACT_ELU);
+  ln_fwd(c, ws + w.cag_w, nullptr, P.E, ws + w.cag_Ee, ws + w.cag_Exh, ws + w.cag_Ers, R);
+  mul(c, ws + w.cag_Gg, ws + w.cag_Ee, ws + w.cag_m, (long long)R * E);
+  lin_fwd(c, ws + w.cag_m, E, P.fc_c, E, E, ws + w.cag_C, E, R, ACT_ELU);
+}
+// dC -> dQ accumulated into dQ_acc, dQh written to dQh_out
+void cag_bwd(Ctx& c, const mpo_cag& P, const Ws& w, float* ws, const float* Q, const float* Qh, const float* dC,
+             float* dQ_acc, float* dQh_out, int R) {
+  const long long n = (long long)R * E;
+  float* t0 = ws + w.s256a; float* t1 = ws + w.s256b; float* t2 = ws + w.s256c;
+  act_bwd(c, dC, E, ws + w.cag_C, E, t0, E, R, E, ACT_ELU);
+  lin_bwd(c, t0, E, ws + w.cag_m, E, P.fc_c, E, E, t1, E, R, false);          // t1 = dm
+  mul(c, t1, ws + w.cag_Ee, t0, n);                                            // t0 = dGg
+  mul(c, t1, ws + w.cag_Gg, t2, n);                                            // t2 = dEe
+  ln_bwd(c, t0, P.G, ws + w.cag_Gxh, ws + w.cag_Grs, t1, R);                   // t1 = du
+  act_bwd(c, t1, E, ws + w.cag_u, E, t1, E, R, E, ACT_ELU);                    // t1 = d(f1+f2)
+  ln_bwd(c, t2, P.E, ws + w.cag_Exh, ws + w.cag_Ers, t0, R);                   // t0 = dw
+  act_bwd(c, t0, E, ws + w.cag_w, E, t0, E, R, E, ACT_ELU);                    // t0 = df3 (post fc3's ELU)
+  act_bwd(c, t0, E, ws + w.cag_f3, E, t0, E, R, E, ACT_ELU);                   // through fc3's own ELU
+  lin_bwd(c, t0, E, Qh, E, P.fc3, E, E, dQh_out, E, R, false);
+  act_bwd(c, t1, E, ws + w.cag_f2, E, t2, E, R, E, ACT_ELU);
+  lin_bwd(c, t2, E, Qh, E, P.fc2, E, E, dQh_out, E, R, true);
+  act_bwd(c, t1, E, ws + w.cag_f1, E, t2, E, R, E, ACT_ELU);
+  lin_bwd(c, t2, E, Q, E, P.fc1, E, E, dQ_acc, E, R, true);
+}
+
+// ---------------------------------------------------------------------------------------------- bilinear fusion
+// reference: models/fusion.py:81-113 (eval: dropouts are identity)
+void bil_side_fwd(Ctx& c, const mpo_lin& Lh, const mpo_lin& Lz, const mpo_lin& Lo, const Ws& w, float* ws, int s,
+                  const float* xa, const float* xb, int B) {
+  lin_fwd(c, xa, E, Lh, BH, E, ws + w.bh[s], BH, B, ACT_RELU);
+  // U[b][k*256+i] = sum_j W[k][i][j] xb[b][j]
+  GemmArgs g{xb, E, 1, Lz.w, 1, E, ws + w.bU[s], (long long)BH * E, nullptr, B, BH * E, E, 1.f, 0, ACT_NONE};
+  c.chk(launch_gemm(g, c.st), "bil.U");
+  bil_gate_fwd_kernel<<<B, 256, 0, c.st>>>(xa, ws + w.bU[s], Lz.b, ws + w.bh[s], ws + w.bg[s], ws + w.bgh[s]);
+  c.chk(cudaGetLastError(), "bil_gate_fwd");
+  lin_fwd(c, ws + w.bgh[s], BH, Lo, BH, BH, ws + w.bo[s], BH, B, ACT_RELU);
+}
+// do (gradient of o_s) in w.bdo[s] -> dxa (=|+=), dxb (+=)
+void bil_side_bwd(Ctx& c, const mpo_lin& Lh, const mpo_lin& Lz, const mpo_lin& Lo, const Ws& w, float* ws, int s,
+                  const float* xa, const float* xb, float* dxa, bool acc_a, float* dxb, int B) {
+  float* dpre = ws + w.bdo[s];
+  act_bwd(c, dpre, BH, ws + w.bo[s], BH, dpre, BH, B, BH, ACT_RELU);
+  lin_bwd(c, dpre, BH, ws + w.bgh[s], BH, Lo, BH, BH, ws + w.bdgh[s], BH, B, false);
+  bil_gate_bwd_kernel<<<B, 256, 0, c.st>>>(xa, ws + w.bU[s], ws + w.bh[s], ws + w.bg[s], ws + w.bdgh[s], ws + w.bdh[s],
+                                           ws + w.bdz[s], ws + w.bV, dxa, acc_a ? 1 : 0);
+  c.chk(cudaGetLastError(), "bil_gate_bwd");
+  // dW[(k,i)][j] += sum_b V[b][(k,i)] xb[b][j] ;  dxb[b][j] += sum_(k,i) V[b][(k,i)] W[(k,i)][j] ; db += colsum(dz)
+  if (Lz.gw != nullptr) {
+    GemmArgs g{ws + w.bV, 1, (long long)BH * E, xb, E, 1, Lz.gw, E, nullptr, BH * E, E, B, 1.f, 1, ACT_NONE};
+    c.chk(launch_gemm(g, c.st), "bil.dW");
+    colsum_kernel<<<1, 128, 0, c.st>>>(ws + w.bdz[s], BH, nullptr, 0, Lz.gb, B, BH);
+  }
+  GemmArgs g2{ws + w.bV, (long long)BH * E, 1, Lz.w, E, 1, dxb, E, nullptr, B, E, BH * E, 1.f, 1, ACT_NONE};
+  c.chk(launch_gemm(g2, c.st), "bil.dxb");
+  lin_bwd(c, ws + w.bdh[s], BH, xa, E, Lh, BH, E, dxa, E, B, true);
+}
+
+int finish(Ctx& c) {
+  if (c.err == cudaSuccess) return MPO_OK;
+  snprintf(g_err, sizeof(g_err), "tail (%s): %s", c.where, cudaGetErrorString(c.err));
+  return MPO_E_CUDA;
+}
+
+int check_model(const mpo_model* m, const mpo_tail_io* io, const char* who) {
+  if (!m || !io) return fail(MPO_E_ARG, "%s: NULL model/io", who);
+  if (m->variant != MPO_VARIANT_MCAT && m->variant != MPO_VARIANT_NACAGAT) return fail(MPO_E_UNSUPPORTED, "%s: unknown variant", who);
+  if (m->fusion != MPO_FUSION_CONCAT && m->fusion != MPO_FUSION_BILINEAR) return fail(MPO_E_UNSUPPORTED, "%s: unsupported fusion", who);
+  if (m->n_classes < 1 || m->n_classes > 16) return fail(MPO_E_ARG, "%s: n_classes out of range", who);
+  if (io->num_slides <= 0) return fail(MPO_E_ARG, "%s: num_slides must be positive", who);
+  if (!io->ws) return fail(MPO_E_ARG, "%s: workspace is NULL", who);
+  if (num_sms() <= 0) return fail(MPO_E_CUDA, "%s: no CUDA device (this library has no CPU fallback)", who);
+  return MPO_OK;
+}
+
+}  // namespace
+}  // namespace mpo
+
+using namespace mpo;
+
+extern "C" {
+
+int64_t mpo_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(mpo_bag);
+    case 1: return sizeof(mpo_model);
+    case 2: return sizeof(mpo_tail_io);
+    default: return -1;
+  }
+}
+
+int64_t mpo_tail_ws_floats(const mpo_model* m, int32_t B) {
+  if (!m || B <= 0) return -1;
+  Ws w;
+  build_layout(m, B, w);
+  return w.lay.total;
+}
+
+int64_t mpo_tail_ws_lookup(const mpo_model* m, int32_t B, const char* name, int64_t* length) {
+  if (!m || B <= 0 || !name) return -1;
+  Ws w;
+  build_layout(m, B, w);
+  for (auto& it : w.lay.items)
+    if (it.first == name) { if (length) *length = it.second.second; return it.second.first; }
+  return -1;
+}
+
+int mpo_tail_pre_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
+  int rc = check_model(m, io, "mpo_tail_pre_fwd");
+  if (rc) return rc;
+  if (!io->qp || !io->qk) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_fwd: qp/qk are NULL");
+  const int B = io->num_slides, R = 6 * B;
+  Ws w; build_layout(m, B, w);
+  float* ws = io->ws;
+  Ctx c{static_cast<cudaStream_t>(stream)};
+  // SNN encoders (mcat.py:32-45,90-92): G_bag row (b, i) = ELU(W2 ELU(W1 x_i + b1) + b2)
+  for (int i = 0; i < MPO_Q; ++i) {
+    if (!io->omics[i]) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_fwd: omics pointer is NULL");
+    const int d = m->omic_dims[i];
+    lin_fwd(c, io->omics[i], d, m->snn[i][0], E, d, ws + w.snn_h[i], E, B, ACT_ELU);
+    lin_fwd(c, ws + w.snn_h[i], E, m->snn[i][1], E, E, ws + w.G + i * E, 6 * E, B, ACT_ELU);
+  }
+  // query in-projection (rows 0..255 of co_attention.in_proj): q = W_q g + b_q
+  lin_fwd(c, ws + w.G, E, sub(m->coattn_in, 0, E), E, E, io->qp, E, R, ACT_NONE);
+  // key fold: qk[r][d] = sum_e q[r][e] W_k[e][d] / sqrt(256)
+  {
+    const float* Wk = m->coattn_in.w + (long long)E * E;
+    GemmArgs g{io->qp, E, 1, Wk, E, 1, io->qk, E, nullptr, R, E, E, 1.f / 16.f, 0, ACT_NONE};
+    c.chk(launch_gemm(g, c.st), "fold");
+  }
+  if (m->variant == MPO_VARIANT_NACAGAT) {
+    if (!io->kc) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_fwd: kc is NULL (NaCAGaT)");
+    // kc[r] = q[r] . b_k / 16
+    const float* bk = m->coattn_in.b + E;
+    GemmArgs g{io->qp, E, 1, bk, 1, 0, io->kc, 1, nullptr, R, 1, E, 1.f / 16.f, 0, ACT_NONE};
+    c.chk(launch_gemm(g, c.st), "kc");
+  }
+  return finish(c);
+}
+
+int mpo_tail_post_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
+  int rc = check_model(m, io, "mpo_tail_post_fwd");
+  if (rc) return rc;
+  if (!io->pooled || !io->hazards || !io->S || !io->Y || !io->att_path || !io->att_omic)
+    return fail(MPO_E_ARG, "%s", "mpo_tail_post_fwd: NULL pointer");
+  const int B = io->num_slides, R = 6 * B, K = m->n_classes;
+  Ws w; build_layout(m, B, w);
+  float* ws = io->ws;
+  Ctx c{static_cast<cudaStream_t>(stream)};
+  // value and output projections on the pooled vectors (folded form of mcat.py:97)
+  lin_fwd(c, io->pooled, E, sub(m->coattn_in, 2 * E, E), E, E, ws + w.v, E, R, ACT_NONE);
+  lin_fwd(c, ws + w.v, E, m->coattn_out, E, E, ws + w.hc, E, R, ACT_NONE);
+  if (m->variant == MPO_VARIANT_NACAGAT) {
+    if (!io->qp) return fail(MPO_E_ARG, "%s", "mpo_tail_post_fwd: qp is NULL (NaCAGaT)");
+    cag_fwd(c, m->cag, w, ws, ws + w.G, io->qp, R);                      // blocks.py:110
+    add(c, ws + w.hc, ws + w.cag_C, ws + w.hc, (long long)R * E);        // blocks.py:111
+  }
+  // set-based transformers (mcat.py:101-102)
+  enc_fwd(c, m->path_tr[0], w.enc[0], ws, ws + w.hc, B);
+  enc_fwd(c, m->path_tr[1], w.enc[1], ws, ws + w.enc[0].y2, B);
+  enc_fwd(c, m->omic_tr[0], w.enc[2], ws, ws + w.G, B);
+  enc_fwd(c, m->omic_tr[1], w.enc[3], ws, ws + w.enc[2].y2, B);
+  // global attention pooling (mcat.py:105-115)
+  pool_fwd(c, m->path_pool, w.pool[0], ws, ws + w.enc[1].y2, io->att_path, B);
+  pool_fwd(c, m->omic_pool, w.pool[1], ws, ws + w.enc[3].y2, io->att_omic, B);
+  const float* hpath = ws + w.pool[0].h;
+  const float* homic = ws + w.pool[1].h;
+  const float* hfin;
+  if (m->fusion == MPO_FUSION_CONCAT) {            // fusion.py:17-19
+    cudaMemcpy2DAsync(ws + w.cat, 2 * E * 4, hpath, E * 4, E * 4, B, cudaMemcpyDeviceToDevice, c.st);
+    cudaMemcpy2DAsync(ws + w.cat + E, 2 * E * 4, homic, E * 4, E * 4, B, cudaMemcpyDeviceToDevice, c.st);
+    lin_fwd(c, ws + w.cat, 2 * E, m->fusion0, E, 2 * E, ws + w.z1, E, B, ACT_RELU);
+    lin_fwd(c, ws + w.z1, E, m->fusion2, E, E, ws + w.z2, E, B, ACT_RELU);
+    hfin = ws + w.z2;
+  } else {                                          // fusion.py:81-113
+    bil_side_fwd(c, m->bil.h1, m->bil.z1, m->bil.o1, w, ws, 0, hpath, homic, B);
+    bil_side_fwd(c, m->bil.h2, m->bil.z2, m->bil.o2, w, ws, 1, homic, hpath, B);
+    bil_kron_fwd_kernel<<<B, 256, 0, c.st>>>(ws + w.bo[0], ws + w.bo[1], ws + w.kp, ws + w.cat130);
+    c.chk(cudaGetLastError(), "bil_kron_fwd");
+    lin_fwd(c, ws + w.kp, 1089, m->bil.fc1, BMM, 1089, ws + w.cat130, 130, B, ACT_RELU);
+    lin_fwd(c, ws + w.cat130, 130, m->bil.fc2, E, 130, ws + w.bf2, E, B, ACT_RELU);
+    hfin = ws + w.bf2;
+  }
+  lin_fwd(c, hfin, E, m->classifier, K, E, ws + w.logits, K, B, ACT_NONE);
+  surv_head_fwd_kernel<<<nblk(B, 128), 128, 0, c.st>>>(ws + w.logits, io->hazards, io->S, io->Y, B, K);
+  c.chk(cudaGetLastError(), "surv_head_fwd");
+  return finish(c);
+}
+
+int mpo_surv_loss(int32_t kind, const float* hazards, const float* S, const int64_t* label, const float* censor,
+                  float alpha, float eps, float grad_scale, float* loss, float* dhaz, float* dS, int32_t B,
+                  int32_t n_classes, void* stream) {
+  if (kind != MPO_LOSS_NLL && kind != MPO_LOSS_CES) return fail(MPO_E_UNSUPPORTED, "%s", "mpo_surv_loss: unknown loss kind");
+  if (!hazards || !S || !label || !censor || !loss || !dhaz || !dS || B <= 0)
+    return fail(MPO_E_ARG, "%s", "mpo_surv_loss: bad arguments");
+  if (num_sms() <= 0) return fail(MPO_E_CUDA, "%s", "mpo_surv_loss: no CUDA device (this library has no CPU fallback)");
+  surv_loss_kernel<<<nblk(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(kind, hazards, S, label, censor, alpha,
+                                                                               eps, grad_scale, loss, dhaz, dS, B,
+                                                                               n_classes);
+  return check_cuda(cudaGetLastError(), "surv_loss_kernel");
+}
+
+int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dhaz, const float* dS, const float* dY,
+                      void* stream) {
+  int rc = check_model(m, io, "mpo_tail_post_bwd");
+  if (rc) return rc;
+  if (!io->pooled || !io->dpooled || !io->hazards || !io->S || !io->Y)
+    return fail(MPO_E_ARG, "%s", "mpo_tail_post_bwd: NULL pointer");
+  const int B = io->num_slides, R = 6 * B, K = m->n_classes;
+  Ws w; build_layout(m, B, w);
+  float* ws = io->ws;
+  Ctx c{static_cast<cudaStream_t>(stream)};
+  surv_head_bwd_kernel<<<nblk(B, 128), 128, 0, c.st>>>(io->hazards, io->S, io->Y, dhaz, dS, dY, ws + w.dlogits, B, K);
+  c.chk(cudaGetLastError(), "surv_head_bwd");
+  const float* hpath = ws + w.pool[0].h;
+  const float* homic = ws + w.pool[1].h;
+  float* dhpath = ws + w.dcat;          // [B,256] views used as outputs of the fusion backward
+  float* dhomic = ws + w.dcat + (long long)B * E;
+  if (m->fusion == MPO_FUSION_CONCAT) {
+    lin_bwd(c, ws + w.dlogits, K, ws + w.z2, E, m->classifier, K, E, ws + w.dh, E, B, false);
+    act_bwd(c, ws + w.dh, E, ws + w.z2, E, ws + w.dz2, E, B, E, ACT_RELU);
+    lin_bwd(c, ws + w.dz2, E, ws + w.z1, E, m->fusion2, E, E, ws + w.dh, E, B, false);
+    act_bwd(c, ws + w.dh, E, ws + w.z1, E, ws + w.dz1, E, B, E, ACT_RELU);
+    float* dcat = ws + w.s512;          // [B,512] scratch
+    lin_bwd(c, ws + w.dz1, E, ws + w.cat, 2 * E, m->fusion0, E, 2 * E, dcat, 2 * E, B, false);
+    cudaMemcpy2DAsync(dhpath, E * 4, dcat, 2 * E * 4, E * 4, B, cudaMemcpyDeviceToDevice, c.st);
+    cudaMemcpy2DAsync(dhomic, E * 4, dcat + E, 2 * E * 4, E * 4, B, cudaMemcpyDeviceToDevice, c.st);
+  } else {
+    lin_bwd(c, ws + w.dlogits, K, ws + w.bf2, E, m->classifier, K, E, ws + w.dh, E, B, false);
+    act_bwd(c, ws + w.dh, E, ws + w.bf2, E, ws + w.dz2, E, B, E, ACT_RELU);
+    lin_bwd(c, ws + w.dz2, E, ws + w.cat130, 130, m->bil.fc2, E, 130, ws + w.bdcat130, 130, B, false);
+    // fc1 (its output sits in cat130[:, :64])
+    act_bwd(c, ws + w.bdcat130, 130, ws + w.cat130, 130, ws + w.dz1, BMM, B, BMM, ACT_RELU);
+    lin_bwd(c, ws + w.dz1, BMM, ws + w.kp, 1089, m->bil.fc1, BMM, 1089, ws + w.bdkp, 1089, B, false);
+    bil_kron_bwd_kernel<<<B, 64, 0, c.st>>>(ws + w.bo[0], ws + w.bo[1], ws + w.bdkp, ws + w.bdcat130, ws + w.bdo[0],
+                                            ws + w.bdo[1]);
+    c.chk(cudaGetLastError(), "bil_kron_bwd");
+    // side 1: xa = h_path, xb = h_omic ; side 2: xa = h_omic, xb = h_path
+    cudaMemsetAsync(dhomic, 0, (size_t)B * E * 4, c.st);
+    bil_side_bwd(c, m->bil.h1, m->bil.z1, m->bil.o1, w, ws, 0, hpath, homic, dhpath, false, dhomic, B);
+    bil_side_bwd(c, m->bil.h2, m->bil.z2, m->bil.o2, w, ws, 1, homic, hpath, dhomic, true, dhpath, B);
+  }
+  // pooling heads -> token gradients
+  pool_bwd(c, m->path_pool, w.pool[0], w, ws, ws + w.enc[1].y2, dhpath, ws + w.dhp[0], ws + w.dtok[0], B);
+  pool_bwd(c, m->omic_pool, w.pool[1], w, ws, ws + w.enc[3].y2, dhomic, ws + w.dhp[1], ws + w.dtok[1], B);
+  // transformers
+  float* dhc = ws + w.dxa;              // [R,256]; dxa/dxb are free again after the pooling backward
+  enc_bwd(c, m->path_tr[1], w.enc[1], w, ws, ws + w.enc[0].y2, ws + w.dtok[0], ws + w.dxb, B);
+  enc_bwd(c, m->path_tr[0], w.enc[0], w, ws, ws + w.hc, ws + w.dxb, dhc, B);
+  enc_bwd(c, m->omic_tr[1], w.enc[3], w, ws, ws + w.enc[2].y2, ws + w.dtok[1], ws + w.dxb, B);
+  enc_bwd(c, m->omic_tr[0], w.enc[2], w, ws, ws + w.G, ws + w.dxb, ws + w.dG, B);
+  if (m->variant == MPO_VARIANT_NACAGAT) {
+    cag_bwd(c, m->cag, w, ws, ws + w.G, io->qp, dhc, ws + w.dG, ws + w.dqp, R);
+  }
+  // output and value projections back to the pooled vectors
+  lin_bwd(c, dhc, E, ws + w.v, E, m->coattn_out, E, E, ws + w.dxb, E, R, false);
+  lin_bwd(c, ws + w.dxb, E, io->pooled, E, sub(m->coattn_in, 2 * E, E), E, E, io->dpooled, E, R, false);
+  return finish(c);
+}
+
+int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
+  int rc = check_model(m, io, "mpo_tail_pre_bwd");
+  if (rc) return rc;
+  if (!io->dqk || !io->qp) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_bwd: NULL pointer");
+  const int B = io->num_slides, R = 6 * B;
+  Ws w; build_layout(m, B, w);
+  float* ws = io->ws;
+  Ctx c{static_cast<cudaStream_t>(stream)};
+  const bool nac = m->variant == MPO_VARIANT_NACAGAT;
+  const float* Wk = m->coattn_in.w + (long long)E * E;
+  float* gWk = m->coattn_in.gw ? m->coattn_in.gw + (long long)E * E : nullptr;
+  // key fold backward: dq[r][e] (+)= sum_d dqk[r][d] W_k[e][d] / 16 ; dW_k[e][d] += sum_r q[r][e] dqk[r][d] / 16
+  {
+    GemmArgs g{io->dqk, E, 1, Wk, 1, E, ws + w.dqp, E, nullptr, R, E, E, 1.f / 16.f, nac ? 1 : 0, ACT_NONE};
+    c.chk(launch_gemm(g, c.st), "fold.dq");
+    if (gWk) {
+      GemmArgs g2{io->qp, 1, E, io->dqk, E, 1, gWk, E, nullptr, E, E, R, 1.f / 16.f, 1, ACT_NONE};
+      c.chk(launch_gemm(g2, c.st), "fold.dWk");
+    }
+  }
+  if (nac) {
+    if (!io->dkc || !io->dtq) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_bwd: dkc/dtq are NULL (NaCAGaT)");
+    const float* bk = m->coattn_in.b + E;
+    float* gbk = m->coattn_in.gb ? m->coattn_in.gb + E : nullptr;
+    // kc = q . b_k / 16 :  dq += dkc b_k / 16 ; db_k += sum_r dkc[r] q[r] / 16
+    GemmArgs g{io->dkc, 1, 0, bk, 0, 1, ws + w.dqp, E, nullptr, R, E, 1, 1.f / 16.f, 1, ACT_NONE};
+    c.chk(launch_gemm(g, c.st), "kc.dq");
+    if (gbk) {
+      GemmArgs g2{io->dkc, 0, 1, io->qp, E, 1, gbk, E, nullptr, 1, E, R, 1.f / 16.f, 1, ACT_NONE};
+      c.chk(launch_gemm(g2, c.st), "kc.dbk");
+    }
+    // tanh(q) branch of the pre-gate: dq += dtq * (1 - tanh(q)^2)
+    act(c, io->qp, ws + w.s256a, (long long)R * E, ACT_TANH);
+    act_bwd(c, io->dtq, E, ws + w.s256a, E, ws + w.s256b, E, R, E, ACT_TANH);
+    add(c, ws + w.dqp, ws + w.s256b, ws + w.dqp, (long long)R * E);
+  }
+  // query in-projection
+  lin_bwd(c, ws + w.dqp, E, ws + w.G, E, sub(m->coattn_in, 0, E), E, E, ws + w.dG, E, R, true);
+  // SNN encoders
+  for (int i = 0; i < MPO_Q; ++i) {
+    const int d = m->omic_dims[i];
+    float* dz2 = ws + w.dz2;   // [B,256]
+    float* dz1 = ws + w.dz1;
+    act_bwd(c, ws + w.dG + i * E, 6 * E, ws + w.G + i * E, 6 * E, dz2, E, B, E, ACT_ELU);
+    lin_bwd(c, dz2, E, ws + w.snn_h[i], E, m->snn[i][1], E, E, ws + w.dh, E, B, false);
+    act_bwd(c, ws + w.dh, E, ws + w.snn_h[i], E, dz1, E, B, E, ACT_ELU);
+    lin_bwd(c, dz1, E, io->omics[i], d, m->snn[i][0], E, d, nullptr, 0, B, false);
+  }
+  return finish(c);
+}
+
+}  // extern "C"

@@ -1,0 +1,556 @@
+// fp32 building blocks of the slide "tail": everything that runs on the 6 omic tokens per slide
+// (SNN encoders, query projection, transformer encoders, gated attention pooling, fusion, survival head, losses).
+// All kernels are batched over the B slides of a step: token rows are laid out [slide][token] (R = 6B rows of 256).
+// The work is latency-bound: plain CUDA-core kernels, fp32 throughout.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "mpo_ptx.cuh"
+
+namespace mpo {
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };
+
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(x, 0.f);
+    case ACT_ELU: return x > 0.f ? x : expm1f(x);
+    case ACT_TANH: return tanhf(x);
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+    default: return x;
+  }
+}
+// derivative expressed through the activation OUTPUT y
+__device__ __forceinline__ float act_bwd_from_out(float y, int act) {
+  switch (act) {
+    case ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case ACT_ELU: return y > 0.f ? 1.f : y + 1.f;
+    case ACT_TANH: return 1.f - y * y;
+    case ACT_SIGMOID: return y * (1.f - y);
+    default: return 1.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic strided SIMT GEMM:  C[m][n] (+)= act(alpha * sum_k A(m,k) B(k,n) + bias[n])
+//   A(m,k) = A[m*sa_m + k*sa_k],  B(k,n) = B[k*sb_k + n*sb_n];  64x64x16 tiles, 256 threads, 4x4 per thread
+// ------------------------------------------------------------------------------------------------
+struct GemmArgs {
+  const float* A; long long sa_m, sa_k;
+  const float* B; long long sb_k, sb_n;
+  float* C; long long ldc;
+  const float* bias;
+  int M, N, K;
+  float alpha;
+  int accumulate;
+  int act;
+};
+
+template <bool A_KC, bool B_NC>
+__global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
+  __shared__ float As[16][68];
+  __shared__ float Bs[16][68];
+  const int t = threadIdx.x;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = t & 15, ty = t >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < g.K; k0 += 16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int mm, kk;
+      if (A_KC) { kk = t & 15; mm = (t >> 4) + 16 * j; } else { mm = t & 63; kk = (t >> 6) + 4 * j; }
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < g.M && k < g.K) ? g.A[m * g.sa_m + k * g.sa_k] : 0.f;
+      int nn, kb;
+      if (B_NC) { nn = t & 63; kb = (t >> 6) + 4 * j; } else { kb = t & 15; nn = (t >> 4) + 16 * j; }
+      const int n = n0 + nn, k2 = k0 + kb;
+      Bs[kb][nn] = (n < g.N && k2 < g.K) ? g.B[k2 * g.sb_k + n * g.sb_n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float v = g.alpha * acc[i][j];
+      if (g.bias != nullptr) v += g.bias[n];
+      v = act_fwd(v, g.act);
+      float* c = g.C + m * g.ldc + n;
+      *c = g.accumulate ? (*c + v) : v;
+    }
+  }
+}
+
+inline cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return cudaSuccess;
+  dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
+  const bool akc = (g.sa_k == 1), bnc = (g.sb_n == 1);
+  if (akc && bnc) gemm_kernel<true, true><<<grid, 256, 0, st>>>(g);
+  else if (akc && !bnc) gemm_kernel<true, false><<<grid, 256, 0, st>>>(g);
+  else if (!akc && bnc) gemm_kernel<false, true><<<grid, 256, 0, st>>>(g);
+  else gemm_kernel<false, false><<<grid, 256, 0, st>>>(g);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise helpers
+// ------------------------------------------------------------------------------------------------
+// dz[r][c] = dy[r][c] * act'(y[r][c])     (row strides allow views into wider buffers)
+__global__ void act_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ y,
+                               long long ldy, float* __restrict__ dz, long long lddz, int rows, int cols, int act) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * cols) return;
+  const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+  dz[r * lddz + c] = dy[r * lddy + c] * act_bwd_from_out(y[r * ldy + c], act);
+}
+
+// out[r][c] = a[r][c] + b[r][c]
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                           long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+__global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                           long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] * b[i];
+}
+// y = act(x) elementwise, in or out of place
+__global__ void act_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int act) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = act_fwd(x[i], act);
+}
+__global__ void fill_kernel(float* __restrict__ x, long long n, float v) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = v;
+}
+
+// g[c] += sum_r x[r][c]   (and optionally of x*y): bias / LayerNorm parameter gradients
+__global__ void colsum_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ y, long long ldy,
+                              float* __restrict__ g, int rows, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  if (y == nullptr) {
+    for (int r = 0; r < rows; ++r) s += x[r * ldx + c];
+  } else {
+    for (int r = 0; r < rows; ++r) s = fmaf(x[r * ldx + c], y[r * ldy + c], s);
+  }
+  g[c] += s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over 256 features, one warp per row:  y = LN(a + b) * gamma + beta   (b may be null)
+// saves xhat and rstd for the backward pass           (torch.nn.LayerNorm, eps 1e-5, biased variance)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ xhat,
+                     float* __restrict__ rstd, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = lane + 32 * j;
+    v[j] = a[row * 256 + c] + (b ? b[row * 256 + c] : 0.f);
+    s += v[j];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mu = s * (1.f / 256.f);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const float d = v[j] - mu; q = fmaf(d, d, q); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rs = rsqrtf(q * (1.f / 256.f) + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = lane + 32 * j;
+    const float xh = (v[j] - mu) * rs;
+    xhat[row * 256 + c] = xh;
+    y[row * 256 + c] = fmaf(xh, gamma[c], beta[c]);
+  }
+  if (lane == 0) rstd[row] = rs;
+}
+
+// dx = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)),  dxh = dy * gamma;  also writes t = dy * xhat
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ gamma, const float* __restrict__ xhat,
+                     const float* __restrict__ rstd, float* __restrict__ dx, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float dxh[8], xh[8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = lane + 32 * j;
+    xh[j] = xhat[row * 256 + c];
+    dxh[j] = dy[row * 256 + c] * gamma[c];
+    s1 += dxh[j];
+    s2 = fmaf(dxh[j], xh[j], s2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  s1 *= (1.f / 256.f);
+  s2 *= (1.f / 256.f);
+  const float rs = rstd[row];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dx[row * 256 + lane + 32 * j] = rs * (dxh[j] - s1 - xh[j] * s2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 8-head self-attention over the 6 tokens of a slide (nn.TransformerEncoderLayer's self_attn, head_dim 32)
+// one warp per (slide, head); lane = head-dim index.  qkv rows: [q(256) | k(256) | v(256)]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mha6_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ probs, float* __restrict__ ctx, int B) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= B * 8) return;
+  const int b = w >> 3, h = w & 7;
+  float q[6], k[6], v[6];
+#pragma unroll
+  for (int l = 0; l < 6; ++l) {
+    const float* row = qkv + static_cast<size_t>(b * 6 + l) * 768 + h * 32 + lane;
+    q[l] = row[0]; k[l] = row[256]; v[l] = row[512];
+  }
+  const float scale = 0.17677669529663687f;   // 1/sqrt(32)
+#pragma unroll
+  for (int l1 = 0; l1 < 6; ++l1) {
+    float s[6];
+#pragma unroll
+    for (int l2 = 0; l2 < 6; ++l2) {
+      float d = q[l1] * k[l2];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      s[l2] = d * scale;
+    }
+    float m = s[0];
+#pragma unroll
+    for (int l2 = 1; l2 < 6; ++l2) m = fmaxf(m, s[l2]);
+    float sum = 0.f;
+#pragma unroll
+    for (int l2 = 0; l2 < 6; ++l2) { s[l2] = expf(s[l2] - m); sum += s[l2]; }
+    const float inv = 1.f / sum;
+    float c = 0.f;
+#pragma unroll
+    for (int l2 = 0; l2 < 6; ++l2) {
+      s[l2] *= inv;
+      c = fmaf(s[l2], v[l2], c);
+      if (lane == 0) probs[(static_cast<size_t>(w) * 6 + l1) * 6 + l2] = s[l2];
+    }
+    ctx[static_cast<size_t>(b * 6 + l1) * 256 + h * 32 + lane] = c;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mha6_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs, const float* __restrict__ dctx,
+                float* __restrict__ dqkv, int B) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= B * 8) return;
+  const int b = w >> 3, h = w & 7;
+  float q[6], k[6], v[6], dc[6];
+#pragma unroll
+  for (int l = 0; l < 6; ++l) {
+    const float* row = qkv + static_cast<size_t>(b * 6 + l) * 768 + h * 32 + lane;
+    q[l] = row[0]; k[l] = row[256]; v[l] = row[512];
+    dc[l] = dctx[static_cast<size_t>(b * 6 + l) * 256 + h * 32 + lane];
+  }
+  float dq[6], dk[6], dv[6];
+#pragma unroll
+  for (int l = 0; l < 6; ++l) { dq[l] = 0.f; dk[l] = 0.f; dv[l] = 0.f; }
+  const float scale = 0.17677669529663687f;
+#pragma unroll
+  for (int l1 = 0; l1 < 6; ++l1) {
+    float a[6], da[6];
+    float dot = 0.f;
+#pragma unroll
+    for (int l2 = 0; l2 < 6; ++l2) {
+      a[l2] = probs[(static_cast<size_t>(w) * 6 + l1) * 6 + l2];
+      float d = dc[l1] * v[l2];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      da[l2] = d;
+      dot = fmaf(d, a[l2], dot);
+      dv[l2] = fmaf(a[l2], dc[l1], dv[l2]);
+    }
+#pragma unroll
+    for (int l2 = 0; l2 < 6; ++l2) {
+      const float ds = a[l2] * (da[l2] - dot) * scale;
+      dq[l1] = fmaf(ds, k[l2], dq[l1]);
+      dk[l2] = fmaf(ds, q[l1], dk[l2]);
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < 6; ++l) {
+    float* row = dqkv + static_cast<size_t>(b * 6 + l) * 768 + h * 32 + lane;
+    row[0] = dq[l]; row[256] = dk[l]; row[512] = dv[l];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gated attention pooling core (reference: models/blocks.py:42-48 + models/mcat/mcat.py:105-108)
+// one block (256 threads = feature index) per slide
+//   A[l] = sum_d a[l][d] b[l][d] wc[d] + bc ;  w = softmax_l(A) ;  hp[d] = sum_l w[l] x[l][d]
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r += sh[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ bgate,
+                const float* __restrict__ wc, const float* __restrict__ bc, float* __restrict__ logits,
+                float* __restrict__ w, float* __restrict__ hp) {
+  __shared__ float sh[8];
+  const int b = blockIdx.x, d = threadIdx.x;
+  float A[6];
+#pragma unroll
+  for (int l = 0; l < 6; ++l) {
+    const size_t o = static_cast<size_t>(b * 6 + l) * 256 + d;
+    A[l] = block_sum_256(a[o] * bgate[o] * wc[d], sh) + bc[0];
+  }
+  float m = A[0];
+#pragma unroll
+  for (int l = 1; l < 6; ++l) m = fmaxf(m, A[l]);
+  float e[6], sum = 0.f;
+#pragma unroll
+  for (int l = 0; l < 6; ++l) { e[l] = expf(A[l] - m); sum += e[l]; }
+  float acc = 0.f;
+#pragma unroll
+  for (int l = 0; l < 6; ++l) {
+    e[l] /= sum;
+    acc = fmaf(e[l], x[static_cast<size_t>(b * 6 + l) * 256 + d], acc);
+  }
+  hp[static_cast<size_t>(b) * 256 + d] = acc;
+  if (d < 6) { logits[b * 6 + d] = A[d]; w[b * 6 + d] = e[d]; }
+}
+
+// dx (overwritten) gets the value-path gradient w[l]*dhp; da_pre/db_pre are the gradients at the pre-activations of
+// the tanh / sigmoid branches; gwc/gbc are accumulated with atomics (one add per slide and feature)
+__global__ void __launch_bounds__(256)
+pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ bgate,
+                const float* __restrict__ wc, const float* __restrict__ w, const float* __restrict__ dhp,
+                float* __restrict__ dx, float* __restrict__ da_pre, float* __restrict__ db_pre,
+                float* __restrict__ gwc, float* __restrict__ gbc) {
+  __shared__ float sh[8];
+  const int b = blockIdx.x, d = threadIdx.x;
+  const float g = dhp[static_cast<size_t>(b) * 256 + d];
+  float wl[6], dw[6];
+  float dot = 0.f;
+#pragma unroll
+  for (int l = 0; l < 6; ++l) {
+    wl[l] = w[b * 6 + l];
+    dw[l] = block_sum_256(g * x[static_cast<size_t>(b * 6 + l) * 256 + d], sh);
+    dot = fmaf(dw[l], wl[l], dot);
+  }
+  float gw = 0.f, gb = 0.f;
+#pragma unroll
+  for (int l = 0; l < 6; ++l) {
+    const size_t o = static_cast<size_t>(b * 6 + l) * 256 + d;
+    const float dA = wl[l] * (dw[l] - dot);
+    const float av = a[o], bv = bgate[o];
+    const float dab = dA * wc[d];
+    dx[o] = wl[l] * g;
+    da_pre[o] = dab * bv * (1.f - av * av);
+    db_pre[o] = dab * av * bv * (1.f - bv);
+    gw = fmaf(dA, av * bv, gw);
+    gb += dA;
+  }
+  if (gwc != nullptr) atomicAdd(gwc + d, gw);
+  if (gbc != nullptr && d == 0) atomicAdd(gbc, gb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// survival head (models/mcat/mcat.py:126-138) and losses (models/loss.py:5-43), one thread per slide
+// ------------------------------------------------------------------------------------------------
+__global__ void surv_head_fwd_kernel(const float* __restrict__ logits, float* __restrict__ hazards,
+                                     float* __restrict__ S, float* __restrict__ Y, int B, int K) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float m = -INFINITY;
+  for (int j = 0; j < K; ++j) m = fmaxf(m, logits[b * K + j]);
+  float sum = 0.f, s = 1.f;
+  for (int j = 0; j < K; ++j) {
+    const float z = logits[b * K + j];
+    const float hz = 1.f / (1.f + expf(-z));
+    hazards[b * K + j] = hz;
+    s *= (1.f - hz);
+    S[b * K + j] = s;
+    sum += expf(z - m);
+  }
+  for (int j = 0; j < K; ++j) Y[b * K + j] = expf(logits[b * K + j] - m) / sum;
+}
+
+// dlogits from upstream gradients of hazards, S and Y (any may be null)
+__global__ void surv_head_bwd_kernel(const float* __restrict__ hazards, const float* __restrict__ S,
+                                     const float* __restrict__ Y, const float* __restrict__ dhaz,
+                                     const float* __restrict__ dS, const float* __restrict__ dY,
+                                     float* __restrict__ dlogits, int B, int K) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float dotY = 0.f;
+  if (dY) for (int j = 0; j < K; ++j) dotY = fmaf(dY[b * K + j], Y[b * K + j], dotY);
+  float tail = 0.f;   // sum_{j >= t} dS_j S_j, built from the last interval backwards
+  for (int t = K - 1; t >= 0; --t) {
+    const float hz = hazards[b * K + t];
+    if (dS) tail = fmaf(dS[b * K + t], S[b * K + t], tail);
+    float dh = dhaz ? dhaz[b * K + t] : 0.f;
+    dh -= tail / (1.f - hz);
+    float dl = dh * hz * (1.f - hz);
+    if (dY) dl += Y[b * K + t] * (dY[b * K + t] - dotY);
+    dlogits[b * K + t] = dl;
+  }
+}
+
+// kind 0 = NLL (alpha .15), 1 = CES (alpha .75); grad_scale multiplies the gradients (e.g. 1/grad_acc_step)
+__global__ void surv_loss_kernel(int kind, const float* __restrict__ hazards, const float* __restrict__ S,
+                                 const int64_t* __restrict__ label, const float* __restrict__ censor, float alpha,
+                                 float eps, float grad_scale, float* __restrict__ loss, float* __restrict__ dhaz,
+                                 float* __restrict__ dS, int B, int K) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int y = static_cast<int>(label[b]);
+  const float c = censor[b];
+  for (int j = 0; j < K; ++j) { dhaz[b * K + j] = 0.f; dS[b * K + j] = 0.f; }
+  const float s_prev = y == 0 ? 1.f : S[b * K + y - 1];
+  const float h_y = hazards[b * K + y];
+  const float unc = -(1.f - c) * (logf(fmaxf(s_prev, eps)) + logf(fmaxf(h_y, eps)));
+  float w_unc;
+  float l;
+  if (kind == 0) {
+    const float s_y = S[b * K + y];
+    const float cen = -c * logf(fmaxf(s_y, eps));
+    l = (1.f - alpha) * (cen + unc) + alpha * unc;
+    w_unc = 1.f;
+    if (s_y > eps) dS[b * K + y] += grad_scale * (1.f - alpha) * (-c / s_y);
+  } else {
+    const float s_y = fmaxf(S[b * K + y], eps);
+    const float ce = -(c * logf(s_y) + (1.f - c) * logf(1.f - s_y));
+    l = (1.f - alpha) * ce + alpha * unc;
+    w_unc = alpha;
+    if (S[b * K + y] > eps) dS[b * K + y] += grad_scale * (1.f - alpha) * (-(c / s_y) + (1.f - c) / (1.f - s_y));
+  }
+  if (y >= 1 && s_prev > eps) dS[b * K + y - 1] += grad_scale * w_unc * (-(1.f - c) / s_prev);
+  if (h_y > eps) dhaz[b * K + y] += grad_scale * w_unc * (-(1.f - c) / h_y);
+  loss[b] = l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bilinear-fusion helpers (models/fusion.py:81-113)
+// ------------------------------------------------------------------------------------------------
+// z[b][k] = sum_i x1[b][i] U[b][k*256+i] + bias[k];  g = sigmoid(z);  gh = g * h          (U = x2 W_z^T, by GEMM)
+__global__ void __launch_bounds__(256)
+bil_gate_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ U, const float* __restrict__ bias,
+                    const float* __restrict__ h, float* __restrict__ g, float* __restrict__ gh) {
+  const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int k = wid; k < 32; k += 8) {
+    float s = 0.f;
+    for (int i = lane; i < 256; i += 32) s = fmaf(x1[b * 256 + i], U[(static_cast<size_t>(b) * 32 + k) * 256 + i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      const float gg = 1.f / (1.f + expf(-(s + bias[k])));
+      g[b * 32 + k] = gg;
+      gh[b * 32 + k] = gg * h[b * 32 + k];
+    }
+  }
+}
+// from dgh: dh_pre = dgh*g*1[h>0], dz = dgh*h*g(1-g);  V[b][k*256+i] = dz[b][k] x1[b][i];  dx1[b][i] (+)= sum_k dz U
+__global__ void __launch_bounds__(256)
+bil_gate_bwd_kernel(const float* __restrict__ x1, const float* __restrict__ U, const float* __restrict__ h,
+                    const float* __restrict__ g, const float* __restrict__ dgh, float* __restrict__ dh_pre,
+                    float* __restrict__ dz, float* __restrict__ V, float* __restrict__ dx1, int accumulate_dx1) {
+  __shared__ float dz_s[32];
+  const int b = blockIdx.x, i = threadIdx.x;
+  if (i < 32) {
+    const float gg = g[b * 32 + i], hh = h[b * 32 + i], d = dgh[b * 32 + i];
+    dh_pre[b * 32 + i] = hh > 0.f ? d * gg : 0.f;
+    const float z = d * hh * gg * (1.f - gg);
+    dz[b * 32 + i] = z;
+    dz_s[i] = z;
+  }
+  __syncthreads();
+  const float xi = x1[b * 256 + i];
+  float acc = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < 32; ++k) {
+    const size_t o = (static_cast<size_t>(b) * 32 + k) * 256 + i;
+    V[o] = dz_s[k] * xi;
+    acc = fmaf(dz_s[k], U[o], acc);
+  }
+  float* dst = dx1 + b * 256 + i;
+  *dst = accumulate_dx1 ? (*dst + acc) : acc;
+}
+// kp[b][i*33+j] = o1e[i]*o2e[j] with o?e = [o?, 1];  cat tail = [o1e, o2e] written at cat[b][64..130)
+__global__ void bil_kron_fwd_kernel(const float* __restrict__ o1, const float* __restrict__ o2,
+                                    float* __restrict__ kp, float* __restrict__ cat) {
+  const int b = blockIdx.x;
+  for (int e = threadIdx.x; e < 33 * 33; e += blockDim.x) {
+    const int i = e / 33, j = e % 33;
+    const float a = i < 32 ? o1[b * 32 + i] : 1.f;
+    const float c = j < 32 ? o2[b * 32 + j] : 1.f;
+    kp[static_cast<size_t>(b) * 1089 + e] = a * c;
+  }
+  for (int e = threadIdx.x; e < 66; e += blockDim.x) {
+    const int i = e % 33;
+    const float v = e < 33 ? (i < 32 ? o1[b * 32 + i] : 1.f) : (i < 32 ? o2[b * 32 + i] : 1.f);
+    cat[static_cast<size_t>(b) * 130 + 64 + e] = v;
+  }
+}
+// do1[b][i] = dcat[b][64+i] + sum_j dkp[b][i*33+j] o2e[j];  do2[b][j] = dcat[b][97+j] + sum_i dkp[b][i*33+j] o1e[i]
+__global__ void bil_kron_bwd_kernel(const float* __restrict__ o1, const float* __restrict__ o2,
+                                    const float* __restrict__ dkp, const float* __restrict__ dcat,
+                                    float* __restrict__ do1, float* __restrict__ do2) {
+  const int b = blockIdx.x, t = threadIdx.x;   // 64 threads
+  if (t < 32) {
+    float s = dcat[static_cast<size_t>(b) * 130 + 64 + t];
+    for (int j = 0; j < 33; ++j) s = fmaf(dkp[static_cast<size_t>(b) * 1089 + t * 33 + j], j < 32 ? o2[b * 32 + j] : 1.f, s);
+    do1[b * 32 + t] = s;
+  } else if (t < 64) {
+    const int j = t - 32;
+    float s = dcat[static_cast<size_t>(b) * 130 + 97 + j];
+    for (int i = 0; i < 33; ++i) s = fmaf(dkp[static_cast<size_t>(b) * 1089 + i * 33 + j], i < 32 ? o1[b * 32 + i] : 1.f, s);
+    do2[b * 32 + j] = s;
+  }
+}
+
+}  // namespace mpo

@@ -1,0 +1,367 @@
+"""Slide engine: drives the C-ABI stages for a batch of slides (pre -> bag forward -> post -> loss -> post
+backward -> bag backward -> pre backward) on behalf of the drop-in modules.
+
+Stage order mirrors the reference forward (models/mcat/mcat.py:84-142) and its autograd graph.  PyTorch's role here
+is limited to owning device memory / streams and, for the per-slide module API, to carrying the gradients back
+into nn.Parameter.grad through one torch.autograd.Function.
+"""
+import ctypes
+import itertools
+
+import torch
+
+from . import _lib
+from . import bagpass as bp
+from .bagpass import D, Q, _ptr, _stream, require_cuda
+
+VARIANT_MCAT, VARIANT_NACAGAT = 0, 1
+FUSION_CONCAT, FUSION_BILINEAR = 0, 1
+_FUSION_CODE = {"concat": FUSION_CONCAT, "bilinear": FUSION_BILINEAR}
+
+_seed_counter = itertools.count(1)
+
+
+def _next_seed():
+    return (torch.initial_seed() * 2654435761 + next(_seed_counter) * 40503) & 0xFFFFFFFF
+
+
+def _lin_names(prefix):
+    return prefix + ".weight", prefix + ".bias"
+
+
+class ModelBinding:
+    """Maps a module's parameters onto struct mpo_model.  grads: {param name: tensor} or None (inference)."""
+
+    def __init__(self, module, variant, fusion, omic_sizes, n_classes):
+        if fusion not in _FUSION_CODE:
+            raise NotImplementedError(
+                "fusion=%r is not implemented on the B200 path (concat and bilinear are; gated_concat is listed "
+                "as a next step in SURVEY.md 8f)" % fusion)
+        if len(omic_sizes) != Q:
+            raise NotImplementedError("the B200 kernels are built for 6 omic signature groups, got %d" % len(omic_sizes))
+        self.module = module
+        self.variant = variant
+        self.fusion = _FUSION_CODE[fusion]
+        self.omic_sizes = [int(d) for d in omic_sizes]
+        self.n_classes = int(n_classes)
+        self.names = [n for n, _ in module.named_parameters()]
+
+    def params(self):
+        return dict(self.module.named_parameters())
+
+    def build(self, grads=None):
+        P = self.params()
+        for n, p in P.items():
+            if not p.is_cuda:
+                raise RuntimeError("parameter %s is on %s: move the model to a CUDA device (no CPU fallback)" % (n, p.device))
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("parameter %s must be contiguous float32" % n)
+        keep = []
+
+        def lin(prefix, wname=None, bname=None):
+            wn, bn = (wname, bname) if wname else _lin_names(prefix)
+            L = _lib.MpoLin()
+            L.w = P[wn].data_ptr()
+            L.b = P[bn].data_ptr()
+            if grads is not None:
+                L.gw = grads[wn].data_ptr()
+                L.gb = grads[bn].data_ptr()
+            return L
+
+        def norm(prefix):
+            N = _lib.MpoNorm()
+            N.g = P[prefix + ".weight"].data_ptr()
+            N.b = P[prefix + ".bias"].data_ptr()
+            if grads is not None:
+                N.gg = grads[prefix + ".weight"].data_ptr()
+                N.gb = grads[prefix + ".bias"].data_ptr()
+            return N
+
+        def enc_layer(prefix):
+            E = _lib.MpoEncoderLayer()
+            E.in_proj = lin(None, prefix + ".self_attn.in_proj_weight", prefix + ".self_attn.in_proj_bias")
+            E.out_proj = lin(prefix + ".self_attn.out_proj")
+            E.linear1 = lin(prefix + ".linear1")
+            E.linear2 = lin(prefix + ".linear2")
+            E.norm1 = norm(prefix + ".norm1")
+            E.norm2 = norm(prefix + ".norm2")
+            return E
+
+        def pool(head, rho):
+            H = _lib.MpoPoolHead()
+            H.att_a = lin(head + ".attention_a.0")
+            H.att_b = lin(head + ".attention_b.0")
+            H.att_c = lin(head + ".attention_c")
+            H.rho = lin(rho + ".0")
+            return H
+
+        m = _lib.MpoModel()
+        m.variant = self.variant
+        m.fusion = self.fusion
+        m.n_classes = self.n_classes
+        for i, d in enumerate(self.omic_sizes):
+            m.omic_dims[i] = d
+            m.snn[i][0] = lin("G.%d.0.0" % i)
+            m.snn[i][1] = lin("G.%d.1.0" % i)
+        m.H = lin("H.0")
+        m.coattn_in = lin(None, "co_attention.in_proj_weight", "co_attention.in_proj_bias")
+        m.coattn_out = lin("co_attention.out_proj")
+        if self.variant == VARIANT_NACAGAT:
+            c = _lib.MpoCag()
+            c.fc1 = lin("co_attention.CAG.fc1.0")
+            c.fc2 = lin("co_attention.CAG.fc2.0")
+            c.fc3 = lin("co_attention.CAG.fc3.0")
+            c.fc_c = lin("co_attention.CAG.fc_c.0")
+            c.G = norm("co_attention.CAG.G.1")
+            c.E = norm("co_attention.CAG.E.1")
+            m.cag = c
+        for l in range(2):
+            m.path_tr[l] = enc_layer("path_transformer.layers.%d" % l)
+            m.omic_tr[l] = enc_layer("omic_transformer.layers.%d" % l)
+        m.path_pool = pool("path_attention_head", "path_rho")
+        m.omic_pool = pool("omic_attention_head", "omic_rho")
+        if self.fusion == FUSION_CONCAT:
+            m.fusion0 = lin("fusion_layer.fusion_layer.0")
+            m.fusion2 = lin("fusion_layer.fusion_layer.2")
+        else:
+            b = _lib.MpoBilinear()
+            b.h1 = lin("fusion_layer.linear_h1.0")
+            b.z1 = lin("fusion_layer.linear_z1")
+            b.o1 = lin("fusion_layer.linear_o1.0")
+            b.h2 = lin("fusion_layer.linear_h2.0")
+            b.z2 = lin("fusion_layer.linear_z2")
+            b.o2 = lin("fusion_layer.linear_o2.0")
+            b.fc1 = lin("fusion_layer.fc1.0")
+            b.fc2 = lin("fusion_layer.fc2.0")
+            m.bil = b
+        m.classifier = lin("classifier")
+        keep.append(P)
+        keep.append(grads)
+        m._keepalive = keep
+        return m
+
+
+class SlideState:
+    """Everything one forward pass leaves behind for the backward pass."""
+    pass
+
+
+class SlideEngine:
+    def __init__(self, binding, bag_dropout=0.25):
+        self.binding = binding
+        self.bag_dropout = float(bag_dropout)
+        self._ws_cache = {}
+        self._w_bf16 = None
+
+    # -- helpers
+    def _tail_ws(self, model, B, device, reuse):
+        """fresh workspace per pass unless the caller guarantees forward/backward alternate (BatchTrainer)."""
+        key = (B, str(device))
+        if reuse and key in self._ws_cache:
+            return self._ws_cache[key]
+        n = _lib.lib().mpo_tail_ws_floats(ctypes.byref(model), B)
+        if n <= 0:
+            raise RuntimeError("mpo_tail_ws_floats failed")
+        ws = torch.empty(n, dtype=torch.float32, device=device)
+        if reuse:
+            self._ws_cache = {key: ws}   # keep one size around
+        return ws
+
+    def ws_view(self, model, st, name):
+        """named intermediate of the tail workspace (tests / debugging)."""
+        n = ctypes.c_int64()
+        off = _lib.lib().mpo_tail_ws_lookup(ctypes.byref(model), st.B, name.encode(), ctypes.byref(n))
+        if off < 0:
+            raise KeyError(name)
+        return st.tail_ws[off:off + n.value]
+
+    def _io(self, st):
+        io = _lib.MpoTailIo()
+        io.num_slides = st.B
+        for i in range(Q):
+            io.omics[i] = st.omics[i].data_ptr()
+        io.ws = st.tail_ws.data_ptr()
+        io.qp = st.qp.data_ptr()
+        io.qk = st.qk.data_ptr()
+        io.kc = st.kc.data_ptr() if st.kc is not None else None
+        io.pooled = st.bag_ws.pooled.data_ptr()
+        io.dpooled = st.dpooled.data_ptr() if st.dpooled is not None else None
+        io.dqk = st.dqk.data_ptr() if st.dqk is not None else None
+        io.hazards = st.hazards.data_ptr()
+        io.S = st.S.data_ptr()
+        io.Y = st.Y.data_ptr()
+        io.att_path = st.att_path.data_ptr()
+        io.att_omic = st.att_omic.data_ptr()
+        return io
+
+    # -- forward
+    def forward(self, model, bag, omics, train=False, save_for_backward=True, seed=None, reuse_ws=False):
+        """bag: PackedBag of B slides; omics: 6 tensors [B, d_i] float32 on the GPU."""
+        bnd = self.binding
+        if bnd.variant == VARIANT_NACAGAT:
+            raise NotImplementedError("NaCAGaT bag kernels are not wired into this build yet")
+        dev = bag.x.device
+        B = bag.num_slides
+        st = SlideState()
+        st.B, st.bag, st.train = B, bag, bool(train)
+        st.omics = []
+        for i, o in enumerate(omics):
+            require_cuda(o, "omics[%d]" % i)
+            o = o.to(torch.float32).reshape(B, -1).contiguous()
+            if o.shape[1] != bnd.omic_sizes[i]:
+                raise RuntimeError("omics[%d] has width %d, the model expects %d" % (i, o.shape[1], bnd.omic_sizes[i]))
+            st.omics.append(o)
+        f32 = dict(dtype=torch.float32, device=dev)
+        K = bnd.n_classes
+        st.tail_ws = self._tail_ws(model, B, dev, reuse_ws)
+        st.qp = torch.empty((B, Q, D), **f32)
+        st.qk = torch.empty((B, Q, D), **f32)
+        st.kc = None
+        st.dpooled = st.dqk = None
+        st.hazards = torch.empty((B, K), **f32)
+        st.S = torch.empty((B, K), **f32)
+        st.Y = torch.empty((B, K), **f32)
+        st.att_path = torch.empty((B, Q), **f32)
+        st.att_omic = torch.empty((B, Q), **f32)
+        st.bag_ws = bp.BagWorkspace(bag, save_h=save_for_backward)
+        st.drop_p = self.bag_dropout if train else 0.0
+        st.seed = (_next_seed() if seed is None else seed) if train else 0
+        P = bnd.params()
+        # bf16 streaming copy of H.0.weight
+        w_h = P["H.0.weight"]
+        if self._w_bf16 is None or self._w_bf16.device != w_h.device:
+            self._w_bf16 = torch.empty(w_h.shape, dtype=torch.bfloat16, device=w_h.device)
+        bp.cast_bf16(w_h.detach(), out=self._w_bf16)
+        io = self._io(st)
+        s = _stream()
+        _lib.call("mpo_tail_pre_fwd", ctypes.byref(model), ctypes.byref(io), s)
+        bp.bag_forward(bag, self._w_bf16, P["H.0.bias"].detach(), st.qk, st.bag_ws, seed=st.seed, drop_p=st.drop_p)
+        _lib.call("mpo_tail_post_fwd", ctypes.byref(model), ctypes.byref(io), s)
+        return st
+
+    def attention_map(self, st):
+        """normalised co-attention map [6, total_rows] (attention_scores['coattn'])."""
+        return bp.attention_map(st.bag, st.bag_ws)
+
+    # -- backward
+    def backward(self, model, st, dhaz, dS, dY):
+        """model must carry gradient pointers; they are accumulated into."""
+        dev = st.bag.x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        st.dpooled = torch.empty((st.B, Q, D), **f32)
+        io = self._io(st)
+        s = _stream()
+
+        def prep(g):
+            if g is None:
+                return None
+            return g.detach().to(torch.float32).reshape(st.B, -1).contiguous()
+
+        dhaz, dS, dY = prep(dhaz), prep(dS), prep(dY)
+        _lib.call("mpo_tail_post_bwd", ctypes.byref(model), ctypes.byref(io), _ptr(dhaz), _ptr(dS), _ptr(dY), s)
+        if not model.H.gw or not model.H.gb:
+            raise RuntimeError("backward needs a model binding with gradient buffers")
+        gw, gb = ctypes.c_void_p(model.H.gw), ctypes.c_void_p(model.H.gb)
+        st.bag_ws.ensure_bwd(st.bag)
+        st.dqk = torch.empty((st.B, Q, D), **f32)
+        ws = st.bag_ws
+        _lib.call("mpo_bag_bwd", st.bag.c(), _ptr(ws.h_saved), _ptr(ws.scores), _ptr(ws.lse), _ptr(ws.pooled),
+                  _ptr(st.dpooled), _ptr(st.qk), _ptr(ws.dz), _ptr(ws.part_dqk), _ptr(ws.part_db), _ptr(st.dqk),
+                  gw, gb, ctypes.c_float(st.drop_p), s)
+        io = self._io(st)
+        _lib.call("mpo_tail_pre_bwd", ctypes.byref(model), ctypes.byref(io), s)
+
+
+# ------------------------------------------------------------------------------------------------ per-slide autograd
+class _SlideFn(torch.autograd.Function):
+    """One slide through the engine with gradients delivered to nn.Parameter.grad by autograd."""
+
+    @staticmethod
+    def forward(ctx, engine, want_map, train, wsi, n_omics, *rest):
+        omics = rest[:n_omics]
+        params = rest[n_omics:]
+        bnd = engine.binding
+        bag = bp.PackedBag.from_slides([wsi.detach()])
+        needs_bwd = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+        model = bnd.build(grads=None)
+        st = engine.forward(model, bag, [o.detach().reshape(1, -1) for o in omics], train=train,
+                            save_for_backward=needs_bwd)
+        ctx.engine, ctx.state, ctx.n_omics, ctx.n_params = engine, st, n_omics, len(params)
+        coattn = engine.attention_map(st) if want_map else torch.empty(0, device=wsi.device)
+        outs = (st.hazards, st.S, st.Y, coattn, st.att_path, st.att_omic)
+        ctx.mark_non_differentiable(coattn, st.att_path, st.att_omic)
+        return outs
+
+    @staticmethod
+    def backward(ctx, dhaz, dS, dY, *unused):
+        engine, st = ctx.engine, ctx.state
+        bnd = engine.binding
+        P = bnd.params()
+        if st.bag_ws.h_saved is None:
+            raise RuntimeError("this forward pass did not keep activations (it ran under no_grad)")
+        total = sum(p.numel() for p in P.values())
+        flat = torch.zeros(total, dtype=torch.float32, device=st.bag.x.device)
+        grads, off = {}, 0
+        for n, p in P.items():
+            grads[n] = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        model = bnd.build(grads=grads)
+        engine.backward(model, st, dhaz, dS, dY)
+        return (None, None, None, None, None) + (None,) * ctx.n_omics + tuple(grads[n] for n in bnd.names)
+
+
+def run_slide(engine, wsi, omics, want_map, train):
+    """Module-level entry used by the drop-in forward()s.  Returns hazards, S, Y [1,K], coattn or None, path, omic."""
+    require_cuda(wsi, "wsi")
+    bnd = engine.binding
+    params = [dict(bnd.module.named_parameters())[n] for n in bnd.names]
+    outs = _SlideFn.apply(engine, bool(want_map), bool(train), wsi, len(omics), *omics, *params)
+    hazards, S, Y, coattn, a_path, a_omic = outs
+    return hazards, S, Y, (coattn if want_map else None), a_path, a_omic
+
+
+# ------------------------------------------------------------------------------------------------ batched training
+class BatchTrainer:
+    """Forward + loss + backward for B slides per call with gradients accumulated straight into one flat fp32
+    buffer whose slices are the parameters' .grad (so a single NCCL all-reduce covers the whole model).
+
+    Loop semantics follow the reference driver (models/mcat/main.py:30-74): loss / grad_acc_step, gradients
+    accumulate until the caller steps the optimizer."""
+
+    def __init__(self, module, loss="nll", alpha=None, eps=1e-7, grad_acc_step=32):
+        self.module = module
+        self.engine = module._engine
+        bnd = self.engine.binding
+        P = bnd.params()
+        dev = next(iter(P.values())).device
+        total = sum(p.numel() for p in P.values())
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grads, off = {}, 0
+        for n, p in P.items():
+            g = self.flat_grad[off:off + p.numel()].view_as(p)
+            p.grad = g
+            self.grads[n] = g
+            off += p.numel()
+        self.kind = {"nll": 0, "ces": 1}[loss]
+        self.alpha = float(alpha if alpha is not None else (0.15 if loss == "nll" else 0.75))
+        self.eps = float(eps)
+        self.grad_acc_step = int(grad_acc_step)
+        self.model = bnd.build(grads=self.grads)
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def step(self, bag, omics, labels, censor, train=True, seed=None):
+        """Returns (loss [B], hazards [B,K], S [B,K]).  labels int64 [B], censor float32 [B], on the GPU."""
+        eng = self.engine
+        st = eng.forward(self.model, bag, omics, train=train, save_for_backward=True, seed=seed, reuse_ws=True)
+        B, K = st.B, eng.binding.n_classes
+        loss = torch.empty(B, dtype=torch.float32, device=bag.x.device)
+        dhz = torch.empty((B, K), dtype=torch.float32, device=bag.x.device)
+        dS = torch.empty((B, K), dtype=torch.float32, device=bag.x.device)
+        _lib.call("mpo_surv_loss", self.kind, _ptr(st.hazards), _ptr(st.S), _ptr(labels), _ptr(censor),
+                  ctypes.c_float(self.alpha), ctypes.c_float(self.eps), ctypes.c_float(1.0 / self.grad_acc_step),
+                  _ptr(loss), _ptr(dhz), _ptr(dS), B, K, _stream())
+        eng.backward(self.model, st, dhz, dS, None)
+        self.last_state = st
+        return loss, st.hazards, st.S
