@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Headline benchmark: slides/s for one train step (forward + loss + backward + Adam) of the slide hot path at
+16 384 patches per slide, on N B200s of one node (data-parallel over slides, weak scaling).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm on the host cores (oracle port, numpy)
+
+Prints ONE JSON line on rank 0 (contract in the task description / DESIGN.md section "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PATCH = 16384
+ALGO_BYTES_PER_PATCH_PASS = 2048          # one bf16 row of 1024 features, read once per pass
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default=os.environ.get("MPO_BENCH_MODEL", "mcat"), choices=["mcat", "nacagat"])
+    ap.add_argument("--batch", type=int, default=32, help="slides per GPU per step (= the reference's grad_acc_step)")
+    ap.add_argument("--patches", type=int, default=N_PATCH)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU (reference algorithm)
+def cpu_reference_rate(model, n_patch, budget_s=12.0, min_steps=2, steps=None):
+    """fwd+bwd of the reference algorithm (oracle port, fp32 numpy) on the host cores; returns slides/s."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mpo_oracle as orc
+    from importlib import import_module
+    synth = import_module("multimodal-path-omic_b200.synth")
+    orc.use_dtype(np.float32)
+    shapes = reference_shapes(model)
+    state = synth.make_state(shapes, 0, model=model)
+    bag, omics, label, censor = synth.make_slide(0, n_patch)
+    times = []
+    t_end = time.time() + budget_s
+    while True:
+        t0 = time.time()
+        orc.model_forward_backward(state, bag, omics, label, censor, model=model, fusion="concat", loss="nll")
+        times.append(time.time() - t0)
+        if steps is not None:
+            if len(times) >= steps:
+                break
+        elif len(times) >= min_steps and time.time() > t_end:
+            break
+    orc.use_dtype(np.float64)
+    times.sort()
+    med = times[len(times) // 2]
+    return 1.0 / med, len(times), med
+
+
+def reference_shapes(model):
+    """state_dict shapes of the drop-in module (identical to the reference's, tests/test_modules.py checks it)."""
+    import torch
+    from importlib import import_module
+    synth = import_module("multimodal-path-omic_b200.synth")
+    if model == "mcat":
+        cls = import_module("multimodal-path-omic_b200.mcat").MultimodalCoAttentionTransformer
+    else:
+        cls = import_module("multimodal-path-omic_b200.nacagat").NarrowContextualAttentionGateTransformer
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = cls(omic_sizes=list(synth.OMIC_SIZES))
+    return {k: tuple(v.shape) for k, v in net.state_dict().items()}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    warm = max(1, min(args.warmup, 2))
+    rate0, _, _ = cpu_reference_rate(args.model, args.patches, steps=warm)
+    rate, n, med = cpu_reference_rate(args.model, args.patches, steps=max(1, args.steps))
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "slides/sec (fwd+bwd, 16k patches)", "value": rate, "unit": "slides/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model}_train_step_{args.patches}_patches", "slides_per_step": 1,
+                   "note": "reference algorithm restated in numpy (oracle port): the reference itself is a PyTorch "
+                           "package that cannot travel to the GPU box; each step is one slide fwd+bwd on the host cores"},
+        "cpu_baseline": {"value": rate, "unit": "slides/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} x 1 slide of {args.patches} patches, fp32 numpy, all BLAS threads"},
+        "e2e": {"value": rate, "unit": "slides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from importlib import import_module
+    import warnings
+    warnings.filterwarnings("ignore")
+
+    pkg = "multimodal-path-omic_b200."
+    synth = import_module(pkg + "synth")
+    sp = import_module(pkg + "slidepath")
+    bpm = import_module(pkg + "bagpass")
+    lib = import_module(pkg + "_lib")
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    if args.model == "mcat":
+        cls = import_module(pkg + "mcat").MultimodalCoAttentionTransformer
+    else:
+        cls = import_module(pkg + "nacagat").NarrowContextualAttentionGateTransformer
+    torch.manual_seed(0)
+    net = cls(omic_sizes=list(synth.OMIC_SIZES)).to(dev)
+    net.train()
+    B, N = args.batch, args.patches
+    trainer = sp.BatchTrainer(net, loss="nll", grad_acc_step=B * world)
+    opt = torch.optim.Adam(net.parameters(), lr=2e-4, weight_decay=1e-5, fused=True)   # reference: mcat/main.py:298
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    lengths = (N,) * B
+    x = torch.empty((B * N, 1024), dtype=torch.bfloat16, device=dev)
+    for b in range(B):      # chunked: avoids a 4 GB fp32 temporary
+        x[b * N:(b + 1) * N] = torch.randn((N, 1024), generator=gen, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    bag = bpm.PackedBag(x, lengths)
+    omics = [torch.randn((B, d), generator=gen, device=dev) for d in synth.OMIC_SIZES]
+    labels = torch.randint(0, 4, (B,), generator=gen, device=dev, dtype=torch.int64)
+    censor = torch.randint(0, 2, (B,), generator=gen, device=dev).to(torch.float32)
+
+    def one_step():
+        loss, _, _ = trainer.step(bag, omics, labels, censor, train=True)
+        if world > 1:
+            dist.all_reduce(trainer.flat_grad)          # one NCCL all-reduce of the flat fp32 gradient per step
+        opt.step()
+        trainer.zero_grad()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        one_step()
+    barrier()
+    lib.lib().mpo_launch_count(1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = int(lib.lib().mpo_launch_count(0))
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- per-stage device times and the roofline of the dominant kernel (rank 0, separate pass)
+    stages, roof = {}, None
+    if rank == 0:
+        eng = trainer.engine
+        st = eng.forward(trainer.model, bag, omics, train=True, save_for_backward=True, reuse_ws=True)
+        dpooled = torch.randn((B, 6, 256), device=dev) * 1e-3
+        gw = torch.zeros((256, 1024), device=dev)
+        gb = torch.zeros(256, device=dev)
+        P = dict(net.named_parameters())
+
+        def t_stage(fn, reps=5):
+            fn(); torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b_.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b_) / reps
+
+        stages["bag_fwd_ms"] = t_stage(lambda: bpm.bag_forward(bag, eng._w_bf16, P["H.0.bias"].detach(), st.qk, st.bag_ws,
+                                                              seed=1, drop_p=st.drop_p))
+        stages["bag_bwd_ms"] = t_stage(lambda: bpm.bag_backward(bag, st.bag_ws, dpooled, st.qk, gw, gb, drop_p=st.drop_p))
+        stages["step_ms"] = ms / args.steps
+        stages["tail_and_rest_ms"] = max(0.0, stages["step_ms"] - stages["bag_fwd_ms"] - stages["bag_bwd_ms"])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        algo_bytes = B * N * ALGO_BYTES_PER_PATCH_PASS
+        dom = "bag_fwd" if stages["bag_fwd_ms"] >= stages["bag_bwd_ms"] else "bag_bwd"
+        dom_ms = stages[dom + "_ms"]
+        ach = algo_bytes / (dom_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom + ("_kernel (tcgen05 projection + fused co-attention)" if dom == "bag_fwd"
+                                                   else " (dz stream + tcgen05 dW_H GEMM)"),
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                "whole_step_achieved": 2 * algo_bytes / (stages["step_ms"] * 1e-3) / 1e9,
+                "whole_step_frac": 2 * algo_bytes / (stages["step_ms"] * 1e-3) / 1e9 / peak}
+
+    # ---- end to end: host-resident pinned bags, H2D inside the timed region, loss read back every step
+    e2e = None
+    if not args.no_e2e:
+        nset = 2
+        host_x = [torch.empty((B * N, 1024), dtype=torch.bfloat16).pin_memory() for _ in range(nset)]
+        for hx in host_x:
+            hx.copy_(x.cpu())
+        host_om = [[o.cpu().pin_memory() for o in omics] for _ in range(nset)]
+        host_lab = labels.cpu().pin_memory(); host_cen = censor.cpu().pin_memory()
+        dev_x = [torch.empty_like(x) for _ in range(2)]
+        dev_bags = [bpm.PackedBag(dx, lengths) for dx in dev_x]
+        copy_stream = torch.cuda.Stream(device=dev)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        loss_host = torch.empty(B, dtype=torch.float32).pin_memory()
+
+        def stage_in(k):
+            slot = k % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[slot])
+                dev_x[slot].copy_(host_x[k % nset], non_blocking=True)
+                om = [h.to(dev, non_blocking=True) for h in host_om[k % nset]]
+                lab = host_lab.to(dev, non_blocking=True); cen = host_cen.to(dev, non_blocking=True)
+                ready[slot].record(copy_stream)
+            return om, lab, cen
+
+        def e2e_loop(k_steps):
+            nxt = stage_in(0)
+            for k in range(k_steps):
+                slot = k % 2
+                om, lab, cen = nxt
+                if k + 1 < k_steps:
+                    nxt = stage_in(k + 1)
+                torch.cuda.current_stream().wait_event(ready[slot])
+                loss, _, _ = trainer.step(dev_bags[slot], om, lab, cen, train=True)
+                freed[slot].record(torch.cuda.current_stream())
+                if world > 1:
+                    dist.all_reduce(trainer.flat_grad)
+                opt.step(); trainer.zero_grad()
+                loss_host.copy_(loss, non_blocking=True)
+                torch.cuda.current_stream().synchronize()      # the caller reads the loss every step (main.py:49)
+
+        for f in freed:
+            f.record(torch.cuda.current_stream())
+        e2e_steps = max(2, min(args.steps, 6))
+        e2e_loop(2)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(e2e_steps)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = B * N * 1024 * 2 + sum(B * d * 4 for d in synth.OMIC_SIZES) + B * 8 + B * 4
+        e2e = {"value": world * B * e2e_steps / float(dt.item()), "unit": "slides/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": B * 4, "steps": e2e_steps,
+               "note": "pinned host bf16 bags, double-buffered H2D on a copy stream, loss read back every step"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, n, med = cpu_reference_rate(args.model, N, budget_s=12.0)
+        cpu = {"value": rate, "unit": "slides/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{n} x 1 slide of {N} patches fwd+bwd, oracle port in fp32 numpy, all BLAS threads"}
+
+    if rank == 0:
+        line = {
+            "metric": "slides/sec (fwd+bwd, 16k patches)", "value": value, "unit": "slides/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.model}_train_step_{N}_patches", "slides_per_gpu_per_step": B,
+                       "global_slides_per_step": B * world, "patches_per_slide": N, "features": 1024,
+                       "parallelism": f"dp{world}", "mode": "train (dropout on the bag embedding), NLL loss, Adam step per "
+                       "batch, one fp32 gradient all-reduce per step when N>1",
+                       "l2": f"each step streams {B * N * 2048 / 1e9:.2f} GB of bag per GPU (> 126 MB L2), no flush needed"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "stages": stages,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run on this node
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)]
+        cmd += sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,8 @@ extern "C" {
 
 const char* mpo_last_error(void);
 int mpo_version(void);
+/* number of CUDA kernels this library has launched since the last reset (bench.py's gpu_launches) */
+int64_t mpo_launch_count(int32_t reset);
 
 /* Packed bag: the bf16 patch features of all slides of a batch, slide after slide, no padding rows.
  * tile_info[t] = {slide, first packed row, valid rows (1..128), tile index within the slide};
@@ -59,7 +61,8 @@ int mpo_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
  *   part_pool fp32 [num_tiles][6][256]   workspace
  *   pooled    fp32 [num_slides][6][256]  sum_n a_in h_n
  *   lse       fp32 [num_slides][6]       log-sum-exp of the scores of each query
- *   h_saved   bf16 [total_rows][256] or NULL (inference): activations kept for mpo_bag_bwd
+ *   h_saved   fp16 [total_rows][256] or NULL (inference): activations kept for mpo_bag_bwd (fp16, not bf16:
+ *             11 mantissa bits keep the pooled vectors of small bags inside the 1e-3 parity gate)
  *   drop_p    dropout probability on H in train mode (0 = eval); seed selects the mask stream */
 int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, const float* qk, float* scores,
                 float* part_ml, float* part_pool, float* pooled, float* lse, void* h_saved, uint32_t seed,

@@ -116,7 +116,7 @@ SIGNATURES = {
     "mpo_tail_pre_bwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],
 }
 # functions with a non-int return type
-OTHER_EXPORTS = ["mpo_tail_ws_floats", "mpo_tail_ws_lookup", "mpo_sizeof"]
+OTHER_EXPORTS = ["mpo_tail_ws_floats", "mpo_tail_ws_lookup", "mpo_sizeof", "mpo_launch_count"]
 
 
 def _declare(L):
@@ -126,6 +126,8 @@ def _declare(L):
         fn.argtypes = argtypes
     L.mpo_tail_ws_floats.restype = c_i64
     L.mpo_tail_ws_floats.argtypes = [ctypes.POINTER(MpoModel), c_i32]
+    L.mpo_launch_count.restype = c_i64
+    L.mpo_launch_count.argtypes = [c_i32]
     L.mpo_sizeof.restype = c_i64
     L.mpo_sizeof.argtypes = [c_i32]
     for which, st in enumerate((MpoBag, MpoModel, MpoTailIo)):

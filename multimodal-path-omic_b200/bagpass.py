@@ -126,7 +126,7 @@ class BagWorkspace:
         self.part_pool = torch.empty((T, Q, D), **f32)
         self.pooled = torch.empty((B, Q, D), **f32)
         self.lse = torch.empty((B, Q), **f32)
-        self.h_saved = torch.empty((R, D), dtype=torch.bfloat16, device=dev) if save_h else None
+        self.h_saved = torch.empty((R, D), dtype=torch.float16, device=dev) if save_h else None
         self.dz = None
         self.part_dqk = None
         self.part_db = None

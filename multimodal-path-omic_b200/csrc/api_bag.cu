@@ -10,6 +10,7 @@
 namespace mpo {
 
 thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 int fail(int code, const char* fmt, const char* detail) {
   snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -119,6 +120,11 @@ extern "C" {
 
 const char* mpo_last_error(void) { return g_err; }
 int mpo_version(void) { return 100; }
+int64_t mpo_launch_count(int32_t reset) {
+  const int64_t n = static_cast<int64_t>(g_launches);
+  if (reset) g_launches = 0;
+  return n;
+}
 
 int mpo_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
   if (n < 0 || (n > 0 && (!src || !dst))) return fail(MPO_E_ARG, "%s", "mpo_cast_bf16: null pointer");
@@ -128,6 +134,7 @@ int mpo_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
   const int64_t blocks = (groups + threads - 1) / threads;
   cast_bf16_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
       src, static_cast<__nv_bfloat16*>(dst), n);
+  count_launch();
   return check_cuda(cudaGetLastError(), "mpo_cast_bf16");
 }
 
@@ -164,7 +171,7 @@ int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, c
   p.scores = scores;
   p.part_ml = part_ml;
   p.part_pool = part_pool;
-  p.h_out = static_cast<__nv_bfloat16*>(h_saved);
+  p.h_out = static_cast<__half*>(h_saved);
   p.seed = seed;
   p.drop_thr = static_cast<uint32_t>(drop_p * 256.f + 0.5f);
   p.drop_scale = p.drop_thr ? 256.f / static_cast<float>(256 - p.drop_thr) : 1.f;
@@ -182,6 +189,7 @@ int mpo_attn_map(const mpo_bag* bag, const float* scores, const float* lse, floa
   if (!scores || !lse || !amap) return fail(MPO_E_ARG, "%s", "mpo_attn_map: null pointer");
   attn_map_kernel<<<bag->num_tiles, kTileM, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const TileInfo*>(bag->tile_info), scores, lse, amap, static_cast<int>(bag->total_rows));
+  count_launch();
   return check_cuda(cudaGetLastError(), "attn_map_kernel");
 }
 
@@ -199,7 +207,7 @@ int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, co
   p.tile_info = reinterpret_cast<const TileInfo*>(bag->tile_info);
   p.num_tiles = bag->num_tiles;
   p.total_rows = static_cast<int>(bag->total_rows);
-  p.h = static_cast<const __nv_bfloat16*>(h_saved);
+  p.h = static_cast<const __half*>(h_saved);
   p.scores = scores;
   p.lse = lse;
   p.pooled = pooled;
@@ -230,6 +238,7 @@ int mpo_lse_combine(const float* lse_in, const float* pooled_in, int32_t nshards
   if (nshards <= 0 || !lse_in || !pooled_in || !lse_out || !pooled_out)
     return fail(MPO_E_ARG, "%s", "mpo_lse_combine: bad arguments");
   lse_combine_kernel<<<kQ, kD, 0, static_cast<cudaStream_t>(stream)>>>(lse_in, pooled_in, nshards, lse_out, pooled_out);
+  count_launch();
   return check_cuda(cudaGetLastError(), "lse_combine_kernel");
 }
 

@@ -1,6 +1,6 @@
 // Bag-pass backward for MCAT (autograd of models/mcat/mcat.py:87,97 in the reference).
 //
-//  bag_bwd_dz_kernel  (CUDA cores, streaming): from the saved bf16 activations h_n, the saved raw scores and
+//  bag_bwd_dz_kernel  (CUDA cores, streaming): from the saved fp16 activations h_n, the saved raw scores and
 //      the upstream gradient dPooled[6,256] it forms, per patch,
 //          a_in  = exp(s_in - lse_i)
 //          ds_in = a_in (dPooled_i . h_n - delta_i),      delta_i = dPooled_i . pooled_i
@@ -12,6 +12,7 @@
 //      fp32 accumulators in TMEM, reduced into the gradient buffer with red.global.add.
 #include "mpo_ptx.cuh"
 #include "mpo_common.cuh"
+#include "launchers.h"
 
 namespace mpo {
 
@@ -21,7 +22,6 @@ constexpr int kDzSmemBytes = kDzWarps * 7 * kD * 4;   // cross-warp reduction bu
 
 __global__ void __launch_bounds__(kDzWarps * 32, 1) bag_bwd_dz_kernel(const BagBwdDzParams p) {
   extern __shared__ float red[];   // [8 warps][7][256]
-  __shared__ float delta_s[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x;
   const TileInfo ti = p.tile_info[t];
@@ -70,10 +70,8 @@ __global__ void __launch_bounds__(kDzWarps * 32, 1) bag_bwd_dz_kernel(const BagB
     const size_t grow = static_cast<size_t>(ti.row0 + n);
     const uint4 hv = *reinterpret_cast<const uint4*>(p.h + grow * kD + lane * 8);
     float h[8];
-    h[0] = bf16lo_to_f32(hv.x); h[1] = bf16hi_to_f32(hv.x);
-    h[2] = bf16lo_to_f32(hv.y); h[3] = bf16hi_to_f32(hv.y);
-    h[4] = bf16lo_to_f32(hv.z); h[5] = bf16hi_to_f32(hv.z);
-    h[6] = bf16lo_to_f32(hv.w); h[7] = bf16hi_to_f32(hv.w);
+    { const float2 t0 = unpack_f16x2(hv.x), t1 = unpack_f16x2(hv.y), t2 = unpack_f16x2(hv.z), t3 = unpack_f16x2(hv.w);
+      h[0] = t0.x; h[1] = t0.y; h[2] = t1.x; h[3] = t1.y; h[4] = t2.x; h[5] = t2.y; h[6] = t3.x; h[7] = t3.y; }
     float a[kQ], ds[kQ];
 #pragma unroll
     for (int i = 0; i < kQ; ++i) {
@@ -115,7 +113,6 @@ __global__ void __launch_bounds__(kDzWarps * 32, 1) bag_bwd_dz_kernel(const BagB
   }
   *reinterpret_cast<float4*>(mine + 6 * kD + lane * 8) = make_float4(db[0], db[1], db[2], db[3]);
   *reinterpret_cast<float4*>(mine + 6 * kD + lane * 8 + 4) = make_float4(db[4], db[5], db[6], db[7]);
-  (void)delta_s;
   __syncthreads();
   for (int e = threadIdx.x; e < 7 * kD; e += blockDim.x) {
     float v = 0.f;
@@ -268,6 +265,7 @@ cudaError_t launch_bag_bwd_dz(const BagBwdDzParams& prm, cudaStream_t stream) {
   }
   if (prm.num_tiles <= 0) return cudaSuccess;
   bag_bwd_dz_kernel<<<prm.num_tiles, kDzWarps * 32, kDzSmemBytes, stream>>>(prm);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -275,6 +273,7 @@ cudaError_t launch_bag_bwd_reduce(const int* tile_prefix, const float* part_dqk,
                                   float* grad_bias, int B, int num_tiles, cudaStream_t stream) {
   bag_bwd_reduce_kernel<<<dim3(B + 1, kQ), 256, 0, stream>>>(tile_prefix, part_dqk, part_db, dqk, grad_bias, B,
                                                             num_tiles);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -292,6 +291,7 @@ cudaError_t launch_bag_bwd_dw(const CUtensorMap& tm_dz, const CUtensorMap& tm_x,
   if (splits > chunks) splits = chunks;
   if (splits < 1) splits = 1;
   bag_bwd_dw_kernel<<<4 * splits, kDwThreads, kDwSmemBytes, stream>>>(tm_dz, tm_x, grad_w, total_rows, splits);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -4,7 +4,7 @@
 //   TMA (warp 0)  : X tile [128 x 1024] and W_H [256 x 1024] in 64-wide K blocks, 128B-swizzled, 3-stage ring
 //   MMA (warp 1)  : tcgen05.mma M=128 N=256 K=16, fp32 accumulators in TMEM, two accumulator stages
 //   epilogue (8 w): TMEM -> registers; +bias, ReLU, (dropout); six folded-query dots per patch (fp32);
-//                   H tile staged once in shared memory as bf16; tile-local softmax statistics;
+//                   H tile staged once in shared memory as fp16; tile-local softmax statistics;
 //                   pooled[6,256] += p^T H from the staged tile; per-tile (m, l, pooled) partial written.
 // The K/V projections of the reference's nn.MultiheadAttention are folded away exactly:
 //   score_in = h_n . (W_k^T q_i)/sqrt(d)   (the b_k term is constant over n and cancels in the softmax)
@@ -12,6 +12,7 @@
 // A second kernel merges the per-tile partials by log-sum-exp per slide.
 #include "mpo_ptx.cuh"
 #include "mpo_common.cuh"
+#include "launchers.h"
 
 namespace mpo {
 
@@ -19,7 +20,7 @@ constexpr int kStages = 3;
 constexpr int kABytes = kTileM * kBK * 2;            // 16 KB
 constexpr int kBBytes = kD * kBK * 2;                // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;       // 48 KB
-constexpr int kStagingBytes = kTileM * kD * 2;       // 64 KB  bf16 H tile, K-major SW128 (4 blocks of 128x64)
+constexpr int kStagingBytes = kTileM * kD * 2;       // 64 KB  fp16 H tile, K-major SW128 (4 blocks of 128x64)
 constexpr int kEpiThreads = 256;
 constexpr int kFwdThreads = 64 + kEpiThreads;
 
@@ -159,7 +160,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
 
-      // ---- phase 1: accumulator -> h (fp32) -> score partials, bf16 tile in shared memory
+      // ---- phase 1: accumulator -> h (fp32) -> score partials, fp16 tile in shared memory
       float s[kQ];
 #pragma unroll
       for (int i = 0; i < kQ; ++i) s[i] = 0.f;
@@ -210,10 +211,10 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             s[i] = fmaf(h[7], q1.w, s[i]);
           }
           uint4 pk;
-          pk.x = pack_bf16x2(h[0], h[1]);
-          pk.y = pack_bf16x2(h[2], h[3]);
-          pk.z = pack_bf16x2(h[4], h[5]);
-          pk.w = pack_bf16x2(h[6], h[7]);
+          pk.x = pack_f16x2(h[0], h[1]);
+          pk.y = pack_f16x2(h[2], h[3]);
+          pk.z = pack_f16x2(h[4], h[5]);
+          pk.w = pack_f16x2(h[6], h[7]);
           const int j16 = (col0 + j) >> 3;           // 16-byte chunk index within the 512 B row
           const int cb = j16 >> 3, jj = j16 & 7;     // 64-feature block, chunk within the 128 B swizzle row
           *reinterpret_cast<uint4*>(staging + cb * (kTileM * 128) + r * 128 + ((jj ^ (r & 7)) << 4)) = pk;
@@ -268,7 +269,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             wsum_s[et] + wsum_s[8 + et] + wsum_s[16 + et] + wsum_s[24 + et];
       }
 
-      // ---- phase 2: pooled[i][d] += sum_n p[n][i] * h[n][d] from the staged bf16 tile
+      // ---- phase 2: pooled[i][d] += sum_n p[n][i] * h[n][d] from the staged fp16 tile
       const int fg = et & 63;    // four features 4fg..4fg+3
       const int pg = et >> 6;    // 32 patch rows pg*32..pg*32+31
       float acc[kQ][4];
@@ -277,15 +278,15 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       {
         const int j16 = fg >> 1, cb = j16 >> 3, jj = j16 & 7;
         const uint8_t* colbase = staging + cb * (kTileM * 128) + (fg & 1) * 8;
-        __nv_bfloat16* hout = p.h_out;
+        __half* hout = p.h_out;
 #pragma unroll 4
         for (int nn = 0; nn < 32; ++nn) {
           const int n = pg * 32 + nn;
           const uint2 hv = *reinterpret_cast<const uint2*>(colbase + n * 128 + ((jj ^ (n & 7)) << 4));
           const float4 p0 = *reinterpret_cast<const float4*>(P_s + n * 8);
           const float2 p1 = *reinterpret_cast<const float2*>(P_s + n * 8 + 4);
-          const float h0 = bf16lo_to_f32(hv.x), h1 = bf16hi_to_f32(hv.x);
-          const float h2 = bf16lo_to_f32(hv.y), h3 = bf16hi_to_f32(hv.y);
+          const float2 h01 = unpack_f16x2(hv.x), h23 = unpack_f16x2(hv.y);
+          const float h0 = h01.x, h1 = h01.y, h2 = h23.x, h3 = h23.y;
           const float pw[kQ] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y};
 #pragma unroll
           for (int i = 0; i < kQ; ++i) {
@@ -360,6 +361,7 @@ cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, con
   if (prm.num_tiles <= 0) return cudaSuccess;
   const int grid = prm.num_tiles < num_sms ? prm.num_tiles : num_sms;
   bag_fwd_kernel<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(tm_x, tm_w, prm);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -367,6 +369,7 @@ cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, const
                              float* lse, int B, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
   bag_merge_kernel<<<dim3(B, kQ), 256, 0, stream>>>(tile_prefix, part_ml, part_pool, pooled, lse);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -10,6 +10,8 @@ extern thread_local char g_err[512];
 int fail(int code, const char* fmt, const char* detail);
 int check_cuda(cudaError_t e, const char* where);
 int num_sms();
+extern unsigned long long g_launches;   // kernels launched by this library since the last reset
+inline void count_launch(int n = 1) { g_launches += n; }
 
 cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const BagFwdParams& prm, int num_sms,
                            cudaStream_t stream);

@@ -3,6 +3,7 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace mpo {
 
@@ -30,7 +31,7 @@ struct BagFwdParams {
   float* scores;               // [6][total_rows]             raw scores (pre-softmax)
   float* part_ml;              // [num_tiles][12]             tile max (6) and tile sum of exp (6)
   float* part_pool;            // [num_tiles][6][256]         sum_n exp(s - m_tile) h_n
-  __nv_bfloat16* h_out;        // [total_rows][256] or null   saved activations for the backward pass
+  __half* h_out;               // [total_rows][256] or null   saved activations (fp16) for the backward pass
   uint32_t seed;               // dropout stream (train mode)
   uint32_t drop_thr;           // drop an element when its 8 random bits < drop_thr (0 = eval)
   float drop_scale;            // 1 / keep probability
@@ -40,7 +41,7 @@ struct BagBwdDzParams {
   const TileInfo* tile_info;
   int num_tiles;
   int total_rows;
-  const __nv_bfloat16* h;      // [total_rows][256] saved by the forward pass
+  const __half* h;             // [total_rows][256] fp16, saved by the forward pass
   const float* scores;         // [6][total_rows]
   const float* lse;            // [B][6]
   const float* pooled;         // [B][6][256]

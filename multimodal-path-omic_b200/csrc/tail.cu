@@ -140,37 +140,37 @@ void lin_bwd(Ctx& c, const float* dz, long long lddz, const float* x, long long 
     c.chk(launch_gemm(g, c.st), "lin_bwd.wgrad");
   }
   if (L.gb != nullptr) {
-    colsum_kernel<<<nblk(out, 128), 128, 0, c.st>>>(dz, lddz, nullptr, 0, L.gb, rows, out);
+    colsum_kernel<<<nblk(out, 128), 128, 0, c.st>>>(dz, lddz, nullptr, 0, L.gb, rows, out); count_launch();
     c.chk(cudaGetLastError(), "lin_bwd.bgrad");
   }
 }
 void act_bwd(Ctx& c, const float* dy, long long lddy, const float* y, long long ldy, float* dz, long long lddz, int rows,
              int cols, int act) {
-  act_bwd_kernel<<<nblk((long long)rows * cols), 256, 0, c.st>>>(dy, lddy, y, ldy, dz, lddz, rows, cols, act);
+  act_bwd_kernel<<<nblk((long long)rows * cols), 256, 0, c.st>>>(dy, lddy, y, ldy, dz, lddz, rows, cols, act); count_launch();
   c.chk(cudaGetLastError(), "act_bwd");
 }
 void add(Ctx& c, const float* a, const float* b, float* out, long long n) {
-  add_kernel<<<nblk(n), 256, 0, c.st>>>(a, b, out, n);
+  add_kernel<<<nblk(n), 256, 0, c.st>>>(a, b, out, n); count_launch();
   c.chk(cudaGetLastError(), "add");
 }
 void mul(Ctx& c, const float* a, const float* b, float* out, long long n) {
-  mul_kernel<<<nblk(n), 256, 0, c.st>>>(a, b, out, n);
+  mul_kernel<<<nblk(n), 256, 0, c.st>>>(a, b, out, n); count_launch();
   c.chk(cudaGetLastError(), "mul");
 }
 void act(Ctx& c, const float* x, float* y, long long n, int a) {
-  act_kernel<<<nblk(n), 256, 0, c.st>>>(x, y, n, a);
+  act_kernel<<<nblk(n), 256, 0, c.st>>>(x, y, n, a); count_launch();
   c.chk(cudaGetLastError(), "act");
 }
 void ln_fwd(Ctx& c, const float* a, const float* b, const mpo_norm& N, float* y, float* xh, float* rs, int rows) {
-  layernorm_fwd_kernel<<<nblk(rows, 8), 256, 0, c.st>>>(a, b, N.g, N.b, y, xh, rs, rows);
+  layernorm_fwd_kernel<<<nblk(rows, 8), 256, 0, c.st>>>(a, b, N.g, N.b, y, xh, rs, rows); count_launch();
   c.chk(cudaGetLastError(), "ln_fwd");
 }
 void ln_bwd(Ctx& c, const float* dy, const mpo_norm& N, const float* xh, const float* rs, float* dx, int rows) {
-  layernorm_bwd_kernel<<<nblk(rows, 8), 256, 0, c.st>>>(dy, N.g, xh, rs, dx, rows);
+  layernorm_bwd_kernel<<<nblk(rows, 8), 256, 0, c.st>>>(dy, N.g, xh, rs, dx, rows); count_launch();
   c.chk(cudaGetLastError(), "ln_bwd");
   if (N.gg != nullptr) {
-    colsum_kernel<<<nblk(E, 128), 128, 0, c.st>>>(dy, E, xh, E, N.gg, rows, E);
-    colsum_kernel<<<nblk(E, 128), 128, 0, c.st>>>(dy, E, nullptr, 0, N.gb, rows, E);
+    colsum_kernel<<<nblk(E, 128), 128, 0, c.st>>>(dy, E, xh, E, N.gg, rows, E); count_launch();
+    colsum_kernel<<<nblk(E, 128), 128, 0, c.st>>>(dy, E, nullptr, 0, N.gb, rows, E); count_launch();
     c.chk(cudaGetLastError(), "ln_bwd.params");
   }
 }
@@ -180,7 +180,7 @@ void ln_bwd(Ctx& c, const float* dy, const mpo_norm& N, const float* xh, const f
 void enc_fwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, float* ws, const float* x, int B) {
   const int R = 6 * B;
   lin_fwd(c, x, E, P.in_proj, 3 * E, E, ws + b.qkv, 3 * E, R, ACT_NONE);
-  mha6_fwd_kernel<<<nblk((long long)B * 8, 8), 256, 0, c.st>>>(ws + b.qkv, ws + b.probs, ws + b.ctx, B);
+  mha6_fwd_kernel<<<nblk((long long)B * 8, 8), 256, 0, c.st>>>(ws + b.qkv, ws + b.probs, ws + b.ctx, B); count_launch();
   c.chk(cudaGetLastError(), "mha6_fwd");
   lin_fwd(c, ws + b.ctx, E, P.out_proj, E, E, ws + b.sa, E, R, ACT_NONE);
   ln_fwd(c, x, ws + b.sa, P.norm1, ws + b.y1, ws + b.xh1, ws + b.rs1, R);
@@ -209,7 +209,7 @@ void enc_bwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, const Ws& w, f
   float* dctx = ws + w.s256b;
   lin_bwd(c, dr1, E, ws + b.ctx, E, P.out_proj, E, E, dctx, E, R, false);
   float* dqkv = ws + w.s768;
-  mha6_bwd_kernel<<<nblk((long long)B * 8, 8), 256, 0, c.st>>>(ws + b.qkv, ws + b.probs, dctx, dqkv, B);
+  mha6_bwd_kernel<<<nblk((long long)B * 8, 8), 256, 0, c.st>>>(ws + b.qkv, ws + b.probs, dctx, dqkv, B); count_launch();
   c.chk(cudaGetLastError(), "mha6_bwd");
   lin_bwd(c, dqkv, 3 * E, x, E, P.in_proj, 3 * E, E, dx_out, E, R, false);
   add(c, dx_out, dr1, dx_out, (long long)R * E);
@@ -221,7 +221,7 @@ void pool_fwd(Ctx& c, const mpo_pool_head& P, const PoolBuf& b, float* ws, const
   const int R = 6 * B;
   lin_fwd(c, x, E, P.att_a, E, E, ws + b.a, E, R, ACT_TANH);
   lin_fwd(c, x, E, P.att_b, E, E, ws + b.b, E, R, ACT_SIGMOID);
-  pool_fwd_kernel<<<B, 256, 0, c.st>>>(x, ws + b.a, ws + b.b, P.att_c.w, P.att_c.b, att_logits, ws + b.w, ws + b.hp);
+  pool_fwd_kernel<<<B, 256, 0, c.st>>>(x, ws + b.a, ws + b.b, P.att_c.w, P.att_c.b, att_logits, ws + b.w, ws + b.hp); count_launch();
   c.chk(cudaGetLastError(), "pool_fwd");
   lin_fwd(c, ws + b.hp, E, P.rho, E, E, ws + b.h, E, B, ACT_RELU);
 }
@@ -233,7 +233,7 @@ void pool_bwd(Ctx& c, const mpo_pool_head& P, const PoolBuf& b, const Ws& w, flo
   act_bwd(c, dh, E, ws + b.h, E, dzr, E, B, E, ACT_RELU);
   lin_bwd(c, dzr, E, ws + b.hp, E, P.rho, E, E, dhp, E, B, false);
   pool_bwd_kernel<<<B, 256, 0, c.st>>>(x, ws + b.a, ws + b.b, P.att_c.w, ws + b.w, dhp, dx_out, ws + w.dxa, ws + w.dxb,
-                                       P.att_c.gw, P.att_c.gb);
+                                       P.att_c.gw, P.att_c.gb); count_launch();
   c.chk(cudaGetLastError(), "pool_bwd");
   lin_bwd(c, ws + w.dxa, E, x, E, P.att_a, E, E, dx_out, E, R, true);
   lin_bwd(c, ws + w.dxb, E, x, E, P.att_b, E, E, dx_out, E, R, true);
@@ -282,7 +282,7 @@ void bil_side_fwd(Ctx& c, const mpo_lin& Lh, const mpo_lin& Lz, const mpo_lin& L
   // U[b][k*256+i] = sum_j W[k][i][j] xb[b][j]
   GemmArgs g{xb, E, 1, Lz.w, 1, E, ws + w.bU[s], (long long)BH * E, nullptr, B, BH * E, E, 1.f, 0, ACT_NONE};
   c.chk(launch_gemm(g, c.st), "bil.U");
-  bil_gate_fwd_kernel<<<B, 256, 0, c.st>>>(xa, ws + w.bU[s], Lz.b, ws + w.bh[s], ws + w.bg[s], ws + w.bgh[s]);
+  bil_gate_fwd_kernel<<<B, 256, 0, c.st>>>(xa, ws + w.bU[s], Lz.b, ws + w.bh[s], ws + w.bg[s], ws + w.bgh[s]); count_launch();
   c.chk(cudaGetLastError(), "bil_gate_fwd");
   lin_fwd(c, ws + w.bgh[s], BH, Lo, BH, BH, ws + w.bo[s], BH, B, ACT_RELU);
 }
@@ -293,13 +293,13 @@ void bil_side_bwd(Ctx& c, const mpo_lin& Lh, const mpo_lin& Lz, const mpo_lin& L
   act_bwd(c, dpre, BH, ws + w.bo[s], BH, dpre, BH, B, BH, ACT_RELU);
   lin_bwd(c, dpre, BH, ws + w.bgh[s], BH, Lo, BH, BH, ws + w.bdgh[s], BH, B, false);
   bil_gate_bwd_kernel<<<B, 256, 0, c.st>>>(xa, ws + w.bU[s], ws + w.bh[s], ws + w.bg[s], ws + w.bdgh[s], ws + w.bdh[s],
-                                           ws + w.bdz[s], ws + w.bV, dxa, acc_a ? 1 : 0);
+                                           ws + w.bdz[s], ws + w.bV, dxa, acc_a ? 1 : 0); count_launch();
   c.chk(cudaGetLastError(), "bil_gate_bwd");
   // dW[(k,i)][j] += sum_b V[b][(k,i)] xb[b][j] ;  dxb[b][j] += sum_(k,i) V[b][(k,i)] W[(k,i)][j] ; db += colsum(dz)
   if (Lz.gw != nullptr) {
     GemmArgs g{ws + w.bV, 1, (long long)BH * E, xb, E, 1, Lz.gw, E, nullptr, BH * E, E, B, 1.f, 1, ACT_NONE};
     c.chk(launch_gemm(g, c.st), "bil.dW");
-    colsum_kernel<<<1, 128, 0, c.st>>>(ws + w.bdz[s], BH, nullptr, 0, Lz.gb, B, BH);
+    colsum_kernel<<<1, 128, 0, c.st>>>(ws + w.bdz[s], BH, nullptr, 0, Lz.gb, B, BH); count_launch();
   }
   GemmArgs g2{ws + w.bV, (long long)BH * E, 1, Lz.w, E, 1, dxb, E, nullptr, B, E, BH * E, 1.f, 1, ACT_NONE};
   c.chk(launch_gemm(g2, c.st), "bil.dxb");
@@ -425,14 +425,14 @@ int mpo_tail_post_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   } else {                                          // fusion.py:81-113
     bil_side_fwd(c, m->bil.h1, m->bil.z1, m->bil.o1, w, ws, 0, hpath, homic, B);
     bil_side_fwd(c, m->bil.h2, m->bil.z2, m->bil.o2, w, ws, 1, homic, hpath, B);
-    bil_kron_fwd_kernel<<<B, 256, 0, c.st>>>(ws + w.bo[0], ws + w.bo[1], ws + w.kp, ws + w.cat130);
+    bil_kron_fwd_kernel<<<B, 256, 0, c.st>>>(ws + w.bo[0], ws + w.bo[1], ws + w.kp, ws + w.cat130); count_launch();
     c.chk(cudaGetLastError(), "bil_kron_fwd");
     lin_fwd(c, ws + w.kp, 1089, m->bil.fc1, BMM, 1089, ws + w.cat130, 130, B, ACT_RELU);
     lin_fwd(c, ws + w.cat130, 130, m->bil.fc2, E, 130, ws + w.bf2, E, B, ACT_RELU);
     hfin = ws + w.bf2;
   }
   lin_fwd(c, hfin, E, m->classifier, K, E, ws + w.logits, K, B, ACT_NONE);
-  surv_head_fwd_kernel<<<nblk(B, 128), 128, 0, c.st>>>(ws + w.logits, io->hazards, io->S, io->Y, B, K);
+  surv_head_fwd_kernel<<<nblk(B, 128), 128, 0, c.st>>>(ws + w.logits, io->hazards, io->S, io->Y, B, K); count_launch();
   c.chk(cudaGetLastError(), "surv_head_fwd");
   return finish(c);
 }
@@ -446,7 +446,7 @@ int mpo_surv_loss(int32_t kind, const float* hazards, const float* S, const int6
   if (num_sms() <= 0) return fail(MPO_E_CUDA, "%s", "mpo_surv_loss: no CUDA device (this library has no CPU fallback)");
   surv_loss_kernel<<<nblk(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(kind, hazards, S, label, censor, alpha,
                                                                                eps, grad_scale, loss, dhaz, dS, B,
-                                                                               n_classes);
+                                                                               n_classes); count_launch();
   return check_cuda(cudaGetLastError(), "surv_loss_kernel");
 }
 
@@ -460,7 +460,7 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
   Ws w; build_layout(m, B, w);
   float* ws = io->ws;
   Ctx c{static_cast<cudaStream_t>(stream)};
-  surv_head_bwd_kernel<<<nblk(B, 128), 128, 0, c.st>>>(io->hazards, io->S, io->Y, dhaz, dS, dY, ws + w.dlogits, B, K);
+  surv_head_bwd_kernel<<<nblk(B, 128), 128, 0, c.st>>>(io->hazards, io->S, io->Y, dhaz, dS, dY, ws + w.dlogits, B, K); count_launch();
   c.chk(cudaGetLastError(), "surv_head_bwd");
   const float* hpath = ws + w.pool[0].h;
   const float* homic = ws + w.pool[1].h;
@@ -483,7 +483,7 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
     act_bwd(c, ws + w.bdcat130, 130, ws + w.cat130, 130, ws + w.dz1, BMM, B, BMM, ACT_RELU);
     lin_bwd(c, ws + w.dz1, BMM, ws + w.kp, 1089, m->bil.fc1, BMM, 1089, ws + w.bdkp, 1089, B, false);
     bil_kron_bwd_kernel<<<B, 64, 0, c.st>>>(ws + w.bo[0], ws + w.bo[1], ws + w.bdkp, ws + w.bdcat130, ws + w.bdo[0],
-                                            ws + w.bdo[1]);
+                                            ws + w.bdo[1]); count_launch();
     c.chk(cudaGetLastError(), "bil_kron_bwd");
     // side 1: xa = h_path, xb = h_omic ; side 2: xa = h_omic, xb = h_path
     cudaMemsetAsync(dhomic, 0, (size_t)B * E * 4, c.st);

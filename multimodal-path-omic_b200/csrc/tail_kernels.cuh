@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdint.h>
 #include "mpo_ptx.cuh"
+#include "launchers.h"
 
 namespace mpo {
 
@@ -111,6 +112,7 @@ inline cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t st) {
   else if (akc && !bnc) gemm_kernel<true, false><<<grid, 256, 0, st>>>(g);
   else if (!akc && bnc) gemm_kernel<false, true><<<grid, 256, 0, st>>>(g);
   else gemm_kernel<false, false><<<grid, 256, 0, st>>>(g);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -277,12 +277,11 @@ class _SlideFn(torch.autograd.Function):
     """One slide through the engine with gradients delivered to nn.Parameter.grad by autograd."""
 
     @staticmethod
-    def forward(ctx, engine, want_map, train, wsi, n_omics, *rest):
+    def forward(ctx, engine, want_map, train, needs_bwd, wsi, n_omics, *rest):
         omics = rest[:n_omics]
         params = rest[n_omics:]
         bnd = engine.binding
         bag = bp.PackedBag.from_slides([wsi.detach()])
-        needs_bwd = any(p.requires_grad for p in params) and torch.is_grad_enabled()
         model = bnd.build(grads=None)
         st = engine.forward(model, bag, [o.detach().reshape(1, -1) for o in omics], train=train,
                             save_for_backward=needs_bwd)
@@ -307,7 +306,7 @@ class _SlideFn(torch.autograd.Function):
             off += p.numel()
         model = bnd.build(grads=grads)
         engine.backward(model, st, dhaz, dS, dY)
-        return (None, None, None, None, None) + (None,) * ctx.n_omics + tuple(grads[n] for n in bnd.names)
+        return (None, None, None, None, None, None) + (None,) * ctx.n_omics + tuple(grads[n] for n in bnd.names)
 
 
 def run_slide(engine, wsi, omics, want_map, train):
@@ -315,7 +314,8 @@ def run_slide(engine, wsi, omics, want_map, train):
     require_cuda(wsi, "wsi")
     bnd = engine.binding
     params = [dict(bnd.module.named_parameters())[n] for n in bnd.names]
-    outs = _SlideFn.apply(engine, bool(want_map), bool(train), wsi, len(omics), *omics, *params)
+    needs_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    outs = _SlideFn.apply(engine, bool(want_map), bool(train), needs_bwd, wsi, len(omics), *omics, *params)
     hazards, S, Y, coattn, a_path, a_omic = outs
     return hazards, S, Y, (coattn if want_map else None), a_path, a_omic
 

@@ -16,8 +16,14 @@ Parameters are passed as a dict  state_dict-key -> numpy array  (same keys as th
 """
 import numpy as np
 
-F64 = np.float64
+F64 = np.float64      # working precision; bench.py's cpu_baseline leg switches it to float32 with use_dtype()
 LN_EPS = 1e-5
+
+
+def use_dtype(dtype):
+    """float64 (default, the checker) or float32 (timing the reference algorithm at the reference's precision)."""
+    global F64
+    F64 = dtype
 
 
 # ------------------------------------------------------------------------------------------------ primitives

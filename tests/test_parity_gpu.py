@@ -44,9 +44,18 @@ def supported(case):
 
 
 def rel_err(got, ref):
+    """element-wise relative error (hazards, survival curves, risk: all O(0.1..1) quantities)."""
     got = np.asarray(got, np.float64)
     ref = np.asarray(ref, np.float64)
     return float(np.max(np.abs(got - ref) / (np.abs(ref) + 1e-9)))
+
+
+def vec_rel_err(got, ref):
+    """error relative to the largest entry of the vector: the pooling logits of attention_scores['path'/'omic']
+    are signed values around zero, so an element-wise ratio is meaningless for the entries that nearly vanish."""
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    return float(np.max(np.abs(got - ref)) / (np.max(np.abs(ref)) + 1e-30))
 
 
 @pytest.mark.parametrize("name", golden_cases())
@@ -66,7 +75,7 @@ def test_forward_backward_matches_reference(name):
     errs = dict(hazards=rel_err(hazards.detach().cpu(), g["hazards"]), S=rel_err(S.detach().cpu(), g["S"]),
                 Y=rel_err(Y.detach().cpu(), g["Y"]),
                 risk=rel_err((-S.sum(dim=1)).detach().cpu(), g["risk"]),
-                path=rel_err(att["path"].cpu(), g["path"]), omic=rel_err(att["omic"].cpu(), g["omic"]))
+                path=vec_rel_err(att["path"].cpu(), g["path"]), omic=vec_rel_err(att["omic"].cpu(), g["omic"]))
     # attention map: relative where the weight matters, absolute floor 1e-6/N-scale for vanishing weights
     A, Aref = att["coattn"].cpu().numpy().astype(np.float64), g["coattn"].astype(np.float64)
     errs["coattn"] = float(np.max(np.abs(A - Aref) / (np.abs(Aref) + 1e-3 * Aref.max())))
