@@ -196,8 +196,10 @@ def run_ours(args, rank, world, local_rank):
     labels = torch.randint(0, 4, (B,), generator=gen, device=dev, dtype=torch.int64)
     censor = torch.randint(0, 2, (B,), generator=gen, device=dev).to(torch.float32)
 
+    graphed = trainer.capture(bag, omics, labels, censor, train=True)   # the whole step replays as one CUDA graph
+
     def one_step():
-        loss, _, _ = trainer.step(bag, omics, labels, censor, train=True)
+        loss, _, _ = graphed.replay()
         if world > 1:
             dist.all_reduce(trainer.flat_grad)          # one NCCL all-reduce of the flat fp32 gradient per step
         opt.step()
@@ -235,7 +237,7 @@ def run_ours(args, rank, world, local_rank):
     stages, roof = {}, None
     if rank == 0:
         eng = trainer.engine
-        st = eng.forward(trainer.model, bag, omics, train=True, save_for_backward=True, reuse_ws=True)
+        st = graphed.state
         dpooled = torch.randn((B, 6, 256), device=dev) * 1e-3
         gw = torch.zeros((256, 1024), device=dev)
         gb = torch.zeros(256, device=dev)
@@ -284,6 +286,10 @@ def run_ours(args, rank, world, local_rank):
         host_lab = labels.cpu().pin_memory(); host_cen = censor.cpu().pin_memory()
         dev_x = [torch.empty_like(x) for _ in range(2)]
         dev_bags = [bpm.PackedBag(dx, lengths) for dx in dev_x]
+        dev_om = [[torch.empty_like(o) for o in omics] for _ in range(2)]
+        dev_lab = [torch.empty_like(labels) for _ in range(2)]
+        dev_cen = [torch.empty_like(censor) for _ in range(2)]
+        steps_g = [trainer.capture(dev_bags[i], dev_om[i], dev_lab[i], dev_cen[i], train=True) for i in range(2)]
         copy_stream = torch.cuda.Stream(device=dev)
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
@@ -294,20 +300,21 @@ def run_ours(args, rank, world, local_rank):
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[slot])
                 dev_x[slot].copy_(host_x[k % nset], non_blocking=True)
-                om = [h.to(dev, non_blocking=True) for h in host_om[k % nset]]
-                lab = host_lab.to(dev, non_blocking=True); cen = host_cen.to(dev, non_blocking=True)
+                for d_, h_ in zip(dev_om[slot], host_om[k % nset]):
+                    d_.copy_(h_, non_blocking=True)
+                dev_lab[slot].copy_(host_lab, non_blocking=True)
+                dev_cen[slot].copy_(host_cen, non_blocking=True)
                 ready[slot].record(copy_stream)
-            return om, lab, cen
+            return None
 
         def e2e_loop(k_steps):
-            nxt = stage_in(0)
+            stage_in(0)
             for k in range(k_steps):
                 slot = k % 2
-                om, lab, cen = nxt
                 if k + 1 < k_steps:
-                    nxt = stage_in(k + 1)
+                    stage_in(k + 1)
                 torch.cuda.current_stream().wait_event(ready[slot])
-                loss, _, _ = trainer.step(dev_bags[slot], om, lab, cen, train=True)
+                loss, _, _ = steps_g[slot].replay()
                 freed[slot].record(torch.cuda.current_stream())
                 if world > 1:
                     dist.all_reduce(trainer.flat_grad)

@@ -63,10 +63,14 @@ int mpo_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
  *   lse       fp32 [num_slides][6]       log-sum-exp of the scores of each query
  *   h_saved   fp16 [total_rows][256] or NULL (inference): activations kept for mpo_bag_bwd (fp16, not bf16:
  *             11 mantissa bits keep the pooled vectors of small bags inside the 1e-3 parity gate)
- *   drop_p    dropout probability on H in train mode (0 = eval); seed selects the mask stream */
+ *   drop_p    dropout probability on H in train mode (0 = eval); seed selects the mask stream; when seed_dev is
+ *             non-NULL the stream id is seed ^ *seed_dev, read on the device (so a captured CUDA graph draws a new
+ *             mask on every replay; advance it with mpo_advance_seed) */
 int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, const float* qk, float* scores,
                 float* part_ml, float* part_pool, float* pooled, float* lse, void* h_saved, uint32_t seed,
-                float drop_p, void* stream);
+                const uint32_t* seed_dev, float drop_p, void* stream);
+/* *seed_dev = hash(*seed_dev + golden ratio): one tiny kernel, stream-ordered (graph-capturable) */
+int mpo_advance_seed(uint32_t* seed_dev, void* stream);
 
 /* Normalised co-attention map A[i][n] = exp(scores[i][n] - lse[slide(n)][i])  (attention_scores['coattn'],
  * mcat.py:97,140).  amap fp32 [6][total_rows]. */

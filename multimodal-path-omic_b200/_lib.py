@@ -103,7 +103,8 @@ def lib():
 SIGNATURES = {
     "mpo_cast_bf16": [c_void_p, c_void_p, c_i64, c_void_p],
     "mpo_bag_fwd": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                    c_void_p, c_void_p, c_u32, c_float, c_void_p],
+                    c_void_p, c_void_p, c_u32, c_void_p, c_float, c_void_p],
+    "mpo_advance_seed": [c_void_p, c_void_p],
     "mpo_attn_map": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p],
     "mpo_bag_bwd": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p],

@@ -139,11 +139,11 @@ class BagWorkspace:
             self.part_db = torch.empty((bag.num_tiles, D), dtype=torch.float32, device=dev)
 
 
-def bag_forward(bag, w_h_bf16, bias_h, qk, ws, seed=0, drop_p=0.0):
+def bag_forward(bag, w_h_bf16, bias_h, qk, ws, seed=0, drop_p=0.0, seed_dev=None):
     """mpo_bag_fwd: fills ws.scores / ws.pooled / ws.lse (and ws.h_saved when allocated)."""
     _lib.call("mpo_bag_fwd", bag.c(), _ptr(w_h_bf16), _ptr(bias_h), _ptr(qk), _ptr(ws.scores), _ptr(ws.part_ml),
               _ptr(ws.part_pool), _ptr(ws.pooled), _ptr(ws.lse), _ptr(ws.h_saved), ctypes.c_uint32(seed & 0xFFFFFFFF),
-              ctypes.c_float(drop_p), _stream())
+              _ptr(seed_dev), ctypes.c_float(drop_p), _stream())
 
 
 def attention_map(bag, ws, out=None):

@@ -150,7 +150,7 @@ static int check_bag(const mpo_bag* bag, const char* who) {
 
 int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, const float* qk, float* scores,
                 float* part_ml, float* part_pool, float* pooled, float* lse, void* h_saved, uint32_t seed,
-                float drop_p, void* stream) {
+                const uint32_t* seed_dev, float drop_p, void* stream) {
   int rc = check_bag(bag, "mpo_bag_fwd");
   if (rc) return rc;
   if (bag->total_rows == 0 || bag->num_tiles == 0) return MPO_OK;
@@ -173,6 +173,7 @@ int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, c
   p.part_pool = part_pool;
   p.h_out = static_cast<__half*>(h_saved);
   p.seed = seed;
+  p.seed_dev = seed_dev;
   p.drop_thr = static_cast<uint32_t>(drop_p * 256.f + 0.5f);
   p.drop_scale = p.drop_thr ? 256.f / static_cast<float>(256 - p.drop_thr) : 1.f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -180,6 +181,15 @@ int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, c
   if (rc) return rc;
   return check_cuda(launch_bag_merge(bag->tile_prefix, part_ml, part_pool, pooled, lse, bag->num_slides, st),
                     "bag_merge_kernel");
+}
+
+__global__ void advance_seed_kernel(uint32_t* s) { *s = mpo::hash_u32(*s + 0x9E3779B9u); }
+
+int mpo_advance_seed(uint32_t* seed_dev, void* stream) {
+  if (!seed_dev) return fail(MPO_E_ARG, "%s", "mpo_advance_seed: NULL pointer");
+  advance_seed_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(seed_dev);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "advance_seed_kernel");
 }
 
 int mpo_attn_map(const mpo_bag* bag, const float* scores, const float* lse, float* amap, void* stream) {

@@ -143,6 +143,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     float* red_s = reinterpret_cast<float*>(staging);   // aliases the staged tile after phase 2
 
     bias_s[et] = p.bias[et];
+    const uint32_t seed = p.seed_dev != nullptr ? (p.seed ^ __ldg(p.seed_dev)) : p.seed;
     int cur_slide = -1;
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
@@ -189,8 +190,8 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           if (p.drop_thr != 0) {
             // one 32-bit draw covers four consecutive features of this patch row
             const uint32_t base = (grow * kD + col0 + j) >> 2;
-            const uint32_t r0 = rng_u32(p.seed, 0u, base);
-            const uint32_t r1 = rng_u32(p.seed, 0u, base + 1);
+            const uint32_t r0 = rng_u32(seed, 0u, base);
+            const uint32_t r1 = rng_u32(seed, 0u, base + 1);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               h[e] = (((r0 >> (8 * e)) & 0xFFu) < p.drop_thr) ? 0.f : h[e] * p.drop_scale;

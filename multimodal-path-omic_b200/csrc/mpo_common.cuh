@@ -33,6 +33,7 @@ struct BagFwdParams {
   float* part_pool;            // [num_tiles][6][256]         sum_n exp(s - m_tile) h_n
   __half* h_out;               // [total_rows][256] or null   saved activations (fp16) for the backward pass
   uint32_t seed;               // dropout stream (train mode)
+  const uint32_t* seed_dev;    // when non-null the stream id is read from device memory (CUDA-graph replays)
   uint32_t drop_thr;           // drop an element when its 8 random bits < drop_thr (0 = eval)
   float drop_scale;            // 1 / keep probability
 };

@@ -194,25 +194,15 @@ class SlideEngine:
         io.att_omic = st.att_omic.data_ptr()
         return io
 
-    # -- forward
-    def forward(self, model, bag, omics, train=False, save_for_backward=True, seed=None, reuse_ws=False):
-        """bag: PackedBag of B slides; omics: 6 tensors [B, d_i] float32 on the GPU."""
+    # -- buffers
+    def alloc_state(self, model, bag, save_for_backward=True, reuse_ws=False, with_backward_buffers=False):
+        """All device buffers one pass over `bag` needs (caller-owned in the C ABI, allocated through torch)."""
         bnd = self.binding
-        if bnd.variant == VARIANT_NACAGAT:
-            raise NotImplementedError("NaCAGaT bag kernels are not wired into this build yet")
         dev = bag.x.device
-        B = bag.num_slides
-        st = SlideState()
-        st.B, st.bag, st.train = B, bag, bool(train)
-        st.omics = []
-        for i, o in enumerate(omics):
-            require_cuda(o, "omics[%d]" % i)
-            o = o.to(torch.float32).reshape(B, -1).contiguous()
-            if o.shape[1] != bnd.omic_sizes[i]:
-                raise RuntimeError("omics[%d] has width %d, the model expects %d" % (i, o.shape[1], bnd.omic_sizes[i]))
-            st.omics.append(o)
+        B, K = bag.num_slides, bnd.n_classes
         f32 = dict(dtype=torch.float32, device=dev)
-        K = bnd.n_classes
+        st = SlideState()
+        st.B, st.bag = B, bag
         st.tail_ws = self._tail_ws(model, B, dev, reuse_ws)
         st.qp = torch.empty((B, Q, D), **f32)
         st.qk = torch.empty((B, Q, D), **f32)
@@ -224,10 +214,41 @@ class SlideEngine:
         st.att_path = torch.empty((B, Q), **f32)
         st.att_omic = torch.empty((B, Q), **f32)
         st.bag_ws = bp.BagWorkspace(bag, save_h=save_for_backward)
+        st.seed_dev = None
+        if with_backward_buffers:
+            st.bag_ws.ensure_bwd(bag)
+            st.dpooled = torch.empty((B, Q, D), **f32)
+            st.dqk = torch.empty((B, Q, D), **f32)
+            st.loss = torch.empty(B, **f32)
+            st.dhz = torch.empty((B, K), **f32)
+            st.dS = torch.empty((B, K), **f32)
+        return st
+
+    # -- forward
+    def forward(self, model, bag, omics, train=False, save_for_backward=True, seed=None, reuse_ws=False,
+                after_bag=None, st=None):
+        """bag: PackedBag of B slides; omics: 6 tensors [B, d_i] float32 on the GPU.  `st` reuses the buffers of an
+        earlier alloc_state() (static addresses: needed for CUDA-graph capture)."""
+        bnd = self.binding
+        if bnd.variant == VARIANT_NACAGAT:
+            raise NotImplementedError("NaCAGaT bag kernels are not wired into this build yet")
+        B = bag.num_slides
+        if st is None:
+            st = self.alloc_state(model, bag, save_for_backward, reuse_ws)
+        elif st.B != B or st.bag is not bag:
+            raise RuntimeError("the reused slide state was allocated for a different packed bag")
+        st.train = bool(train)
+        st.omics = []
+        for i, o in enumerate(omics):
+            require_cuda(o, "omics[%d]" % i)
+            o = o.to(torch.float32).reshape(B, -1).contiguous()
+            if o.shape[1] != bnd.omic_sizes[i]:
+                raise RuntimeError("omics[%d] has width %d, the model expects %d" % (i, o.shape[1], bnd.omic_sizes[i]))
+            st.omics.append(o)
         st.drop_p = self.bag_dropout if train else 0.0
         st.seed = (_next_seed() if seed is None else seed) if train else 0
         P = bnd.params()
-        # bf16 streaming copy of H.0.weight
+        # bf16 streaming copy of H.0.weight (refreshed every pass: the optimizer updates the fp32 master in place)
         w_h = P["H.0.weight"]
         if self._w_bf16 is None or self._w_bf16.device != w_h.device:
             self._w_bf16 = torch.empty(w_h.shape, dtype=torch.bfloat16, device=w_h.device)
@@ -235,7 +256,10 @@ class SlideEngine:
         io = self._io(st)
         s = _stream()
         _lib.call("mpo_tail_pre_fwd", ctypes.byref(model), ctypes.byref(io), s)
-        bp.bag_forward(bag, self._w_bf16, P["H.0.bias"].detach(), st.qk, st.bag_ws, seed=st.seed, drop_p=st.drop_p)
+        bp.bag_forward(bag, self._w_bf16, P["H.0.bias"].detach(), st.qk, st.bag_ws, seed=st.seed, drop_p=st.drop_p,
+                       seed_dev=st.seed_dev if train else None)
+        if after_bag is not None:        # e.g. the cross-GPU log-sum-exp combine of a patch-sharded bag (dp.py)
+            after_bag(st)
         _lib.call("mpo_tail_post_fwd", ctypes.byref(model), ctypes.byref(io), s)
         return st
 
@@ -248,7 +272,8 @@ class SlideEngine:
         """model must carry gradient pointers; they are accumulated into."""
         dev = st.bag.x.device
         f32 = dict(dtype=torch.float32, device=dev)
-        st.dpooled = torch.empty((st.B, Q, D), **f32)
+        if st.dpooled is None:
+            st.dpooled = torch.empty((st.B, Q, D), **f32)
         io = self._io(st)
         s = _stream()
 
@@ -263,7 +288,8 @@ class SlideEngine:
             raise RuntimeError("backward needs a model binding with gradient buffers")
         gw, gb = ctypes.c_void_p(model.H.gw), ctypes.c_void_p(model.H.gb)
         st.bag_ws.ensure_bwd(st.bag)
-        st.dqk = torch.empty((st.B, Q, D), **f32)
+        if st.dqk is None:
+            st.dqk = torch.empty((st.B, Q, D), **f32)
         ws = st.bag_ws
         _lib.call("mpo_bag_bwd", st.bag.c(), _ptr(ws.h_saved), _ptr(ws.scores), _ptr(ws.lse), _ptr(ws.pooled),
                   _ptr(st.dpooled), _ptr(st.qk), _ptr(ws.dz), _ptr(ws.part_dqk), _ptr(ws.part_db), _ptr(st.dqk),
@@ -351,17 +377,63 @@ class BatchTrainer:
     def zero_grad(self):
         self.flat_grad.zero_()
 
-    def step(self, bag, omics, labels, censor, train=True, seed=None):
-        """Returns (loss [B], hazards [B,K], S [B,K]).  labels int64 [B], censor float32 [B], on the GPU."""
+    def _run(self, st, bag, omics, labels, censor, train, seed):
         eng = self.engine
-        st = eng.forward(self.model, bag, omics, train=train, save_for_backward=True, seed=seed, reuse_ws=True)
+        if st is not None and st.seed_dev is not None and train:
+            _lib.call("mpo_advance_seed", _ptr(st.seed_dev), _stream())
+        st = eng.forward(self.model, bag, omics, train=train, save_for_backward=True, seed=seed, reuse_ws=True, st=st)
         B, K = st.B, eng.binding.n_classes
-        loss = torch.empty(B, dtype=torch.float32, device=bag.x.device)
-        dhz = torch.empty((B, K), dtype=torch.float32, device=bag.x.device)
-        dS = torch.empty((B, K), dtype=torch.float32, device=bag.x.device)
+        if getattr(st, "loss", None) is None:
+            dev = bag.x.device
+            st.loss = torch.empty(B, dtype=torch.float32, device=dev)
+            st.dhz = torch.empty((B, K), dtype=torch.float32, device=dev)
+            st.dS = torch.empty((B, K), dtype=torch.float32, device=dev)
         _lib.call("mpo_surv_loss", self.kind, _ptr(st.hazards), _ptr(st.S), _ptr(labels), _ptr(censor),
                   ctypes.c_float(self.alpha), ctypes.c_float(self.eps), ctypes.c_float(1.0 / self.grad_acc_step),
-                  _ptr(loss), _ptr(dhz), _ptr(dS), B, K, _stream())
-        eng.backward(self.model, st, dhz, dS, None)
+                  _ptr(st.loss), _ptr(st.dhz), _ptr(st.dS), B, K, _stream())
+        eng.backward(self.model, st, st.dhz, st.dS, None)
+        return st
+
+    def step(self, bag, omics, labels, censor, train=True, seed=None):
+        """Returns (loss [B], hazards [B,K], S [B,K]).  labels int64 [B], censor float32 [B], on the GPU."""
+        st = self._run(None, bag, omics, labels, censor, train, seed)
         self.last_state = st
-        return loss, st.hazards, st.S
+        return st.loss, st.hazards, st.S
+
+    def capture(self, bag, omics, labels, censor, train=True):
+        """Record one step (forward + loss + backward) over these STATIC buffers into a CUDA graph.
+
+        The caller refreshes the contents of bag.x / omics / labels / censor in place and calls replay(); the
+        ~250 small tail launches then cost one graph launch.  Dropout masks change on every replay
+        through a device-side seed."""
+        eng = self.engine
+        dev = bag.x.device
+        st = eng.alloc_state(self.model, bag, save_for_backward=True, reuse_ws=False, with_backward_buffers=True)
+        st.seed_dev = torch.tensor([_next_seed()], dtype=torch.int64, device=dev).to(torch.int32)
+        omics = [o.to(torch.float32).reshape(bag.num_slides, -1).contiguous() for o in omics]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):                         # warm-up outside the capture (lazy kernel attributes etc.)
+                self._run(st, bag, omics, labels, censor, train, 0)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.flat_grad.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._run(st, bag, omics, labels, censor, train, 0)
+        self.flat_grad.zero_()
+        self.last_state = st
+        return GraphedStep(graph, st, (bag, omics, labels, censor))
+
+
+class GraphedStep:
+    """A captured train step over static buffers: refresh the buffers in place, then replay()."""
+
+    def __init__(self, graph, state, static_inputs):
+        self.graph, self.state, self.static_inputs = graph, state, static_inputs
+
+    def replay(self):
+        self.graph.replay()
+        st = self.state
+        return st.loss, st.hazards, st.S

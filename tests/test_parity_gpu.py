@@ -145,6 +145,34 @@ def test_batched_trainer_equals_per_slide_gradients():
         assert err < 2e-3, (k, err)
 
 
+def test_graph_replay_equals_eager_step():
+    """A captured CUDA-graph step accumulates the same gradients as the eager step (eval mode, so no dropout)."""
+    synth = _pkg("synth")
+    sp = _pkg("slidepath")
+    bpm = _pkg("bagpass")
+    case = load_case("mcat_concat_300")
+    net = build_model(case).eval()
+    lens = [300, 200, 129]
+    slides = [synth.make_slide(200 + i, n) for i, n in enumerate(lens)]
+    pb = bpm.PackedBag.from_slides([torch.from_numpy(s[0]).cuda() for s in slides])
+    om = [torch.stack([torch.from_numpy(s[1][i]) for s in slides]).cuda() for i in range(6)]
+    labels = torch.tensor([s[2] for s in slides], dtype=torch.int64, device="cuda")
+    cens = torch.tensor([s[3] for s in slides], dtype=torch.float32, device="cuda")
+    tr = sp.BatchTrainer(net, loss="ces", grad_acc_step=3)
+    tr.zero_grad()
+    loss_e, _, _ = tr.step(pb, om, labels, cens, train=False)
+    g_eager = tr.flat_grad.clone()
+    loss_e = loss_e.clone()
+    g = tr.capture(pb, om, labels, cens, train=False)
+    tr.zero_grad()
+    loss_g, _, _ = g.replay()
+    loss_g2, _, _ = g.replay()
+    torch.cuda.synchronize()
+    assert torch.allclose(loss_g, loss_e, rtol=1e-6, atol=1e-7)
+    # two replays accumulate twice the gradient (atomics in dW_H make the sum order-dependent: allow fp32 noise)
+    assert float((tr.flat_grad - 2 * g_eager).norm() / (2 * g_eager).norm()) < 1e-5
+
+
 def test_cpu_tensors_are_refused():
     case = load_case("mcat_concat_300")
     net = build_model(case, device="cpu").eval()
