@@ -286,9 +286,11 @@ def run_ours(args, rank, world, local_rank):
         host_lab = labels.cpu().pin_memory(); host_cen = censor.cpu().pin_memory()
         dev_x = [torch.empty_like(x) for _ in range(2)]
         dev_bags = [bpm.PackedBag(dx, lengths) for dx in dev_x]
-        dev_om = [[torch.empty_like(o) for o in omics] for _ in range(2)]
-        dev_lab = [torch.empty_like(labels) for _ in range(2)]
-        dev_cen = [torch.empty_like(censor) for _ in range(2)]
+        dev_om = [[o.clone() for o in omics] for _ in range(2)]
+        dev_lab = [labels.clone() for _ in range(2)]
+        dev_cen = [censor.clone() for _ in range(2)]
+        for dx in dev_x:
+            dx.copy_(x)
         steps_g = [trainer.capture(dev_bags[i], dev_om[i], dev_lab[i], dev_cen[i], train=True) for i in range(2)]
         copy_stream = torch.cuda.Stream(device=dev)
         ready = [torch.cuda.Event() for _ in range(2)]

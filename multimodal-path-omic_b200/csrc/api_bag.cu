@@ -160,7 +160,7 @@ int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, c
   CUtensorMap tm_x, tm_w;
   rc = make_tmap_bf16_2d(&tm_x, bag->x, static_cast<uint64_t>(bag->total_rows), kDIn, kBK, kTileM);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tm_w, w_h_bf16, kD, kDIn, kBK, kD);
+  rc = make_tmap_bf16_2d(&tm_w, w_h_bf16, kD, kDIn, kBK, kD / fwd_cluster_size());   // one multicast slice per CTA
   if (rc) return rc;
   BagFwdParams p;
   p.tile_info = reinterpret_cast<const TileInfo*>(bag->tile_info);

@@ -13,6 +13,7 @@
 #include "mpo_ptx.cuh"
 #include "mpo_common.cuh"
 #include "launchers.h"
+#include <cstdlib>
 
 namespace mpo {
 
@@ -40,6 +41,10 @@ struct FwdSmem {
 constexpr int kFwdSmemBytes = FwdSmem::total + 1024;  // + slack for manual 1024 B alignment
 
 
+// kC = CTAs per cluster.  With kC > 1 every CTA still owns its own tiles, but the cluster walks the K blocks in
+// lock step and each CTA fetches only 1/kC of every W_H block, multicasting it to all kC shared memories: the L2 ->
+// SM traffic for the weights drops by kC (W_H re-reads, not the bag, are what saturates the L2 slices at kC = 1).
+template <int kC>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                const BagFwdParams p) {
@@ -61,7 +66,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     tma_prefetch_desc(&tm_w);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], kC);     // one tcgen05.commit arrival from every CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -75,8 +80,13 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (kC > 1) cluster_sync_all();     // remote CTAs' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t cta_rank = kC > 1 ? cluster_ctarank() : 0;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << kC) - 1);
+  // every CTA of a cluster runs the same number of pipeline iterations; surplus ones are dummies without MMAs
+  const int iters = (p.num_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -85,14 +95,21 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       const uint64_t pol_keep = policy_evict_last();      // W_H is re-read by every tile: keep it in L2
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const int row0 = p.tile_info[t].row0;
+      constexpr int kWRows = kD / kC;                     // W_H rows this CTA fetches per K block
+      for (int it = 0; it < iters; ++it) {
+        const int t = blockIdx.x + it * gridDim.x;
+        const int row0 = t < p.num_tiles ? p.tile_info[t].row0 : 0;
         for (int kb = 0; kb < kKBlocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + FwdSmem::stages + stage * kStageBytes;
           mbar_expect_tx(&full_bar[stage], kStageBytes);
           tma_load_2d(sa, &tm_x, &full_bar[stage], kb * kBK, row0, pol_stream);
-          tma_load_2d(sa + kABytes, &tm_w, &full_bar[stage], kb * kBK, 0, pol_keep);
+          if (kC == 1) {
+            tma_load_2d(sa + kABytes, &tm_w, &full_bar[stage], kb * kBK, 0, pol_keep);
+          } else {
+            tma_load_2d_mcast(sa + kABytes + cta_rank * (kWRows * 128), &tm_w, &full_bar[stage], kb * kBK,
+                              cta_rank * kWRows, kMask, pol_keep);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -103,28 +120,34 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, kD, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      for (int it = 0; it < iters; ++it) {
+        const bool real = blockIdx.x + it * gridDim.x < static_cast<unsigned>(p.num_tiles);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);   // epilogue has drained this accumulator stage
-        tc_fence_after();
+        if (real) {
+          mbar_wait(&tempty_bar[as], aphase ^ 1);   // epilogue has drained this accumulator stage
+          tc_fence_after();
+        }
         const uint32_t d_tmem = tmem_base + as * kD;
         for (int kb = 0; kb < kKBlocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + FwdSmem::stages + stage * kStageBytes);
-          const uint32_t b_addr = a_addr + kABytes;
+          if (real) {
+            const uint32_t a_addr = smem_u32(smem + FwdSmem::stages + stage * kStageBytes);
+            const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+              const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+              umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
+          // frees this smem stage -- in every CTA of the cluster -- once these MMAs retire
+          if (kC == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_mcast(&empty_bar[stage], kMask);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);        // accumulator complete -> epilogue
+        if (real) umma_commit(&tfull_bar[as]);      // accumulator complete -> epilogue
       }
     }
   } else {
@@ -320,6 +343,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if (kC > 1) cluster_sync_all();     // nobody leaves while a peer may still multicast into / arrive on its smem
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -351,19 +375,58 @@ bag_merge_kernel(const int* __restrict__ tile_prefix,   // [B+1] first tile of e
 // ------------------------------------------------------------------------------------------------
 // host launchers (C++ side; the extern "C" surface is in api.cu)
 // ------------------------------------------------------------------------------------------------
-cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const BagFwdParams& prm, int num_sms,
-                           cudaStream_t stream) {
+template <int kC>
+static cudaError_t launch_fwd_cluster(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const BagFwdParams& prm,
+                                      int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
+  static int max_clusters = 0;
+  auto kern = bag_fwd_kernel<kC>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kFwdThreads);
+  cfg.dynamicSmemBytes = kFwdSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(bag_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
     if (e != cudaSuccess) return e;
+    cfg.gridDim = dim3(num_sms / kC * kC);
+    e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+    if (e != cudaSuccess) return e;
+    if (max_clusters < 1) return cudaErrorInvalidConfiguration;
     attr_set = true;
   }
-  if (prm.num_tiles <= 0) return cudaSuccess;
-  const int grid = prm.num_tiles < num_sms ? prm.num_tiles : num_sms;
-  bag_fwd_kernel<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(tm_x, tm_w, prm);
+  int clusters = (prm.num_tiles + kC - 1) / kC;
+  if (clusters > max_clusters) clusters = max_clusters;
+  cfg.gridDim = dim3(clusters * kC);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x, tm_w, prm);
   count_launch();
-  return cudaGetLastError();
+  return e;
+}
+
+int fwd_cluster_size() {
+  static int c = -1;
+  if (c < 0) {
+    const char* env = getenv("MPO_FWD_CLUSTER");
+    c = env ? atoi(env) : 2;
+    if (c != 1 && c != 2 && c != 4) c = 2;
+  }
+  return c;
+}
+
+cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const BagFwdParams& prm, int num_sms,
+                           cudaStream_t stream) {
+  if (prm.num_tiles <= 0) return cudaSuccess;
+  switch (fwd_cluster_size()) {
+    case 1: return launch_fwd_cluster<1>(tm_x, tm_w, prm, num_sms, stream);
+    case 4: return launch_fwd_cluster<4>(tm_x, tm_w, prm, num_sms, stream);
+    default: return launch_fwd_cluster<2>(tm_x, tm_w, prm, num_sms, stream);
+  }
 }
 
 cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, const float* part_pool, float* pooled,

@@ -453,6 +453,7 @@ __global__ void surv_loss_kernel(int kind, const float* __restrict__ hazards, co
   const int y = static_cast<int>(label[b]);
   const float c = censor[b];
   for (int j = 0; j < K; ++j) { dhaz[b * K + j] = 0.f; dS[b * K + j] = 0.f; }
+  if (y < 0 || y >= K) { loss[b] = NAN; return; }   // out-of-range label: poison the loss, touch nothing else
   const float s_prev = y == 0 ? 1.f : S[b * K + y - 1];
   const float h_y = hazards[b * K + y];
   const float unc = -(1.f - c) * (logf(fmaxf(s_prev, eps)) + logf(fmaxf(h_y, eps)));
