@@ -1,6 +1,7 @@
 // extern "C" surface for the bag stage (declared in include/mpo_b200.h) + small auxiliary kernels.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include "../../include/mpo_b200.h"
 #include "mpo_ptx.cuh"
@@ -174,6 +175,7 @@ int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, c
   p.h_out = static_cast<__half*>(h_saved);
   p.seed = seed;
   p.seed_dev = seed_dev;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MPO_FWD_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   p.drop_thr = static_cast<uint32_t>(drop_p * 256.f + 0.5f);
   p.drop_scale = p.drop_thr ? 256.f / static_cast<float>(256 - p.drop_thr) : 1.f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -124,20 +124,37 @@ __global__ void __launch_bounds__(kDzWarps * 32, 1) bag_bwd_dz_kernel(const BagB
 }
 
 // dqk[b][i][d] = sum over the slide's tiles;  db_H[d] += sum over all tiles (gradient accumulation)
+// 4 tile groups x 64 float4 columns per block so that many independent loads are in flight
 __global__ void __launch_bounds__(256)
 bag_bwd_reduce_kernel(const int* __restrict__ tile_prefix, const float* __restrict__ part_dqk,
                       const float* __restrict__ part_db, float* __restrict__ dqk, float* __restrict__ grad_bias,
                       int B, int num_tiles) {
-  const int d = threadIdx.x;
-  if (static_cast<int>(blockIdx.x) < B) {
-    const int b = blockIdx.x, i = blockIdx.y;
-    float v = 0.f;
-    for (int t = tile_prefix[b]; t < tile_prefix[b + 1]; ++t) v += part_dqk[(static_cast<size_t>(t) * kQ + i) * kD + d];
-    dqk[(static_cast<size_t>(b) * kQ + i) * kD + d] = v;
-  } else if (blockIdx.y == 0) {
-    float v = 0.f;
-    for (int t = 0; t < num_tiles; ++t) v += part_db[static_cast<size_t>(t) * kD + d];
-    grad_bias[d] += v;
+  __shared__ float4 acc_s[4][64];
+  const int tid = threadIdx.x, tg = tid >> 6, dq = tid & 63;
+  const bool is_bias = static_cast<int>(blockIdx.x) >= B;
+  if (is_bias && blockIdx.y != 0) return;
+  const int b = blockIdx.x, i = blockIdx.y;
+  const int t0 = is_bias ? 0 : tile_prefix[b];
+  const int t1 = is_bias ? num_tiles : tile_prefix[b + 1];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int t = t0 + tg; t < t1; t += 4) {
+    const float* src = is_bias ? part_db + static_cast<size_t>(t) * kD : part_dqk + (static_cast<size_t>(t) * kQ + i) * kD;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + dq);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  acc_s[tg][dq] = acc;
+  __syncthreads();
+  if (tid < 64) {
+    float4 r = acc_s[0][tid];
+#pragma unroll
+    for (int g = 1; g < 4; ++g) { r.x += acc_s[g][tid].x; r.y += acc_s[g][tid].y; r.z += acc_s[g][tid].z; r.w += acc_s[g][tid].w; }
+    if (is_bias) {
+      float* g4 = grad_bias + tid * 4;      // scalar: the caller's gradient view need not be 16-byte aligned
+      g4[0] += r.x; g4[1] += r.y; g4[2] += r.z; g4[3] += r.w;
+    } else {
+      reinterpret_cast<float4*>(dqk + (static_cast<size_t>(b) * kQ + i) * kD)[tid] = r;
+    }
   }
 }
 
@@ -158,7 +175,8 @@ bag_bwd_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
                   float* __restrict__ grad_w,   // [256][1024] fp32, accumulated
                   int total_rows, int num_splits) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128B-swizzle atoms, by pointer arithmetic so the compiler keeps the shared state space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwStages * kDwStageBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kDwStages;

@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
 bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                const BagFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128B-swizzle atoms, by pointer arithmetic so the compiler keeps the shared state space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::bars);
   uint64_t* full_bar = bars;                 // [kStages]
@@ -98,13 +99,19 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       constexpr int kWRows = kD / kC;                     // W_H rows this CTA fetches per K block
       for (int it = 0; it < iters; ++it) {
         const int t = blockIdx.x + it * gridDim.x;
-        const int row0 = t < p.num_tiles ? p.tile_info[t].row0 : 0;
+        int row0 = t < p.num_tiles ? p.tile_info[t].row0 : 0;
+        if (p.debug & 2) row0 = (blockIdx.x & 7) * kTileM;
+        const int tn = t + gridDim.x;
+        const int row_next = tn < p.num_tiles ? p.tile_info[tn].row0 : -1;
         for (int kb = 0; kb < kKBlocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + FwdSmem::stages + stage * kStageBytes;
-          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          const bool skip_w = (p.debug & 1) && it > 0;
+          mbar_expect_tx(&full_bar[stage], skip_w ? kABytes : kStageBytes);
           tma_load_2d(sa, &tm_x, &full_bar[stage], kb * kBK, row0, pol_stream);
-          if (kC == 1) {
+          if ((p.debug & 4) && row_next >= 0) tma_prefetch_l2_2d(&tm_x, kb * kBK, row_next);
+          if (skip_w) {
+          } else if (kC == 1) {
             tma_load_2d(sa + kABytes, &tm_w, &full_bar[stage], kb * kBK, 0, pol_keep);
           } else {
             tma_load_2d_mcast(sa + kABytes + cta_rank * (kWRows * 128), &tm_w, &full_bar[stage], kb * kBK,
@@ -358,18 +365,50 @@ __global__ void __launch_bounds__(256)
 bag_merge_kernel(const int* __restrict__ tile_prefix,   // [B+1] first tile of each slide
                  const float* __restrict__ part_ml, const float* __restrict__ part_pool,
                  float* __restrict__ pooled, float* __restrict__ lse) {
-  const int b = blockIdx.x, i = blockIdx.y, d = threadIdx.x;
+  // one block per (slide, query); 4 tile groups x 64 float4 feature columns, many independent loads in flight
+  __shared__ float red[8];
+  __shared__ float4 acc_s[4][64];
+  const int b = blockIdx.x, i = blockIdx.y, tid = threadIdx.x;
   const int t0 = tile_prefix[b], t1 = tile_prefix[b + 1];
-  float M = -INFINITY;
-  for (int t = t0; t < t1; ++t) M = fmaxf(M, part_ml[static_cast<size_t>(t) * 12 + i]);
-  float L = 0.f, acc = 0.f;
-  for (int t = t0; t < t1; ++t) {
-    const float w = __expf(part_ml[static_cast<size_t>(t) * 12 + i] - M);
-    L = fmaf(part_ml[static_cast<size_t>(t) * 12 + 6 + i], w, L);
-    acc = fmaf(part_pool[(static_cast<size_t>(t) * kQ + i) * kD + d], w, acc);
+  float m = -INFINITY;
+  for (int t = t0 + tid; t < t1; t += 256) m = fmaxf(m, __ldg(part_ml + static_cast<size_t>(t) * 12 + i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((tid & 31) == 0) red[tid >> 5] = m;
+  __syncthreads();
+  float M = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) M = fmaxf(M, red[w]);
+  __syncthreads();
+  float l = 0.f;
+  for (int t = t0 + tid; t < t1; t += 256)
+    l = fmaf(__ldg(part_ml + static_cast<size_t>(t) * 12 + 6 + i), __expf(__ldg(part_ml + static_cast<size_t>(t) * 12 + i) - M), l);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if ((tid & 31) == 0) red[tid >> 5] = l;
+  __syncthreads();
+  float L = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) L += red[w];
+  const int tg = tid >> 6, dq = tid & 63;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int t = t0 + tg; t < t1; t += 4) {
+    const float w = __expf(__ldg(part_ml + static_cast<size_t>(t) * 12 + i) - M);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(part_pool + (static_cast<size_t>(t) * kQ + i) * kD) + dq);
+    acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
   }
-  pooled[(static_cast<size_t>(b) * kQ + i) * kD + d] = acc / L;
-  if (d == 0) lse[b * kQ + i] = M + __logf(L);
+  acc_s[tg][dq] = acc;
+  __syncthreads();
+  if (tid < 64) {
+    const float inv = 1.f / L;
+    float4 r = acc_s[0][tid];
+#pragma unroll
+    for (int g = 1; g < 4; ++g) { r.x += acc_s[g][tid].x; r.y += acc_s[g][tid].y; r.z += acc_s[g][tid].z; r.w += acc_s[g][tid].w; }
+    r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
+    reinterpret_cast<float4*>(pooled + (static_cast<size_t>(b) * kQ + i) * kD)[tid] = r;
+  }
+  if (tid == 0) lse[b * kQ + i] = M + __logf(L);
 }
 
 // ------------------------------------------------------------------------------------------------

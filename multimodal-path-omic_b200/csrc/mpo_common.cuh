@@ -36,6 +36,8 @@ struct BagFwdParams {
   const uint32_t* seed_dev;    // when non-null the stream id is read from device memory (CUDA-graph replays)
   uint32_t drop_thr;           // drop an element when its 8 random bits < drop_thr (0 = eval)
   float drop_scale;            // 1 / keep probability
+  int debug;                   // timing experiments only (env MPO_FWD_DEBUG): bit0 skip W loads, bit1 X from L2,
+                               // bit2 L2-prefetch the next tile's X
 };
 
 struct BagBwdDzParams {

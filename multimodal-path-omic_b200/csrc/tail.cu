@@ -125,22 +125,21 @@ mpo_lin sub(const mpo_lin& L, int row0, int in) {   // rows [row0, ...) of a pac
 // y[rows,out] = act(x[rows,in] W^T + b)
 void lin_fwd(Ctx& c, const float* x, long long ldx, const mpo_lin& L, int out, int in, float* y, long long ldy, int rows,
              int act) {
-  GemmArgs g{x, ldx, 1, L.w, 1, in, y, ldy, L.b, rows, out, in, 1.f, 0, act};
+  GemmArgs g{x, ldx, 1, L.w, 1, in, y, ldy, L.b, rows, out, in, 1.f, 0, act, nullptr};
   c.chk(launch_gemm(g, c.st), "lin_fwd");
 }
 // dz [rows,out] is the gradient at the pre-activation.  dx (=|+=) dz W ; gw += dz^T x ; gb += colsum(dz)
 void lin_bwd(Ctx& c, const float* dz, long long lddz, const float* x, long long ldx, const mpo_lin& L, int out, int in,
              float* dx, long long lddx, int rows, bool acc_dx) {
   if (dx != nullptr) {
-    GemmArgs g{dz, lddz, 1, L.w, in, 1, dx, lddx, nullptr, rows, in, out, 1.f, acc_dx ? 1 : 0, ACT_NONE};
+    GemmArgs g{dz, lddz, 1, L.w, in, 1, dx, lddx, nullptr, rows, in, out, 1.f, acc_dx ? 1 : 0, ACT_NONE, nullptr};
     c.chk(launch_gemm(g, c.st), "lin_bwd.dgrad");
   }
-  if (L.gw != nullptr) {
-    GemmArgs g{dz, 1, lddz, x, ldx, 1, L.gw, in, nullptr, out, in, rows, 1.f, 1, ACT_NONE};
+  if (L.gw != nullptr) {     // gw += dz^T x, with gb += rowsum(dz^T) fused into the same kernel
+    GemmArgs g{dz, 1, lddz, x, ldx, 1, L.gw, in, nullptr, out, in, rows, 1.f, 1, ACT_NONE, L.gb};
     c.chk(launch_gemm(g, c.st), "lin_bwd.wgrad");
-  }
-  if (L.gb != nullptr) {
-    colsum_kernel<<<nblk(out, 128), 128, 0, c.st>>>(dz, lddz, nullptr, 0, L.gb, rows, out); count_launch();
+  } else if (L.gb != nullptr) {
+    colsum_kernel<<<nblk(out, 32), 256, 0, c.st>>>(dz, lddz, nullptr, 0, L.gb, rows, out); count_launch();
     c.chk(cudaGetLastError(), "lin_bwd.bgrad");
   }
 }
@@ -169,8 +168,8 @@ void ln_bwd(Ctx& c, const float* dy, const mpo_norm& N, const float* xh, const f
   layernorm_bwd_kernel<<<nblk(rows, 8), 256, 0, c.st>>>(dy, N.g, xh, rs, dx, rows); count_launch();
   c.chk(cudaGetLastError(), "ln_bwd");
   if (N.gg != nullptr) {
-    colsum_kernel<<<nblk(E, 128), 128, 0, c.st>>>(dy, E, xh, E, N.gg, rows, E); count_launch();
-    colsum_kernel<<<nblk(E, 128), 128, 0, c.st>>>(dy, E, nullptr, 0, N.gb, rows, E); count_launch();
+    colsum_kernel<<<nblk(E, 32), 256, 0, c.st>>>(dy, E, xh, E, N.gg, rows, E); count_launch();
+    colsum_kernel<<<nblk(E, 32), 256, 0, c.st>>>(dy, E, nullptr, 0, N.gb, rows, E); count_launch();
     c.chk(cudaGetLastError(), "ln_bwd.params");
   }
 }
@@ -196,7 +195,7 @@ void enc_bwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, const Ws& w, f
   ln_bwd(c, dy2, P.norm2, ws + b.xh2, ws + b.rs2, dr2, R);
   float* df = ws + w.s512;
   {   // linear2: dz = dr2
-    GemmArgs g{dr2, E, 1, P.linear2.w, FF, 1, df, FF, nullptr, R, FF, E, 1.f, 0, ACT_NONE};
+    GemmArgs g{dr2, E, 1, P.linear2.w, FF, 1, df, FF, nullptr, R, FF, E, 1.f, 0, ACT_NONE, nullptr};
     c.chk(launch_gemm(g, c.st), "enc.lin2.dgrad");
     lin_bwd(c, dr2, E, ws + b.f, FF, P.linear2, E, FF, nullptr, 0, R, false);
   }
@@ -280,7 +279,7 @@ void bil_side_fwd(Ctx& c, const mpo_lin& Lh, const mpo_lin& Lz, const mpo_lin& L
                   const float* xa, const float* xb, int B) {
   lin_fwd(c, xa, E, Lh, BH, E, ws + w.bh[s], BH, B, ACT_RELU);
   // U[b][k*256+i] = sum_j W[k][i][j] xb[b][j]
-  GemmArgs g{xb, E, 1, Lz.w, 1, E, ws + w.bU[s], (long long)BH * E, nullptr, B, BH * E, E, 1.f, 0, ACT_NONE};
+  GemmArgs g{xb, E, 1, Lz.w, 1, E, ws + w.bU[s], (long long)BH * E, nullptr, B, BH * E, E, 1.f, 0, ACT_NONE, nullptr};
   c.chk(launch_gemm(g, c.st), "bil.U");
   bil_gate_fwd_kernel<<<B, 256, 0, c.st>>>(xa, ws + w.bU[s], Lz.b, ws + w.bh[s], ws + w.bg[s], ws + w.bgh[s]); count_launch();
   c.chk(cudaGetLastError(), "bil_gate_fwd");
@@ -297,11 +296,11 @@ void bil_side_bwd(Ctx& c, const mpo_lin& Lh, const mpo_lin& Lz, const mpo_lin& L
   c.chk(cudaGetLastError(), "bil_gate_bwd");
   // dW[(k,i)][j] += sum_b V[b][(k,i)] xb[b][j] ;  dxb[b][j] += sum_(k,i) V[b][(k,i)] W[(k,i)][j] ; db += colsum(dz)
   if (Lz.gw != nullptr) {
-    GemmArgs g{ws + w.bV, 1, (long long)BH * E, xb, E, 1, Lz.gw, E, nullptr, BH * E, E, B, 1.f, 1, ACT_NONE};
+    GemmArgs g{ws + w.bV, 1, (long long)BH * E, xb, E, 1, Lz.gw, E, nullptr, BH * E, E, B, 1.f, 1, ACT_NONE, nullptr};
     c.chk(launch_gemm(g, c.st), "bil.dW");
-    colsum_kernel<<<1, 128, 0, c.st>>>(ws + w.bdz[s], BH, nullptr, 0, Lz.gb, B, BH); count_launch();
+    colsum_kernel<<<1, 256, 0, c.st>>>(ws + w.bdz[s], BH, nullptr, 0, Lz.gb, B, BH); count_launch();
   }
-  GemmArgs g2{ws + w.bV, (long long)BH * E, 1, Lz.w, E, 1, dxb, E, nullptr, B, E, BH * E, 1.f, 1, ACT_NONE};
+  GemmArgs g2{ws + w.bV, (long long)BH * E, 1, Lz.w, E, 1, dxb, E, nullptr, B, E, BH * E, 1.f, 1, ACT_NONE, nullptr};
   c.chk(launch_gemm(g2, c.st), "bil.dxb");
   lin_bwd(c, ws + w.bdh[s], BH, xa, E, Lh, BH, E, dxa, E, B, true);
 }
@@ -375,14 +374,14 @@ int mpo_tail_pre_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   // key fold: qk[r][d] = sum_e q[r][e] W_k[e][d] / sqrt(256)
   {
     const float* Wk = m->coattn_in.w + (long long)E * E;
-    GemmArgs g{io->qp, E, 1, Wk, E, 1, io->qk, E, nullptr, R, E, E, 1.f / 16.f, 0, ACT_NONE};
+    GemmArgs g{io->qp, E, 1, Wk, E, 1, io->qk, E, nullptr, R, E, E, 1.f / 16.f, 0, ACT_NONE, nullptr};
     c.chk(launch_gemm(g, c.st), "fold");
   }
   if (m->variant == MPO_VARIANT_NACAGAT) {
     if (!io->kc) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_fwd: kc is NULL (NaCAGaT)");
     // kc[r] = q[r] . b_k / 16
     const float* bk = m->coattn_in.b + E;
-    GemmArgs g{io->qp, E, 1, bk, 1, 0, io->kc, 1, nullptr, R, 1, E, 1.f / 16.f, 0, ACT_NONE};
+    GemmArgs g{io->qp, E, 1, bk, 1, 0, io->kc, 1, nullptr, R, 1, E, 1.f / 16.f, 0, ACT_NONE, nullptr};
     c.chk(launch_gemm(g, c.st), "kc");
   }
   return finish(c);
@@ -521,10 +520,10 @@ int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   float* gWk = m->coattn_in.gw ? m->coattn_in.gw + (long long)E * E : nullptr;
   // key fold backward: dq[r][e] (+)= sum_d dqk[r][d] W_k[e][d] / 16 ; dW_k[e][d] += sum_r q[r][e] dqk[r][d] / 16
   {
-    GemmArgs g{io->dqk, E, 1, Wk, 1, E, ws + w.dqp, E, nullptr, R, E, E, 1.f / 16.f, nac ? 1 : 0, ACT_NONE};
+    GemmArgs g{io->dqk, E, 1, Wk, 1, E, ws + w.dqp, E, nullptr, R, E, E, 1.f / 16.f, nac ? 1 : 0, ACT_NONE, nullptr};
     c.chk(launch_gemm(g, c.st), "fold.dq");
     if (gWk) {
-      GemmArgs g2{io->qp, 1, E, io->dqk, E, 1, gWk, E, nullptr, E, E, R, 1.f / 16.f, 1, ACT_NONE};
+      GemmArgs g2{io->qp, 1, E, io->dqk, E, 1, gWk, E, nullptr, E, E, R, 1.f / 16.f, 1, ACT_NONE, nullptr};
       c.chk(launch_gemm(g2, c.st), "fold.dWk");
     }
   }
@@ -533,10 +532,10 @@ int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
     const float* bk = m->coattn_in.b + E;
     float* gbk = m->coattn_in.gb ? m->coattn_in.gb + E : nullptr;
     // kc = q . b_k / 16 :  dq += dkc b_k / 16 ; db_k += sum_r dkc[r] q[r] / 16
-    GemmArgs g{io->dkc, 1, 0, bk, 0, 1, ws + w.dqp, E, nullptr, R, E, 1, 1.f / 16.f, 1, ACT_NONE};
+    GemmArgs g{io->dkc, 1, 0, bk, 0, 1, ws + w.dqp, E, nullptr, R, E, 1, 1.f / 16.f, 1, ACT_NONE, nullptr};
     c.chk(launch_gemm(g, c.st), "kc.dq");
     if (gbk) {
-      GemmArgs g2{io->dkc, 0, 1, io->qp, E, 1, gbk, E, nullptr, 1, E, R, 1.f / 16.f, 1, ACT_NONE};
+      GemmArgs g2{io->dkc, 0, 1, io->qp, E, 1, gbk, E, nullptr, 1, E, R, 1.f / 16.f, 1, ACT_NONE, nullptr};
       c.chk(launch_gemm(g2, c.st), "kc.dbk");
     }
     // tanh(q) branch of the pre-gate: dq += dtq * (1 - tanh(q)^2)

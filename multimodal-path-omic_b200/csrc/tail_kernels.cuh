@@ -46,50 +46,98 @@ struct GemmArgs {
   float alpha;
   int accumulate;
   int act;
+  float* rowsum;      // optional: rowsum[m] += alpha * sum_k A(m,k)   (fused bias gradient)
 };
 
-template <bool A_KC, bool B_NC>
+// The tail is a long chain of small dependent GEMMs, so the kernel is built for latency: 32-deep K steps,
+// global loads of step k+1 issued into registers before the math of step k (double-buffered shared memory, one
+// barrier per step), and a narrow 32-row tile variant so that few-row problems still spread over many SMs.
+// Optional fused bias gradient: rowsum[m] += sum_k A(m,k) (used by the weight-gradient GEMMs, where A = dz^T).
+template <int BM, bool A_KC, bool B_NC>
 __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
-  __shared__ float As[16][68];
-  __shared__ float Bs[16][68];
+  constexpr int BN = 64, BK = 32;
+  constexpr int TM = BM / 16;                 // rows per thread (4 or 2)
+  constexpr int A_PER = BM * BK / 256;        // elements of the A tile each thread stages (8 or 4)
+  constexpr int B_PER = BN * BK / 256;        // 8
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int t = threadIdx.x;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int tx = t & 15, ty = t >> 4;
-  float acc[4][4];
+  float acc[TM][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float ra[A_PER], rb[B_PER];
+  float rsum = 0.f;                            // fused row sum of A (threads t < BM own row m0 + t)
 
-  for (int k0 = 0; k0 < g.K; k0 += 16) {
+  auto load_tile = [&](int k0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < A_PER; ++j) {
       int mm, kk;
-      if (A_KC) { kk = t & 15; mm = (t >> 4) + 16 * j; } else { mm = t & 63; kk = (t >> 6) + 4 * j; }
+      if (A_KC) { kk = t & 31; mm = (t >> 5) + 8 * j; } else { mm = t % BM; kk = t / BM + (256 / BM) * j; }
       const int m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < g.M && k < g.K) ? g.A[m * g.sa_m + k * g.sa_k] : 0.f;
-      int nn, kb;
-      if (B_NC) { nn = t & 63; kb = (t >> 6) + 4 * j; } else { kb = t & 15; nn = (t >> 4) + 16 * j; }
-      const int n = n0 + nn, k2 = k0 + kb;
-      Bs[kb][nn] = (n < g.N && k2 < g.K) ? g.B[k2 * g.sb_k + n * g.sb_n] : 0.f;
+      ra[j] = (m < g.M && k < g.K) ? __ldg(g.A + m * g.sa_m + k * g.sa_k) : 0.f;
     }
-    __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
+    for (int j = 0; j < B_PER; ++j) {
+      int nn, kk;
+      if (B_NC) { nn = t & 63; kk = (t >> 6) + 4 * j; } else { kk = t & 31; nn = (t >> 5) + 8 * j; }
+      const int n = n0 + nn, k = k0 + kk;
+      rb[j] = (n < g.N && k < g.K) ? __ldg(g.B + k * g.sb_k + n * g.sb_n) : 0.f;
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j) {
+      int mm, kk;
+      if (A_KC) { kk = t & 31; mm = (t >> 5) + 8 * j; } else { mm = t % BM; kk = t / BM + (256 / BM) * j; }
+      As[buf][kk][mm] = ra[j];
+    }
+#pragma unroll
+    for (int j = 0; j < B_PER; ++j) {
+      int nn, kk;
+      if (B_NC) { nn = t & 63; kk = (t >> 6) + 4 * j; } else { kk = t & 31; nn = (t >> 5) + 8 * j; }
+      Bs[buf][kk][nn] = rb[j];
+    }
+  };
+
+  const int nsteps = (g.K + BK - 1) / BK;
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (int s = 0; s < nsteps; ++s) {
+    const int buf = s & 1;
+    if (s + 1 < nsteps) load_tile((s + 1) * BK);       // in flight during the math below
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[TM];
+      if (TM == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+        av[0] = a.x; av[1] = a.y; av[TM > 2 ? 2 : 0] = a.z; av[TM > 2 ? 3 : 1] = a.w;
+      } else {
+        const float2 a = *reinterpret_cast<const float2*>(&As[buf][kk][ty * 2]);
+        av[0] = a.x; av[1] = a.y;
+      }
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
       const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
+    if (g.rowsum != nullptr && blockIdx.x == 0 && t < BM) {
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) rsum += As[buf][kk][t];
+    }
+    if (s + 1 < nsteps) store_tile(buf ^ 1);
     __syncthreads();
   }
+  if (g.rowsum != nullptr && blockIdx.x == 0 && t < BM && m0 + t < g.M) g.rowsum[m0 + t] += g.alpha * rsum;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
     if (m >= g.M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -104,14 +152,22 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
   }
 }
 
+template <int BM>
+inline void launch_gemm_bm(const GemmArgs& g, cudaStream_t st) {
+  dim3 grid((g.N + 63) / 64, (g.M + BM - 1) / BM);
+  const bool akc = (g.sa_k == 1), bnc = (g.sb_n == 1);
+  if (akc && bnc) gemm_kernel<BM, true, true><<<grid, 256, 0, st>>>(g);
+  else if (akc && !bnc) gemm_kernel<BM, true, false><<<grid, 256, 0, st>>>(g);
+  else if (!akc && bnc) gemm_kernel<BM, false, true><<<grid, 256, 0, st>>>(g);
+  else gemm_kernel<BM, false, false><<<grid, 256, 0, st>>>(g);
+}
+
 inline cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
-  dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
-  const bool akc = (g.sa_k == 1), bnc = (g.sb_n == 1);
-  if (akc && bnc) gemm_kernel<true, true><<<grid, 256, 0, st>>>(g);
-  else if (akc && !bnc) gemm_kernel<true, false><<<grid, 256, 0, st>>>(g);
-  else if (!akc && bnc) gemm_kernel<false, true><<<grid, 256, 0, st>>>(g);
-  else gemm_kernel<false, false><<<grid, 256, 0, st>>>(g);
+  // narrow tiles when 64-row tiles would leave most SMs idle
+  const long long blocks64 = static_cast<long long>((g.N + 63) / 64) * ((g.M + 63) / 64);
+  if (blocks64 < 96) launch_gemm_bm<32>(g, st);
+  else launch_gemm_bm<64>(g, st);
   count_launch();
   return cudaGetLastError();
 }
@@ -149,18 +205,32 @@ __global__ void fill_kernel(float* __restrict__ x, long long n, float v) {
   if (i < n) x[i] = v;
 }
 
-// g[c] += sum_r x[r][c]   (and optionally of x*y): bias / LayerNorm parameter gradients
-__global__ void colsum_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ y, long long ldy,
-                              float* __restrict__ g, int rows, int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+// g[c] += sum_r x[r][c]   (and optionally of x*y): bias / LayerNorm parameter gradients.
+// block = 32 columns x 8 row groups; rows are strided over the groups, then reduced through shared memory.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ y, long long ldy,
+              float* __restrict__ g, int rows, int cols) {
+  __shared__ float part[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float s = 0.f;
-  if (y == nullptr) {
-    for (int r = 0; r < rows; ++r) s += x[r * ldx + c];
-  } else {
-    for (int r = 0; r < rows; ++r) s = fmaf(x[r * ldx + c], y[r * ldy + c], s);
+  if (c < cols) {
+    if (y == nullptr) {
+#pragma unroll 4
+      for (int r = ry; r < rows; r += 8) s += x[r * ldx + c];
+    } else {
+#pragma unroll 4
+      for (int r = ry; r < rows; r += 8) s = fmaf(x[r * ldx + c], y[r * ldy + c], s);
+    }
   }
-  g[c] += s;
+  part[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += part[i][cx];
+    g[c] += v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
