@@ -51,15 +51,15 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D row-major bf16 tensor [rows][cols]; box = box_cols x box_rows, 128-byte swizzle (box_cols * 2 B == 128 B)
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols,
-                      uint32_t box_rows) {
+int make_tmap_16b_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols,
+                     uint32_t box_rows, bool is_f16) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(MPO_E_CUDA, "%s", "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(out, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -67,6 +67,11 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
     return MPO_E_CUDA;
   }
   return MPO_OK;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols,
+                      uint32_t box_rows) {
+  return make_tmap_16b_2d(out, base, rows, cols, box_cols, box_rows, false);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -179,7 +184,12 @@ int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, c
   p.drop_thr = static_cast<uint32_t>(drop_p * 256.f + 0.5f);
   p.drop_scale = p.drop_thr ? 256.f / static_cast<float>(256 - p.drop_thr) : 1.f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = check_cuda(launch_bag_fwd(tm_x, tm_w, p, num_sms(), st), "bag_fwd_kernel");
+  CUtensorMap tm_h = tm_x;   // placeholder when nothing is saved (never dereferenced by the kernel)
+  if (h_saved != nullptr) {
+    rc = make_tmap_16b_2d(&tm_h, h_saved, static_cast<uint64_t>(bag->total_rows), kD, 64, kTileM, true);
+    if (rc) return rc;
+  }
+  rc = check_cuda(launch_bag_fwd(tm_x, tm_w, tm_h, p, num_sms(), st), "bag_fwd_kernel");
   if (rc) return rc;
   return check_cuda(launch_bag_merge(bag->tile_prefix, part_ml, part_pool, pooled, lse, bag->num_slides, st),
                     "bag_merge_kernel");

@@ -1,11 +1,15 @@
 // Bag-pass forward for MCAT (reference: models/mcat/mcat.py:87 `H_bag = self.H(wsi)` and :97 co-attention).
 //
-// One persistent CTA per SM streams 128-patch tiles of the packed bf16 bag:
+// One persistent CTA per SM streams 128-patch tiles of the packed bf16 bag; everything GEMM-shaped runs on tcgen05:
 //   TMA (warp 0)  : X tile [128 x 1024] and W_H [256 x 1024] in 64-wide K blocks, 128B-swizzled, 3-stage ring
-//   MMA (warp 1)  : tcgen05.mma M=128 N=256 K=16, fp32 accumulators in TMEM, two accumulator stages
-//   epilogue (8 w): TMEM -> registers; +bias, ReLU, (dropout); six folded-query dots per patch (fp32);
-//                   H tile staged once in shared memory as fp16; tile-local softmax statistics;
-//                   pooled[6,256] += p^T H from the staged tile; per-tile (m, l, pooled) partial written.
+//   MMA (warp 1)  : H = X W_H^T, tcgen05.mma M=128 N=256 K=16, fp32 accumulators in TMEM, two accumulator stages
+//   epilogue (8 w): (1) TMEM -> registers; +bias, ReLU, (dropout); the H tile is written ONCE to shared memory as
+//                       fp16 in the canonical 128B-swizzle layout (and TMA-stored to HBM when the backward needs it);
+//                   (2) scores S[128 x 6] = H qk^T: a second tcgen05.mma straight from that staged tile
+//                       (A = H K-major, B = folded queries, N = 16), read back one patch row per thread;
+//                   (3) tile-local softmax statistics (warp shuffles), weights p written as a tiny fp16 B operand;
+//                   (4) pooled[6 x 256] = p^T H: a third tcgen05.mma on the SAME staged bytes, now read M-major
+//                       (A = H^T, N = 16, K = 128 patches), read back one feature per thread -> per-tile partial.
 // The K/V projections of the reference's nn.MultiheadAttention are folded away exactly:
 //   score_in = h_n . (W_k^T q_i)/sqrt(d)   (the b_k term is constant over n and cancels in the softmax)
 //   out_i    = W_v (sum_n a_in h_n) + b_v  (done in the tail on the pooled vector)
@@ -28,12 +32,11 @@ constexpr int kFwdThreads = 64 + kEpiThreads;
 struct FwdSmem {
   // offsets from the 1024-aligned base
   static constexpr int stages = 0;
-  static constexpr int staging = kStages * kStageBytes;                 // 147456
-  static constexpr int qk = staging + kStagingBytes;                    // fp32 [6][256]
-  static constexpr int bias = qk + kQ * kD * 4;                         // fp32 [256]
-  static constexpr int P = bias + kD * 4;                               // fp32 [128][8]
-  static constexpr int spart = P + kTileM * 8 * 4;                      // fp32 [128][8]
-  static constexpr int wred = spart + kTileM * 8 * 4;                   // fp32 [2][4][8]
+  static constexpr int staging = kStages * kStageBytes;                 // 147456: fp16 H tile [4][128][64]
+  static constexpr int qkB = staging + kStagingBytes;                   // fp16 [4 k-blocks][16 rows][64]  (8 KB)
+  static constexpr int Pb = qkB + 4 * 16 * 128;                         // fp16 [2 k-blocks][16 rows][64]  (4 KB)
+  static constexpr int bias = Pb + 2 * 16 * 128;                        // fp32 [256]
+  static constexpr int wred = bias + kD * 4;                            // fp32 [2][4][8]
   static constexpr int bars = wred + 2 * 4 * 8 * 4;                     // mbarriers
   static constexpr int tmem_slot = bars + 16 * 8;
   static constexpr int total = tmem_slot + 16;
@@ -47,7 +50,7 @@ constexpr int kFwdSmemBytes = FwdSmem::total + 1024;  // + slack for manual 1024
 template <int kC>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-               const BagFwdParams p) {
+               const __grid_constant__ CUtensorMap tm_h, const BagFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms, by pointer arithmetic so the compiler keeps the shared state space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -57,6 +60,8 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   uint64_t* empty_bar = bars + kStages;      // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+  uint64_t* s_bar = tempty_bar + 2;          // scores MMA done
+  uint64_t* d_bar = s_bar + 1;               // pooled MMA done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FwdSmem::tmem_slot);
 
   const int warp = threadIdx.x >> 5;
@@ -73,6 +78,8 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kEpiThreads / 32);
     }
+    mbar_init(s_bar, 1);
+    mbar_init(d_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -161,62 +168,67 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     // ---------------------------------------------------------------- epilogue warps (2..9)
     const int et = threadIdx.x - 64;           // 0..255
     const int qd = warp & 3;                   // TMEM lane quadrant this warp may access
-    const int ch = (warp - 2) >> 2;            // column half handled in phase 1
-    const int r = qd * 32 + lane;              // tile row (patch) owned in phase 1
-    float* qk_s = reinterpret_cast<float*>(smem + FwdSmem::qk);
+    const int ch = (warp - 2) >> 2;            // column half handled in step (1), feature half in step (4)
+    const int r = qd * 32 + lane;              // tile row (patch) owned in steps (1)-(3)
     float* bias_s = reinterpret_cast<float*>(smem + FwdSmem::bias);
-    float* P_s = reinterpret_cast<float*>(smem + FwdSmem::P);
-    float* spart_s = reinterpret_cast<float*>(smem + FwdSmem::spart);
     float* wmax_s = reinterpret_cast<float*>(smem + FwdSmem::wred);
     float* wsum_s = wmax_s + 4 * 8;
     uint8_t* staging = smem + FwdSmem::staging;
-    float* red_s = reinterpret_cast<float*>(staging);   // aliases the staged tile after phase 2
+    uint8_t* qkB = smem + FwdSmem::qkB;
+    uint8_t* Pb = smem + FwdSmem::Pb;
+    constexpr uint32_t idesc_s = umma_idesc(kTileM, 16, 0, 0, 0, 0);   // S  = H   qk^T : fp16, A K-major, B K-major
+    constexpr uint32_t idesc_d = umma_idesc(kTileM, 16, 0, 0, 1, 0);   // D2 = H^T p^T  : fp16, A M-major, B K-major
 
     bias_s[et] = p.bias[et];
+    // zero the two small B operands once: rows 6..15 (the N padding) stay zero for the whole kernel
+    for (int o = et * 16; o < 4 * 16 * 128 + 2 * 16 * 128; o += kEpiThreads * 16)
+      *reinterpret_cast<uint4*>(qkB + o) = make_uint4(0, 0, 0, 0);
     const uint32_t seed = p.seed_dev != nullptr ? (p.seed ^ __ldg(p.seed_dev)) : p.seed;
     int cur_slide = -1;
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const TileInfo ti = p.tile_info[t];
+      if (et == 32) tma_store_wait_read();      // the previous tile's H store no longer reads the staged tile
+      named_bar_sync(1, kEpiThreads);           // staging / B operands of the previous tile are free
       if (ti.slide != cur_slide) {
         cur_slide = ti.slide;
+        // folded queries of this slide -> fp16 B operand [16 x 256], K-major, 128B swizzle (4 blocks of 64 features)
         const float* src = p.qk + static_cast<size_t>(ti.slide) * kQ * kD;
 #pragma unroll
-        for (int j = 0; j < kQ; ++j) qk_s[et + j * 256] = src[et + j * 256];
+        for (int i = 0; i < kQ; ++i) {
+          const __half v = __float2half_rn(src[i * kD + et]);
+          *reinterpret_cast<__half*>(qkB + (et >> 6) * 2048 + i * 128 + ((((et & 63) >> 3) ^ i) << 4) + (et & 7) * 2) = v;
+        }
       }
-      named_bar_sync(1, kEpiThreads);   // qk/bias visible; previous tile's reduction buffer is free
 
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const uint32_t tphase = it & 1;
+      const uint32_t acc_col = tmem_base + as * kD;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
 
-      // ---- phase 1: accumulator -> h (fp32) -> score partials, fp16 tile in shared memory
-      float s[kQ];
-#pragma unroll
-      for (int i = 0; i < kQ; ++i) s[i] = 0.f;
+      // ---- (1) accumulator -> h = relu(acc + bias) (dropout) -> fp16 tile in shared memory
       const uint32_t grow = static_cast<uint32_t>(ti.row0 + r);
 #pragma unroll 1
       for (int c4 = 0; c4 < 4; ++c4) {
         const int col0 = ch * 128 + c4 * 32;
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + as * kD + col0, v);
+        tmem_ld_32x32b_x32(acc_col + (static_cast<uint32_t>(qd * 32) << 16) + col0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           float h[8];
           const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col0 + j);
           const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col0 + j + 4);
-          h[0] = __uint_as_float(v[j + 0]) + b0.x;
-          h[1] = __uint_as_float(v[j + 1]) + b0.y;
-          h[2] = __uint_as_float(v[j + 2]) + b0.z;
-          h[3] = __uint_as_float(v[j + 3]) + b0.w;
-          h[4] = __uint_as_float(v[j + 4]) + b1.x;
-          h[5] = __uint_as_float(v[j + 5]) + b1.y;
-          h[6] = __uint_as_float(v[j + 6]) + b1.z;
-          h[7] = __uint_as_float(v[j + 7]) + b1.w;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) h[e] = fmaxf(h[e], 0.f);
+          h[0] = fmaxf(__uint_as_float(v[j + 0]) + b0.x, 0.f);
+          h[1] = fmaxf(__uint_as_float(v[j + 1]) + b0.y, 0.f);
+          h[2] = fmaxf(__uint_as_float(v[j + 2]) + b0.z, 0.f);
+          h[3] = fmaxf(__uint_as_float(v[j + 3]) + b0.w, 0.f);
+          h[4] = fmaxf(__uint_as_float(v[j + 4]) + b1.x, 0.f);
+          h[5] = fmaxf(__uint_as_float(v[j + 5]) + b1.y, 0.f);
+          h[6] = fmaxf(__uint_as_float(v[j + 6]) + b1.z, 0.f);
+          h[7] = fmaxf(__uint_as_float(v[j + 7]) + b1.w, 0.f);
           if (p.drop_thr != 0) {
             // one 32-bit draw covers four consecutive features of this patch row
             const uint32_t base = (grow * kD + col0 + j) >> 2;
@@ -228,19 +240,6 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
               h[4 + e] = (((r1 >> (8 * e)) & 0xFFu) < p.drop_thr) ? 0.f : h[4 + e] * p.drop_scale;
             }
           }
-#pragma unroll
-          for (int i = 0; i < kQ; ++i) {
-            const float4 q0 = *reinterpret_cast<const float4*>(qk_s + i * kD + col0 + j);
-            const float4 q1 = *reinterpret_cast<const float4*>(qk_s + i * kD + col0 + j + 4);
-            s[i] = fmaf(h[0], q0.x, s[i]);
-            s[i] = fmaf(h[1], q0.y, s[i]);
-            s[i] = fmaf(h[2], q0.z, s[i]);
-            s[i] = fmaf(h[3], q0.w, s[i]);
-            s[i] = fmaf(h[4], q1.x, s[i]);
-            s[i] = fmaf(h[5], q1.y, s[i]);
-            s[i] = fmaf(h[6], q1.z, s[i]);
-            s[i] = fmaf(h[7], q1.w, s[i]);
-          }
           uint4 pk;
           pk.x = pack_f16x2(h[0], h[1]);
           pk.y = pack_f16x2(h[2], h[3]);
@@ -251,48 +250,62 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           *reinterpret_cast<uint4*>(staging + cb * (kTileM * 128) + r * 128 + ((jj ^ (r & 7)) << 4)) = pk;
         }
       }
-      // accumulator stage fully read: hand it back to the MMA warp
+      fence_proxy_async_smem();      // generic-proxy writes of the tile -> visible to UMMA / TMA (async proxy)
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-
-      if (ch == 1) {
-        *reinterpret_cast<float4*>(spart_s + r * 8) = make_float4(s[0], s[1], s[2], s[3]);
-        *reinterpret_cast<float2*>(spart_s + r * 8 + 4) = make_float2(s[4], s[5]);
-      }
       named_bar_sync(1, kEpiThreads);
 
-      // ---- tile-local softmax statistics (threads of column half 0 own one patch row each)
+      // ---- (2) S = H qk^T on the tensor core (16 K-steps of 16 features), into columns [0,16) of the drained stage
+      if (et == 0) {
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(staging), b0 = smem_u32(qkB);
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(acc_col, umma_desc_sw128(a0 + cb * (kTileM * 128) + k * 32, 16, 1024),
+                      umma_desc_sw128(b0 + cb * 2048 + k * 32, 16, 1024), idesc_s, (cb | k) != 0 ? 1u : 0u);
+        umma_commit(s_bar);
+      } else if (et == 32 && p.h_out != nullptr) {
+        // keep the activations for the backward pass: one TMA store per 64-feature block, straight from the tile
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) tma_store_2d(&tm_h, staging + cb * (kTileM * 128), cb * 64, ti.row0);
+        tma_store_commit();
+      }
+
+      // ---- (3) tile-local softmax statistics; one patch row per thread of column half 0
       const bool valid = r < ti.nvalid;
       if (ch == 0) {
-        const float4 o0 = *reinterpret_cast<const float4*>(spart_s + r * 8);
-        const float2 o1 = *reinterpret_cast<const float2*>(spart_s + r * 8 + 4);
-        s[0] += o0.x; s[1] += o0.y; s[2] += o0.z; s[3] += o0.w; s[4] += o1.x; s[5] += o1.y;
+        mbar_wait(s_bar, tphase);
+        tc_fence_after();
+        uint32_t sv[16];
+        tmem_ld_32x32b_x16(acc_col + (static_cast<uint32_t>(qd * 32) << 16), sv);
+        tmem_ld_wait();
+        float s[kQ];
 #pragma unroll
         for (int i = 0; i < kQ; ++i) {
+          s[i] = __uint_as_float(sv[i]);
           if (valid) p.scores[static_cast<size_t>(i) * p.total_rows + ti.row0 + r] = s[i];
           float m = valid ? s[i] : -INFINITY;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
           if (lane == 0) wmax_s[qd * 8 + i] = m;
         }
-      }
-      named_bar_sync(1, kEpiThreads);
-      if (ch == 0) {
-        float pr[8];
+        named_bar_sync(2, 128);
 #pragma unroll
         for (int i = 0; i < kQ; ++i) {
           const float m = fmaxf(fmaxf(wmax_s[i], wmax_s[8 + i]), fmaxf(wmax_s[16 + i], wmax_s[24 + i]));
-          pr[i] = valid ? __expf(s[i] - m) : 0.f;
-          float l = pr[i];
+          const float pr = valid ? __expf(s[i] - m) : 0.f;
+          const __half ph = __float2half_rn(pr);
+          // p^T as a B operand [16 queries x 128 patches], K-major (patches), 128B swizzle, 2 blocks of 64 patches
+          *reinterpret_cast<__half*>(Pb + (r >> 6) * 2048 + i * 128 + ((((r & 63) >> 3) ^ i) << 4) + (r & 7) * 2) = ph;
+          float l = __half2float(ph);               // the sum uses the weights the MMA will see
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
           if (lane == 0) wsum_s[qd * 8 + i] = l;
-          if (et == 0) p.part_ml[static_cast<size_t>(t) * 12 + i] = m;   // et==0 is warp 2 lane 0 (ch 0)
+          if (et == 0) p.part_ml[static_cast<size_t>(t) * 12 + i] = m;
         }
-        pr[6] = 0.f; pr[7] = 0.f;
-        *reinterpret_cast<float4*>(P_s + r * 8) = make_float4(pr[0], pr[1], pr[2], pr[3]);
-        *reinterpret_cast<float4*>(P_s + r * 8 + 4) = make_float4(pr[4], pr[5], pr[6], pr[7]);
+        fence_proxy_async_smem();
+        tc_fence_before();
       }
       named_bar_sync(1, kEpiThreads);
       if (et < kQ) {
@@ -300,52 +313,35 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             wsum_s[et] + wsum_s[8 + et] + wsum_s[16 + et] + wsum_s[24 + et];
       }
 
-      // ---- phase 2: pooled[i][d] += sum_n p[n][i] * h[n][d] from the staged fp16 tile
-      const int fg = et & 63;    // four features 4fg..4fg+3
-      const int pg = et >> 6;    // 32 patch rows pg*32..pg*32+31
-      float acc[kQ][4];
+      // ---- (4) pooled = p^T H on the tensor core: A = the same staged bytes read M-major (features), K = 128 patches
+      if (et == 0) {
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(staging), b0 = smem_u32(Pb);
 #pragma unroll
-      for (int i = 0; i < kQ; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+        for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16(acc_col + 16 + mh * 16,
+                      umma_desc_sw128(a0 + mh * 2 * (kTileM * 128) + kk * 2048, kTileM * 128, 1024),
+                      umma_desc_sw128(b0 + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), idesc_d, kk != 0 ? 1u : 0u);
+        umma_commit(d_bar);
+      }
+      mbar_wait(d_bar, tphase);
+      tc_fence_after();
       {
-        const int j16 = fg >> 1, cb = j16 >> 3, jj = j16 & 7;
-        const uint8_t* colbase = staging + cb * (kTileM * 128) + (fg & 1) * 8;
-        __half* hout = p.h_out;
-#pragma unroll 4
-        for (int nn = 0; nn < 32; ++nn) {
-          const int n = pg * 32 + nn;
-          const uint2 hv = *reinterpret_cast<const uint2*>(colbase + n * 128 + ((jj ^ (n & 7)) << 4));
-          const float4 p0 = *reinterpret_cast<const float4*>(P_s + n * 8);
-          const float2 p1 = *reinterpret_cast<const float2*>(P_s + n * 8 + 4);
-          const float2 h01 = unpack_f16x2(hv.x), h23 = unpack_f16x2(hv.y);
-          const float h0 = h01.x, h1 = h01.y, h2 = h23.x, h3 = h23.y;
-          const float pw[kQ] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y};
+        uint32_t dv[16];
+        tmem_ld_32x32b_x16(acc_col + (static_cast<uint32_t>(qd * 32) << 16) + 16 + ch * 16, dv);
+        tmem_ld_wait();
+        float* dst = p.part_pool + static_cast<size_t>(t) * (kQ * kD) + ch * 128 + qd * 32 + lane;
 #pragma unroll
-          for (int i = 0; i < kQ; ++i) {
-            acc[i][0] = fmaf(pw[i], h0, acc[i][0]);
-            acc[i][1] = fmaf(pw[i], h1, acc[i][1]);
-            acc[i][2] = fmaf(pw[i], h2, acc[i][2]);
-            acc[i][3] = fmaf(pw[i], h3, acc[i][3]);
-          }
-          if (hout != nullptr && n < ti.nvalid) {
-            *reinterpret_cast<uint2*>(hout + static_cast<size_t>(ti.row0 + n) * kD + fg * 4) = hv;
-          }
-        }
+        for (int i = 0; i < kQ; ++i) dst[i * kD] = __uint_as_float(dv[i]);
       }
-      named_bar_sync(1, kEpiThreads);    // every read of the staged tile is done -> reuse it for the reduction
-#pragma unroll
-      for (int i = 0; i < kQ; ++i) {
-        *reinterpret_cast<float4*>(red_s + pg * (kQ * kD) + i * kD + fg * 4) =
-            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      }
-      named_bar_sync(1, kEpiThreads);
-      float* dst = p.part_pool + static_cast<size_t>(t) * (kQ * kD);
-#pragma unroll
-      for (int j = 0; j < kQ; ++j) {
-        const int e = et + j * 256;
-        dst[e] = red_s[e] + red_s[kQ * kD + e] + red_s[2 * kQ * kD + e] + red_s[3 * kQ * kD + e];
-      }
-      // the barrier at the top of the next iteration orders these reads before the next phase-1 writes
+      // accumulator stage (H, S and pooled columns) fully consumed: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
+    if (et == 32) tma_store_wait_read();
   }
 
   tc_fence_before();
@@ -415,7 +411,8 @@ bag_merge_kernel(const int* __restrict__ tile_prefix,   // [B+1] first tile of e
 // host launchers (C++ side; the extern "C" surface is in api.cu)
 // ------------------------------------------------------------------------------------------------
 template <int kC>
-static cudaError_t launch_fwd_cluster(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const BagFwdParams& prm,
+static cudaError_t launch_fwd_cluster(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const CUtensorMap& tm_h,
+                                      const BagFwdParams& prm,
                                       int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   static int max_clusters = 0;
@@ -443,7 +440,7 @@ static cudaError_t launch_fwd_cluster(const CUtensorMap& tm_x, const CUtensorMap
   int clusters = (prm.num_tiles + kC - 1) / kC;
   if (clusters > max_clusters) clusters = max_clusters;
   cfg.gridDim = dim3(clusters * kC);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x, tm_w, prm);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x, tm_w, tm_h, prm);
   count_launch();
   return e;
 }
@@ -458,13 +455,13 @@ int fwd_cluster_size() {
   return c;
 }
 
-cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const BagFwdParams& prm, int num_sms,
-                           cudaStream_t stream) {
+cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const CUtensorMap& tm_h,
+                           const BagFwdParams& prm, int num_sms, cudaStream_t stream) {
   if (prm.num_tiles <= 0) return cudaSuccess;
   switch (fwd_cluster_size()) {
-    case 1: return launch_fwd_cluster<1>(tm_x, tm_w, prm, num_sms, stream);
-    case 4: return launch_fwd_cluster<4>(tm_x, tm_w, prm, num_sms, stream);
-    default: return launch_fwd_cluster<2>(tm_x, tm_w, prm, num_sms, stream);
+    case 1: return launch_fwd_cluster<1>(tm_x, tm_w, tm_h, prm, num_sms, stream);
+    case 4: return launch_fwd_cluster<4>(tm_x, tm_w, tm_h, prm, num_sms, stream);
+    default: return launch_fwd_cluster<2>(tm_x, tm_w, tm_h, prm, num_sms, stream);
   }
 }
 

@@ -14,8 +14,8 @@ extern unsigned long long g_launches;   // kernels launched by this library sinc
 inline void count_launch(int n = 1) { g_launches += n; }
 
 int fwd_cluster_size();   // CTAs per cluster of the forward bag kernel (1, 2 or 4; env MPO_FWD_CLUSTER)
-cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const BagFwdParams& prm, int num_sms,
-                           cudaStream_t stream);
+cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const CUtensorMap& tm_h,
+                           const BagFwdParams& prm, int num_sms, cudaStream_t stream);
 cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, const float* part_pool, float* pooled,
                              float* lse, int B, cudaStream_t stream);
 cudaError_t launch_bag_bwd_dz(const BagBwdDzParams& prm, cudaStream_t stream);
