@@ -132,13 +132,16 @@ bag_bwd_reduce_kernel(const int* __restrict__ tile_prefix, const float* __restri
   __shared__ float4 acc_s[4][64];
   const int tid = threadIdx.x, tg = tid >> 6, dq = tid & 63;
   const bool is_bias = static_cast<int>(blockIdx.x) >= B;
-  if (is_bias && blockIdx.y != 0) return;
   const int b = blockIdx.x, i = blockIdx.y;
-  const int t0 = is_bias ? 0 : tile_prefix[b];
+  // bias blocks: (gridDim.x - B) * 6 chunks share the tiles round-robin and finish with atomics
+  const int nchunk = (static_cast<int>(gridDim.x) - B) * kQ;
+  const int chunk = (static_cast<int>(blockIdx.x) - B) * kQ + i;
+  const int t0 = is_bias ? chunk * 4 : tile_prefix[b];
   const int t1 = is_bias ? num_tiles : tile_prefix[b + 1];
+  const int tstep = is_bias ? nchunk * 4 : 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-  for (int t = t0 + tg; t < t1; t += 4) {
+  for (int t = t0 + tg; t < t1; t += tstep) {
     const float* src = is_bias ? part_db + static_cast<size_t>(t) * kD : part_dqk + (static_cast<size_t>(t) * kQ + i) * kD;
     const float4 v = __ldg(reinterpret_cast<const float4*>(src) + dq);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -150,8 +153,8 @@ bag_bwd_reduce_kernel(const int* __restrict__ tile_prefix, const float* __restri
 #pragma unroll
     for (int g = 1; g < 4; ++g) { r.x += acc_s[g][tid].x; r.y += acc_s[g][tid].y; r.z += acc_s[g][tid].z; r.w += acc_s[g][tid].w; }
     if (is_bias) {
-      float* g4 = grad_bias + tid * 4;      // scalar: the caller's gradient view need not be 16-byte aligned
-      g4[0] += r.x; g4[1] += r.y; g4[2] += r.z; g4[3] += r.w;
+      float* g4 = grad_bias + tid * 4;
+      atomicAdd(g4 + 0, r.x); atomicAdd(g4 + 1, r.y); atomicAdd(g4 + 2, r.z); atomicAdd(g4 + 3, r.w);
     } else {
       reinterpret_cast<float4*>(dqk + (static_cast<size_t>(b) * kQ + i) * kD)[tid] = r;
     }
@@ -289,7 +292,7 @@ cudaError_t launch_bag_bwd_dz(const BagBwdDzParams& prm, cudaStream_t stream) {
 
 cudaError_t launch_bag_bwd_reduce(const int* tile_prefix, const float* part_dqk, const float* part_db, float* dqk,
                                   float* grad_bias, int B, int num_tiles, cudaStream_t stream) {
-  bag_bwd_reduce_kernel<<<dim3(B + 1, kQ), 256, 0, stream>>>(tile_prefix, part_dqk, part_db, dqk, grad_bias, B,
+  bag_bwd_reduce_kernel<<<dim3(B + 16, kQ), 256, 0, stream>>>(tile_prefix, part_dqk, part_db, dqk, grad_bias, B,
                                                             num_tiles);
   count_launch();
   return cudaGetLastError();

@@ -5,10 +5,10 @@
 //   MMA (warp 1)  : H = X W_H^T, tcgen05.mma M=128 N=256 K=16, fp32 accumulators in TMEM, two accumulator stages
 //   epilogue (8 w): (1) TMEM -> registers; +bias, ReLU, (dropout); the H tile is written ONCE to shared memory as
 //                       fp16 in the canonical 128B-swizzle layout (and TMA-stored to HBM when the backward needs it);
-//                   (2) scores S[128 x 6] = H qk^T: a second tcgen05.mma straight from that staged tile
-//                       (A = H K-major, B = folded queries, N = 16), read back one patch row per thread;
+//                   (2) the six folded-query dots per patch are taken in the same register pass, in fp32 (an fp16
+//                       tensor-core product would cost the attention map its 1e-3 parity on sharp softmaxes);
 //                   (3) tile-local softmax statistics (warp shuffles), weights p written as a tiny fp16 B operand;
-//                   (4) pooled[6 x 256] = p^T H: a third tcgen05.mma on the SAME staged bytes, now read M-major
+//                   (4) pooled[6 x 256] = p^T H: a second tcgen05.mma on the staged bytes, read M-major
 //                       (A = H^T, N = 16, K = 128 patches), read back one feature per thread -> per-tile partial.
 // The K/V projections of the reference's nn.MultiheadAttention are folded away exactly:
 //   score_in = h_n . (W_k^T q_i)/sqrt(d)   (the b_k term is constant over n and cancels in the softmax)
@@ -33,10 +33,11 @@ struct FwdSmem {
   // offsets from the 1024-aligned base
   static constexpr int stages = 0;
   static constexpr int staging = kStages * kStageBytes;                 // 147456: fp16 H tile [4][128][64]
-  static constexpr int qkB = staging + kStagingBytes;                   // fp16 [4 k-blocks][16 rows][64]  (8 KB)
-  static constexpr int Pb = qkB + 4 * 16 * 128;                         // fp16 [2 k-blocks][16 rows][64]  (4 KB)
-  static constexpr int bias = Pb + 2 * 16 * 128;                        // fp32 [256]
-  static constexpr int wred = bias + kD * 4;                            // fp32 [2][4][8]
+  static constexpr int Pb = staging + kStagingBytes;                    // fp16 [2 k-blocks][16 rows][64]  (4 KB)
+  static constexpr int qk = Pb + 2 * 16 * 128;                          // fp32 [6][256] folded queries of the slide
+  static constexpr int bias = qk + kQ * kD * 4;                         // fp32 [256]
+  static constexpr int spart = bias + kD * 4;                           // fp32 [128][8] score partials of column half 1
+  static constexpr int wred = spart + kTileM * 8 * 4;                   // fp32 [2][4][8]
   static constexpr int bars = wred + 2 * 4 * 8 * 4;                     // mbarriers
   static constexpr int tmem_slot = bars + 16 * 8;
   static constexpr int total = tmem_slot + 16;
@@ -60,8 +61,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   uint64_t* empty_bar = bars + kStages;      // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]
-  uint64_t* s_bar = tempty_bar + 2;          // scores MMA done
-  uint64_t* d_bar = s_bar + 1;               // pooled MMA done
+  uint64_t* d_bar = tempty_bar + 2;          // pooled MMA done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FwdSmem::tmem_slot);
 
   const int warp = threadIdx.x >> 5;
@@ -78,7 +78,6 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kEpiThreads / 32);
     }
-    mbar_init(s_bar, 1);
     mbar_init(d_bar, 1);
     fence_mbar_init();
   }
@@ -114,6 +113,11 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + FwdSmem::stages + stage * kStageBytes;
           const bool skip_w = (p.debug & 1) && it > 0;
+          if ((p.debug & 8) && it > 0) {            // timing experiment: no TMA traffic at all
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full_bar[stage], skip_w ? kABytes : kStageBytes);
           tma_load_2d(sa, &tm_x, &full_bar[stage], kb * kBK, row0, pol_stream);
           if ((p.debug & 4) && row_next >= 0) tma_prefetch_l2_2d(&tm_x, kb * kBK, row_next);
@@ -146,7 +150,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         for (int kb = 0; kb < kKBlocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (real) {
+          if (real && !(p.debug & 16)) {            // (debug bit 4: timing experiment without the main MMAs)
             const uint32_t a_addr = smem_u32(smem + FwdSmem::stages + stage * kStageBytes);
             const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
@@ -171,35 +175,30 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const int ch = (warp - 2) >> 2;            // column half handled in step (1), feature half in step (4)
     const int r = qd * 32 + lane;              // tile row (patch) owned in steps (1)-(3)
     float* bias_s = reinterpret_cast<float*>(smem + FwdSmem::bias);
+    float* qk_s = reinterpret_cast<float*>(smem + FwdSmem::qk);
+    float* spart_s = reinterpret_cast<float*>(smem + FwdSmem::spart);
     float* wmax_s = reinterpret_cast<float*>(smem + FwdSmem::wred);
     float* wsum_s = wmax_s + 4 * 8;
     uint8_t* staging = smem + FwdSmem::staging;
-    uint8_t* qkB = smem + FwdSmem::qkB;
     uint8_t* Pb = smem + FwdSmem::Pb;
-    constexpr uint32_t idesc_s = umma_idesc(kTileM, 16, 0, 0, 0, 0);   // S  = H   qk^T : fp16, A K-major, B K-major
     constexpr uint32_t idesc_d = umma_idesc(kTileM, 16, 0, 0, 1, 0);   // D2 = H^T p^T  : fp16, A M-major, B K-major
 
     bias_s[et] = p.bias[et];
-    // zero the two small B operands once: rows 6..15 (the N padding) stay zero for the whole kernel
-    for (int o = et * 16; o < 4 * 16 * 128 + 2 * 16 * 128; o += kEpiThreads * 16)
-      *reinterpret_cast<uint4*>(qkB + o) = make_uint4(0, 0, 0, 0);
+    // zero the small B operand once: rows 6..15 (the N padding) stay zero for the whole kernel
+    *reinterpret_cast<uint4*>(Pb + et * 16) = make_uint4(0, 0, 0, 0);
     const uint32_t seed = p.seed_dev != nullptr ? (p.seed ^ __ldg(p.seed_dev)) : p.seed;
     int cur_slide = -1;
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const TileInfo ti = p.tile_info[t];
       if (et == 32) tma_store_wait_read();      // the previous tile's H store no longer reads the staged tile
-      named_bar_sync(1, kEpiThreads);           // staging / B operands of the previous tile are free
       if (ti.slide != cur_slide) {
         cur_slide = ti.slide;
-        // folded queries of this slide -> fp16 B operand [16 x 256], K-major, 128B swizzle (4 blocks of 64 features)
         const float* src = p.qk + static_cast<size_t>(ti.slide) * kQ * kD;
 #pragma unroll
-        for (int i = 0; i < kQ; ++i) {
-          const __half v = __float2half_rn(src[i * kD + et]);
-          *reinterpret_cast<__half*>(qkB + (et >> 6) * 2048 + i * 128 + ((((et & 63) >> 3) ^ i) << 4) + (et & 7) * 2) = v;
-        }
+        for (int j = 0; j < kQ; ++j) qk_s[et + j * 256] = src[et + j * 256];
       }
+      named_bar_sync(1, kEpiThreads);           // qk visible; staging / P operand of the previous tile are free
 
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -208,7 +207,10 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
 
-      // ---- (1) accumulator -> h = relu(acc + bias) (dropout) -> fp16 tile in shared memory
+      // ---- (1)+(2) accumulator -> h = relu(acc + bias) (dropout); fp32 score partials; fp16 tile in shared memory
+      float s[kQ];
+#pragma unroll
+      for (int i = 0; i < kQ; ++i) s[i] = 0.f;
       const uint32_t grow = static_cast<uint32_t>(ti.row0 + r);
 #pragma unroll 1
       for (int c4 = 0; c4 < 4; ++c4) {
@@ -240,6 +242,19 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
               h[4 + e] = (((r1 >> (8 * e)) & 0xFFu) < p.drop_thr) ? 0.f : h[4 + e] * p.drop_scale;
             }
           }
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) {
+            const float4 q0 = *reinterpret_cast<const float4*>(qk_s + i * kD + col0 + j);
+            const float4 q1 = *reinterpret_cast<const float4*>(qk_s + i * kD + col0 + j + 4);
+            s[i] = fmaf(h[0], q0.x, s[i]);
+            s[i] = fmaf(h[1], q0.y, s[i]);
+            s[i] = fmaf(h[2], q0.z, s[i]);
+            s[i] = fmaf(h[3], q0.w, s[i]);
+            s[i] = fmaf(h[4], q1.x, s[i]);
+            s[i] = fmaf(h[5], q1.y, s[i]);
+            s[i] = fmaf(h[6], q1.z, s[i]);
+            s[i] = fmaf(h[7], q1.w, s[i]);
+          }
           uint4 pk;
           pk.x = pack_f16x2(h[0], h[1]);
           pk.y = pack_f16x2(h[2], h[3]);
@@ -250,22 +265,14 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           *reinterpret_cast<uint4*>(staging + cb * (kTileM * 128) + r * 128 + ((jj ^ (r & 7)) << 4)) = pk;
         }
       }
+      if (ch == 1) {
+        *reinterpret_cast<float4*>(spart_s + r * 8) = make_float4(s[0], s[1], s[2], s[3]);
+        *reinterpret_cast<float2*>(spart_s + r * 8 + 4) = make_float2(s[4], s[5]);
+      }
       fence_proxy_async_smem();      // generic-proxy writes of the tile -> visible to UMMA / TMA (async proxy)
       tc_fence_before();
       named_bar_sync(1, kEpiThreads);
-
-      // ---- (2) S = H qk^T on the tensor core (16 K-steps of 16 features), into columns [0,16) of the drained stage
-      if (et == 0) {
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(staging), b0 = smem_u32(qkB);
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(acc_col, umma_desc_sw128(a0 + cb * (kTileM * 128) + k * 32, 16, 1024),
-                      umma_desc_sw128(b0 + cb * 2048 + k * 32, 16, 1024), idesc_s, (cb | k) != 0 ? 1u : 0u);
-        umma_commit(s_bar);
-      } else if (et == 32 && p.h_out != nullptr) {
+      if (et == 32 && p.h_out != nullptr) {
         // keep the activations for the backward pass: one TMA store per 64-feature block, straight from the tile
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) tma_store_2d(&tm_h, staging + cb * (kTileM * 128), cb * 64, ti.row0);
@@ -275,15 +282,11 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       // ---- (3) tile-local softmax statistics; one patch row per thread of column half 0
       const bool valid = r < ti.nvalid;
       if (ch == 0) {
-        mbar_wait(s_bar, tphase);
-        tc_fence_after();
-        uint32_t sv[16];
-        tmem_ld_32x32b_x16(acc_col + (static_cast<uint32_t>(qd * 32) << 16), sv);
-        tmem_ld_wait();
-        float s[kQ];
+        const float4 o0 = *reinterpret_cast<const float4*>(spart_s + r * 8);
+        const float2 o1 = *reinterpret_cast<const float2*>(spart_s + r * 8 + 4);
+        s[0] += o0.x; s[1] += o0.y; s[2] += o0.z; s[3] += o0.w; s[4] += o1.x; s[5] += o1.y;
 #pragma unroll
         for (int i = 0; i < kQ; ++i) {
-          s[i] = __uint_as_float(sv[i]);
           if (valid) p.scores[static_cast<size_t>(i) * p.total_rows + ti.row0 + r] = s[i];
           float m = valid ? s[i] : -INFINITY;
 #pragma unroll
@@ -321,7 +324,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         for (int mh = 0; mh < 2; ++mh)
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_bf16(acc_col + 16 + mh * 16,
+            umma_bf16(acc_col + mh * 16,
                       umma_desc_sw128(a0 + mh * 2 * (kTileM * 128) + kk * 2048, kTileM * 128, 1024),
                       umma_desc_sw128(b0 + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), idesc_d, kk != 0 ? 1u : 0u);
         umma_commit(d_bar);
@@ -330,7 +333,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       tc_fence_after();
       {
         uint32_t dv[16];
-        tmem_ld_32x32b_x16(acc_col + (static_cast<uint32_t>(qd * 32) << 16) + 16 + ch * 16, dv);
+        tmem_ld_32x32b_x16(acc_col + (static_cast<uint32_t>(qd * 32) << 16) + ch * 16, dv);
         tmem_ld_wait();
         float* dst = p.part_pool + static_cast<size_t>(t) * (kQ * kD) + ch * 128 + qd * 32 + lane;
 #pragma unroll
