@@ -298,10 +298,15 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         for (int i = 0; i < kQ; ++i) {
           const float m = fmaxf(fmaxf(wmax_s[i], wmax_s[8 + i]), fmaxf(wmax_s[16 + i], wmax_s[24 + i]));
           const float pr = valid ? __expf(s[i] - m) : 0.f;
+          // p^T as a B operand [16 rows x 128 patches], K-major (patches), 128B swizzle, 2 blocks of 64 patches.
+          // fp16 has 11 bits: rows 0..5 carry the leading part, rows 6..11 the remainder (the N = 16 tile has room),
+          // so the pooled sum sees ~22-bit weights and tiny bags keep their 1e-3 parity.
           const __half ph = __float2half_rn(pr);
-          // p^T as a B operand [16 queries x 128 patches], K-major (patches), 128B swizzle, 2 blocks of 64 patches
-          *reinterpret_cast<__half*>(Pb + (r >> 6) * 2048 + i * 128 + ((((r & 63) >> 3) ^ i) << 4) + (r & 7) * 2) = ph;
-          float l = __half2float(ph);               // the sum uses the weights the MMA will see
+          const __half pl = __float2half_rn(pr - __half2float(ph));
+          uint8_t* pcol = Pb + (r >> 6) * 2048 + (r & 7) * 2;
+          *reinterpret_cast<__half*>(pcol + i * 128 + ((((r & 63) >> 3) ^ i) << 4)) = ph;
+          *reinterpret_cast<__half*>(pcol + (i + 6) * 128 + ((((r & 63) >> 3) ^ ((i + 6) & 7)) << 4)) = pl;
+          float l = __half2float(ph) + __half2float(pl);   // the sum uses the weights the MMA will see
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
           if (lane == 0) wsum_s[qd * 8 + i] = l;
@@ -337,7 +342,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         tmem_ld_wait();
         float* dst = p.part_pool + static_cast<size_t>(t) * (kQ * kD) + ch * 128 + qd * 32 + lane;
 #pragma unroll
-        for (int i = 0; i < kQ; ++i) dst[i * kD] = __uint_as_float(dv[i]);
+        for (int i = 0; i < kQ; ++i) dst[i * kD] = __uint_as_float(dv[i]) + __uint_as_float(dv[i + 6]);
       }
       // accumulator stage (H, S and pooled columns) fully consumed: hand it back to the MMA warp
       tc_fence_before();

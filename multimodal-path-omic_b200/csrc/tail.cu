@@ -2,6 +2,7 @@
 // tail_kernels.cuh, batched over the B slides of a step, all on the caller's stream.  Mirrors, stage by stage,
 // what the reference modules compute on the 6 omic tokens (file:line given at each stage).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -41,7 +42,10 @@ struct Ws {
   long long bh[2], bU[2], bg[2], bgh[2], bo[2], kp, cat130, bf2;   // bilinear fusion
   long long logits;
   // gradients / scratch
-  long long dlogits, dh, dcat, dz1, dz2, dhp[2], dxa, dxb, dtok[2], s768, s512, s256a, s256b, s256c, dG, dqp;
+  long long dlogits, dh, dcat, dz1, dz2, dhp[2], dtok[2], dG, dqp, dhc, dv;
+  // per-branch scratch (0 = path / main stream, 1 = omic / second stream): the branches run concurrently
+  long long dxa[2], dxb[2], dzr[2], dmid[2], s768[2], s512[2], s256a[2], s256b[2], s256c[2];
+  long long snn_dz1[MPO_Q], snn_dz2[MPO_Q], snn_dh[MPO_Q];
   long long bV, bdkp, bdcat130, bdo[2], bdgh[2], bdh[2], bdz[2], bdx[2];
   Layout lay;
 };
@@ -96,20 +100,66 @@ void build_layout(const mpo_model* m, int B, Ws& w) {
   w.dh = L.add("dh", (long long)B * E);
   w.dcat = L.add("dcat", (long long)B * 2 * E); w.dz1 = L.add("dz1", (long long)B * E); w.dz2 = L.add("dz2", (long long)B * E);
   w.dhp[0] = L.add("dhp_path", (long long)B * E); w.dhp[1] = L.add("dhp_omic", (long long)B * E);
-  w.dxa = L.add("dxa", R * E); w.dxb = L.add("dxb", R * E);
   w.dtok[0] = L.add("dtok_path", R * E); w.dtok[1] = L.add("dtok_omic", R * E);
-  w.s768 = L.add("s768", R * 3 * E); w.s512 = L.add("s512", R * FF);
-  w.s256a = L.add("s256a", R * E); w.s256b = L.add("s256b", R * E); w.s256c = L.add("s256c", R * E);
-  w.dG = L.add("dG", R * E); w.dqp = L.add("dqp", R * E);
+  for (int s = 0; s < 2; ++s) {
+    auto A = [&](const char* t, long long n) { snprintf(nm, sizeof nm, "scr%d_%s", s, t); return L.add(nm, n); };
+    w.dxa[s] = A("dxa", R * E); w.dxb[s] = A("dxb", R * E); w.dzr[s] = A("dzr", (long long)B * E);
+    w.dmid[s] = A("dmid", R * E); w.s768[s] = A("s768", R * 3 * E); w.s512[s] = A("s512", R * FF);
+    w.s256a[s] = A("s256a", R * E); w.s256b[s] = A("s256b", R * E); w.s256c[s] = A("s256c", R * E);
+  }
+  for (int i = 0; i < MPO_Q; ++i) {
+    snprintf(nm, sizeof nm, "snn_dz1_%d", i); w.snn_dz1[i] = L.add(nm, (long long)B * E);
+    snprintf(nm, sizeof nm, "snn_dz2_%d", i); w.snn_dz2[i] = L.add(nm, (long long)B * E);
+    snprintf(nm, sizeof nm, "snn_dh_%d", i); w.snn_dh[i] = L.add(nm, (long long)B * E);
+  }
+  w.dG = L.add("dG", R * E); w.dqp = L.add("dqp", R * E); w.dhc = L.add("dhc", R * E); w.dv = L.add("dv", R * E);
 }
 
 // ---------------------------------------------------------------------------------------------- op helpers
+// Auxiliary streams: the path and omic branches of the tail are independent, and weight-gradient GEMMs are off the
+// critical path of the backward pass.  Everything forks from / joins back into the caller's stream through
+// events, so the whole tail is still "stream-ordered on `stream`" for the caller and is CUDA-graph capturable.
+struct StreamPool {
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // 0: second branch, 1: wgrads of main, 2: wgrads of second
+  cudaEvent_t ev[64] = {};
+  int next = 0;
+  int state = 0;   // 0 = not created, 1 = ready, -1 = disabled
+};
+StreamPool& stream_pool() {
+  static StreamPool pools[32];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  StreamPool& p = pools[dev & 31];
+  if (p.state == 0) {
+    const char* env = getenv("MPO_TAIL_STREAMS");
+    if (env && atoi(env) == 0) { p.state = -1; return p; }
+    bool ok = true;
+    for (auto& s : p.aux) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& e : p.ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    p.state = ok ? 1 : -1;
+  }
+  return p;
+}
+
 struct Ctx {
-  cudaStream_t st;
+  cudaStream_t st;             // compute stream of this branch
+  cudaStream_t wst = nullptr;  // weight-gradient stream of this branch (nullptr: same as st)
+  int sb = 0;                  // scratch set of this branch
   cudaError_t err = cudaSuccess;
   const char* where = "";
   void chk(cudaError_t e, const char* w) { if (err == cudaSuccess && e != cudaSuccess) { err = e; where = w; } }
 };
+// `to` waits for everything submitted to `from` so far
+void dep(Ctx& c, cudaStream_t from, cudaStream_t to) {
+  if (from == to || from == nullptr || to == nullptr) return;
+  StreamPool& p = stream_pool();
+  cudaEvent_t e = p.ev[p.next];
+  p.next = (p.next + 1) & 63;
+  c.chk(cudaEventRecord(e, from), "event record");
+  c.chk(cudaStreamWaitEvent(to, e, 0), "stream wait");
+}
+// the compute stream waits for this branch's pending weight-gradient GEMMs (before their inputs are overwritten)
+void join_w(Ctx& c) { if (c.wst) dep(c, c.wst, c.st); }
 
 inline unsigned nblk(long long n, int t = 256) { return static_cast<unsigned>((n + t - 1) / t); }
 
@@ -137,7 +187,9 @@ void lin_bwd(Ctx& c, const float* dz, long long lddz, const float* x, long long 
   }
   if (L.gw != nullptr) {     // gw += dz^T x, with gb += rowsum(dz^T) fused into the same kernel
     GemmArgs g{dz, 1, lddz, x, ldx, 1, L.gw, in, nullptr, out, in, rows, 1.f, 1, ACT_NONE, L.gb};
-    c.chk(launch_gemm(g, c.st), "lin_bwd.wgrad");
+    cudaStream_t ws_ = c.wst ? c.wst : c.st;
+    if (c.wst) dep(c, c.st, c.wst);          // dz is complete on the compute stream
+    c.chk(launch_gemm(g, ws_), "lin_bwd.wgrad");
   } else if (L.gb != nullptr) {
     colsum_kernel<<<nblk(out, 32), 256, 0, c.st>>>(dz, lddz, nullptr, 0, L.gb, rows, out); count_launch();
     c.chk(cudaGetLastError(), "lin_bwd.bgrad");
@@ -168,8 +220,10 @@ void ln_bwd(Ctx& c, const float* dy, const mpo_norm& N, const float* xh, const f
   layernorm_bwd_kernel<<<nblk(rows, 8), 256, 0, c.st>>>(dy, N.g, xh, rs, dx, rows); count_launch();
   c.chk(cudaGetLastError(), "ln_bwd");
   if (N.gg != nullptr) {
-    colsum_kernel<<<nblk(E, 32), 256, 0, c.st>>>(dy, E, xh, E, N.gg, rows, E); count_launch();
-    colsum_kernel<<<nblk(E, 32), 256, 0, c.st>>>(dy, E, nullptr, 0, N.gb, rows, E); count_launch();
+    cudaStream_t ws_ = c.wst ? c.wst : c.st;
+    if (c.wst) dep(c, c.st, c.wst);
+    colsum_kernel<<<nblk(E, 32), 256, 0, ws_>>>(dy, E, xh, E, N.gg, rows, E); count_launch();
+    colsum_kernel<<<nblk(E, 32), 256, 0, ws_>>>(dy, E, nullptr, 0, N.gb, rows, E); count_launch();
     c.chk(cudaGetLastError(), "ln_bwd.params");
   }
 }
@@ -187,27 +241,25 @@ void enc_fwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, float* ws, con
   lin_fwd(c, ws + b.f, FF, P.linear2, E, FF, ws + b.f2, E, R, ACT_NONE);
   ln_fwd(c, ws + b.y1, ws + b.f2, P.norm2, ws + b.y2, ws + b.xh2, ws + b.rs2, R);
 }
-// dy2 -> dx (written to dx_out).  Uses scratch s768/s512/s256a/s256b.
+// dy2 -> dx (written to dx_out).  Scratch of branch c.sb; every gradient that a pending weight-gradient GEMM still
+// reads keeps its own buffer until the next join_w().
 void enc_bwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, const Ws& w, float* ws, const float* x,
              const float* dy2, float* dx_out, int B) {
   const int R = 6 * B;
-  float* dr2 = ws + w.s256a;       // gradient of (y1 + f2)
+  join_w(c);
+  float* dr2 = ws + w.s256a[c.sb];     // gradient of (y1 + f2)
   ln_bwd(c, dy2, P.norm2, ws + b.xh2, ws + b.rs2, dr2, R);
-  float* df = ws + w.s512;
-  {   // linear2: dz = dr2
-    GemmArgs g{dr2, E, 1, P.linear2.w, FF, 1, df, FF, nullptr, R, FF, E, 1.f, 0, ACT_NONE, nullptr};
-    c.chk(launch_gemm(g, c.st), "enc.lin2.dgrad");
-    lin_bwd(c, dr2, E, ws + b.f, FF, P.linear2, E, FF, nullptr, 0, R, false);
-  }
+  float* df = ws + w.s512[c.sb];
+  lin_bwd(c, dr2, E, ws + b.f, FF, P.linear2, E, FF, df, FF, R, false);
   act_bwd(c, df, FF, ws + b.f, FF, df, FF, R, FF, ACT_RELU);
-  float* dy1 = ws + w.s256b;
+  float* dy1 = ws + w.s256b[c.sb];
   lin_bwd(c, df, FF, ws + b.y1, E, P.linear1, FF, E, dy1, E, R, false);
   add(c, dy1, dr2, dy1, (long long)R * E);
-  float* dr1 = ws + w.s256a;       // gradient of (x + sa); dr2 no longer needed
+  float* dr1 = ws + w.s256c[c.sb];     // gradient of (x + sa)
   ln_bwd(c, dy1, P.norm1, ws + b.xh1, ws + b.rs1, dr1, R);
-  float* dctx = ws + w.s256b;
+  float* dctx = ws + w.dxb[c.sb];
   lin_bwd(c, dr1, E, ws + b.ctx, E, P.out_proj, E, E, dctx, E, R, false);
-  float* dqkv = ws + w.s768;
+  float* dqkv = ws + w.s768[c.sb];
   mha6_bwd_kernel<<<nblk((long long)B * 8, 8), 256, 0, c.st>>>(ws + b.qkv, ws + b.probs, dctx, dqkv, B); count_launch();
   c.chk(cudaGetLastError(), "mha6_bwd");
   lin_bwd(c, dqkv, 3 * E, x, E, P.in_proj, 3 * E, E, dx_out, E, R, false);
@@ -228,14 +280,16 @@ void pool_fwd(Ctx& c, const mpo_pool_head& P, const PoolBuf& b, float* ws, const
 void pool_bwd(Ctx& c, const mpo_pool_head& P, const PoolBuf& b, const Ws& w, float* ws, const float* x, const float* dh,
               float* dhp, float* dx_out, int B) {
   const int R = 6 * B;
-  float* dzr = ws + w.dz1;   // reuse a [B,256] scratch
+  join_w(c);
+  float* dzr = ws + w.dzr[c.sb];
   act_bwd(c, dh, E, ws + b.h, E, dzr, E, B, E, ACT_RELU);
   lin_bwd(c, dzr, E, ws + b.hp, E, P.rho, E, E, dhp, E, B, false);
-  pool_bwd_kernel<<<B, 256, 0, c.st>>>(x, ws + b.a, ws + b.b, P.att_c.w, ws + b.w, dhp, dx_out, ws + w.dxa, ws + w.dxb,
-                                       P.att_c.gw, P.att_c.gb); count_launch();
+  pool_bwd_kernel<<<B, 256, 0, c.st>>>(x, ws + b.a, ws + b.b, P.att_c.w, ws + b.w, dhp, dx_out, ws + w.dxa[c.sb],
+                                       ws + w.dxb[c.sb], P.att_c.gw, P.att_c.gb); count_launch();
   c.chk(cudaGetLastError(), "pool_bwd");
-  lin_bwd(c, ws + w.dxa, E, x, E, P.att_a, E, E, dx_out, E, R, true);
-  lin_bwd(c, ws + w.dxb, E, x, E, P.att_b, E, E, dx_out, E, R, true);
+  lin_bwd(c, ws + w.dxa[c.sb], E, x, E, P.att_a, E, E, dx_out, E, R, true);
+  lin_bwd(c, ws + w.dxb[c.sb], E, x, E, P.att_b, E, E, dx_out, E, R, true);
+  join_w(c);                 // dxa / dxb are reused right away by the encoder backward
 }
 
 // ---------------------------------------------------------------------------------------------- CAG (NaCAGaT)
@@ -253,10 +307,13 @@ void cag_fwd(Ctx& c, const mpo_cag& P, const Ws& w, float* ws, const float* Q, c
   lin_fwd(c, ws + w.cag_m, E, P.fc_c, E, E, ws + w.cag_C, E, R, ACT_ELU);
 }
 // dC -> dQ accumulated into dQ_acc, dQh written to dQh_out
-void cag_bwd(Ctx& c, const mpo_cag& P, const Ws& w, float* ws, const float* Q, const float* Qh, const float* dC,
+void cag_bwd(Ctx& c0, const mpo_cag& P, const Ws& w, float* ws, const float* Q, const float* Qh, const float* dC,
              float* dQ_acc, float* dQh_out, int R) {
   const long long n = (long long)R * E;
-  float* t0 = ws + w.s256a; float* t1 = ws + w.s256b; float* t2 = ws + w.s256c;
+  join_w(c0);
+  Ctx c = c0;                // scratch is recycled aggressively here: keep the weight gradients on the compute stream
+  c.wst = nullptr;
+  float* t0 = ws + w.s256a[0]; float* t1 = ws + w.s256b[0]; float* t2 = ws + w.s256c[0];
   act_bwd(c, dC, E, ws + w.cag_C, E, t0, E, R, E, ACT_ELU);
   lin_bwd(c, t0, E, ws + w.cag_m, E, P.fc_c, E, E, t1, E, R, false);          // t1 = dm
   mul(c, t1, ws + w.cag_Ee, t0, n);                                            // t0 = dGg
@@ -271,6 +328,7 @@ void cag_bwd(Ctx& c, const mpo_cag& P, const Ws& w, float* ws, const float* Q, c
   lin_bwd(c, t2, E, Qh, E, P.fc2, E, E, dQh_out, E, R, true);
   act_bwd(c, t1, E, ws + w.cag_f1, E, t2, E, R, E, ACT_ELU);
   lin_bwd(c, t2, E, Q, E, P.fc1, E, E, dQ_acc, E, R, true);
+  c0.chk(c.err, c.where);
 }
 
 // ---------------------------------------------------------------------------------------------- bilinear fusion
@@ -303,6 +361,44 @@ void bil_side_bwd(Ctx& c, const mpo_lin& Lh, const mpo_lin& Lz, const mpo_lin& L
   GemmArgs g2{ws + w.bV, (long long)BH * E, 1, Lz.w, E, 1, dxb, E, nullptr, B, E, BH * E, 1.f, 1, ACT_NONE, nullptr};
   c.chk(launch_gemm(g2, c.st), "bil.dxb");
   lin_bwd(c, ws + w.bdh[s], BH, xa, E, Lh, BH, E, dxa, E, B, true);
+}
+
+// main context + (optional) second-branch context sharing the caller's stream as the join point
+struct Branches {
+  Ctx main, second;
+  bool par;
+};
+Branches make_branches(cudaStream_t stream, bool async_wgrad) {
+  StreamPool& p = stream_pool();
+  Branches b;
+  b.par = p.state == 1;
+  b.main.st = stream;
+  b.main.sb = 0;
+  b.second.sb = 1;
+  if (b.par) {
+    b.second.st = p.aux[0];
+    b.main.wst = async_wgrad ? p.aux[1] : nullptr;
+    b.second.wst = async_wgrad ? p.aux[2] : nullptr;
+  } else {
+    b.second.st = stream;     // everything in program order on the caller's stream
+  }
+  return b;
+}
+// second branch (and both weight-gradient streams) start after everything already on the caller's stream
+void fork(Branches& b) {
+  if (!b.par) return;
+  dep(b.main, b.main.st, b.second.st);
+  if (b.main.wst) dep(b.main, b.main.st, b.main.wst);
+  if (b.second.wst) dep(b.main, b.main.st, b.second.wst);
+}
+// the caller's stream waits for the second branch and for every pending weight gradient
+void join(Branches& b) {
+  if (b.par) {
+    if (b.second.wst) dep(b.main, b.second.wst, b.main.st);
+    if (b.main.wst) dep(b.main, b.main.wst, b.main.st);
+    dep(b.main, b.second.st, b.main.st);
+  }
+  b.main.chk(b.second.err, b.second.where);
 }
 
 int finish(Ctx& c) {
@@ -361,14 +457,20 @@ int mpo_tail_pre_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   const int B = io->num_slides, R = 6 * B;
   Ws w; build_layout(m, B, w);
   float* ws = io->ws;
-  Ctx c{static_cast<cudaStream_t>(stream)};
-  // SNN encoders (mcat.py:32-45,90-92): G_bag row (b, i) = ELU(W2 ELU(W1 x_i + b1) + b2)
-  for (int i = 0; i < MPO_Q; ++i) {
+  Branches br = make_branches(static_cast<cudaStream_t>(stream), false);
+  Ctx& c = br.main;
+  // SNN encoders (mcat.py:32-45,90-92): G_bag row (b, i) = ELU(W2 ELU(W1 x_i + b1) + b2); six independent chains,
+  // alternated over the two branch streams
+  for (int i = 0; i < MPO_Q; ++i)
     if (!io->omics[i]) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_fwd: omics pointer is NULL");
+  fork(br);
+  for (int i = 0; i < MPO_Q; ++i) {
+    Ctx& ci = (i & 1) ? br.second : br.main;
     const int d = m->omic_dims[i];
-    lin_fwd(c, io->omics[i], d, m->snn[i][0], E, d, ws + w.snn_h[i], E, B, ACT_ELU);
-    lin_fwd(c, ws + w.snn_h[i], E, m->snn[i][1], E, E, ws + w.G + i * E, 6 * E, B, ACT_ELU);
+    lin_fwd(ci, io->omics[i], d, m->snn[i][0], E, d, ws + w.snn_h[i], E, B, ACT_ELU);
+    lin_fwd(ci, ws + w.snn_h[i], E, m->snn[i][1], E, E, ws + w.G + i * E, 6 * E, B, ACT_ELU);
   }
+  join(br);
   // query in-projection (rows 0..255 of co_attention.in_proj): q = W_q g + b_q
   lin_fwd(c, ws + w.G, E, sub(m->coattn_in, 0, E), E, E, io->qp, E, R, ACT_NONE);
   // key fold: qk[r][d] = sum_e q[r][e] W_k[e][d] / sqrt(256)
@@ -395,23 +497,27 @@ int mpo_tail_post_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   const int B = io->num_slides, R = 6 * B, K = m->n_classes;
   Ws w; build_layout(m, B, w);
   float* ws = io->ws;
-  Ctx c{static_cast<cudaStream_t>(stream)};
-  // value and output projections on the pooled vectors (folded form of mcat.py:97)
+  Branches br = make_branches(static_cast<cudaStream_t>(stream), false);
+  Ctx& c = br.main;
+  Ctx& co = br.second;
+  if (m->variant == MPO_VARIANT_NACAGAT && !io->qp) return fail(MPO_E_ARG, "%s", "mpo_tail_post_fwd: qp is NULL (NaCAGaT)");
+  fork(br);
+  // omic branch (second stream): omic transformer + pooling (mcat.py:102,111-115) -- independent of the bag
+  enc_fwd(co, m->omic_tr[0], w.enc[2], ws, ws + w.G, B);
+  enc_fwd(co, m->omic_tr[1], w.enc[3], ws, ws + w.enc[2].y2, B);
+  pool_fwd(co, m->omic_pool, w.pool[1], ws, ws + w.enc[3].y2, io->att_omic, B);
+  // path branch: value and output projections on the pooled vectors (folded form of mcat.py:97)
   lin_fwd(c, io->pooled, E, sub(m->coattn_in, 2 * E, E), E, E, ws + w.v, E, R, ACT_NONE);
   lin_fwd(c, ws + w.v, E, m->coattn_out, E, E, ws + w.hc, E, R, ACT_NONE);
   if (m->variant == MPO_VARIANT_NACAGAT) {
-    if (!io->qp) return fail(MPO_E_ARG, "%s", "mpo_tail_post_fwd: qp is NULL (NaCAGaT)");
     cag_fwd(c, m->cag, w, ws, ws + w.G, io->qp, R);                      // blocks.py:110
     add(c, ws + w.hc, ws + w.cag_C, ws + w.hc, (long long)R * E);        // blocks.py:111
   }
-  // set-based transformers (mcat.py:101-102)
+  // path transformer + pooling (mcat.py:101,105-109)
   enc_fwd(c, m->path_tr[0], w.enc[0], ws, ws + w.hc, B);
   enc_fwd(c, m->path_tr[1], w.enc[1], ws, ws + w.enc[0].y2, B);
-  enc_fwd(c, m->omic_tr[0], w.enc[2], ws, ws + w.G, B);
-  enc_fwd(c, m->omic_tr[1], w.enc[3], ws, ws + w.enc[2].y2, B);
-  // global attention pooling (mcat.py:105-115)
   pool_fwd(c, m->path_pool, w.pool[0], ws, ws + w.enc[1].y2, io->att_path, B);
-  pool_fwd(c, m->omic_pool, w.pool[1], ws, ws + w.enc[3].y2, io->att_omic, B);
+  join(br);
   const float* hpath = ws + w.pool[0].h;
   const float* homic = ws + w.pool[1].h;
   const float* hfin;
@@ -458,7 +564,9 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
   const int B = io->num_slides, R = 6 * B, K = m->n_classes;
   Ws w; build_layout(m, B, w);
   float* ws = io->ws;
-  Ctx c{static_cast<cudaStream_t>(stream)};
+  Branches br = make_branches(static_cast<cudaStream_t>(stream), true);
+  Ctx c = br.main;            // fusion / head part: synchronous weight gradients on the caller's stream
+  c.wst = nullptr;
   surv_head_bwd_kernel<<<nblk(B, 128), 128, 0, c.st>>>(io->hazards, io->S, io->Y, dhaz, dS, dY, ws + w.dlogits, B, K); count_launch();
   c.chk(cudaGetLastError(), "surv_head_bwd");
   const float* hpath = ws + w.pool[0].h;
@@ -470,7 +578,7 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
     act_bwd(c, ws + w.dh, E, ws + w.z2, E, ws + w.dz2, E, B, E, ACT_RELU);
     lin_bwd(c, ws + w.dz2, E, ws + w.z1, E, m->fusion2, E, E, ws + w.dh, E, B, false);
     act_bwd(c, ws + w.dh, E, ws + w.z1, E, ws + w.dz1, E, B, E, ACT_RELU);
-    float* dcat = ws + w.s512;          // [B,512] scratch
+    float* dcat = ws + w.s512[0];       // [B,512] scratch
     lin_bwd(c, ws + w.dz1, E, ws + w.cat, 2 * E, m->fusion0, E, 2 * E, dcat, 2 * E, B, false);
     cudaMemcpy2DAsync(dhpath, E * 4, dcat, 2 * E * 4, E * 4, B, cudaMemcpyDeviceToDevice, c.st);
     cudaMemcpy2DAsync(dhomic, E * 4, dcat + E, 2 * E * 4, E * 4, B, cudaMemcpyDeviceToDevice, c.st);
@@ -489,22 +597,28 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
     bil_side_bwd(c, m->bil.h1, m->bil.z1, m->bil.o1, w, ws, 0, hpath, homic, dhpath, false, dhomic, B);
     bil_side_bwd(c, m->bil.h2, m->bil.z2, m->bil.o2, w, ws, 1, homic, hpath, dhomic, true, dhpath, B);
   }
-  // pooling heads -> token gradients
-  pool_bwd(c, m->path_pool, w.pool[0], w, ws, ws + w.enc[1].y2, dhpath, ws + w.dhp[0], ws + w.dtok[0], B);
-  pool_bwd(c, m->omic_pool, w.pool[1], w, ws, ws + w.enc[3].y2, dhomic, ws + w.dhp[1], ws + w.dtok[1], B);
-  // transformers
-  float* dhc = ws + w.dxa;              // [R,256]; dxa/dxb are free again after the pooling backward
-  enc_bwd(c, m->path_tr[1], w.enc[1], w, ws, ws + w.enc[0].y2, ws + w.dtok[0], ws + w.dxb, B);
-  enc_bwd(c, m->path_tr[0], w.enc[0], w, ws, ws + w.hc, ws + w.dxb, dhc, B);
-  enc_bwd(c, m->omic_tr[1], w.enc[3], w, ws, ws + w.enc[2].y2, ws + w.dtok[1], ws + w.dxb, B);
-  enc_bwd(c, m->omic_tr[0], w.enc[2], w, ws, ws + w.G, ws + w.dxb, ws + w.dG, B);
-  if (m->variant == MPO_VARIANT_NACAGAT) {
-    cag_bwd(c, m->cag, w, ws, ws + w.G, io->qp, dhc, ws + w.dG, ws + w.dqp, R);
-  }
+  br.main.chk(c.err, c.where);
+  // from here the path and omic branches are independent: two streams, weight gradients on two more
+  fork(br);
+  Ctx& cp = br.main;
+  Ctx& co = br.second;
+  pool_bwd(co, m->omic_pool, w.pool[1], w, ws, ws + w.enc[3].y2, dhomic, ws + w.dhp[1], ws + w.dtok[1], B);
+  enc_bwd(co, m->omic_tr[1], w.enc[3], w, ws, ws + w.enc[2].y2, ws + w.dtok[1], ws + w.dmid[1], B);
+  enc_bwd(co, m->omic_tr[0], w.enc[2], w, ws, ws + w.G, ws + w.dmid[1], ws + w.dG, B);
+  float* dhc = ws + w.dhc;
+  pool_bwd(cp, m->path_pool, w.pool[0], w, ws, ws + w.enc[1].y2, dhpath, ws + w.dhp[0], ws + w.dtok[0], B);
+  enc_bwd(cp, m->path_tr[1], w.enc[1], w, ws, ws + w.enc[0].y2, ws + w.dtok[0], ws + w.dmid[0], B);
+  enc_bwd(cp, m->path_tr[0], w.enc[0], w, ws, ws + w.hc, ws + w.dmid[0], dhc, B);
   // output and value projections back to the pooled vectors
-  lin_bwd(c, dhc, E, ws + w.v, E, m->coattn_out, E, E, ws + w.dxb, E, R, false);
-  lin_bwd(c, ws + w.dxb, E, io->pooled, E, sub(m->coattn_in, 2 * E, E), E, E, io->dpooled, E, R, false);
-  return finish(c);
+  join_w(cp);
+  lin_bwd(cp, dhc, E, ws + w.v, E, m->coattn_out, E, E, ws + w.dv, E, R, false);
+  lin_bwd(cp, ws + w.dv, E, io->pooled, E, sub(m->coattn_in, 2 * E, E), E, E, io->dpooled, E, R, false);
+  join(br);
+  if (m->variant == MPO_VARIANT_NACAGAT) {   // needs dG of the omic branch: after the join
+    cag_bwd(br.main, m->cag, w, ws, ws + w.G, io->qp, dhc, ws + w.dG, ws + w.dqp, R);
+  }
+  Ctx& cfin = br.main;
+  return finish(cfin);
 }
 
 int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
@@ -514,8 +628,11 @@ int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   const int B = io->num_slides, R = 6 * B;
   Ws w; build_layout(m, B, w);
   float* ws = io->ws;
-  Ctx c{static_cast<cudaStream_t>(stream)};
+  Branches br = make_branches(static_cast<cudaStream_t>(stream), true);
+  Ctx c = br.main;             // query / fold part: synchronous weight gradients
+  c.wst = nullptr;
   const bool nac = m->variant == MPO_VARIANT_NACAGAT;
+  if (nac && (!io->dkc || !io->dtq)) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_bwd: dkc/dtq are NULL (NaCAGaT)");
   const float* Wk = m->coattn_in.w + (long long)E * E;
   float* gWk = m->coattn_in.gw ? m->coattn_in.gw + (long long)E * E : nullptr;
   // key fold backward: dq[r][e] (+)= sum_d dqk[r][d] W_k[e][d] / 16 ; dW_k[e][d] += sum_r q[r][e] dqk[r][d] / 16
@@ -528,7 +645,6 @@ int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
     }
   }
   if (nac) {
-    if (!io->dkc || !io->dtq) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_bwd: dkc/dtq are NULL (NaCAGaT)");
     const float* bk = m->coattn_in.b + E;
     float* gbk = m->coattn_in.gb ? m->coattn_in.gb + E : nullptr;
     // kc = q . b_k / 16 :  dq += dkc b_k / 16 ; db_k += sum_r dkc[r] q[r] / 16
@@ -539,23 +655,28 @@ int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
       c.chk(launch_gemm(g2, c.st), "kc.dbk");
     }
     // tanh(q) branch of the pre-gate: dq += dtq * (1 - tanh(q)^2)
-    act(c, io->qp, ws + w.s256a, (long long)R * E, ACT_TANH);
-    act_bwd(c, io->dtq, E, ws + w.s256a, E, ws + w.s256b, E, R, E, ACT_TANH);
-    add(c, ws + w.dqp, ws + w.s256b, ws + w.dqp, (long long)R * E);
+    act(c, io->qp, ws + w.s256a[0], (long long)R * E, ACT_TANH);
+    act_bwd(c, io->dtq, E, ws + w.s256a[0], E, ws + w.s256b[0], E, R, E, ACT_TANH);
+    add(c, ws + w.dqp, ws + w.s256b[0], ws + w.dqp, (long long)R * E);
   }
   // query in-projection
   lin_bwd(c, ws + w.dqp, E, ws + w.G, E, sub(m->coattn_in, 0, E), E, E, ws + w.dG, E, R, true);
-  // SNN encoders
+  br.main.chk(c.err, c.where);
+  // SNN encoders: six independent chains over the two branch streams, weight gradients on the side streams
+  fork(br);
   for (int i = 0; i < MPO_Q; ++i) {
+    Ctx& ci = (i & 1) ? br.second : br.main;
     const int d = m->omic_dims[i];
-    float* dz2 = ws + w.dz2;   // [B,256]
-    float* dz1 = ws + w.dz1;
-    act_bwd(c, ws + w.dG + i * E, 6 * E, ws + w.G + i * E, 6 * E, dz2, E, B, E, ACT_ELU);
-    lin_bwd(c, dz2, E, ws + w.snn_h[i], E, m->snn[i][1], E, E, ws + w.dh, E, B, false);
-    act_bwd(c, ws + w.dh, E, ws + w.snn_h[i], E, dz1, E, B, E, ACT_ELU);
-    lin_bwd(c, dz1, E, io->omics[i], d, m->snn[i][0], E, d, nullptr, 0, B, false);
+    float* dz2 = ws + w.snn_dz2[i];   // [B,256] each, private to the chain
+    float* dz1 = ws + w.snn_dz1[i];
+    float* dh = ws + w.snn_dh[i];
+    act_bwd(ci, ws + w.dG + i * E, 6 * E, ws + w.G + i * E, 6 * E, dz2, E, B, E, ACT_ELU);
+    lin_bwd(ci, dz2, E, ws + w.snn_h[i], E, m->snn[i][1], E, E, dh, E, B, false);
+    act_bwd(ci, dh, E, ws + w.snn_h[i], E, dz1, E, B, E, ACT_ELU);
+    lin_bwd(ci, dz1, E, io->omics[i], d, m->snn[i][0], E, d, nullptr, 0, B, false);
   }
-  return finish(c);
+  join(br);
+  return finish(br.main);
 }
 
 }  // extern "C"
