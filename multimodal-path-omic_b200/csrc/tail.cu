@@ -143,7 +143,8 @@ StreamPool& stream_pool() {
 
 struct Ctx {
   cudaStream_t st;             // compute stream of this branch
-  cudaStream_t wst = nullptr;  // weight-gradient stream of this branch (nullptr: same as st)
+  cudaStream_t wst = nullptr;  // weight-gradient stream of this branch, valid when async_w
+  bool async_w = false;        // (a null stream handle is the legacy default stream, so it cannot double as "none")
   int sb = 0;                  // scratch set of this branch
   cudaError_t err = cudaSuccess;
   const char* where = "";
@@ -151,7 +152,7 @@ struct Ctx {
 };
 // `to` waits for everything submitted to `from` so far
 void dep(Ctx& c, cudaStream_t from, cudaStream_t to) {
-  if (from == to || from == nullptr || to == nullptr) return;
+  if (from == to) return;
   StreamPool& p = stream_pool();
   cudaEvent_t e = p.ev[p.next];
   p.next = (p.next + 1) & 63;
@@ -159,7 +160,7 @@ void dep(Ctx& c, cudaStream_t from, cudaStream_t to) {
   c.chk(cudaStreamWaitEvent(to, e, 0), "stream wait");
 }
 // the compute stream waits for this branch's pending weight-gradient GEMMs (before their inputs are overwritten)
-void join_w(Ctx& c) { if (c.wst) dep(c, c.wst, c.st); }
+void join_w(Ctx& c) { if (c.async_w) dep(c, c.wst, c.st); }
 
 inline unsigned nblk(long long n, int t = 256) { return static_cast<unsigned>((n + t - 1) / t); }
 
@@ -187,8 +188,8 @@ void lin_bwd(Ctx& c, const float* dz, long long lddz, const float* x, long long 
   }
   if (L.gw != nullptr) {     // gw += dz^T x, with gb += rowsum(dz^T) fused into the same kernel
     GemmArgs g{dz, 1, lddz, x, ldx, 1, L.gw, in, nullptr, out, in, rows, 1.f, 1, ACT_NONE, L.gb};
-    cudaStream_t ws_ = c.wst ? c.wst : c.st;
-    if (c.wst) dep(c, c.st, c.wst);          // dz is complete on the compute stream
+    cudaStream_t ws_ = c.async_w ? c.wst : c.st;
+    if (c.async_w) dep(c, c.st, c.wst);      // dz is complete on the compute stream
     c.chk(launch_gemm(g, ws_), "lin_bwd.wgrad");
   } else if (L.gb != nullptr) {
     colsum_kernel<<<nblk(out, 32), 256, 0, c.st>>>(dz, lddz, nullptr, 0, L.gb, rows, out); count_launch();
@@ -220,8 +221,8 @@ void ln_bwd(Ctx& c, const float* dy, const mpo_norm& N, const float* xh, const f
   layernorm_bwd_kernel<<<nblk(rows, 8), 256, 0, c.st>>>(dy, N.g, xh, rs, dx, rows); count_launch();
   c.chk(cudaGetLastError(), "ln_bwd");
   if (N.gg != nullptr) {
-    cudaStream_t ws_ = c.wst ? c.wst : c.st;
-    if (c.wst) dep(c, c.st, c.wst);
+    cudaStream_t ws_ = c.async_w ? c.wst : c.st;
+    if (c.async_w) dep(c, c.st, c.wst);
     colsum_kernel<<<nblk(E, 32), 256, 0, ws_>>>(dy, E, xh, E, N.gg, rows, E); count_launch();
     colsum_kernel<<<nblk(E, 32), 256, 0, ws_>>>(dy, E, nullptr, 0, N.gb, rows, E); count_launch();
     c.chk(cudaGetLastError(), "ln_bwd.params");
@@ -312,7 +313,7 @@ void cag_bwd(Ctx& c0, const mpo_cag& P, const Ws& w, float* ws, const float* Q, 
   const long long n = (long long)R * E;
   join_w(c0);
   Ctx c = c0;                // scratch is recycled aggressively here: keep the weight gradients on the compute stream
-  c.wst = nullptr;
+  c.async_w = false;
   float* t0 = ws + w.s256a[0]; float* t1 = ws + w.s256b[0]; float* t2 = ws + w.s256c[0];
   act_bwd(c, dC, E, ws + w.cag_C, E, t0, E, R, E, ACT_ELU);
   lin_bwd(c, t0, E, ws + w.cag_m, E, P.fc_c, E, E, t1, E, R, false);          // t1 = dm
@@ -377,8 +378,9 @@ Branches make_branches(cudaStream_t stream, bool async_wgrad) {
   b.second.sb = 1;
   if (b.par) {
     b.second.st = p.aux[0];
-    b.main.wst = async_wgrad ? p.aux[1] : nullptr;
-    b.second.wst = async_wgrad ? p.aux[2] : nullptr;
+    b.main.wst = p.aux[1];
+    b.second.wst = p.aux[2];
+    b.main.async_w = b.second.async_w = async_wgrad;
   } else {
     b.second.st = stream;     // everything in program order on the caller's stream
   }
@@ -388,14 +390,14 @@ Branches make_branches(cudaStream_t stream, bool async_wgrad) {
 void fork(Branches& b) {
   if (!b.par) return;
   dep(b.main, b.main.st, b.second.st);
-  if (b.main.wst) dep(b.main, b.main.st, b.main.wst);
-  if (b.second.wst) dep(b.main, b.main.st, b.second.wst);
+  if (b.main.async_w) dep(b.main, b.main.st, b.main.wst);
+  if (b.second.async_w) dep(b.main, b.main.st, b.second.wst);
 }
 // the caller's stream waits for the second branch and for every pending weight gradient
 void join(Branches& b) {
   if (b.par) {
-    if (b.second.wst) dep(b.main, b.second.wst, b.main.st);
-    if (b.main.wst) dep(b.main, b.main.wst, b.main.st);
+    if (b.second.async_w) dep(b.main, b.second.wst, b.main.st);
+    if (b.main.async_w) dep(b.main, b.main.wst, b.main.st);
     dep(b.main, b.second.st, b.main.st);
   }
   b.main.chk(b.second.err, b.second.where);
@@ -566,7 +568,7 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
   float* ws = io->ws;
   Branches br = make_branches(static_cast<cudaStream_t>(stream), true);
   Ctx c = br.main;            // fusion / head part: synchronous weight gradients on the caller's stream
-  c.wst = nullptr;
+  c.async_w = false;
   surv_head_bwd_kernel<<<nblk(B, 128), 128, 0, c.st>>>(io->hazards, io->S, io->Y, dhaz, dS, dY, ws + w.dlogits, B, K); count_launch();
   c.chk(cudaGetLastError(), "surv_head_bwd");
   const float* hpath = ws + w.pool[0].h;
@@ -630,7 +632,7 @@ int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   float* ws = io->ws;
   Branches br = make_branches(static_cast<cudaStream_t>(stream), true);
   Ctx c = br.main;             // query / fold part: synchronous weight gradients
-  c.wst = nullptr;
+  c.async_w = false;
   const bool nac = m->variant == MPO_VARIANT_NACAGAT;
   if (nac && (!io->dkc || !io->dtq)) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_bwd: dkc/dtq are NULL (NaCAGaT)");
   const float* Wk = m->coattn_in.w + (long long)E * E;
