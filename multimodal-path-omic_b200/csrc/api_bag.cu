@@ -240,7 +240,12 @@ int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, co
   p.part_db = part_db;
   const uint32_t thr = static_cast<uint32_t>(drop_p * 256.f + 0.5f);
   p.keep_scale = thr ? 256.f / static_cast<float>(256 - thr) : 1.f;
-  rc = check_cuda(launch_bag_bwd_dz(p, st), "bag_bwd_dz_kernel");
+  CUtensorMap tm_h, tm_dzs;
+  rc = make_tmap_16b_2d(&tm_h, h_saved, static_cast<uint64_t>(bag->total_rows), kD, 64, kTileM, true);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tm_dzs, dz_ws, static_cast<uint64_t>(bag->total_rows), kD, 64, kTileM);
+  if (rc) return rc;
+  rc = check_cuda(launch_bag_bwd_dz(tm_h, tm_dzs, p, num_sms(), st), "bag_bwd_dz_kernel");
   if (rc) return rc;
   rc = check_cuda(launch_bag_bwd_reduce(bag->tile_prefix, part_dqk, part_db, dqk, grad_b_h, bag->num_slides,
                                         bag->num_tiles, st),

@@ -17,110 +17,389 @@
 namespace mpo {
 
 
-constexpr int kDzWarps = 8;
-constexpr int kDzSmemBytes = kDzWarps * 7 * kD * 4;   // cross-warp reduction buffer
+// ------------------------------------------------------------------------------------------------
+// dz stage on tcgen05.  Per 128-patch tile (one persistent CTA per SM, contiguous tile ranges per CTA):
+//   TMA      : saved fp16 activation tile H [128 x 256] -> shared memory (two buffers, prefetch one tile ahead)
+//   MMA-G    : G[128 x 16]    = H dP^T          (dP of the slide as fp16 hi/lo rows, scaled per query to ~1)
+//   threads  : a_i = exp(s_i - lse_i), ds_i = a_i (g_i - delta_i) per patch row; written as tiny bf16 / fp16 operands
+//   MMA-dZ   : dZ'[128 x 256] = [a | ds] [dP ; qk]   (bf16 hi/lo, K = 48)      -> TMEM
+//   MMA-dqk  : dqk^T[256 x 16] = H^T ds           (H tile read M-major, per-tile power-of-two scale on ds)
+//   threads  : dz = dZ' * 1[h > 0] * keep_scale -> bf16, written IN PLACE over the H tile; TMA store to HBM
+//   MMA-db   : db[256] = dz^T 1                    (dz tile read M-major against a ones operand)
+// Everything rank-6-shaped that the CUDA-core version did with shuffles and 12 FMAs per element is a handful of
+// N = 16 / K = 48 tensor-core instructions here; the threads only touch each element once (mask + pack).
+// ------------------------------------------------------------------------------------------------
+constexpr int kDzThreads = 64 + 256;
+struct DzSmem {
+  static constexpr int tile = 0;                       // 2 x 64 KB  fp16 H tile [4][128][64] SW128 (later: bf16 dz tile)
+  static constexpr int C = 2 * 65536;                  // bf16 [128][64] K-major (48 used)   16 KB
+  static constexpr int Dm = C + 16384;                 // bf16 [256][64] K-major (48 used)   32 KB
+  static constexpr int DP = Dm + 32768;                // fp16 [4][16][64] K-major            8 KB
+  static constexpr int DS = DP + 8192;                 // fp16 [2][16][64] K-major (K = rows) 4 KB
+  static constexpr int ones = DS + 4096;               // bf16 [2][16][64] row 0 = 1          4 KB
+  static constexpr int scal = ones + 4096;             // fp32 scratch (see below)            1 KB
+  static constexpr int bars = scal + 1024;
+  static constexpr int tmem_slot = bars + 128;
+  static constexpr int total = tmem_slot + 16;
+};
+constexpr int kDzSmemBytes = DzSmem::total + 1024;
+constexpr uint32_t kColG = 0, kColQ = 32, kColB = 64, kColZ = 256;
 
-__global__ void __launch_bounds__(kDzWarps * 32, 1) bag_bwd_dz_kernel(const BagBwdDzParams p) {
-  extern __shared__ float red[];   // [8 warps][7][256]
+// power-of-two scale that brings m into [1, 2) (1 when m is zero / denormal); *inv receives its reciprocal
+__device__ __forceinline__ float pow2_scale(float m, float* inv) {
+  const uint32_t e = (__float_as_uint(m) >> 23) & 0xFFu;
+  if (e == 0u || e >= 254u) { *inv = 1.f; return 1.f; }
+  *inv = __uint_as_float(e << 23);
+  return __uint_as_float((254u - e) << 23);
+}
+
+__global__ void __launch_bounds__(kDzThreads, 1)
+bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_dz,
+                  const BagBwdDzParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DzSmem::bars);
+  uint64_t* full_bar = bars;          // [2] TMA -> issuer
+  uint64_t* empty_bar = bars + 2;     // [2] tile buffer free again (store has read it + MMA-db retired)
+  uint64_t* op_bar = bars + 4;        // per-slide operands in place (8 warp arrivals)
+  uint64_t* g_bar = bars + 5;         // MMA-G retired
+  uint64_t* c_bar = bars + 6;         // C / DS operands written (8 warp arrivals)
+  uint64_t* z_bar = bars + 7;         // MMA-dZ + MMA-dqk retired
+  uint64_t* w_bar = bars + 8;         // dz tile written in place (8 warp arrivals)
+  uint64_t* b_bar = bars + 9;         // MMA-db retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DzSmem::tmem_slot);
+  float* scal = reinterpret_cast<float*>(smem + DzSmem::scal);
+  // scal: [0..7] delta_i, [8..15] lse_i, [16..23] 1/dp_scale_i, [32..127] warp partials [8][12], [128..159] row-warp max [4][8]
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x;
-  const TileInfo ti = p.tile_info[t];
-  const size_t sb = static_cast<size_t>(ti.slide) * kQ * kD;
+  // contiguous tile range of this CTA (consecutive tiles mostly share a slide -> per-slide operands are rebuilt rarely)
+  const int per = (p.num_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int t_begin = min(p.num_tiles, static_cast<int>(blockIdx.x) * per);
+  const int t_end = min(p.num_tiles, t_begin + per);
 
-  // per-lane slices (8 features) of dPooled and qk; delta_i via a warp reduction
-  float dP[kQ][8], qk[kQ][8];
-  float lse_r[kQ];
-#pragma unroll
-  for (int i = 0; i < kQ; ++i) {
-    const float4 a0 = *reinterpret_cast<const float4*>(p.dpooled + sb + i * kD + lane * 8);
-    const float4 a1 = *reinterpret_cast<const float4*>(p.dpooled + sb + i * kD + lane * 8 + 4);
-    dP[i][0] = a0.x; dP[i][1] = a0.y; dP[i][2] = a0.z; dP[i][3] = a0.w;
-    dP[i][4] = a1.x; dP[i][5] = a1.y; dP[i][6] = a1.z; dP[i][7] = a1.w;
-    const float4 q0 = *reinterpret_cast<const float4*>(p.qk + sb + i * kD + lane * 8);
-    const float4 q1 = *reinterpret_cast<const float4*>(p.qk + sb + i * kD + lane * 8 + 4);
-    qk[i][0] = q0.x; qk[i][1] = q0.y; qk[i][2] = q0.z; qk[i][3] = q0.w;
-    qk[i][4] = q1.x; qk[i][5] = q1.y; qk[i][6] = q1.z; qk[i][7] = q1.w;
-    lse_r[i] = p.lse[ti.slide * kQ + i];
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_h);
+    tma_prefetch_desc(&tm_dz);
+    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
+    mbar_init(op_bar, 8); mbar_init(g_bar, 1); mbar_init(c_bar, 8); mbar_init(z_bar, 1); mbar_init(w_bar, 8);
+    mbar_init(b_bar, 1);
+    fence_mbar_init();
   }
-  float delta[kQ];
-#pragma unroll
-  for (int i = 0; i < kQ; ++i) {
-    const float4 c0 = *reinterpret_cast<const float4*>(p.pooled + sb + i * kD + lane * 8);
-    const float4 c1 = *reinterpret_cast<const float4*>(p.pooled + sb + i * kD + lane * 8 + 4);
-    float v = dP[i][0] * c0.x + dP[i][1] * c0.y + dP[i][2] * c0.z + dP[i][3] * c0.w + dP[i][4] * c1.x +
-              dP[i][5] * c1.y + dP[i][6] * c1.z + dP[i][7] * c1.w;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    delta[i] = v;
-  }
-
-  float dqk[kQ][8], db[8];
-#pragma unroll
-  for (int i = 0; i < kQ; ++i)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) dqk[i][e] = 0.f;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) db[e] = 0.f;
-
-  // each warp owns 16 consecutive rows of the tile
-#pragma unroll 1
-  for (int rr = 0; rr < kTileM / kDzWarps; ++rr) {
-    const int n = warp * (kTileM / kDzWarps) + rr;
-    if (n >= ti.nvalid) break;   // warp-uniform
-    const size_t grow = static_cast<size_t>(ti.row0 + n);
-    const uint4 hv = *reinterpret_cast<const uint4*>(p.h + grow * kD + lane * 8);
-    float h[8];
-    { const float2 t0 = unpack_f16x2(hv.x), t1 = unpack_f16x2(hv.y), t2 = unpack_f16x2(hv.z), t3 = unpack_f16x2(hv.w);
-      h[0] = t0.x; h[1] = t0.y; h[2] = t1.x; h[3] = t1.y; h[4] = t2.x; h[5] = t2.y; h[6] = t3.x; h[7] = t3.y; }
-    float a[kQ], ds[kQ];
-#pragma unroll
-    for (int i = 0; i < kQ; ++i) {
-      float g = 0.f;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) g = fmaf(dP[i][e], h[e], g);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-      a[i] = __expf(__ldg(p.scores + static_cast<size_t>(i) * p.total_rows + grow) - lse_r[i]);
-      ds[i] = a[i] * (g - delta[i]);
-    }
-    float dzv[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = 0.f;
-#pragma unroll
-      for (int i = 0; i < kQ; ++i) v = fmaf(a[i], dP[i][e], fmaf(ds[i], qk[i][e], v));
-      dzv[e] = h[e] > 0.f ? v * p.keep_scale : 0.f;
-      db[e] += dzv[e];
-    }
-#pragma unroll
-    for (int i = 0; i < kQ; ++i)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) dqk[i][e] = fmaf(ds[i], h[e], dqk[i][e]);
-    uint4 pk;
-    pk.x = pack_bf16x2(dzv[0], dzv[1]);
-    pk.y = pack_bf16x2(dzv[2], dzv[3]);
-    pk.z = pack_bf16x2(dzv[4], dzv[5]);
-    pk.w = pack_bf16x2(dzv[6], dzv[7]);
-    *reinterpret_cast<uint4*>(p.dz + grow * kD + lane * 8) = pk;
-  }
-
-  // cross-warp reduction of the per-lane partial sums
-  float* mine = red + warp * (7 * kD);
-#pragma unroll
-  for (int i = 0; i < kQ; ++i) {
-    *reinterpret_cast<float4*>(mine + i * kD + lane * 8) = make_float4(dqk[i][0], dqk[i][1], dqk[i][2], dqk[i][3]);
-    *reinterpret_cast<float4*>(mine + i * kD + lane * 8 + 4) = make_float4(dqk[i][4], dqk[i][5], dqk[i][6], dqk[i][7]);
-  }
-  *reinterpret_cast<float4*>(mine + 6 * kD + lane * 8) = make_float4(db[0], db[1], db[2], db[3]);
-  *reinterpret_cast<float4*>(mine + 6 * kD + lane * 8 + 4) = make_float4(db[4], db[5], db[6], db[7]);
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  // zero the small operand buffers once (padding rows / columns stay zero), set the ones operand
+  for (int o = threadIdx.x * 16; o < DzSmem::scal - DzSmem::C; o += kDzThreads * 16)
+    *reinterpret_cast<uint4*>(smem + DzSmem::C + o) = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  for (int e = threadIdx.x; e < 7 * kD; e += blockDim.x) {
-    float v = 0.f;
-#pragma unroll
-    for (int w = 0; w < kDzWarps; ++w) v += red[w * (7 * kD) + e];
-    if (e < kQ * kD) p.part_dqk[static_cast<size_t>(t) * (kQ * kD) + e] = v;
-    else p.part_db[static_cast<size_t>(t) * kD + (e - kQ * kD)] = v;
+  if (threadIdx.x < 128) {
+    // ones operand: B[n = 0][k = threadIdx.x] = 1.0 (bf16), K-major, 2 blocks of 64 k
+    const int k = threadIdx.x;
+    *reinterpret_cast<__nv_bfloat16*>(smem + DzSmem::ones + (k >> 6) * 2048 + ((((k & 63) >> 3) ^ 0) << 4) + (k & 7) * 2) =
+        __float2bfloat16_rn(1.f);
   }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer: H tiles
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_first();
+      int it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&empty_bar[buf], ph ^ 1);
+        uint8_t* dst = smem + DzSmem::tile + buf * 65536;
+        mbar_expect_tx(&full_bar[buf], 65536);
+        const int row0 = p.tile_info[t].row0;
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) tma_load_2d(dst + cb * 16384, &tm_h, &full_bar[buf], cb * 64, row0, pol);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA / TMA-store issuer
+    if (lane == 0) {
+      constexpr uint32_t id_g = umma_idesc(128, 16, 0, 0, 0, 0);       // fp16 x fp16, both K-major
+      constexpr uint32_t id_z = umma_idesc_bf16(128, 256, 0, 0);       // bf16 x bf16, both K-major
+      constexpr uint32_t id_q = umma_idesc(128, 16, 0, 0, 1, 0);       // fp16, A M-major (H^T)
+      constexpr uint32_t id_b = umma_idesc(128, 16, 1, 1, 1, 0);       // bf16, A M-major (dz^T)
+      const uint32_t aC = smem_u32(smem + DzSmem::C), aD = smem_u32(smem + DzSmem::Dm);
+      const uint32_t aDP = smem_u32(smem + DzSmem::DP), aDS = smem_u32(smem + DzSmem::DS);
+      const uint32_t aOne = smem_u32(smem + DzSmem::ones);
+      int it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1, tph = it & 1;
+        const uint32_t aT = smem_u32(smem + DzSmem::tile + buf * 65536);
+        mbar_wait(op_bar, tph);
+        mbar_wait(&full_bar[buf], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + kColG, umma_desc_sw128(aT + kb * 16384 + k * 32, 16, 1024),
+                      umma_desc_sw128(aDP + kb * 2048 + k * 32, 16, 1024), id_g, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(g_bar);
+        mbar_wait(c_bar, tph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          umma_bf16(tmem_base + kColZ, umma_desc_sw128(aC + k * 32, 16, 1024), umma_desc_sw128(aD + k * 32, 16, 1024),
+                    id_z, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16(tmem_base + kColQ + mh * 16, umma_desc_sw128(aT + mh * 2 * 16384 + kk * 2048, 16384, 1024),
+                      umma_desc_sw128(aDS + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), id_q, kk != 0 ? 1u : 0u);
+        umma_commit(z_bar);
+        mbar_wait(w_bar, tph);
+        tc_fence_after();
+        const TileInfo ti = p.tile_info[t];
+        const bool full_tile = ti.nvalid == kTileM;
+        if (full_tile) {
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) tma_store_2d(&tm_dz, smem + DzSmem::tile + buf * 65536 + cb * 16384, cb * 64, ti.row0);
+          tma_store_commit();
+        }
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16(tmem_base + kColB + mh * 16, umma_desc_sw128(aT + mh * 2 * 16384 + kk * 2048, 16384, 1024),
+                      umma_desc_sw128(aOne + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), id_b, kk != 0 ? 1u : 0u);
+        umma_commit(b_bar);
+        umma_commit(&empty_bar[buf]);            // arrival 1 of 2: MMA-db no longer reads the tile
+        if (full_tile) tma_store_wait_read();
+        mbar_arrive(&empty_bar[buf]);            // arrival 2 of 2: the store has read it
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- 8 compute warps
+    const int et = threadIdx.x - 64;           // 0..255 : feature owned when building per-slide operands / reading dqk, db
+    const int qd = warp & 3;                   // TMEM lane quadrant
+    const int ch = (warp - 2) >> 2;            // column half (epilogue) / feature half (dqk, db read-back)
+    const int r = qd * 32 + lane;              // patch row of the tile
+    uint8_t* Cs = smem + DzSmem::C;
+    uint8_t* Ds = smem + DzSmem::Dm;
+    uint8_t* DPs = smem + DzSmem::DP;
+    uint8_t* DSs = smem + DzSmem::DS;
+    int cur_slide = -1;
+    int it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const TileInfo ti = p.tile_info[t];
+      const int buf = it & 1;
+      const uint32_t tph = it & 1;
+      uint8_t* tile = smem + DzSmem::tile + buf * 65536;
+      // ---- per-slide operands: D = [dP ; qk] (bf16 hi | hi | lo), DP = dP (fp16 hi/lo, scaled), delta, lse
+      if (ti.slide != cur_slide) {
+        cur_slide = ti.slide;
+        const size_t sb = static_cast<size_t>(ti.slide) * kQ * kD;
+        float dp[kQ], qv[kQ], red[12];
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
+          dp[i] = p.dpooled[sb + i * kD + et];
+          qv[i] = p.qk[sb + i * kD + et];
+          red[i] = dp[i] * p.pooled[sb + i * kD + et];     // delta_i partial
+          red[6 + i] = fabsf(dp[i]);                       // max |dP_i|
+        }
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            red[i] += __shfl_xor_sync(0xffffffffu, red[i], o);
+            red[6 + i] = fmaxf(red[6 + i], __shfl_xor_sync(0xffffffffu, red[6 + i], o));
+          }
+        }
+        named_bar_sync(1, 256);                            // previous tile no longer reads scal
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 12; ++j) scal[32 + (warp - 2) * 12 + j] = red[j];
+        }
+        named_bar_sync(1, 256);
+        float dscale[kQ];
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
+          float s = 0.f, m = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) { s += scal[32 + w * 12 + i]; m = fmaxf(m, scal[32 + w * 12 + 6 + i]); }
+          float inv;
+          dscale[i] = pow2_scale(m, &inv);
+          if (et == 0) { scal[i] = s; scal[8 + i] = p.lse[ti.slide * kQ + i]; scal[16 + i] = inv; }
+        }
+        // D row `et`: k 0..5 dP hi, 6..11 qk hi, 16..27 the same hi values, 32..43 the lo parts
+        uint32_t hi[6], lo[6];
+        {
+          float v[12];
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) { v[i] = dp[i]; v[6 + i] = qv[i]; }
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+            hi[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+            lo[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+          }
+        }
+        uint8_t* drow = Ds + et * 128;
+        const int sw = et & 7;
+        *reinterpret_cast<uint4*>(drow + ((0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(drow + ((1 ^ sw) << 4)) = make_uint4(hi[4], hi[5], 0u, 0u);
+        *reinterpret_cast<uint4*>(drow + ((2 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(drow + ((3 ^ sw) << 4)) = make_uint4(hi[4], hi[5], 0u, 0u);
+        *reinterpret_cast<uint4*>(drow + ((4 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(drow + ((5 ^ sw) << 4)) = make_uint4(lo[4], lo[5], 0u, 0u);
+        // DP[n][k = et]: rows 0..5 hi, 6..11 lo of dP_i * scale_i (fp16), K-major in 4 blocks of 64 k
+        uint8_t* pcol = DPs + (et >> 6) * 2048 + (et & 7) * 2;
+        const int kc = (et & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
+          const float v = dp[i] * dscale[i];
+          const __half vh = __float2half_rn(v);
+          const __half vl = __float2half_rn(v - __half2float(vh));
+          *reinterpret_cast<__half*>(pcol + i * 128 + ((kc ^ i) << 4)) = vh;
+          *reinterpret_cast<__half*>(pcol + (i + 6) * 128 + ((kc ^ ((i + 6) & 7)) << 4)) = vl;
+        }
+        fence_proxy_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(op_bar);
+      named_bar_sync(1, 256);                  // scal[0..23] visible to everyone
+
+      // ---- per-row scalars (one patch row per thread of warps 2..5)
+      float a[kQ], ds[kQ];
+      const bool valid = r < ti.nvalid;
+      if (ch == 0) {
+        float sc[kQ];
+#pragma unroll
+        for (int i = 0; i < kQ; ++i)
+          sc[i] = valid ? __ldg(p.scores + static_cast<size_t>(i) * p.total_rows + ti.row0 + r) : 0.f;
+        mbar_wait(g_bar, tph);
+        tc_fence_after();
+        uint32_t gv[16];
+        tmem_ld_32x32b_x16(tmem_base + kColG + (static_cast<uint32_t>(qd * 32) << 16), gv);
+        tmem_ld_wait();
+        float amax[kQ];
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
+          const float g = (__uint_as_float(gv[i]) + __uint_as_float(gv[i + 6])) * scal[16 + i];
+          a[i] = valid ? __expf(sc[i] - scal[8 + i]) : 0.f;
+          ds[i] = a[i] * (g - scal[i]);
+          float m = fabsf(ds[i]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          amax[i] = m;
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) scal[128 + qd * 8 + i] = amax[i];
+        }
+        // C row r : k 0..5 a hi, 6..11 ds hi, 16..27 lo parts, 32..43 hi again (pairs with the lo half of D)
+        {
+          float v[12];
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) { v[i] = a[i]; v[6 + i] = ds[i]; }
+          uint32_t hi[6], lo[6];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+            hi[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+            lo[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+          }
+          uint8_t* crow = Cs + r * 128;
+          const int sw = r & 7;
+          *reinterpret_cast<uint4*>(crow + ((0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(crow + ((1 ^ sw) << 4)) = make_uint4(hi[4], hi[5], 0u, 0u);
+          *reinterpret_cast<uint4*>(crow + ((2 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(crow + ((3 ^ sw) << 4)) = make_uint4(lo[4], lo[5], 0u, 0u);
+          *reinterpret_cast<uint4*>(crow + ((4 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(crow + ((5 ^ sw) << 4)) = make_uint4(hi[4], hi[5], 0u, 0u);
+        }
+        named_bar_sync(2, 128);                // tile maxima of |ds_i| from the four row warps
+        uint8_t* pcol = DSs + (r >> 6) * 2048 + (r & 7) * 2;
+        const int kc = (r & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
+          const float m = fmaxf(fmaxf(scal[128 + i], scal[136 + i]), fmaxf(scal[144 + i], scal[152 + i]));
+          float inv;
+          const float s = pow2_scale(m, &inv);
+          const float v = ds[i] * s;
+          const __half vh = __float2half_rn(v);
+          const __half vl = __float2half_rn(v - __half2float(vh));
+          *reinterpret_cast<__half*>(pcol + i * 128 + ((kc ^ i) << 4)) = vh;
+          *reinterpret_cast<__half*>(pcol + (i + 6) * 128 + ((kc ^ ((i + 6) & 7)) << 4)) = vl;
+          if (r == 0) scal[24 + i] = inv;      // un-scale factor for the dqk read-back
+        }
+        fence_proxy_async_smem();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(c_bar);
+
+      // ---- dz = dZ' * 1[h > 0] * keep_scale, in place over the H tile (row r, column half ch)
+      mbar_wait(z_bar, tph);
+      tc_fence_after();
+      __nv_bfloat16* grow_out = p.dz + static_cast<size_t>(ti.row0 + r) * kD;
+      const bool direct = ti.nvalid != kTileM;     // ragged tile: rows are stored by the threads, not by TMA
+#pragma unroll 1
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int col0 = ch * 128 + c4 * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + kColZ + (static_cast<uint32_t>(qd * 32) << 16) + col0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const int j16 = (col0 + j) >> 3;
+          const int cb = j16 >> 3, jj = j16 & 7;
+          uint4* slot = reinterpret_cast<uint4*>(tile + cb * 16384 + r * 128 + ((jj ^ (r & 7)) << 4));
+          const uint4 hv = *slot;
+          const float2 h0 = unpack_f16x2(hv.x), h1 = unpack_f16x2(hv.y), h2 = unpack_f16x2(hv.z), h3 = unpack_f16x2(hv.w);
+          const float ks = p.keep_scale;
+          uint4 o;
+          o.x = pack_bf16x2(h0.x > 0.f ? __uint_as_float(v[j + 0]) * ks : 0.f, h0.y > 0.f ? __uint_as_float(v[j + 1]) * ks : 0.f);
+          o.y = pack_bf16x2(h1.x > 0.f ? __uint_as_float(v[j + 2]) * ks : 0.f, h1.y > 0.f ? __uint_as_float(v[j + 3]) * ks : 0.f);
+          o.z = pack_bf16x2(h2.x > 0.f ? __uint_as_float(v[j + 4]) * ks : 0.f, h2.y > 0.f ? __uint_as_float(v[j + 5]) * ks : 0.f);
+          o.w = pack_bf16x2(h3.x > 0.f ? __uint_as_float(v[j + 6]) * ks : 0.f, h3.y > 0.f ? __uint_as_float(v[j + 7]) * ks : 0.f);
+          *slot = o;
+          if (direct && valid) *reinterpret_cast<uint4*>(grow_out + col0 + j) = o;
+        }
+      }
+      // dqk partial of this tile: feature f = ch * 128 + qd * 32 + lane
+      {
+        uint32_t qv[16];
+        tmem_ld_32x32b_x16(tmem_base + kColQ + ch * 16 + (static_cast<uint32_t>(qd * 32) << 16), qv);
+        tmem_ld_wait();
+        float* dst = p.part_dqk + static_cast<size_t>(t) * (kQ * kD) + ch * 128 + qd * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) dst[i * kD] = (__uint_as_float(qv[i]) + __uint_as_float(qv[i + 6])) * scal[24 + i];
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(w_bar);
+
+      // ---- db partial
+      mbar_wait(b_bar, tph);
+      tc_fence_after();
+      {
+        uint32_t bv[16];
+        tmem_ld_32x32b_x16(tmem_base + kColB + ch * 16 + (static_cast<uint32_t>(qd * 32) << 16), bv);
+        tmem_ld_wait();
+        p.part_db[static_cast<size_t>(t) * kD + ch * 128 + qd * 32 + lane] = __uint_as_float(bv[0]);
+      }
+      tc_fence_before();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // dqk[b][i][d] = sum over the slide's tiles;  db_H[d] += sum over all tiles (gradient accumulation)
@@ -277,7 +556,8 @@ bag_bwd_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
-cudaError_t launch_bag_bwd_dz(const BagBwdDzParams& prm, cudaStream_t stream) {
+cudaError_t launch_bag_bwd_dz(const CUtensorMap& tm_h, const CUtensorMap& tm_dz, const BagBwdDzParams& prm, int num_sms,
+                              cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(bag_bwd_dz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDzSmemBytes);
@@ -285,7 +565,8 @@ cudaError_t launch_bag_bwd_dz(const BagBwdDzParams& prm, cudaStream_t stream) {
     attr_set = true;
   }
   if (prm.num_tiles <= 0) return cudaSuccess;
-  bag_bwd_dz_kernel<<<prm.num_tiles, kDzWarps * 32, kDzSmemBytes, stream>>>(prm);
+  const int grid = prm.num_tiles < num_sms ? prm.num_tiles : num_sms;
+  bag_bwd_dz_kernel<<<grid, kDzThreads, kDzSmemBytes, stream>>>(tm_h, tm_dz, prm);
   count_launch();
   return cudaGetLastError();
 }

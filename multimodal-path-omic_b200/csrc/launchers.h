@@ -18,7 +18,8 @@ cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, con
                            const BagFwdParams& prm, int num_sms, cudaStream_t stream);
 cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, const float* part_pool, float* pooled,
                              float* lse, int B, cudaStream_t stream);
-cudaError_t launch_bag_bwd_dz(const BagBwdDzParams& prm, cudaStream_t stream);
+cudaError_t launch_bag_bwd_dz(const CUtensorMap& tm_h, const CUtensorMap& tm_dz, const BagBwdDzParams& prm, int num_sms,
+                              cudaStream_t stream);
 cudaError_t launch_bag_bwd_reduce(const int* tile_prefix, const float* part_dqk, const float* part_db, float* dqk,
                                   float* grad_bias, int B, int num_tiles, cudaStream_t stream);
 cudaError_t launch_bag_bwd_dw(const CUtensorMap& tm_dz, const CUtensorMap& tm_x, float* grad_w, int total_rows,

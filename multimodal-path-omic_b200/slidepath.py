@@ -420,20 +420,25 @@ class BatchTrainer:
         torch.cuda.synchronize()
         self.flat_grad.zero_()
         graph = torch.cuda.CUDAGraph()
+        _lib.lib().mpo_launch_count(1)
         with torch.cuda.graph(graph):
             self._run(st, bag, omics, labels, censor, train, 0)
+        launches = int(_lib.lib().mpo_launch_count(1))     # kernels recorded into the graph = launched per replay
         self.flat_grad.zero_()
         self.last_state = st
-        return GraphedStep(graph, st, (bag, omics, labels, censor))
+        return GraphedStep(graph, st, (bag, omics, labels, censor), launches)
 
 
 class GraphedStep:
     """A captured train step over static buffers: refresh the buffers in place, then replay()."""
 
-    def __init__(self, graph, state, static_inputs):
+    def __init__(self, graph, state, static_inputs, launches=0):
         self.graph, self.state, self.static_inputs = graph, state, static_inputs
+        self.launches_per_replay = launches     # kernels of libmpo_b200.so inside the captured step
+        self.replays = 0
 
     def replay(self):
         self.graph.replay()
+        self.replays += 1
         st = self.state
         return st.loss, st.hazards, st.S
