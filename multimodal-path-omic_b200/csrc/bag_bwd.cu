@@ -129,20 +129,26 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
       const uint32_t aDP = smem_u32(smem + DzSmem::DP), aDS = smem_u32(smem + DzSmem::DS);
       const uint32_t aOne = smem_u32(smem + DzSmem::ones);
       int it = 0;
+      bool g_early = false;
+      auto issue_g = [&](uint32_t a_tile) {
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + kColG, umma_desc_sw128(a_tile + kb * 16384 + k * 32, 16, 1024),
+                      umma_desc_sw128(aDP + kb * 2048 + k * 32, 16, 1024), id_g, (kb | k) != 0 ? 1u : 0u);
+      };
       for (int t = t_begin; t < t_end; ++t, ++it) {
         const int buf = it & 1;
         const uint32_t ph = (it >> 1) & 1, tph = it & 1;
         const uint32_t aT = smem_u32(smem + DzSmem::tile + buf * 65536);
         mbar_wait(op_bar, tph);
-        mbar_wait(&full_bar[buf], ph);
-        tc_fence_after();
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + kColG, umma_desc_sw128(aT + kb * 16384 + k * 32, 16, 1024),
-                      umma_desc_sw128(aDP + kb * 2048 + k * 32, 16, 1024), id_g, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(g_bar);
+        if (!g_early) {
+          mbar_wait(&full_bar[buf], ph);
+          tc_fence_after();
+          issue_g(aT);
+          umma_commit(g_bar);
+        }
         mbar_wait(c_bar, tph);
         tc_fence_after();
 #pragma unroll
@@ -156,6 +162,17 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
             umma_bf16(tmem_base + kColQ + mh * 16, umma_desc_sw128(aT + mh * 2 * 16384 + kk * 2048, 16384, 1024),
                       umma_desc_sw128(aDS + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), id_q, kk != 0 ? 1u : 0u);
         umma_commit(z_bar);
+        // MMA-G of the next tile already now (same slide: same dP operand), so that it overlaps this tile's epilogue;
+        // every row thread has consumed this tile's G by the time c_bar completed
+        g_early = false;
+        if (t + 1 < t_end && p.tile_info[t + 1].slide == p.tile_info[t].slide) {
+          const int nb = (it + 1) & 1;
+          mbar_wait(&full_bar[nb], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_g(smem_u32(smem + DzSmem::tile + nb * 65536));
+          umma_commit(g_bar);
+          g_early = true;
+        }
         mbar_wait(w_bar, tph);
         tc_fence_after();
         const TileInfo ti = p.tile_info[t];
@@ -189,6 +206,18 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
     uint8_t* DSs = smem + DzSmem::DS;
     int cur_slide = -1;
     int it = 0;
+    int prev_t = -1;
+    // db partial of tile `tt` (its MMA-db was issued after the tile was written): read one tile late, so nobody
+    // waits for that MMA -- by then it has long retired
+    auto read_db = [&](int tt, uint32_t parity) {
+      mbar_wait(b_bar, parity);
+      tc_fence_after();
+      uint32_t bv[16];
+      tmem_ld_32x32b_x16(tmem_base + kColB + ch * 16 + (static_cast<uint32_t>(qd * 32) << 16), bv);
+      tmem_ld_wait();
+      p.part_db[static_cast<size_t>(tt) * kD + ch * 128 + qd * 32 + lane] = __uint_as_float(bv[0]);
+      tc_fence_before();
+    };
     for (int t = t_begin; t < t_end; ++t, ++it) {
       const TileInfo ti = p.tile_info[t];
       const int buf = it & 1;
@@ -343,6 +372,7 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
       if (lane == 0) mbar_arrive(c_bar);
 
       // ---- dz = dZ' * 1[h > 0] * keep_scale, in place over the H tile (row r, column half ch)
+      if (prev_t >= 0) read_db(prev_t, tph ^ 1);     // before this tile's w_bar arrival lets MMA-db overwrite it
       mbar_wait(z_bar, tph);
       tc_fence_after();
       __nv_bfloat16* grow_out = p.dz + static_cast<size_t>(ti.row0 + r) * kD;
@@ -384,17 +414,9 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(w_bar);
 
-      // ---- db partial
-      mbar_wait(b_bar, tph);
-      tc_fence_after();
-      {
-        uint32_t bv[16];
-        tmem_ld_32x32b_x16(tmem_base + kColB + ch * 16 + (static_cast<uint32_t>(qd * 32) << 16), bv);
-        tmem_ld_wait();
-        p.part_db[static_cast<size_t>(t) * kD + ch * 128 + qd * 32 + lane] = __uint_as_float(bv[0]);
-      }
-      tc_fence_before();
+      prev_t = t;
     }
+    if (prev_t >= 0) read_db(prev_t, (it - 1) & 1);
   }
 
   tc_fence_before();
@@ -545,7 +567,10 @@ bag_bwd_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
           tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + mh * 256 + c0, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(__uint_as_float(v[j])),
+                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                         : "memory");
         }
       }
     }
