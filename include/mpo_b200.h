@@ -63,12 +63,41 @@ int mpo_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
  *   lse       fp32 [num_slides][6]       log-sum-exp of the scores of each query
  *   h_saved   fp16 [total_rows][256] or NULL (inference): activations kept for mpo_bag_bwd (fp16, not bf16:
  *             11 mantissa bits keep the pooled vectors of small bags inside the 1e-3 parity gate)
+ *   pooled == NULL selects the projection-only pass used by NaCAGaT (h_saved and scores are written, part_ml,
+ *             part_pool, lse are ignored): the softmax then runs on the gated scores in mpo_bag_gate_fwd
+ *   h_lo      fp16 [total_rows][256] or NULL: the remainder h - fp16(h); NaCAGaT's key projection (mpo_bag_gate_fwd)
+ *             runs on the pair (h_saved, h_lo) so that its tanh gate sees ~22-bit activations
  *   drop_p    dropout probability on H in train mode (0 = eval); seed selects the mask stream; when seed_dev is
  *             non-NULL the stream id is seed ^ *seed_dev, read on the device (so a captured CUDA graph draws a new
  *             mask on every replay; advance it with mpo_advance_seed) */
 int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, const float* qk, float* scores,
-                float* part_ml, float* part_pool, float* pooled, float* lse, void* h_saved, uint32_t seed,
+                float* part_ml, float* part_pool, float* pooled, float* lse, void* h_saved, void* h_lo, uint32_t seed,
                 const uint32_t* seed_dev, float drop_p, void* stream);
+/* fp32 -> fp16 (round to nearest even): the fp16 streaming copy of NaCAGaT's key projection W_k */
+int mpo_cast_f16(const float* src, void* dst_f16, int64_t n, void* stream);
+
+/* NaCAGaT gate pass.  Replaces the attention core of models/blocks.py:156-192 (PreGatingContextualAttention /
+ * multi_head_attention_forward): key projection k = W_k h + b_k, pre-gate P = (tanh(q).tanh(k) + 1)/2, gated scores
+ * s' = s P, softmax over the patches, attention dropout (train) and the weighted sum of H.  Runs after mpo_bag_fwd
+ * called with pooled == NULL (projection + raw folded scores h.qk only; h_saved is then mandatory).
+ *   w_k_f16   fp16 [256][256]           co_attention.in_proj_weight[256:512] (mpo_cast_f16 of the fp32 master)
+ *   bias_k    fp32 [256]                co_attention.in_proj_bias[256:512]
+ *   qp, kc    from mpo_tail_pre_fwd     q_i = W_q g_i + b_q  and  kc_i = b_k . q_i / 16
+ *   scores    fp32 [6][total_rows]      in: h.qk_i ; when pgate != NULL rewritten as s = h.qk_i + kc_i (for the backward)
+ *   scores_g  fp32 [6][total_rows]      out: s'
+ *   pgate     fp32 [6][total_rows] and t_saved fp16 [total_rows][256] (tanh(k)): kept for mpo_bag_bwd_nacagat, or both NULL
+ *   part_ml   fp32 [num_tiles][18], part_pool fp32 [num_tiles][6][256]   workspaces
+ *   pooled    fp32 [B][6][256] sum_n a'_in h_n ; lse fp32 [B][6] of s' ; suma fp32 [B][6] sum_n a'_in (1 without dropout)
+ *   attn_drop_p  dropout on the attention weights in train mode (blocks.py:52,189-190: 0.25), 0 in eval; the mask
+ *             stream is (seed ^ *seed_dev) as in mpo_bag_fwd, site 1 */
+int mpo_bag_gate_fwd(const mpo_bag* bag, const void* h_saved, const void* h_lo, const void* w_k_f16, const float* bias_k, const float* qp,
+                     const float* kc, float* scores, float* scores_g, float* pgate, void* t_saved, float* part_ml,
+                     float* part_pool, float* pooled, float* lse, float* suma, uint32_t seed, const uint32_t* seed_dev,
+                     float attn_drop_p, void* stream);
+/* NaCAGaT attention map: dropout(softmax(s')) -- the reference returns the post-dropout weights (blocks.py:189-199) */
+int mpo_attn_map_dropout(const mpo_bag* bag, const float* scores_g, const float* lse, float* amap, uint32_t seed,
+                         const uint32_t* seed_dev, float attn_drop_p, void* stream);
+
 /* *seed_dev = hash(*seed_dev + golden ratio): one tiny kernel, stream-ordered (graph-capturable) */
 int mpo_advance_seed(uint32_t* seed_dev, void* stream);
 
@@ -160,6 +189,8 @@ typedef struct mpo_tail_io {
   float* qk;                            /* out of pre_fwd : [B][6][256] folded queries W_k^T q / 16   */
   float* kc;                            /* out of pre_fwd : [B][6] key-bias score term b_k.q/16 (NaCAGaT; else NULL) */
   const float* pooled;                  /* in  to post_fwd: [B][6][256] from mpo_bag_fwd             */
+  const float* suma;                    /* in  to post_fwd: [B][6] sum_n a'_in (NaCAGaT with attention dropout) or NULL (= 1) */
+  float* dsuma;                         /* out of post_bwd: [B][6] gradient of suma (written when suma != NULL)       */
   float* dpooled;                       /* out of post_bwd: [B][6][256]                               */
   const float* dqk;                     /* in  to pre_bwd : [B][6][256] from mpo_bag_bwd             */
   const float* dkc;                     /* in  to pre_bwd : [B][6]      (NaCAGaT; else NULL)          */

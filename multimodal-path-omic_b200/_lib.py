@@ -70,7 +70,8 @@ class MpoTailIo(ctypes.Structure):
     """struct mpo_tail_io (include/mpo_b200.h)."""
     _fields_ = [
         ("num_slides", c_i32), ("omics", c_void_p * 6), ("ws", c_void_p),
-        ("qp", c_void_p), ("qk", c_void_p), ("kc", c_void_p), ("pooled", c_void_p), ("dpooled", c_void_p),
+        ("qp", c_void_p), ("qk", c_void_p), ("kc", c_void_p), ("pooled", c_void_p), ("suma", c_void_p), ("dsuma", c_void_p),
+        ("dpooled", c_void_p),
         ("dqk", c_void_p), ("dkc", c_void_p), ("dtq", c_void_p),
         ("hazards", c_void_p), ("S", c_void_p), ("Y", c_void_p), ("att_path", c_void_p), ("att_omic", c_void_p),
     ]
@@ -103,7 +104,10 @@ def lib():
 SIGNATURES = {
     "mpo_cast_bf16": [c_void_p, c_void_p, c_i64, c_void_p],
     "mpo_bag_fwd": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                    c_void_p, c_void_p, c_u32, c_void_p, c_float, c_void_p],
+                    c_void_p, c_void_p, c_void_p, c_u32, c_void_p, c_float, c_void_p],
+    "mpo_cast_f16": [c_void_p, c_void_p, c_i64, c_void_p],
+    "mpo_bag_gate_fwd": [ctypes.POINTER(MpoBag)] + [c_void_p] * 15 + [c_u32, c_void_p, c_float, c_void_p],
+    "mpo_attn_map_dropout": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_u32, c_void_p, c_float, c_void_p],
     "mpo_advance_seed": [c_void_p, c_void_p],
     "mpo_attn_map": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p],
     "mpo_bag_bwd": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

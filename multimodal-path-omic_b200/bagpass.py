@@ -117,12 +117,21 @@ class PackedBag:
 class BagWorkspace:
     """Per-batch device buffers of the bag stage (caller-owned in the C ABI; allocated here through torch)."""
 
-    def __init__(self, bag, save_h):
+    def __init__(self, bag, save_h, nacagat=False, save_gate=False):
         dev = bag.x.device
         T, B, R = bag.num_tiles, bag.num_slides, bag.total_rows
         f32 = dict(dtype=torch.float32, device=dev)
         self.scores = torch.empty((Q, R), **f32)
-        self.part_ml = torch.empty((T, 12), **f32)
+        self.nacagat = nacagat
+        self.scores_g = self.pgate = self.t_saved = self.suma = self.h_lo = None
+        if nacagat:
+            self.h_lo = torch.empty((R, D), dtype=torch.float16, device=dev)        # gate pass (mpo_bag_gate_fwd): gated scores always; P and tanh(k) only for a backward pass
+            self.scores_g = torch.empty((Q, R), **f32)
+            self.suma = torch.empty((B, Q), **f32)
+            if save_gate:
+                self.pgate = torch.empty((Q, R), **f32)
+                self.t_saved = torch.empty((R, D), dtype=torch.float16, device=dev)
+        self.part_ml = torch.empty((T, 18 if nacagat else 12), **f32)
         self.part_pool = torch.empty((T, Q, D), **f32)
         self.pooled = torch.empty((B, Q, D), **f32)
         self.lse = torch.empty((B, Q), **f32)
@@ -142,15 +151,44 @@ class BagWorkspace:
 def bag_forward(bag, w_h_bf16, bias_h, qk, ws, seed=0, drop_p=0.0, seed_dev=None):
     """mpo_bag_fwd: fills ws.scores / ws.pooled / ws.lse (and ws.h_saved when allocated)."""
     _lib.call("mpo_bag_fwd", bag.c(), _ptr(w_h_bf16), _ptr(bias_h), _ptr(qk), _ptr(ws.scores), _ptr(ws.part_ml),
-              _ptr(ws.part_pool), _ptr(ws.pooled), _ptr(ws.lse), _ptr(ws.h_saved), ctypes.c_uint32(seed & 0xFFFFFFFF),
+              _ptr(ws.part_pool), _ptr(ws.pooled), _ptr(ws.lse), _ptr(ws.h_saved), None, ctypes.c_uint32(seed & 0xFFFFFFFF),
               _ptr(seed_dev), ctypes.c_float(drop_p), _stream())
 
 
-def attention_map(bag, ws, out=None):
+def attention_map(bag, ws, out=None, seed=0, seed_dev=None, attn_drop_p=0.0):
     if out is None:
         out = torch.empty_like(ws.scores)
-    _lib.call("mpo_attn_map", bag.c(), _ptr(ws.scores), _ptr(ws.lse), _ptr(out), _stream())
+    if ws.nacagat:
+        _lib.call("mpo_attn_map_dropout", bag.c(), _ptr(ws.scores_g), _ptr(ws.lse), _ptr(out),
+                  ctypes.c_uint32(seed & 0xFFFFFFFF), _ptr(seed_dev), ctypes.c_float(attn_drop_p), _stream())
+    else:
+        _lib.call("mpo_attn_map", bag.c(), _ptr(ws.scores), _ptr(ws.lse), _ptr(out), _stream())
     return out
+
+
+def cast_f16(src, out=None):
+    """fp32 -> fp16 through mpo_cast_f16."""
+    require_cuda(src, "cast_f16 input")
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.float16, device=src.device)
+    _lib.call("mpo_cast_f16", _ptr(src), _ptr(out), src.numel(), _stream())
+    return out
+
+
+def bag_project(bag, w_h_bf16, bias_h, qk, ws, seed=0, drop_p=0.0, seed_dev=None):
+    """mpo_bag_fwd with pooled == NULL: activations (ws.h_saved) and raw folded scores only (NaCAGaT)."""
+    _lib.call("mpo_bag_fwd", bag.c(), _ptr(w_h_bf16), _ptr(bias_h), _ptr(qk), _ptr(ws.scores), None, None, None, None,
+              _ptr(ws.h_saved), _ptr(ws.h_lo), ctypes.c_uint32(seed & 0xFFFFFFFF), _ptr(seed_dev), ctypes.c_float(drop_p),
+              _stream())
+
+
+def bag_gate_forward(bag, w_k_f16, bias_k, qp, kc, ws, seed=0, attn_drop_p=0.0, seed_dev=None):
+    """mpo_bag_gate_fwd: fills ws.scores_g / ws.pooled / ws.lse / ws.suma (and ws.pgate, ws.t_saved when allocated)."""
+    _lib.call("mpo_bag_gate_fwd", bag.c(), _ptr(ws.h_saved), _ptr(ws.h_lo), _ptr(w_k_f16), _ptr(bias_k), _ptr(qp), _ptr(kc),
+              _ptr(ws.scores), _ptr(ws.scores_g), _ptr(ws.pgate), _ptr(ws.t_saved), _ptr(ws.part_ml), _ptr(ws.part_pool),
+              _ptr(ws.pooled), _ptr(ws.lse), _ptr(ws.suma), ctypes.c_uint32(seed & 0xFFFFFFFF), _ptr(seed_dev),
+              ctypes.c_float(attn_drop_p), _stream())
 
 
 def bag_backward(bag, ws, dpooled, qk, grad_w_h, grad_b_h, drop_p=0.0):

@@ -89,6 +89,32 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
   }
 }
 
+__global__ void cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+
+// NaCAGaT: amap = dropout(softmax(s')) -- the reference returns the post-dropout weights in train mode (blocks.py:189-199)
+__global__ void attn_map_drop_kernel(const TileInfo* __restrict__ tile_info, const float* __restrict__ scores,
+                                     const float* __restrict__ lse, float* __restrict__ amap, int total_rows,
+                                     uint32_t seed, const uint32_t* __restrict__ seed_dev, uint32_t thr, float scale) {
+  const TileInfo ti = tile_info[blockIdx.x];
+  const int r = threadIdx.x;
+  if (r >= ti.nvalid) return;
+  const uint32_t sd = seed_dev != nullptr ? (seed ^ __ldg(seed_dev)) : seed;
+#pragma unroll
+  for (int i = 0; i < kQ; ++i) {
+    const size_t o = static_cast<size_t>(i) * total_rows + ti.row0 + r;
+    float a = __expf(scores[o] - lse[ti.slide * kQ + i]);
+    if (thr != 0) {
+      const uint32_t rb = rng_u32(sd, 1u, static_cast<uint32_t>(i) * static_cast<uint32_t>(total_rows) +
+                                               static_cast<uint32_t>(ti.row0 + r)) & 0xFFu;
+      a = rb < thr ? 0.f : a * scale;
+    }
+    amap[o] = a;
+  }
+}
+
 // one block per tile: amap[i][row] = exp(scores[i][row] - lse[slide][i])
 __global__ void attn_map_kernel(const TileInfo* __restrict__ tile_info, const float* __restrict__ scores,
                                 const float* __restrict__ lse, float* __restrict__ amap, int total_rows) {
@@ -155,13 +181,16 @@ static int check_bag(const mpo_bag* bag, const char* who) {
 }
 
 int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, const float* qk, float* scores,
-                float* part_ml, float* part_pool, float* pooled, float* lse, void* h_saved, uint32_t seed,
+                float* part_ml, float* part_pool, float* pooled, float* lse, void* h_saved, void* h_lo, uint32_t seed,
                 const uint32_t* seed_dev, float drop_p, void* stream) {
   int rc = check_bag(bag, "mpo_bag_fwd");
   if (rc) return rc;
   if (bag->total_rows == 0 || bag->num_tiles == 0) return MPO_OK;
-  if (!w_h_bf16 || !bias_h || !qk || !scores || !part_ml || !part_pool || !pooled || !lse)
-    return fail(MPO_E_ARG, "%s", "mpo_bag_fwd: null pointer");
+  const bool project_only = pooled == nullptr;      // NaCAGaT: activations + raw scores, softmax in mpo_bag_gate_fwd
+  if (!w_h_bf16 || !bias_h || !qk || !scores) return fail(MPO_E_ARG, "%s", "mpo_bag_fwd: null pointer");
+  if (!project_only && (!part_ml || !part_pool || !lse)) return fail(MPO_E_ARG, "%s", "mpo_bag_fwd: null pointer");
+  if (project_only && (!h_saved || !h_lo))
+    return fail(MPO_E_ARG, "%s", "mpo_bag_fwd: a projection-only pass needs h_saved and h_lo");
   if (drop_p < 0.f || drop_p >= 1.f) return fail(MPO_E_ARG, "%s", "mpo_bag_fwd: drop_p must be in [0,1)");
   CUtensorMap tm_x, tm_w;
   rc = make_tmap_bf16_2d(&tm_x, bag->x, static_cast<uint64_t>(bag->total_rows), kDIn, kBK, kTileM);
@@ -178,8 +207,10 @@ int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, c
   p.part_ml = part_ml;
   p.part_pool = part_pool;
   p.h_out = static_cast<__half*>(h_saved);
+  p.h_lo_out = static_cast<__half*>(h_lo);
   p.seed = seed;
   p.seed_dev = seed_dev;
+  p.skip_pool = project_only ? 1 : 0;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MPO_FWD_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   p.drop_thr = static_cast<uint32_t>(drop_p * 256.f + 0.5f);
   p.drop_scale = p.drop_thr ? 256.f / static_cast<float>(256 - p.drop_thr) : 1.f;
@@ -190,8 +221,8 @@ int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, c
     if (rc) return rc;
   }
   rc = check_cuda(launch_bag_fwd(tm_x, tm_w, tm_h, p, num_sms(), st), "bag_fwd_kernel");
-  if (rc) return rc;
-  return check_cuda(launch_bag_merge(bag->tile_prefix, part_ml, part_pool, pooled, lse, bag->num_slides, st),
+  if (rc || project_only) return rc;
+  return check_cuda(launch_bag_merge(bag->tile_prefix, part_ml, 12, part_pool, pooled, lse, nullptr, bag->num_slides, st),
                     "bag_merge_kernel");
 }
 
@@ -213,6 +244,72 @@ int mpo_attn_map(const mpo_bag* bag, const float* scores, const float* lse, floa
       reinterpret_cast<const TileInfo*>(bag->tile_info), scores, lse, amap, static_cast<int>(bag->total_rows));
   count_launch();
   return check_cuda(cudaGetLastError(), "attn_map_kernel");
+}
+
+int mpo_cast_f16(const float* src, void* dst, int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && (!src || !dst))) return fail(MPO_E_ARG, "%s", "mpo_cast_f16: null pointer");
+  if (n == 0) return MPO_OK;
+  cast_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__half*>(dst), n);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "mpo_cast_f16");
+}
+
+static void drop_params(float drop_p, uint32_t* thr, float* scale) {
+  *thr = static_cast<uint32_t>(drop_p * 256.f + 0.5f);
+  *scale = *thr ? 256.f / static_cast<float>(256 - *thr) : 1.f;
+}
+
+int mpo_bag_gate_fwd(const mpo_bag* bag, const void* h_saved, const void* h_lo, const void* w_k_f16, const float* bias_k, const float* qp,
+                     const float* kc, float* scores, float* scores_g, float* pgate, void* t_saved, float* part_ml,
+                     float* part_pool, float* pooled, float* lse, float* suma, uint32_t seed, const uint32_t* seed_dev,
+                     float attn_drop_p, void* stream) {
+  int rc = check_bag(bag, "mpo_bag_gate_fwd");
+  if (rc) return rc;
+  if (bag->total_rows == 0 || bag->num_tiles == 0) return MPO_OK;
+  if (!h_saved || !h_lo || !w_k_f16 || !bias_k || !qp || !kc || !scores || !scores_g || !part_ml || !part_pool || !pooled ||
+      !lse || !suma)
+    return fail(MPO_E_ARG, "%s", "mpo_bag_gate_fwd: null pointer");
+  if ((pgate == nullptr) != (t_saved == nullptr))
+    return fail(MPO_E_ARG, "%s", "mpo_bag_gate_fwd: pgate and t_saved are kept (or dropped) together");
+  if (attn_drop_p < 0.f || attn_drop_p >= 1.f) return fail(MPO_E_ARG, "%s", "mpo_bag_gate_fwd: drop_p must be in [0,1)");
+  CUtensorMap tm_h, tm_hlo, tm_w;
+  rc = make_tmap_16b_2d(&tm_h, h_saved, static_cast<uint64_t>(bag->total_rows), kD, 64, kTileM, true);
+  if (rc) return rc;
+  rc = make_tmap_16b_2d(&tm_hlo, h_lo, static_cast<uint64_t>(bag->total_rows), kD, 64, kTileM, true);
+  if (rc) return rc;
+  rc = make_tmap_16b_2d(&tm_w, w_k_f16, kD, kD, 64, kD, true);
+  if (rc) return rc;
+  BagGateParams p;
+  p.tile_info = reinterpret_cast<const TileInfo*>(bag->tile_info);
+  p.num_tiles = bag->num_tiles;
+  p.total_rows = static_cast<int>(bag->total_rows);
+  p.qp = qp; p.kc = kc; p.bias_k = bias_k;
+  p.scores = scores; p.scores_g = scores_g; p.pgate = pgate;
+  p.t_out = static_cast<__half*>(t_saved);
+  p.part_ml = part_ml; p.part_pool = part_pool;
+  p.seed = seed; p.seed_dev = seed_dev;
+  drop_params(attn_drop_p, &p.drop_thr, &p.drop_scale);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = check_cuda(launch_bag_gate(tm_h, tm_hlo, tm_w, p, num_sms(), st), "bag_gate_kernel");
+  if (rc) return rc;
+  return check_cuda(launch_bag_merge(bag->tile_prefix, part_ml, 18, part_pool, pooled, lse, suma, bag->num_slides, st),
+                    "bag_merge_kernel");
+}
+
+int mpo_attn_map_dropout(const mpo_bag* bag, const float* scores_g, const float* lse, float* amap, uint32_t seed,
+                         const uint32_t* seed_dev, float attn_drop_p, void* stream) {
+  int rc = check_bag(bag, "mpo_attn_map_dropout");
+  if (rc) return rc;
+  if (bag->num_tiles == 0) return MPO_OK;
+  if (!scores_g || !lse || !amap) return fail(MPO_E_ARG, "%s", "mpo_attn_map_dropout: null pointer");
+  uint32_t thr; float scale;
+  drop_params(attn_drop_p, &thr, &scale);
+  attn_map_drop_kernel<<<bag->num_tiles, kTileM, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const TileInfo*>(bag->tile_info), scores_g, lse, amap, static_cast<int>(bag->total_rows), seed,
+      seed_dev, thr, scale);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "attn_map_drop_kernel");
 }
 
 int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, const float* lse, const float* pooled,

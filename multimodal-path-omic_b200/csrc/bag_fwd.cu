@@ -260,6 +260,17 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           pk.y = pack_f16x2(h[2], h[3]);
           pk.z = pack_f16x2(h[4], h[5]);
           pk.w = pack_f16x2(h[6], h[7]);
+          if (p.h_lo_out != nullptr && grow < static_cast<uint32_t>(p.total_rows)) {
+            // NaCAGaT: the fp16 remainder h - fp16(h), so that the key projection K = H W_k^T (tensor cores, in
+            // bag_gate_kernel) sees ~22-bit activations: its tanh gate dots feed a softmax argument directly
+            const float2 a0 = unpack_f16x2(pk.x), a1 = unpack_f16x2(pk.y), a2 = unpack_f16x2(pk.z), a3 = unpack_f16x2(pk.w);
+            uint4 lo;
+            lo.x = pack_f16x2(h[0] - a0.x, h[1] - a0.y);
+            lo.y = pack_f16x2(h[2] - a1.x, h[3] - a1.y);
+            lo.z = pack_f16x2(h[4] - a2.x, h[5] - a2.y);
+            lo.w = pack_f16x2(h[6] - a3.x, h[7] - a3.y);
+            *reinterpret_cast<uint4*>(p.h_lo_out + static_cast<size_t>(grow) * kD + col0 + j) = lo;
+          }
           const int j16 = (col0 + j) >> 3;           // 16-byte chunk index within the 512 B row
           const int cb = j16 >> 3, jj = j16 & 7;     // 64-feature block, chunk within the 128 B swizzle row
           *reinterpret_cast<uint4*>(staging + cb * (kTileM * 128) + r * 128 + ((jj ^ (r & 7)) << 4)) = pk;
@@ -286,8 +297,19 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         const float2 o1 = *reinterpret_cast<const float2*>(spart_s + r * 8 + 4);
         s[0] += o0.x; s[1] += o0.y; s[2] += o0.z; s[3] += o0.w; s[4] += o1.x; s[5] += o1.y;
 #pragma unroll
-        for (int i = 0; i < kQ; ++i) {
+        for (int i = 0; i < kQ; ++i)
           if (valid) p.scores[static_cast<size_t>(i) * p.total_rows + ti.row0 + r] = s[i];
+      }
+      if (p.skip_pool) {
+        // NaCAGaT: the softmax runs on the gated scores in bag_gate_kernel; this pass only projects and scores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        continue;
+      }
+      if (ch == 0) {
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
           float m = valid ? s[i] : -INFINITY;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -367,15 +389,16 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 bag_merge_kernel(const int* __restrict__ tile_prefix,   // [B+1] first tile of each slide
-                 const float* __restrict__ part_ml, const float* __restrict__ part_pool,
-                 float* __restrict__ pooled, float* __restrict__ lse) {
+                 const float* __restrict__ part_ml, const int mls,   // per-tile stats, mls floats per tile (12 or 18)
+                 const float* __restrict__ part_pool, float* __restrict__ pooled, float* __restrict__ lse,
+                 float* __restrict__ suma) {   // suma (NaCAGaT, mls = 18): sum_n of the dropped-and-rescaled weights
   // one block per (slide, query); 4 tile groups x 64 float4 feature columns, many independent loads in flight
   __shared__ float red[8];
   __shared__ float4 acc_s[4][64];
   const int b = blockIdx.x, i = blockIdx.y, tid = threadIdx.x;
   const int t0 = tile_prefix[b], t1 = tile_prefix[b + 1];
   float m = -INFINITY;
-  for (int t = t0 + tid; t < t1; t += 256) m = fmaxf(m, __ldg(part_ml + static_cast<size_t>(t) * 12 + i));
+  for (int t = t0 + tid; t < t1; t += 256) m = fmaxf(m, __ldg(part_ml + static_cast<size_t>(t) * mls + i));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((tid & 31) == 0) red[tid >> 5] = m;
@@ -386,7 +409,7 @@ bag_merge_kernel(const int* __restrict__ tile_prefix,   // [B+1] first tile of e
   __syncthreads();
   float l = 0.f;
   for (int t = t0 + tid; t < t1; t += 256)
-    l = fmaf(__ldg(part_ml + static_cast<size_t>(t) * 12 + 6 + i), __expf(__ldg(part_ml + static_cast<size_t>(t) * 12 + i) - M), l);
+    l = fmaf(__ldg(part_ml + static_cast<size_t>(t) * mls + 6 + i), __expf(__ldg(part_ml + static_cast<size_t>(t) * mls + i) - M), l);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
   if ((tid & 31) == 0) red[tid >> 5] = l;
@@ -398,7 +421,7 @@ bag_merge_kernel(const int* __restrict__ tile_prefix,   // [B+1] first tile of e
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
   for (int t = t0 + tg; t < t1; t += 4) {
-    const float w = __expf(__ldg(part_ml + static_cast<size_t>(t) * 12 + i) - M);
+    const float w = __expf(__ldg(part_ml + static_cast<size_t>(t) * mls + i) - M);
     const float4 v = __ldg(reinterpret_cast<const float4*>(part_pool + (static_cast<size_t>(t) * kQ + i) * kD) + dq);
     acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
   }
@@ -413,6 +436,22 @@ bag_merge_kernel(const int* __restrict__ tile_prefix,   // [B+1] first tile of e
     reinterpret_cast<float4*>(pooled + (static_cast<size_t>(b) * kQ + i) * kD)[tid] = r;
   }
   if (tid == 0) lse[b * kQ + i] = M + __logf(L);
+  if (suma != nullptr) {       // block-uniform
+    __syncthreads();
+    float ld = 0.f;
+    for (int t = t0 + tid; t < t1; t += 256)
+      ld = fmaf(__ldg(part_ml + static_cast<size_t>(t) * mls + 12 + i), __expf(__ldg(part_ml + static_cast<size_t>(t) * mls + i) - M), ld);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
+    if ((tid & 31) == 0) red[tid >> 5] = ld;
+    __syncthreads();
+    if (tid == 0) {
+      float LD = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) LD += red[w];
+      suma[b * kQ + i] = LD / L;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -473,10 +512,10 @@ cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, con
   }
 }
 
-cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, const float* part_pool, float* pooled,
-                             float* lse, int B, cudaStream_t stream) {
+cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, int ml_stride, const float* part_pool,
+                             float* pooled, float* lse, float* suma, int B, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
-  bag_merge_kernel<<<dim3(B, kQ), 256, 0, stream>>>(tile_prefix, part_ml, part_pool, pooled, lse);
+  bag_merge_kernel<<<dim3(B, kQ), 256, 0, stream>>>(tile_prefix, part_ml, ml_stride, part_pool, pooled, lse, suma);
   count_launch();
   return cudaGetLastError();
 }

@@ -16,8 +16,10 @@ inline void count_launch(int n = 1) { g_launches += n; }
 int fwd_cluster_size();   // CTAs per cluster of the forward bag kernel (1, 2 or 4; env MPO_FWD_CLUSTER)
 cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const CUtensorMap& tm_h,
                            const BagFwdParams& prm, int num_sms, cudaStream_t stream);
-cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, const float* part_pool, float* pooled,
-                             float* lse, int B, cudaStream_t stream);
+cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, int ml_stride, const float* part_pool,
+                             float* pooled, float* lse, float* suma, int B, cudaStream_t stream);
+cudaError_t launch_bag_gate(const CUtensorMap& tm_h, const CUtensorMap& tm_hlo, const CUtensorMap& tm_w,
+                            const BagGateParams& prm, int num_sms, cudaStream_t stream);
 cudaError_t launch_bag_bwd_dz(const CUtensorMap& tm_h, const CUtensorMap& tm_dz, const BagBwdDzParams& prm, int num_sms,
                               cudaStream_t stream);
 cudaError_t launch_bag_bwd_reduce(const int* tile_prefix, const float* part_dqk, const float* part_db, float* dqk,

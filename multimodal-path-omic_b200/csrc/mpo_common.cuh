@@ -32,12 +32,34 @@ struct BagFwdParams {
   float* part_ml;              // [num_tiles][12]             tile max (6) and tile sum of exp (6)
   float* part_pool;            // [num_tiles][6][256]         sum_n exp(s - m_tile) h_n
   __half* h_out;               // [total_rows][256] or null   saved activations (fp16) for the backward pass
+  __half* h_lo_out;            // [total_rows][256] or null   fp16 remainder h - fp16(h) (NaCAGaT key projection)
   uint32_t seed;               // dropout stream (train mode)
   const uint32_t* seed_dev;    // when non-null the stream id is read from device memory (CUDA-graph replays)
   uint32_t drop_thr;           // drop an element when its 8 random bits < drop_thr (0 = eval)
   float drop_scale;            // 1 / keep probability
+  int skip_pool;               // 1: write activations and raw scores only (NaCAGaT: softmax runs on gated scores)
   int debug;                   // timing experiments only (env MPO_FWD_DEBUG): bit0 skip W loads, bit1 X from L2,
                                // bit2 L2-prefetch the next tile's X
+};
+
+// NaCAGaT gate pass (bag_gate.cu)
+struct BagGateParams {
+  const TileInfo* tile_info;
+  int num_tiles;
+  int total_rows;
+  const float* qp;             // [B][6][256]   projected queries q_i (tanh taken in the kernel)
+  const float* kc;             // [B][6]        key-bias score term b_k . q_i / 16
+  const float* bias_k;         // [256]         co_attention.in_proj_bias[256:512]
+  float* scores;               // [6][total_rows] in: h.qk_i ; rewritten as s = h.qk_i + kc_i when pgate != null
+  float* scores_g;             // [6][total_rows] out: gated scores s' = s P
+  float* pgate;                // [6][total_rows] out: P (kept for the backward pass) or null
+  __half* t_out;               // [total_rows][256] out: tanh(k) fp16 (kept for the backward pass) or null
+  float* part_ml;              // [num_tiles][18]  tile max, sum of exp, sum of dropped-and-rescaled exp
+  float* part_pool;            // [num_tiles][6][256]
+  uint32_t seed;
+  const uint32_t* seed_dev;
+  uint32_t drop_thr;           // attention dropout (blocks.py:189-190): drop when 8 random bits < drop_thr
+  float drop_scale;
 };
 
 struct BagBwdDzParams {

@@ -509,7 +509,17 @@ int mpo_tail_post_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   enc_fwd(co, m->omic_tr[1], w.enc[3], ws, ws + w.enc[2].y2, B);
   pool_fwd(co, m->omic_pool, w.pool[1], ws, ws + w.enc[3].y2, io->att_omic, B);
   // path branch: value and output projections on the pooled vectors (folded form of mcat.py:97)
-  lin_fwd(c, io->pooled, E, sub(m->coattn_in, 2 * E, E), E, E, ws + w.v, E, R, ACT_NONE);
+  if (io->suma == nullptr) {
+    lin_fwd(c, io->pooled, E, sub(m->coattn_in, 2 * E, E), E, E, ws + w.v, E, R, ACT_NONE);
+  } else {
+    // attention dropout leaves sum_n a'_in != 1: v_i = W_v pooled_i + (sum_n a'_in) b_v   (blocks.py:189-192)
+    mpo_lin Lv = sub(m->coattn_in, 2 * E, E);
+    const float* bv = Lv.b;
+    Lv.b = nullptr;
+    lin_fwd(c, io->pooled, E, Lv, E, E, ws + w.v, E, R, ACT_NONE);
+    GemmArgs g{io->suma, 1, 0, bv, 0, 1, ws + w.v, E, nullptr, R, E, 1, 1.f, 1, ACT_NONE, nullptr};
+    c.chk(launch_gemm(g, c.st), "v.suma_bias");
+  }
   lin_fwd(c, ws + w.v, E, m->coattn_out, E, E, ws + w.hc, E, R, ACT_NONE);
   if (m->variant == MPO_VARIANT_NACAGAT) {
     cag_fwd(c, m->cag, w, ws, ws + w.G, io->qp, R);                      // blocks.py:110
@@ -614,7 +624,23 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
   // output and value projections back to the pooled vectors
   join_w(cp);
   lin_bwd(cp, dhc, E, ws + w.v, E, m->coattn_out, E, E, ws + w.dv, E, R, false);
-  lin_bwd(cp, ws + w.dv, E, io->pooled, E, sub(m->coattn_in, 2 * E, E), E, E, io->dpooled, E, R, false);
+  if (io->suma == nullptr) {
+    lin_bwd(cp, ws + w.dv, E, io->pooled, E, sub(m->coattn_in, 2 * E, E), E, E, io->dpooled, E, R, false);
+  } else {
+    if (!io->dsuma) return fail(MPO_E_ARG, "%s", "mpo_tail_post_bwd: dsuma is NULL although suma is given");
+    mpo_lin Lv = sub(m->coattn_in, 2 * E, E);
+    float* gbv = Lv.gb;
+    const float* bv = Lv.b;
+    Lv.gb = nullptr;
+    lin_bwd(cp, ws + w.dv, E, io->pooled, E, Lv, E, E, io->dpooled, E, R, false);
+    // dsuma[r] = dv[r] . b_v ;  db_v[e] += sum_r suma[r] dv[r][e]
+    GemmArgs g1{ws + w.dv, E, 1, bv, 1, 0, io->dsuma, 1, nullptr, R, 1, E, 1.f, 0, ACT_NONE, nullptr};
+    cp.chk(launch_gemm(g1, cp.st), "v.dsuma");
+    if (gbv) {
+      GemmArgs g2{io->suma, 0, 1, ws + w.dv, E, 1, gbv, E, nullptr, 1, E, R, 1.f, 1, ACT_NONE, nullptr};
+      cp.chk(launch_gemm(g2, cp.st), "v.dbv");
+    }
+  }
   join(br);
   if (m->variant == MPO_VARIANT_NACAGAT) {   // needs dG of the omic branch: after the join
     cag_bwd(br.main, m->cag, w, ws, ws + w.G, io->qp, dhc, ws + w.dG, ws + w.dqp, R);

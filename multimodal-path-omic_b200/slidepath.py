@@ -147,11 +147,13 @@ class SlideState:
 
 
 class SlideEngine:
-    def __init__(self, binding, bag_dropout=0.25):
+    def __init__(self, binding, bag_dropout=0.25, attn_dropout=0.25):
         self.binding = binding
         self.bag_dropout = float(bag_dropout)
+        self.attn_dropout = float(attn_dropout)     # NaCAGaT: PreGatingContextualAttention(dropout_p=0.25), blocks.py:52
         self._ws_cache = {}
         self._w_bf16 = None
+        self._wk_f16 = None
 
     # -- helpers
     def _tail_ws(self, model, B, device, reuse):
@@ -185,6 +187,12 @@ class SlideEngine:
         io.qk = st.qk.data_ptr()
         io.kc = st.kc.data_ptr() if st.kc is not None else None
         io.pooled = st.bag_ws.pooled.data_ptr()
+        # sum_n a'_in differs from 1 only under attention dropout (NaCAGaT, train mode)
+        use_suma = st.bag_ws.nacagat and getattr(st, "attn_p", 0.0) > 0.0
+        io.suma = st.bag_ws.suma.data_ptr() if use_suma else None
+        io.dsuma = st.dsuma.data_ptr() if (use_suma and st.dsuma is not None) else None
+        io.dkc = st.dkc.data_ptr() if st.dkc is not None else None
+        io.dtq = st.dtq.data_ptr() if st.dtq is not None else None
         io.dpooled = st.dpooled.data_ptr() if st.dpooled is not None else None
         io.dqk = st.dqk.data_ptr() if st.dqk is not None else None
         io.hazards = st.hazards.data_ptr()
@@ -206,14 +214,16 @@ class SlideEngine:
         st.tail_ws = self._tail_ws(model, B, dev, reuse_ws)
         st.qp = torch.empty((B, Q, D), **f32)
         st.qk = torch.empty((B, Q, D), **f32)
-        st.kc = None
-        st.dpooled = st.dqk = None
+        nac = bnd.variant == VARIANT_NACAGAT
+        st.kc = torch.empty((B, Q), **f32) if nac else None
+        st.dpooled = st.dqk = st.dsuma = st.dkc = st.dtq = None
         st.hazards = torch.empty((B, K), **f32)
         st.S = torch.empty((B, K), **f32)
         st.Y = torch.empty((B, K), **f32)
         st.att_path = torch.empty((B, Q), **f32)
         st.att_omic = torch.empty((B, Q), **f32)
-        st.bag_ws = bp.BagWorkspace(bag, save_h=save_for_backward)
+        st.bag_ws = bp.BagWorkspace(bag, save_h=save_for_backward or nac, nacagat=nac,
+                                    save_gate=nac and save_for_backward)
         st.seed_dev = None
         if with_backward_buffers:
             st.bag_ws.ensure_bwd(bag)
@@ -230,8 +240,7 @@ class SlideEngine:
         """bag: PackedBag of B slides; omics: 6 tensors [B, d_i] float32 on the GPU.  `st` reuses the buffers of an
         earlier alloc_state() (static addresses: needed for CUDA-graph capture)."""
         bnd = self.binding
-        if bnd.variant == VARIANT_NACAGAT:
-            raise NotImplementedError("NaCAGaT bag kernels are not wired into this build yet")
+        nac = bnd.variant == VARIANT_NACAGAT
         B = bag.num_slides
         if st is None:
             st = self.alloc_state(model, bag, save_for_backward, reuse_ws)
@@ -246,6 +255,7 @@ class SlideEngine:
                 raise RuntimeError("omics[%d] has width %d, the model expects %d" % (i, o.shape[1], bnd.omic_sizes[i]))
             st.omics.append(o)
         st.drop_p = self.bag_dropout if train else 0.0
+        st.attn_p = self.attn_dropout if (train and nac) else 0.0
         st.seed = (_next_seed() if seed is None else seed) if train else 0
         P = bnd.params()
         # bf16 streaming copy of H.0.weight (refreshed every pass: the optimizer updates the fp32 master in place)
@@ -256,8 +266,20 @@ class SlideEngine:
         io = self._io(st)
         s = _stream()
         _lib.call("mpo_tail_pre_fwd", ctypes.byref(model), ctypes.byref(io), s)
-        bp.bag_forward(bag, self._w_bf16, P["H.0.bias"].detach(), st.qk, st.bag_ws, seed=st.seed, drop_p=st.drop_p,
-                       seed_dev=st.seed_dev if train else None)
+        if nac:
+            # fp16 streaming copy of the key projection (the gate kernels read it as a tensor-core operand)
+            w_in = P["co_attention.in_proj_weight"].detach()
+            if self._wk_f16 is None or self._wk_f16.device != w_in.device:
+                self._wk_f16 = torch.empty((D, D), dtype=torch.float16, device=w_in.device)
+            bp.cast_f16(w_in[D:2 * D], out=self._wk_f16)
+            sd = st.seed_dev if train else None
+            bp.bag_project(bag, self._w_bf16, P["H.0.bias"].detach(), st.qk, st.bag_ws, seed=st.seed, drop_p=st.drop_p,
+                           seed_dev=sd)
+            bp.bag_gate_forward(bag, self._wk_f16, P["co_attention.in_proj_bias"].detach()[D:2 * D], st.qp, st.kc,
+                                st.bag_ws, seed=st.seed, attn_drop_p=st.attn_p, seed_dev=sd)
+        else:
+            bp.bag_forward(bag, self._w_bf16, P["H.0.bias"].detach(), st.qk, st.bag_ws, seed=st.seed, drop_p=st.drop_p,
+                           seed_dev=st.seed_dev if train else None)
         if after_bag is not None:        # e.g. the cross-GPU log-sum-exp combine of a patch-sharded bag (dp.py)
             after_bag(st)
         _lib.call("mpo_tail_post_fwd", ctypes.byref(model), ctypes.byref(io), s)
@@ -265,7 +287,8 @@ class SlideEngine:
 
     def attention_map(self, st):
         """normalised co-attention map [6, total_rows] (attention_scores['coattn'])."""
-        return bp.attention_map(st.bag, st.bag_ws)
+        return bp.attention_map(st.bag, st.bag_ws, seed=st.seed, seed_dev=st.seed_dev if st.train else None,
+                                attn_drop_p=getattr(st, "attn_p", 0.0))
 
     # -- backward
     def backward(self, model, st, dhaz, dS, dY):
