@@ -114,6 +114,49 @@ int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, co
                 const float* dpooled, const float* qk, void* dz_ws, float* part_dqk, float* part_db, float* dqk,
                 float* grad_w_h, float* grad_b_h, float drop_p, void* stream);
 
+/* NaCAGaT bag-pass backward (autograd of nacagat.py:83,93 / blocks.py:156-192 w.r.t. H.0.*, the key projection and the
+ * query-side operands).  All pointers are device pointers; workspaces are caller-owned. */
+typedef struct mpo_nacagat_bwd {
+  /* kept by mpo_bag_fwd (projection-only) and mpo_bag_gate_fwd */
+  const void* h_saved;        /* fp16 [total_rows][256]                                     */
+  const void* t_saved;        /* fp16 [total_rows][256]  tanh(k)                            */
+  const float* scores;        /* fp32 [6][total_rows]    s (with the key-bias term)         */
+  const float* pgate;         /* fp32 [6][total_rows]    P                                  */
+  const float* lse;           /* fp32 [B][6]             of s' = s P                        */
+  const float* pooled;        /* fp32 [B][6][256]                                           */
+  const float* suma;          /* fp32 [B][6] or NULL (no attention dropout)                 */
+  /* upstream gradients (mpo_tail_post_bwd) */
+  const float* dpooled;       /* fp32 [B][6][256]                                           */
+  const float* dsuma;         /* fp32 [B][6] or NULL, together with suma                    */
+  /* query-side operands (mpo_tail_pre_fwd) and the fp16 key projection */
+  const float* qk;            /* fp32 [B][6][256]                                           */
+  const float* qp;            /* fp32 [B][6][256]                                           */
+  const void* w_k_f16;        /* fp16 [256][256]                                            */
+  /* workspaces */
+  void* dz_ws;                /* bf16 [total_rows][256]                                     */
+  void* dkg_ws;               /* fp16 [total_rows][256]                                     */
+  float* dg_ws;               /* fp32 [6][total_rows]                                       */
+  float* part_dqk;            /* fp32 [num_tiles][6][256]                                   */
+  float* part_dtq;            /* fp32 [num_tiles][6][256]                                   */
+  float* part_db;             /* fp32 [num_tiles][256]                                      */
+  float* part_dbk;            /* fp32 [num_tiles][256]                                      */
+  float* part_dkc;            /* fp32 [num_tiles][8]                                        */
+  uint32_t* dg_max;           /* one word                                                   */
+  /* results: dqk, dkc, dtq are overwritten (inputs of mpo_tail_pre_bwd); grad_* are accumulated */
+  float* dqk;                 /* fp32 [B][6][256]                                           */
+  float* dkc;                 /* fp32 [B][6]                                                */
+  float* dtq;                 /* fp32 [B][6][256]  gradient w.r.t. tanh(q_i)                */
+  float* grad_w_h;            /* fp32 [256][1024]                                           */
+  float* grad_b_h;            /* fp32 [256]                                                 */
+  float* grad_w_k;            /* fp32 [256][256]   gate part of co_attention.in_proj_weight[256:512]' gradient */
+  float* grad_b_k;            /* fp32 [256]        gate part of co_attention.in_proj_bias[256:512]'s gradient  */
+  float drop_p;               /* bag dropout of the forward pass                            */
+  float attn_drop_p;          /* attention dropout of the forward pass                      */
+  uint32_t seed;              /* mask stream of the forward pass                            */
+  const uint32_t* seed_dev;
+} mpo_nacagat_bwd;
+int mpo_bag_bwd_nacagat(const mpo_bag* bag, const mpo_nacagat_bwd* args, void* stream);
+
 /* Cross-shard log-sum-exp combine for one bag split by patch range over `nshards` ranks:
  * lse_in fp32 [nshards][6], pooled_in fp32 [nshards][6][256] (each shard's normalised result, e.g. after an
  * all-gather) -> lse_out [6], pooled_out [6][256]. */
@@ -200,7 +243,8 @@ typedef struct mpo_tail_io {
   float* att_path; float* att_omic;     /* [B][6] raw pooling logits (attention_scores['path'/'omic']) */
 } mpo_tail_io;
 
-/* ABI self-check for bindings: sizeof(mpo_bag) (which = 0), sizeof(mpo_model) (1), sizeof(mpo_tail_io) (2) */
+/* ABI self-check for bindings: sizeof(mpo_bag) (which = 0), sizeof(mpo_model) (1), sizeof(mpo_tail_io) (2),
+ * sizeof(mpo_nacagat_bwd) (3) */
 int64_t mpo_sizeof(int32_t which);
 /* workspace size in floats for a batch of B slides */
 int64_t mpo_tail_ws_floats(const mpo_model* m, int32_t B);

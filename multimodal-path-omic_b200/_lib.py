@@ -77,6 +77,15 @@ class MpoTailIo(ctypes.Structure):
     ]
 
 
+class MpoNacagatBwd(ctypes.Structure):
+    """struct mpo_nacagat_bwd (include/mpo_b200.h)."""
+    _fields_ = [(n, c_void_p) for n in (
+        "h_saved", "t_saved", "scores", "pgate", "lse", "pooled", "suma", "dpooled", "dsuma", "qk", "qp", "w_k_f16",
+        "dz_ws", "dkg_ws", "dg_ws", "part_dqk", "part_dtq", "part_db", "part_dbk", "part_dkc", "dg_max",
+        "dqk", "dkc", "dtq", "grad_w_h", "grad_b_h", "grad_w_k", "grad_b_k")] + [
+        ("drop_p", c_float), ("attn_drop_p", c_float), ("seed", c_u32), ("seed_dev", c_void_p)]
+
+
 _lib = None
 
 
@@ -112,6 +121,7 @@ SIGNATURES = {
     "mpo_attn_map": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p],
     "mpo_bag_bwd": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p],
+    "mpo_bag_bwd_nacagat": [ctypes.POINTER(MpoBag), ctypes.POINTER(MpoNacagatBwd), c_void_p],
     "mpo_lse_combine": [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p],
     "mpo_tail_pre_fwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],
     "mpo_tail_post_fwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],
@@ -135,7 +145,7 @@ def _declare(L):
     L.mpo_launch_count.argtypes = [c_i32]
     L.mpo_sizeof.restype = c_i64
     L.mpo_sizeof.argtypes = [c_i32]
-    for which, st in enumerate((MpoBag, MpoModel, MpoTailIo)):
+    for which, st in enumerate((MpoBag, MpoModel, MpoTailIo, MpoNacagatBwd)):
         if L.mpo_sizeof(which) != ctypes.sizeof(st):
             raise RuntimeError("ABI mismatch: %s is %d bytes in libmpo_b200.so but %d in the ctypes binding"
                                % (st.__name__, L.mpo_sizeof(which), ctypes.sizeof(st)))

@@ -146,6 +146,13 @@ class BagWorkspace:
             self.dz = torch.empty((bag.total_rows, D), dtype=torch.bfloat16, device=dev)
             self.part_dqk = torch.empty((bag.num_tiles, Q, D), dtype=torch.float32, device=dev)
             self.part_db = torch.empty((bag.num_tiles, D), dtype=torch.float32, device=dev)
+            if self.nacagat:
+                self.dkg = torch.empty((bag.total_rows, D), dtype=torch.float16, device=dev)
+                self.dg = torch.empty((Q, bag.total_rows), dtype=torch.float32, device=dev)
+                self.part_dtq = torch.empty((bag.num_tiles, Q, D), dtype=torch.float32, device=dev)
+                self.part_dbk = torch.empty((bag.num_tiles, D), dtype=torch.float32, device=dev)
+                self.part_dkc = torch.empty((bag.num_tiles, 8), dtype=torch.float32, device=dev)
+                self.dg_max = torch.zeros(1, dtype=torch.int32, device=dev)
 
 
 def bag_forward(bag, w_h_bf16, bias_h, qk, ws, seed=0, drop_p=0.0, seed_dev=None):

@@ -322,17 +322,16 @@ int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, co
       !grad_w_h || !grad_b_h)
     return fail(MPO_E_ARG, "%s", "mpo_bag_bwd: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  BagBwdDzParams p;
+  BagBwdDzParams p = {};
   p.tile_info = reinterpret_cast<const TileInfo*>(bag->tile_info);
   p.num_tiles = bag->num_tiles;
   p.total_rows = static_cast<int>(bag->total_rows);
-  p.h = static_cast<const __half*>(h_saved);
   p.scores = scores;
   p.lse = lse;
   p.pooled = pooled;
   p.dpooled = dpooled;
   p.qk = qk;
-  p.dz = static_cast<__nv_bfloat16*>(dz_ws);
+  p.out = dz_ws;
   p.part_dqk = part_dqk;
   p.part_db = part_db;
   const uint32_t thr = static_cast<uint32_t>(drop_p * 256.f + 0.5f);
@@ -342,7 +341,7 @@ int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, co
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_dzs, dz_ws, static_cast<uint64_t>(bag->total_rows), kD, 64, kTileM);
   if (rc) return rc;
-  rc = check_cuda(launch_bag_bwd_dz(tm_h, tm_dzs, p, num_sms(), st), "bag_bwd_dz_kernel");
+  rc = check_cuda(launch_bag_bwd_dz(0, tm_h, tm_dzs, p, num_sms(), st), "bag_bwd_dz_kernel");
   if (rc) return rc;
   rc = check_cuda(launch_bag_bwd_reduce(bag->tile_prefix, part_dqk, part_db, dqk, grad_b_h, bag->num_slides,
                                         bag->num_tiles, st),
@@ -353,8 +352,77 @@ int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, co
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_x, bag->x, static_cast<uint64_t>(bag->total_rows), kDIn, 64, 64);
   if (rc) return rc;
-  return check_cuda(launch_bag_bwd_dw(tm_dz, tm_x, grad_w_h, static_cast<int>(bag->total_rows), num_sms(), st),
+  return check_cuda(launch_bag_bwd_dw(tm_dz, tm_x, grad_w_h, static_cast<int>(bag->total_rows), kDIn, kDIn, false, nullptr,
+                                          num_sms(), st),
                     "bag_bwd_dw_kernel");
+}
+
+int mpo_bag_bwd_nacagat(const mpo_bag* bag, const mpo_nacagat_bwd* a, void* stream) {
+  int rc = check_bag(bag, "mpo_bag_bwd_nacagat");
+  if (rc) return rc;
+  if (!a) return fail(MPO_E_ARG, "%s", "mpo_bag_bwd_nacagat: argument block is NULL");
+  if (bag->total_rows == 0 || bag->num_tiles == 0) return MPO_OK;
+  if (!a->h_saved || !a->t_saved || !a->scores || !a->pgate || !a->lse || !a->pooled || !a->dpooled || !a->qk || !a->qp ||
+      !a->w_k_f16 || !a->dz_ws || !a->dkg_ws || !a->dg_ws || !a->part_dqk || !a->part_dtq || !a->part_db || !a->part_dbk ||
+      !a->part_dkc || !a->dg_max || !a->dqk || !a->dkc || !a->dtq || !a->grad_w_h || !a->grad_b_h || !a->grad_w_k ||
+      !a->grad_b_k)
+    return fail(MPO_E_ARG, "%s", "mpo_bag_bwd_nacagat: null pointer");
+  if ((a->suma == nullptr) != (a->dsuma == nullptr))
+    return fail(MPO_E_ARG, "%s", "mpo_bag_bwd_nacagat: suma and dsuma go together");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint64_t R = static_cast<uint64_t>(bag->total_rows);
+  const int ns = num_sms();
+  CUtensorMap tm_h, tm_t, tm_dz, tm_dkg, tm_wk;
+  if ((rc = make_tmap_16b_2d(&tm_h, a->h_saved, R, kD, 64, kTileM, true))) return rc;
+  if ((rc = make_tmap_16b_2d(&tm_t, a->t_saved, R, kD, 64, kTileM, true))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm_dz, a->dz_ws, R, kD, 64, kTileM))) return rc;
+  if ((rc = make_tmap_16b_2d(&tm_dkg, a->dkg_ws, R, kD, 64, kTileM, true))) return rc;
+  if ((rc = make_tmap_16b_2d(&tm_wk, a->w_k_f16, kD, kD, 64, 64, true))) return rc;
+  rc = check_cuda(cudaMemsetAsync(a->dg_max, 0, sizeof(uint32_t), st), "memset dg_max");
+  if (rc) return rc;
+
+  BagBwdDzParams p = {};
+  p.tile_info = reinterpret_cast<const TileInfo*>(bag->tile_info);
+  p.num_tiles = bag->num_tiles;
+  p.total_rows = static_cast<int>(bag->total_rows);
+  p.scores = a->scores; p.lse = a->lse; p.pooled = a->pooled; p.dpooled = a->dpooled; p.qk = a->qk;
+  p.pgate = a->pgate; p.suma = a->suma; p.dsuma = a->dsuma; p.qp = a->qp;
+  p.dg = a->dg_ws; p.dg_max = a->dg_max; p.part_dkc = a->part_dkc;
+  p.seed = a->seed; p.seed_dev = a->seed_dev;
+  drop_params(a->attn_drop_p, &p.attn_thr, &p.attn_scale);
+  { uint32_t thr; drop_params(a->drop_p, &thr, &p.keep_scale); }
+  // value / fold path: dz_part, dqk, dkc, dg
+  p.out = a->dz_ws; p.part_dqk = a->part_dqk; p.part_db = nullptr;
+  if ((rc = check_cuda(launch_bag_bwd_dz(1, tm_h, tm_dz, p, ns, st), "bag_bwd_dz_kernel<nacagat dh>"))) return rc;
+  if ((rc = check_cuda(launch_bag_bwd_reduce(bag->tile_prefix, a->part_dqk, nullptr, a->dqk, nullptr, bag->num_slides,
+                                             bag->num_tiles, st), "bag_bwd_reduce_kernel"))) return rc;
+  if ((rc = check_cuda(launch_bag_bwd_dkc(bag->tile_prefix, a->part_dkc, a->dkc, bag->num_slides, st),
+                       "bag_bwd_dkc_kernel"))) return rc;
+  // gate path: dkg = (1 - tanh(k)^2) (dg tq) gs, dtq, gate part of db_k
+  p.out = a->dkg_ws; p.part_dqk = a->part_dtq; p.part_db = a->part_dbk;
+  if ((rc = check_cuda(launch_bag_bwd_dz(2, tm_t, tm_dkg, p, ns, st), "bag_bwd_dz_kernel<nacagat dkg>"))) return rc;
+  if ((rc = check_cuda(launch_bag_bwd_reduce(bag->tile_prefix, a->part_dtq, a->part_dbk, a->dtq, a->grad_b_k,
+                                             bag->num_slides, bag->num_tiles, st), "bag_bwd_reduce_kernel"))) return rc;
+  // key-projection path into dz, db_H
+  BagDhkParams d = {};
+  d.tile_info = p.tile_info; d.num_tiles = p.num_tiles; d.total_rows = p.total_rows;
+  d.h = static_cast<const __half*>(a->h_saved);
+  d.dz = static_cast<__nv_bfloat16*>(a->dz_ws);
+  d.part_db = a->part_db; d.dg_max = a->dg_max; d.keep_scale = p.keep_scale;
+  CUtensorMap tm_dkg_a = tm_dkg;
+  if ((rc = check_cuda(launch_bag_dhk(tm_dkg_a, tm_wk, tm_dz, d, ns, st), "bag_dhk_kernel"))) return rc;
+  if ((rc = check_cuda(launch_bag_bwd_reduce(bag->tile_prefix, a->part_dqk, a->part_db, a->dqk, a->grad_b_h, 0,
+                                             bag->num_tiles, st), "bag_bwd_reduce_kernel (bias)"))) return rc;
+  // weight gradients: dW_H += dz^T X (bf16), dW_k += dkg^T H / gs (fp16)
+  CUtensorMap tm_dz64, tm_x64, tm_dkg64, tm_h64;
+  if ((rc = make_tmap_bf16_2d(&tm_dz64, a->dz_ws, R, kD, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm_x64, bag->x, R, kDIn, 64, 64))) return rc;
+  if ((rc = make_tmap_16b_2d(&tm_dkg64, a->dkg_ws, R, kD, 64, 64, true))) return rc;
+  if ((rc = make_tmap_16b_2d(&tm_h64, a->h_saved, R, kD, 64, 64, true))) return rc;
+  if ((rc = check_cuda(launch_bag_bwd_dw(tm_dz64, tm_x64, a->grad_w_h, p.total_rows, kDIn, kDIn, false, nullptr, ns, st),
+                       "bag_bwd_dw_kernel"))) return rc;
+  return check_cuda(launch_bag_bwd_dw(tm_dkg64, tm_h64, a->grad_w_k, p.total_rows, kD, kD, true, a->dg_max, ns, st),
+                    "bag_bwd_dw_kernel (W_k)");
 }
 
 int mpo_lse_combine(const float* lse_in, const float* pooled_in, int32_t nshards, float* lse_out, float* pooled_out,

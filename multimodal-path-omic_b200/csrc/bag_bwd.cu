@@ -18,25 +18,30 @@ namespace mpo {
 
 
 // ------------------------------------------------------------------------------------------------
-// dz stage on tcgen05.  Per 128-patch tile (one persistent CTA per SM, contiguous tile ranges per CTA):
-//   TMA      : saved fp16 activation tile H [128 x 256] -> shared memory (two buffers, prefetch one tile ahead)
-//   MMA-G    : G[128 x 16]    = H dP^T          (dP of the slide as fp16 hi/lo rows, scaled per query to ~1)
-//   threads  : a_i = exp(s_i - lse_i), ds_i = a_i (g_i - delta_i) per patch row; written as tiny bf16 / fp16 operands
-//   MMA-dZ   : dZ'[128 x 256] = [a | ds] [dP ; qk]   (bf16 hi/lo, K = 48)      -> TMEM
-//   MMA-dqk  : dqk^T[256 x 16] = H^T ds           (H tile read M-major, per-tile power-of-two scale on ds)
-//   threads  : dz = dZ' * 1[h > 0] * keep_scale -> bf16, written IN PLACE over the H tile; TMA store to HBM
-//   MMA-db   : db[256] = dz^T 1                    (dz tile read M-major against a ones operand)
-// Everything rank-6-shaped that the CUDA-core version did with shuffles and 12 FMAs per element is a handful of
-// N = 16 / K = 48 tensor-core instructions here; the threads only touch each element once (mask + pack).
+// Row-expand stage on tcgen05, three modes sharing one pipeline.  Per 128-patch tile (one persistent CTA per SM,
+// contiguous tile ranges per CTA):
+//   TMA      : a saved fp16 tile [128 x 256] (H, or tanh(k) in mode 2) -> shared memory (two buffers, one tile ahead)
+//   MMA-G    : G[128 x 16]    = H dP^T            (dP of the slide as fp16 hi/lo rows, scaled per query to ~1)
+//   threads  : per-patch scalars (softmax weights and their gradients), written as tiny bf16 / fp16 operands
+//   MMA-dZ   : Z[128 x 256]   = [a | ds] [dP ; qk]   (bf16 hi/lo, K = 48)       -> TMEM
+//   MMA-dqk  : Q^T[256 x 16]  = tile^T ds            (tile read M-major, power-of-two scale on ds)
+//   threads  : out = f(Z, tile) -> 16-bit, written IN PLACE over the tile; TMA store to HBM
+//   MMA-db   : b[256] = out^T 1                      (out tile read M-major against a ones operand)
+// kDzMcat    (MCAT, autograd of mcat.py:87,97):    out = dz = Z 1[h > 0] keep_scale (bf16); Q = dqk; b = db_H
+// kDzNacDh   (NaCAGaT value/fold path, blocks.py:184-192): same with the gated softmax, attention dropout and the
+//            gate-side scalars dg_i = ds'_i s_i / 2 written out per patch; no b (the dz tile is not final yet)
+// kDzNacDkg  (NaCAGaT gate path, blocks.py:185-186): tile = tanh(k); Z = dg tq; out = dkg = (1 - t^2) Z gs (fp16,
+//            gs a batch-wide power of two); Q = dtq = sum_n dg_n tanh(k_n); b = gate part of db_k
 // ------------------------------------------------------------------------------------------------
+constexpr int kDzMcat = 0, kDzNacDh = 1, kDzNacDkg = 2;
 constexpr int kDzThreads = 64 + 256;
 struct DzSmem {
-  static constexpr int tile = 0;                       // 2 x 64 KB  fp16 H tile [4][128][64] SW128 (later: bf16 dz tile)
+  static constexpr int tile = 0;                       // 2 x 64 KB  fp16 tile [4][128][64] SW128 (later: the 16-bit output tile)
   static constexpr int C = 2 * 65536;                  // bf16 [128][64] K-major (48 used)   16 KB
   static constexpr int Dm = C + 16384;                 // bf16 [256][64] K-major (48 used)   32 KB
   static constexpr int DP = Dm + 32768;                // fp16 [4][16][64] K-major            8 KB
   static constexpr int DS = DP + 8192;                 // fp16 [2][16][64] K-major (K = rows) 4 KB
-  static constexpr int ones = DS + 4096;               // bf16 [2][16][64] row 0 = 1          4 KB
+  static constexpr int ones = DS + 4096;               // 16-bit [2][16][64] row 0 = 1        4 KB
   static constexpr int scal = ones + 4096;             // fp32 scratch (see below)            1 KB
   static constexpr int bars = scal + 1024;
   static constexpr int tmem_slot = bars + 128;
@@ -52,24 +57,65 @@ __device__ __forceinline__ float pow2_scale(float m, float* inv) {
   *inv = __uint_as_float(e << 23);
   return __uint_as_float((254u - e) << 23);
 }
+// batch-wide scale of the gate-path gradients: |dkg| <= sum_i |dg_i| |tq_i| <= 6 max|dg|
+__device__ __forceinline__ float gate_scale(const uint32_t* dg_max, float* inv) {
+  return pow2_scale(8.f * __uint_as_float(*dg_max), inv);
+}
 
+// hi/lo bf16 pairs of 12 values -> the C / D operand row layout: k 0..11 hi, 16..27 `mid`, 32..43 `last`
+__device__ __forceinline__ void split_bf16x12(const float (&v)[12], uint32_t (&hi)[6], uint32_t (&lo)[6]) {
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+    hi[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+    lo[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+  }
+}
+__device__ __forceinline__ void store_row48(uint8_t* row, int sw, const uint32_t (&a)[6], const uint32_t (&b)[6],
+                                            const uint32_t (&c)[6]) {
+  *reinterpret_cast<uint4*>(row + ((0 ^ sw) << 4)) = make_uint4(a[0], a[1], a[2], a[3]);
+  *reinterpret_cast<uint4*>(row + ((1 ^ sw) << 4)) = make_uint4(a[4], a[5], 0u, 0u);
+  *reinterpret_cast<uint4*>(row + ((2 ^ sw) << 4)) = make_uint4(b[0], b[1], b[2], b[3]);
+  *reinterpret_cast<uint4*>(row + ((3 ^ sw) << 4)) = make_uint4(b[4], b[5], 0u, 0u);
+  *reinterpret_cast<uint4*>(row + ((4 ^ sw) << 4)) = make_uint4(c[0], c[1], c[2], c[3]);
+  *reinterpret_cast<uint4*>(row + ((5 ^ sw) << 4)) = make_uint4(c[4], c[5], 0u, 0u);
+}
+// 6 values -> fp16 hi/lo entries of a [16 x 128] K-major operand column (rows 0..5 hi, 6..11 lo)
+__device__ __forceinline__ void store_col_f16(uint8_t* base, int k, const float (&v)[kQ]) {
+  uint8_t* pcol = base + (k >> 6) * 2048 + (k & 7) * 2;
+  const int kc = (k & 63) >> 3;
+#pragma unroll
+  for (int i = 0; i < kQ; ++i) {
+    const __half vh = __float2half_rn(v[i]);
+    const __half vl = __float2half_rn(v[i] - __half2float(vh));
+    *reinterpret_cast<__half*>(pcol + i * 128 + ((kc ^ i) << 4)) = vh;
+    *reinterpret_cast<__half*>(pcol + (i + 6) * 128 + ((kc ^ ((i + 6) & 7)) << 4)) = vl;
+  }
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(kDzThreads, 1)
-bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_dz,
+bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                   const BagBwdDzParams p) {
+  constexpr bool kHasG = MODE != kDzNacDkg;      // MMA-G (dots of the tile rows with dP)
+  constexpr bool kHasB = MODE != kDzNacDh;       // MMA-db (column sums of the output tile)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DzSmem::bars);
   uint64_t* full_bar = bars;          // [2] TMA -> issuer
-  uint64_t* empty_bar = bars + 2;     // [2] tile buffer free again (store has read it + MMA-db retired)
+  uint64_t* empty_bar = bars + 2;     // [2] tile buffer free again (store has read it + last MMA reading it retired)
   uint64_t* op_bar = bars + 4;        // per-slide operands in place (8 warp arrivals)
   uint64_t* g_bar = bars + 5;         // MMA-G retired
   uint64_t* c_bar = bars + 6;         // C / DS operands written (8 warp arrivals)
   uint64_t* z_bar = bars + 7;         // MMA-dZ + MMA-dqk retired
-  uint64_t* w_bar = bars + 8;         // dz tile written in place (8 warp arrivals)
+  uint64_t* w_bar = bars + 8;         // output tile written in place (8 warp arrivals)
   uint64_t* b_bar = bars + 9;         // MMA-db retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DzSmem::tmem_slot);
   float* scal = reinterpret_cast<float*>(smem + DzSmem::scal);
-  // scal: [0..7] delta_i, [8..15] lse_i, [16..23] 1/dp_scale_i, [32..127] warp partials [8][12], [128..159] row-warp max [4][8]
+  // scal: [0..7] delta_i, [8..15] lse_i, [16..23] 1/dp_scale_i, [24..31] ds un-scale, [32..127] warp partials [8][12],
+  //       [128..159] row-warp max [4][8], [160..167] dsuma_i, [168..175] row-warp sums of ds [4][8] at 168..199
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // contiguous tile range of this CTA (consecutive tiles mostly share a slide -> per-slide operands are rebuilt rarely)
@@ -78,8 +124,8 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
   const int t_end = min(p.num_tiles, t_begin + per);
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_h);
-    tma_prefetch_desc(&tm_dz);
+    tma_prefetch_desc(&tm_in);
+    tma_prefetch_desc(&tm_out);
     for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
     mbar_init(op_bar, 8); mbar_init(g_bar, 1); mbar_init(c_bar, 8); mbar_init(z_bar, 1); mbar_init(w_bar, 8);
     mbar_init(b_bar, 1);
@@ -91,10 +137,10 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
     *reinterpret_cast<uint4*>(smem + DzSmem::C + o) = make_uint4(0, 0, 0, 0);
   __syncthreads();
   if (threadIdx.x < 128) {
-    // ones operand: B[n = 0][k = threadIdx.x] = 1.0 (bf16), K-major, 2 blocks of 64 k
+    // ones operand: B[n = 0][k = threadIdx.x] = 1.0 in the format of the output tile, K-major, 2 blocks of 64 k
     const int k = threadIdx.x;
-    *reinterpret_cast<__nv_bfloat16*>(smem + DzSmem::ones + (k >> 6) * 2048 + ((((k & 63) >> 3) ^ 0) << 4) + (k & 7) * 2) =
-        __float2bfloat16_rn(1.f);
+    *reinterpret_cast<uint16_t*>(smem + DzSmem::ones + (k >> 6) * 2048 + (((k & 63) >> 3) << 4) + (k & 7) * 2) =
+        MODE == kDzNacDkg ? static_cast<uint16_t>(0x3C00) : static_cast<uint16_t>(0x3F80);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -103,7 +149,7 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer: H tiles
+    // ---------------------------------------------------------------- TMA producer: input tiles
     if (lane == 0) {
       const uint64_t pol = policy_evict_first();
       int it = 0;
@@ -115,7 +161,7 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
         mbar_expect_tx(&full_bar[buf], 65536);
         const int row0 = p.tile_info[t].row0;
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) tma_load_2d(dst + cb * 16384, &tm_h, &full_bar[buf], cb * 64, row0, pol);
+        for (int cb = 0; cb < 4; ++cb) tma_load_2d(dst + cb * 16384, &tm_in, &full_bar[buf], cb * 64, row0, pol);
       }
     }
   } else if (warp == 1) {
@@ -123,8 +169,9 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t id_g = umma_idesc(128, 16, 0, 0, 0, 0);       // fp16 x fp16, both K-major
       constexpr uint32_t id_z = umma_idesc_bf16(128, 256, 0, 0);       // bf16 x bf16, both K-major
-      constexpr uint32_t id_q = umma_idesc(128, 16, 0, 0, 1, 0);       // fp16, A M-major (H^T)
-      constexpr uint32_t id_b = umma_idesc(128, 16, 1, 1, 1, 0);       // bf16, A M-major (dz^T)
+      constexpr uint32_t id_q = umma_idesc(128, 16, 0, 0, 1, 0);       // fp16, A M-major (tile^T)
+      constexpr uint32_t id_b = MODE == kDzNacDkg ? umma_idesc(128, 16, 0, 0, 1, 0)    // fp16 output tile
+                                                  : umma_idesc(128, 16, 1, 1, 1, 0);   // bf16 output tile
       const uint32_t aC = smem_u32(smem + DzSmem::C), aD = smem_u32(smem + DzSmem::Dm);
       const uint32_t aDP = smem_u32(smem + DzSmem::DP), aDS = smem_u32(smem + DzSmem::DS);
       const uint32_t aOne = smem_u32(smem + DzSmem::ones);
@@ -143,13 +190,14 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
         const uint32_t ph = (it >> 1) & 1, tph = it & 1;
         const uint32_t aT = smem_u32(smem + DzSmem::tile + buf * 65536);
         mbar_wait(op_bar, tph);
-        if (!g_early) {
+        if (kHasG && !g_early) {
           mbar_wait(&full_bar[buf], ph);
           tc_fence_after();
           issue_g(aT);
           umma_commit(g_bar);
         }
         mbar_wait(c_bar, tph);
+        if (!kHasG) mbar_wait(&full_bar[buf], ph);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 3; ++k)
@@ -165,7 +213,7 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
         // MMA-G of the next tile already now (same slide: same dP operand), so that it overlaps this tile's epilogue;
         // every row thread has consumed this tile's G by the time c_bar completed
         g_early = false;
-        if (t + 1 < t_end && p.tile_info[t + 1].slide == p.tile_info[t].slide) {
+        if (kHasG && t + 1 < t_end && p.tile_info[t + 1].slide == p.tile_info[t].slide) {
           const int nb = (it + 1) & 1;
           mbar_wait(&full_bar[nb], ((it + 1) >> 1) & 1);
           tc_fence_after();
@@ -179,35 +227,40 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
         const bool full_tile = ti.nvalid == kTileM;
         if (full_tile) {
 #pragma unroll
-          for (int cb = 0; cb < 4; ++cb) tma_store_2d(&tm_dz, smem + DzSmem::tile + buf * 65536 + cb * 16384, cb * 64, ti.row0);
+          for (int cb = 0; cb < 4; ++cb) tma_store_2d(&tm_out, smem + DzSmem::tile + buf * 65536 + cb * 16384, cb * 64, ti.row0);
           tma_store_commit();
         }
+        if (kHasB) {
 #pragma unroll
-        for (int mh = 0; mh < 2; ++mh)
+          for (int mh = 0; mh < 2; ++mh)
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_bf16(tmem_base + kColB + mh * 16, umma_desc_sw128(aT + mh * 2 * 16384 + kk * 2048, 16384, 1024),
-                      umma_desc_sw128(aOne + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), id_b, kk != 0 ? 1u : 0u);
-        umma_commit(b_bar);
-        umma_commit(&empty_bar[buf]);            // arrival 1 of 2: MMA-db no longer reads the tile
+            for (int kk = 0; kk < 8; ++kk)
+              umma_bf16(tmem_base + kColB + mh * 16, umma_desc_sw128(aT + mh * 2 * 16384 + kk * 2048, 16384, 1024),
+                        umma_desc_sw128(aOne + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), id_b, kk != 0 ? 1u : 0u);
+          umma_commit(b_bar);
+        }
+        umma_commit(&empty_bar[buf]);            // arrival 1 of 2: no MMA reads the tile any more
         if (full_tile) tma_store_wait_read();
         mbar_arrive(&empty_bar[buf]);            // arrival 2 of 2: the store has read it
       }
     }
   } else {
     // ---------------------------------------------------------------- 8 compute warps
-    const int et = threadIdx.x - 64;           // 0..255 : feature owned when building per-slide operands / reading dqk, db
+    const int et = threadIdx.x - 64;           // 0..255 : feature owned when building per-slide operands / reading Q, b
     const int qd = warp & 3;                   // TMEM lane quadrant
-    const int ch = (warp - 2) >> 2;            // column half (epilogue) / feature half (dqk, db read-back)
+    const int ch = (warp - 2) >> 2;            // column half (epilogue) / feature half (Q, b read-back)
     const int r = qd * 32 + lane;              // patch row of the tile
     uint8_t* Cs = smem + DzSmem::C;
     uint8_t* Ds = smem + DzSmem::Dm;
     uint8_t* DPs = smem + DzSmem::DP;
     uint8_t* DSs = smem + DzSmem::DS;
+    float gs = 1.f, inv_gs = 1.f;
+    if (MODE == kDzNacDkg) gs = gate_scale(p.dg_max, &inv_gs);
+    const uint32_t seed = p.seed_dev != nullptr ? (p.seed ^ __ldg(p.seed_dev)) : p.seed;
     int cur_slide = -1;
     int it = 0;
     int prev_t = -1;
-    // db partial of tile `tt` (its MMA-db was issued after the tile was written): read one tile late, so nobody
+    // b partial of tile `tt` (its MMA-db was issued after the tile was written): read one tile late, so nobody
     // waits for that MMA -- by then it has long retired
     auto read_db = [&](int tt, uint32_t parity) {
       mbar_wait(b_bar, parity);
@@ -215,7 +268,7 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
       uint32_t bv[16];
       tmem_ld_32x32b_x16(tmem_base + kColB + ch * 16 + (static_cast<uint32_t>(qd * 32) << 16), bv);
       tmem_ld_wait();
-      p.part_db[static_cast<size_t>(tt) * kD + ch * 128 + qd * 32 + lane] = __uint_as_float(bv[0]);
+      p.part_db[static_cast<size_t>(tt) * kD + ch * 128 + qd * 32 + lane] = __uint_as_float(bv[0]) * inv_gs;
       tc_fence_before();
     };
     for (int t = t_begin; t < t_end; ++t, ++it) {
@@ -223,75 +276,73 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
       const int buf = it & 1;
       const uint32_t tph = it & 1;
       uint8_t* tile = smem + DzSmem::tile + buf * 65536;
-      // ---- per-slide operands: D = [dP ; qk] (bf16 hi | hi | lo), DP = dP (fp16 hi/lo, scaled), delta, lse
+      // ---- per-slide operands
       if (ti.slide != cur_slide) {
         cur_slide = ti.slide;
         const size_t sb = static_cast<size_t>(ti.slide) * kQ * kD;
-        float dp[kQ], qv[kQ], red[12];
-#pragma unroll
-        for (int i = 0; i < kQ; ++i) {
-          dp[i] = p.dpooled[sb + i * kD + et];
-          qv[i] = p.qk[sb + i * kD + et];
-          red[i] = dp[i] * p.pooled[sb + i * kD + et];     // delta_i partial
-          red[6 + i] = fabsf(dp[i]);                       // max |dP_i|
-        }
-#pragma unroll
-        for (int i = 0; i < kQ; ++i) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            red[i] += __shfl_xor_sync(0xffffffffu, red[i], o);
-            red[6 + i] = fmaxf(red[6 + i], __shfl_xor_sync(0xffffffffu, red[6 + i], o));
-          }
-        }
-        named_bar_sync(1, 256);                            // previous tile no longer reads scal
-        if (lane == 0) {
-#pragma unroll
-          for (int j = 0; j < 12; ++j) scal[32 + (warp - 2) * 12 + j] = red[j];
-        }
-        named_bar_sync(1, 256);
-        float dscale[kQ];
-#pragma unroll
-        for (int i = 0; i < kQ; ++i) {
-          float s = 0.f, m = 0.f;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) { s += scal[32 + w * 12 + i]; m = fmaxf(m, scal[32 + w * 12 + 6 + i]); }
-          float inv;
-          dscale[i] = pow2_scale(m, &inv);
-          if (et == 0) { scal[i] = s; scal[8 + i] = p.lse[ti.slide * kQ + i]; scal[16 + i] = inv; }
-        }
-        // D row `et`: k 0..5 dP hi, 6..11 qk hi, 16..27 the same hi values, 32..43 the lo parts
-        uint32_t hi[6], lo[6];
-        {
+        if (MODE == kDzNacDkg) {
+          // D row `et` = tanh(q_i)[et] in the dP slots (hi | hi | lo), zeros in the qk slots
+          named_bar_sync(1, 256);
           float v[12];
 #pragma unroll
-          for (int i = 0; i < kQ; ++i) { v[i] = dp[i]; v[6 + i] = qv[i]; }
+          for (int i = 0; i < kQ; ++i) { v[i] = tanhf(p.qp[sb + i * kD + et]); v[6 + i] = 0.f; }
+          uint32_t hi[6], lo[6];
+          split_bf16x12(v, hi, lo);
+          store_row48(Ds + et * 128, et & 7, hi, hi, lo);
+        } else {
+          float dp[kQ], qv[kQ], red[12];
 #pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-            hi[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-            lo[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+          for (int i = 0; i < kQ; ++i) {
+            dp[i] = p.dpooled[sb + i * kD + et];
+            qv[i] = p.qk[sb + i * kD + et];
+            red[i] = dp[i] * p.pooled[sb + i * kD + et];     // delta_i partial
+            red[6 + i] = fabsf(dp[i]);                       // max |dP_i|
           }
-        }
-        uint8_t* drow = Ds + et * 128;
-        const int sw = et & 7;
-        *reinterpret_cast<uint4*>(drow + ((0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(drow + ((1 ^ sw) << 4)) = make_uint4(hi[4], hi[5], 0u, 0u);
-        *reinterpret_cast<uint4*>(drow + ((2 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(drow + ((3 ^ sw) << 4)) = make_uint4(hi[4], hi[5], 0u, 0u);
-        *reinterpret_cast<uint4*>(drow + ((4 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(drow + ((5 ^ sw) << 4)) = make_uint4(lo[4], lo[5], 0u, 0u);
-        // DP[n][k = et]: rows 0..5 hi, 6..11 lo of dP_i * scale_i (fp16), K-major in 4 blocks of 64 k
-        uint8_t* pcol = DPs + (et >> 6) * 2048 + (et & 7) * 2;
-        const int kc = (et & 63) >> 3;
 #pragma unroll
-        for (int i = 0; i < kQ; ++i) {
-          const float v = dp[i] * dscale[i];
-          const __half vh = __float2half_rn(v);
-          const __half vl = __float2half_rn(v - __half2float(vh));
-          *reinterpret_cast<__half*>(pcol + i * 128 + ((kc ^ i) << 4)) = vh;
-          *reinterpret_cast<__half*>(pcol + (i + 6) * 128 + ((kc ^ ((i + 6) & 7)) << 4)) = vl;
+          for (int i = 0; i < kQ; ++i) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              red[i] += __shfl_xor_sync(0xffffffffu, red[i], o);
+              red[6 + i] = fmaxf(red[6 + i], __shfl_xor_sync(0xffffffffu, red[6 + i], o));
+            }
+          }
+          named_bar_sync(1, 256);                            // previous tile no longer reads scal
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) scal[32 + (warp - 2) * 12 + j] = red[j];
+          }
+          named_bar_sync(1, 256);
+          float dscale[kQ];
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) {
+            float s = 0.f, m = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { s += scal[32 + w * 12 + i]; m = fmaxf(m, scal[32 + w * 12 + 6 + i]); }
+            float inv;
+            dscale[i] = pow2_scale(m, &inv);
+            if (et == 0) {
+              float dsum = 0.f;
+              if (MODE == kDzNacDh && p.dsuma != nullptr) {   // delta_i = dP_i . pooled_i + dsuma_i suma_i
+                dsum = p.dsuma[ti.slide * kQ + i];
+                s += dsum * p.suma[ti.slide * kQ + i];
+              }
+              scal[i] = s; scal[8 + i] = p.lse[ti.slide * kQ + i]; scal[16 + i] = inv; scal[160 + i] = dsum;
+            }
+          }
+          // D row `et`: k 0..5 dP hi, 6..11 qk hi, 16..27 the same hi values, 32..43 the lo parts
+          {
+            float v[12];
+#pragma unroll
+            for (int i = 0; i < kQ; ++i) { v[i] = dp[i]; v[6 + i] = qv[i]; }
+            uint32_t hi[6], lo[6];
+            split_bf16x12(v, hi, lo);
+            store_row48(Ds + et * 128, et & 7, hi, hi, lo);
+          }
+          // DP[n][k = et]: rows 0..5 hi, 6..11 lo of dP_i * scale_i (fp16), K-major in 4 blocks of 64 k
+          float v6[kQ];
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) v6[i] = dp[i] * dscale[i];
+          store_col_f16(DPs, et, v6);
         }
         fence_proxy_async_smem();
       }
@@ -300,82 +351,116 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
       named_bar_sync(1, 256);                  // scal[0..23] visible to everyone
 
       // ---- per-row scalars (one patch row per thread of warps 2..5)
-      float a[kQ], ds[kQ];
       const bool valid = r < ti.nvalid;
+      const size_t grow = static_cast<size_t>(ti.row0 + r);
       if (ch == 0) {
-        float sc[kQ];
+        float c12[12];                         // C row: [a'_i | ds_i]  (mode 2: [dg_i | 0])
+        float ds[kQ];                          // DS column (mode 2: dg_i gs)
+        float dgmax = 0.f;                     // mode 1: max_i |dg_i| of this row
+        if (MODE == kDzNacDkg) {
 #pragma unroll
-        for (int i = 0; i < kQ; ++i)
-          sc[i] = valid ? __ldg(p.scores + static_cast<size_t>(i) * p.total_rows + ti.row0 + r) : 0.f;
-        mbar_wait(g_bar, tph);
-        tc_fence_after();
-        uint32_t gv[16];
-        tmem_ld_32x32b_x16(tmem_base + kColG + (static_cast<uint32_t>(qd * 32) << 16), gv);
-        tmem_ld_wait();
+          for (int i = 0; i < kQ; ++i) {
+            const float dg = valid ? __ldg(p.dg + static_cast<size_t>(i) * p.total_rows + grow) : 0.f;
+            c12[i] = dg; c12[6 + i] = 0.f;
+            ds[i] = dg * gs;
+          }
+        } else {
+          float sc[kQ], pg[kQ];
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) {
+            sc[i] = valid ? __ldg(p.scores + static_cast<size_t>(i) * p.total_rows + grow) : 0.f;
+            pg[i] = (MODE == kDzNacDh && valid) ? __ldg(p.pgate + static_cast<size_t>(i) * p.total_rows + grow) : 1.f;
+          }
+          mbar_wait(g_bar, tph);
+          tc_fence_after();
+          uint32_t gv[16];
+          tmem_ld_32x32b_x16(tmem_base + kColG + (static_cast<uint32_t>(qd * 32) << 16), gv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) {
+            const float g = (__uint_as_float(gv[i]) + __uint_as_float(gv[i + 6])) * scal[16 + i];
+            if (MODE == kDzMcat) {
+              const float a = valid ? __expf(sc[i] - scal[8 + i]) : 0.f;
+              ds[i] = a * (g - scal[i]);
+              c12[i] = a;
+            } else {
+              // gated softmax with attention dropout: a' = a msc, da = msc (g + dsuma), ds' = a (da - delta)
+              const float a = valid ? __expf(sc[i] * pg[i] - scal[8 + i]) : 0.f;
+              float msc = 1.f;
+              if (p.attn_thr != 0) {
+                const uint32_t rb = rng_u32(seed, 1u, static_cast<uint32_t>(i) * static_cast<uint32_t>(p.total_rows) +
+                                                          static_cast<uint32_t>(grow)) & 0xFFu;
+                msc = rb < p.attn_thr ? 0.f : p.attn_scale;
+              }
+              const float dsp = a * (msc * (g + scal[160 + i]) - scal[i]);
+              ds[i] = dsp * pg[i];
+              c12[i] = a * msc;
+              const float dgi = 0.5f * dsp * sc[i];
+              if (valid) p.dg[static_cast<size_t>(i) * p.total_rows + grow] = dgi;
+              dgmax = fmaxf(dgmax, fabsf(dgi));
+            }
+            c12[6 + i] = ds[i];
+          }
+        }
         float amax[kQ];
 #pragma unroll
         for (int i = 0; i < kQ; ++i) {
-          const float g = (__uint_as_float(gv[i]) + __uint_as_float(gv[i + 6])) * scal[16 + i];
-          a[i] = valid ? __expf(sc[i] - scal[8 + i]) : 0.f;
-          ds[i] = a[i] * (g - scal[i]);
           float m = fabsf(ds[i]);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
           amax[i] = m;
         }
+        if (MODE == kDzNacDh) {
+          // per-tile sums of ds_i (gradient of the key-bias score term kc_i) and the batch-wide max |dg|
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) {
+            float sm = ds[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+            if (lane == 0) scal[168 + qd * 8 + i] = sm;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) dgmax = fmaxf(dgmax, __shfl_xor_sync(0xffffffffu, dgmax, o));
+          if (lane == 0 && dgmax > 0.f) atomicMax(p.dg_max, __float_as_uint(dgmax));   // non-negative floats order like uints
+        }
         if (lane == 0) {
 #pragma unroll
           for (int i = 0; i < kQ; ++i) scal[128 + qd * 8 + i] = amax[i];
         }
-        // C row r : k 0..5 a hi, 6..11 ds hi, 16..27 lo parts, 32..43 hi again (pairs with the lo half of D)
         {
-          float v[12];
-#pragma unroll
-          for (int i = 0; i < kQ; ++i) { v[i] = a[i]; v[6 + i] = ds[i]; }
           uint32_t hi[6], lo[6];
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-            hi[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-            lo[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
-          }
-          uint8_t* crow = Cs + r * 128;
-          const int sw = r & 7;
-          *reinterpret_cast<uint4*>(crow + ((0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(crow + ((1 ^ sw) << 4)) = make_uint4(hi[4], hi[5], 0u, 0u);
-          *reinterpret_cast<uint4*>(crow + ((2 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<uint4*>(crow + ((3 ^ sw) << 4)) = make_uint4(lo[4], lo[5], 0u, 0u);
-          *reinterpret_cast<uint4*>(crow + ((4 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(crow + ((5 ^ sw) << 4)) = make_uint4(hi[4], hi[5], 0u, 0u);
+          split_bf16x12(c12, hi, lo);
+          store_row48(Cs + r * 128, r & 7, hi, lo, hi);     // k 16..27 lo (x D hi), 32..43 hi (x D lo)
         }
         named_bar_sync(2, 128);                // tile maxima of |ds_i| from the four row warps
-        uint8_t* pcol = DSs + (r >> 6) * 2048 + (r & 7) * 2;
-        const int kc = (r & 63) >> 3;
+        float v6[kQ];
 #pragma unroll
         for (int i = 0; i < kQ; ++i) {
-          const float m = fmaxf(fmaxf(scal[128 + i], scal[136 + i]), fmaxf(scal[144 + i], scal[152 + i]));
-          float inv;
-          const float s = pow2_scale(m, &inv);
-          const float v = ds[i] * s;
-          const __half vh = __float2half_rn(v);
-          const __half vl = __float2half_rn(v - __half2float(vh));
-          *reinterpret_cast<__half*>(pcol + i * 128 + ((kc ^ i) << 4)) = vh;
-          *reinterpret_cast<__half*>(pcol + (i + 6) * 128 + ((kc ^ ((i + 6) & 7)) << 4)) = vl;
-          if (r == 0) scal[24 + i] = inv;      // un-scale factor for the dqk read-back
+          if (MODE == kDzNacDkg) {
+            v6[i] = ds[i];                     // already scaled by the batch-wide gs
+            if (r == 0) scal[24 + i] = inv_gs;
+          } else {
+            const float m = fmaxf(fmaxf(scal[128 + i], scal[136 + i]), fmaxf(scal[144 + i], scal[152 + i]));
+            float inv;
+            const float s = pow2_scale(m, &inv);
+            v6[i] = ds[i] * s;
+            if (r == 0) scal[24 + i] = inv;    // un-scale factor for the Q read-back
+          }
         }
+        store_col_f16(DSs, r, v6);
+        if (MODE == kDzNacDh && r < kQ)
+          p.part_dkc[static_cast<size_t>(t) * 8 + r] = scal[168 + r] + scal[176 + r] + scal[184 + r] + scal[192 + r];
         fence_proxy_async_smem();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(c_bar);
 
-      // ---- dz = dZ' * 1[h > 0] * keep_scale, in place over the H tile (row r, column half ch)
-      if (prev_t >= 0) read_db(prev_t, tph ^ 1);     // before this tile's w_bar arrival lets MMA-db overwrite it
+      // ---- output tile, in place over the input tile (row r, column half ch)
+      if (kHasB && prev_t >= 0) read_db(prev_t, tph ^ 1);     // before this tile's w_bar arrival lets MMA-db overwrite it
       mbar_wait(z_bar, tph);
       tc_fence_after();
-      __nv_bfloat16* grow_out = p.dz + static_cast<size_t>(ti.row0 + r) * kD;
+      uint16_t* grow_out = static_cast<uint16_t*>(p.out) + grow * kD;
       const bool direct = ti.nvalid != kTileM;     // ragged tile: rows are stored by the threads, not by TMA
 #pragma unroll 1
       for (int c4 = 0; c4 < 4; ++c4) {
@@ -390,17 +475,27 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
           uint4* slot = reinterpret_cast<uint4*>(tile + cb * 16384 + r * 128 + ((jj ^ (r & 7)) << 4));
           const uint4 hv = *slot;
           const float2 h0 = unpack_f16x2(hv.x), h1 = unpack_f16x2(hv.y), h2 = unpack_f16x2(hv.z), h3 = unpack_f16x2(hv.w);
-          const float ks = p.keep_scale;
+          const float hh[8] = {h0.x, h0.y, h1.x, h1.y, h2.x, h2.y, h3.x, h3.y};
+          float o8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float z = __uint_as_float(v[j + e]);
+            if (MODE == kDzNacDkg) o8[e] = (1.f - hh[e] * hh[e]) * z * gs;
+            else o8[e] = hh[e] > 0.f ? z * p.keep_scale : 0.f;
+          }
           uint4 o;
-          o.x = pack_bf16x2(h0.x > 0.f ? __uint_as_float(v[j + 0]) * ks : 0.f, h0.y > 0.f ? __uint_as_float(v[j + 1]) * ks : 0.f);
-          o.y = pack_bf16x2(h1.x > 0.f ? __uint_as_float(v[j + 2]) * ks : 0.f, h1.y > 0.f ? __uint_as_float(v[j + 3]) * ks : 0.f);
-          o.z = pack_bf16x2(h2.x > 0.f ? __uint_as_float(v[j + 4]) * ks : 0.f, h2.y > 0.f ? __uint_as_float(v[j + 5]) * ks : 0.f);
-          o.w = pack_bf16x2(h3.x > 0.f ? __uint_as_float(v[j + 6]) * ks : 0.f, h3.y > 0.f ? __uint_as_float(v[j + 7]) * ks : 0.f);
+          if (MODE == kDzNacDkg) {
+            o.x = pack_f16x2(o8[0], o8[1]); o.y = pack_f16x2(o8[2], o8[3]);
+            o.z = pack_f16x2(o8[4], o8[5]); o.w = pack_f16x2(o8[6], o8[7]);
+          } else {
+            o.x = pack_bf16x2(o8[0], o8[1]); o.y = pack_bf16x2(o8[2], o8[3]);
+            o.z = pack_bf16x2(o8[4], o8[5]); o.w = pack_bf16x2(o8[6], o8[7]);
+          }
           *slot = o;
           if (direct && valid) *reinterpret_cast<uint4*>(grow_out + col0 + j) = o;
         }
       }
-      // dqk partial of this tile: feature f = ch * 128 + qd * 32 + lane
+      // Q partial of this tile: feature f = ch * 128 + qd * 32 + lane
       {
         uint32_t qv[16];
         tmem_ld_32x32b_x16(tmem_base + kColQ + ch * 16 + (static_cast<uint32_t>(qd * 32) << 16), qv);
@@ -416,7 +511,7 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
 
       prev_t = t;
     }
-    if (prev_t >= 0) read_db(prev_t, (it - 1) & 1);
+    if (kHasB && prev_t >= 0) read_db(prev_t, (it - 1) & 1);
   }
 
   tc_fence_before();
@@ -476,8 +571,9 @@ constexpr int kDwSmemBytes = kDwStages * kDwStageBytes + 256 + 1024;
 
 __global__ void __launch_bounds__(kDwThreads, 1)
 bag_bwd_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_x,
-                  float* __restrict__ grad_w,   // [256][1024] fp32, accumulated
-                  int total_rows, int num_splits) {
+                  float* __restrict__ grad_w,   // [256][ld] fp32, accumulated
+                  int total_rows, int num_splits, int ncb, int ld, uint32_t idesc,
+                  const uint32_t* __restrict__ dg_max) {   // non-null: the A operand carries the batch-wide gate scale
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms, by pointer arithmetic so the compiler keeps the shared state space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -488,8 +584,8 @@ bag_bwd_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kDwStages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cb = blockIdx.x & 3;          // which 256-column block of X / dW_H
-  const int sp = blockIdx.x >> 2;         // split-K index over patch rows
+  const int cb = blockIdx.x % ncb;        // which 256-column block of the B operand / of the gradient
+  const int sp = blockIdx.x / ncb;        // split-K index over patch rows
   const int chunks_total = (total_rows + kDwBK - 1) / kDwBK;
   const int per = (chunks_total + num_splits - 1) / num_splits;
   const int c_begin = sp * per;
@@ -529,8 +625,7 @@ bag_bwd_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 1, 1);   // A and B both M/N-major
-      int stage = 0; uint32_t phase = 0;
+      int stage = 0; uint32_t phase = 0;       // idesc: M 128, N 256, A and B both M/N-major, bf16 or fp16 operands
       for (int c = 0; c < n_chunks; ++c) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -555,12 +650,14 @@ bag_bwd_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
     // epilogue: 4 warps, thread = one feature row per M half; reduce into the fp32 gradient
     const int qd = warp & 3;
     if (n_chunks > 0) {
+      float inv = 1.f;
+      if (dg_max != nullptr) (void)gate_scale(dg_max, &inv);
       mbar_wait(done_bar, 0);
       tc_fence_after();
 #pragma unroll 1
       for (int mh = 0; mh < 2; ++mh) {
         const int f = mh * 128 + qd * 32 + lane;
-        float* dst = grad_w + static_cast<size_t>(f) * kDIn + cb * 256;
+        float* dst = grad_w + static_cast<size_t>(f) * ld + cb * 256;
 #pragma unroll 1
         for (int c0 = 0; c0 < 256; c0 += 32) {
           uint32_t v[32];
@@ -568,8 +665,9 @@ bag_bwd_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(__uint_as_float(v[j])),
-                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j),
+                         "f"(__uint_as_float(v[j]) * inv), "f"(__uint_as_float(v[j + 1]) * inv),
+                         "f"(__uint_as_float(v[j + 2]) * inv), "f"(__uint_as_float(v[j + 3]) * inv)
                          : "memory");
         }
       }
@@ -581,31 +679,58 @@ bag_bwd_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
-cudaError_t launch_bag_bwd_dz(const CUtensorMap& tm_h, const CUtensorMap& tm_dz, const BagBwdDzParams& prm, int num_sms,
-                              cudaStream_t stream) {
+// dkc[b][i] = sum over the slide's tiles of the per-tile sums of ds_i (one warp per slide and query)
+__global__ void bag_bwd_dkc_kernel(const int* __restrict__ tile_prefix, const float* __restrict__ part_dkc,
+                                   float* __restrict__ dkc) {
+  const int b = blockIdx.x, i = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float v = 0.f;
+  for (int t = tile_prefix[b] + lane; t < tile_prefix[b + 1]; t += 32) v += part_dkc[static_cast<size_t>(t) * 8 + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) dkc[b * kQ + i] = v;
+}
+cudaError_t launch_bag_bwd_dkc(const int* tile_prefix, const float* part_dkc, float* dkc, int B, cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  bag_bwd_dkc_kernel<<<B, kQ * 32, 0, stream>>>(tile_prefix, part_dkc, dkc);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launch_dz_mode(const CUtensorMap& tm_in, const CUtensorMap& tm_out, const BagBwdDzParams& prm,
+                                  int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(bag_bwd_dz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDzSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(bag_bwd_dz_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDzSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   if (prm.num_tiles <= 0) return cudaSuccess;
   const int grid = prm.num_tiles < num_sms ? prm.num_tiles : num_sms;
-  bag_bwd_dz_kernel<<<grid, kDzThreads, kDzSmemBytes, stream>>>(tm_h, tm_dz, prm);
+  bag_bwd_dz_kernel<MODE><<<grid, kDzThreads, kDzSmemBytes, stream>>>(tm_in, tm_out, prm);
   count_launch();
   return cudaGetLastError();
+}
+cudaError_t launch_bag_bwd_dz(int mode, const CUtensorMap& tm_in, const CUtensorMap& tm_out, const BagBwdDzParams& prm,
+                              int num_sms, cudaStream_t stream) {
+  switch (mode) {
+    case kDzMcat: return launch_dz_mode<kDzMcat>(tm_in, tm_out, prm, num_sms, stream);
+    case kDzNacDh: return launch_dz_mode<kDzNacDh>(tm_in, tm_out, prm, num_sms, stream);
+    case kDzNacDkg: return launch_dz_mode<kDzNacDkg>(tm_in, tm_out, prm, num_sms, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t launch_bag_bwd_reduce(const int* tile_prefix, const float* part_dqk, const float* part_db, float* dqk,
                                   float* grad_bias, int B, int num_tiles, cudaStream_t stream) {
-  bag_bwd_reduce_kernel<<<dim3(B + 16, kQ), 256, 0, stream>>>(tile_prefix, part_dqk, part_db, dqk, grad_bias, B,
-                                                            num_tiles);
+  bag_bwd_reduce_kernel<<<dim3(B + (part_db != nullptr ? 16 : 0), kQ), 256, 0, stream>>>(tile_prefix, part_dqk, part_db,
+                                                                                        dqk, grad_bias, B, num_tiles);
   count_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_bag_bwd_dw(const CUtensorMap& tm_dz, const CUtensorMap& tm_x, float* grad_w, int total_rows,
-                              int num_sms, cudaStream_t stream) {
+                              int ncols, int ld, bool f16, const uint32_t* dg_max, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(bag_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes);
@@ -614,10 +739,13 @@ cudaError_t launch_bag_bwd_dw(const CUtensorMap& tm_dz, const CUtensorMap& tm_x,
   }
   if (total_rows <= 0) return cudaSuccess;
   const int chunks = (total_rows + kDwBK - 1) / kDwBK;
-  int splits = num_sms / 4;
+  const int ncb = ncols / 256;
+  int splits = num_sms / ncb;
   if (splits > chunks) splits = chunks;
   if (splits < 1) splits = 1;
-  bag_bwd_dw_kernel<<<4 * splits, kDwThreads, kDwSmemBytes, stream>>>(tm_dz, tm_x, grad_w, total_rows, splits);
+  const uint32_t idesc = f16 ? umma_idesc(128, 256, 0, 0, 1, 1) : umma_idesc_bf16(128, 256, 1, 1);
+  bag_bwd_dw_kernel<<<ncb * splits, kDwThreads, kDwSmemBytes, stream>>>(tm_dz, tm_x, grad_w, total_rows, splits, ncb, ld,
+                                                                       idesc, dg_max);
   count_launch();
   return cudaGetLastError();
 }

@@ -38,6 +38,15 @@ struct GateSmem {
 };
 constexpr int kGateSmemBytes = GateSmem::total + 1024;
 
+// batch-wide power-of-two scale of the gate-path gradients (same formula as gate_scale in bag_bwd.cu)
+__device__ __forceinline__ float pow2_scale_gate(const uint32_t* dg_max, float* inv) {
+  const float m = 8.f * __uint_as_float(*dg_max);
+  const uint32_t e = (__float_as_uint(m) >> 23) & 0xFFu;
+  if (e == 0u || e >= 254u) { *inv = 1.f; return 1.f; }
+  *inv = __uint_as_float(e << 23);
+  return __uint_as_float((254u - e) << 23);
+}
+
 // tanh from ex2 + rcp (2 MUFU): absolute error ~1e-7 -- tanh.approx (2^-11) is too coarse for a 256-term gate dot
 __device__ __forceinline__ float tanh_fast(float x) {
   const float e = __expf(2.f * x);
@@ -288,6 +297,219 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bag_dhk_kernel (backward): the key-projection path of the gradient at the bag activations,
+//     dz = dz_part + (dkg W_k) 1[h > 0] keep_scale,      dkg W_k on tcgen05 with W_k read N-major,
+// then db_H = column sums of the final dz tile (a ones-operand MMA on the staged tile) and a TMA store of dz.
+// dkg arrives as fp16 scaled by the batch-wide power of two gs (bag_bwd.cu); un-scaled here.
+// ------------------------------------------------------------------------------------------------
+struct DhkSmem {
+  static constexpr int A = 0;                          // fp16 dkg tile [4][128][64] SW128; later the bf16 dz tile   64 KB
+  static constexpr int W = 65536;                      // fp16 W_k ring: 2 x ([4 N blocks][64 k rows][64]) SW128     64 KB
+  static constexpr int ones = W + 65536;               // bf16 [2][16][64] row 0 = 1                                 4 KB
+  static constexpr int bars = ones + 4096;
+  static constexpr int tmem_slot = bars + 128;
+  static constexpr int total = tmem_slot + 16;
+};
+constexpr int kDhkSmemBytes = DhkSmem::total + 1024;
+
+__global__ void __launch_bounds__(kGateThreads, 1)
+bag_dhk_kernel(const __grid_constant__ CUtensorMap tm_dkg, const __grid_constant__ CUtensorMap tm_w,
+               const __grid_constant__ CUtensorMap tm_dz, const BagDhkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DhkSmem::bars);
+  uint64_t* a_full = bars;            // dkg tile landed
+  uint64_t* a_empty = bars + 1;       // tile buffer free (2 arrivals: MMA-db retired, store has read it)
+  uint64_t* acc_full = bars + 2;      // dkg W_k complete
+  uint64_t* acc_empty = bars + 3;     // accumulators drained (8 warp arrivals)
+  uint64_t* w_ready = bars + 4;       // dz tile written in place (8 warp arrivals)
+  uint64_t* b_bar = bars + 5;         // MMA-db retired
+  uint64_t* w_full = bars + 6;        // [2]
+  uint64_t* w_empty = bars + 8;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DhkSmem::tmem_slot);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = (p.num_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int t_begin = min(p.num_tiles, static_cast<int>(blockIdx.x) * per);
+  const int t_end = min(p.num_tiles, t_begin + per);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_dkg); tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_dz);
+    mbar_init(a_full, 1); mbar_init(a_empty, 2); mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
+    mbar_init(w_ready, 8); mbar_init(b_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  for (int o = threadIdx.x * 16; o < 4096; o += kGateThreads * 16)
+    *reinterpret_cast<uint4*>(smem + DhkSmem::ones + o) = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int k = threadIdx.x;
+    *reinterpret_cast<uint16_t*>(smem + DhkSmem::ones + (k >> 6) * 2048 + (((k & 63) >> 3) << 4) + (k & 7) * 2) = 0x3F80;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kColZ = 0, kColB = 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+      int it = 0, ws = 0;
+      uint32_t wph = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        mbar_wait(a_empty, (it & 1) ^ 1);
+        mbar_expect_tx(a_full, 65536);
+        const int row0 = p.tile_info[t].row0;
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) tma_load_2d(smem + DhkSmem::A + cb * 16384, &tm_dkg, a_full, cb * 64, row0, pol_stream);
+        // W_k is read N-major: a ring slot holds the key features e in [64 kb, 64 kb + 64) (the K slice matching
+        // A's block kb) for all 256 columns d, as four 64-column N blocks of [64 k rows][128 B]
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(&w_empty[ws], wph ^ 1);
+          mbar_expect_tx(&w_full[ws], 32768);
+#pragma unroll
+          for (int nb = 0; nb < 4; ++nb)
+            tma_load_2d(smem + DhkSmem::W + ws * 32768 + nb * 8192, &tm_w, &w_full[ws], nb * 64, kb * 64, pol_keep);
+          if (++ws == 2) { ws = 0; wph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id_k = umma_idesc(128, 256, 0, 0, 0, 1);     // fp16: A K-major (dkg), B N-major (W_k)
+      constexpr uint32_t id_b = umma_idesc(128, 16, 1, 1, 1, 0);      // bf16: A M-major (dz^T), B K-major (ones)
+      const uint32_t aW = smem_u32(smem + DhkSmem::W), aA = smem_u32(smem + DhkSmem::A);
+      const uint32_t aOne = smem_u32(smem + DhkSmem::ones);
+      int it = 0, ws = 0;
+      uint32_t wph = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const uint32_t ph = it & 1;
+        mbar_wait(acc_empty, ph ^ 1);
+        mbar_wait(a_full, ph);
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(&w_full[ws], wph);
+          tc_fence_after();
+          const uint32_t wb = aW + ws * 32768;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + kColZ, umma_desc_sw128(aA + kb * 16384 + k * 32, 16, 1024),
+                      umma_desc_sw128(wb + k * 2048, 8192, 1024), id_k, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&w_empty[ws]);
+          if (++ws == 2) { ws = 0; wph ^= 1; }
+        }
+        umma_commit(acc_full);
+        mbar_wait(w_ready, ph);
+        tc_fence_after();
+        const TileInfo ti = p.tile_info[t];
+        const bool full_tile = ti.nvalid == kTileM;
+        if (full_tile) {
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) tma_store_2d(&tm_dz, smem + DhkSmem::A + cb * 16384, cb * 64, ti.row0);
+          tma_store_commit();
+        }
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16(tmem_base + kColB + mh * 16, umma_desc_sw128(aA + mh * 2 * 16384 + kk * 2048, 16384, 1024),
+                      umma_desc_sw128(aOne + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), id_b, kk != 0 ? 1u : 0u);
+        umma_commit(b_bar);
+        umma_commit(a_empty);
+        if (full_tile) tma_store_wait_read();
+        mbar_arrive(a_empty);
+      }
+    }
+  } else {
+    const int qd = warp & 3;
+    const int ch = (warp - 2) >> 2;
+    const int r = qd * 32 + lane;
+    float inv_gs;
+    (void)pow2_scale_gate(p.dg_max, &inv_gs);
+    const float ks = p.keep_scale * inv_gs;
+    int it = 0, prev_t = -1;
+    auto read_db = [&](int tt, uint32_t parity) {
+      mbar_wait(b_bar, parity);
+      tc_fence_after();
+      uint32_t bv[16];
+      tmem_ld_32x32b_x16(tmem_base + kColB + ch * 16 + (static_cast<uint32_t>(qd * 32) << 16), bv);
+      tmem_ld_wait();
+      p.part_db[static_cast<size_t>(tt) * kD + ch * 128 + qd * 32 + lane] = __uint_as_float(bv[0]);
+      tc_fence_before();
+    };
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const TileInfo ti = p.tile_info[t];
+      const uint32_t ph = it & 1;
+      const bool valid = r < ti.nvalid;
+      const bool direct = ti.nvalid != kTileM;
+      // rows past the end of the packed bag do not exist in the global buffers: clamp the address, mask the value
+      const size_t grow = static_cast<size_t>(min(ti.row0 + r, p.total_rows - 1));
+      const uint4* zp = reinterpret_cast<const uint4*>(p.dz + grow * kD + ch * 128);
+      const uint4* hp = reinterpret_cast<const uint4*>(p.h + grow * kD + ch * 128);
+      if (prev_t >= 0) read_db(prev_t, ph ^ 1);
+      mbar_wait(acc_full, ph);
+      tc_fence_after();
+      uint8_t* tile = smem + DhkSmem::A;
+#pragma unroll 1
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int col0 = ch * 128 + c4 * 32;
+        uint4 zin[4], hin[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { zin[q] = zp[c4 * 4 + q]; hin[q] = hp[c4 * 4 + q]; }
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + kColZ + (static_cast<uint32_t>(qd * 32) << 16) + col0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = q * 8;
+          const uint32_t zi[4] = {zin[q].x, zin[q].y, zin[q].z, zin[q].w};
+          const uint32_t hi_[4] = {hin[q].x, hin[q].y, hin[q].z, hin[q].w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 hh = unpack_f16x2(hi_[e]);
+            const float z0 = bf16lo_to_f32(zi[e]) + (hh.x > 0.f ? __uint_as_float(v[j + 2 * e]) * ks : 0.f);
+            const float z1 = bf16hi_to_f32(zi[e]) + (hh.y > 0.f ? __uint_as_float(v[j + 2 * e + 1]) * ks : 0.f);
+            ow[e] = valid ? pack_bf16x2(z0, z1) : 0u;
+          }
+          const uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          const int j16 = (col0 + j) >> 3;
+          const int cb = j16 >> 3, jj = j16 & 7;
+          *reinterpret_cast<uint4*>(tile + cb * 16384 + r * 128 + ((jj ^ (r & 7)) << 4)) = o;
+          if (direct && valid) *reinterpret_cast<uint4*>(p.dz + grow * kD + col0 + j) = o;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(acc_empty); mbar_arrive(w_ready); }
+      prev_t = t;
+    }
+    if (prev_t >= 0) read_db(prev_t, (it - 1) & 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+cudaError_t launch_bag_dhk(const CUtensorMap& tm_dkg, const CUtensorMap& tm_w, const CUtensorMap& tm_dz,
+                           const BagDhkParams& prm, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(bag_dhk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDhkSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (prm.num_tiles <= 0) return cudaSuccess;
+  const int grid = prm.num_tiles < num_sms ? prm.num_tiles : num_sms;
+  bag_dhk_kernel<<<grid, kGateThreads, kDhkSmemBytes, stream>>>(tm_dkg, tm_w, tm_dz, prm);
+  count_launch();
+  return cudaGetLastError();
 }
 
 cudaError_t launch_bag_gate(const CUtensorMap& tm_h, const CUtensorMap& tm_hlo, const CUtensorMap& tm_w,

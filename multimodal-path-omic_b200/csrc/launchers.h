@@ -20,11 +20,14 @@ cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, int m
                              float* pooled, float* lse, float* suma, int B, cudaStream_t stream);
 cudaError_t launch_bag_gate(const CUtensorMap& tm_h, const CUtensorMap& tm_hlo, const CUtensorMap& tm_w,
                             const BagGateParams& prm, int num_sms, cudaStream_t stream);
-cudaError_t launch_bag_bwd_dz(const CUtensorMap& tm_h, const CUtensorMap& tm_dz, const BagBwdDzParams& prm, int num_sms,
-                              cudaStream_t stream);
+cudaError_t launch_bag_dhk(const CUtensorMap& tm_dkg, const CUtensorMap& tm_w, const CUtensorMap& tm_dz,
+                           const BagDhkParams& prm, int num_sms, cudaStream_t stream);
+cudaError_t launch_bag_bwd_dz(int mode, const CUtensorMap& tm_in, const CUtensorMap& tm_out, const BagBwdDzParams& prm,
+                              int num_sms, cudaStream_t stream);
 cudaError_t launch_bag_bwd_reduce(const int* tile_prefix, const float* part_dqk, const float* part_db, float* dqk,
                                   float* grad_bias, int B, int num_tiles, cudaStream_t stream);
 cudaError_t launch_bag_bwd_dw(const CUtensorMap& tm_dz, const CUtensorMap& tm_x, float* grad_w, int total_rows,
-                              int num_sms, cudaStream_t stream);
+                              int ncols, int ld, bool f16, const uint32_t* dg_max, int num_sms, cudaStream_t stream);
+cudaError_t launch_bag_bwd_dkc(const int* tile_prefix, const float* part_dkc, float* dkc, int B, cudaStream_t stream);
 
 }  // namespace mpo

@@ -62,20 +62,43 @@ struct BagGateParams {
   float drop_scale;
 };
 
+// NaCAGaT backward, key-projection path (bag_gate.cu: bag_dhk_kernel)
+struct BagDhkParams {
+  const TileInfo* tile_info;
+  int num_tiles;
+  int total_rows;
+  const __half* h;             // [total_rows][256]  saved activations (ReLU / dropout mask)
+  __nv_bfloat16* dz;           // [total_rows][256]  in: value/fold part of dz ; out: the complete dz
+  float* part_db;              // [num_tiles][256]   per-tile column sums of dz
+  const uint32_t* dg_max;      // bits of the batch-wide max |dg| (scale of dkg)
+  float keep_scale;
+};
+
 struct BagBwdDzParams {
   const TileInfo* tile_info;
   int num_tiles;
   int total_rows;
-  const __half* h;             // [total_rows][256] fp16, saved by the forward pass
-  const float* scores;         // [6][total_rows]
-  const float* lse;            // [B][6]
+  const float* scores;         // [6][total_rows]  raw scores s (NaCAGaT: including the key-bias term)
+  const float* lse;            // [B][6]           log-sum-exp of the softmax argument (s, or s P for NaCAGaT)
   const float* pooled;         // [B][6][256]
   const float* dpooled;        // [B][6][256]
   const float* qk;             // [B][6][256]
-  __nv_bfloat16* dz;           // [total_rows][256]
-  float* part_dqk;             // [num_tiles][6][256]
-  float* part_db;              // [num_tiles][256]
+  void* out;                   // [total_rows][256] 16-bit output tile rows (dz bf16 / dkg fp16), for ragged tiles
+  float* part_dqk;             // [num_tiles][6][256]  per-tile Q partials (dqk, or dtq in mode 2)
+  float* part_db;              // [num_tiles][256]     per-tile column sums of the output (modes 0 and 2)
   float keep_scale;            // 1/(1-p) in train mode, 1 in eval
+  // NaCAGaT (modes 1 and 2)
+  const float* pgate;          // [6][total_rows]  P
+  const float* suma;           // [B][6]           sum_n a'_in            (with dsuma; null = no attention dropout)
+  const float* dsuma;          // [B][6]           gradient of suma
+  const float* qp;             // [B][6][256]      projected queries (mode 2: tanh taken in the kernel)
+  float* dg;                   // [6][total_rows]  mode 1 writes, mode 2 reads the gate-dot gradients
+  uint32_t* dg_max;            // bits of max |dg| over the batch (mode 1: atomicMax; mode 2: scale source)
+  float* part_dkc;             // [num_tiles][8]   per-tile sums of ds_i (mode 1)
+  uint32_t seed;
+  const uint32_t* seed_dev;
+  uint32_t attn_thr;           // attention dropout threshold (0 = off) and rescale factor
+  float attn_scale;
 };
 
 }  // namespace mpo

@@ -432,6 +432,7 @@ int64_t mpo_sizeof(int32_t which) {
     case 0: return sizeof(mpo_bag);
     case 1: return sizeof(mpo_model);
     case 2: return sizeof(mpo_tail_io);
+    case 3: return sizeof(mpo_nacagat_bwd);
     default: return -1;
   }
 }

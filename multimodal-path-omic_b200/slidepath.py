@@ -229,6 +229,10 @@ class SlideEngine:
             st.bag_ws.ensure_bwd(bag)
             st.dpooled = torch.empty((B, Q, D), **f32)
             st.dqk = torch.empty((B, Q, D), **f32)
+            if nac:
+                st.dsuma = torch.empty((B, Q), **f32)
+                st.dkc = torch.empty((B, Q), **f32)
+                st.dtq = torch.empty((B, Q, D), **f32)
             st.loss = torch.empty(B, **f32)
             st.dhz = torch.empty((B, K), **f32)
             st.dS = torch.empty((B, K), **f32)
@@ -297,6 +301,10 @@ class SlideEngine:
         f32 = dict(dtype=torch.float32, device=dev)
         if st.dpooled is None:
             st.dpooled = torch.empty((st.B, Q, D), **f32)
+        if st.bag_ws.nacagat and st.dsuma is None:
+            st.dsuma = torch.empty((st.B, Q), **f32)
+            st.dkc = torch.empty((st.B, Q), **f32)
+            st.dtq = torch.empty((st.B, Q, D), **f32)
         io = self._io(st)
         s = _stream()
 
@@ -314,9 +322,33 @@ class SlideEngine:
         if st.dqk is None:
             st.dqk = torch.empty((st.B, Q, D), **f32)
         ws = st.bag_ws
-        _lib.call("mpo_bag_bwd", st.bag.c(), _ptr(ws.h_saved), _ptr(ws.scores), _ptr(ws.lse), _ptr(ws.pooled),
-                  _ptr(st.dpooled), _ptr(st.qk), _ptr(ws.dz), _ptr(ws.part_dqk), _ptr(ws.part_db), _ptr(st.dqk),
-                  gw, gb, ctypes.c_float(st.drop_p), s)
+        if ws.nacagat:
+            if ws.t_saved is None:
+                raise RuntimeError("this NaCAGaT forward pass did not keep the gate activations (it ran under no_grad)")
+            if st.dkc is None:
+                st.dkc = torch.empty((st.B, Q), **f32)
+                st.dtq = torch.empty((st.B, Q, D), **f32)
+            use_suma = getattr(st, "attn_p", 0.0) > 0.0
+            a = _lib.MpoNacagatBwd()
+            for name, t in (("h_saved", ws.h_saved), ("t_saved", ws.t_saved), ("scores", ws.scores), ("pgate", ws.pgate),
+                            ("lse", ws.lse), ("pooled", ws.pooled), ("suma", ws.suma if use_suma else None),
+                            ("dpooled", st.dpooled), ("dsuma", st.dsuma if use_suma else None), ("qk", st.qk),
+                            ("qp", st.qp), ("w_k_f16", self._wk_f16), ("dz_ws", ws.dz), ("dkg_ws", ws.dkg),
+                            ("dg_ws", ws.dg), ("part_dqk", ws.part_dqk), ("part_dtq", ws.part_dtq),
+                            ("part_db", ws.part_db), ("part_dbk", ws.part_dbk), ("part_dkc", ws.part_dkc),
+                            ("dg_max", ws.dg_max), ("dqk", st.dqk), ("dkc", st.dkc), ("dtq", st.dtq)):
+                setattr(a, name, t.data_ptr() if t is not None else None)
+            a.grad_w_h, a.grad_b_h = model.H.gw, model.H.gb
+            a.grad_w_k = model.coattn_in.gw + D * D * 4           # key block of co_attention.in_proj_weight.grad
+            a.grad_b_k = model.coattn_in.gb + D * 4
+            a.drop_p, a.attn_drop_p = st.drop_p, getattr(st, "attn_p", 0.0)
+            a.seed = st.seed & 0xFFFFFFFF
+            a.seed_dev = st.seed_dev.data_ptr() if (st.seed_dev is not None and st.train) else None
+            _lib.call("mpo_bag_bwd_nacagat", st.bag.c(), ctypes.byref(a), s)
+        else:
+            _lib.call("mpo_bag_bwd", st.bag.c(), _ptr(ws.h_saved), _ptr(ws.scores), _ptr(ws.lse), _ptr(ws.pooled),
+                      _ptr(st.dpooled), _ptr(st.qk), _ptr(ws.dz), _ptr(ws.part_dqk), _ptr(ws.part_db), _ptr(st.dqk),
+                      gw, gb, ctypes.c_float(st.drop_p), s)
         io = self._io(st)
         _lib.call("mpo_tail_pre_bwd", ctypes.byref(model), ctypes.byref(io), s)
 
