@@ -3,6 +3,7 @@
 // All kernels are batched over the B slides of a step: token rows are laid out [slide][token] (R = 6B rows of 256).
 // The work is latency-bound: plain CUDA-core kernels, fp32 throughout.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -162,12 +163,111 @@ inline void launch_gemm_bm(const GemmArgs& g, cudaStream_t st) {
   else gemm_kernel<BM, false, false><<<grid, 256, 0, st>>>(g);
 }
 
+// Latency-first variant for the chain of small dependent GEMMs: a 32x32 output tile per CTA, and the WHOLE K
+// extent of the tile (in chunks of 256) fetched with one wave of independent loads before any math, so a GEMM costs
+// one L2 round trip instead of one per 32-deep K step.  Same contract as gemm_kernel.
+constexpr int kFkBM = 32, kFkBN = 32, kFkBK = 256;
+template <bool A_KC, bool B_NC>
+__global__ void __launch_bounds__(256) gemm_fullk_kernel(const GemmArgs g) {
+  extern __shared__ __align__(16) float fk_smem[];
+  float (*As)[kFkBM + 2] = reinterpret_cast<float (*)[kFkBM + 2]>(fk_smem);
+  float (*Bs)[kFkBN + 2] = reinterpret_cast<float (*)[kFkBN + 2]>(fk_smem + kFkBK * (kFkBM + 2));
+  const int t = threadIdx.x;
+  const int m0 = blockIdx.y * kFkBM, n0 = blockIdx.x * kFkBN;
+  const int tx = t & 15, ty = t >> 4;          // thread -> rows ty*2..+1, cols tx*2..+1
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float rsum = 0.f;
+  constexpr int PER = kFkBM * kFkBK / 256;     // 32 elements of each operand tile per thread and chunk
+  for (int k0 = 0; k0 < g.K; k0 += kFkBK) {
+    float ra[PER], rb[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      int mm, kk;
+      if (A_KC) { kk = (t & 31) + 32 * (j & 7); mm = (t >> 5) + 8 * (j >> 3); } else { mm = t & 31; kk = (t >> 5) + 8 * j; }
+      const int m = m0 + mm, k = k0 + kk;
+      ra[j] = (m < g.M && k < g.K) ? __ldg(g.A + m * g.sa_m + k * g.sa_k) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      int nn, kk;
+      if (B_NC) { nn = t & 31; kk = (t >> 5) + 8 * j; } else { kk = (t & 31) + 32 * (j & 7); nn = (t >> 5) + 8 * (j >> 3); }
+      const int n = n0 + nn, k = k0 + kk;
+      rb[j] = (n < g.N && k < g.K) ? __ldg(g.B + k * g.sb_k + n * g.sb_n) : 0.f;
+    }
+    if (k0 > 0) __syncthreads();               // previous chunk's math is done with the tiles
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      int mm, kk;
+      if (A_KC) { kk = (t & 31) + 32 * (j & 7); mm = (t >> 5) + 8 * (j >> 3); } else { mm = t & 31; kk = (t >> 5) + 8 * j; }
+      As[kk][mm] = ra[j];
+    }
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      int nn, kk;
+      if (B_NC) { nn = t & 31; kk = (t >> 5) + 8 * j; } else { kk = (t & 31) + 32 * (j & 7); nn = (t >> 5) + 8 * (j >> 3); }
+      Bs[kk][nn] = rb[j];
+    }
+    __syncthreads();
+    const int kmax = min(kFkBK, g.K - k0);
+#pragma unroll 8
+    for (int kk = 0; kk < kmax; ++kk) {
+      const float2 a = *reinterpret_cast<const float2*>(&As[kk][ty * 2]);
+      const float2 b = *reinterpret_cast<const float2*>(&Bs[kk][tx * 2]);
+      acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+      acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+    }
+    if (g.rowsum != nullptr && blockIdx.x == 0 && t < kFkBM) {
+      for (int kk = 0; kk < kmax; ++kk) rsum += As[kk][t];
+    }
+  }
+  if (g.rowsum != nullptr && blockIdx.x == 0 && t < kFkBM && m0 + t < g.M) g.rowsum[m0 + t] += g.alpha * rsum;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + ty * 2 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = n0 + tx * 2 + j;
+      if (n >= g.N) continue;
+      float v = g.alpha * acc[i][j];
+      if (g.bias != nullptr) v += g.bias[n];
+      v = act_fwd(v, g.act);
+      float* c = g.C + m * g.ldc + n;
+      *c = g.accumulate ? (*c + v) : v;
+    }
+  }
+}
+inline void launch_gemm_fullk(const GemmArgs& g, cudaStream_t st) {
+  dim3 grid((g.N + kFkBN - 1) / kFkBN, (g.M + kFkBM - 1) / kFkBM);
+  const bool akc = (g.sa_k == 1), bnc = (g.sb_n == 1);
+  constexpr int smem = kFkBK * (kFkBM + 2 + kFkBN + 2) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gemm_fullk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(gemm_fullk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(gemm_fullk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(gemm_fullk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_set = true;
+  }
+  if (akc && bnc) gemm_fullk_kernel<true, true><<<grid, 256, smem, st>>>(g);
+  else if (akc && !bnc) gemm_fullk_kernel<true, false><<<grid, 256, smem, st>>>(g);
+  else if (!akc && bnc) gemm_fullk_kernel<false, true><<<grid, 256, smem, st>>>(g);
+  else gemm_fullk_kernel<false, false><<<grid, 256, smem, st>>>(g);
+}
+
 inline cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
-  // narrow tiles when 64-row tiles would leave most SMs idle
-  const long long blocks64 = static_cast<long long>((g.N + 63) / 64) * ((g.M + 63) / 64);
-  if (blocks64 < 96) launch_gemm_bm<32>(g, st);
-  else launch_gemm_bm<64>(g, st);
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("MPO_TAIL_GEMM"); mode = e ? atoi(e) : 1; }
+  const long long blocks32 = static_cast<long long>((g.N + 31) / 32) * ((g.M + 31) / 32);
+  if (mode == 1 && blocks32 <= 1184 && g.K <= 4 * kFkBK) {
+    launch_gemm_fullk(g, st);                  // the latency-bound regime of the slide tail
+  } else {
+    // narrow tiles when 64-row tiles would leave most SMs idle
+    const long long blocks64 = static_cast<long long>((g.N + 63) / 64) * ((g.M + 63) / 64);
+    if (blocks64 < 96) launch_gemm_bm<32>(g, st);
+    else launch_gemm_bm<64>(g, st);
+  }
   count_launch();
   return cudaGetLastError();
 }
