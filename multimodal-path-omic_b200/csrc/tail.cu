@@ -158,6 +158,7 @@ void dep(Ctx& c, cudaStream_t from, cudaStream_t to) {
   p.next = (p.next + 1) & 63;
   c.chk(cudaEventRecord(e, from), "event record");
   c.chk(cudaStreamWaitEvent(to, e, 0), "stream wait");
+  pdl_bar_next(to);
 }
 // the compute stream waits for this branch's pending weight-gradient GEMMs (before their inputs are overwritten)
 void join_w(Ctx& c) { if (c.async_w) dep(c, c.wst, c.st); }
@@ -192,39 +193,39 @@ void lin_bwd(Ctx& c, const float* dz, long long lddz, const float* x, long long 
     if (c.async_w) dep(c, c.st, c.wst);      // dz is complete on the compute stream
     c.chk(launch_gemm(g, ws_), "lin_bwd.wgrad");
   } else if (L.gb != nullptr) {
-    colsum_kernel<<<nblk(out, 32), 256, 0, c.st>>>(dz, lddz, nullptr, 0, L.gb, rows, out); count_launch();
+    launch_k(colsum_kernel, dim3(nblk(out, 32)), dim3(256), 0, c.st, dz, lddz, nullptr, 0, L.gb, rows, out); count_launch();
     c.chk(cudaGetLastError(), "lin_bwd.bgrad");
   }
 }
 void act_bwd(Ctx& c, const float* dy, long long lddy, const float* y, long long ldy, float* dz, long long lddz, int rows,
              int cols, int act) {
-  act_bwd_kernel<<<nblk((long long)rows * cols), 256, 0, c.st>>>(dy, lddy, y, ldy, dz, lddz, rows, cols, act); count_launch();
+  launch_k(act_bwd_kernel, dim3(nblk((long long)rows * cols)), dim3(256), 0, c.st, dy, lddy, y, ldy, dz, lddz, rows, cols, act); count_launch();
   c.chk(cudaGetLastError(), "act_bwd");
 }
 void add(Ctx& c, const float* a, const float* b, float* out, long long n) {
-  add_kernel<<<nblk(n), 256, 0, c.st>>>(a, b, out, n); count_launch();
+  launch_k(add_kernel, dim3(nblk(n)), dim3(256), 0, c.st, a, b, out, n); count_launch();
   c.chk(cudaGetLastError(), "add");
 }
 void mul(Ctx& c, const float* a, const float* b, float* out, long long n) {
-  mul_kernel<<<nblk(n), 256, 0, c.st>>>(a, b, out, n); count_launch();
+  launch_k(mul_kernel, dim3(nblk(n)), dim3(256), 0, c.st, a, b, out, n); count_launch();
   c.chk(cudaGetLastError(), "mul");
 }
 void act(Ctx& c, const float* x, float* y, long long n, int a) {
-  act_kernel<<<nblk(n), 256, 0, c.st>>>(x, y, n, a); count_launch();
+  launch_k(act_kernel, dim3(nblk(n)), dim3(256), 0, c.st, x, y, n, a); count_launch();
   c.chk(cudaGetLastError(), "act");
 }
 void ln_fwd(Ctx& c, const float* a, const float* b, const mpo_norm& N, float* y, float* xh, float* rs, int rows) {
-  layernorm_fwd_kernel<<<nblk(rows, 8), 256, 0, c.st>>>(a, b, N.g, N.b, y, xh, rs, rows); count_launch();
+  launch_k(layernorm_fwd_kernel, dim3(nblk(rows, 8)), dim3(256), 0, c.st, a, b, N.g, N.b, y, xh, rs, rows); count_launch();
   c.chk(cudaGetLastError(), "ln_fwd");
 }
 void ln_bwd(Ctx& c, const float* dy, const mpo_norm& N, const float* xh, const float* rs, float* dx, int rows) {
-  layernorm_bwd_kernel<<<nblk(rows, 8), 256, 0, c.st>>>(dy, N.g, xh, rs, dx, rows); count_launch();
+  launch_k(layernorm_bwd_kernel, dim3(nblk(rows, 8)), dim3(256), 0, c.st, dy, N.g, xh, rs, dx, rows); count_launch();
   c.chk(cudaGetLastError(), "ln_bwd");
   if (N.gg != nullptr) {
     cudaStream_t ws_ = c.async_w ? c.wst : c.st;
     if (c.async_w) dep(c, c.st, c.wst);
-    colsum_kernel<<<nblk(E, 32), 256, 0, ws_>>>(dy, E, xh, E, N.gg, rows, E); count_launch();
-    colsum_kernel<<<nblk(E, 32), 256, 0, ws_>>>(dy, E, nullptr, 0, N.gb, rows, E); count_launch();
+    launch_k(colsum_kernel, dim3(nblk(E, 32)), dim3(256), 0, ws_, dy, E, xh, E, N.gg, rows, E); count_launch();
+    launch_k(colsum_kernel, dim3(nblk(E, 32)), dim3(256), 0, ws_, dy, E, nullptr, 0, N.gb, rows, E); count_launch();
     c.chk(cudaGetLastError(), "ln_bwd.params");
   }
 }
@@ -234,7 +235,7 @@ void ln_bwd(Ctx& c, const float* dy, const mpo_norm& N, const float* xh, const f
 void enc_fwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, float* ws, const float* x, int B) {
   const int R = 6 * B;
   lin_fwd(c, x, E, P.in_proj, 3 * E, E, ws + b.qkv, 3 * E, R, ACT_NONE);
-  mha6_fwd_kernel<<<nblk((long long)B * 8, 8), 256, 0, c.st>>>(ws + b.qkv, ws + b.probs, ws + b.ctx, B); count_launch();
+  launch_k(mha6_fwd_kernel, dim3(nblk((long long)B * 8, 8)), dim3(256), 0, c.st, ws + b.qkv, ws + b.probs, ws + b.ctx, B); count_launch();
   c.chk(cudaGetLastError(), "mha6_fwd");
   lin_fwd(c, ws + b.ctx, E, P.out_proj, E, E, ws + b.sa, E, R, ACT_NONE);
   ln_fwd(c, x, ws + b.sa, P.norm1, ws + b.y1, ws + b.xh1, ws + b.rs1, R);
@@ -261,7 +262,7 @@ void enc_bwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, const Ws& w, f
   float* dctx = ws + w.dxb[c.sb];
   lin_bwd(c, dr1, E, ws + b.ctx, E, P.out_proj, E, E, dctx, E, R, false);
   float* dqkv = ws + w.s768[c.sb];
-  mha6_bwd_kernel<<<nblk((long long)B * 8, 8), 256, 0, c.st>>>(ws + b.qkv, ws + b.probs, dctx, dqkv, B); count_launch();
+  launch_k(mha6_bwd_kernel, dim3(nblk((long long)B * 8, 8)), dim3(256), 0, c.st, ws + b.qkv, ws + b.probs, dctx, dqkv, B); count_launch();
   c.chk(cudaGetLastError(), "mha6_bwd");
   lin_bwd(c, dqkv, 3 * E, x, E, P.in_proj, 3 * E, E, dx_out, E, R, false);
   add(c, dx_out, dr1, dx_out, (long long)R * E);
@@ -273,7 +274,7 @@ void pool_fwd(Ctx& c, const mpo_pool_head& P, const PoolBuf& b, float* ws, const
   const int R = 6 * B;
   lin_fwd(c, x, E, P.att_a, E, E, ws + b.a, E, R, ACT_TANH);
   lin_fwd(c, x, E, P.att_b, E, E, ws + b.b, E, R, ACT_SIGMOID);
-  pool_fwd_kernel<<<B, 256, 0, c.st>>>(x, ws + b.a, ws + b.b, P.att_c.w, P.att_c.b, att_logits, ws + b.w, ws + b.hp); count_launch();
+  launch_k(pool_fwd_kernel, dim3(B), dim3(256), 0, c.st, x, ws + b.a, ws + b.b, P.att_c.w, P.att_c.b, att_logits, ws + b.w, ws + b.hp); count_launch();
   c.chk(cudaGetLastError(), "pool_fwd");
   lin_fwd(c, ws + b.hp, E, P.rho, E, E, ws + b.h, E, B, ACT_RELU);
 }
@@ -285,7 +286,7 @@ void pool_bwd(Ctx& c, const mpo_pool_head& P, const PoolBuf& b, const Ws& w, flo
   float* dzr = ws + w.dzr[c.sb];
   act_bwd(c, dh, E, ws + b.h, E, dzr, E, B, E, ACT_RELU);
   lin_bwd(c, dzr, E, ws + b.hp, E, P.rho, E, E, dhp, E, B, false);
-  pool_bwd_kernel<<<B, 256, 0, c.st>>>(x, ws + b.a, ws + b.b, P.att_c.w, ws + b.w, dhp, dx_out, ws + w.dxa[c.sb],
+  launch_k(pool_bwd_kernel, dim3(B), dim3(256), 0, c.st, x, ws + b.a, ws + b.b, P.att_c.w, ws + b.w, dhp, dx_out, ws + w.dxa[c.sb],
                                        ws + w.dxb[c.sb], P.att_c.gw, P.att_c.gb); count_launch();
   c.chk(cudaGetLastError(), "pool_bwd");
   lin_bwd(c, ws + w.dxa[c.sb], E, x, E, P.att_a, E, E, dx_out, E, R, true);
@@ -340,7 +341,7 @@ void bil_side_fwd(Ctx& c, const mpo_lin& Lh, const mpo_lin& Lz, const mpo_lin& L
   // U[b][k*256+i] = sum_j W[k][i][j] xb[b][j]
   GemmArgs g{xb, E, 1, Lz.w, 1, E, ws + w.bU[s], (long long)BH * E, nullptr, B, BH * E, E, 1.f, 0, ACT_NONE, nullptr};
   c.chk(launch_gemm(g, c.st), "bil.U");
-  bil_gate_fwd_kernel<<<B, 256, 0, c.st>>>(xa, ws + w.bU[s], Lz.b, ws + w.bh[s], ws + w.bg[s], ws + w.bgh[s]); count_launch();
+  launch_k(bil_gate_fwd_kernel, dim3(B), dim3(256), 0, c.st, xa, ws + w.bU[s], Lz.b, ws + w.bh[s], ws + w.bg[s], ws + w.bgh[s]); count_launch();
   c.chk(cudaGetLastError(), "bil_gate_fwd");
   lin_fwd(c, ws + w.bgh[s], BH, Lo, BH, BH, ws + w.bo[s], BH, B, ACT_RELU);
 }
@@ -350,14 +351,14 @@ void bil_side_bwd(Ctx& c, const mpo_lin& Lh, const mpo_lin& Lz, const mpo_lin& L
   float* dpre = ws + w.bdo[s];
   act_bwd(c, dpre, BH, ws + w.bo[s], BH, dpre, BH, B, BH, ACT_RELU);
   lin_bwd(c, dpre, BH, ws + w.bgh[s], BH, Lo, BH, BH, ws + w.bdgh[s], BH, B, false);
-  bil_gate_bwd_kernel<<<B, 256, 0, c.st>>>(xa, ws + w.bU[s], ws + w.bh[s], ws + w.bg[s], ws + w.bdgh[s], ws + w.bdh[s],
+  launch_k(bil_gate_bwd_kernel, dim3(B), dim3(256), 0, c.st, xa, ws + w.bU[s], ws + w.bh[s], ws + w.bg[s], ws + w.bdgh[s], ws + w.bdh[s],
                                            ws + w.bdz[s], ws + w.bV, dxa, acc_a ? 1 : 0); count_launch();
   c.chk(cudaGetLastError(), "bil_gate_bwd");
   // dW[(k,i)][j] += sum_b V[b][(k,i)] xb[b][j] ;  dxb[b][j] += sum_(k,i) V[b][(k,i)] W[(k,i)][j] ; db += colsum(dz)
   if (Lz.gw != nullptr) {
     GemmArgs g{ws + w.bV, 1, (long long)BH * E, xb, E, 1, Lz.gw, E, nullptr, BH * E, E, B, 1.f, 1, ACT_NONE, nullptr};
     c.chk(launch_gemm(g, c.st), "bil.dW");
-    colsum_kernel<<<1, 256, 0, c.st>>>(ws + w.bdz[s], BH, nullptr, 0, Lz.gb, B, BH); count_launch();
+    launch_k(colsum_kernel, dim3(1), dim3(256), 0, c.st, ws + w.bdz[s], BH, nullptr, 0, Lz.gb, B, BH); count_launch();
   }
   GemmArgs g2{ws + w.bV, (long long)BH * E, 1, Lz.w, E, 1, dxb, E, nullptr, B, E, BH * E, 1.f, 1, ACT_NONE, nullptr};
   c.chk(launch_gemm(g2, c.st), "bil.dxb");
@@ -543,14 +544,14 @@ int mpo_tail_post_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   } else {                                          // fusion.py:81-113
     bil_side_fwd(c, m->bil.h1, m->bil.z1, m->bil.o1, w, ws, 0, hpath, homic, B);
     bil_side_fwd(c, m->bil.h2, m->bil.z2, m->bil.o2, w, ws, 1, homic, hpath, B);
-    bil_kron_fwd_kernel<<<B, 256, 0, c.st>>>(ws + w.bo[0], ws + w.bo[1], ws + w.kp, ws + w.cat130); count_launch();
+    launch_k(bil_kron_fwd_kernel, dim3(B), dim3(256), 0, c.st, ws + w.bo[0], ws + w.bo[1], ws + w.kp, ws + w.cat130); count_launch();
     c.chk(cudaGetLastError(), "bil_kron_fwd");
     lin_fwd(c, ws + w.kp, 1089, m->bil.fc1, BMM, 1089, ws + w.cat130, 130, B, ACT_RELU);
     lin_fwd(c, ws + w.cat130, 130, m->bil.fc2, E, 130, ws + w.bf2, E, B, ACT_RELU);
     hfin = ws + w.bf2;
   }
   lin_fwd(c, hfin, E, m->classifier, K, E, ws + w.logits, K, B, ACT_NONE);
-  surv_head_fwd_kernel<<<nblk(B, 128), 128, 0, c.st>>>(ws + w.logits, io->hazards, io->S, io->Y, B, K); count_launch();
+  launch_k(surv_head_fwd_kernel, dim3(nblk(B, 128)), dim3(128), 0, c.st, ws + w.logits, io->hazards, io->S, io->Y, B, K); count_launch();
   c.chk(cudaGetLastError(), "surv_head_fwd");
   return finish(c);
 }
@@ -562,7 +563,7 @@ int mpo_surv_loss(int32_t kind, const float* hazards, const float* S, const int6
   if (!hazards || !S || !label || !censor || !loss || !dhaz || !dS || B <= 0)
     return fail(MPO_E_ARG, "%s", "mpo_surv_loss: bad arguments");
   if (num_sms() <= 0) return fail(MPO_E_CUDA, "%s", "mpo_surv_loss: no CUDA device (this library has no CPU fallback)");
-  surv_loss_kernel<<<nblk(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(kind, hazards, S, label, censor, alpha,
+  launch_k(surv_loss_kernel, dim3(nblk(B, 128)), dim3(128), 0, static_cast<cudaStream_t>(stream), kind, hazards, S, label, censor, alpha,
                                                                                eps, grad_scale, loss, dhaz, dS, B,
                                                                                n_classes); count_launch();
   return check_cuda(cudaGetLastError(), "surv_loss_kernel");
@@ -580,7 +581,7 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
   Branches br = make_branches(static_cast<cudaStream_t>(stream), true);
   Ctx c = br.main;            // fusion / head part: synchronous weight gradients on the caller's stream
   c.async_w = false;
-  surv_head_bwd_kernel<<<nblk(B, 128), 128, 0, c.st>>>(io->hazards, io->S, io->Y, dhaz, dS, dY, ws + w.dlogits, B, K); count_launch();
+  launch_k(surv_head_bwd_kernel, dim3(nblk(B, 128)), dim3(128), 0, c.st, io->hazards, io->S, io->Y, dhaz, dS, dY, ws + w.dlogits, B, K); count_launch();
   c.chk(cudaGetLastError(), "surv_head_bwd");
   const float* hpath = ws + w.pool[0].h;
   const float* homic = ws + w.pool[1].h;
@@ -602,7 +603,7 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
     // fc1 (its output sits in cat130[:, :64])
     act_bwd(c, ws + w.bdcat130, 130, ws + w.cat130, 130, ws + w.dz1, BMM, B, BMM, ACT_RELU);
     lin_bwd(c, ws + w.dz1, BMM, ws + w.kp, 1089, m->bil.fc1, BMM, 1089, ws + w.bdkp, 1089, B, false);
-    bil_kron_bwd_kernel<<<B, 64, 0, c.st>>>(ws + w.bo[0], ws + w.bo[1], ws + w.bdkp, ws + w.bdcat130, ws + w.bdo[0],
+    launch_k(bil_kron_bwd_kernel, dim3(B), dim3(64), 0, c.st, ws + w.bo[0], ws + w.bo[1], ws + w.bdkp, ws + w.bdcat130, ws + w.bdo[0],
                                             ws + w.bdo[1]); count_launch();
     c.chk(cudaGetLastError(), "bil_kron_bwd");
     // side 1: xa = h_path, xb = h_omic ; side 2: xa = h_omic, xb = h_path

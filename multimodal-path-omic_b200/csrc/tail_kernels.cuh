@@ -35,6 +35,55 @@ __device__ __forceinline__ float act_bwd_from_out(float y, int act) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the tail is a chain of ~100 small dependent kernels, so the launch latency
+// between them is the critical path.  Every tail kernel is launched with the programmatic-stream-serialization
+// attribute and starts with pdl_enter(): wait until the predecessor grid has completed (its writes are visible),
+// then let the successor be scheduled so that its launch -- and, for the GEMMs, the loads of its weight
+// operand, which no kernel of the pass writes -- overlaps this kernel's execution.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_launch_dependents(); }
+
+inline int& pdl_kind() { static int k = 0; return k; }   // bisect aid: 1 while a GEMM is being launched
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MPO_TAIL_PDL"); on = e ? atoi(e) : 1; }
+  if (on == 2) return pdl_kind() >= 1;      // GEMMs only
+  if (on == 3) return pdl_kind() == 0;      // everything but the GEMMs
+  if (on == 4) return pdl_kind() == 2;      // full-K GEMMs only
+  return on != 0;
+}
+// A stream that has just been made to wait on another stream's event launches its next kernel fully serialized:
+// the programmatic relaxation is only meant for the kernel -> kernel edge inside one stream.
+struct PdlBars { cudaStream_t s[8]; bool used[8]; };
+inline PdlBars& pdl_bars() { static PdlBars b = {}; return b; }
+inline void pdl_bar_next(cudaStream_t st) {       // (a null handle is the legacy default stream: a valid key)
+  PdlBars& b = pdl_bars();
+  for (int i = 0; i < 8; ++i) if (b.used[i] && b.s[i] == st) return;
+  for (int i = 0; i < 8; ++i) if (!b.used[i]) { b.used[i] = true; b.s[i] = st; return; }
+}
+inline bool pdl_take_bar(cudaStream_t st) {
+  PdlBars& b = pdl_bars();
+  for (int i = 0; i < 8; ++i) if (b.used[i] && b.s[i] == st) { b.used[i] = false; return true; }
+  return false;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl_enabled() && !pdl_take_bar(st)) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic strided SIMT GEMM:  C[m][n] (+)= act(alpha * sum_k A(m,k) B(k,n) + bias[n])
 //   A(m,k) = A[m*sa_m + k*sa_k],  B(k,n) = B[k*sb_k + n*sb_n];  64x64x16 tiles, 256 threads, 4x4 per thread
 // ------------------------------------------------------------------------------------------------
@@ -56,6 +105,7 @@ struct GemmArgs {
 // Optional fused bias gradient: rowsum[m] += sum_k A(m,k) (used by the weight-gradient GEMMs, where A = dz^T).
 template <int BM, bool A_KC, bool B_NC>
 __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
+  pdl_enter();
   constexpr int BN = 64, BK = 32;
   constexpr int TM = BM / 16;                 // rows per thread (4 or 2)
   constexpr int A_PER = BM * BK / 256;        // elements of the A tile each thread stages (8 or 4)
@@ -157,10 +207,10 @@ template <int BM>
 inline void launch_gemm_bm(const GemmArgs& g, cudaStream_t st) {
   dim3 grid((g.N + 63) / 64, (g.M + BM - 1) / BM);
   const bool akc = (g.sa_k == 1), bnc = (g.sb_n == 1);
-  if (akc && bnc) gemm_kernel<BM, true, true><<<grid, 256, 0, st>>>(g);
-  else if (akc && !bnc) gemm_kernel<BM, true, false><<<grid, 256, 0, st>>>(g);
-  else if (!akc && bnc) gemm_kernel<BM, false, true><<<grid, 256, 0, st>>>(g);
-  else gemm_kernel<BM, false, false><<<grid, 256, 0, st>>>(g);
+  if (akc && bnc) launch_k(gemm_kernel<BM, true, true>, dim3(grid), dim3(256), 0, st, g);
+  else if (akc && !bnc) launch_k(gemm_kernel<BM, true, false>, dim3(grid), dim3(256), 0, st, g);
+  else if (!akc && bnc) launch_k(gemm_kernel<BM, false, true>, dim3(grid), dim3(256), 0, st, g);
+  else launch_k(gemm_kernel<BM, false, false>, dim3(grid), dim3(256), 0, st, g);
 }
 
 // Latency-first variant for the chain of small dependent GEMMs: a 32x32 output tile per CTA, and the WHOLE K
@@ -182,17 +232,22 @@ __global__ void __launch_bounds__(256) gemm_fullk_kernel(const GemmArgs g) {
     float ra[PER], rb[PER];
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
-      int mm, kk;
-      if (A_KC) { kk = (t & 31) + 32 * (j & 7); mm = (t >> 5) + 8 * (j >> 3); } else { mm = t & 31; kk = (t >> 5) + 8 * j; }
-      const int m = m0 + mm, k = k0 + kk;
-      ra[j] = (m < g.M && k < g.K) ? __ldg(g.A + m * g.sa_m + k * g.sa_k) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
       int nn, kk;
       if (B_NC) { nn = t & 31; kk = (t >> 5) + 8 * j; } else { kk = (t & 31) + 32 * (j & 7); nn = (t >> 5) + 8 * (j >> 3); }
       const int n = n0 + nn, k = k0 + kk;
       rb[j] = (n < g.N && k < g.K) ? __ldg(g.B + k * g.sb_k + n * g.sb_n) : 0.f;
+    }
+    // B is a weight, or an activation of an earlier pass, in every GEMM of the tail -- never written by the
+    // preceding kernel -- so its loads (above) run ahead of the grid-dependency wait.  A is loaded with volatile
+    // asm: __ldg loads are "pure" to the compiler and would be scheduled above the wait together with B's.
+    if (k0 == 0) pdl_enter();
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      int mm, kk;
+      if (A_KC) { kk = (t & 31) + 32 * (j & 7); mm = (t >> 5) + 8 * (j >> 3); } else { mm = t & 31; kk = (t >> 5) + 8 * j; }
+      const int m = m0 + mm, k = k0 + kk;
+      ra[j] = 0.f;
+      if (m < g.M && k < g.K) asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(ra[j]) : "l"(g.A + m * g.sa_m + k * g.sa_k));
     }
     if (k0 > 0) __syncthreads();               // previous chunk's math is done with the tiles
 #pragma unroll
@@ -249,10 +304,10 @@ inline void launch_gemm_fullk(const GemmArgs& g, cudaStream_t st) {
     cudaFuncSetAttribute(gemm_fullk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_set = true;
   }
-  if (akc && bnc) gemm_fullk_kernel<true, true><<<grid, 256, smem, st>>>(g);
-  else if (akc && !bnc) gemm_fullk_kernel<true, false><<<grid, 256, smem, st>>>(g);
-  else if (!akc && bnc) gemm_fullk_kernel<false, true><<<grid, 256, smem, st>>>(g);
-  else gemm_fullk_kernel<false, false><<<grid, 256, smem, st>>>(g);
+  if (akc && bnc) launch_k(gemm_fullk_kernel<true, true>, dim3(grid), dim3(256), smem, st, g);
+  else if (akc && !bnc) launch_k(gemm_fullk_kernel<true, false>, dim3(grid), dim3(256), smem, st, g);
+  else if (!akc && bnc) launch_k(gemm_fullk_kernel<false, true>, dim3(grid), dim3(256), smem, st, g);
+  else launch_k(gemm_fullk_kernel<false, false>, dim3(grid), dim3(256), smem, st, g);
 }
 
 inline cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t st) {
@@ -260,7 +315,9 @@ inline cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t st) {
   static int mode = -1;
   if (mode < 0) { const char* e = getenv("MPO_TAIL_GEMM"); mode = e ? atoi(e) : 1; }
   const long long blocks32 = static_cast<long long>((g.N + 31) / 32) * ((g.M + 31) / 32);
+  pdl_kind() = 1;
   if (mode == 1 && blocks32 <= 1184 && g.K <= 4 * kFkBK) {
+    pdl_kind() = 2;
     launch_gemm_fullk(g, st);                  // the latency-bound regime of the slide tail
   } else {
     // narrow tiles when 64-row tiles would leave most SMs idle
@@ -268,6 +325,7 @@ inline cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t st) {
     if (blocks64 < 96) launch_gemm_bm<32>(g, st);
     else launch_gemm_bm<64>(g, st);
   }
+  pdl_kind() = 0;
   count_launch();
   return cudaGetLastError();
 }
@@ -278,6 +336,7 @@ inline cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t st) {
 // dz[r][c] = dy[r][c] * act'(y[r][c])     (row strides allow views into wider buffers)
 __global__ void act_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ y,
                                long long ldy, float* __restrict__ dz, long long lddz, int rows, int cols, int act) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(rows) * cols) return;
   const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
@@ -287,20 +346,24 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, long long lddy, con
 // out[r][c] = a[r][c] + b[r][c]
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                            long long n) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + b[i];
 }
 __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                            long long n) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] * b[i];
 }
 // y = act(x) elementwise, in or out of place
 __global__ void act_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int act) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) y[i] = act_fwd(x[i], act);
 }
 __global__ void fill_kernel(float* __restrict__ x, long long n, float v) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) x[i] = v;
 }
@@ -310,6 +373,7 @@ __global__ void fill_kernel(float* __restrict__ x, long long n, float v) {
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ y, long long ldy,
               float* __restrict__ g, int rows, int cols) {
+  pdl_enter();
   __shared__ float part[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -341,6 +405,7 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ xhat,
                      float* __restrict__ rstd, int rows) {
+  pdl_enter();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -375,6 +440,7 @@ layernorm_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, c
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ gamma, const float* __restrict__ xhat,
                      const float* __restrict__ rstd, float* __restrict__ dx, int rows) {
+  pdl_enter();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -406,6 +472,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ gam
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 mha6_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ probs, float* __restrict__ ctx, int B) {
+  pdl_enter();
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (w >= B * 8) return;
@@ -448,6 +515,7 @@ mha6_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ probs, float*
 __global__ void __launch_bounds__(256)
 mha6_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs, const float* __restrict__ dctx,
                 float* __restrict__ dqkv, int B) {
+  pdl_enter();
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (w >= B * 8) return;
@@ -512,6 +580,7 @@ __global__ void __launch_bounds__(256)
 pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ bgate,
                 const float* __restrict__ wc, const float* __restrict__ bc, float* __restrict__ logits,
                 float* __restrict__ w, float* __restrict__ hp) {
+  pdl_enter();
   __shared__ float sh[8];
   const int b = blockIdx.x, d = threadIdx.x;
   float A[6];
@@ -543,6 +612,7 @@ pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a, const 
                 const float* __restrict__ wc, const float* __restrict__ w, const float* __restrict__ dhp,
                 float* __restrict__ dx, float* __restrict__ da_pre, float* __restrict__ db_pre,
                 float* __restrict__ gwc, float* __restrict__ gbc) {
+  pdl_enter();
   __shared__ float sh[8];
   const int b = blockIdx.x, d = threadIdx.x;
   const float g = dhp[static_cast<size_t>(b) * 256 + d];
@@ -576,6 +646,7 @@ pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a, const 
 // ------------------------------------------------------------------------------------------------
 __global__ void surv_head_fwd_kernel(const float* __restrict__ logits, float* __restrict__ hazards,
                                      float* __restrict__ S, float* __restrict__ Y, int B, int K) {
+  pdl_enter();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float m = -INFINITY;
@@ -597,6 +668,7 @@ __global__ void surv_head_bwd_kernel(const float* __restrict__ hazards, const fl
                                      const float* __restrict__ Y, const float* __restrict__ dhaz,
                                      const float* __restrict__ dS, const float* __restrict__ dY,
                                      float* __restrict__ dlogits, int B, int K) {
+  pdl_enter();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float dotY = 0.f;
@@ -618,6 +690,7 @@ __global__ void surv_loss_kernel(int kind, const float* __restrict__ hazards, co
                                  const int64_t* __restrict__ label, const float* __restrict__ censor, float alpha,
                                  float eps, float grad_scale, float* __restrict__ loss, float* __restrict__ dhaz,
                                  float* __restrict__ dS, int B, int K) {
+  pdl_enter();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int y = static_cast<int>(label[b]);
@@ -654,6 +727,7 @@ __global__ void surv_loss_kernel(int kind, const float* __restrict__ hazards, co
 __global__ void __launch_bounds__(256)
 bil_gate_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ U, const float* __restrict__ bias,
                     const float* __restrict__ h, float* __restrict__ g, float* __restrict__ gh) {
+  pdl_enter();
   const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int k = wid; k < 32; k += 8) {
     float s = 0.f;
@@ -672,6 +746,7 @@ __global__ void __launch_bounds__(256)
 bil_gate_bwd_kernel(const float* __restrict__ x1, const float* __restrict__ U, const float* __restrict__ h,
                     const float* __restrict__ g, const float* __restrict__ dgh, float* __restrict__ dh_pre,
                     float* __restrict__ dz, float* __restrict__ V, float* __restrict__ dx1, int accumulate_dx1) {
+  pdl_enter();
   __shared__ float dz_s[32];
   const int b = blockIdx.x, i = threadIdx.x;
   if (i < 32) {
@@ -696,6 +771,7 @@ bil_gate_bwd_kernel(const float* __restrict__ x1, const float* __restrict__ U, c
 // kp[b][i*33+j] = o1e[i]*o2e[j] with o?e = [o?, 1];  cat tail = [o1e, o2e] written at cat[b][64..130)
 __global__ void bil_kron_fwd_kernel(const float* __restrict__ o1, const float* __restrict__ o2,
                                     float* __restrict__ kp, float* __restrict__ cat) {
+  pdl_enter();
   const int b = blockIdx.x;
   for (int e = threadIdx.x; e < 33 * 33; e += blockDim.x) {
     const int i = e / 33, j = e % 33;
@@ -713,6 +789,7 @@ __global__ void bil_kron_fwd_kernel(const float* __restrict__ o1, const float* _
 __global__ void bil_kron_bwd_kernel(const float* __restrict__ o1, const float* __restrict__ o2,
                                     const float* __restrict__ dkp, const float* __restrict__ dcat,
                                     float* __restrict__ do1, float* __restrict__ do2) {
+  pdl_enter();
   const int b = blockIdx.x, t = threadIdx.x;   // 64 threads
   if (t < 32) {
     float s = dcat[static_cast<size_t>(b) * 130 + 64 + t];
