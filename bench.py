@@ -19,6 +19,13 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 N_PATCH = 16384
 ALGO_BYTES_PER_PATCH_PASS = 2048          # one bf16 row of 1024 features, read once per pass
@@ -151,7 +158,7 @@ def run_reference(args, rank):
         "e2e": {"value": rate, "unit": "slides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -259,9 +266,24 @@ def run_ours(args, rank, world, local_rank):
             b_.record(); torch.cuda.synchronize()
             return a.elapsed_time(b_) / reps
 
-        stages["bag_fwd_ms"] = t_stage(lambda: bpm.bag_forward(bag, eng._w_bf16, P["H.0.bias"].detach(), st.qk, st.bag_ws,
-                                                              seed=1, drop_p=st.drop_p))
-        stages["bag_bwd_ms"] = t_stage(lambda: bpm.bag_backward(bag, st.bag_ws, dpooled, st.qk, gw, gb, drop_p=st.drop_p))
+        if args.model == "mcat":
+            stages["bag_fwd_ms"] = t_stage(lambda: bpm.bag_forward(bag, eng._w_bf16, P["H.0.bias"].detach(), st.qk,
+                                                                  st.bag_ws, seed=1, drop_p=st.drop_p))
+            stages["bag_bwd_ms"] = t_stage(lambda: bpm.bag_backward(bag, st.bag_ws, dpooled, st.qk, gw, gb,
+                                                                   drop_p=st.drop_p))
+        else:
+            # NaCAGaT: projection pass + gate pass forward; the whole mpo_bag_bwd_nacagat chain backward
+            bk = P["co_attention.in_proj_bias"].detach()[256:512]
+
+            def nac_fwd():
+                bpm.bag_project(bag, eng._w_bf16, P["H.0.bias"].detach(), st.qk, st.bag_ws, seed=1, drop_p=st.drop_p)
+                bpm.bag_gate_forward(bag, eng._wk_f16, bk, st.qp, st.kc, st.bag_ws, seed=1, attn_drop_p=st.attn_p)
+
+            def nac_bwd():
+                st.dpooled.copy_(dpooled)
+                eng.bag_backward_only(trainer.model, st)
+            stages["bag_fwd_ms"] = t_stage(nac_fwd)
+            stages["bag_bwd_ms"] = t_stage(nac_bwd)
         stages["step_ms"] = ms / args.steps
         stages["tail_and_rest_ms"] = max(0.0, stages["step_ms"] - stages["bag_fwd_ms"] - stages["bag_bwd_ms"])
         peaks = {}
@@ -284,8 +306,9 @@ def run_ours(args, rank, world, local_rank):
                 traffic = float(ent["dram_bytes_per_launch"])
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": dom + ("_kernel (tcgen05 projection + fused co-attention)" if dom == "bag_fwd"
-                                                   else " (dz stream + tcgen05 dW_H GEMM)"),
+        roof = {"bound": "hbm", "kernel": dom + (" (tcgen05 projection + fused co-attention"
+                                                   + (", gate pass" if args.model != "mcat" else "") + ")"
+                                                   if dom == "bag_fwd" else " (tcgen05 row-expand dz stage + split-K dW GEMM)"),
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                 "whole_step_achieved": 2 * algo_bytes / (stages["step_ms"] * 1e-3) / 1e9,
@@ -375,13 +398,19 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
             "stages": stages,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse()
+    # the contract is ONE JSON line on stdout: libraries that write banners to fd 1 (NCCL prints its version there)
+    # are sent to stderr; the result line goes to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -393,7 +422,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)]
         cmd += sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))
     run_ours(args, rank, world, local_rank)
 
 

@@ -294,27 +294,11 @@ class SlideEngine:
         return bp.attention_map(st.bag, st.bag_ws, seed=st.seed, seed_dev=st.seed_dev if st.train else None,
                                 attn_drop_p=getattr(st, "attn_p", 0.0))
 
-    # -- backward
-    def backward(self, model, st, dhaz, dS, dY):
-        """model must carry gradient pointers; they are accumulated into."""
+    def bag_backward_only(self, model, st):
+        """the bag stage of the backward pass (mpo_bag_bwd / mpo_bag_bwd_nacagat) given st.dpooled (and st.dsuma)."""
         dev = st.bag.x.device
         f32 = dict(dtype=torch.float32, device=dev)
-        if st.dpooled is None:
-            st.dpooled = torch.empty((st.B, Q, D), **f32)
-        if st.bag_ws.nacagat and st.dsuma is None:
-            st.dsuma = torch.empty((st.B, Q), **f32)
-            st.dkc = torch.empty((st.B, Q), **f32)
-            st.dtq = torch.empty((st.B, Q, D), **f32)
-        io = self._io(st)
         s = _stream()
-
-        def prep(g):
-            if g is None:
-                return None
-            return g.detach().to(torch.float32).reshape(st.B, -1).contiguous()
-
-        dhaz, dS, dY = prep(dhaz), prep(dS), prep(dY)
-        _lib.call("mpo_tail_post_bwd", ctypes.byref(model), ctypes.byref(io), _ptr(dhaz), _ptr(dS), _ptr(dY), s)
         if not model.H.gw or not model.H.gb:
             raise RuntimeError("backward needs a model binding with gradient buffers")
         gw, gb = ctypes.c_void_p(model.H.gw), ctypes.c_void_p(model.H.gb)
@@ -349,6 +333,29 @@ class SlideEngine:
             _lib.call("mpo_bag_bwd", st.bag.c(), _ptr(ws.h_saved), _ptr(ws.scores), _ptr(ws.lse), _ptr(ws.pooled),
                       _ptr(st.dpooled), _ptr(st.qk), _ptr(ws.dz), _ptr(ws.part_dqk), _ptr(ws.part_db), _ptr(st.dqk),
                       gw, gb, ctypes.c_float(st.drop_p), s)
+
+    # -- backward
+    def backward(self, model, st, dhaz, dS, dY):
+        """model must carry gradient pointers; they are accumulated into."""
+        dev = st.bag.x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        if st.dpooled is None:
+            st.dpooled = torch.empty((st.B, Q, D), **f32)
+        if st.bag_ws.nacagat and st.dsuma is None:
+            st.dsuma = torch.empty((st.B, Q), **f32)
+            st.dkc = torch.empty((st.B, Q), **f32)
+            st.dtq = torch.empty((st.B, Q, D), **f32)
+        io = self._io(st)
+        s = _stream()
+
+        def prep(g):
+            if g is None:
+                return None
+            return g.detach().to(torch.float32).reshape(st.B, -1).contiguous()
+
+        dhaz, dS, dY = prep(dhaz), prep(dS), prep(dY)
+        _lib.call("mpo_tail_post_bwd", ctypes.byref(model), ctypes.byref(io), _ptr(dhaz), _ptr(dS), _ptr(dY), s)
+        self.bag_backward_only(model, st)
         io = self._io(st)
         _lib.call("mpo_tail_pre_bwd", ctypes.byref(model), ctypes.byref(io), s)
 

@@ -1,0 +1,103 @@
+"""2-GPU checks (NCCL), run when the box has at least two devices (`gpurun --gpus 2 -- python -m pytest tests -m gpu`):
+  * one bag sharded by patch range over two ranks + cross-GPU log-sum-exp combine == the reference outputs
+    (golden fixture generated from the unmodified reference, BASELINE config 5);
+  * data-parallel gradients: two ranks x 2 slides, one all-reduce == one rank x 4 slides."""
+import os
+import sys
+from importlib import import_module
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import load_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _pkg(name):
+    return import_module("multimodal-path-omic_b200." + name)
+
+
+def _build(case, dev):
+    synth = _pkg("synth")
+    cls = _pkg("mcat").MultimodalCoAttentionTransformer if case["model"] == "mcat" else \
+        _pkg("nacagat").NarrowContextualAttentionGateTransformer
+    net = cls(omic_sizes=list(synth.OMIC_SIZES), fusion=case["fusion"])
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in case["state"].items()})
+    return net.to(dev).eval()
+
+
+def _worker(rank, world, port, q):
+    import warnings
+    warnings.filterwarnings("ignore")
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dp = _pkg("dp"); sp = _pkg("slidepath"); bpm = _pkg("bagpass"); synth = _pkg("synth")
+    # ---- 1) patch-range sharded inference
+    case = load_case("mcat_concat_4096")
+    net = _build(case, dev)
+    a, b = dp.patch_range(case["n"], rank, world)
+    wsi = torch.from_numpy(case["bag"][a:b]).to(dev)
+    omics = [torch.from_numpy(o).to(dev) for o in case["omics"]]
+    hz, S, Y, amap = dp.sharded_inference(net, wsi, omics)
+    res = dict(rank=rank, hazards=hz.cpu().numpy(), amap=amap.cpu().numpy(), rows=(a, b))
+    # ---- 2) data-parallel gradients
+    lens = [300, 517, 129, 1000]
+    slides = [synth.make_slide(300 + i, n) for i, n in enumerate(lens)]
+    mine = dp.slide_shard(len(slides), rank, world)
+    tr = sp.BatchTrainer(net, loss="nll", grad_acc_step=len(slides))
+    tr.zero_grad()
+    pb = bpm.PackedBag.from_slides([torch.from_numpy(slides[i][0]).to(dev) for i in mine])
+    om = [torch.stack([torch.from_numpy(slides[i][1][j]) for i in mine]).to(dev) for j in range(6)]
+    labels = torch.tensor([slides[i][2] for i in mine], dtype=torch.int64, device=dev)
+    cens = torch.tensor([slides[i][3] for i in mine], dtype=torch.float32, device=dev)
+    tr.step(pb, om, labels, cens, train=False)
+    dp.all_reduce_gradients(tr.flat_grad)
+    res["grad_dp"] = tr.flat_grad.cpu().numpy()
+    if rank == 0:
+        tr.zero_grad()
+        pb = bpm.PackedBag.from_slides([torch.from_numpy(s[0]).to(dev) for s in slides])
+        om = [torch.stack([torch.from_numpy(s[1][j]) for s in slides]).to(dev) for j in range(6)]
+        labels = torch.tensor([s[2] for s in slides], dtype=torch.int64, device=dev)
+        cens = torch.tensor([s[3] for s in slides], dtype=torch.float32, device=dev)
+        tr.step(pb, om, labels, cens, train=False)
+        res["grad_one"] = tr.flat_grad.cpu().numpy()
+    torch.cuda.synchronize()
+    q.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_sharded_inference_and_dp_gradients():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=300) for _ in range(world)], key=lambda r: r["rank"])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    case = load_case("mcat_concat_4096")
+    g = case["gold"]
+    for r in got:
+        assert np.max(np.abs(r["hazards"] - g["hazards"]) / np.abs(g["hazards"])) < 1e-3
+    amap = np.concatenate([r["amap"] for r in got], axis=1).astype(np.float64)
+    ref = g["coattn"].astype(np.float64)
+    assert amap.shape == ref.shape
+    assert np.max(np.abs(amap - ref) / (np.abs(ref) + 1e-3 * ref.max())) < 1e-3
+    g1, gd = got[0]["grad_one"].astype(np.float64), got[0]["grad_dp"].astype(np.float64)
+    assert np.linalg.norm(gd - g1) / np.linalg.norm(g1) < 2e-3
+    assert np.allclose(got[0]["grad_dp"], got[1]["grad_dp"])
