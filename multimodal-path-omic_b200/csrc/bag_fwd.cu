@@ -26,7 +26,8 @@ constexpr int kABytes = kTileM * kBK * 2;            // 16 KB
 constexpr int kBBytes = kD * kBK * 2;                // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;       // 48 KB
 constexpr int kStagingBytes = kTileM * kD * 2;       // 64 KB  fp16 H tile, K-major SW128 (4 blocks of 128x64)
-constexpr int kEpiThreads = 256;
+constexpr int kEpiThreads = 512;                     // 16 epilogue warps: 4 per TMEM lane quadrant, 64 columns each
+constexpr int kCG = kEpiThreads / 128;               // column groups
 constexpr int kFwdThreads = 64 + kEpiThreads;
 
 struct FwdSmem {
@@ -169,10 +170,10 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue warps (2..9)
-    const int et = threadIdx.x - 64;           // 0..255
+    // ---------------------------------------------------------------- epilogue warps (2..17)
+    const int et = threadIdx.x - 64;           // 0..511
     const int qd = warp & 3;                   // TMEM lane quadrant this warp may access
-    const int ch = (warp - 2) >> 2;            // column half handled in step (1), feature half in step (4)
+    const int ch = (warp - 2) >> 2;            // column group (64 columns) in step (1); feature half in step (4) when < 2
     const int r = qd * 32 + lane;              // tile row (patch) owned in steps (1)-(3)
     float* bias_s = reinterpret_cast<float*>(smem + FwdSmem::bias);
     float* qk_s = reinterpret_cast<float*>(smem + FwdSmem::qk);
@@ -183,20 +184,43 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     uint8_t* Pb = smem + FwdSmem::Pb;
     constexpr uint32_t idesc_d = umma_idesc(kTileM, 16, 0, 0, 1, 0);   // D2 = H^T p^T  : fp16, A M-major, B K-major
 
-    bias_s[et] = p.bias[et];
-    // zero the small B operand once: rows 6..15 (the N padding) stay zero for the whole kernel
-    *reinterpret_cast<uint4*>(Pb + et * 16) = make_uint4(0, 0, 0, 0);
+    if (et < kD) {
+      bias_s[et] = p.bias[et];
+      // zero the small B operand once.  Rows 12..15 (the N padding) may later hold score partials (step 2 borrows the
+      // buffer): they only feed accumulator columns 12..15, which nobody reads
+      *reinterpret_cast<uint4*>(Pb + et * 16) = make_uint4(0, 0, 0, 0);
+    }
     const uint32_t seed = p.seed_dev != nullptr ? (p.seed ^ __ldg(p.seed_dev)) : p.seed;
     int cur_slide = -1;
     int it = 0;
+    int prev_t = -1;
+    // pooled partial of tile `tt` (accumulator stage `pas`): read one iteration late, so that nobody waits for the
+    // pooled MMA -- it retires while the next tile's accumulators are being awaited -- then hand the stage back
+    auto read_pooled = [&](int tt, int pas, uint32_t parity) {
+      mbar_wait(d_bar, parity);
+      tc_fence_after();
+      if (ch < 2) {
+        uint32_t dv[16];
+        tmem_ld_32x32b_x16(tmem_base + pas * kD + (static_cast<uint32_t>(qd * 32) << 16) + ch * 16, dv);
+        tmem_ld_wait();
+        float* dst = p.part_pool + static_cast<size_t>(tt) * (kQ * kD) + ch * 128 + qd * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) dst[i * kD] = __uint_as_float(dv[i]) + __uint_as_float(dv[i + 6]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[pas]);
+    };
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const TileInfo ti = p.tile_info[t];
+      if (prev_t >= 0) read_pooled(prev_t, (it - 1) & 1, (it - 1) & 1);   // also: the staged tile / P operand are free again
+      prev_t = -1;
       if (et == 32) tma_store_wait_read();      // the previous tile's H store no longer reads the staged tile
       if (ti.slide != cur_slide) {
         cur_slide = ti.slide;
         const float* src = p.qk + static_cast<size_t>(ti.slide) * kQ * kD;
 #pragma unroll
-        for (int j = 0; j < kQ; ++j) qk_s[et + j * 256] = src[et + j * 256];
+        for (int j = 0; j < kQ * kD / kEpiThreads; ++j) qk_s[et + j * kEpiThreads] = src[et + j * kEpiThreads];
       }
       named_bar_sync(1, kEpiThreads);           // qk visible; staging / P operand of the previous tile are free
 
@@ -213,8 +237,8 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       for (int i = 0; i < kQ; ++i) s[i] = 0.f;
       const uint32_t grow = static_cast<uint32_t>(ti.row0 + r);
 #pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const int col0 = ch * 128 + c4 * 32;
+      for (int c4 = 0; c4 < 8 / kCG; ++c4) {
+        const int col0 = ch * (kD / kCG) + c4 * 32;
         uint32_t v[32];
         tmem_ld_32x32b_x32(acc_col + (static_cast<uint32_t>(qd * 32) << 16) + col0, v);
         tmem_ld_wait();
@@ -276,12 +300,27 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           *reinterpret_cast<uint4*>(staging + cb * (kTileM * 128) + r * 128 + ((jj ^ (r & 7)) << 4)) = pk;
         }
       }
-      if (ch == 1) {
-        *reinterpret_cast<float4*>(spart_s + r * 8) = make_float4(s[0], s[1], s[2], s[3]);
-        *reinterpret_cast<float2*>(spart_s + r * 8 + 4) = make_float2(s[4], s[5]);
+      // score partials of the four column groups -> group 0, in two levels (two 4 KB scratch sets: spart and, until
+      // step 3 rewrites it, the P operand buffer): groups 1 and 3 publish, 0 and 2 add; group 2 publishes, 0 adds
+      float* scr = (ch == 1 || ch == 2) ? spart_s : reinterpret_cast<float*>(Pb);
+      if (ch == 1 || ch == 3) {
+        *reinterpret_cast<float4*>(scr + r * 8) = make_float4(s[0], s[1], s[2], s[3]);
+        *reinterpret_cast<float2*>(scr + r * 8 + 4) = make_float2(s[4], s[5]);
       }
       fence_proxy_async_smem();      // generic-proxy writes of the tile -> visible to UMMA / TMA (async proxy)
       tc_fence_before();
+      named_bar_sync(1, kEpiThreads);
+      if (ch == 0 || ch == 2) {
+        const float* src = ch == 0 ? spart_s : reinterpret_cast<const float*>(Pb);
+        const float4 o0 = *reinterpret_cast<const float4*>(src + r * 8);
+        const float2 o1 = *reinterpret_cast<const float2*>(src + r * 8 + 4);
+        s[0] += o0.x; s[1] += o0.y; s[2] += o0.z; s[3] += o0.w; s[4] += o1.x; s[5] += o1.y;
+      }
+      named_bar_sync(3, kEpiThreads);
+      if (ch == 2) {
+        *reinterpret_cast<float4*>(spart_s + r * 8) = make_float4(s[0], s[1], s[2], s[3]);
+        *reinterpret_cast<float2*>(spart_s + r * 8 + 4) = make_float2(s[4], s[5]);
+      }
       named_bar_sync(1, kEpiThreads);
       if (et == 32 && p.h_out != nullptr) {
         // keep the activations for the backward pass: one TMA store per 64-feature block, straight from the tile
@@ -328,6 +367,9 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           uint8_t* pcol = Pb + (r >> 6) * 2048 + (r & 7) * 2;
           *reinterpret_cast<__half*>(pcol + i * 128 + ((((r & 63) >> 3) ^ i) << 4)) = ph;
           *reinterpret_cast<__half*>(pcol + (i + 6) * 128 + ((((r & 63) >> 3) ^ ((i + 6) & 7)) << 4)) = pl;
+          if (i < 4) {   // rows 12..15 held score partials: clear this patch's column (keeps the padding finite)
+            *reinterpret_cast<__half*>(pcol + (i + 12) * 128 + ((((r & 63) >> 3) ^ ((i + 12) & 7)) << 4)) = __float2half_rn(0.f);
+          }
           float l = __half2float(ph) + __half2float(pl);   // the sum uses the weights the MMA will see
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
@@ -356,21 +398,9 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                       umma_desc_sw128(b0 + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), idesc_d, kk != 0 ? 1u : 0u);
         umma_commit(d_bar);
       }
-      mbar_wait(d_bar, tphase);
-      tc_fence_after();
-      {
-        uint32_t dv[16];
-        tmem_ld_32x32b_x16(acc_col + (static_cast<uint32_t>(qd * 32) << 16) + ch * 16, dv);
-        tmem_ld_wait();
-        float* dst = p.part_pool + static_cast<size_t>(t) * (kQ * kD) + ch * 128 + qd * 32 + lane;
-#pragma unroll
-        for (int i = 0; i < kQ; ++i) dst[i * kD] = __uint_as_float(dv[i]) + __uint_as_float(dv[i + 6]);
-      }
-      // accumulator stage (H, S and pooled columns) fully consumed: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      prev_t = t;
     }
+    if (prev_t >= 0) read_pooled(prev_t, (it - 1) & 1, (it - 1) & 1);
     if (et == 32) tma_store_wait_read();
   }
 
