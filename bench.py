@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--patches", type=int, default=N_PATCH)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary configurations (NaCAGaT, scaled window)")
     return ap.parse_args()
 
 
@@ -379,6 +380,50 @@ def run_ours(args, rank, world, local_rank):
                "d2h_bytes_per_step": B * 4, "steps": e2e_steps,
                "note": "pinned host bf16 bags, double-buffered H2D on a copy stream, loss read back every step"}
 
+    # ---- secondary configurations measured in the same run (N = 1 only): BASELINE config 2 (NaCAGaT train step) and
+    # the scaled accumulation window of SURVEY 8e (128 slides per optimizer step instead of the reference's 32)
+    also = None
+    if world == 1 and not args.no_also:
+        del graphed
+        torch.cuda.empty_cache()
+
+        def quick_rate(model_name, Bq, steps):
+            mcls = import_module(pkg + "mcat").MultimodalCoAttentionTransformer if model_name == "mcat" else \
+                import_module(pkg + "nacagat").NarrowContextualAttentionGateTransformer
+            torch.manual_seed(0)
+            qnet = mcls(omic_sizes=list(synth.OMIC_SIZES)).to(dev).train()
+            qtr = sp.BatchTrainer(qnet, loss="nll", grad_acc_step=Bq)
+            qopt = torch.optim.Adam(qnet.parameters(), lr=2e-4, weight_decay=1e-5, fused=True)
+            if Bq == B:
+                qx = x
+            else:
+                qx = torch.empty((Bq * N, 1024), dtype=torch.bfloat16, device=dev)
+                for b in range(Bq):
+                    qx[b * N:(b + 1) * N] = x[(b % B) * N:(b % B + 1) * N]
+            qbag = bpm.PackedBag(qx, (N,) * Bq)
+            qom = [torch.randn((Bq, d), generator=gen, device=dev) for d in synth.OMIC_SIZES]
+            qlab = torch.randint(0, 4, (Bq,), generator=gen, device=dev, dtype=torch.int64)
+            qcen = torch.randint(0, 2, (Bq,), generator=gen, device=dev).to(torch.float32)
+            qg = qtr.capture(qbag, qom, qlab, qcen, train=True)
+
+            def qstep():
+                qg.replay(); qopt.step(); qtr.zero_grad()
+            for _ in range(3):
+                qstep()
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                qstep()
+            b_.record(); torch.cuda.synchronize()
+            msq = a.elapsed_time(b_) / steps
+            return {"slides_per_s": Bq / (msq * 1e-3), "ms_per_step": msq, "slides_per_step": Bq,
+                    "gpu_launches_per_step": qg.launches_per_replay}
+        also = {}
+        other = "nacagat" if args.model == "mcat" else "mcat"
+        also[f"{other}_train_step_{N}_patches_B{B}"] = quick_rate(other, B, max(5, args.steps))
+        also[f"{args.model}_scaled_window_B{4 * B}"] = quick_rate(args.model, 4 * B, max(3, args.steps // 2))
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         rate, n, med = cpu_reference_rate(args.model, N, budget_s=12.0)
@@ -396,7 +441,7 @@ def run_ours(args, rank, world, local_rank):
                        "batch, one fp32 gradient all-reduce per step when N>1",
                        "l2": f"each step streams {B * N * 2048 / 1e9:.2f} GB of bag per GPU (> 126 MB L2), no flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "stages": stages,
+            "stages": stages, "also": also,
         }
         emit(line)
     if world > 1:
