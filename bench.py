@@ -191,7 +191,7 @@ def run_ours(args, rank, world, local_rank):
     net.train()
     B, N = args.batch, args.patches
     trainer = sp.BatchTrainer(net, loss="nll", grad_acc_step=B * world)
-    opt = torch.optim.Adam(net.parameters(), lr=2e-4, weight_decay=1e-5, fused=True)   # reference: mcat/main.py:298
+    trainer.use_flat_adam(lr=2e-4, weight_decay=1e-5)      # Adam(lr 2e-4, wd 1e-5): reference mcat/main.py:298, config.yaml
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -204,14 +204,15 @@ def run_ours(args, rank, world, local_rank):
     labels = torch.randint(0, 4, (B,), generator=gen, device=dev, dtype=torch.int64)
     censor = torch.randint(0, 2, (B,), generator=gen, device=dev).to(torch.float32)
 
-    graphed = trainer.capture(bag, omics, labels, censor, train=True)   # the whole step replays as one CUDA graph
+    # the whole step replays as one CUDA graph; on one GPU the Adam update rides in it, with several GPUs the
+    # gradient all-reduce sits between the graph and the (then eager, two-launch) Adam update
+    graphed = trainer.capture(bag, omics, labels, censor, train=True, with_adam=(world == 1))
 
     def one_step():
         loss, _, _ = graphed.replay()
         if world > 1:
             dist.all_reduce(trainer.flat_grad)          # one NCCL all-reduce of the flat fp32 gradient per step
-        opt.step()
-        trainer.zero_grad()
+            trainer.adam_step(zero_grad=True)
         return loss
 
     def barrier():
@@ -331,7 +332,8 @@ def run_ours(args, rank, world, local_rank):
         dev_cen = [censor.clone() for _ in range(2)]
         for dx in dev_x:
             dx.copy_(x)
-        steps_g = [trainer.capture(dev_bags[i], dev_om[i], dev_lab[i], dev_cen[i], train=True) for i in range(2)]
+        steps_g = [trainer.capture(dev_bags[i], dev_om[i], dev_lab[i], dev_cen[i], train=True, with_adam=(world == 1))
+                   for i in range(2)]
         copy_stream = torch.cuda.Stream(device=dev)
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
@@ -360,7 +362,7 @@ def run_ours(args, rank, world, local_rank):
                 freed[slot].record(torch.cuda.current_stream())
                 if world > 1:
                     dist.all_reduce(trainer.flat_grad)
-                opt.step(); trainer.zero_grad()
+                    trainer.adam_step(zero_grad=True)
                 loss_host.copy_(loss, non_blocking=True)
                 torch.cuda.current_stream().synchronize()      # the caller reads the loss every step (main.py:49)
 
@@ -393,7 +395,7 @@ def run_ours(args, rank, world, local_rank):
             torch.manual_seed(0)
             qnet = mcls(omic_sizes=list(synth.OMIC_SIZES)).to(dev).train()
             qtr = sp.BatchTrainer(qnet, loss="nll", grad_acc_step=Bq)
-            qopt = torch.optim.Adam(qnet.parameters(), lr=2e-4, weight_decay=1e-5, fused=True)
+            qtr.use_flat_adam(lr=2e-4, weight_decay=1e-5)
             if Bq == B:
                 qx = x
             else:
@@ -404,10 +406,10 @@ def run_ours(args, rank, world, local_rank):
             qom = [torch.randn((Bq, d), generator=gen, device=dev) for d in synth.OMIC_SIZES]
             qlab = torch.randint(0, 4, (Bq,), generator=gen, device=dev, dtype=torch.int64)
             qcen = torch.randint(0, 2, (Bq,), generator=gen, device=dev).to(torch.float32)
-            qg = qtr.capture(qbag, qom, qlab, qcen, train=True)
+            qg = qtr.capture(qbag, qom, qlab, qcen, train=True, with_adam=True)
 
             def qstep():
-                qg.replay(); qopt.step(); qtr.zero_grad()
+                qg.replay()
             for _ in range(3):
                 qstep()
             torch.cuda.synchronize()
@@ -437,8 +439,10 @@ def run_ours(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.model}_train_step_{N}_patches", "slides_per_gpu_per_step": B,
                        "global_slides_per_step": B * world, "patches_per_slide": N, "features": 1024,
-                       "parallelism": f"dp{world}", "mode": "train (dropout on the bag embedding), NLL loss, Adam step per "
-                       "batch, one fp32 gradient all-reduce per step when N>1",
+                       "parallelism": f"dp{world}", "mode": "train (dropout on the bag embedding"
+                       + (" and on the attention weights" if args.model != "mcat" else "") + "; the tail dropouts are not "
+                       "implemented yet), NLL loss, Adam(lr 2e-4, wd 1e-5) step per batch (mpo_adam_step, in the graph at N=1), "
+                       "one fp32 gradient all-reduce per step when N>1",
                        "l2": f"each step streams {B * N * 2048 / 1e9:.2f} GB of bag per GPU (> 126 MB L2), no flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
             "stages": stages, "also": also,

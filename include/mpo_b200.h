@@ -157,6 +157,14 @@ typedef struct mpo_nacagat_bwd {
 } mpo_nacagat_bwd;
 int mpo_bag_bwd_nacagat(const mpo_bag* bag, const mpo_nacagat_bwd* args, void* stream);
 
+/* Optimizer step of the reference drivers (torch.optim.Adam with L2 weight decay, models/mcat/main.py:298-299;
+ * SURVEY 8a row a14) over ONE flat fp32 buffer holding every parameter (and the matching flat gradient buffer the
+ * backward entry points accumulate into), fused with zeroing the gradients of the next accumulation window.
+ * *step_dev is the number of steps taken so far (bias correction); the call increments it on the device, so the
+ * step can sit inside a captured CUDA graph.  n must be a multiple of 4 and the buffers 16-byte aligned. */
+int mpo_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t* step_dev, int32_t zero_grad, void* stream);
+
 /* Cross-shard log-sum-exp combine for one bag split by patch range over `nshards` ranks:
  * lse_in fp32 [nshards][6], pooled_in fp32 [nshards][6][256] (each shard's normalised result, e.g. after an
  * all-gather) -> lse_out [6], pooled_out [6][256]. */

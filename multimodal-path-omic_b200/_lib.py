@@ -122,6 +122,8 @@ SIGNATURES = {
     "mpo_bag_bwd": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p],
     "mpo_bag_bwd_nacagat": [ctypes.POINTER(MpoBag), ctypes.POINTER(MpoNacagatBwd), c_void_p],
+    "mpo_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float,
+                      c_void_p, c_i32, c_void_p],
     "mpo_lse_combine": [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p],
     "mpo_tail_pre_fwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],
     "mpo_tail_post_fwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],

@@ -425,6 +425,52 @@ int mpo_bag_bwd_nacagat(const mpo_bag* bag, const mpo_nacagat_bwd* a, void* stre
                     "bag_bwd_dw_kernel (W_k)");
 }
 
+// Adam with L2 weight decay over one flat fp32 parameter buffer (torch.optim.Adam semantics, the optimizer of the
+// reference drivers: models/mcat/main.py:298-299), fused with zeroing the gradient buffer for the next window.
+__global__ void __launch_bounds__(256)
+adam_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                 float lr, float b1, float b2, float eps, float wd, const int32_t* __restrict__ step_dev, int zero_grad) {
+  const float t = static_cast<float>(*step_dev + 1);
+  const float bc1 = 1.f - powf(b1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  const float step_size = lr / bc1;
+  for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x * 4) {
+    float4 pv = *reinterpret_cast<float4*>(p + i), gv = *reinterpret_cast<float4*>(g + i);
+    float4 mv = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+    float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ge = gp[e] + wd * pp[e];
+      mp[e] = mp[e] + (ge - mp[e]) * (1.f - b1);
+      vp[e] = b2 * vp[e] + (1.f - b2) * ge * ge;
+      pp[e] -= step_size * mp[e] / (sqrtf(vp[e]) / bc2_sqrt + eps);
+    }
+    *reinterpret_cast<float4*>(p + i) = pv;
+    *reinterpret_cast<float4*>(m + i) = mv;
+    *reinterpret_cast<float4*>(v + i) = vv;
+    if (zero_grad) *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__global__ void bump_step_kernel(int32_t* s) { *s += 1; }
+
+int mpo_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t* step_dev, int32_t zero_grad, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step_dev || n < 0 || (n & 3))
+    return fail(MPO_E_ARG, "%s", "mpo_adam_step: null pointer or n not a multiple of 4");
+  if (num_sms() <= 0) return fail(MPO_E_CUDA, "%s", "mpo_adam_step: no CUDA device (this library has no CPU fallback)");
+  if (n == 0) return MPO_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t groups = n / 4;
+  int blocks = static_cast<int>((groups + 255) / 256);
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  adam_step_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                           step_dev, zero_grad);
+  bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
+  count_launch(2);
+  return check_cuda(cudaGetLastError(), "adam_step_kernel");
+}
+
 int mpo_lse_combine(const float* lse_in, const float* pooled_in, int32_t nshards, float* lse_out, float* pooled_out,
                     void* stream) {
   if (nshards <= 0 || !lse_in || !pooled_in || !lse_out || !pooled_out)

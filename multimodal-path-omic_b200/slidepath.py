@@ -422,14 +422,20 @@ class BatchTrainer:
         bnd = self.engine.binding
         P = bnd.params()
         dev = next(iter(P.values())).device
-        total = sum(p.numel() for p in P.values())
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.grads, off = {}, 0
+        # every parameter (and its gradient) is a 256-byte-aligned slice of one flat fp32 buffer: one all-reduce and
+        # one optimizer kernel cover the whole model
+        self.offsets, off = {}, 0
         for n, p in P.items():
-            g = self.flat_grad[off:off + p.numel()].view_as(p)
+            self.offsets[n] = off
+            off += (p.numel() + 63) // 64 * 64
+        total = off
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_param = None
+        self.grads = {}
+        for n, p in P.items():
+            g = self.flat_grad[self.offsets[n]:self.offsets[n] + p.numel()].view_as(p)
             p.grad = g
             self.grads[n] = g
-            off += p.numel()
         self.kind = {"nll": 0, "ces": 1}[loss]
         self.alpha = float(alpha if alpha is not None else (0.15 if loss == "nll" else 0.75))
         self.eps = float(eps)
@@ -438,6 +444,30 @@ class BatchTrainer:
 
     def zero_grad(self):
         self.flat_grad.zero_()
+
+    # -- optimizer over the flat buffers (mpo_adam_step)
+    def use_flat_adam(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5):
+        """Moves the parameters into one flat buffer (their nn.Parameter objects stay, .data becomes a view) and
+        sets up Adam state; adam_step() then updates the whole model with one kernel (reference optimizer:
+        torch.optim.Adam(lr=2e-4, weight_decay=1e-5), models/mcat/main.py:298-299, config.yaml:60-62)."""
+        P = self.engine.binding.params()
+        dev = self.flat_grad.device
+        self.flat_param = torch.zeros_like(self.flat_grad)
+        for n, p in P.items():
+            view = self.flat_param[self.offsets[n]:self.offsets[n] + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+        self.adam_m = torch.zeros_like(self.flat_grad)
+        self.adam_v = torch.zeros_like(self.flat_grad)
+        self.adam_step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.adam_hp = (float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay))
+        self.model = self.engine.binding.build(grads=self.grads)      # parameter addresses changed
+
+    def adam_step(self, zero_grad=True):
+        lr, b1, b2, eps, wd = self.adam_hp
+        _lib.call("mpo_adam_step", _ptr(self.flat_param), _ptr(self.flat_grad), _ptr(self.adam_m), _ptr(self.adam_v),
+                  self.flat_grad.numel(), ctypes.c_float(lr), ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps),
+                  ctypes.c_float(wd), _ptr(self.adam_step_dev), 1 if zero_grad else 0, _stream())
 
     def _run(self, st, bag, omics, labels, censor, train, seed):
         eng = self.engine
@@ -462,7 +492,7 @@ class BatchTrainer:
         self.last_state = st
         return st.loss, st.hazards, st.S
 
-    def capture(self, bag, omics, labels, censor, train=True):
+    def capture(self, bag, omics, labels, censor, train=True, with_adam=False):
         """Record one step (forward + loss + backward) over these STATIC buffers into a CUDA graph.
 
         The caller refreshes the contents of bag.x / omics / labels / censor in place and calls replay(); the
@@ -485,6 +515,8 @@ class BatchTrainer:
         _lib.lib().mpo_launch_count(1)
         with torch.cuda.graph(graph):
             self._run(st, bag, omics, labels, censor, train, 0)
+            if with_adam:        # single-GPU: the optimizer step (and the gradient reset) ride in the same graph
+                self.adam_step(zero_grad=True)
         launches = int(_lib.lib().mpo_launch_count(1))     # kernels recorded into the graph = launched per replay
         self.flat_grad.zero_()
         self.last_state = st

@@ -178,3 +178,28 @@ def test_cpu_tensors_are_refused():
     net = build_model(case, device="cpu").eval()
     with pytest.raises(RuntimeError):
         net(torch.from_numpy(case["bag"]), [torch.from_numpy(o) for o in case["omics"]])
+
+
+def test_flat_adam_matches_torch_adam():
+    """mpo_adam_step over the flat buffers == torch.optim.Adam(lr 2e-4, weight_decay 1e-5) (the reference's
+    optimizer, models/mcat/main.py:298-299), three steps, gradients zeroed by the fused step."""
+    import copy
+    sp = _pkg("slidepath")
+    case = load_case("mcat_concat_300")
+    net = build_model(case).eval()
+    ref = copy.deepcopy(net)
+    tr = sp.BatchTrainer(net, loss="nll", grad_acc_step=1)
+    tr.use_flat_adam(lr=2e-4, weight_decay=1e-5)
+    opt = torch.optim.Adam(ref.parameters(), lr=2e-4, weight_decay=1e-5)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for _ in range(3):
+        for (n, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+            g = torch.randn(p.shape, generator=gen, device="cuda") * 1e-2
+            p.grad.copy_(g)
+            q.grad = g.clone()
+        tr.adam_step(zero_grad=True)
+        opt.step()
+    torch.cuda.synchronize()
+    assert float(tr.flat_grad.abs().max()) == 0.0
+    for (n, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), n
