@@ -567,6 +567,63 @@ def model_forward_backward(P, wsi, omics, label=None, censor=None, model="mcat",
     return out
 
 
+# ------------------------------------------------------------------------------------------------ GE-NaCAGaT
+def ge_forward_backward(P, wsi, label=None, want_grads=True):
+    """One slide through GeneExprNarrowContextualAttentionGateTransformer (models/ge_nacagat/ge_nacagat.py:41-72), eval
+    mode: H projection, 1-head N x N self-attention over the patches (the averaged map is returned), 2-layer 8-head
+    encoder over the N tokens, gated attention pooling over N, 3-class softmax.  The loss is the reference driver's
+    nn.CrossEntropyLoss applied to the already soft-maxed Y (models/ge_nacagat/main.py:29,33: a double softmax)."""
+    P = _to64(P)
+    X = np.asarray(wsi, F64)
+    if X.ndim == 3:
+        X = X[0]
+    N = X.shape[0]
+    H = bag_proj_fwd(P, X)
+    E = H.shape[1]
+    Win, bin_ = P["self_attention.in_proj_weight"], P["self_attention.in_proj_bias"]
+    qkv = linear(H, Win, bin_)
+    q, k, v = np.split(qkv, 3, axis=1)
+    s = (q @ k.T) / np.sqrt(E)
+    a = softmax(s, axis=-1)                      # [N,N]; one head, so the head average is the map itself
+    ctx = a @ v
+    sa = linear(ctx, P["self_attention.out_proj.weight"], P["self_attention.out_proj.bias"])
+    pt, cpt = encoder_fwd(P, "path_transformer", sa)
+    A_path, h, cpp = pool_fwd(P, "path_attention_head", "path_rho", pt)
+    logits = linear(h[None, :], P["classifier.weight"], P["classifier.bias"])[0]
+    Y = softmax(logits, axis=-1)
+    out = dict(Y=Y, attn=a, path=A_path, logits=logits)
+    if label is None:
+        return out
+    z = softmax(Y, axis=-1)
+    out["loss"] = float(-np.log(z[int(label)]))
+    if not want_grads:
+        return out
+    grads = Grads()
+    dY = z.copy()
+    dY[int(label)] -= 1.0
+    dlogits = softmax_bwd(dY, Y, axis=-1)
+    dh, dWc, dbc = linear_bwd(dlogits[None, :], h[None, :], P["classifier.weight"])
+    grads.add("classifier.weight", dWc)
+    grads.add("classifier.bias", dbc)
+    dpt = pool_bwd(P, "path_attention_head", "path_rho", cpp, dh[0], grads)
+    dsa = encoder_bwd(P, "path_transformer", cpt, dpt, grads)
+    dctx, dWo, dbo = linear_bwd(dsa, ctx, P["self_attention.out_proj.weight"])
+    grads.add("self_attention.out_proj.weight", dWo)
+    grads.add("self_attention.out_proj.bias", dbo)
+    da = dctx @ v.T
+    dv = a.T @ dctx
+    ds = softmax_bwd(da, a, axis=-1) / np.sqrt(E)
+    dq = ds @ k
+    dk = ds.T @ q
+    dqkv = np.concatenate([dq, dk, dv], axis=1)
+    dH, dWin, dbin = linear_bwd(dqkv, H, Win)
+    grads.add("self_attention.in_proj_weight", dWin)
+    grads.add("self_attention.in_proj_bias", dbin)
+    bag_proj_bwd(P, X, H, dH, grads)
+    out["grads"] = dict(grads)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ folded bag stage
 def folded_bag_stage(W_h, b_h, qk, X):
     """The algebra the CUDA bag kernels implement: returns H, scores [6,N], lse [6], pooled [6,256]."""

@@ -32,6 +32,14 @@ CASES = [
 ]
 
 
+GE_CASES = [
+    # name,        N,   seed, sharpen
+    ("ge_300", 300, 21, 1.0),
+    ("ge_sharp_517", 517, 22, 4.0),
+    ("ge_1000", 1000, 23, 2.0),
+]
+
+
 def import_reference():
     sys.modules.setdefault("h5py", types.ModuleType("h5py"))      # models/utils.py:1 imports it, unused on this path
     if REF not in sys.path:
@@ -88,6 +96,39 @@ def main():
         np.savez_compressed(os.path.join(outdir, name + ".npz"), **rec)
         print(f"{name}: hazards={rec['hazards'].round(5).tolist()} loss_nll={rec['loss_nll']:.6f} "
               f"coattn max={rec['coattn'].max():.3e} min={rec['coattn'].min():.3e}")
+
+    # GE-NaCAGaT (models/ge_nacagat/ge_nacagat.py): Y, the N x N self-attention map (digest + corner block), the
+    # pooling logits, the driver's CrossEntropyLoss on Y (models/ge_nacagat/main.py:33) and its gradient digests
+    from models.ge_nacagat.ge_nacagat import GeneExprNarrowContextualAttentionGateTransformer as GE
+    for name, n, seed, sharpen in GE_CASES:
+        torch.manual_seed(seed)
+        net = GE()
+        shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        state = synth.make_state(shapes, seed, model="ge", sharpen=sharpen)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()})
+        net.eval()
+        bag, _, label, _ = synth.make_slide(seed, n)
+        label = label % 3
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            Y, att = net(wsi=torch.from_numpy(bag))
+        loss = torch.nn.CrossEntropyLoss()(Y.unsqueeze(0), torch.tensor([label]))
+        net.zero_grad()
+        loss.backward()
+        A = att["attn"].detach().numpy()
+        rec = dict(Y=Y.detach().numpy(), path=att["path"].detach().numpy(), attn_corner=A[:64, :64].copy(),
+                   attn_digest=synth.grad_digest("attn", A), attn_rowmax=A.max(axis=1), loss=np.float64(loss.item()),
+                   meta=np.array([n, seed, label, 0.0, sharpen], dtype=np.float64))
+        names = []
+        for k, p_ in net.named_parameters():
+            g = p_.grad.detach().numpy() if p_.grad is not None else np.zeros(tuple(p_.shape), np.float32)
+            rec["gd/" + k] = synth.grad_digest(k, g)
+            names.append(k)
+        rec["param_names"] = np.array(names)
+        rec["param_shapes"] = np.array([str(shapes[k]) for k in names])
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), **rec)
+        print(f"{name}: Y={rec['Y'].round(5).tolist()} loss={rec['loss']:.6f} attn max={A.max():.3e}")
 
     # loss known answers: the reference's own test vectors (models/loss.py:108-121) plus the SURVEY 8c probes
     hz = torch.tensor([0.51, 0.52, 0.49, 0.48]).reshape(1, 4)

@@ -12,7 +12,22 @@ synth = import_module("multimodal-path-omic_b200.synth")
 
 def golden_cases():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not p.endswith("loss_known_answers.npz"))
+                  if not p.endswith("loss_known_answers.npz") and not os.path.basename(p).startswith("ge_"))
+
+
+def ge_cases():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "ge_*.npz")))
+
+
+def load_ge_case(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    n, seed, label, _, sharpen = z["meta"]
+    names = [str(s) for s in z["param_names"]]
+    shapes = {k: ast.literal_eval(str(s)) for k, s in zip(names, z["param_shapes"])}
+    state = synth.make_state(shapes, int(seed), model="ge", sharpen=float(sharpen))
+    bag, _, _, _ = synth.make_slide(int(seed), int(n))
+    return dict(name=name, model="ge", n=int(n), seed=int(seed), label=int(label), state=state, bag=bag, gold=z,
+                param_names=names)
 
 
 def load_case(name):

@@ -6,7 +6,7 @@ import sys
 import numpy as np
 import pytest
 
-from helpers import GOLDEN_DIR, digest_errors, golden_cases, load_case
+from helpers import GOLDEN_DIR, digest_errors, ge_cases, golden_cases, load_case, load_ge_case
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 import mpo_oracle as orc  # noqa: E402
@@ -31,6 +31,30 @@ def test_oracle_matches_reference_fixture(name):
     assert abs(ces["loss"] - float(g["loss_ces"])) < 1e-5
     worst, details = digest_errors(c, out["grads"])
     assert worst < GRAD_TOL, sorted(details, key=lambda d: -d[2])[:3]
+    assert set(out["grads"].keys()) == set(c["param_names"])
+
+
+@pytest.mark.parametrize("name", ge_cases())
+def test_oracle_matches_reference_ge_fixture(name):
+    """GE-NaCAGaT (models/ge_nacagat/ge_nacagat.py) forward + the driver's double-softmax cross-entropy + gradients."""
+    from importlib import import_module
+    synth = import_module("multimodal-path-omic_b200.synth")
+    c = load_ge_case(name)
+    out = orc.ge_forward_backward(c["state"], c["bag"], c["label"])
+    g = c["gold"]
+    assert np.max(np.abs(out["Y"] - g["Y"]) / np.abs(g["Y"])) < OUT_TOL
+    assert np.max(np.abs(out["path"] - g["path"])) / np.max(np.abs(g["path"])) < OUT_TOL
+    A = out["attn"]
+    assert A.shape == (c["n"], c["n"])
+    assert np.max(np.abs(A[:64, :64] - g["attn_corner"]) / (np.abs(g["attn_corner"]) + 1e-3 * g["attn_corner"].max())) < 1e-3
+    assert np.max(np.abs(A.max(axis=1) - g["attn_rowmax"]) / g["attn_rowmax"]) < 1e-3
+    dref = g["attn_digest"]
+    dgot = synth.grad_digest("attn", A)
+    assert abs(dgot[0] - dref[0]) / dref[0] < 1e-4
+    assert abs(out["loss"] - float(g["loss"])) < 1e-5
+    worst, details = digest_errors(c, out["grads"])
+    # the reference's fp32 softmax-over-N reductions leave ~2e-3 of noise on its smallest gradients (norm 6e-6)
+    assert worst < 5 * GRAD_TOL, sorted(details, key=lambda d: -d[2])[:3]
     assert set(out["grads"].keys()) == set(c["param_names"])
 
 
