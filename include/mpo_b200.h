@@ -274,6 +274,34 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
 /* autograd of pre_fwd: consumes io->dqk and the workspace gradients, finishes co_attention.in_proj and SNN grads */
 int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * GE-NaCAGaT (models/ge_nacagat/ge_nacagat.py:9-72): WSI-only gene-expression classifier.  One slide per call.
+ * H projection = mpo_bag_fwd with pooled == NULL (h_saved + h_lo); then 1-head N x N self-attention over the patches
+ * (ge_nacagat.py:27,49 -- the map is returned, as in the reference), the 2-layer 8-head encoder over N tokens (:30-32,53),
+ * gated attention pooling over N (:56-60), classifier and soft-max (:66-68).  First functional version: the attention
+ * matrices are materialised in fp32 (N <= 46340), fp32 CUDA-core GEMMs; tensor cores in the projection and dW_H only.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct mpo_ge_model {
+  int32_t n_classes;                    /* 3 */
+  mpo_lin H;                            /* H.0 [256,1024]: only gw / gb are used here (dW_H, db_H)          */
+  mpo_lin sa_in;                        /* self_attention.in_proj_{weight,bias} [768,256]                     */
+  mpo_lin sa_out;                       /* self_attention.out_proj [256,256]                                  */
+  mpo_encoder_layer tr[2];              /* path_transformer.layers.{0,1}                                      */
+  mpo_pool_head pool;                   /* path_attention_head + path_rho                                     */
+  mpo_lin classifier;                   /* [n_classes,256]                                                    */
+} mpo_ge_model;
+/* workspace size in floats for a slide of N patches (dominated by 17 N x N attention matrices) */
+int64_t mpo_ge_ws_floats(int64_t N);
+/* attn fp32 [N][N] (attention_scores['attn']), path fp32 [N] raw pooling logits (attention_scores['path']), Y [n_classes] */
+int mpo_ge_fwd(const mpo_ge_model* m, int64_t N, const void* h_hi, const void* h_lo, float* ws, float* attn, float* path,
+               float* Y, void* stream);
+/* the reference driver's loss: nn.CrossEntropyLoss on the soft-maxed Y (models/ge_nacagat/main.py:29,33); dY scaled by grad_scale */
+int mpo_ge_ce_loss(const float* Y, const int64_t* label, int32_t n_classes, float grad_scale, float* loss, float* dY,
+                   void* stream);
+/* autograd of mpo_ge_fwd (+ the projection) given dY; gradients accumulated into m->*.gw/gb; dz_ws bf16 [N][256] */
+int mpo_ge_bwd(const mpo_ge_model* m, const mpo_bag* bag, const void* h_hi, float* ws, const float* attn, const float* path,
+               const float* Y, const float* dY, void* dz_ws, float keep_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,12 @@ class MpoTailIo(ctypes.Structure):
     ]
 
 
+class MpoGeModel(ctypes.Structure):
+    """struct mpo_ge_model (include/mpo_b200.h)."""
+    _fields_ = [("n_classes", c_i32), ("H", MpoLin), ("sa_in", MpoLin), ("sa_out", MpoLin), ("tr", MpoEncoderLayer * 2),
+                ("pool", MpoPoolHead), ("classifier", MpoLin)]
+
+
 class MpoNacagatBwd(ctypes.Structure):
     """struct mpo_nacagat_bwd (include/mpo_b200.h)."""
     _fields_ = [(n, c_void_p) for n in (
@@ -124,6 +130,10 @@ SIGNATURES = {
     "mpo_bag_bwd_nacagat": [ctypes.POINTER(MpoBag), ctypes.POINTER(MpoNacagatBwd), c_void_p],
     "mpo_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float,
                       c_void_p, c_i32, c_void_p],
+    "mpo_ge_fwd": [ctypes.POINTER(MpoGeModel), c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "mpo_ge_ce_loss": [c_void_p, c_void_p, c_i32, c_float, c_void_p, c_void_p, c_void_p],
+    "mpo_ge_bwd": [ctypes.POINTER(MpoGeModel), ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                   c_void_p, c_void_p, c_float, c_void_p],
     "mpo_lse_combine": [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p],
     "mpo_tail_pre_fwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],
     "mpo_tail_post_fwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],
@@ -133,7 +143,7 @@ SIGNATURES = {
     "mpo_tail_pre_bwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],
 }
 # functions with a non-int return type
-OTHER_EXPORTS = ["mpo_tail_ws_floats", "mpo_tail_ws_lookup", "mpo_sizeof", "mpo_launch_count"]
+OTHER_EXPORTS = ["mpo_tail_ws_floats", "mpo_tail_ws_lookup", "mpo_sizeof", "mpo_launch_count", "mpo_ge_ws_floats"]
 
 
 def _declare(L):
@@ -143,11 +153,13 @@ def _declare(L):
         fn.argtypes = argtypes
     L.mpo_tail_ws_floats.restype = c_i64
     L.mpo_tail_ws_floats.argtypes = [ctypes.POINTER(MpoModel), c_i32]
+    L.mpo_ge_ws_floats.restype = c_i64
+    L.mpo_ge_ws_floats.argtypes = [c_i64]
     L.mpo_launch_count.restype = c_i64
     L.mpo_launch_count.argtypes = [c_i32]
     L.mpo_sizeof.restype = c_i64
     L.mpo_sizeof.argtypes = [c_i32]
-    for which, st in enumerate((MpoBag, MpoModel, MpoTailIo, MpoNacagatBwd)):
+    for which, st in enumerate((MpoBag, MpoModel, MpoTailIo, MpoNacagatBwd, MpoGeModel)):
         if L.mpo_sizeof(which) != ctypes.sizeof(st):
             raise RuntimeError("ABI mismatch: %s is %d bytes in libmpo_b200.so but %d in the ctypes binding"
                                % (st.__name__, L.mpo_sizeof(which), ctypes.sizeof(st)))

@@ -177,14 +177,14 @@ mpo_lin sub(const mpo_lin& L, int row0, int in) {   // rows [row0, ...) of a pac
 // y[rows,out] = act(x[rows,in] W^T + b)
 void lin_fwd(Ctx& c, const float* x, long long ldx, const mpo_lin& L, int out, int in, float* y, long long ldy, int rows,
              int act) {
-  GemmArgs g{x, ldx, 1, L.w, 1, in, y, ldy, L.b, rows, out, in, 1.f, 0, act, nullptr};
+  GemmArgs g{x, ldx, 1, L.w, 1, in, y, ldy, L.b, rows, out, in, 1.f, 0, act, nullptr, 1};
   c.chk(launch_gemm(g, c.st), "lin_fwd");
 }
 // dz [rows,out] is the gradient at the pre-activation.  dx (=|+=) dz W ; gw += dz^T x ; gb += colsum(dz)
 void lin_bwd(Ctx& c, const float* dz, long long lddz, const float* x, long long ldx, const mpo_lin& L, int out, int in,
              float* dx, long long lddx, int rows, bool acc_dx) {
   if (dx != nullptr) {
-    GemmArgs g{dz, lddz, 1, L.w, in, 1, dx, lddx, nullptr, rows, in, out, 1.f, acc_dx ? 1 : 0, ACT_NONE, nullptr};
+    GemmArgs g{dz, lddz, 1, L.w, in, 1, dx, lddx, nullptr, rows, in, out, 1.f, acc_dx ? 1 : 0, ACT_NONE, nullptr, 1};
     c.chk(launch_gemm(g, c.st), "lin_bwd.dgrad");
   }
   if (L.gw != nullptr) {     // gw += dz^T x, with gb += rowsum(dz^T) fused into the same kernel
@@ -421,6 +421,91 @@ int check_model(const mpo_model* m, const mpo_tail_io* io, const char* who) {
   return MPO_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- GE-NaCAGaT
+// reference: models/ge_nacagat/ge_nacagat.py:41-72.  One slide per call; every stage is a bag-scale op over the N
+// patch tokens.  First functional version: fp32 CUDA-core GEMMs with the N x N attention matrices materialised
+// (the reference does the same and returns the 1-head map), tensor cores only in the H projection / dW_H.
+struct GeEnc { long long qkv, probs, ctx, sa, y1, xh1, rs1, f, f2, y2, xh2, rs2; };
+struct GeWs {
+  long long H, sa_qkv, sa_ctx, sa_out;
+  GeEnc enc[2];
+  long long pa, pb, pab, pw, hp, h, logits;
+  long long dlogits, dh, dzr, dhp, dw, dA, dab, t0, dx, dr2, df, dy1, dr1, dctx, dqkv, dP, dmid, dH, dzf;
+  long long total;
+};
+void ge_layout(long long N, GeWs& w) {
+  long long off = 0;
+  auto A = [&](long long n) { const long long o = off; off += (n + 63) / 64 * 64; return o; };
+  w.H = A(N * E); w.sa_qkv = A(N * 3 * E); w.sa_ctx = A(N * E); w.sa_out = A(N * E);
+  for (int l = 0; l < 2; ++l) {
+    GeEnc& b = w.enc[l];
+    b.qkv = A(N * 3 * E); b.probs = A(8 * N * N); b.ctx = A(N * E); b.sa = A(N * E); b.y1 = A(N * E); b.xh1 = A(N * E);
+    b.rs1 = A(N); b.f = A(N * FF); b.f2 = A(N * E); b.y2 = A(N * E); b.xh2 = A(N * E); b.rs2 = A(N);
+  }
+  w.pa = A(N * E); w.pb = A(N * E); w.pab = A(N * E); w.pw = A(N); w.hp = A(E); w.h = A(E); w.logits = A(16);
+  w.dlogits = A(16); w.dh = A(E); w.dzr = A(E); w.dhp = A(E); w.dw = A(N); w.dA = A(N); w.dab = A(N * E); w.t0 = A(N * E);
+  w.dx = A(N * E); w.dr2 = A(N * E); w.df = A(N * FF); w.dy1 = A(N * E); w.dr1 = A(N * E); w.dctx = A(N * E);
+  w.dqkv = A(N * 3 * E); w.dP = A(N * N); w.dmid = A(N * E); w.dH = A(N * E); w.dzf = A(N * E);
+  w.total = off;
+}
+// multi-head attention over N tokens from a packed [N, 3E] projection: probs [nh][N][N], ctx [N, E]
+void ge_attn_fwd(Ctx& c, const float* qkv, float* probs, float* ctx, int N, int nh) {
+  const int hd = E / nh;
+  const float scale = 1.f / sqrtf(static_cast<float>(hd));
+  for (int h = 0; h < nh; ++h) {
+    float* P = probs + (long long)h * N * N;
+    GemmArgs s{qkv + h * hd, 3 * E, 1, qkv + E + h * hd, 1, 3 * E, P, N, nullptr, N, N, hd, scale, 0, ACT_NONE, nullptr};
+    c.chk(launch_gemm(s, c.st), "ge.scores");
+    launch_k(row_softmax_kernel, dim3(N), dim3(256), 0, c.st, P, (long long)N, N); count_launch();
+    GemmArgs o{P, N, 1, qkv + 2 * E + h * hd, 3 * E, 1, ctx + h * hd, E, nullptr, N, hd, N, 1.f, 0, ACT_NONE, nullptr};
+    c.chk(launch_gemm(o, c.st), "ge.ctx");
+  }
+  c.chk(cudaGetLastError(), "ge_attn_fwd");
+}
+// dctx [N, E] -> dqkv [N, 3E]; dP is an [N, N] scratch
+void ge_attn_bwd(Ctx& c, const float* qkv, const float* probs, const float* dctx, float* dP, float* dqkv, int N, int nh) {
+  const int hd = E / nh;
+  const float scale = 1.f / sqrtf(static_cast<float>(hd));
+  for (int h = 0; h < nh; ++h) {
+    const float* P = probs + (long long)h * N * N;
+    // dP = dctx_h V_h^T ; dV_h = P^T dctx_h
+    GemmArgs g1{dctx + h * hd, E, 1, qkv + 2 * E + h * hd, 1, 3 * E, dP, N, nullptr, N, N, hd, 1.f, 0, ACT_NONE, nullptr};
+    c.chk(launch_gemm(g1, c.st), "ge.dP");
+    GemmArgs g2{P, 1, N, dctx + h * hd, E, 1, dqkv + 2 * E + h * hd, 3 * E, nullptr, N, hd, N, 1.f, 0, ACT_NONE, nullptr};
+    c.chk(launch_gemm(g2, c.st), "ge.dV");
+    launch_k(row_softmax_bwd_kernel, dim3(N), dim3(256), 0, c.st, P, (long long)N, dP, (long long)N, N, scale); count_launch();
+    // dQ_h = dS K_h ; dK_h = dS^T Q_h
+    GemmArgs g3{dP, N, 1, qkv + E + h * hd, 3 * E, 1, dqkv + h * hd, 3 * E, nullptr, N, hd, N, 1.f, 0, ACT_NONE, nullptr};
+    c.chk(launch_gemm(g3, c.st), "ge.dQ");
+    GemmArgs g4{dP, 1, N, qkv + h * hd, 3 * E, 1, dqkv + E + h * hd, 3 * E, nullptr, N, hd, N, 1.f, 0, ACT_NONE, nullptr};
+    c.chk(launch_gemm(g4, c.st), "ge.dK");
+  }
+  c.chk(cudaGetLastError(), "ge_attn_bwd");
+}
+void ge_enc_fwd(Ctx& c, const mpo_encoder_layer& P, const GeEnc& b, float* ws, const float* x, int N) {
+  lin_fwd(c, x, E, P.in_proj, 3 * E, E, ws + b.qkv, 3 * E, N, ACT_NONE);
+  ge_attn_fwd(c, ws + b.qkv, ws + b.probs, ws + b.ctx, N, 8);
+  lin_fwd(c, ws + b.ctx, E, P.out_proj, E, E, ws + b.sa, E, N, ACT_NONE);
+  ln_fwd(c, x, ws + b.sa, P.norm1, ws + b.y1, ws + b.xh1, ws + b.rs1, N);
+  lin_fwd(c, ws + b.y1, E, P.linear1, FF, E, ws + b.f, FF, N, ACT_RELU);
+  lin_fwd(c, ws + b.f, FF, P.linear2, E, FF, ws + b.f2, E, N, ACT_NONE);
+  ln_fwd(c, ws + b.y1, ws + b.f2, P.norm2, ws + b.y2, ws + b.xh2, ws + b.rs2, N);
+}
+void ge_enc_bwd(Ctx& c, const mpo_encoder_layer& P, const GeEnc& b, const GeWs& w, float* ws, const float* x,
+                const float* dy2, float* dx_out, int N) {
+  const long long n = (long long)N * E;
+  ln_bwd(c, dy2, P.norm2, ws + b.xh2, ws + b.rs2, ws + w.dr2, N);
+  lin_bwd(c, ws + w.dr2, E, ws + b.f, FF, P.linear2, E, FF, ws + w.df, FF, N, false);
+  act_bwd(c, ws + w.df, FF, ws + b.f, FF, ws + w.df, FF, N, FF, ACT_RELU);
+  lin_bwd(c, ws + w.df, FF, ws + b.y1, E, P.linear1, FF, E, ws + w.dy1, E, N, false);
+  add(c, ws + w.dy1, ws + w.dr2, ws + w.dy1, n);
+  ln_bwd(c, ws + w.dy1, P.norm1, ws + b.xh1, ws + b.rs1, ws + w.dr1, N);
+  lin_bwd(c, ws + w.dr1, E, ws + b.ctx, E, P.out_proj, E, E, ws + w.dctx, E, N, false);
+  ge_attn_bwd(c, ws + b.qkv, ws + b.probs, ws + w.dctx, ws + w.dP, ws + w.dqkv, N, 8);
+  lin_bwd(c, ws + w.dqkv, 3 * E, x, E, P.in_proj, 3 * E, E, dx_out, E, N, false);
+  add(c, dx_out, ws + w.dr1, dx_out, n);
+}
+
 }  // namespace
 }  // namespace mpo
 
@@ -434,6 +519,7 @@ int64_t mpo_sizeof(int32_t which) {
     case 1: return sizeof(mpo_model);
     case 2: return sizeof(mpo_tail_io);
     case 3: return sizeof(mpo_nacagat_bwd);
+    case 4: return sizeof(mpo_ge_model);
     default: return -1;
   }
 }
@@ -707,6 +793,121 @@ int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   }
   join(br);
   return finish(br.main);
+}
+
+// ------------------------------------------------------------------------------------------------ GE-NaCAGaT
+int64_t mpo_ge_ws_floats(int64_t N) {
+  if (N <= 0) return -1;
+  GeWs w; ge_layout(N, w);
+  return w.total;
+}
+
+static int check_ge(const mpo_ge_model* m, int64_t N, const char* who) {
+  if (!m) return fail(MPO_E_ARG, "%s: NULL model", who);
+  if (N <= 0 || N > 46340) return fail(MPO_E_ARG, "%s: N out of range", who);
+  if (m->n_classes < 1 || m->n_classes > 16) return fail(MPO_E_ARG, "%s: n_classes out of range", who);
+  if (num_sms() <= 0) return fail(MPO_E_CUDA, "%s: no CUDA device (this library has no CPU fallback)", who);
+  return MPO_OK;
+}
+
+int mpo_ge_fwd(const mpo_ge_model* m, int64_t N64, const void* h_hi, const void* h_lo, float* ws, float* attn,
+               float* path, float* Y, void* stream) {
+  int rc = check_ge(m, N64, "mpo_ge_fwd");
+  if (rc) return rc;
+  if (!h_hi || !h_lo || !ws || !attn || !path || !Y) return fail(MPO_E_ARG, "%s", "mpo_ge_fwd: NULL pointer");
+  const int N = static_cast<int>(N64);
+  GeWs w; ge_layout(N, w);
+  Ctx c; c.st = static_cast<cudaStream_t>(stream);
+  const long long n = (long long)N * E;
+  launch_k(ge_h_kernel, dim3(nblk(n)), dim3(256), 0, c.st, static_cast<const __half*>(h_hi), static_cast<const __half*>(h_lo),
+           ws + w.H, n); count_launch();
+  // self-attention over the patches, one head (ge_nacagat.py:27,49); the averaged map IS the head's map
+  lin_fwd(c, ws + w.H, E, m->sa_in, 3 * E, E, ws + w.sa_qkv, 3 * E, N, ACT_NONE);
+  ge_attn_fwd(c, ws + w.sa_qkv, attn, ws + w.sa_ctx, N, 1);
+  lin_fwd(c, ws + w.sa_ctx, E, m->sa_out, E, E, ws + w.sa_out, E, N, ACT_NONE);
+  // encoder over the N tokens (ge_nacagat.py:30-32,53)
+  ge_enc_fwd(c, m->tr[0], w.enc[0], ws, ws + w.sa_out, N);
+  ge_enc_fwd(c, m->tr[1], w.enc[1], ws, ws + w.enc[0].y2, N);
+  const float* x = ws + w.enc[1].y2;
+  // gated attention pooling over N (blocks.py:42-48, ge_nacagat.py:56-60)
+  lin_fwd(c, x, E, m->pool.att_a, E, E, ws + w.pa, E, N, ACT_TANH);
+  lin_fwd(c, x, E, m->pool.att_b, E, E, ws + w.pb, E, N, ACT_SIGMOID);
+  mul(c, ws + w.pa, ws + w.pb, ws + w.pab, n);
+  lin_fwd(c, ws + w.pab, E, m->pool.att_c, 1, E, path, 1, N, ACT_NONE);                 // raw logits A [N] (returned)
+  c.chk(cudaMemcpyAsync(ws + w.pw, path, (size_t)N * 4, cudaMemcpyDeviceToDevice, c.st), "ge.copy");
+  launch_k(row_softmax_kernel, dim3(1), dim3(256), 0, c.st, ws + w.pw, (long long)N, N); count_launch();
+  { GemmArgs g{ws + w.pw, N, 1, x, E, 1, ws + w.hp, E, nullptr, 1, E, N, 1.f, 0, ACT_NONE, nullptr};
+    c.chk(launch_gemm(g, c.st), "ge.pool"); }
+  lin_fwd(c, ws + w.hp, E, m->pool.rho, E, E, ws + w.h, E, 1, ACT_RELU);
+  lin_fwd(c, ws + w.h, E, m->classifier, m->n_classes, E, ws + w.logits, m->n_classes, 1, ACT_NONE);
+  c.chk(cudaMemcpyAsync(Y, ws + w.logits, (size_t)m->n_classes * 4, cudaMemcpyDeviceToDevice, c.st), "ge.copyY");
+  launch_k(row_softmax_kernel, dim3(1), dim3(256), 0, c.st, Y, (long long)m->n_classes, m->n_classes); count_launch();
+  c.chk(cudaGetLastError(), "mpo_ge_fwd");
+  return finish(c);
+}
+
+int mpo_ge_ce_loss(const float* Y, const int64_t* label, int32_t n_classes, float grad_scale, float* loss, float* dY,
+                   void* stream) {
+  if (!Y || !label || !loss || !dY || n_classes < 1) return fail(MPO_E_ARG, "%s", "mpo_ge_ce_loss: bad arguments");
+  if (num_sms() <= 0) return fail(MPO_E_CUDA, "%s", "mpo_ge_ce_loss: no CUDA device (this library has no CPU fallback)");
+  launch_k(ge_ce_loss_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream), Y,
+           reinterpret_cast<const long long*>(label), n_classes, grad_scale, loss, dY); count_launch();
+  return check_cuda(cudaGetLastError(), "ge_ce_loss_kernel");
+}
+
+int mpo_ge_bwd(const mpo_ge_model* m, const mpo_bag* bag, const void* h_hi, float* ws, const float* attn, const float* path,
+               const float* Y, const float* dY, void* dz_ws, float keep_scale, void* stream) {
+  if (!bag) return fail(MPO_E_ARG, "%s", "mpo_ge_bwd: bag is NULL");
+  int rc = check_ge(m, bag->total_rows, "mpo_ge_bwd");
+  if (rc) return rc;
+  if (!h_hi || !ws || !attn || !path || !Y || !dY || !dz_ws || !bag->x || bag->num_slides != 1)
+    return fail(MPO_E_ARG, "%s", "mpo_ge_bwd: NULL pointer (or more than one slide)");
+  if (!m->H.gw || !m->H.gb) return fail(MPO_E_ARG, "%s", "mpo_ge_bwd: the model carries no gradient buffers");
+  const int N = static_cast<int>(bag->total_rows);
+  GeWs w; ge_layout(N, w);
+  Ctx c; c.st = static_cast<cudaStream_t>(stream);
+  const long long n = (long long)N * E;
+  const int K = m->n_classes;
+  const float* x = ws + w.enc[1].y2;
+  // Y = softmax(logits)
+  c.chk(cudaMemcpyAsync(ws + w.dlogits, dY, (size_t)K * 4, cudaMemcpyDeviceToDevice, c.st), "ge.copy");
+  launch_k(row_softmax_bwd_kernel, dim3(1), dim3(256), 0, c.st, Y, (long long)K, ws + w.dlogits, (long long)K, K, 1.f); count_launch();
+  lin_bwd(c, ws + w.dlogits, K, ws + w.h, E, m->classifier, K, E, ws + w.dh, E, 1, false);
+  act_bwd(c, ws + w.dh, E, ws + w.h, E, ws + w.dzr, E, 1, E, ACT_RELU);
+  lin_bwd(c, ws + w.dzr, E, ws + w.hp, E, m->pool.rho, E, E, ws + w.dhp, E, 1, false);
+  // pooled = softmax(A)^T x : dw = dhp x^T [N], dx = w dhp [N,E]
+  { GemmArgs g{ws + w.dhp, E, 1, x, 1, E, ws + w.dw, N, nullptr, 1, N, E, 1.f, 0, ACT_NONE, nullptr};
+    c.chk(launch_gemm(g, c.st), "ge.dw"); }
+  { GemmArgs g{ws + w.pw, 1, 0, ws + w.dhp, 0, 1, ws + w.dx, E, nullptr, N, E, 1, 1.f, 0, ACT_NONE, nullptr};
+    c.chk(launch_gemm(g, c.st), "ge.dx"); }
+  launch_k(row_softmax_bwd_kernel, dim3(1), dim3(256), 0, c.st, ws + w.pw, (long long)N, ws + w.dw, (long long)N, N, 1.f); count_launch();
+  // A = (a * b) w_c + b_c
+  lin_bwd(c, ws + w.dw, 1, ws + w.pab, E, m->pool.att_c, 1, E, ws + w.dab, E, N, false);
+  mul(c, ws + w.dab, ws + w.pb, ws + w.t0, n);
+  act_bwd(c, ws + w.t0, E, ws + w.pa, E, ws + w.t0, E, N, E, ACT_TANH);
+  lin_bwd(c, ws + w.t0, E, x, E, m->pool.att_a, E, E, ws + w.dx, E, N, true);
+  mul(c, ws + w.dab, ws + w.pa, ws + w.t0, n);
+  act_bwd(c, ws + w.t0, E, ws + w.pb, E, ws + w.t0, E, N, E, ACT_SIGMOID);
+  lin_bwd(c, ws + w.t0, E, x, E, m->pool.att_b, E, E, ws + w.dx, E, N, true);
+  // encoder
+  ge_enc_bwd(c, m->tr[1], w.enc[1], w, ws, ws + w.enc[0].y2, ws + w.dx, ws + w.dmid, N);
+  ge_enc_bwd(c, m->tr[0], w.enc[0], w, ws, ws + w.sa_out, ws + w.dmid, ws + w.dx, N);
+  // self-attention
+  lin_bwd(c, ws + w.dx, E, ws + w.sa_ctx, E, m->sa_out, E, E, ws + w.dctx, E, N, false);
+  ge_attn_bwd(c, ws + w.sa_qkv, attn, ws + w.dctx, ws + w.dP, ws + w.dqkv, N, 1);
+  lin_bwd(c, ws + w.dqkv, 3 * E, ws + w.H, E, m->sa_in, 3 * E, E, ws + w.dH, E, N, false);
+  // H projection: dz = dH * mask; db_H += colsum(dz); dW_H += dz^T X on the tensor cores
+  launch_k(ge_dz_kernel, dim3(nblk(n)), dim3(256), 0, c.st, ws + w.dH, static_cast<const __half*>(h_hi), keep_scale,
+           ws + w.dzf, static_cast<__nv_bfloat16*>(dz_ws), n); count_launch();
+  launch_k(colsum_kernel, dim3(nblk(E, 32)), dim3(256), 0, c.st, ws + w.dzf, (long long)E, nullptr, (long long)0, m->H.gb, N, E); count_launch();
+  c.chk(cudaGetLastError(), "mpo_ge_bwd");
+  rc = finish(c);
+  if (rc) return rc;
+  CUtensorMap tm_dz, tm_x;
+  if ((rc = make_tmap_bf16_2d(&tm_dz, dz_ws, static_cast<uint64_t>(N), kD, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm_x, bag->x, static_cast<uint64_t>(N), kDIn, 64, 64))) return rc;
+  return check_cuda(launch_bag_bwd_dw(tm_dz, tm_x, m->H.gw, N, kDIn, kDIn, false, nullptr, num_sms(), c.st),
+                    "bag_bwd_dw_kernel (GE)");
 }
 
 }  // extern "C"

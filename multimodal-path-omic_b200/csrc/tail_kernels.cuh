@@ -97,6 +97,7 @@ struct GemmArgs {
   int accumulate;
   int act;
   float* rowsum;      // optional: rowsum[m] += alpha * sum_k A(m,k)   (fused bias gradient)
+  int b_static;       // 1: B is a parameter (never written inside the pass): its loads may run ahead of the PDL wait
 };
 
 // The tail is a long chain of small dependent GEMMs, so the kernel is built for latency: 32-deep K steps,
@@ -230,17 +231,21 @@ __global__ void __launch_bounds__(256) gemm_fullk_kernel(const GemmArgs g) {
   constexpr int PER = kFkBM * kFkBK / 256;     // 32 elements of each operand tile per thread and chunk
   for (int k0 = 0; k0 < g.K; k0 += kFkBK) {
     float ra[PER], rb[PER];
+    if (k0 == 0 && !g.b_static) pdl_enter();      // B may come from the preceding kernel: nothing is read before the wait
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
       int nn, kk;
       if (B_NC) { nn = t & 31; kk = (t >> 5) + 8 * j; } else { kk = (t & 31) + 32 * (j & 7); nn = (t >> 5) + 8 * (j >> 3); }
       const int n = n0 + nn, k = k0 + kk;
-      rb[j] = (n < g.N && k < g.K) ? __ldg(g.B + k * g.sb_k + n * g.sb_n) : 0.f;
+      rb[j] = 0.f;
+      if (n < g.N && k < g.K) {
+        if (g.b_static) rb[j] = __ldg(g.B + k * g.sb_k + n * g.sb_n);
+        else asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(rb[j]) : "l"(g.B + k * g.sb_k + n * g.sb_n));
+      }
     }
-    // B is a weight, or an activation of an earlier pass, in every GEMM of the tail -- never written by the
-    // preceding kernel -- so its loads (above) run ahead of the grid-dependency wait.  A is loaded with volatile
-    // asm: __ldg loads are "pure" to the compiler and would be scheduled above the wait together with B's.
-    if (k0 == 0) pdl_enter();
+    // when B is a parameter (b_static) its loads (above) run ahead of the grid-dependency wait.  A is loaded with
+    // volatile asm: __ldg loads are "pure" to the compiler and would be scheduled above the wait together with B's.
+    if (k0 == 0 && g.b_static) pdl_enter();
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
       int mm, kk;
@@ -801,6 +806,80 @@ __global__ void bil_kron_bwd_kernel(const float* __restrict__ o1, const float* _
     for (int i = 0; i < 33; ++i) s = fmaf(dkp[static_cast<size_t>(b) * 1089 + i * 33 + j], i < 32 ? o1[b * 32 + i] : 1.f, s);
     do2[b * 32 + j] = s;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GE-NaCAGaT helpers (models/ge_nacagat/ge_nacagat.py): soft-max over rows of N columns, forward and backward
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce_256(float v, bool is_max, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, u) : v + u;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+// x[row][:] = softmax(x[row][:]) in place; one 256-thread block per row
+__global__ void __launch_bounds__(256) row_softmax_kernel(float* __restrict__ x, long long ld, int cols) {
+  pdl_enter();
+  __shared__ float red[8];
+  float* row = x + static_cast<long long>(blockIdx.x) * ld;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, row[c]);
+  m = block_reduce_256(m, true, red);
+  float s = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) { const float e = __expf(row[c] - m); row[c] = e; s += e; }
+  s = block_reduce_256(s, false, red);
+  const float inv = 1.f / s;
+  for (int c = threadIdx.x; c < cols; c += 256) row[c] *= inv;
+}
+// ds[row][c] = a[row][c] (da[row][c] - sum_c a da) * scale, in place over da
+__global__ void __launch_bounds__(256)
+row_softmax_bwd_kernel(const float* __restrict__ a, long long lda, float* __restrict__ da, long long ldd, int cols, float scale) {
+  pdl_enter();
+  __shared__ float red[8];
+  const float* ar = a + static_cast<long long>(blockIdx.x) * lda;
+  float* dr = da + static_cast<long long>(blockIdx.x) * ldd;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) s = fmaf(ar[c], dr[c], s);
+  s = block_reduce_256(s, false, red);
+  for (int c = threadIdx.x; c < cols; c += 256) dr[c] = ar[c] * (dr[c] - s) * scale;
+}
+// H = fp16 hi + fp16 lo (the projection pass keeps both: bag_fwd.cu)
+__global__ void ge_h_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ H, long long n) {
+  pdl_enter();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) H[i] = __half2float(hi[i]) + __half2float(lo[i]);
+}
+// dz = dH * 1[h > 0] * keep_scale: fp32 (bias gradient) and bf16 (operand of the dW_H kernel)
+__global__ void ge_dz_kernel(const float* __restrict__ dH, const __half* __restrict__ hi, float keep, float* __restrict__ dzf,
+                             __nv_bfloat16* __restrict__ dz, long long n) {
+  pdl_enter();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float v = __half2float(hi[i]) > 0.f ? dH[i] * keep : 0.f;
+    dzf[i] = v;
+    dz[i] = __float2bfloat16_rn(v);
+  }
+}
+// nn.CrossEntropyLoss on the already soft-maxed Y (models/ge_nacagat/main.py:29,33): loss = -log softmax(Y)[label]
+__global__ void ge_ce_loss_kernel(const float* __restrict__ Y, const long long* __restrict__ label, int ncls, float scale,
+                                  float* __restrict__ loss, float* __restrict__ dY) {
+  pdl_enter();
+  if (threadIdx.x != 0) return;
+  float m = -INFINITY;
+  for (int j = 0; j < ncls; ++j) m = fmaxf(m, Y[j]);
+  float s = 0.f;
+  for (int j = 0; j < ncls; ++j) s += expf(Y[j] - m);
+  const int y = static_cast<int>(label[0]);
+  *loss = -(Y[y] - m - logf(s));
+  for (int j = 0; j < ncls; ++j) dY[j] = (expf(Y[j] - m) / s - (j == y ? 1.f : 0.f)) * scale;
 }
 
 }  // namespace mpo

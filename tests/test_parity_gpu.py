@@ -203,3 +203,49 @@ def test_flat_adam_matches_torch_adam():
     assert float(tr.flat_grad.abs().max()) == 0.0
     for (n, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
         assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), n
+
+
+from helpers import ge_cases, load_ge_case  # noqa: E402
+
+
+@pytest.mark.parametrize("name", ge_cases())
+def test_ge_nacagat_matches_reference(name):
+    """GE-NaCAGaT (models/ge_nacagat/ge_nacagat.py): Y, the N x N self-attention map, the pooling logits, the driver's
+    cross-entropy on the soft-maxed Y (main.py:29,33) and every parameter gradient against the reference fixtures."""
+    synth = _pkg("synth")
+    ge = _pkg("ge_nacagat")
+    case = load_ge_case(name)
+    net = ge.GeneExprNarrowContextualAttentionGateTransformer()
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in case["state"].items()})
+    net = net.cuda().eval()
+    wsi = torch.from_numpy(case["bag"]).cuda()
+    Y, att = net(wsi=wsi)
+    g = case["gold"]
+    n = case["n"]
+    assert Y.shape == (3,) and att["attn"].shape == (n, n) and att["path"].shape == (1, n)
+    A = att["attn"].cpu().numpy().astype(np.float64)
+    errs = dict(
+        Y=rel_err(Y.detach().cpu(), g["Y"]),
+        path=vec_rel_err(att["path"].cpu(), g["path"]),
+        attn_corner=float(np.max(np.abs(A[:64, :64] - g["attn_corner"]) /
+                                 (np.abs(g["attn_corner"]) + 1e-3 * g["attn_corner"].max()))),
+        attn_rowmax=float(np.max(np.abs(A.max(axis=1) - g["attn_rowmax"]) / g["attn_rowmax"])),
+        attn_norm=float(abs(synth.grad_digest("attn", A)[0] - g["attn_digest"][0]) / g["attn_digest"][0]),
+        rowsum=float(np.max(np.abs(A.sum(axis=1) - 1.0))),
+    )
+    print(name, {k: "%.2e" % v for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v < OUT_TOL, (k, v)
+    label = torch.tensor([case["label"]], device="cuda")
+    loss = ge.ge_cross_entropy(Y, label)
+    assert abs(loss.item() - float(g["loss"])) < 1e-3
+    ref_loss = torch.nn.functional.cross_entropy(Y.detach().unsqueeze(0), label)
+    assert abs(loss.item() - ref_loss.item()) < 1e-5
+    net.zero_grad()
+    loss.backward()
+    grads = {k: (p.grad.detach().cpu().numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32))
+             for k, p in net.named_parameters()}
+    worst, details = digest_errors(case, grads)
+    details.sort(key=lambda d: -d[2])
+    print(name, "grad worst %.2e" % worst, [(k, "%.1e" % nn_, "%.1e" % e) for k, nn_, e in details[:4]])
+    assert worst < GRAD_TOL, details[:5]
