@@ -425,6 +425,30 @@ def run_ours(args, rank, world, local_rank):
         other = "nacagat" if args.model == "mcat" else "mcat"
         also[f"{other}_train_step_{N}_patches_B{B}"] = quick_rate(other, B, max(5, args.steps))
         also[f"{args.model}_scaled_window_B{4 * B}"] = quick_rate(args.model, 4 * B, max(3, args.steps // 2))
+        torch.cuda.empty_cache()
+        # BASELINE config 4a: GE-NaCAGaT train step (forward + the driver's cross-entropy + backward), one slide
+        ge = import_module(pkg + "ge_nacagat")
+        torch.manual_seed(0)
+        gnet = ge.GeneExprNarrowContextualAttentionGateTransformer().to(dev).train()
+        gx = x[:N]
+        glab = torch.tensor([1], device=dev)
+
+        def gstep():
+            Yg, _ = gnet(wsi=gx)
+            ge.ge_cross_entropy(Yg, glab).backward()
+            gnet.zero_grad()
+        gstep(); torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            gstep()
+        b_.record(); torch.cuda.synchronize()
+        msg = a.elapsed_time(b_) / 3
+        also[f"ge_nacagat_train_step_{N}_patches_B1"] = {
+            "slides_per_s": 1e3 / msg, "ms_per_step": msg, "slides_per_step": 1,
+            "note": "first functional version: fp32 CUDA-core GEMMs, N x N attention materialised (DESIGN.md 4.5)"}
+        del gnet
+        torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
