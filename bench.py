@@ -463,9 +463,9 @@ def run_ours(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.model}_train_step_{N}_patches", "slides_per_gpu_per_step": B,
                        "global_slides_per_step": B * world, "patches_per_slide": N, "features": 1024,
-                       "parallelism": f"dp{world}", "mode": "train (dropout on the bag embedding"
-                       + (" and on the attention weights" if args.model != "mcat" else "") + "; the tail dropouts are not "
-                       "implemented yet), NLL loss, Adam(lr 2e-4, wd 1e-5) step per batch (mpo_adam_step, in the graph at N=1), "
+                       "parallelism": f"dp{world}", "mode": "train (every dropout layer of the path on: bag embedding, "
+                       + ("attention weights, " if args.model != "mcat" else "") + "SNN, encoder layers, pooling heads, rho), "
+                       "NLL loss, Adam(lr 2e-4, wd 1e-5) step per batch (mpo_adam_step, in the graph at N=1), "
                        "one fp32 gradient all-reduce per step when N>1",
                        "l2": f"each step streams {B * N * 2048 / 1e9:.2f} GB of bag per GPU (> 126 MB L2), no flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,

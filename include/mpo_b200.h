@@ -249,6 +249,13 @@ typedef struct mpo_tail_io {
   /* model outputs (mcat.py:126-142) */
   float* hazards; float* S; float* Y;   /* [B][n_classes] each                                        */
   float* att_path; float* att_omic;     /* [B][6] raw pooling logits (attention_scores['path'/'omic']) */
+  /* train mode: the dropout layers of the tail (SNN AlphaDropout mcat.py:38,42; encoder layers mcat.py:51-53; pooling
+   * heads blocks.py:34-36 (p fixed at 0.25); rho mcat.py:57; bilinear fusion fusion.py:58-76 (p 0.25)).  drop_p is the
+   * model's `dropout` (0 = eval: every dropout of the tail is the identity); masks come from the stateless RNG keyed by
+   * (seed ^ *seed_dev, site, element), so the backward entry points regenerate them from the same three fields. */
+  float drop_p;
+  uint32_t seed;
+  const uint32_t* seed_dev;
 } mpo_tail_io;
 
 /* ABI self-check for bindings: sizeof(mpo_bag) (which = 0), sizeof(mpo_model) (1), sizeof(mpo_tail_io) (2),

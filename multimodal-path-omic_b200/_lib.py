@@ -74,6 +74,7 @@ class MpoTailIo(ctypes.Structure):
         ("dpooled", c_void_p),
         ("dqk", c_void_p), ("dkc", c_void_p), ("dtq", c_void_p),
         ("hazards", c_void_p), ("S", c_void_p), ("Y", c_void_p), ("att_path", c_void_p), ("att_omic", c_void_p),
+        ("drop_p", c_float), ("seed", c_u32), ("seed_dev", c_void_p),
     ]
 
 

@@ -44,7 +44,7 @@ struct Ws {
   // gradients / scratch
   long long dlogits, dh, dcat, dz1, dz2, dhp[2], dtok[2], dG, dqp, dhc, dv;
   // per-branch scratch (0 = path / main stream, 1 = omic / second stream): the branches run concurrently
-  long long dxa[2], dxb[2], dzr[2], dmid[2], s768[2], s512[2], s256a[2], s256b[2], s256c[2];
+  long long dxa[2], dxb[2], dzr[2], dmid[2], s768[2], s512[2], s256a[2], s256b[2], s256c[2], dmk1[2], dmk2[2];
   long long snn_dz1[MPO_Q], snn_dz2[MPO_Q], snn_dh[MPO_Q];
   long long bV, bdkp, bdcat130, bdo[2], bdgh[2], bdh[2], bdz[2], bdx[2];
   Layout lay;
@@ -106,6 +106,7 @@ void build_layout(const mpo_model* m, int B, Ws& w) {
     w.dxa[s] = A("dxa", R * E); w.dxb[s] = A("dxb", R * E); w.dzr[s] = A("dzr", (long long)B * E);
     w.dmid[s] = A("dmid", R * E); w.s768[s] = A("s768", R * 3 * E); w.s512[s] = A("s512", R * FF);
     w.s256a[s] = A("s256a", R * E); w.s256b[s] = A("s256b", R * E); w.s256c[s] = A("s256c", R * E);
+    w.dmk1[s] = A("dmk1", R * E); w.dmk2[s] = A("dmk2", R * E);
   }
   for (int i = 0; i < MPO_Q; ++i) {
     snprintf(nm, sizeof nm, "snn_dz1_%d", i); w.snn_dz1[i] = L.add(nm, (long long)B * E);
@@ -146,6 +147,9 @@ struct Ctx {
   cudaStream_t wst = nullptr;  // weight-gradient stream of this branch, valid when async_w
   bool async_w = false;        // (a null stream handle is the legacy default stream, so it cannot double as "none")
   int sb = 0;                  // scratch set of this branch
+  float drop_p = 0.f;          // train-mode dropout of the tail (0 = eval); seed of the mask streams
+  uint32_t seed = 0;
+  const uint32_t* seed_dev = nullptr;
   cudaError_t err = cudaSuccess;
   const char* where = "";
   void chk(cudaError_t e, const char* w) { if (err == cudaSuccess && e != cudaSuccess) { err = e; where = w; } }
@@ -163,6 +167,26 @@ void dep(Ctx& c, cudaStream_t from, cudaStream_t to) {
 // the compute stream waits for this branch's pending weight-gradient GEMMs (before their inputs are overwritten)
 void join_w(Ctx& c) { if (c.async_w) dep(c, c.wst, c.st); }
 
+// dropout sites of the tail (the bag stage uses sites 0 and 1)
+enum : uint32_t { SITE_SNN = 16, SITE_ENC = 32, SITE_POOL = 48, SITE_RHO = 52, SITE_BIL = 56 };
+DropSpec no_drop() { DropSpec d = {}; return d; }
+DropSpec mk_drop(const Ctx& c, float p, uint32_t site, bool alpha = false) {
+  DropSpec d = {};
+  if (c.drop_p <= 0.f || p <= 0.f) return d;       // eval, or a model built with dropout = 0
+  d.thr = static_cast<uint32_t>(p * 256.f + 0.5f);
+  if (d.thr == 0) return d;
+  const float pe = static_cast<float>(d.thr) / 256.f;     // the probability actually drawn
+  d.site = site; d.seed = c.seed; d.seed_dev = c.seed_dev; d.alpha = alpha ? 1 : 0;
+  if (alpha) {        // nn.AlphaDropout: a = ((1-p)(1 + p alpha'^2))^-1/2, b = -a alpha' p
+    d.scale = 1.f / sqrtf((1.f - pe) * (1.f + pe * kAlphaPrime * kAlphaPrime));
+    d.shift = -d.scale * kAlphaPrime * pe;
+  } else {
+    d.scale = 1.f / (1.f - pe);
+    d.shift = 0.f;
+  }
+  return d;
+}
+
 inline unsigned nblk(long long n, int t = 256) { return static_cast<unsigned>((n + t - 1) / t); }
 
 mpo_lin sub(const mpo_lin& L, int row0, int in) {   // rows [row0, ...) of a packed projection
@@ -176,8 +200,8 @@ mpo_lin sub(const mpo_lin& L, int row0, int in) {   // rows [row0, ...) of a pac
 
 // y[rows,out] = act(x[rows,in] W^T + b)
 void lin_fwd(Ctx& c, const float* x, long long ldx, const mpo_lin& L, int out, int in, float* y, long long ldy, int rows,
-             int act) {
-  GemmArgs g{x, ldx, 1, L.w, 1, in, y, ldy, L.b, rows, out, in, 1.f, 0, act, nullptr, 1};
+             int act, const DropSpec drop = DropSpec{}) {
+  GemmArgs g{x, ldx, 1, L.w, 1, in, y, ldy, L.b, rows, out, in, 1.f, 0, act, nullptr, 1, drop};
   c.chk(launch_gemm(g, c.st), "lin_fwd");
 }
 // dz [rows,out] is the gradient at the pre-activation.  dx (=|+=) dz W ; gw += dz^T x ; gb += colsum(dz)
@@ -198,8 +222,9 @@ void lin_bwd(Ctx& c, const float* dz, long long lddz, const float* x, long long 
   }
 }
 void act_bwd(Ctx& c, const float* dy, long long lddy, const float* y, long long ldy, float* dz, long long lddz, int rows,
-             int cols, int act) {
-  launch_k(act_bwd_kernel, dim3(nblk((long long)rows * cols)), dim3(256), 0, c.st, dy, lddy, y, ldy, dz, lddz, rows, cols, act); count_launch();
+             int cols, int act, const DropSpec drop = DropSpec{}) {
+  launch_k(act_bwd_kernel, dim3(nblk((long long)rows * cols)), dim3(256), 0, c.st, dy, lddy, y, ldy, dz, lddz, rows, cols, act,
+           drop); count_launch();
   c.chk(cudaGetLastError(), "act_bwd");
 }
 void add(Ctx& c, const float* a, const float* b, float* out, long long n) {
@@ -232,37 +257,52 @@ void ln_bwd(Ctx& c, const float* dy, const mpo_norm& N, const float* xh, const f
 
 // ---------------------------------------------------------------------------------------------- encoder layer
 // reference: nn.TransformerEncoderLayer (post-norm) as built at models/mcat/mcat.py:51-53
-void enc_fwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, float* ws, const float* x, int B) {
+void enc_fwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, float* ws, const float* x, int B, int eidx) {
   const int R = 6 * B;
+  const uint32_t s0 = SITE_ENC + 4 * eidx;      // attention probabilities, dropout1, feed-forward dropout, dropout2
   lin_fwd(c, x, E, P.in_proj, 3 * E, E, ws + b.qkv, 3 * E, R, ACT_NONE);
-  launch_k(mha6_fwd_kernel, dim3(nblk((long long)B * 8, 8)), dim3(256), 0, c.st, ws + b.qkv, ws + b.probs, ws + b.ctx, B); count_launch();
+  launch_k(mha6_fwd_kernel, dim3(nblk((long long)B * 8, 8)), dim3(256), 0, c.st, ws + b.qkv, ws + b.probs, ws + b.ctx, B,
+           mk_drop(c, c.drop_p, s0)); count_launch();
   c.chk(cudaGetLastError(), "mha6_fwd");
-  lin_fwd(c, ws + b.ctx, E, P.out_proj, E, E, ws + b.sa, E, R, ACT_NONE);
+  lin_fwd(c, ws + b.ctx, E, P.out_proj, E, E, ws + b.sa, E, R, ACT_NONE, mk_drop(c, c.drop_p, s0 + 1));
   ln_fwd(c, x, ws + b.sa, P.norm1, ws + b.y1, ws + b.xh1, ws + b.rs1, R);
-  lin_fwd(c, ws + b.y1, E, P.linear1, FF, E, ws + b.f, FF, R, ACT_RELU);
-  lin_fwd(c, ws + b.f, FF, P.linear2, E, FF, ws + b.f2, E, R, ACT_NONE);
+  lin_fwd(c, ws + b.y1, E, P.linear1, FF, E, ws + b.f, FF, R, ACT_RELU, mk_drop(c, c.drop_p, s0 + 2));
+  lin_fwd(c, ws + b.f, FF, P.linear2, E, FF, ws + b.f2, E, R, ACT_NONE, mk_drop(c, c.drop_p, s0 + 3));
   ln_fwd(c, ws + b.y1, ws + b.f2, P.norm2, ws + b.y2, ws + b.xh2, ws + b.rs2, R);
 }
 // dy2 -> dx (written to dx_out).  Scratch of branch c.sb; every gradient that a pending weight-gradient GEMM still
 // reads keeps its own buffer until the next join_w().
 void enc_bwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, const Ws& w, float* ws, const float* x,
-             const float* dy2, float* dx_out, int B) {
+             const float* dy2, float* dx_out, int B, int eidx) {
   const int R = 6 * B;
+  const uint32_t s0 = SITE_ENC + 4 * eidx;
+  const bool train = c.drop_p > 0.f;
   join_w(c);
-  float* dr2 = ws + w.s256a[c.sb];     // gradient of (y1 + f2)
+  float* dr2 = ws + w.s256a[c.sb];     // gradient of (y1 + dropout2(f2))
   ln_bwd(c, dy2, P.norm2, ws + b.xh2, ws + b.rs2, dr2, R);
+  const float* df2 = dr2;              // gradient of f2: through dropout2 in train mode
+  if (train) {
+    act_bwd(c, dr2, E, ws + b.f2, E, ws + w.dmk2[c.sb], E, R, E, ACT_NONE, mk_drop(c, c.drop_p, s0 + 3));
+    df2 = ws + w.dmk2[c.sb];
+  }
   float* df = ws + w.s512[c.sb];
-  lin_bwd(c, dr2, E, ws + b.f, FF, P.linear2, E, FF, df, FF, R, false);
-  act_bwd(c, df, FF, ws + b.f, FF, df, FF, R, FF, ACT_RELU);
+  lin_bwd(c, df2, E, ws + b.f, FF, P.linear2, E, FF, df, FF, R, false);
+  act_bwd(c, df, FF, ws + b.f, FF, df, FF, R, FF, ACT_RELU, mk_drop(c, c.drop_p, s0 + 2));
   float* dy1 = ws + w.s256b[c.sb];
   lin_bwd(c, df, FF, ws + b.y1, E, P.linear1, FF, E, dy1, E, R, false);
   add(c, dy1, dr2, dy1, (long long)R * E);
-  float* dr1 = ws + w.s256c[c.sb];     // gradient of (x + sa)
+  float* dr1 = ws + w.s256c[c.sb];     // gradient of (x + dropout1(sa))
   ln_bwd(c, dy1, P.norm1, ws + b.xh1, ws + b.rs1, dr1, R);
+  const float* dsa = dr1;
+  if (train) {
+    act_bwd(c, dr1, E, ws + b.sa, E, ws + w.dmk1[c.sb], E, R, E, ACT_NONE, mk_drop(c, c.drop_p, s0 + 1));
+    dsa = ws + w.dmk1[c.sb];
+  }
   float* dctx = ws + w.dxb[c.sb];
-  lin_bwd(c, dr1, E, ws + b.ctx, E, P.out_proj, E, E, dctx, E, R, false);
+  lin_bwd(c, dsa, E, ws + b.ctx, E, P.out_proj, E, E, dctx, E, R, false);
   float* dqkv = ws + w.s768[c.sb];
-  launch_k(mha6_bwd_kernel, dim3(nblk((long long)B * 8, 8)), dim3(256), 0, c.st, ws + b.qkv, ws + b.probs, dctx, dqkv, B); count_launch();
+  launch_k(mha6_bwd_kernel, dim3(nblk((long long)B * 8, 8)), dim3(256), 0, c.st, ws + b.qkv, ws + b.probs, dctx, dqkv, B,
+           mk_drop(c, c.drop_p, s0)); count_launch();
   c.chk(cudaGetLastError(), "mha6_bwd");
   lin_bwd(c, dqkv, 3 * E, x, E, P.in_proj, 3 * E, E, dx_out, E, R, false);
   add(c, dx_out, dr1, dx_out, (long long)R * E);
@@ -270,24 +310,27 @@ void enc_bwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, const Ws& w, f
 
 // ---------------------------------------------------------------------------------------------- pooling + rho
 // reference: models/blocks.py:42-48, models/mcat/mcat.py:105-109
-void pool_fwd(Ctx& c, const mpo_pool_head& P, const PoolBuf& b, float* ws, const float* x, float* att_logits, int B) {
+void pool_fwd(Ctx& c, const mpo_pool_head& P, const PoolBuf& b, float* ws, const float* x, float* att_logits, int B,
+              int pidx) {
   const int R = 6 * B;
-  lin_fwd(c, x, E, P.att_a, E, E, ws + b.a, E, R, ACT_TANH);
-  lin_fwd(c, x, E, P.att_b, E, E, ws + b.b, E, R, ACT_SIGMOID);
+  // AttentionNetGated hard-codes p = 0.25 for its two dropout layers (blocks.py:34-36); rho uses the model's dropout
+  lin_fwd(c, x, E, P.att_a, E, E, ws + b.a, E, R, ACT_TANH, mk_drop(c, 0.25f, SITE_POOL + 2 * pidx));
+  lin_fwd(c, x, E, P.att_b, E, E, ws + b.b, E, R, ACT_SIGMOID, mk_drop(c, 0.25f, SITE_POOL + 2 * pidx + 1));
   launch_k(pool_fwd_kernel, dim3(B), dim3(256), 0, c.st, x, ws + b.a, ws + b.b, P.att_c.w, P.att_c.b, att_logits, ws + b.w, ws + b.hp); count_launch();
   c.chk(cudaGetLastError(), "pool_fwd");
-  lin_fwd(c, ws + b.hp, E, P.rho, E, E, ws + b.h, E, B, ACT_RELU);
+  lin_fwd(c, ws + b.hp, E, P.rho, E, E, ws + b.h, E, B, ACT_RELU, mk_drop(c, c.drop_p, SITE_RHO + pidx));
 }
 // dh [B,256] (gradient of rho's output) -> dx_out [R,256]
 void pool_bwd(Ctx& c, const mpo_pool_head& P, const PoolBuf& b, const Ws& w, float* ws, const float* x, const float* dh,
-              float* dhp, float* dx_out, int B) {
+              float* dhp, float* dx_out, int B, int pidx) {
   const int R = 6 * B;
   join_w(c);
   float* dzr = ws + w.dzr[c.sb];
-  act_bwd(c, dh, E, ws + b.h, E, dzr, E, B, E, ACT_RELU);
+  act_bwd(c, dh, E, ws + b.h, E, dzr, E, B, E, ACT_RELU, mk_drop(c, c.drop_p, SITE_RHO + pidx));
   lin_bwd(c, dzr, E, ws + b.hp, E, P.rho, E, E, dhp, E, B, false);
   launch_k(pool_bwd_kernel, dim3(B), dim3(256), 0, c.st, x, ws + b.a, ws + b.b, P.att_c.w, ws + b.w, dhp, dx_out, ws + w.dxa[c.sb],
-                                       ws + w.dxb[c.sb], P.att_c.gw, P.att_c.gb); count_launch();
+           ws + w.dxb[c.sb], P.att_c.gw, P.att_c.gb, mk_drop(c, 0.25f, SITE_POOL + 2 * pidx),
+           mk_drop(c, 0.25f, SITE_POOL + 2 * pidx + 1)); count_launch();
   c.chk(cudaGetLastError(), "pool_bwd");
   lin_bwd(c, ws + w.dxa[c.sb], E, x, E, P.att_a, E, E, dx_out, E, R, true);
   lin_bwd(c, ws + w.dxb[c.sb], E, x, E, P.att_b, E, E, dx_out, E, R, true);
@@ -343,13 +386,13 @@ void bil_side_fwd(Ctx& c, const mpo_lin& Lh, const mpo_lin& Lz, const mpo_lin& L
   c.chk(launch_gemm(g, c.st), "bil.U");
   launch_k(bil_gate_fwd_kernel, dim3(B), dim3(256), 0, c.st, xa, ws + w.bU[s], Lz.b, ws + w.bh[s], ws + w.bg[s], ws + w.bgh[s]); count_launch();
   c.chk(cudaGetLastError(), "bil_gate_fwd");
-  lin_fwd(c, ws + w.bgh[s], BH, Lo, BH, BH, ws + w.bo[s], BH, B, ACT_RELU);
+  lin_fwd(c, ws + w.bgh[s], BH, Lo, BH, BH, ws + w.bo[s], BH, B, ACT_RELU, mk_drop(c, 0.25f, SITE_BIL + s));   // fusion.py:58,62
 }
 // do (gradient of o_s) in w.bdo[s] -> dxa (=|+=), dxb (+=)
 void bil_side_bwd(Ctx& c, const mpo_lin& Lh, const mpo_lin& Lz, const mpo_lin& Lo, const Ws& w, float* ws, int s,
                   const float* xa, const float* xb, float* dxa, bool acc_a, float* dxb, int B) {
   float* dpre = ws + w.bdo[s];
-  act_bwd(c, dpre, BH, ws + w.bo[s], BH, dpre, BH, B, BH, ACT_RELU);
+  act_bwd(c, dpre, BH, ws + w.bo[s], BH, dpre, BH, B, BH, ACT_RELU, mk_drop(c, 0.25f, SITE_BIL + s));
   lin_bwd(c, dpre, BH, ws + w.bgh[s], BH, Lo, BH, BH, ws + w.bdgh[s], BH, B, false);
   launch_k(bil_gate_bwd_kernel, dim3(B), dim3(256), 0, c.st, xa, ws + w.bU[s], ws + w.bh[s], ws + w.bg[s], ws + w.bdgh[s], ws + w.bdh[s],
                                            ws + w.bdz[s], ws + w.bV, dxa, acc_a ? 1 : 0); count_launch();
@@ -370,7 +413,7 @@ struct Branches {
   Ctx main, second;
   bool par;
 };
-Branches make_branches(cudaStream_t stream, bool async_wgrad) {
+Branches make_branches(cudaStream_t stream, bool async_wgrad, const mpo_tail_io* io = nullptr) {
   StreamPool& p = stream_pool();
   Branches b;
   b.par = p.state == 1;
@@ -384,6 +427,11 @@ Branches make_branches(cudaStream_t stream, bool async_wgrad) {
     b.main.async_w = b.second.async_w = async_wgrad;
   } else {
     b.second.st = stream;     // everything in program order on the caller's stream
+  }
+  if (io != nullptr && io->drop_p > 0.f) {
+    b.main.drop_p = b.second.drop_p = io->drop_p;
+    b.main.seed = b.second.seed = io->seed;
+    b.main.seed_dev = b.second.seed_dev = io->seed_dev;
   }
   return b;
 }
@@ -547,7 +595,7 @@ int mpo_tail_pre_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   const int B = io->num_slides, R = 6 * B;
   Ws w; build_layout(m, B, w);
   float* ws = io->ws;
-  Branches br = make_branches(static_cast<cudaStream_t>(stream), false);
+  Branches br = make_branches(static_cast<cudaStream_t>(stream), false, io);
   Ctx& c = br.main;
   // SNN encoders (mcat.py:32-45,90-92): G_bag row (b, i) = ELU(W2 ELU(W1 x_i + b1) + b2); six independent chains,
   // alternated over the two branch streams
@@ -557,8 +605,10 @@ int mpo_tail_pre_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   for (int i = 0; i < MPO_Q; ++i) {
     Ctx& ci = (i & 1) ? br.second : br.main;
     const int d = m->omic_dims[i];
-    lin_fwd(ci, io->omics[i], d, m->snn[i][0], E, d, ws + w.snn_h[i], E, B, ACT_ELU);
-    lin_fwd(ci, ws + w.snn_h[i], E, m->snn[i][1], E, E, ws + w.G + i * E, 6 * E, B, ACT_ELU);
+    // Linear + ELU + AlphaDropout, twice (mcat.py:34-44)
+    lin_fwd(ci, io->omics[i], d, m->snn[i][0], E, d, ws + w.snn_h[i], E, B, ACT_ELU, mk_drop(ci, ci.drop_p, SITE_SNN + 2 * i, true));
+    lin_fwd(ci, ws + w.snn_h[i], E, m->snn[i][1], E, E, ws + w.G + i * E, 6 * E, B, ACT_ELU,
+            mk_drop(ci, ci.drop_p, SITE_SNN + 2 * i + 1, true));
   }
   join(br);
   // query in-projection (rows 0..255 of co_attention.in_proj): q = W_q g + b_q
@@ -587,15 +637,15 @@ int mpo_tail_post_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   const int B = io->num_slides, R = 6 * B, K = m->n_classes;
   Ws w; build_layout(m, B, w);
   float* ws = io->ws;
-  Branches br = make_branches(static_cast<cudaStream_t>(stream), false);
+  Branches br = make_branches(static_cast<cudaStream_t>(stream), false, io);
   Ctx& c = br.main;
   Ctx& co = br.second;
   if (m->variant == MPO_VARIANT_NACAGAT && !io->qp) return fail(MPO_E_ARG, "%s", "mpo_tail_post_fwd: qp is NULL (NaCAGaT)");
   fork(br);
   // omic branch (second stream): omic transformer + pooling (mcat.py:102,111-115) -- independent of the bag
-  enc_fwd(co, m->omic_tr[0], w.enc[2], ws, ws + w.G, B);
-  enc_fwd(co, m->omic_tr[1], w.enc[3], ws, ws + w.enc[2].y2, B);
-  pool_fwd(co, m->omic_pool, w.pool[1], ws, ws + w.enc[3].y2, io->att_omic, B);
+  enc_fwd(co, m->omic_tr[0], w.enc[2], ws, ws + w.G, B, 2);
+  enc_fwd(co, m->omic_tr[1], w.enc[3], ws, ws + w.enc[2].y2, B, 3);
+  pool_fwd(co, m->omic_pool, w.pool[1], ws, ws + w.enc[3].y2, io->att_omic, B, 1);
   // path branch: value and output projections on the pooled vectors (folded form of mcat.py:97)
   if (io->suma == nullptr) {
     lin_fwd(c, io->pooled, E, sub(m->coattn_in, 2 * E, E), E, E, ws + w.v, E, R, ACT_NONE);
@@ -614,9 +664,9 @@ int mpo_tail_post_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
     add(c, ws + w.hc, ws + w.cag_C, ws + w.hc, (long long)R * E);        // blocks.py:111
   }
   // path transformer + pooling (mcat.py:101,105-109)
-  enc_fwd(c, m->path_tr[0], w.enc[0], ws, ws + w.hc, B);
-  enc_fwd(c, m->path_tr[1], w.enc[1], ws, ws + w.enc[0].y2, B);
-  pool_fwd(c, m->path_pool, w.pool[0], ws, ws + w.enc[1].y2, io->att_path, B);
+  enc_fwd(c, m->path_tr[0], w.enc[0], ws, ws + w.hc, B, 0);
+  enc_fwd(c, m->path_tr[1], w.enc[1], ws, ws + w.enc[0].y2, B, 1);
+  pool_fwd(c, m->path_pool, w.pool[0], ws, ws + w.enc[1].y2, io->att_path, B, 0);
   join(br);
   const float* hpath = ws + w.pool[0].h;
   const float* homic = ws + w.pool[1].h;
@@ -630,10 +680,11 @@ int mpo_tail_post_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   } else {                                          // fusion.py:81-113
     bil_side_fwd(c, m->bil.h1, m->bil.z1, m->bil.o1, w, ws, 0, hpath, homic, B);
     bil_side_fwd(c, m->bil.h2, m->bil.z2, m->bil.o2, w, ws, 1, homic, hpath, B);
-    launch_k(bil_kron_fwd_kernel, dim3(B), dim3(256), 0, c.st, ws + w.bo[0], ws + w.bo[1], ws + w.kp, ws + w.cat130); count_launch();
+    launch_k(bil_kron_fwd_kernel, dim3(B), dim3(256), 0, c.st, ws + w.bo[0], ws + w.bo[1], ws + w.kp, ws + w.cat130,
+             mk_drop(c, 0.25f, SITE_BIL + 2)); count_launch();    // post_fusion_dropout, fusion.py:64,107
     c.chk(cudaGetLastError(), "bil_kron_fwd");
-    lin_fwd(c, ws + w.kp, 1089, m->bil.fc1, BMM, 1089, ws + w.cat130, 130, B, ACT_RELU);
-    lin_fwd(c, ws + w.cat130, 130, m->bil.fc2, E, 130, ws + w.bf2, E, B, ACT_RELU);
+    lin_fwd(c, ws + w.kp, 1089, m->bil.fc1, BMM, 1089, ws + w.cat130, 130, B, ACT_RELU, mk_drop(c, 0.25f, SITE_BIL + 3));
+    lin_fwd(c, ws + w.cat130, 130, m->bil.fc2, E, 130, ws + w.bf2, E, B, ACT_RELU, mk_drop(c, 0.25f, SITE_BIL + 4));
     hfin = ws + w.bf2;
   }
   lin_fwd(c, hfin, E, m->classifier, K, E, ws + w.logits, K, B, ACT_NONE);
@@ -664,7 +715,7 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
   const int B = io->num_slides, R = 6 * B, K = m->n_classes;
   Ws w; build_layout(m, B, w);
   float* ws = io->ws;
-  Branches br = make_branches(static_cast<cudaStream_t>(stream), true);
+  Branches br = make_branches(static_cast<cudaStream_t>(stream), true, io);
   Ctx c = br.main;            // fusion / head part: synchronous weight gradients on the caller's stream
   c.async_w = false;
   launch_k(surv_head_bwd_kernel, dim3(nblk(B, 128)), dim3(128), 0, c.st, io->hazards, io->S, io->Y, dhaz, dS, dY, ws + w.dlogits, B, K); count_launch();
@@ -684,13 +735,13 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
     cudaMemcpy2DAsync(dhomic, E * 4, dcat + E, 2 * E * 4, E * 4, B, cudaMemcpyDeviceToDevice, c.st);
   } else {
     lin_bwd(c, ws + w.dlogits, K, ws + w.bf2, E, m->classifier, K, E, ws + w.dh, E, B, false);
-    act_bwd(c, ws + w.dh, E, ws + w.bf2, E, ws + w.dz2, E, B, E, ACT_RELU);
+    act_bwd(c, ws + w.dh, E, ws + w.bf2, E, ws + w.dz2, E, B, E, ACT_RELU, mk_drop(c, 0.25f, SITE_BIL + 4));
     lin_bwd(c, ws + w.dz2, E, ws + w.cat130, 130, m->bil.fc2, E, 130, ws + w.bdcat130, 130, B, false);
     // fc1 (its output sits in cat130[:, :64])
-    act_bwd(c, ws + w.bdcat130, 130, ws + w.cat130, 130, ws + w.dz1, BMM, B, BMM, ACT_RELU);
+    act_bwd(c, ws + w.bdcat130, 130, ws + w.cat130, 130, ws + w.dz1, BMM, B, BMM, ACT_RELU, mk_drop(c, 0.25f, SITE_BIL + 3));
     lin_bwd(c, ws + w.dz1, BMM, ws + w.kp, 1089, m->bil.fc1, BMM, 1089, ws + w.bdkp, 1089, B, false);
     launch_k(bil_kron_bwd_kernel, dim3(B), dim3(64), 0, c.st, ws + w.bo[0], ws + w.bo[1], ws + w.bdkp, ws + w.bdcat130, ws + w.bdo[0],
-                                            ws + w.bdo[1]); count_launch();
+                                            ws + w.bdo[1], mk_drop(c, 0.25f, SITE_BIL + 2)); count_launch();
     c.chk(cudaGetLastError(), "bil_kron_bwd");
     // side 1: xa = h_path, xb = h_omic ; side 2: xa = h_omic, xb = h_path
     cudaMemsetAsync(dhomic, 0, (size_t)B * E * 4, c.st);
@@ -702,13 +753,13 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
   fork(br);
   Ctx& cp = br.main;
   Ctx& co = br.second;
-  pool_bwd(co, m->omic_pool, w.pool[1], w, ws, ws + w.enc[3].y2, dhomic, ws + w.dhp[1], ws + w.dtok[1], B);
-  enc_bwd(co, m->omic_tr[1], w.enc[3], w, ws, ws + w.enc[2].y2, ws + w.dtok[1], ws + w.dmid[1], B);
-  enc_bwd(co, m->omic_tr[0], w.enc[2], w, ws, ws + w.G, ws + w.dmid[1], ws + w.dG, B);
+  pool_bwd(co, m->omic_pool, w.pool[1], w, ws, ws + w.enc[3].y2, dhomic, ws + w.dhp[1], ws + w.dtok[1], B, 1);
+  enc_bwd(co, m->omic_tr[1], w.enc[3], w, ws, ws + w.enc[2].y2, ws + w.dtok[1], ws + w.dmid[1], B, 3);
+  enc_bwd(co, m->omic_tr[0], w.enc[2], w, ws, ws + w.G, ws + w.dmid[1], ws + w.dG, B, 2);
   float* dhc = ws + w.dhc;
-  pool_bwd(cp, m->path_pool, w.pool[0], w, ws, ws + w.enc[1].y2, dhpath, ws + w.dhp[0], ws + w.dtok[0], B);
-  enc_bwd(cp, m->path_tr[1], w.enc[1], w, ws, ws + w.enc[0].y2, ws + w.dtok[0], ws + w.dmid[0], B);
-  enc_bwd(cp, m->path_tr[0], w.enc[0], w, ws, ws + w.hc, ws + w.dmid[0], dhc, B);
+  pool_bwd(cp, m->path_pool, w.pool[0], w, ws, ws + w.enc[1].y2, dhpath, ws + w.dhp[0], ws + w.dtok[0], B, 0);
+  enc_bwd(cp, m->path_tr[1], w.enc[1], w, ws, ws + w.enc[0].y2, ws + w.dtok[0], ws + w.dmid[0], B, 1);
+  enc_bwd(cp, m->path_tr[0], w.enc[0], w, ws, ws + w.hc, ws + w.dmid[0], dhc, B, 0);
   // output and value projections back to the pooled vectors
   join_w(cp);
   lin_bwd(cp, dhc, E, ws + w.v, E, m->coattn_out, E, E, ws + w.dv, E, R, false);
@@ -744,7 +795,7 @@ int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   const int B = io->num_slides, R = 6 * B;
   Ws w; build_layout(m, B, w);
   float* ws = io->ws;
-  Branches br = make_branches(static_cast<cudaStream_t>(stream), true);
+  Branches br = make_branches(static_cast<cudaStream_t>(stream), true, io);
   Ctx c = br.main;             // query / fold part: synchronous weight gradients
   c.async_w = false;
   const bool nac = m->variant == MPO_VARIANT_NACAGAT;
@@ -786,9 +837,10 @@ int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
     float* dz2 = ws + w.snn_dz2[i];   // [B,256] each, private to the chain
     float* dz1 = ws + w.snn_dz1[i];
     float* dh = ws + w.snn_dh[i];
-    act_bwd(ci, ws + w.dG + i * E, 6 * E, ws + w.G + i * E, 6 * E, dz2, E, B, E, ACT_ELU);
+    act_bwd(ci, ws + w.dG + i * E, 6 * E, ws + w.G + i * E, 6 * E, dz2, E, B, E, ACT_ELU,
+            mk_drop(ci, ci.drop_p, SITE_SNN + 2 * i + 1, true));
     lin_bwd(ci, dz2, E, ws + w.snn_h[i], E, m->snn[i][1], E, E, dh, E, B, false);
-    act_bwd(ci, dh, E, ws + w.snn_h[i], E, dz1, E, B, E, ACT_ELU);
+    act_bwd(ci, dh, E, ws + w.snn_h[i], E, dz1, E, B, E, ACT_ELU, mk_drop(ci, ci.drop_p, SITE_SNN + 2 * i, true));
     lin_bwd(ci, dz1, E, io->omics[i], d, m->snn[i][0], E, d, nullptr, 0, B, false);
   }
   join(br);

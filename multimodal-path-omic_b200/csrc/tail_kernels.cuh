@@ -23,6 +23,42 @@ __device__ __forceinline__ float act_fwd(float x, int act) {
     default: return x;
   }
 }
+// ------------------------------------------------------------------------------------------------
+// Train-mode dropout sites of the tail (SNN AlphaDropout mcat.py:38,42; encoder layers mcat.py:51-53; pooling heads
+// blocks.py:34-36; rho mcat.py:57; bilinear fusion fusion.py:58-76).  Masks come from the stateless hash RNG keyed by
+// (seed, site, element index): the backward pass regenerates them instead of storing them.
+// ------------------------------------------------------------------------------------------------
+struct DropSpec {
+  uint32_t thr;               // drop when 8 random bits < thr ; 0 = no dropout at this site
+  float scale;                // regular: 1/(1-p).  alpha: a
+  float shift;                // alpha: b (regular: 0)
+  uint32_t site;
+  uint32_t seed;
+  const uint32_t* seed_dev;   // optional device-side seed word (CUDA-graph replays)
+  int alpha;                  // 1: nn.AlphaDropout
+};
+constexpr float kAlphaPrime = -1.7580993408473766f;      // -selu_lambda * selu_alpha
+__device__ __forceinline__ uint32_t drop_seed(const DropSpec& d) {
+  return d.seed_dev != nullptr ? (d.seed ^ __ldg(d.seed_dev)) : d.seed;
+}
+__device__ __forceinline__ bool drop_keep(const DropSpec& d, uint32_t seedv, uint32_t idx) {
+  return (rng_u32(seedv, d.site, idx) & 0xFFu) >= d.thr;
+}
+// forward: value after the dropout layer
+__device__ __forceinline__ float drop_fwd(float v, const DropSpec& d, uint32_t seedv, uint32_t idx) {
+  const bool keep = drop_keep(d, seedv, idx);
+  if (d.alpha) return (keep ? v : kAlphaPrime) * d.scale + d.shift;
+  return keep ? v * d.scale : 0.f;
+}
+// backward: d(out)/d(in) of the dropout layer at this element
+__device__ __forceinline__ float drop_grad(const DropSpec& d, uint32_t seedv, uint32_t idx) {
+  return drop_keep(d, seedv, idx) ? d.scale : 0.f;
+}
+// value BEFORE the dropout layer, recovered from the stored (post-dropout) output of a kept element
+__device__ __forceinline__ float drop_invert(float y, const DropSpec& d) {
+  return d.alpha ? (y - d.shift) / d.scale : y / d.scale;
+}
+
 // derivative expressed through the activation OUTPUT y
 __device__ __forceinline__ float act_bwd_from_out(float y, int act) {
   switch (act) {
@@ -98,6 +134,7 @@ struct GemmArgs {
   int act;
   float* rowsum;      // optional: rowsum[m] += alpha * sum_k A(m,k)   (fused bias gradient)
   int b_static;       // 1: B is a parameter (never written inside the pass): its loads may run ahead of the PDL wait
+  DropSpec drop;      // dropout on the output, after the activation (element index m * N + n)
 };
 
 // The tail is a long chain of small dependent GEMMs, so the kernel is built for latency: 32-deep K steps,
@@ -198,6 +235,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
       float v = g.alpha * acc[i][j];
       if (g.bias != nullptr) v += g.bias[n];
       v = act_fwd(v, g.act);
+      if (g.drop.thr != 0) v = drop_fwd(v, g.drop, drop_seed(g.drop), static_cast<uint32_t>(m) * static_cast<uint32_t>(g.N) + n);
       float* c = g.C + m * g.ldc + n;
       *c = g.accumulate ? (*c + v) : v;
     }
@@ -292,6 +330,7 @@ __global__ void __launch_bounds__(256) gemm_fullk_kernel(const GemmArgs g) {
       float v = g.alpha * acc[i][j];
       if (g.bias != nullptr) v += g.bias[n];
       v = act_fwd(v, g.act);
+      if (g.drop.thr != 0) v = drop_fwd(v, g.drop, drop_seed(g.drop), static_cast<uint32_t>(m) * static_cast<uint32_t>(g.N) + n);
       float* c = g.C + m * g.ldc + n;
       *c = g.accumulate ? (*c + v) : v;
     }
@@ -340,12 +379,19 @@ inline cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // dz[r][c] = dy[r][c] * act'(y[r][c])     (row strides allow views into wider buffers)
 __global__ void act_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ y,
-                               long long ldy, float* __restrict__ dz, long long lddz, int rows, int cols, int act) {
+                               long long ldy, float* __restrict__ dz, long long lddz, int rows, int cols, int act,
+                               const DropSpec drop) {
   pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(rows) * cols) return;
   const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
-  dz[r * lddz + c] = dy[r * lddy + c] * act_bwd_from_out(y[r * ldy + c], act);
+  float yv = y[r * ldy + c];
+  float g = dy[r * lddy + c];
+  if (drop.thr != 0) {     // y is stored after the dropout layer: undo it for the activation derivative
+    g *= drop_grad(drop, drop_seed(drop), static_cast<uint32_t>(i));
+    yv = drop_invert(yv, drop);
+  }
+  dz[r * lddz + c] = g * act_bwd_from_out(yv, act);
 }
 
 // out[r][c] = a[r][c] + b[r][c]
@@ -476,7 +522,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ gam
 // one warp per (slide, head); lane = head-dim index.  qkv rows: [q(256) | k(256) | v(256)]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-mha6_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ probs, float* __restrict__ ctx, int B) {
+mha6_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ probs, float* __restrict__ ctx, int B,
+                const DropSpec drop) {
   pdl_enter();
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -510,8 +557,10 @@ mha6_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ probs, float*
 #pragma unroll
     for (int l2 = 0; l2 < 6; ++l2) {
       s[l2] *= inv;
-      c = fmaf(s[l2], v[l2], c);
-      if (lane == 0) probs[(static_cast<size_t>(w) * 6 + l1) * 6 + l2] = s[l2];
+      const uint32_t pi = (static_cast<uint32_t>(w) * 6 + l1) * 6 + l2;
+      if (lane == 0) probs[pi] = s[l2];                        // kept before dropout (softmax backward needs it)
+      const float sd = drop.thr != 0 ? drop_fwd(s[l2], drop, drop_seed(drop), pi) : s[l2];
+      c = fmaf(sd, v[l2], c);
     }
     ctx[static_cast<size_t>(b * 6 + l1) * 256 + h * 32 + lane] = c;
   }
@@ -519,7 +568,7 @@ mha6_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ probs, float*
 
 __global__ void __launch_bounds__(256)
 mha6_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs, const float* __restrict__ dctx,
-                float* __restrict__ dqkv, int B) {
+                float* __restrict__ dqkv, int B, const DropSpec drop) {
   pdl_enter();
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -542,13 +591,15 @@ mha6_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs, 
     float dot = 0.f;
 #pragma unroll
     for (int l2 = 0; l2 < 6; ++l2) {
-      a[l2] = probs[(static_cast<size_t>(w) * 6 + l1) * 6 + l2];
+      const uint32_t pi = (static_cast<uint32_t>(w) * 6 + l1) * 6 + l2;
+      a[l2] = probs[pi];
+      const float mg = drop.thr != 0 ? drop_grad(drop, drop_seed(drop), pi) : 1.f;   // d(dropped prob)/d(prob)
       float d = dc[l1] * v[l2];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-      da[l2] = d;
-      dot = fmaf(d, a[l2], dot);
-      dv[l2] = fmaf(a[l2], dc[l1], dv[l2]);
+      da[l2] = d * mg;
+      dot = fmaf(da[l2], a[l2], dot);
+      dv[l2] = fmaf(a[l2] * mg, dc[l1], dv[l2]);
     }
 #pragma unroll
     for (int l2 = 0; l2 < 6; ++l2) {
@@ -616,7 +667,7 @@ __global__ void __launch_bounds__(256)
 pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ bgate,
                 const float* __restrict__ wc, const float* __restrict__ w, const float* __restrict__ dhp,
                 float* __restrict__ dx, float* __restrict__ da_pre, float* __restrict__ db_pre,
-                float* __restrict__ gwc, float* __restrict__ gbc) {
+                float* __restrict__ gwc, float* __restrict__ gbc, const DropSpec drop_a, const DropSpec drop_b) {
   pdl_enter();
   __shared__ float sh[8];
   const int b = blockIdx.x, d = threadIdx.x;
@@ -634,11 +685,14 @@ pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a, const 
   for (int l = 0; l < 6; ++l) {
     const size_t o = static_cast<size_t>(b * 6 + l) * 256 + d;
     const float dA = wl[l] * (dw[l] - dot);
-    const float av = a[o], bv = bgate[o];
+    const float av = a[o], bv = bgate[o];       // as stored: after their dropout layers in train mode
     const float dab = dA * wc[d];
     dx[o] = wl[l] * g;
-    da_pre[o] = dab * bv * (1.f - av * av);
-    db_pre[o] = dab * av * bv * (1.f - bv);
+    float ga = 1.f, gbm = 1.f, a0 = av, b0 = bv;  // dropout derivatives and the pre-dropout activations
+    if (drop_a.thr != 0) { ga = drop_grad(drop_a, drop_seed(drop_a), static_cast<uint32_t>(o)); a0 = drop_invert(av, drop_a); }
+    if (drop_b.thr != 0) { gbm = drop_grad(drop_b, drop_seed(drop_b), static_cast<uint32_t>(o)); b0 = drop_invert(bv, drop_b); }
+    da_pre[o] = dab * bv * ga * (1.f - a0 * a0);
+    db_pre[o] = dab * av * gbm * b0 * (1.f - b0);
     gw = fmaf(dA, av * bv, gw);
     gb += dA;
   }
@@ -775,14 +829,16 @@ bil_gate_bwd_kernel(const float* __restrict__ x1, const float* __restrict__ U, c
 }
 // kp[b][i*33+j] = o1e[i]*o2e[j] with o?e = [o?, 1];  cat tail = [o1e, o2e] written at cat[b][64..130)
 __global__ void bil_kron_fwd_kernel(const float* __restrict__ o1, const float* __restrict__ o2,
-                                    float* __restrict__ kp, float* __restrict__ cat) {
+                                    float* __restrict__ kp, float* __restrict__ cat, const DropSpec drop) {
   pdl_enter();
   const int b = blockIdx.x;
   for (int e = threadIdx.x; e < 33 * 33; e += blockDim.x) {
     const int i = e / 33, j = e % 33;
     const float a = i < 32 ? o1[b * 32 + i] : 1.f;
     const float c = j < 32 ? o2[b * 32 + j] : 1.f;
-    kp[static_cast<size_t>(b) * 1089 + e] = a * c;
+    float v = a * c;
+    if (drop.thr != 0) v = drop_fwd(v, drop, drop_seed(drop), static_cast<uint32_t>(b) * 1089u + e);   // post_fusion_dropout
+    kp[static_cast<size_t>(b) * 1089 + e] = v;
   }
   for (int e = threadIdx.x; e < 66; e += blockDim.x) {
     const int i = e % 33;
@@ -793,17 +849,22 @@ __global__ void bil_kron_fwd_kernel(const float* __restrict__ o1, const float* _
 // do1[b][i] = dcat[b][64+i] + sum_j dkp[b][i*33+j] o2e[j];  do2[b][j] = dcat[b][97+j] + sum_i dkp[b][i*33+j] o1e[i]
 __global__ void bil_kron_bwd_kernel(const float* __restrict__ o1, const float* __restrict__ o2,
                                     const float* __restrict__ dkp, const float* __restrict__ dcat,
-                                    float* __restrict__ do1, float* __restrict__ do2) {
+                                    float* __restrict__ do1, float* __restrict__ do2, const DropSpec drop) {
   pdl_enter();
   const int b = blockIdx.x, t = threadIdx.x;   // 64 threads
+  const uint32_t sd = drop.thr != 0 ? drop_seed(drop) : 0u;
+  auto dk = [&](int e) {
+    const float g = dkp[static_cast<size_t>(b) * 1089 + e];
+    return drop.thr != 0 ? g * drop_grad(drop, sd, static_cast<uint32_t>(b) * 1089u + e) : g;
+  };
   if (t < 32) {
     float s = dcat[static_cast<size_t>(b) * 130 + 64 + t];
-    for (int j = 0; j < 33; ++j) s = fmaf(dkp[static_cast<size_t>(b) * 1089 + t * 33 + j], j < 32 ? o2[b * 32 + j] : 1.f, s);
+    for (int j = 0; j < 33; ++j) s = fmaf(dk(t * 33 + j), j < 32 ? o2[b * 32 + j] : 1.f, s);
     do1[b * 32 + t] = s;
   } else if (t < 64) {
     const int j = t - 32;
     float s = dcat[static_cast<size_t>(b) * 130 + 97 + j];
-    for (int i = 0; i < 33; ++i) s = fmaf(dkp[static_cast<size_t>(b) * 1089 + i * 33 + j], i < 32 ? o1[b * 32 + i] : 1.f, s);
+    for (int i = 0; i < 33; ++i) s = fmaf(dk(i * 33 + j), i < 32 ? o1[b * 32 + i] : 1.f, s);
     do2[b * 32 + j] = s;
   }
 }

@@ -151,6 +151,7 @@ class SlideEngine:
         self.binding = binding
         self.bag_dropout = float(bag_dropout)
         self.attn_dropout = float(attn_dropout)     # NaCAGaT: PreGatingContextualAttention(dropout_p=0.25), blocks.py:52
+        self.tail_dropout = float(bag_dropout)      # the model's `dropout`: SNN / encoder / rho layers (mcat.py:13,38-66)
         self._ws_cache = {}
         self._w_bf16 = None
         self._wk_f16 = None
@@ -200,6 +201,10 @@ class SlideEngine:
         io.Y = st.Y.data_ptr()
         io.att_path = st.att_path.data_ptr()
         io.att_omic = st.att_omic.data_ptr()
+        # train mode: the tail's dropout layers draw from the same (seed, device seed word) as the bag stage
+        io.drop_p = self.tail_dropout if getattr(st, "train", False) else 0.0
+        io.seed = getattr(st, "seed", 0) & 0xFFFFFFFF
+        io.seed_dev = st.seed_dev.data_ptr() if (getattr(st, "train", False) and st.seed_dev is not None) else None
         return io
 
     # -- buffers

@@ -249,3 +249,67 @@ def test_ge_nacagat_matches_reference(name):
     details.sort(key=lambda d: -d[2])
     print(name, "grad worst %.2e" % worst, [(k, "%.1e" % nn_, "%.1e" % e) for k, nn_, e in details[:4]])
     assert worst < GRAD_TOL, details[:5]
+
+
+@pytest.mark.parametrize("model,fusion", [("mcat", "concat"), ("nacagat", "bilinear")])
+def test_train_mode_gradients_match_finite_differences(model, fusion):
+    """Train mode (every dropout layer of the path on, masks fixed by the seed) cannot be compared with the reference
+    bit for bit (different RNG streams); instead the analytic gradients of the CUDA path are checked against
+    central finite differences of its own loss, for parameters spread over every dropout-bearing block of the tail."""
+    synth = _pkg("synth")
+    sp = _pkg("slidepath")
+    bpm = _pkg("bagpass")
+    name = "mcat_concat_300" if model == "mcat" else "nacagat_bilinear_200"
+    case = load_case(name)
+    net = build_model(case).train()
+    lens = [300, 200]
+    slides = [synth.make_slide(400 + i, n) for i, n in enumerate(lens)]
+    pb = bpm.PackedBag.from_slides([torch.from_numpy(s[0]).cuda() for s in slides])
+    om = [torch.stack([torch.from_numpy(s[1][i]) for s in slides]).cuda() for i in range(6)]
+    labels = torch.tensor([s[2] for s in slides], dtype=torch.int64, device="cuda")
+    cens = torch.tensor([s[3] for s in slides], dtype=torch.float32, device="cuda")
+    tr = sp.BatchTrainer(net, loss="nll", grad_acc_step=1)
+    SEED = 20261018
+
+    def loss_sum():
+        tr.zero_grad()
+        loss, _, _ = tr.step(pb, om, labels, cens, train=True, seed=SEED)
+        return float(loss.double().sum().item())
+
+    base = loss_sum()
+    assert abs(loss_sum() - base) < 1e-6          # same seed, same masks
+    tr.zero_grad()
+    loss, _, _ = tr.step(pb, om, labels, cens, train=True, seed=SEED + 1)
+    assert abs(float(loss.double().sum().item()) - base) > 1e-6      # another seed, other masks
+    loss_sum()
+    grads = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    probes = ["classifier.bias", "path_rho.0.bias", "omic_rho.0.weight", "path_attention_head.attention_a.0.weight",
+              "omic_attention_head.attention_b.0.bias", "path_transformer.layers.0.linear1.bias",
+              "path_transformer.layers.1.self_attn.in_proj_weight", "omic_transformer.layers.0.norm1.weight",
+              "omic_transformer.layers.1.linear2.weight", "path_transformer.layers.0.self_attn.out_proj.bias",
+              "G.2.0.0.weight", "G.4.1.0.bias", "co_attention.out_proj.weight"]
+    probes += ["fusion_layer.fusion_layer.0.weight"] if fusion == "concat" else \
+        ["fusion_layer.fc1.0.bias", "fusion_layer.linear_o1.0.weight", "fusion_layer.fc2.0.weight",
+         "co_attention.CAG.fc1.0.bias"]
+    P = dict(net.named_parameters())
+    rng = np.random.default_rng(3)
+    bad, checked = [], 0
+    for k in probes:
+        p = P[k]
+        g = grads[k].reshape(-1)
+        # probe the entry with the largest gradient among 64 random ones (avoids dead units)
+        cand = rng.integers(0, p.numel(), size=64)
+        j = int(cand[int(torch.argmax(g[torch.from_numpy(cand).cuda()].abs()).item())])
+        flat = p.data.reshape(-1)
+        old = float(flat[j].item())
+        eps = 2e-2             # the fp32 loss resolves ~1e-7: the step must move it by >> that
+        flat[j] = old + eps; lp = loss_sum()
+        flat[j] = old - eps; lm = loss_sum()
+        flat[j] = old
+        fd = (lp - lm) / (2 * eps)
+        an = float(g[j].item())
+        checked += 1
+        if abs(fd - an) > 8e-2 * max(abs(an), abs(fd)) + 2e-5:
+            bad.append((k, j, an, fd))
+    print(model, fusion, "checked", checked, "bad", bad)
+    assert len(bad) <= 1, bad       # one probe may straddle a ReLU kink
