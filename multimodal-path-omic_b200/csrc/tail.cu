@@ -31,7 +31,7 @@ struct Layout {
 };
 
 struct EncBuf { long long qkv, probs, ctx, sa, y1, xh1, rs1, f, f2, y2, xh2, rs2; };
-struct PoolBuf { long long a, b, w, hp, h; };
+struct PoolBuf { long long a, b, w, hp, h; long long hld; };   // h: rho output [B][hld] (a view into `cat` for concat fusion)
 
 struct Ws {
   long long snn_h[MPO_Q], G, v, hc;
@@ -74,14 +74,17 @@ void build_layout(const mpo_model* m, int B, Ws& w) {
     b.f = A("f", R * FF); b.f2 = A("f2", R * E); b.y2 = A("y2", R * E); b.xh2 = A("xh2", R * E); b.rs2 = A("rs2", R);
   }
   const char* pn[2] = {"pathpool", "omicpool"};
+  // concat fusion reads [h_path | h_omic] as one [B, 512] row block: the two rho outputs are written straight into it
+  if (m->fusion == MPO_FUSION_CONCAT) w.cat = L.add("cat", (long long)B * 2 * E);
   for (int p = 0; p < 2; ++p) {
     PoolBuf& b = w.pool[p];
     auto A = [&](const char* s, long long n) { snprintf(nm, sizeof nm, "%s_%s", pn[p], s); return L.add(nm, n); };
     b.a = A("a", R * E); b.b = A("b", R * E); b.w = A("w", (long long)B * 6); b.hp = A("hp", (long long)B * E);
-    b.h = A("h", (long long)B * E);
+    if (m->fusion == MPO_FUSION_CONCAT) { b.h = w.cat + p * E; b.hld = 2 * E; }
+    else { b.h = A("h", (long long)B * E); b.hld = E; }
   }
   if (m->fusion == MPO_FUSION_CONCAT) {
-    w.cat = L.add("cat", (long long)B * 2 * E); w.z1 = L.add("z1", (long long)B * E); w.z2 = L.add("z2", (long long)B * E);
+    w.z1 = L.add("z1", (long long)B * E); w.z2 = L.add("z2", (long long)B * E);
   } else {
     for (int s = 0; s < 2; ++s) {
       auto A = [&](const char* t, long long n) { snprintf(nm, sizeof nm, "bil%d_%s", s + 1, t); return L.add(nm, n); };
@@ -121,8 +124,9 @@ void build_layout(const mpo_model* m, int B, Ws& w) {
 // critical path of the backward pass.  Everything forks from / joins back into the caller's stream through
 // events, so the whole tail is still "stream-ordered on `stream`" for the caller and is CUDA-graph capturable.
 struct StreamPool {
-  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // 0: second branch, 1: wgrads of main, 2: wgrads of second
-  cudaEvent_t ev[64] = {};
+  cudaStream_t aux[7] = {};   // 0: second branch, 1: wgrads of main, 2: wgrads of second, 3..6: SNN chains 2..5
+  cudaEvent_t ev[128] = {};
+  int dummy_ = 0;
   int next = 0;
   int state = 0;   // 0 = not created, 1 = ready, -1 = disabled
 };
@@ -159,7 +163,7 @@ void dep(Ctx& c, cudaStream_t from, cudaStream_t to) {
   if (from == to) return;
   StreamPool& p = stream_pool();
   cudaEvent_t e = p.ev[p.next];
-  p.next = (p.next + 1) & 63;
+  p.next = (p.next + 1) & 127;
   c.chk(cudaEventRecord(e, from), "event record");
   c.chk(cudaStreamWaitEvent(to, e, 0), "stream wait");
   pdl_bar_next(to);
@@ -205,10 +209,18 @@ void lin_fwd(Ctx& c, const float* x, long long ldx, const mpo_lin& L, int out, i
   c.chk(launch_gemm(g, c.st), "lin_fwd");
 }
 // dz [rows,out] is the gradient at the pre-activation.  dx (=|+=) dz W ; gw += dz^T x ; gb += colsum(dz)
+// optional epilogues of the data gradient: + addend (residual-branch gradient), * act'(y) of the layer in front (with
+// that layer's dropout undone), so that dx leaves the kernel as the gradient at that layer's pre-activation
+struct DgradEpi {
+  const float* addend = nullptr; long long ld_add = 0;
+  const float* y = nullptr; long long ld_y = 0; int act = ACT_NONE; DropSpec drop = DropSpec{};
+};
 void lin_bwd(Ctx& c, const float* dz, long long lddz, const float* x, long long ldx, const mpo_lin& L, int out, int in,
-             float* dx, long long lddx, int rows, bool acc_dx) {
+             float* dx, long long lddx, int rows, bool acc_dx, const DgradEpi epi = DgradEpi{}) {
   if (dx != nullptr) {
     GemmArgs g{dz, lddz, 1, L.w, in, 1, dx, lddx, nullptr, rows, in, out, 1.f, acc_dx ? 1 : 0, ACT_NONE, nullptr, 1};
+    g.addend = epi.addend; g.ld_add = epi.ld_add;
+    g.bwd_y = epi.y; g.ld_bwd = epi.ld_y; g.bwd_act = epi.act; g.bwd_drop = epi.drop;
     c.chk(launch_gemm(g, c.st), "lin_bwd.dgrad");
   }
   if (L.gw != nullptr) {     // gw += dz^T x, with gb += rowsum(dz^T) fused into the same kernel
@@ -243,8 +255,9 @@ void ln_fwd(Ctx& c, const float* a, const float* b, const mpo_norm& N, float* y,
   launch_k(layernorm_fwd_kernel, dim3(nblk(rows, 8)), dim3(256), 0, c.st, a, b, N.g, N.b, y, xh, rs, rows); count_launch();
   c.chk(cudaGetLastError(), "ln_fwd");
 }
-void ln_bwd(Ctx& c, const float* dy, const mpo_norm& N, const float* xh, const float* rs, float* dx, int rows) {
-  launch_k(layernorm_bwd_kernel, dim3(nblk(rows, 8)), dim3(256), 0, c.st, dy, N.g, xh, rs, dx, rows); count_launch();
+void ln_bwd(Ctx& c, const float* dy, const mpo_norm& N, const float* xh, const float* rs, float* dx, int rows,
+            float* dx_drop = nullptr, const DropSpec drop = DropSpec{}) {
+  launch_k(layernorm_bwd_kernel, dim3(nblk(rows, 8)), dim3(256), 0, c.st, dy, N.g, xh, rs, dx, rows, dx_drop, drop); count_launch();
   c.chk(cudaGetLastError(), "ln_bwd");
   if (N.gg != nullptr) {
     cudaStream_t ws_ = c.async_w ? c.wst : c.st;
@@ -279,24 +292,28 @@ void enc_bwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, const Ws& w, f
   const bool train = c.drop_p > 0.f;
   join_w(c);
   float* dr2 = ws + w.s256a[c.sb];     // gradient of (y1 + dropout2(f2))
-  ln_bwd(c, dy2, P.norm2, ws + b.xh2, ws + b.rs2, dr2, R);
-  const float* df2 = dr2;              // gradient of f2: through dropout2 in train mode
+  const float* df2 = dr2;              // gradient of f2: through dropout2 in train mode (second output of the LN backward)
   if (train) {
-    act_bwd(c, dr2, E, ws + b.f2, E, ws + w.dmk2[c.sb], E, R, E, ACT_NONE, mk_drop(c, c.drop_p, s0 + 3));
+    ln_bwd(c, dy2, P.norm2, ws + b.xh2, ws + b.rs2, dr2, R, ws + w.dmk2[c.sb], mk_drop(c, c.drop_p, s0 + 3));
     df2 = ws + w.dmk2[c.sb];
+  } else {
+    ln_bwd(c, dy2, P.norm2, ws + b.xh2, ws + b.rs2, dr2, R);
   }
+  // linear2 data gradient with the ReLU (+ feed-forward dropout) derivative in its epilogue: df is at linear1's pre-activation
   float* df = ws + w.s512[c.sb];
-  lin_bwd(c, df2, E, ws + b.f, FF, P.linear2, E, FF, df, FF, R, false);
-  act_bwd(c, df, FF, ws + b.f, FF, df, FF, R, FF, ACT_RELU, mk_drop(c, c.drop_p, s0 + 2));
+  DgradEpi e2; e2.y = ws + b.f; e2.ld_y = FF; e2.act = ACT_RELU; e2.drop = mk_drop(c, c.drop_p, s0 + 2);
+  lin_bwd(c, df2, E, ws + b.f, FF, P.linear2, E, FF, df, FF, R, false, e2);
+  // linear1 data gradient + the residual branch: dy1 = df W1 + dr2
   float* dy1 = ws + w.s256b[c.sb];
-  lin_bwd(c, df, FF, ws + b.y1, E, P.linear1, FF, E, dy1, E, R, false);
-  add(c, dy1, dr2, dy1, (long long)R * E);
+  DgradEpi e1; e1.addend = dr2; e1.ld_add = E;
+  lin_bwd(c, df, FF, ws + b.y1, E, P.linear1, FF, E, dy1, E, R, false, e1);
   float* dr1 = ws + w.s256c[c.sb];     // gradient of (x + dropout1(sa))
-  ln_bwd(c, dy1, P.norm1, ws + b.xh1, ws + b.rs1, dr1, R);
   const float* dsa = dr1;
   if (train) {
-    act_bwd(c, dr1, E, ws + b.sa, E, ws + w.dmk1[c.sb], E, R, E, ACT_NONE, mk_drop(c, c.drop_p, s0 + 1));
+    ln_bwd(c, dy1, P.norm1, ws + b.xh1, ws + b.rs1, dr1, R, ws + w.dmk1[c.sb], mk_drop(c, c.drop_p, s0 + 1));
     dsa = ws + w.dmk1[c.sb];
+  } else {
+    ln_bwd(c, dy1, P.norm1, ws + b.xh1, ws + b.rs1, dr1, R);
   }
   float* dctx = ws + w.dxb[c.sb];
   lin_bwd(c, dsa, E, ws + b.ctx, E, P.out_proj, E, E, dctx, E, R, false);
@@ -304,8 +321,9 @@ void enc_bwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, const Ws& w, f
   launch_k(mha6_bwd_kernel, dim3(nblk((long long)B * 8, 8)), dim3(256), 0, c.st, ws + b.qkv, ws + b.probs, dctx, dqkv, B,
            mk_drop(c, c.drop_p, s0)); count_launch();
   c.chk(cudaGetLastError(), "mha6_bwd");
-  lin_bwd(c, dqkv, 3 * E, x, E, P.in_proj, 3 * E, E, dx_out, E, R, false);
-  add(c, dx_out, dr1, dx_out, (long long)R * E);
+  // in_proj data gradient + the residual branch: dx = dqkv W_in + dr1
+  DgradEpi e0; e0.addend = dr1; e0.ld_add = E;
+  lin_bwd(c, dqkv, 3 * E, x, E, P.in_proj, 3 * E, E, dx_out, E, R, false, e0);
 }
 
 // ---------------------------------------------------------------------------------------------- pooling + rho
@@ -318,15 +336,15 @@ void pool_fwd(Ctx& c, const mpo_pool_head& P, const PoolBuf& b, float* ws, const
   lin_fwd(c, x, E, P.att_b, E, E, ws + b.b, E, R, ACT_SIGMOID, mk_drop(c, 0.25f, SITE_POOL + 2 * pidx + 1));
   launch_k(pool_fwd_kernel, dim3(B), dim3(256), 0, c.st, x, ws + b.a, ws + b.b, P.att_c.w, P.att_c.b, att_logits, ws + b.w, ws + b.hp); count_launch();
   c.chk(cudaGetLastError(), "pool_fwd");
-  lin_fwd(c, ws + b.hp, E, P.rho, E, E, ws + b.h, E, B, ACT_RELU, mk_drop(c, c.drop_p, SITE_RHO + pidx));
+  lin_fwd(c, ws + b.hp, E, P.rho, E, E, ws + b.h, b.hld, B, ACT_RELU, mk_drop(c, c.drop_p, SITE_RHO + pidx));
 }
 // dh [B,256] (gradient of rho's output) -> dx_out [R,256]
 void pool_bwd(Ctx& c, const mpo_pool_head& P, const PoolBuf& b, const Ws& w, float* ws, const float* x, const float* dh,
-              float* dhp, float* dx_out, int B, int pidx) {
+              long long lddh, float* dhp, float* dx_out, int B, int pidx) {
   const int R = 6 * B;
   join_w(c);
   float* dzr = ws + w.dzr[c.sb];
-  act_bwd(c, dh, E, ws + b.h, E, dzr, E, B, E, ACT_RELU, mk_drop(c, c.drop_p, SITE_RHO + pidx));
+  act_bwd(c, dh, lddh, ws + b.h, b.hld, dzr, E, B, E, ACT_RELU, mk_drop(c, c.drop_p, SITE_RHO + pidx));
   lin_bwd(c, dzr, E, ws + b.hp, E, P.rho, E, E, dhp, E, B, false);
   launch_k(pool_bwd_kernel, dim3(B), dim3(256), 0, c.st, x, ws + b.a, ws + b.b, P.att_c.w, ws + b.w, dhp, dx_out, ws + w.dxa[c.sb],
            ws + w.dxb[c.sb], P.att_c.gw, P.att_c.gb, mk_drop(c, 0.25f, SITE_POOL + 2 * pidx),
@@ -450,6 +468,25 @@ void join(Branches& b) {
     dep(b.main, b.second.st, b.main.st);
   }
   b.main.chk(b.second.err, b.second.where);
+}
+
+// the six SNN chains on six branches: chain 0 on the caller's stream, 1 on the second-branch stream, 2..5 on their own
+void snn_branches(Branches& b, Ctx (&chain)[MPO_Q]) {
+  StreamPool& p = stream_pool();
+  for (int i = 0; i < MPO_Q; ++i) {
+    chain[i] = b.main;
+    chain[i].async_w = false;          // a chain's weight gradients stay on the chain's own stream
+    if (b.par && i > 0) {
+      chain[i].st = i == 1 ? p.aux[0] : p.aux[1 + i];
+      dep(b.main, b.main.st, chain[i].st);
+    }
+  }
+}
+void snn_join(Branches& b, Ctx (&chain)[MPO_Q]) {
+  for (int i = 0; i < MPO_Q; ++i) {
+    if (chain[i].st != b.main.st) dep(b.main, chain[i].st, b.main.st);
+    b.main.chk(chain[i].err, chain[i].where);
+  }
 }
 
 int finish(Ctx& c) {
@@ -601,16 +638,18 @@ int mpo_tail_pre_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   // alternated over the two branch streams
   for (int i = 0; i < MPO_Q; ++i)
     if (!io->omics[i]) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_fwd: omics pointer is NULL");
-  fork(br);
+  // six independent chains: one branch each (the caller's stream, the second-branch stream, four SNN streams)
+  Ctx chain[MPO_Q];
+  snn_branches(br, chain);
   for (int i = 0; i < MPO_Q; ++i) {
-    Ctx& ci = (i & 1) ? br.second : br.main;
+    Ctx& ci = chain[i];
     const int d = m->omic_dims[i];
     // Linear + ELU + AlphaDropout, twice (mcat.py:34-44)
     lin_fwd(ci, io->omics[i], d, m->snn[i][0], E, d, ws + w.snn_h[i], E, B, ACT_ELU, mk_drop(ci, ci.drop_p, SITE_SNN + 2 * i, true));
     lin_fwd(ci, ws + w.snn_h[i], E, m->snn[i][1], E, E, ws + w.G + i * E, 6 * E, B, ACT_ELU,
             mk_drop(ci, ci.drop_p, SITE_SNN + 2 * i + 1, true));
   }
-  join(br);
+  snn_join(br, chain);
   // query in-projection (rows 0..255 of co_attention.in_proj): q = W_q g + b_q
   lin_fwd(c, ws + w.G, E, sub(m->coattn_in, 0, E), E, E, io->qp, E, R, ACT_NONE);
   // key fold: qk[r][d] = sum_e q[r][e] W_k[e][d] / sqrt(256)
@@ -672,8 +711,6 @@ int mpo_tail_post_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   const float* homic = ws + w.pool[1].h;
   const float* hfin;
   if (m->fusion == MPO_FUSION_CONCAT) {            // fusion.py:17-19
-    cudaMemcpy2DAsync(ws + w.cat, 2 * E * 4, hpath, E * 4, E * 4, B, cudaMemcpyDeviceToDevice, c.st);
-    cudaMemcpy2DAsync(ws + w.cat + E, 2 * E * 4, homic, E * 4, E * 4, B, cudaMemcpyDeviceToDevice, c.st);
     lin_fwd(c, ws + w.cat, 2 * E, m->fusion0, E, 2 * E, ws + w.z1, E, B, ACT_RELU);
     lin_fwd(c, ws + w.z1, E, m->fusion2, E, E, ws + w.z2, E, B, ACT_RELU);
     hfin = ws + w.z2;
@@ -716,23 +753,24 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
   Ws w; build_layout(m, B, w);
   float* ws = io->ws;
   Branches br = make_branches(static_cast<cudaStream_t>(stream), true, io);
-  Ctx c = br.main;            // fusion / head part: synchronous weight gradients on the caller's stream
-  c.async_w = false;
+  Ctx c = br.main;            // fusion / head part: weight gradients on the side stream (joined at the end)
   launch_k(surv_head_bwd_kernel, dim3(nblk(B, 128)), dim3(128), 0, c.st, io->hazards, io->S, io->Y, dhaz, dS, dY, ws + w.dlogits, B, K); count_launch();
   c.chk(cudaGetLastError(), "surv_head_bwd");
   const float* hpath = ws + w.pool[0].h;
   const float* homic = ws + w.pool[1].h;
-  float* dhpath = ws + w.dcat;          // [B,256] views used as outputs of the fusion backward
-  float* dhomic = ws + w.dcat + (long long)B * E;
-  if (m->fusion == MPO_FUSION_CONCAT) {
-    lin_bwd(c, ws + w.dlogits, K, ws + w.z2, E, m->classifier, K, E, ws + w.dh, E, B, false);
-    act_bwd(c, ws + w.dh, E, ws + w.z2, E, ws + w.dz2, E, B, E, ACT_RELU);
-    lin_bwd(c, ws + w.dz2, E, ws + w.z1, E, m->fusion2, E, E, ws + w.dh, E, B, false);
-    act_bwd(c, ws + w.dh, E, ws + w.z1, E, ws + w.dz1, E, B, E, ACT_RELU);
-    float* dcat = ws + w.s512[0];       // [B,512] scratch
-    lin_bwd(c, ws + w.dz1, E, ws + w.cat, 2 * E, m->fusion0, E, 2 * E, dcat, 2 * E, B, false);
-    cudaMemcpy2DAsync(dhpath, E * 4, dcat, 2 * E * 4, E * 4, B, cudaMemcpyDeviceToDevice, c.st);
-    cudaMemcpy2DAsync(dhomic, E * 4, dcat + E, 2 * E * 4, E * 4, B, cudaMemcpyDeviceToDevice, c.st);
+  // gradients of the two rho outputs: [B,256] blocks of `dcat` (bilinear), or the two column halves of the [B,512]
+  // concat gradient (row stride 512)
+  const bool concat = m->fusion == MPO_FUSION_CONCAT;
+  float* dhpath = ws + w.dcat;
+  float* dhomic = concat ? ws + w.dcat + E : ws + w.dcat + (long long)B * E;
+  const long long lddh = concat ? 2 * E : E;
+  if (concat) {
+    // each data gradient carries the ReLU derivative of the layer in front in its epilogue
+    DgradEpi e2; e2.y = ws + w.z2; e2.ld_y = E; e2.act = ACT_RELU;
+    lin_bwd(c, ws + w.dlogits, K, ws + w.z2, E, m->classifier, K, E, ws + w.dz2, E, B, false, e2);
+    DgradEpi e1; e1.y = ws + w.z1; e1.ld_y = E; e1.act = ACT_RELU;
+    lin_bwd(c, ws + w.dz2, E, ws + w.z1, E, m->fusion2, E, E, ws + w.dz1, E, B, false, e1);
+    lin_bwd(c, ws + w.dz1, E, ws + w.cat, 2 * E, m->fusion0, E, 2 * E, ws + w.dcat, 2 * E, B, false);
   } else {
     lin_bwd(c, ws + w.dlogits, K, ws + w.bf2, E, m->classifier, K, E, ws + w.dh, E, B, false);
     act_bwd(c, ws + w.dh, E, ws + w.bf2, E, ws + w.dz2, E, B, E, ACT_RELU, mk_drop(c, 0.25f, SITE_BIL + 4));
@@ -753,11 +791,11 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
   fork(br);
   Ctx& cp = br.main;
   Ctx& co = br.second;
-  pool_bwd(co, m->omic_pool, w.pool[1], w, ws, ws + w.enc[3].y2, dhomic, ws + w.dhp[1], ws + w.dtok[1], B, 1);
+  pool_bwd(co, m->omic_pool, w.pool[1], w, ws, ws + w.enc[3].y2, dhomic, lddh, ws + w.dhp[1], ws + w.dtok[1], B, 1);
   enc_bwd(co, m->omic_tr[1], w.enc[3], w, ws, ws + w.enc[2].y2, ws + w.dtok[1], ws + w.dmid[1], B, 3);
   enc_bwd(co, m->omic_tr[0], w.enc[2], w, ws, ws + w.G, ws + w.dmid[1], ws + w.dG, B, 2);
   float* dhc = ws + w.dhc;
-  pool_bwd(cp, m->path_pool, w.pool[0], w, ws, ws + w.enc[1].y2, dhpath, ws + w.dhp[0], ws + w.dtok[0], B, 0);
+  pool_bwd(cp, m->path_pool, w.pool[0], w, ws, ws + w.enc[1].y2, dhpath, lddh, ws + w.dhp[0], ws + w.dtok[0], B, 0);
   enc_bwd(cp, m->path_tr[1], w.enc[1], w, ws, ws + w.enc[0].y2, ws + w.dtok[0], ws + w.dmid[0], B, 1);
   enc_bwd(cp, m->path_tr[0], w.enc[0], w, ws, ws + w.hc, ws + w.dmid[0], dhc, B, 0);
   // output and value projections back to the pooled vectors
@@ -796,8 +834,7 @@ int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   Ws w; build_layout(m, B, w);
   float* ws = io->ws;
   Branches br = make_branches(static_cast<cudaStream_t>(stream), true, io);
-  Ctx c = br.main;             // query / fold part: synchronous weight gradients
-  c.async_w = false;
+  Ctx c = br.main;             // query / fold part: weight gradients on the side stream (joined at the end)
   const bool nac = m->variant == MPO_VARIANT_NACAGAT;
   if (nac && (!io->dkc || !io->dtq)) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_bwd: dkc/dtq are NULL (NaCAGaT)");
   const float* Wk = m->coattn_in.w + (long long)E * E;
@@ -808,7 +845,8 @@ int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
     c.chk(launch_gemm(g, c.st), "fold.dq");
     if (gWk) {
       GemmArgs g2{io->qp, 1, E, io->dqk, E, 1, gWk, E, nullptr, E, E, R, 1.f / 16.f, 1, ACT_NONE, nullptr};
-      c.chk(launch_gemm(g2, c.st), "fold.dWk");
+      if (c.async_w) dep(c, c.st, c.wst);
+      c.chk(launch_gemm(g2, c.async_w ? c.wst : c.st), "fold.dWk");
     }
   }
   if (nac) {
@@ -819,7 +857,8 @@ int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
     c.chk(launch_gemm(g, c.st), "kc.dq");
     if (gbk) {
       GemmArgs g2{io->dkc, 0, 1, io->qp, E, 1, gbk, E, nullptr, 1, E, R, 1.f / 16.f, 1, ACT_NONE, nullptr};
-      c.chk(launch_gemm(g2, c.st), "kc.dbk");
+      if (c.async_w) dep(c, c.st, c.wst);
+      c.chk(launch_gemm(g2, c.async_w ? c.wst : c.st), "kc.dbk");
     }
     // tanh(q) branch of the pre-gate: dq += dtq * (1 - tanh(q)^2)
     act(c, io->qp, ws + w.s256a[0], (long long)R * E, ACT_TANH);
@@ -829,20 +868,23 @@ int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   // query in-projection
   lin_bwd(c, ws + w.dqp, E, ws + w.G, E, sub(m->coattn_in, 0, E), E, E, ws + w.dG, E, R, true);
   br.main.chk(c.err, c.where);
-  // SNN encoders: six independent chains over the two branch streams, weight gradients on the side streams
+  // SNN encoders: six independent chains on six branches
   fork(br);
+  Ctx chain[MPO_Q];
+  snn_branches(br, chain);
   for (int i = 0; i < MPO_Q; ++i) {
-    Ctx& ci = (i & 1) ? br.second : br.main;
+    Ctx& ci = chain[i];
     const int d = m->omic_dims[i];
     float* dz2 = ws + w.snn_dz2[i];   // [B,256] each, private to the chain
     float* dz1 = ws + w.snn_dz1[i];
-    float* dh = ws + w.snn_dh[i];
     act_bwd(ci, ws + w.dG + i * E, 6 * E, ws + w.G + i * E, 6 * E, dz2, E, B, E, ACT_ELU,
             mk_drop(ci, ci.drop_p, SITE_SNN + 2 * i + 1, true));
-    lin_bwd(ci, dz2, E, ws + w.snn_h[i], E, m->snn[i][1], E, E, dh, E, B, false);
-    act_bwd(ci, dh, E, ws + w.snn_h[i], E, dz1, E, B, E, ACT_ELU, mk_drop(ci, ci.drop_p, SITE_SNN + 2 * i, true));
+    // second linear's data gradient with the first layer's ELU + AlphaDropout derivative in its epilogue
+    DgradEpi e; e.y = ws + w.snn_h[i]; e.ld_y = E; e.act = ACT_ELU; e.drop = mk_drop(ci, ci.drop_p, SITE_SNN + 2 * i, true);
+    lin_bwd(ci, dz2, E, ws + w.snn_h[i], E, m->snn[i][1], E, E, dz1, E, B, false, e);
     lin_bwd(ci, dz1, E, io->omics[i], d, m->snn[i][0], E, d, nullptr, 0, B, false);
   }
+  snn_join(br, chain);
   join(br);
   return finish(br.main);
 }

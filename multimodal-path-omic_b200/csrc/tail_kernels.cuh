@@ -135,6 +135,10 @@ struct GemmArgs {
   float* rowsum;      // optional: rowsum[m] += alpha * sum_k A(m,k)   (fused bias gradient)
   int b_static;       // 1: B is a parameter (never written inside the pass): its loads may run ahead of the PDL wait
   DropSpec drop;      // dropout on the output, after the activation (element index m * N + n)
+  const float* addend; long long ld_add;    // optional: + addend[m][n] (a residual-branch gradient), before `act`
+  const float* bwd_y; long long ld_bwd;     // optional backward epilogue: * act'(y[m][n]) of activation `bwd_act`, where
+  int bwd_act;                              //   y was stored after the dropout layer `bwd_drop` (also undone here)
+  DropSpec bwd_drop;
 };
 
 // The tail is a long chain of small dependent GEMMs, so the kernel is built for latency: 32-deep K steps,
@@ -234,6 +238,15 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
       if (n >= g.N) continue;
       float v = g.alpha * acc[i][j];
       if (g.bias != nullptr) v += g.bias[n];
+      if (g.addend != nullptr) v += g.addend[m * g.ld_add + n];
+      if (g.bwd_y != nullptr) {
+        float yv = g.bwd_y[m * g.ld_bwd + n];
+        if (g.bwd_drop.thr != 0) {
+          v *= drop_grad(g.bwd_drop, drop_seed(g.bwd_drop), static_cast<uint32_t>(m) * static_cast<uint32_t>(g.N) + n);
+          yv = drop_invert(yv, g.bwd_drop);
+        }
+        v *= act_bwd_from_out(yv, g.bwd_act);
+      }
       v = act_fwd(v, g.act);
       if (g.drop.thr != 0) v = drop_fwd(v, g.drop, drop_seed(g.drop), static_cast<uint32_t>(m) * static_cast<uint32_t>(g.N) + n);
       float* c = g.C + m * g.ldc + n;
@@ -329,6 +342,15 @@ __global__ void __launch_bounds__(256) gemm_fullk_kernel(const GemmArgs g) {
       if (n >= g.N) continue;
       float v = g.alpha * acc[i][j];
       if (g.bias != nullptr) v += g.bias[n];
+      if (g.addend != nullptr) v += g.addend[m * g.ld_add + n];
+      if (g.bwd_y != nullptr) {
+        float yv = g.bwd_y[m * g.ld_bwd + n];
+        if (g.bwd_drop.thr != 0) {
+          v *= drop_grad(g.bwd_drop, drop_seed(g.bwd_drop), static_cast<uint32_t>(m) * static_cast<uint32_t>(g.N) + n);
+          yv = drop_invert(yv, g.bwd_drop);
+        }
+        v *= act_bwd_from_out(yv, g.bwd_act);
+      }
       v = act_fwd(v, g.act);
       if (g.drop.thr != 0) v = drop_fwd(v, g.drop, drop_seed(g.drop), static_cast<uint32_t>(m) * static_cast<uint32_t>(g.N) + n);
       float* c = g.C + m * g.ldc + n;
@@ -490,7 +512,8 @@ layernorm_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, c
 // dx = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)),  dxh = dy * gamma;  also writes t = dy * xhat
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ gamma, const float* __restrict__ xhat,
-                     const float* __restrict__ rstd, float* __restrict__ dx, int rows) {
+                     const float* __restrict__ rstd, float* __restrict__ dx, int rows, float* __restrict__ dx_drop,
+                     const DropSpec drop) {   // dx_drop (optional) = dx through the dropout layer in front of the residual
   pdl_enter();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -514,7 +537,12 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ gam
   s2 *= (1.f / 256.f);
   const float rs = rstd[row];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) dx[row * 256 + lane + 32 * j] = rs * (dxh[j] - s1 - xh[j] * s2);
+  for (int j = 0; j < 8; ++j) {
+    const int idx = row * 256 + lane + 32 * j;
+    const float v = rs * (dxh[j] - s1 - xh[j] * s2);
+    dx[idx] = v;
+    if (dx_drop != nullptr) dx_drop[idx] = v * drop_grad(drop, drop_seed(drop), static_cast<uint32_t>(idx));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
