@@ -278,6 +278,12 @@ int mpo_surv_loss(int32_t kind, const float* hazards, const float* S, const int6
  * io->dpooled, and the token-side gradients kept in the workspace for pre_bwd */
 int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dhaz, const float* dS, const float* dY,
                       void* stream);
+/* post_fwd + mpo_surv_loss + post_bwd as one call (the training step of models/mcat/main.py:39-70 between the bag
+ * forward and the bag backward): for MCAT with concat fusion this is ONE cluster kernel (csrc/tail_fused.cu) plus the
+ * grouped weight-gradient kernel; other configurations run the three stages back to back.  Arguments as in
+ * mpo_surv_loss; io->dpooled is written, parameter gradients are accumulated. */
+int mpo_tail_post_step(const mpo_model* m, const mpo_tail_io* io, int32_t kind, const int64_t* label, const float* censor,
+                       float alpha, float eps, float grad_scale, float* loss, float* dhaz, float* dS, void* stream);
 /* autograd of pre_fwd: consumes io->dqk and the workspace gradients, finishes co_attention.in_proj and SNN grads */
 int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream);
 

@@ -1,0 +1,1571 @@
+// Fused cluster tail: the 6-token part of MCAT (reference models/mcat/mcat.py:90-138 and its autograd) as
+//   pre_kernel      SNN encoders, query projection, key fold                       (before the bag forward)
+//   path_kernel     omic + path encoders, pooling, fusion, survival head, loss, and the whole data-gradient chain
+//                   back to d(pooled)                                                (between bag forward and backward)
+//   pre_bwd_kernel  fold / query projection / SNN data gradients                    (after the bag backward)
+//   wgrad_kernel    every weight / bias / LayerNorm gradient of the tail as one grouped launch
+// One thread-block cluster of 8 CTAs owns S slides (M = 6 S token rows).  Activations are replicated in the shared
+// memory of the 8 CTAs; every linear layer is split by output columns (32 per CTA and block), its weight slice is
+// streamed L2 -> shared memory through a 3-stage cp.async ring that runs ahead across layer boundaries, results
+// are broadcast to the peers through distributed shared memory, and the per-row work (LayerNorm, the 6x6 attention
+// of one head per CTA, pooling soft-max, survival head, loss) happens in place.  Slides never mix inside these
+// kernels, so no grid-wide synchronisation is needed; only the weight gradients sum over slides, and they are
+// deferred to wgrad_kernel.  fp32 CUDA-core arithmetic throughout (the 1e-3 parity gate of SURVEY.md 8c).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "../../include/mpo_b200.h"
+#include "launchers.h"
+#include "tail_dev.cuh"
+#include "tail_fused.h"
+#include "tail_ws.h"
+
+namespace mpo {
+namespace fused {
+using tailws::Ws;
+
+constexpr int E = 256;
+constexpr int FF = 512;
+constexpr int CL = 8;              // CTAs per cluster (= heads of the encoder layers)
+constexpr int NT = 256;            // threads per CTA
+constexpr int NW = NT / 32;
+constexpr int KC = 256;            // reduction extent of one weight chunk
+constexpr int WLD = KC + 4;        // padded row pitch of a forward chunk [32][WLD]
+constexpr int CHUNK = 32 * WLD;    // floats per ring slot (a data-gradient chunk [256][32] fits as well)
+constexpr int NSTAGE = 3;
+constexpr int MAXK = 8;            // survival bins supported by the fused kernels
+constexpr int OMIC_LD = 608;       // shared-memory pitch of one omic input row (d_i <= 608)
+
+enum : int { T_FWD = 0, T_DGRAD = 1 };
+
+// One slice of a weight matrix as the 8 CTAs of a cluster consume it.  T_FWD: y = x W^T, the CTA owns rows
+// n0 .. n0+31 of W (output features); T_DGRAD: dx = dz W, the CTA owns columns n0 .. n0+31 of W (input features);
+// n0 = rank * rank_mul + n_off + blk * blk_stride.  Chunks are consumed block by block, KC reduction elements each.
+struct Slice {
+  const float* w;
+  int ld;            // row pitch of W (= in_features)
+  int K;             // reduction extent
+  short nblk, type, rank_mul, blk_stride;
+  int n_off;
+};
+constexpr int MAX_SLICES = 60;
+struct Program { Slice s[MAX_SLICES]; int n; };
+
+struct ProgBuilder {
+  Program& p;
+  bool ok = true;
+  void add(int type, const float* w, int ld, int K, int nblk, int rank_mul, int blk_stride, int n_off) {
+    if (p.n >= MAX_SLICES) { ok = false; return; }
+    Slice& s = p.s[p.n++];
+    s.w = w; s.ld = ld; s.K = K; s.nblk = (short)nblk; s.type = (short)type; s.rank_mul = (short)rank_mul;
+    s.blk_stride = (short)blk_stride; s.n_off = n_off;
+  }
+  void fwd(const float* w, int ld, int K, int nblk = 1, int rank_mul = 32, int blk_stride = 32, int n_off = 0) {
+    add(T_FWD, w, ld, K, nblk, rank_mul, blk_stride, n_off);
+  }
+  void dgrad(const float* w, int ld, int K, int nblk = 1, int rank_mul = 32, int blk_stride = 32, int n_off = 0) {
+    add(T_DGRAD, w, ld, K, nblk, rank_mul, blk_stride, n_off);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ int cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return static_cast<int>(r);
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store v at the same shared-memory offset in every CTA of the cluster
+__device__ __forceinline__ void bcast(float* local, float v) {
+  const uint32_t a = smem_addr(local);
+#pragma unroll
+  for (int rk = 0; rk < CL; ++rk) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rk));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+  }
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// cp.async ring over the chunk sequence of a Program; invariant between acquire() calls: issued == consumed + 2
+struct Pipe {
+  const Slice* sl;
+  int nsl;
+  float* ring;
+  int rank, t;
+  int e, blk, k0;
+  int cons;
+  __device__ __forceinline__ void init(const Program& p, float* ring_, int rank_, int t_) {
+    sl = p.s; nsl = p.n; ring = ring_; rank = rank_; t = t_; e = 0; blk = 0; k0 = 0; cons = 0;
+    issue(0); issue(1);
+  }
+  __device__ __forceinline__ void issue(int slot) {
+    if (e < nsl) {
+      const Slice s = sl[e];
+      const int n0 = rank * s.rank_mul + s.n_off + blk * s.blk_stride;
+      const int kc = min(KC, s.K - k0);
+      float* dst = ring + slot * CHUNK;
+      if (s.type == T_FWD) {
+        const int per_row = kc >> 2;                 // 16-byte pieces per row of the chunk
+        const float* src = s.w + static_cast<size_t>(n0) * s.ld + k0;
+        for (int p = t; p < 32 * per_row; p += NT) {
+          const int row = p / per_row, c4 = p - row * per_row;
+          cp_async16(dst + row * WLD + c4 * 4, src + static_cast<size_t>(row) * s.ld + c4 * 4);
+        }
+      } else {
+        const float* src = s.w + static_cast<size_t>(k0) * s.ld + n0;
+        for (int p = t; p < kc * 8; p += NT) {
+          const int row = p >> 3, c4 = p & 7;
+          cp_async16(dst + row * 32 + c4 * 4, src + static_cast<size_t>(row) * s.ld + c4 * 4);
+        }
+      }
+      k0 += KC;
+      if (k0 >= s.K) { k0 = 0; if (++blk == s.nblk) { blk = 0; ++e; } }
+    }
+    cp_async_commit();
+  }
+  // waits for the next chunk, refills the slot freed by the previous one, returns the chunk
+  __device__ __forceinline__ const float* acquire() {
+    cp_async_wait<NSTAGE - 2>();
+    __syncthreads();
+    issue((cons + 2) % NSTAGE);
+    const float* p = ring + (cons % NSTAGE) * CHUNK;
+    ++cons;
+    return p;
+  }
+};
+
+struct Dev {
+  int rank, t, lane, warp;
+  int s0, B, grow0, Rtot;     // first slide of the cluster, slides in the batch, first token row, token rows in the batch
+  uint32_t seedv;
+  float* ws;
+  float* red;                 // [NW][M][32] cross-warp reduction scratch
+  Pipe pipe;
+};
+
+// acc[r] = sum_k x[r][k] Wslice(k, lane) over the next ceil(Ktot / KC) chunks of the program (this warp's k-slices)
+template <int M>
+__device__ __forceinline__ void gemm_block(Dev& d, int type, const float* xs, int ldx, int Ktot, float (&acc)[M]) {
+#pragma unroll
+  for (int r = 0; r < M; ++r) acc[r] = 0.f;
+  for (int kb = 0; kb < Ktot; kb += KC) {
+    const float* wsm = d.pipe.acquire();
+    const int kc = min(KC, Ktot - kb);
+    const int kbeg = d.warp * 32, kend = min(kbeg + 32, kc);
+    const float* xb = xs + kb;
+    if (type == T_FWD) {
+      const float* wr = wsm + d.lane * WLD;
+#pragma unroll 2
+      for (int k = kbeg; k < kend; k += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wr + k);
+#pragma unroll
+        for (int r = 0; r < M; ++r) {
+          const float4 x4 = *reinterpret_cast<const float4*>(xb + r * ldx + k);
+          acc[r] = fmaf(w4.x, x4.x, fmaf(w4.y, x4.y, fmaf(w4.z, x4.z, fmaf(w4.w, x4.w, acc[r]))));
+        }
+      }
+    } else {
+      const float* wc = wsm + d.lane;
+#pragma unroll 2
+      for (int k = kbeg; k < kend; k += 4) {
+        const float w0 = wc[k * 32], w1 = wc[(k + 1) * 32], w2 = wc[(k + 2) * 32], w3 = wc[(k + 3) * 32];
+#pragma unroll
+        for (int r = 0; r < M; ++r) {
+          const float4 x4 = *reinterpret_cast<const float4*>(xb + r * ldx + k);
+          acc[r] = fmaf(w0, x4.x, fmaf(w1, x4.y, fmaf(w2, x4.z, fmaf(w3, x4.w, acc[r]))));
+        }
+      }
+    }
+  }
+}
+// sums the 8 k-slices; thread (warp, lane) finishes outputs (row warp + 8 i, column lane): epi(row, i, value)
+template <int M, class Epi>
+__device__ __forceinline__ void reduce_epi(Dev& d, const float (&acc)[M], Epi epi) {
+#pragma unroll
+  for (int r = 0; r < M; ++r) d.red[(d.warp * M + r) * 32 + d.lane] = acc[r];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < (M + NW - 1) / NW; ++i) {
+    const int r = d.warp + NW * i;
+    if (r < M) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) v += d.red[(w * M + r) * 32 + d.lane];
+      epi(r, i, v);
+    }
+  }
+}
+
+// rows grow0 .. grow0+M-1 of a [rows][256] global array -> shared [M][256] (zeros past the end of the batch)
+template <int M>
+__device__ __forceinline__ void load_rows(const Dev& d, float* dst, const float* src, int grow0, int rtot) {
+  for (int i = d.t; i < M * 64; i += NT) {
+    const int r = i >> 6, c4 = i & 63;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grow0 + r < rtot) v = __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(grow0 + r) * E) + c4);
+    reinterpret_cast<float4*>(dst)[r * 64 + c4] = v;
+  }
+}
+__device__ __forceinline__ DropSpec site_of(const DropSpec& base, uint32_t site) {
+  DropSpec s = base;
+  s.site = site;
+  return s;
+}
+
+// LayerNorm over 256 features (eps 1e-5, biased variance), one warp per row, replicated in every CTA of the cluster;
+// row r is written to global memory by the CTA of rank r % 8
+template <int M>
+__device__ __forceinline__ void ln_fwd_rows(const Dev& d, const float* src, float* dst, const float* gamma, const float* beta,
+                                            float* y_g, float* xh_g, float* rs_g) {
+  float gm[8], bt[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { gm[j] = __ldg(gamma + d.lane + 32 * j); bt[j] = __ldg(beta + d.lane + 32 * j); }
+  for (int r = d.warp; r < M; r += NW) {
+    float v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] = src[r * E + d.lane + 32 * j]; s += v[j]; }
+    s = warp_sum(s);
+    const float mu = s * (1.f / 256.f);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float dd = v[j] - mu; q = fmaf(dd, dd, q); }
+    q = warp_sum(q);
+    const float rs = rsqrtf(q * (1.f / 256.f) + 1e-5f);
+    const int grow = d.grow0 + r;
+    const bool own = grow < d.Rtot && (r % CL) == d.rank;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = d.lane + 32 * j;
+      const float xh = (v[j] - mu) * rs;
+      const float y = fmaf(xh, gm[j], bt[j]);
+      dst[r * E + c] = y;
+      if (own) { xh_g[static_cast<size_t>(grow) * E + c] = xh; y_g[static_cast<size_t>(grow) * E + c] = y; }
+    }
+    if (own && d.lane == 0) rs_g[grow] = rs;
+  }
+}
+// dr = LayerNorm backward of dy (shared), dd = dr through the dropout layer in front of the residual branch
+template <int M>
+__device__ __forceinline__ void ln_bwd_rows(const Dev& d, const float* dy, float* dr, float* dd, const float* gamma,
+                                            const float* xh_g, const float* rs_g, float* dy_g, float* dd_g,
+                                            const DropSpec dsp) {
+  float gm[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gm[j] = __ldg(gamma + d.lane + 32 * j);
+  for (int r = d.warp; r < M; r += NW) {
+    const int grow = d.grow0 + r;
+    const bool valid = grow < d.Rtot;
+    const bool own = valid && (r % CL) == d.rank;
+    float xh[8], dxh[8], g[8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = d.lane + 32 * j;
+      xh[j] = valid ? __ldcg(xh_g + static_cast<size_t>(grow) * E + c) : 0.f;
+      g[j] = dy[r * E + c];
+      dxh[j] = g[j] * gm[j];
+      s1 += dxh[j];
+      s2 = fmaf(dxh[j], xh[j], s2);
+    }
+    s1 = warp_sum(s1) * (1.f / 256.f);
+    s2 = warp_sum(s2) * (1.f / 256.f);
+    const float rs = valid ? __ldcg(rs_g + grow) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = d.lane + 32 * j;
+      const float v = rs * (dxh[j] - s1 - xh[j] * s2);
+      float vd = v;
+      if (dsp.thr != 0) vd *= drop_grad(dsp, d.seedv, static_cast<uint32_t>(grow) * E + c);
+      dr[r * E + c] = v;
+      dd[r * E + c] = vd;
+      if (own) { dy_g[static_cast<size_t>(grow) * E + c] = g[j]; dd_g[static_cast<size_t>(grow) * E + c] = vd; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ parameter blocks
+struct EncP { const float *w_in, *b_in, *w_out, *b_out, *w1, *b1, *w2, *b2, *g1, *be1, *g2, *be2; };
+struct EncW { int x, qkv, probs, ctx, y1, xh1, rs1, f, y2, xh2, rs2, dy2, df2, df, dy1, dsa, dqkv; };
+struct PoolP { const float *wa, *ba, *wb, *bb, *wc, *bc, *wr, *br; float *gwc, *gbc; };
+struct PoolW { int a, b, w, hp, dzr, da, db; };
+
+struct PathParams {
+  Program prog;
+  EncP enc[4];                 // path.0, path.1, omic.0, omic.1
+  EncW encw[4];
+  PoolP pool[2];               // path, omic
+  PoolW poolw[2];
+  const float *wv, *bv, *wo, *bo, *wf0, *bf0, *wf2, *bf2, *wcl, *bcl;
+  float* ws;
+  const float* pooled;
+  float* dpooled;
+  float *hazards, *S, *Y, *att_path, *att_omic;
+  int off_G, off_v, off_hc, off_cat, off_z1, off_z2, off_logits, off_dlogits, off_dz1, off_dz2, off_dhc, off_dv, off_dG;
+  // loss (F_LOSS) or upstream gradients (F_BWD without F_LOSS)
+  int loss_kind;
+  float loss_alpha, loss_eps, grad_scale;
+  const int64_t* label;
+  const float* censor;
+  float *loss, *dhaz_out, *dS_out;
+  const float *dhaz_in, *dS_in, *dY_in;
+  DropSpec d_model, d_quarter;
+  int B, K, flags;
+};
+static_assert(sizeof(PathParams) <= 4000, "kernel parameter space");
+
+// ------------------------------------------------------------------------------------------------ encoder layer
+// nn.TransformerEncoderLayer(256, nhead 8, ff 512, relu, post-norm) as built at models/mcat/mcat.py:51-53.
+// in: x in XA (replicated); out: y2 in XA.  CTA `rank` owns head `rank` of the self-attention.
+template <int S>
+__device__ __forceinline__ void enc_fwd(Dev& d, const EncP& p, const EncW& w, int eidx, const DropSpec& dm, float* XA,
+                                        float* XB, float* XC, float* BIG, float* QKVL) {
+  constexpr int M = 6 * S;
+  float acc[M];
+  float* ws = d.ws;
+  const uint32_t s0 = SITE_ENC + 4 * eidx;      // attention probabilities, dropout1, feed-forward dropout, dropout2
+  // packed in-projection: this CTA computes q, k, v of its head
+  for (int blk = 0; blk < 3; ++blk) {
+    const int col = blk * E + d.rank * 32 + d.lane;
+    const float bias = __ldg(p.b_in + col);
+    gemm_block<M>(d, T_FWD, XA, E, E, acc);
+    reduce_epi<M>(d, acc, [&](int r, int, float v) {
+      v += bias;
+      QKVL[r * 96 + blk * 32 + d.lane] = v;
+      const int grow = d.grow0 + r;
+      if (grow < d.Rtot) ws[w.qkv + static_cast<size_t>(grow) * 768 + col] = v;
+    });
+  }
+  __syncthreads();
+  // 6 x 6 attention of head `rank`, one warp per (slide, query token); lane = head dimension
+  {
+    const DropSpec da = site_of(dm, s0);
+    const float scale = 0.17677669529663687f;   // 1/sqrt(32)
+    for (int r1 = d.warp; r1 < M; r1 += NW) {
+      const int sl = r1 / 6, l1 = r1 - sl * 6;
+      const float q = QKVL[r1 * 96 + d.lane];
+      float sc[6];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int l2 = 0; l2 < 6; ++l2) {
+        sc[l2] = warp_sum(q * QKVL[(sl * 6 + l2) * 96 + 32 + d.lane]) * scale;
+        mx = fmaxf(mx, sc[l2]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int l2 = 0; l2 < 6; ++l2) { sc[l2] = expf(sc[l2] - mx); sum += sc[l2]; }
+      const float inv = 1.f / sum;
+      const int slide = d.s0 + sl;
+      const uint32_t pi0 = ((static_cast<uint32_t>(slide) * 8 + d.rank) * 6 + l1) * 6;
+      float c = 0.f;
+#pragma unroll
+      for (int l2 = 0; l2 < 6; ++l2) {
+        const float pr = sc[l2] * inv;
+        if (d.lane == 0 && slide < d.B) ws[w.probs + pi0 + l2] = pr;       // kept before dropout
+        const float pd = da.thr != 0 ? drop_fwd(pr, da, d.seedv, pi0 + l2) : pr;
+        c = fmaf(pd, QKVL[(sl * 6 + l2) * 96 + 64 + d.lane], c);
+      }
+      const int col = d.rank * 32 + d.lane;
+      bcast(XB + r1 * E + col, c);
+      if (slide < d.B) ws[w.ctx + static_cast<size_t>(d.grow0 + r1) * E + col] = c;
+    }
+  }
+  cluster_sync();
+  // out-projection + dropout1 + residual
+  {
+    const int col = d.rank * 32 + d.lane;
+    const float bias = __ldg(p.b_out + col);
+    const DropSpec d1 = site_of(dm, s0 + 1);
+    gemm_block<M>(d, T_FWD, XB, E, E, acc);
+    reduce_epi<M>(d, acc, [&](int r, int, float v) {
+      v += bias;
+      if (d1.thr != 0) v = drop_fwd(v, d1, d.seedv, static_cast<uint32_t>(d.grow0 + r) * E + col);
+      bcast(XC + r * E + col, v + XA[r * E + col]);
+    });
+  }
+  cluster_sync();
+  ln_fwd_rows<M>(d, XC, XA, p.g1, p.be1, ws + w.y1, ws + w.xh1, ws + w.rs1);
+  __syncthreads();
+  // feed-forward
+  for (int blk = 0; blk < 2; ++blk) {
+    const int col = d.rank * 64 + blk * 32 + d.lane;
+    const float bias = __ldg(p.b1 + col);
+    const DropSpec d2 = site_of(dm, s0 + 2);
+    gemm_block<M>(d, T_FWD, XA, E, E, acc);
+    reduce_epi<M>(d, acc, [&](int r, int, float v) {
+      v = fmaxf(v + bias, 0.f);
+      const int grow = d.grow0 + r;
+      if (d2.thr != 0) v = drop_fwd(v, d2, d.seedv, static_cast<uint32_t>(grow) * FF + col);
+      bcast(BIG + r * FF + col, v);
+      if (grow < d.Rtot) ws[w.f + static_cast<size_t>(grow) * FF + col] = v;
+    });
+  }
+  cluster_sync();
+  {
+    const int col = d.rank * 32 + d.lane;
+    const float bias = __ldg(p.b2 + col);
+    const DropSpec d3 = site_of(dm, s0 + 3);
+    gemm_block<M>(d, T_FWD, BIG, FF, FF, acc);
+    reduce_epi<M>(d, acc, [&](int r, int, float v) {
+      v += bias;
+      if (d3.thr != 0) v = drop_fwd(v, d3, d.seedv, static_cast<uint32_t>(d.grow0 + r) * E + col);
+      bcast(XC + r * E + col, v + XA[r * E + col]);
+    });
+  }
+  cluster_sync();
+  ln_fwd_rows<M>(d, XC, XA, p.g2, p.be2, ws + w.y2, ws + w.xh2, ws + w.rs2);
+  __syncthreads();
+}
+
+// in: dy2 in XA (replicated); out: dx in XA (and in global memory at dx_g when non-null)
+template <int S>
+__device__ __forceinline__ void enc_bwd(Dev& d, const EncP& p, const EncW& w, int eidx, const DropSpec& dm, float* XA,
+                                        float* XB, float* XC, float* BIG, float* DCTX, float* dx_g) {
+  constexpr int M = 6 * S;
+  float acc[M];
+  float* ws = d.ws;
+  const uint32_t s0 = SITE_ENC + 4 * eidx;
+  // norm2: dr2 -> XB, gradient of linear2's output (through dropout2) -> XC
+  ln_bwd_rows<M>(d, XA, XB, XC, p.g2, ws + w.xh2, ws + w.rs2, ws + w.dy2, ws + w.df2, site_of(dm, s0 + 3));
+  __syncthreads();
+  // linear2 data gradient with the ReLU / feed-forward-dropout derivative: gradient at linear1's pre-activation
+  for (int blk = 0; blk < 2; ++blk) {
+    const int col = d.rank * 64 + blk * 32 + d.lane;
+    const DropSpec d2 = site_of(dm, s0 + 2);
+    float fv[(M + NW - 1) / NW];
+#pragma unroll
+    for (int i = 0; i < (M + NW - 1) / NW; ++i) {
+      const int grow = d.grow0 + d.warp + NW * i;
+      fv[i] = (d.warp + NW * i < M && grow < d.Rtot) ? __ldcg(ws + w.f + static_cast<size_t>(grow) * FF + col) : 0.f;
+    }
+    gemm_block<M>(d, T_DGRAD, XC, E, E, acc);
+    reduce_epi<M>(d, acc, [&](int r, int i, float v) {
+      const int grow = d.grow0 + r;
+      if (d2.thr != 0) v *= drop_grad(d2, d.seedv, static_cast<uint32_t>(grow) * FF + col);
+      v = fv[i] > 0.f ? v : 0.f;          // a kept element is positive exactly when its ReLU output was
+      bcast(BIG + r * FF + col, v);
+      if (grow < d.Rtot) ws[w.df + static_cast<size_t>(grow) * FF + col] = v;
+    });
+  }
+  cluster_sync();
+  // linear1 data gradient + the residual branch: dy1
+  {
+    const int col = d.rank * 32 + d.lane;
+    gemm_block<M>(d, T_DGRAD, BIG, FF, FF, acc);
+    reduce_epi<M>(d, acc, [&](int r, int, float v) { bcast(XA + r * E + col, v + XB[r * E + col]); });
+  }
+  cluster_sync();
+  // norm1: dr1 -> XB, gradient of the attention block's output (through dropout1) -> XC
+  ln_bwd_rows<M>(d, XA, XB, XC, p.g1, ws + w.xh1, ws + w.rs1, ws + w.dy1, ws + w.dsa, site_of(dm, s0 + 1));
+  __syncthreads();
+  // out-projection data gradient: this CTA's 32 columns are its own head
+  {
+    gemm_block<M>(d, T_DGRAD, XC, E, E, acc);
+    reduce_epi<M>(d, acc, [&](int r, int, float v) { DCTX[r * 32 + d.lane] = v; });
+  }
+  __syncthreads();
+  // attention backward of head `rank`, one warp per slide
+  {
+    const DropSpec da = site_of(dm, s0);
+    const float scale = 0.17677669529663687f;
+    for (int sl = d.warp; sl < S; sl += NW) {
+      const int slide = d.s0 + sl;
+      const bool valid = slide < d.B;
+      float q[6], k[6], v[6], dc[6], dq[6], dk[6], dv[6];
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        const float* row = ws + w.qkv + static_cast<size_t>(slide * 6 + l) * 768 + d.rank * 32 + d.lane;
+        q[l] = valid ? __ldcg(row) : 0.f;
+        k[l] = valid ? __ldcg(row + 256) : 0.f;
+        v[l] = valid ? __ldcg(row + 512) : 0.f;
+        dc[l] = DCTX[(sl * 6 + l) * 32 + d.lane];
+        dq[l] = 0.f; dk[l] = 0.f; dv[l] = 0.f;
+      }
+      const uint32_t pw = (static_cast<uint32_t>(slide) * 8 + d.rank) * 36;
+#pragma unroll
+      for (int l1 = 0; l1 < 6; ++l1) {
+        float a[6], dA[6];
+        float dot = 0.f;
+#pragma unroll
+        for (int l2 = 0; l2 < 6; ++l2) {
+          const uint32_t pi = pw + l1 * 6 + l2;
+          a[l2] = valid ? __ldcg(ws + w.probs + pi) : 0.f;
+          const float mg = da.thr != 0 ? drop_grad(da, d.seedv, pi) : 1.f;
+          dA[l2] = warp_sum(dc[l1] * v[l2]) * mg;
+          dot = fmaf(dA[l2], a[l2], dot);
+          dv[l2] = fmaf(a[l2] * mg, dc[l1], dv[l2]);
+        }
+#pragma unroll
+        for (int l2 = 0; l2 < 6; ++l2) {
+          const float ds = a[l2] * (dA[l2] - dot) * scale;
+          dq[l1] = fmaf(ds, k[l2], dq[l1]);
+          dk[l2] = fmaf(ds, q[l1], dk[l2]);
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        const int r = sl * 6 + l;
+        const int col = d.rank * 32 + d.lane;
+        bcast(BIG + r * 768 + col, dq[l]);
+        bcast(BIG + r * 768 + 256 + col, dk[l]);
+        bcast(BIG + r * 768 + 512 + col, dv[l]);
+        if (valid) {
+          float* row = ws + w.dqkv + static_cast<size_t>(d.grow0 + r) * 768 + col;
+          row[0] = dq[l]; row[256] = dk[l]; row[512] = dv[l];
+        }
+      }
+    }
+  }
+  cluster_sync();
+  // in-projection data gradient + the residual branch: dx
+  {
+    const int col = d.rank * 32 + d.lane;
+    gemm_block<M>(d, T_DGRAD, BIG, 768, 768, acc);
+    reduce_epi<M>(d, acc, [&](int r, int, float v) {
+      v += XB[r * E + col];
+      bcast(XA + r * E + col, v);
+      const int grow = d.grow0 + r;
+      if (dx_g != nullptr && grow < d.Rtot) dx_g[static_cast<size_t>(grow) * E + col] = v;
+    });
+  }
+  cluster_sync();
+}
+
+// ------------------------------------------------------------------------------------------------ pooling + rho
+// AttentionNetGated (models/blocks.py:42-48) + soft-max pooling + rho (models/mcat/mcat.py:105-109).
+// in: tokens in XA; out: rho output broadcast into CAT[s][p * 256 + .]
+template <int S>
+__device__ __forceinline__ void pool_fwd(Dev& d, const PoolP& p, const PoolW& w, int pidx, const DropSpec& dm,
+                                         const DropSpec& dq, float* att_out, int off_cat, float* XA, float* AL, float* BL,
+                                         float* PA, float* AW, float* HP, float* CAT) {
+  constexpr int M = 6 * S;
+  float acc[M];
+  float* ws = d.ws;
+  const int col = d.rank * 32 + d.lane;
+  for (int br = 0; br < 2; ++br) {
+    const float bias = __ldg((br == 0 ? p.ba : p.bb) + col);
+    const DropSpec ds = site_of(dq, SITE_POOL + 2 * pidx + br);
+    float* dst = br == 0 ? AL : BL;
+    const int off = br == 0 ? w.a : w.b;
+    gemm_block<M>(d, T_FWD, XA, E, E, acc);
+    reduce_epi<M>(d, acc, [&](int r, int, float v) {
+      v += bias;
+      v = br == 0 ? tanhf(v) : 1.f / (1.f + expf(-v));
+      const int grow = d.grow0 + r;
+      if (ds.thr != 0) v = drop_fwd(v, ds, d.seedv, static_cast<uint32_t>(grow) * E + col);
+      dst[r * 32 + d.lane] = v;
+      if (grow < d.Rtot) ws[off + static_cast<size_t>(grow) * E + col] = v;
+    });
+  }
+  __syncthreads();
+  {
+    const float wc = __ldg(p.wc + col);
+    for (int r = d.warp; r < M; r += NW) {
+      const float v = warp_sum(AL[r * 32 + d.lane] * BL[r * 32 + d.lane] * wc);
+      if (d.lane == 0) bcast(PA + d.rank * M + r, v);
+    }
+  }
+  cluster_sync();
+  if (d.t < M) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < CL; ++k) a += PA[k * M + d.t];
+    a += __ldg(p.bc);
+    PA[CL * M + d.t] = a;                       // raw logits A
+    const int grow = d.grow0 + d.t;
+    if (d.rank == 0 && grow < d.Rtot) att_out[grow] = a;
+  }
+  __syncthreads();
+  if (d.t < S) {
+    const float* A = PA + CL * M + d.t * 6;
+    float m = A[0];
+#pragma unroll
+    for (int l = 1; l < 6; ++l) m = fmaxf(m, A[l]);
+    float e[6], sum = 0.f;
+#pragma unroll
+    for (int l = 0; l < 6; ++l) { e[l] = expf(A[l] - m); sum += e[l]; }
+#pragma unroll
+    for (int l = 0; l < 6; ++l) {
+      const float wl = e[l] / sum;
+      AW[d.t * 6 + l] = wl;
+      if (d.rank == 0 && d.s0 + d.t < d.B) ws[w.w + (d.s0 + d.t) * 6 + l] = wl;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    float h = 0.f;
+#pragma unroll
+    for (int l = 0; l < 6; ++l) h = fmaf(AW[s * 6 + l], XA[(s * 6 + l) * E + d.t], h);
+    HP[s * E + d.t] = h;
+    if (d.rank == 0 && d.s0 + s < d.B) ws[w.hp + static_cast<size_t>(d.s0 + s) * E + d.t] = h;
+  }
+  __syncthreads();
+  {
+    float accs[S];
+    const float bias = __ldg(p.br + col);
+    const DropSpec dr = site_of(dm, SITE_RHO + pidx);
+    gemm_block<S>(d, T_FWD, HP, E, E, accs);
+    reduce_epi<S>(d, accs, [&](int s, int, float v) {
+      v = fmaxf(v + bias, 0.f);
+      const int slide = d.s0 + s;
+      if (dr.thr != 0) v = drop_fwd(v, dr, d.seedv, static_cast<uint32_t>(slide) * E + col);
+      bcast(CAT + s * 2 * E + pidx * E + col, v);
+      if (slide < d.B) ws[off_cat + static_cast<size_t>(slide) * 2 * E + pidx * E + col] = v;
+    });
+  }
+  cluster_sync();
+}
+
+// in: DZR[s][p*256 + .] = gradient at rho's pre-activation; out: gradient of the tokens in XA
+template <int S>
+__device__ __forceinline__ void pool_bwd(Dev& d, const PoolP& p, const PoolW& w, int pidx, const DropSpec& dq,
+                                         const float* tok_g, float* XA, float* BIG, float* AL, float* BL, float* PA,
+                                         float* AW, float* DHP, const float* DZR) {
+  constexpr int M = 6 * S;
+  float* ws = d.ws;
+  const int col = d.rank * 32 + d.lane;
+  // rho data gradient
+  {
+    float accs[S];
+    gemm_block<S>(d, T_DGRAD, DZR + pidx * E, 2 * E, E, accs);
+    reduce_epi<S>(d, accs, [&](int s, int, float v) { bcast(DHP + s * E + col, v); });
+  }
+  // this pooling head's tokens, own columns of the two gate branches, pooling weights
+  load_rows<M>(d, XA, tok_g, d.grow0, d.Rtot);
+  for (int i = d.t; i < M * 32; i += NT) {
+    const int r = i >> 5, n = i & 31;
+    const int grow = d.grow0 + r;
+    const bool valid = grow < d.Rtot;
+    AL[i] = valid ? __ldcg(ws + w.a + static_cast<size_t>(grow) * E + d.rank * 32 + n) : 0.f;
+    BL[i] = valid ? __ldcg(ws + w.b + static_cast<size_t>(grow) * E + d.rank * 32 + n) : 0.f;
+  }
+  if (d.t < M) AW[d.t] = (d.grow0 + d.t < d.Rtot) ? __ldcg(ws + w.w + d.grow0 + d.t) : 0.f;
+  cluster_sync();
+  // dw[r] = dhp . x[r]
+  for (int r = d.warp; r < M; r += NW) {
+    const int s = r / 6;
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v = fmaf(DHP[s * E + d.lane + 32 * j], XA[r * E + d.lane + 32 * j], v);
+    v = warp_sum(v);
+    if (d.lane == 0) PA[r] = v;
+  }
+  __syncthreads();
+  if (d.t < S) {
+    float dot = 0.f;
+#pragma unroll
+    for (int l = 0; l < 6; ++l) dot = fmaf(PA[d.t * 6 + l], AW[d.t * 6 + l], dot);
+#pragma unroll
+    for (int l = 0; l < 6; ++l) PA[M + d.t * 6 + l] = AW[d.t * 6 + l] * (PA[d.t * 6 + l] - dot);      // dA
+  }
+  __syncthreads();
+  {
+    const float wc = __ldg(p.wc + col);
+    const DropSpec dsa = site_of(dq, SITE_POOL + 2 * pidx), dsb = site_of(dq, SITE_POOL + 2 * pidx + 1);
+    float gw = 0.f;
+#pragma unroll
+    for (int i = 0; i < (M + NW - 1) / NW; ++i) {
+      const int r = d.warp + NW * i;
+      if (r < M) {
+        const int grow = d.grow0 + r;
+        const uint32_t o = static_cast<uint32_t>(grow) * E + col;
+        const float dA = PA[M + r];
+        const float av = AL[r * 32 + d.lane], bv = BL[r * 32 + d.lane];   // as stored: after their dropout layers
+        const float dab = dA * wc;
+        float ga = 1.f, gb = 1.f, a0 = av, b0 = bv;
+        if (dsa.thr != 0) { ga = drop_grad(dsa, d.seedv, o); a0 = drop_invert(av, dsa); }
+        if (dsb.thr != 0) { gb = drop_grad(dsb, d.seedv, o); b0 = drop_invert(bv, dsb); }
+        const float da_pre = dab * bv * ga * (1.f - a0 * a0);
+        const float db_pre = dab * av * gb * b0 * (1.f - b0);
+        bcast(BIG + r * FF + col, da_pre);
+        bcast(BIG + r * FF + E + col, db_pre);
+        if (grow < d.Rtot) {
+          ws[w.da + static_cast<size_t>(grow) * E + col] = da_pre;
+          ws[w.db + static_cast<size_t>(grow) * E + col] = db_pre;
+          gw = fmaf(dA, av * bv, gw);
+        }
+      }
+    }
+    // attention_c parameter gradients: one atomic per (cluster, column)
+    d.red[d.warp * 32 + d.lane] = gw;
+    __syncthreads();
+    if (d.warp == 0 && p.gwc != nullptr) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) v += d.red[k * 32 + d.lane];
+      atomicAdd(p.gwc + col, v);
+    }
+    if (d.rank == 0 && d.t == 0 && p.gbc != nullptr) {
+      float v = 0.f;
+      for (int r = 0; r < M; ++r) if (d.grow0 + r < d.Rtot) v += PA[M + r];
+      atomicAdd(p.gbc, v);
+    }
+  }
+  cluster_sync();
+  // gradient of the tokens: both gate branches' data gradients + the value path of the pooling
+  {
+    float acc[M];
+    gemm_block<M>(d, T_DGRAD, BIG, FF, FF, acc);          // chunks: attention_a then attention_b
+    reduce_epi<M>(d, acc, [&](int r, int, float v) {
+      v = fmaf(AW[r], DHP[(r / 6) * E + col], v);
+      bcast(XA + r * E + col, v);
+    });
+  }
+  cluster_sync();
+}
+
+// ------------------------------------------------------------------------------------------------ path kernel
+template <int S>
+struct PathSmem {
+  static constexpr int M = 6 * S;
+  static constexpr int ring = 0;
+  static constexpr int XA = ring + NSTAGE * CHUNK;
+  static constexpr int XB = XA + M * E;
+  static constexpr int XC = XB + M * E;
+  static constexpr int BIG = XC + M * E;
+  static constexpr int RED = BIG + M * 768;
+  static constexpr int QKVL = RED + NW * M * 32;
+  static constexpr int AL = QKVL + M * 96;
+  static constexpr int BL = AL + M * 32;
+  static constexpr int PA = BL + M * 32;              // [CL + 1][M]
+  static constexpr int AW = PA + (CL + 1) * M + 4;
+  static constexpr int HP = ((AW + M + 3) / 4) * 4;
+  static constexpr int CAT = HP + S * E;
+  static constexpr int Z1 = CAT + S * 2 * E;
+  static constexpr int Z2 = Z1 + S * E;
+  static constexpr int DZS = Z2 + S * E;
+  static constexpr int DZ1 = DZS + S * E;
+  static constexpr int DZR = DZ1 + S * E;
+  static constexpr int DHP = DZR + S * 2 * E;
+  static constexpr int SM = DHP + S * E;              // small per-slide vectors: 8 x [S][MAXK]
+  static constexpr int total = SM + 8 * S * MAXK;
+};
+
+template <int S>
+__global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ PathParams P) {
+  constexpr int M = 6 * S;
+  using L = PathSmem<S>;
+  extern __shared__ __align__(16) float sm[];
+  Dev d;
+  d.rank = cluster_rank();
+  d.t = threadIdx.x; d.lane = d.t & 31; d.warp = d.t >> 5;
+  d.s0 = (blockIdx.x / CL) * S;
+  d.B = P.B; d.grow0 = d.s0 * 6; d.Rtot = 6 * P.B;
+  d.seedv = drop_seed(P.d_model);
+  d.ws = P.ws;
+  d.red = sm + L::RED;
+  d.pipe.init(P.prog, sm + L::ring, d.rank, d.t);
+  float* ws = P.ws;
+  float *XA = sm + L::XA, *XB = sm + L::XB, *XC = sm + L::XC, *BIG = sm + L::BIG, *QKVL = sm + L::QKVL;
+  float *AL = sm + L::AL, *BL = sm + L::BL, *PA = sm + L::PA, *AW = sm + L::AW, *HP = sm + L::HP, *CAT = sm + L::CAT;
+  float *Z1 = sm + L::Z1, *Z2 = sm + L::Z2, *DZS = sm + L::DZS, *DZ1 = sm + L::DZ1, *DZR = sm + L::DZR, *DHP = sm + L::DHP;
+  float* LG = sm + L::SM;                 // logits
+  float* HZ = LG + S * MAXK;              // hazards
+  float* SV = HZ + S * MAXK;              // S
+  float* YV = SV + S * MAXK;              // Y
+  float* DH = YV + S * MAXK;              // d hazards
+  float* DS = DH + S * MAXK;              // d S
+  float* DYv = DS + S * MAXK;             // d Y
+  float* DLG = DYv + S * MAXK;            // d logits
+  const int K = P.K;
+  const int col = d.rank * 32 + d.lane;
+  const DropSpec& dm = P.d_model;
+  const DropSpec& dq = P.d_quarter;
+  cluster_sync();                         // every CTA of the cluster is running before any remote store
+
+  if (P.flags & F_FWD) {
+    // ---- omic branch: encoders + pooling over the SNN tokens (mcat.py:102,111-115)
+    load_rows<M>(d, XA, ws + P.off_G, d.grow0, d.Rtot);
+    enc_fwd<S>(d, P.enc[2], P.encw[2], 2, dm, XA, XB, XC, BIG, QKVL);
+    enc_fwd<S>(d, P.enc[3], P.encw[3], 3, dm, XA, XB, XC, BIG, QKVL);
+    pool_fwd<S>(d, P.pool[1], P.poolw[1], 1, dm, dq, P.att_omic, P.off_cat, XA, AL, BL, PA, AW, HP, CAT);
+    // ---- path branch: value / output projections of the pooled vectors (folded form of mcat.py:97)
+    load_rows<M>(d, XA, P.pooled, d.grow0, d.Rtot);
+    {
+      float acc[M];
+      const float bias = __ldg(P.bv + col);
+      gemm_block<M>(d, T_FWD, XA, E, E, acc);
+      reduce_epi<M>(d, acc, [&](int r, int, float v) {
+        v += bias;
+        bcast(XB + r * E + col, v);
+        if (d.grow0 + r < d.Rtot) ws[P.off_v + static_cast<size_t>(d.grow0 + r) * E + col] = v;
+      });
+    }
+    cluster_sync();
+    {
+      float acc[M];
+      const float bias = __ldg(P.bo + col);
+      gemm_block<M>(d, T_FWD, XB, E, E, acc);
+      reduce_epi<M>(d, acc, [&](int r, int, float v) {
+        v += bias;
+        bcast(XA + r * E + col, v);
+        if (d.grow0 + r < d.Rtot) ws[P.off_hc + static_cast<size_t>(d.grow0 + r) * E + col] = v;
+      });
+    }
+    cluster_sync();
+    enc_fwd<S>(d, P.enc[0], P.encw[0], 0, dm, XA, XB, XC, BIG, QKVL);
+    enc_fwd<S>(d, P.enc[1], P.encw[1], 1, dm, XA, XB, XC, BIG, QKVL);
+    pool_fwd<S>(d, P.pool[0], P.poolw[0], 0, dm, dq, P.att_path, P.off_cat, XA, AL, BL, PA, AW, HP, CAT);
+    // ---- concat fusion (fusion.py:17-19)
+    {
+      float accs[S];
+      const float bias = __ldg(P.bf0 + col);
+      gemm_block<S>(d, T_FWD, CAT, 2 * E, 2 * E, accs);
+      reduce_epi<S>(d, accs, [&](int s, int, float v) {
+        v = fmaxf(v + bias, 0.f);
+        bcast(Z1 + s * E + col, v);
+        if (d.s0 + s < d.B) ws[P.off_z1 + static_cast<size_t>(d.s0 + s) * E + col] = v;
+      });
+    }
+    cluster_sync();
+    {
+      float accs[S];
+      const float bias = __ldg(P.bf2 + col);
+      gemm_block<S>(d, T_FWD, Z1, E, E, accs);
+      reduce_epi<S>(d, accs, [&](int s, int, float v) {
+        v = fmaxf(v + bias, 0.f);
+        bcast(Z2 + s * E + col, v);
+        if (d.s0 + s < d.B) ws[P.off_z2 + static_cast<size_t>(d.s0 + s) * E + col] = v;
+      });
+    }
+    cluster_sync();
+    // ---- classifier + survival head (mcat.py:126-138), replicated in every CTA
+    for (int pr = d.warp; pr < S * K; pr += NW) {
+      const int s = pr / K, k = pr - s * K;
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v = fmaf(Z2[s * E + d.lane + 32 * j], __ldg(P.wcl + k * E + d.lane + 32 * j), v);
+      v = warp_sum(v);
+      if (d.lane == 0) LG[s * MAXK + k] = v + __ldg(P.bcl + k);
+    }
+    __syncthreads();
+    if (d.t < S) {
+      const int s = d.t, slide = d.s0 + s;
+      float m = -INFINITY;
+      for (int j = 0; j < K; ++j) m = fmaxf(m, LG[s * MAXK + j]);
+      float sum = 0.f, sv = 1.f;
+      for (int j = 0; j < K; ++j) {
+        const float z = LG[s * MAXK + j];
+        const float hz = 1.f / (1.f + expf(-z));
+        HZ[s * MAXK + j] = hz;
+        sv *= (1.f - hz);
+        SV[s * MAXK + j] = sv;
+        sum += expf(z - m);
+      }
+      for (int j = 0; j < K; ++j) YV[s * MAXK + j] = expf(LG[s * MAXK + j] - m) / sum;
+      if (d.rank == 0 && slide < d.B) {
+        for (int j = 0; j < K; ++j) {
+          P.hazards[slide * K + j] = HZ[s * MAXK + j];
+          P.S[slide * K + j] = SV[s * MAXK + j];
+          P.Y[slide * K + j] = YV[s * MAXK + j];
+          ws[P.off_logits + slide * K + j] = LG[s * MAXK + j];
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  if (P.flags & F_BWD) {
+    if (!(P.flags & F_FWD)) {
+      // activations of the forward pass come back from the workspace
+      for (int i = d.t; i < S * E; i += NT) {
+        const int s = i / E, c = i - s * E;
+        const bool valid = d.s0 + s < d.B;
+        Z1[i] = valid ? __ldcg(ws + P.off_z1 + static_cast<size_t>(d.s0 + s) * E + c) : 0.f;
+        Z2[i] = valid ? __ldcg(ws + P.off_z2 + static_cast<size_t>(d.s0 + s) * E + c) : 0.f;
+        CAT[s * 2 * E + c] = valid ? __ldcg(ws + P.off_cat + static_cast<size_t>(d.s0 + s) * 2 * E + c) : 0.f;
+        CAT[s * 2 * E + E + c] = valid ? __ldcg(ws + P.off_cat + static_cast<size_t>(d.s0 + s) * 2 * E + E + c) : 0.f;
+      }
+      if (d.t < S * K) {
+        const int s = d.t / K, j = d.t - s * K, slide = d.s0 + s;
+        const bool valid = slide < d.B;
+        HZ[s * MAXK + j] = valid ? P.hazards[slide * K + j] : 0.5f;
+        SV[s * MAXK + j] = valid ? P.S[slide * K + j] : 0.5f;
+        YV[s * MAXK + j] = valid ? P.Y[slide * K + j] : 0.f;
+      }
+      __syncthreads();
+    }
+    // ---- loss gradients (models/loss.py:5-43) or the caller's upstream gradients
+    if (d.t < S) {
+      const int s = d.t, slide = d.s0 + s;
+      const bool valid = slide < d.B;
+      for (int j = 0; j < K; ++j) { DH[s * MAXK + j] = 0.f; DS[s * MAXK + j] = 0.f; DYv[s * MAXK + j] = 0.f; }
+      if (P.flags & F_LOSS) {
+        if (valid) {
+          const int y = static_cast<int>(P.label[slide]);
+          const float c = P.censor[slide];
+          const float alpha = P.loss_alpha, eps = P.loss_eps, gs = P.grad_scale;
+          float l = NAN;
+          if (y >= 0 && y < K) {
+            const float s_prev = y == 0 ? 1.f : SV[s * MAXK + y - 1];
+            const float h_y = HZ[s * MAXK + y];
+            const float unc = -(1.f - c) * (logf(fmaxf(s_prev, eps)) + logf(fmaxf(h_y, eps)));
+            float w_unc;
+            if (P.loss_kind == MPO_LOSS_NLL) {
+              const float s_y = SV[s * MAXK + y];
+              const float cen = -c * logf(fmaxf(s_y, eps));
+              l = (1.f - alpha) * (cen + unc) + alpha * unc;
+              w_unc = 1.f;
+              if (s_y > eps) DS[s * MAXK + y] += gs * (1.f - alpha) * (-c / s_y);
+            } else {
+              const float s_y = fmaxf(SV[s * MAXK + y], eps);
+              const float ce = -(c * logf(s_y) + (1.f - c) * logf(1.f - s_y));
+              l = (1.f - alpha) * ce + alpha * unc;
+              w_unc = alpha;
+              if (SV[s * MAXK + y] > eps) DS[s * MAXK + y] += gs * (1.f - alpha) * (-(c / s_y) + (1.f - c) / (1.f - s_y));
+            }
+            if (y >= 1 && s_prev > eps) DS[s * MAXK + y - 1] += gs * w_unc * (-(1.f - c) / s_prev);
+            if (h_y > eps) DH[s * MAXK + y] += gs * w_unc * (-(1.f - c) / h_y);
+          }
+          if (d.rank == 0) {
+            P.loss[slide] = l;
+            for (int j = 0; j < K; ++j) {
+              if (P.dhaz_out) P.dhaz_out[slide * K + j] = DH[s * MAXK + j];
+              if (P.dS_out) P.dS_out[slide * K + j] = DS[s * MAXK + j];
+            }
+          }
+        }
+      } else if (valid) {
+        for (int j = 0; j < K; ++j) {
+          if (P.dhaz_in) DH[s * MAXK + j] = P.dhaz_in[slide * K + j];
+          if (P.dS_in) DS[s * MAXK + j] = P.dS_in[slide * K + j];
+          if (P.dY_in) DYv[s * MAXK + j] = P.dY_in[slide * K + j];
+        }
+      }
+      // survival head backward
+      float dotY = 0.f;
+      for (int j = 0; j < K; ++j) dotY = fmaf(DYv[s * MAXK + j], YV[s * MAXK + j], dotY);
+      float tail = 0.f;
+      for (int tt = K - 1; tt >= 0; --tt) {
+        const float hz = HZ[s * MAXK + tt];
+        tail = fmaf(DS[s * MAXK + tt], SV[s * MAXK + tt], tail);
+        float dh = DH[s * MAXK + tt] - tail / (1.f - hz);
+        float dl = dh * hz * (1.f - hz) + YV[s * MAXK + tt] * (DYv[s * MAXK + tt] - dotY);
+        DLG[s * MAXK + tt] = dl;
+        if (d.rank == 0 && valid) ws[P.off_dlogits + slide * K + tt] = dl;
+      }
+    }
+    __syncthreads();
+    // ---- classifier data gradient with fusion layer 2's ReLU derivative (replicated; thread = feature)
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      float g = 0.f;
+      for (int k = 0; k < K; ++k) g = fmaf(DLG[s * MAXK + k], __ldg(P.wcl + k * E + d.t), g);
+      g = Z2[s * E + d.t] > 0.f ? g : 0.f;
+      DZS[s * E + d.t] = g;
+      if (d.rank == 0 && d.s0 + s < d.B) ws[P.off_dz2 + static_cast<size_t>(d.s0 + s) * E + d.t] = g;
+    }
+    __syncthreads();
+    {
+      float accs[S];
+      gemm_block<S>(d, T_DGRAD, DZS, E, E, accs);
+      reduce_epi<S>(d, accs, [&](int s, int, float v) {
+        v = Z1[s * E + col] > 0.f ? v : 0.f;
+        bcast(DZ1 + s * E + col, v);
+        if (d.s0 + s < d.B) ws[P.off_dz1 + static_cast<size_t>(d.s0 + s) * E + col] = v;
+      });
+    }
+    cluster_sync();
+    // fusion layer 0 data gradient: the gradient of [h_path | h_omic], taken through rho's dropout and ReLU
+    for (int blk = 0; blk < 2; ++blk) {
+      float accs[S];
+      const int c2 = d.rank * 64 + blk * 32 + d.lane;     // column of the [., 512] concat
+      const int pidx = c2 >> 8, c = c2 & 255;
+      const DropSpec dr = site_of(dm, SITE_RHO + pidx);
+      gemm_block<S>(d, T_DGRAD, DZ1, E, E, accs);
+      reduce_epi<S>(d, accs, [&](int s, int, float v) {
+        const int slide = d.s0 + s;
+        float hv = CAT[s * 2 * E + c2];
+        if (dr.thr != 0) { v *= drop_grad(dr, d.seedv, static_cast<uint32_t>(slide) * E + c); hv = drop_invert(hv, dr); }
+        v = hv > 0.f ? v : 0.f;
+        bcast(DZR + s * 2 * E + c2, v);
+        if (slide < d.B) ws[P.poolw[pidx].dzr + static_cast<size_t>(slide) * E + c] = v;
+      });
+    }
+    cluster_sync();
+    // ---- omic branch backward -> dG (completed by pre_bwd_kernel)
+    pool_bwd<S>(d, P.pool[1], P.poolw[1], 1, dq, ws + P.encw[3].y2, XA, BIG, AL, BL, PA, AW, DHP, DZR);
+    enc_bwd<S>(d, P.enc[3], P.encw[3], 3, dm, XA, XB, XC, BIG, AL, nullptr);
+    enc_bwd<S>(d, P.enc[2], P.encw[2], 2, dm, XA, XB, XC, BIG, AL, ws + P.off_dG);
+    // ---- path branch backward -> d(pooled)
+    pool_bwd<S>(d, P.pool[0], P.poolw[0], 0, dq, ws + P.encw[1].y2, XA, BIG, AL, BL, PA, AW, DHP, DZR);
+    enc_bwd<S>(d, P.enc[1], P.encw[1], 1, dm, XA, XB, XC, BIG, AL, nullptr);
+    enc_bwd<S>(d, P.enc[0], P.encw[0], 0, dm, XA, XB, XC, BIG, AL, ws + P.off_dhc);
+    {
+      float acc[M];
+      gemm_block<M>(d, T_DGRAD, XA, E, E, acc);
+      reduce_epi<M>(d, acc, [&](int r, int, float v) {
+        bcast(XB + r * E + col, v);
+        if (d.grow0 + r < d.Rtot) ws[P.off_dv + static_cast<size_t>(d.grow0 + r) * E + col] = v;
+      });
+    }
+    cluster_sync();
+    {
+      float acc[M];
+      gemm_block<M>(d, T_DGRAD, XB, E, E, acc);
+      reduce_epi<M>(d, acc, [&](int r, int, float v) {
+        if (d.grow0 + r < d.Rtot) P.dpooled[static_cast<size_t>(d.grow0 + r) * E + col] = v;
+      });
+    }
+  }
+  cp_async_wait<0>();
+  cluster_sync();                         // no CTA exits while a peer may still store into its shared memory
+}
+
+// ------------------------------------------------------------------------------------------------ pre kernels
+struct PreParams {
+  Program prog;
+  const float* omics[MPO_Q];
+  int omic_dims[MPO_Q];
+  const float* b1[MPO_Q];
+  const float* b2[MPO_Q];
+  const float* bq;
+  float* ws;
+  float *qp, *qk;
+  const float* dqk;
+  int off_snn_h[MPO_Q], off_G, off_dqp, off_dG, off_snn_dz1[MPO_Q], off_snn_dz2[MPO_Q];
+  DropSpec d_alpha;
+  int B;
+};
+static_assert(sizeof(PreParams) <= 4000, "kernel parameter space");
+
+template <int S>
+struct PreSmem {
+  static constexpr int M = 6 * S;
+  static constexpr int ring = 0;
+  static constexpr int XO = ring + NSTAGE * CHUNK;       // [6][S][OMIC_LD] omic inputs
+  static constexpr int H1 = XO + MPO_Q * S * OMIC_LD;    // [6][S][256]
+  static constexpr int G = H1 + MPO_Q * S * E;           // [M][256]
+  static constexpr int QP = G + M * E;                   // [M][256]
+  static constexpr int RED = QP + M * E;
+  static constexpr int total = RED + NW * M * 32;
+};
+
+// SNN encoders (mcat.py:32-45,90-92), query in-projection (rows 0..255 of co_attention.in_proj) and the key fold
+// qk = W_k^T q / 16
+template <int S>
+__global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreParams P) {
+  constexpr int M = 6 * S;
+  using L = PreSmem<S>;
+  extern __shared__ __align__(16) float sm[];
+  Dev d;
+  d.rank = cluster_rank();
+  d.t = threadIdx.x; d.lane = d.t & 31; d.warp = d.t >> 5;
+  d.s0 = (blockIdx.x / CL) * S;
+  d.B = P.B; d.grow0 = d.s0 * 6; d.Rtot = 6 * P.B;
+  d.seedv = drop_seed(P.d_alpha);
+  d.ws = P.ws;
+  d.red = sm + L::RED;
+  d.pipe.init(P.prog, sm + L::ring, d.rank, d.t);
+  float* ws = P.ws;
+  float *XO = sm + L::XO, *H1 = sm + L::H1, *G = sm + L::G, *QP = sm + L::QP;
+  const int col = d.rank * 32 + d.lane;
+  for (int i = 0; i < MPO_Q; ++i) {
+    const int dim = P.omic_dims[i];
+    for (int j = d.t; j < S * dim; j += NT) {
+      const int s = j / dim, c = j - s * dim;
+      XO[(i * S + s) * OMIC_LD + c] = (d.s0 + s < d.B) ? __ldg(P.omics[i] + static_cast<size_t>(d.s0 + s) * dim + c) : 0.f;
+    }
+  }
+  cluster_sync();
+  for (int i = 0; i < MPO_Q; ++i) {
+    float accs[S];
+    const float bias = __ldg(P.b1[i] + col);
+    const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * i);
+    gemm_block<S>(d, T_FWD, XO + i * S * OMIC_LD, OMIC_LD, P.omic_dims[i], accs);
+    reduce_epi<S>(d, accs, [&](int s, int, float v) {
+      v += bias;
+      v = v > 0.f ? v : expm1f(v);
+      const int slide = d.s0 + s;
+      if (ds.thr != 0) v = drop_fwd(v, ds, d.seedv, static_cast<uint32_t>(slide) * E + col);
+      bcast(H1 + (i * S + s) * E + col, v);
+      if (slide < d.B) ws[P.off_snn_h[i] + static_cast<size_t>(slide) * E + col] = v;
+    });
+  }
+  cluster_sync();
+  for (int i = 0; i < MPO_Q; ++i) {
+    float accs[S];
+    const float bias = __ldg(P.b2[i] + col);
+    const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * i + 1);
+    gemm_block<S>(d, T_FWD, H1 + i * S * E, E, E, accs);
+    reduce_epi<S>(d, accs, [&](int s, int, float v) {
+      v += bias;
+      v = v > 0.f ? v : expm1f(v);
+      const int slide = d.s0 + s;
+      if (ds.thr != 0) v = drop_fwd(v, ds, d.seedv, static_cast<uint32_t>(slide) * E + col);
+      bcast(G + (s * 6 + i) * E + col, v);
+      if (slide < d.B) ws[P.off_G + static_cast<size_t>(slide * 6 + i) * E + col] = v;
+    });
+  }
+  cluster_sync();
+  {
+    float acc[M];
+    const float bias = __ldg(P.bq + col);
+    gemm_block<M>(d, T_FWD, G, E, E, acc);
+    reduce_epi<M>(d, acc, [&](int r, int, float v) {
+      v += bias;
+      bcast(QP + r * E + col, v);
+      if (d.grow0 + r < d.Rtot) P.qp[static_cast<size_t>(d.grow0 + r) * E + col] = v;
+    });
+  }
+  cluster_sync();
+  {
+    float acc[M];
+    gemm_block<M>(d, T_DGRAD, QP, E, E, acc);
+    reduce_epi<M>(d, acc, [&](int r, int, float v) {
+      if (d.grow0 + r < d.Rtot) P.qk[static_cast<size_t>(d.grow0 + r) * E + col] = v * (1.f / 16.f);
+    });
+  }
+  cp_async_wait<0>();
+  cluster_sync();
+}
+
+// autograd of pre_kernel: fold, query projection (+ the omic branch's dG), SNN data gradients
+template <int S>
+__global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ PreParams P) {
+  constexpr int M = 6 * S;
+  using L = PreSmem<S>;
+  extern __shared__ __align__(16) float sm[];
+  Dev d;
+  d.rank = cluster_rank();
+  d.t = threadIdx.x; d.lane = d.t & 31; d.warp = d.t >> 5;
+  d.s0 = (blockIdx.x / CL) * S;
+  d.B = P.B; d.grow0 = d.s0 * 6; d.Rtot = 6 * P.B;
+  d.seedv = drop_seed(P.d_alpha);
+  d.ws = P.ws;
+  d.red = sm + L::RED;
+  d.pipe.init(P.prog, sm + L::ring, d.rank, d.t);
+  float* ws = P.ws;
+  float *XA = sm + L::G, *XB = sm + L::QP, *DZ2 = sm + L::H1;     // DZ2: [M][256], row s*6+i
+  const int col = d.rank * 32 + d.lane;
+  load_rows<M>(d, XA, P.dqk, d.grow0, d.Rtot);
+  cluster_sync();
+  // dq[r][e] = sum_d dqk[r][d] W_k[e][d] / 16
+  {
+    float acc[M];
+    gemm_block<M>(d, T_FWD, XA, E, E, acc);
+    reduce_epi<M>(d, acc, [&](int r, int, float v) {
+      v *= (1.f / 16.f);
+      bcast(XB + r * E + col, v);
+      if (d.grow0 + r < d.Rtot) ws[P.off_dqp + static_cast<size_t>(d.grow0 + r) * E + col] = v;
+    });
+  }
+  cluster_sync();
+  // dG = dq W_q + (omic branch), then through the second SNN layer's ELU + AlphaDropout
+  {
+    float acc[M];
+    float dg0[(M + NW - 1) / NW], gv[(M + NW - 1) / NW];
+#pragma unroll
+    for (int i = 0; i < (M + NW - 1) / NW; ++i) {
+      const int r = d.warp + NW * i, grow = d.grow0 + r;
+      const bool valid = r < M && grow < d.Rtot;
+      dg0[i] = valid ? __ldcg(ws + P.off_dG + static_cast<size_t>(grow) * E + col) : 0.f;
+      gv[i] = valid ? __ldcg(ws + P.off_G + static_cast<size_t>(grow) * E + col) : 0.f;
+    }
+    gemm_block<M>(d, T_DGRAD, XB, E, E, acc);
+    reduce_epi<M>(d, acc, [&](int r, int i, float v) {
+      v += dg0[i];
+      const int s = r / 6, om = r - s * 6, slide = d.s0 + s;
+      const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * om + 1);
+      float y = gv[i];
+      if (ds.thr != 0) { v *= drop_grad(ds, d.seedv, static_cast<uint32_t>(slide) * E + col); y = drop_invert(y, ds); }
+      v *= (y > 0.f ? 1.f : y + 1.f);
+      bcast(DZ2 + r * E + col, v);
+      if (slide < d.B) ws[P.off_snn_dz2[om] + static_cast<size_t>(slide) * E + col] = v;
+    });
+  }
+  cluster_sync();
+  for (int i = 0; i < MPO_Q; ++i) {
+    float accs[S];
+    float hv[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      hv[s] = (d.s0 + s < d.B) ? __ldcg(ws + P.off_snn_h[i] + static_cast<size_t>(d.s0 + s) * E + col) : 0.f;
+    const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * i);
+    gemm_block<S>(d, T_DGRAD, DZ2 + i * E, 6 * E, E, accs);
+    reduce_epi<S>(d, accs, [&](int s, int, float v) {
+      const int slide = d.s0 + s;
+      float y = hv[s];
+      if (ds.thr != 0) { v *= drop_grad(ds, d.seedv, static_cast<uint32_t>(slide) * E + col); y = drop_invert(y, ds); }
+      v *= (y > 0.f ? 1.f : y + 1.f);
+      if (slide < d.B) ws[P.off_snn_dz1[i] + static_cast<size_t>(slide) * E + col] = v;
+    });
+  }
+  cp_async_wait<0>();
+  cluster_sync();
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradients
+// kind 0: gw[o][i] += alpha * sum_r dz[r][o] x[r][i]  and  gb[o] += sum_r dz[r][o]     (64 x 64 tiles)
+// kind 1: LayerNorm: gw[c] += sum_r dz[r][c] x[r][c]  and  gb[c] += sum_r dz[r][c]     (64-column tiles)
+struct WJob {
+  const float* dz;
+  const float* x;
+  float* gw;
+  float* gb;
+  int lddz, ldx, out, in, rows, tile0, kind;
+  float alpha;
+};
+constexpr int MAX_JOBS = 60;
+struct WParams { WJob job[MAX_JOBS]; int njobs; int ntiles; };
+static_assert(sizeof(WParams) <= 4000, "kernel parameter space");
+
+__global__ void __launch_bounds__(256) wgrad_kernel(const __grid_constant__ WParams P) {
+  __shared__ __align__(16) float As[2][32][64 + 4];
+  __shared__ __align__(16) float Bs[2][32][64 + 4];
+  const int t = threadIdx.x;
+  int j = 0;
+  while (j + 1 < P.njobs && static_cast<int>(blockIdx.x) >= P.job[j + 1].tile0) ++j;
+  const WJob& J = P.job[j];
+  const int tile = blockIdx.x - J.tile0;
+  if (J.kind == 1) {
+    const int c = tile * 64 + (t & 63), part = t >> 6;       // 4 row groups
+    float s1 = 0.f, s2 = 0.f;
+    if (c < J.out)
+      for (int r = part; r < J.rows; r += 4) {
+        const float g = __ldcg(J.dz + static_cast<size_t>(r) * J.lddz + c);
+        s1 = fmaf(g, __ldcg(J.x + static_cast<size_t>(r) * J.ldx + c), s1);
+        s2 += g;
+      }
+    As[0][part][t & 63] = s1;
+    Bs[0][part][t & 63] = s2;
+    __syncthreads();
+    if (part == 0 && c < J.out) {
+      J.gw[c] += As[0][0][t] + As[0][1][t] + As[0][2][t] + As[0][3][t];
+      J.gb[c] += Bs[0][0][t] + Bs[0][1][t] + Bs[0][2][t] + Bs[0][3][t];
+    }
+    return;
+  }
+  const int tiles_in = (J.in + 63) / 64;
+  const int o0 = (tile / tiles_in) * 64, i0 = (tile % tiles_in) * 64;
+  const int tx = t & 15, ty = t >> 4;            // outputs (o0 + ty*4 .. +3, i0 + tx*4 .. +3)
+  const int lc = t & 63, lr = t >> 6;            // staging: column lc, rows lr + 4 q
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  float bsum = 0.f;                              // bias gradient of column o0 + lc (threads with lr == 0 finish it)
+  float ra[8], rb[8];
+  auto load = [&](int r0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int r = r0 + lr + 4 * q;
+      ra[q] = (r < J.rows && o0 + lc < J.out) ? __ldcg(J.dz + static_cast<size_t>(r) * J.lddz + o0 + lc) : 0.f;
+      rb[q] = (r < J.rows && i0 + lc < J.in) ? __ldcg(J.x + static_cast<size_t>(r) * J.ldx + i0 + lc) : 0.f;
+    }
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { As[buf][lr + 4 * q][lc] = ra[q]; Bs[buf][lr + 4 * q][lc] = rb[q]; }
+  };
+  const int nsteps = (J.rows + 31) / 32;
+  load(0);
+  store(0);
+  __syncthreads();
+  for (int s = 0; s < nsteps; ++s) {
+    const int buf = s & 1;
+    if (s + 1 < nsteps) load((s + 1) * 32);
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) acc[aa][bb] = fmaf(av[aa], bv[bb], acc[aa][bb]);
+    }
+    if (J.gb != nullptr && i0 == 0 && t < 64) {
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) bsum += As[buf][kk][t];
+    }
+    if (s + 1 < nsteps) store(buf ^ 1);
+    __syncthreads();
+  }
+  if (J.gb != nullptr && i0 == 0 && t < 64 && o0 + t < J.out) J.gb[o0 + t] += bsum;
+#pragma unroll
+  for (int aa = 0; aa < 4; ++aa) {
+    const int o = o0 + ty * 4 + aa;
+    if (o >= J.out) continue;
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+      const int i = i0 + tx * 4 + bb;
+      if (i < J.in) J.gw[static_cast<size_t>(o) * J.in + i] += J.alpha * acc[aa][bb];
+    }
+  }
+}
+
+struct JobBuilder {
+  WParams& p;
+  bool ok = true;
+  void push(int kind, const float* dz, int lddz, const float* x, int ldx, float* gw, float* gb, int out, int in, int rows,
+            float alpha) {
+    if (gw == nullptr) return;
+    if (p.njobs >= MAX_JOBS) { ok = false; return; }
+    WJob& j = p.job[p.njobs++];
+    j.dz = dz; j.x = x; j.gw = gw; j.gb = gb; j.lddz = lddz; j.ldx = ldx; j.out = out; j.in = in; j.rows = rows;
+    j.kind = kind; j.alpha = alpha; j.tile0 = p.ntiles;
+    p.ntiles += kind == 1 ? (out + 63) / 64 : ((out + 63) / 64) * ((in + 63) / 64);
+  }
+  void lin(const float* dz, int lddz, const float* x, int ldx, const mpo_lin& L, int out, int in, int rows, float alpha = 1.f) {
+    push(0, dz, lddz, x, ldx, L.gw, L.gb, out, in, rows, alpha);
+  }
+  void norm(const float* dy, const float* xh, const mpo_norm& N, int rows) { push(1, dy, E, xh, E, N.gg, N.gb, E, E, rows, 1.f); }
+};
+
+// ------------------------------------------------------------------------------------------------ host side
+DropSpec host_drop(const mpo_tail_io* io, float p, bool alpha) {
+  DropSpec d = {};
+  if (io->drop_p <= 0.f || p <= 0.f) return d;
+  d.thr = static_cast<uint32_t>(p * 256.f + 0.5f);
+  if (d.thr == 0) return d;
+  const float pe = static_cast<float>(d.thr) / 256.f;
+  d.seed = io->seed; d.seed_dev = io->seed_dev; d.alpha = alpha ? 1 : 0;
+  if (alpha) {
+    d.scale = 1.f / sqrtf((1.f - pe) * (1.f + pe * kAlphaPrime * kAlphaPrime));
+    d.shift = -d.scale * kAlphaPrime * pe;
+  } else {
+    d.scale = 1.f / (1.f - pe);
+    d.shift = 0.f;
+  }
+  return d;
+}
+
+template <typename K, typename PT>
+cudaError_t launch_cluster(K kern, const PT& prm, int nclusters, size_t smem_bytes, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(nclusters * CL));
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, prm);
+  count_launch();
+  return e;
+}
+
+int slides_per_cluster(int B) {
+  const char* env = getenv("MPO_TAIL_FUSED_S");
+  const int forced = env ? atoi(env) : 0;
+  if (forced == 1 || forced == 2) return forced;
+  return B >= 24 ? 2 : 1;        // 32 slides -> 16 clusters = 128 CTAs; small batches spread over more SMs
+}
+
+bool eligible(const mpo_model* m, const mpo_tail_io* io) {
+  const char* env = getenv("MPO_TAIL_FUSED");        // read on every call: tests flip it to compare the two tails
+  if (env != nullptr && atoi(env) == 0) return false;
+  if (m->variant != MPO_VARIANT_MCAT || m->fusion != MPO_FUSION_CONCAT) return false;
+  if (m->n_classes > MAXK || io->suma != nullptr) return false;
+  for (int i = 0; i < MPO_Q; ++i)
+    if (m->omic_dims[i] % 4 != 0 || m->omic_dims[i] > OMIC_LD || m->omic_dims[i] < 4) return false;
+  return true;
+}
+
+static int fin(cudaError_t e, const char* where) {
+  if (e == cudaSuccess) e = cudaGetLastError();
+  return check_cuda(e, where);
+}
+
+static void fill_pre(const mpo_model* m, const mpo_tail_io* io, const Ws& w, PreParams& P) {
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < MPO_Q; ++i) {
+    P.omics[i] = io->omics[i]; P.omic_dims[i] = m->omic_dims[i];
+    P.b1[i] = m->snn[i][0].b; P.b2[i] = m->snn[i][1].b;
+    P.off_snn_h[i] = static_cast<int>(w.snn_h[i]);
+    P.off_snn_dz1[i] = static_cast<int>(w.snn_dz1[i]); P.off_snn_dz2[i] = static_cast<int>(w.snn_dz2[i]);
+  }
+  P.bq = m->coattn_in.b;
+  P.ws = io->ws; P.qp = io->qp; P.qk = io->qk; P.dqk = io->dqk;
+  P.off_G = static_cast<int>(w.G); P.off_dqp = static_cast<int>(w.dqp); P.off_dG = static_cast<int>(w.dG);
+  P.d_alpha = host_drop(io, io->drop_p, true);
+  P.B = io->num_slides;
+}
+
+int pre_fwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t st) {
+  static PreParams P;
+  fill_pre(m, io, w, P);
+  ProgBuilder pb{P.prog};
+  for (int i = 0; i < MPO_Q; ++i) pb.fwd(m->snn[i][0].w, m->omic_dims[i], m->omic_dims[i]);
+  for (int i = 0; i < MPO_Q; ++i) pb.fwd(m->snn[i][1].w, E, E);
+  pb.fwd(m->coattn_in.w, E, E);
+  pb.dgrad(m->coattn_in.w + static_cast<size_t>(E) * E, E, E);
+  if (!pb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
+  const int B = io->num_slides, S = slides_per_cluster(B), ncl = (B + S - 1) / S;
+  cudaError_t e = S == 2 ? launch_cluster(pre_kernel<2>, P, ncl, PreSmem<2>::total * sizeof(float), st)
+                         : launch_cluster(pre_kernel<1>, P, ncl, PreSmem<1>::total * sizeof(float), st);
+  return fin(e, "pre_kernel (fused tail)");
+}
+
+static int launch_wgrad(const WParams& W, cudaStream_t st) {
+  if (W.ntiles == 0) return MPO_OK;
+  wgrad_kernel<<<W.ntiles, 256, 0, st>>>(W);
+  count_launch();
+  return fin(cudaSuccess, "wgrad_kernel (fused tail)");
+}
+
+int pre_bwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t st) {
+  static PreParams P;
+  fill_pre(m, io, w, P);
+  ProgBuilder pb{P.prog};
+  pb.fwd(m->coattn_in.w + static_cast<size_t>(E) * E, E, E);
+  pb.dgrad(m->coattn_in.w, E, E);
+  for (int i = 0; i < MPO_Q; ++i) pb.dgrad(m->snn[i][1].w, E, E);
+  if (!pb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
+  const int B = io->num_slides, R = 6 * B, S = slides_per_cluster(B), ncl = (B + S - 1) / S;
+  cudaError_t e = S == 2 ? launch_cluster(pre_bwd_kernel<2>, P, ncl, PreSmem<2>::total * sizeof(float), st)
+                         : launch_cluster(pre_bwd_kernel<1>, P, ncl, PreSmem<1>::total * sizeof(float), st);
+  int rc = fin(e, "pre_bwd_kernel (fused tail)");
+  if (rc) return rc;
+  static WParams W;
+  memset(&W, 0, sizeof(W));
+  JobBuilder jb{W};
+  float* ws = io->ws;
+  for (int i = 0; i < MPO_Q; ++i) {
+    jb.lin(ws + w.snn_dz1[i], E, io->omics[i], m->omic_dims[i], m->snn[i][0], E, m->omic_dims[i], B);
+    jb.lin(ws + w.snn_dz2[i], E, ws + w.snn_h[i], E, m->snn[i][1], E, E, B);
+  }
+  // query block of co_attention.in_proj, and the key block through the fold: dW_k[e][d] += sum_r q[r][e] dqk[r][d] / 16
+  mpo_lin Lq = m->coattn_in;
+  jb.lin(ws + w.dqp, E, ws + w.G, E, Lq, E, E, R);
+  mpo_lin Lk = {nullptr, nullptr, m->coattn_in.gw ? m->coattn_in.gw + static_cast<size_t>(E) * E : nullptr, nullptr};
+  jb.lin(io->qp, E, io->dqk, E, Lk, E, E, R, 1.f / 16.f);
+  if (!jb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: job table overflow");
+  return launch_wgrad(W, st);
+}
+
+int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, const LossArgs* loss, const float* dhaz,
+         const float* dS, const float* dY, cudaStream_t st) {
+  static PathParams P;
+  memset(&P, 0, sizeof(P));
+  const int B = io->num_slides, R = 6 * B, K = m->n_classes;
+  const mpo_encoder_layer* enc[4] = {&m->path_tr[0], &m->path_tr[1], &m->omic_tr[0], &m->omic_tr[1]};
+  const long long enc_x[4] = {w.hc, w.enc[0].y2, w.G, w.enc[2].y2};
+  for (int e = 0; e < 4; ++e) {
+    const mpo_encoder_layer& L = *enc[e];
+    P.enc[e] = EncP{L.in_proj.w, L.in_proj.b, L.out_proj.w, L.out_proj.b, L.linear1.w, L.linear1.b, L.linear2.w,
+                    L.linear2.b, L.norm1.g, L.norm1.b, L.norm2.g, L.norm2.b};
+    const tailws::EncBuf& b = w.enc[e];
+    const Ws::FzEnc& f = w.fz_enc[e];
+    P.encw[e] = EncW{(int)enc_x[e], (int)b.qkv, (int)b.probs, (int)b.ctx, (int)b.y1, (int)b.xh1, (int)b.rs1, (int)b.f,
+                     (int)b.y2, (int)b.xh2, (int)b.rs2, (int)f.dy2, (int)f.df2, (int)f.df, (int)f.dy1, (int)f.dsa,
+                     (int)f.dqkv};
+  }
+  const mpo_pool_head* pool[2] = {&m->path_pool, &m->omic_pool};
+  for (int p = 0; p < 2; ++p) {
+    const mpo_pool_head& H = *pool[p];
+    P.pool[p] = PoolP{H.att_a.w, H.att_a.b, H.att_b.w, H.att_b.b, H.att_c.w, H.att_c.b, H.rho.w, H.rho.b,
+                      (flags & F_BWD) ? H.att_c.gw : nullptr, (flags & F_BWD) ? H.att_c.gb : nullptr};
+    P.poolw[p] = PoolW{(int)w.pool[p].a, (int)w.pool[p].b, (int)w.pool[p].w, (int)w.pool[p].hp, (int)w.fz_pool[p].dzr,
+                       (int)w.fz_pool[p].da, (int)w.fz_pool[p].db};
+  }
+  const float* Wv = m->coattn_in.w + static_cast<size_t>(2 * E) * E;
+  P.wv = Wv; P.bv = m->coattn_in.b + 2 * E;
+  P.wo = m->coattn_out.w; P.bo = m->coattn_out.b;
+  P.wf0 = m->fusion0.w; P.bf0 = m->fusion0.b; P.wf2 = m->fusion2.w; P.bf2 = m->fusion2.b;
+  P.wcl = m->classifier.w; P.bcl = m->classifier.b;
+  P.ws = io->ws; P.pooled = io->pooled; P.dpooled = io->dpooled;
+  P.hazards = io->hazards; P.S = io->S; P.Y = io->Y; P.att_path = io->att_path; P.att_omic = io->att_omic;
+  P.off_G = (int)w.G; P.off_v = (int)w.v; P.off_hc = (int)w.hc; P.off_cat = (int)w.cat; P.off_z1 = (int)w.z1;
+  P.off_z2 = (int)w.z2; P.off_logits = (int)w.logits; P.off_dlogits = (int)w.dlogits; P.off_dz1 = (int)w.dz1;
+  P.off_dz2 = (int)w.dz2; P.off_dhc = (int)w.dhc; P.off_dv = (int)w.dv; P.off_dG = (int)w.dG;
+  if (flags & F_LOSS) {
+    P.loss_kind = loss->kind; P.loss_alpha = loss->alpha; P.loss_eps = loss->eps; P.grad_scale = loss->grad_scale;
+    P.label = loss->label; P.censor = loss->censor; P.loss = loss->loss; P.dhaz_out = loss->dhaz; P.dS_out = loss->dS;
+  }
+  P.dhaz_in = dhaz; P.dS_in = dS; P.dY_in = dY;
+  P.d_model = host_drop(io, io->drop_p, false);
+  P.d_quarter = host_drop(io, 0.25f, false);        // AttentionNetGated hard-codes p = 0.25 (blocks.py:34-36)
+  P.B = B; P.K = K; P.flags = flags;
+
+  ProgBuilder pb{P.prog};
+  auto enc_f = [&](const mpo_encoder_layer& L) {
+    pb.fwd(L.in_proj.w, E, E, 3, 32, E);
+    pb.fwd(L.out_proj.w, E, E);
+    pb.fwd(L.linear1.w, E, E, 2, 64, 32);
+    pb.fwd(L.linear2.w, FF, FF);
+  };
+  auto enc_b = [&](const mpo_encoder_layer& L) {
+    pb.dgrad(L.linear2.w, FF, E, 2, 64, 32);
+    pb.dgrad(L.linear1.w, E, FF);
+    pb.dgrad(L.out_proj.w, E, E);
+    pb.dgrad(L.in_proj.w, E, 3 * E);
+  };
+  auto pool_f = [&](const mpo_pool_head& H) { pb.fwd(H.att_a.w, E, E); pb.fwd(H.att_b.w, E, E); pb.fwd(H.rho.w, E, E); };
+  auto pool_b = [&](const mpo_pool_head& H) { pb.dgrad(H.rho.w, E, E); pb.dgrad(H.att_a.w, E, E); pb.dgrad(H.att_b.w, E, E); };
+  if (flags & F_FWD) {
+    enc_f(m->omic_tr[0]); enc_f(m->omic_tr[1]); pool_f(m->omic_pool);
+    pb.fwd(Wv, E, E); pb.fwd(m->coattn_out.w, E, E);
+    enc_f(m->path_tr[0]); enc_f(m->path_tr[1]); pool_f(m->path_pool);
+    pb.fwd(m->fusion0.w, 2 * E, 2 * E); pb.fwd(m->fusion2.w, E, E);
+  }
+  if (flags & F_BWD) {
+    pb.dgrad(m->fusion2.w, E, E);
+    pb.dgrad(m->fusion0.w, 2 * E, E, 2, 64, 32);
+    pool_b(m->omic_pool); enc_b(m->omic_tr[1]); enc_b(m->omic_tr[0]);
+    pool_b(m->path_pool); enc_b(m->path_tr[1]); enc_b(m->path_tr[0]);
+    pb.dgrad(m->coattn_out.w, E, E); pb.dgrad(Wv, E, E);
+  }
+  if (!pb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
+  const int S = slides_per_cluster(B), ncl = (B + S - 1) / S;
+  cudaError_t e = S == 2 ? launch_cluster(path_kernel<2>, P, ncl, PathSmem<2>::total * sizeof(float), st)
+                         : launch_cluster(path_kernel<1>, P, ncl, PathSmem<1>::total * sizeof(float), st);
+  int rc = fin(e, "path_kernel (fused tail)");
+  if (rc || !(flags & F_BWD)) return rc;
+
+  static WParams W;
+  memset(&W, 0, sizeof(W));
+  JobBuilder jb{W};
+  float* ws = io->ws;
+  for (int e4 = 0; e4 < 4; ++e4) {
+    const mpo_encoder_layer& L = *enc[e4];
+    const tailws::EncBuf& b = w.enc[e4];
+    const Ws::FzEnc& f = w.fz_enc[e4];
+    jb.lin(ws + f.dqkv, 3 * E, ws + enc_x[e4], E, L.in_proj, 3 * E, E, R);
+    jb.lin(ws + f.dsa, E, ws + b.ctx, E, L.out_proj, E, E, R);
+    jb.lin(ws + f.df, FF, ws + b.y1, E, L.linear1, FF, E, R);
+    jb.lin(ws + f.df2, E, ws + b.f, FF, L.linear2, E, FF, R);
+    jb.norm(ws + f.dy1, ws + b.xh1, L.norm1, R);
+    jb.norm(ws + f.dy2, ws + b.xh2, L.norm2, R);
+  }
+  const long long tok[2] = {w.enc[1].y2, w.enc[3].y2};
+  for (int p = 0; p < 2; ++p) {
+    const mpo_pool_head& H = *pool[p];
+    jb.lin(ws + w.fz_pool[p].da, E, ws + tok[p], E, H.att_a, E, E, R);
+    jb.lin(ws + w.fz_pool[p].db, E, ws + tok[p], E, H.att_b, E, E, R);
+    jb.lin(ws + w.fz_pool[p].dzr, E, ws + w.pool[p].hp, E, H.rho, E, E, B);
+  }
+  jb.lin(ws + w.dz1, E, ws + w.cat, 2 * E, m->fusion0, E, 2 * E, B);
+  jb.lin(ws + w.dz2, E, ws + w.z1, E, m->fusion2, E, E, B);
+  jb.lin(ws + w.dlogits, K, ws + w.z2, E, m->classifier, K, E, B);
+  jb.lin(ws + w.dhc, E, ws + w.v, E, m->coattn_out, E, E, R);
+  mpo_lin Lv = {nullptr, nullptr, m->coattn_in.gw ? m->coattn_in.gw + static_cast<size_t>(2 * E) * E : nullptr,
+                m->coattn_in.gb ? m->coattn_in.gb + 2 * E : nullptr};
+  jb.lin(ws + w.dv, E, io->pooled, E, Lv, E, E, R);
+  if (!jb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: job table overflow");
+  return launch_wgrad(W, st);
+}
+
+}  // namespace fused
+}  // namespace mpo

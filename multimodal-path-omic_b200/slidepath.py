@@ -245,7 +245,7 @@ class SlideEngine:
 
     # -- forward
     def forward(self, model, bag, omics, train=False, save_for_backward=True, seed=None, reuse_ws=False,
-                after_bag=None, st=None):
+                after_bag=None, st=None, post=None):
         """bag: PackedBag of B slides; omics: 6 tensors [B, d_i] float32 on the GPU.  `st` reuses the buffers of an
         earlier alloc_state() (static addresses: needed for CUDA-graph capture)."""
         bnd = self.binding
@@ -291,7 +291,10 @@ class SlideEngine:
                            seed_dev=st.seed_dev if train else None)
         if after_bag is not None:        # e.g. the cross-GPU log-sum-exp combine of a patch-sharded bag (dp.py)
             after_bag(st)
-        _lib.call("mpo_tail_post_fwd", ctypes.byref(model), ctypes.byref(io), s)
+        if post is not None:             # training step: post forward + loss + post backward as one C-ABI call
+            post(st, io, s)
+        else:
+            _lib.call("mpo_tail_post_fwd", ctypes.byref(model), ctypes.byref(io), s)
         return st
 
     def attention_map(self, st):
@@ -340,8 +343,9 @@ class SlideEngine:
                       gw, gb, ctypes.c_float(st.drop_p), s)
 
     # -- backward
-    def backward(self, model, st, dhaz, dS, dY):
-        """model must carry gradient pointers; they are accumulated into."""
+    def backward(self, model, st, dhaz, dS, dY, post_done=False):
+        """model must carry gradient pointers; they are accumulated into.  post_done: the post stage's backward
+        already ran inside mpo_tail_post_step (st.dpooled is filled)."""
         dev = st.bag.x.device
         f32 = dict(dtype=torch.float32, device=dev)
         if st.dpooled is None:
@@ -358,8 +362,9 @@ class SlideEngine:
                 return None
             return g.detach().to(torch.float32).reshape(st.B, -1).contiguous()
 
-        dhaz, dS, dY = prep(dhaz), prep(dS), prep(dY)
-        _lib.call("mpo_tail_post_bwd", ctypes.byref(model), ctypes.byref(io), _ptr(dhaz), _ptr(dS), _ptr(dY), s)
+        if not post_done:
+            dhaz, dS, dY = prep(dhaz), prep(dS), prep(dY)
+            _lib.call("mpo_tail_post_bwd", ctypes.byref(model), ctypes.byref(io), _ptr(dhaz), _ptr(dS), _ptr(dY), s)
         self.bag_backward_only(model, st)
         io = self._io(st)
         _lib.call("mpo_tail_pre_bwd", ctypes.byref(model), ctypes.byref(io), s)
@@ -478,17 +483,18 @@ class BatchTrainer:
         eng = self.engine
         if st is not None and st.seed_dev is not None and train:
             _lib.call("mpo_advance_seed", _ptr(st.seed_dev), _stream())
-        st = eng.forward(self.model, bag, omics, train=train, save_for_backward=True, seed=seed, reuse_ws=True, st=st)
-        B, K = st.B, eng.binding.n_classes
-        if getattr(st, "loss", None) is None:
-            dev = bag.x.device
-            st.loss = torch.empty(B, dtype=torch.float32, device=dev)
-            st.dhz = torch.empty((B, K), dtype=torch.float32, device=dev)
-            st.dS = torch.empty((B, K), dtype=torch.float32, device=dev)
-        _lib.call("mpo_surv_loss", self.kind, _ptr(st.hazards), _ptr(st.S), _ptr(labels), _ptr(censor),
-                  ctypes.c_float(self.alpha), ctypes.c_float(self.eps), ctypes.c_float(1.0 / self.grad_acc_step),
-                  _ptr(st.loss), _ptr(st.dhz), _ptr(st.dS), B, K, _stream())
-        eng.backward(self.model, st, st.dhz, st.dS, None)
+        if st is None:
+            st = eng.alloc_state(self.model, bag, save_for_backward=True, reuse_ws=True, with_backward_buffers=True)
+
+        def post(st_, io, s):
+            # post forward + loss (models/loss.py) + post backward in one call: one cluster kernel on the fused path
+            _lib.call("mpo_tail_post_step", ctypes.byref(self.model), ctypes.byref(io), self.kind, _ptr(labels),
+                      _ptr(censor), ctypes.c_float(self.alpha), ctypes.c_float(self.eps),
+                      ctypes.c_float(1.0 / self.grad_acc_step), _ptr(st_.loss), _ptr(st_.dhz), _ptr(st_.dS), s)
+
+        st = eng.forward(self.model, bag, omics, train=train, save_for_backward=True, seed=seed, reuse_ws=True, st=st,
+                         post=post)
+        eng.backward(self.model, st, st.dhz, st.dS, None, post_done=True)
         return st
 
     def step(self, bag, omics, labels, censor, train=True, seed=None):
