@@ -59,4 +59,7 @@ for k in a:
         bad += 1
     if flag or os.environ.get("CMP_ALL"):
         print("%-60s max|x|=%.3e  rel err %.3e%s%s" % (k, den, err, " NaN" if nan else "", flag))
+        if os.environ.get("CMP_VALS") and flag:
+            print("    ref  ", [float("%.3e" % v) for v in x[:6].tolist()], " nz=%d/%d" % (int((x != 0).sum()), x.numel()))
+            print("    fused", [float("%.3e" % v) for v in y[:6].tolist()], " nz=%d/%d" % (int((y != 0).sum()), y.numel()))
 print("compared %d tensors, %d differ (B=%d N=%d train=%s)" % (len(a), bad, B, N, train))
