@@ -26,7 +26,9 @@ using tailws::Ws;
 
 constexpr int E = 256;
 constexpr int FF = 512;
-constexpr int CL = 8;              // CTAs per cluster (= heads of the encoder layers)
+constexpr int CL = 4;              // CTAs per cluster: 33 clusters of 4 CTAs (215 KB each) fit a B200 at once, only 15 of 8
+constexpr int NV = 8;              // 32-column blocks of a 256-wide layer (= heads of the encoder layers)
+constexpr int NB = NV / CL;        // column blocks (heads) owned by one CTA: "virtual ranks" rank * NB + nb
 constexpr int NT = 256;            // threads per CTA
 constexpr int NW = NT / 32;
 constexpr int KC = 256;            // reduction extent of one weight chunk
@@ -48,7 +50,7 @@ struct Chunk {
   short ld;              // row pitch of W (in_features)
   short kc_type;         // kc (reduction elements, multiple of 4, <= KC) | type << 15
 };
-constexpr int MAX_CHUNKS = 96;
+constexpr int MAX_CHUNKS = 192;
 struct Program { Chunk c[MAX_CHUNKS]; int n; };
 
 struct ProgBuilder {
@@ -387,7 +389,7 @@ struct PathParams {
   DropSpec d_model, d_quarter;
   int B, K, flags;
 };
-static_assert(sizeof(PathParams) <= 4000, "kernel parameter space");
+static_assert(sizeof(PathParams) <= 8000, "kernel parameter space (large kernel parameters, CUDA 12.1+)");
 
 // ------------------------------------------------------------------------------------------------ encoder layer
 // nn.TransformerEncoderLayer(256, nhead 8, ff 512, relu, post-norm) as built at models/mcat/mcat.py:51-53.
@@ -398,31 +400,34 @@ __device__ __forceinline__ void enc_fwd(Dev& d, const EncP& p, const EncW& w, in
   constexpr int M = 6 * S;
   float* ws = d.ws;
   const uint32_t s0 = SITE_ENC + 4 * eidx;      // attention probabilities, dropout1, feed-forward dropout, dropout2
-  // packed in-projection: this CTA computes q, k, v of its head
-  for (int blk = 0; blk < 3; ++blk) {
-    const int col = blk * E + d.rank * 32 + d.lane;
-    const float bias = __ldg(p.b_in + col);
-    gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
-    reduce_epi<M>(d, [&](int r, int, float v) {
-      v += bias;
-      QKVL[r * 96 + blk * 32 + d.lane] = v;
-      const int grow = d.grow0 + r;
-      if (grow < d.Rtot) ws[w.qkv + static_cast<size_t>(grow) * 768 + col] = v;
-    });
-  }
+  // packed in-projection: this CTA computes q, k, v of its heads
+  for (int nb = 0; nb < NB; ++nb)
+    for (int blk = 0; blk < 3; ++blk) {
+      const int col = blk * E + (d.rank * NB + nb) * 32 + d.lane;
+      const float bias = __ldg(p.b_in + col);
+      gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
+      reduce_epi<M>(d, [&](int r, int, float v) {
+        v += bias;
+        QKVL[(nb * M + r) * 96 + blk * 32 + d.lane] = v;
+        const int grow = d.grow0 + r;
+        if (grow < d.Rtot) ws[w.qkv + static_cast<size_t>(grow) * 768 + col] = v;
+      });
+    }
   __syncthreads();
   // 6 x 6 attention of head `rank`, one warp per (slide, query token); lane = head dimension
   {
     const DropSpec da = site_of(dm, s0);
     const float scale = 0.17677669529663687f;   // 1/sqrt(32)
-    for (int r1 = d.warp; r1 < M; r1 += NW) {
+    for (int it = d.warp; it < NB * M; it += NW) {
+      const int nb = it / M, r1 = it - nb * M, head = d.rank * NB + nb;
+      const float* Q = QKVL + nb * M * 96;
       const int sl = r1 / 6, l1 = r1 - sl * 6;
-      const float q = QKVL[r1 * 96 + d.lane];
+      const float q = Q[r1 * 96 + d.lane];
       float sc[6];
       float mx = -INFINITY;
 #pragma unroll
       for (int l2 = 0; l2 < 6; ++l2) {
-        sc[l2] = warp_sum(q * QKVL[(sl * 6 + l2) * 96 + 32 + d.lane]) * scale;
+        sc[l2] = warp_sum(q * Q[(sl * 6 + l2) * 96 + 32 + d.lane]) * scale;
         mx = fmaxf(mx, sc[l2]);
       }
       float sum = 0.f;
@@ -430,24 +435,24 @@ __device__ __forceinline__ void enc_fwd(Dev& d, const EncP& p, const EncW& w, in
       for (int l2 = 0; l2 < 6; ++l2) { sc[l2] = expf(sc[l2] - mx); sum += sc[l2]; }
       const float inv = 1.f / sum;
       const int slide = d.s0 + sl;
-      const uint32_t pi0 = ((static_cast<uint32_t>(slide) * 8 + d.rank) * 6 + l1) * 6;
+      const uint32_t pi0 = ((static_cast<uint32_t>(slide) * 8 + head) * 6 + l1) * 6;
       float c = 0.f;
 #pragma unroll
       for (int l2 = 0; l2 < 6; ++l2) {
         const float pr = sc[l2] * inv;
         if (d.lane == 0 && slide < d.B) ws[w.probs + pi0 + l2] = pr;       // kept before dropout
         const float pd = da.thr != 0 ? drop_fwd(pr, da, d.seedv, pi0 + l2) : pr;
-        c = fmaf(pd, QKVL[(sl * 6 + l2) * 96 + 64 + d.lane], c);
+        c = fmaf(pd, Q[(sl * 6 + l2) * 96 + 64 + d.lane], c);
       }
-      const int col = d.rank * 32 + d.lane;
+      const int col = head * 32 + d.lane;
       bcast(XB + r1 * E + col, c);
       if (slide < d.B) ws[w.ctx + static_cast<size_t>(d.grow0 + r1) * E + col] = c;
     }
   }
   cluster_sync();
   // out-projection + dropout1 + residual
-  {
-    const int col = d.rank * 32 + d.lane;
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float bias = __ldg(p.b_out + col);
     const DropSpec d1 = site_of(dm, s0 + 1);
     gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XB, E);
@@ -461,8 +466,8 @@ __device__ __forceinline__ void enc_fwd(Dev& d, const EncP& p, const EncW& w, in
   ln_fwd_rows<M>(row_ctx(d), XC, XA, p.g1, p.be1, ws + w.y1, ws + w.xh1, ws + w.rs1);
   __syncthreads();
   // feed-forward
-  for (int blk = 0; blk < 2; ++blk) {
-    const int col = d.rank * 64 + blk * 32 + d.lane;
+  for (int blk = 0; blk < 2 * NB; ++blk) {
+    const int col = d.rank * (64 * NB) + blk * 32 + d.lane;
     const float bias = __ldg(p.b1 + col);
     const DropSpec d2 = site_of(dm, s0 + 2);
     gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
@@ -475,8 +480,8 @@ __device__ __forceinline__ void enc_fwd(Dev& d, const EncP& p, const EncW& w, in
     });
   }
   cluster_sync();
-  {
-    const int col = d.rank * 32 + d.lane;
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float bias = __ldg(p.b2 + col);
     const DropSpec d3 = site_of(dm, s0 + 3);
     gemm_block<M, T_FWD, FF>(*d.pipe, smem_addr(d.red), BIG, FF);
@@ -503,8 +508,8 @@ __device__ __forceinline__ void enc_bwd(Dev& d, const EncP& p, const EncW& w, in
   ln_bwd_rows<M>(row_ctx(d), XA, XB, XC, p.g2, ws + w.xh2, ws + w.rs2, ws + w.dy2, ws + w.df2, site_of(dm, s0 + 3));
   __syncthreads();
   // linear2 data gradient with the ReLU / feed-forward-dropout derivative: gradient at linear1's pre-activation
-  for (int blk = 0; blk < 2; ++blk) {
-    const int col = d.rank * 64 + blk * 32 + d.lane;
+  for (int blk = 0; blk < 2 * NB; ++blk) {
+    const int col = d.rank * (64 * NB) + blk * 32 + d.lane;
     const DropSpec d2 = site_of(dm, s0 + 2);
     float fv[(M + NW - 1) / NW];
 #pragma unroll
@@ -523,8 +528,8 @@ __device__ __forceinline__ void enc_bwd(Dev& d, const EncP& p, const EncW& w, in
   }
   cluster_sync();
   // linear1 data gradient + the residual branch: dy1
-  {
-    const int col = d.rank * 32 + d.lane;
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     gemm_block<M, T_DGRAD, FF>(*d.pipe, smem_addr(d.red), BIG, FF);
     reduce_epi<M>(d, [&](int r, int, float v) { bcast(XA + r * E + col, v + XB[r * E + col]); });
   }
@@ -532,10 +537,10 @@ __device__ __forceinline__ void enc_bwd(Dev& d, const EncP& p, const EncW& w, in
   // norm1: dr1 -> XB, gradient of the attention block's output (through dropout1) -> XC
   ln_bwd_rows<M>(row_ctx(d), XA, XB, XC, p.g1, ws + w.xh1, ws + w.rs1, ws + w.dy1, ws + w.dsa, site_of(dm, s0 + 1));
   __syncthreads();
-  // out-projection data gradient: this CTA's 32 columns are its own head
-  {
+  // out-projection data gradient: this CTA's column blocks are its own heads
+  for (int nb = 0; nb < NB; ++nb) {
     gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XC, E);
-    reduce_epi<M>(d, [&](int r, int, float v) { DCTX[r * 32 + d.lane] = v; });
+    reduce_epi<M>(d, [&](int r, int, float v) { DCTX[(nb * M + r) * 32 + d.lane] = v; });
   }
   __syncthreads();
   // attention backward of head `rank`, spread over all warps: (A) dA = dctx v^T as 36 S warp dot products,
@@ -543,28 +548,30 @@ __device__ __forceinline__ void enc_bwd(Dev& d, const EncP& p, const EncW& w, in
   {
     const DropSpec da = site_of(dm, s0);
     const float scale = 0.17677669529663687f;
-    float* PRm = SCR;                 // saved probabilities   [S][6][6]
-    float* DAm = SCR + S * 36;        // dctx . v
-    float* AMG = SCR + 2 * S * 36;    // a * dropout derivative
-    float* DSm = SCR + 3 * S * 36;    // gradient of the scaled scores
-    for (int i = d.t; i < M * 96; i += NT) {
-      const int r = i / 96, c = i - r * 96, grow = d.grow0 + r;
-      QKVL[i] = grow < d.Rtot ? __ldcg(ws + w.qkv + static_cast<size_t>(grow) * 768 + (c >> 5) * 256 + d.rank * 32 + (c & 31)) : 0.f;
+    constexpr int NP = NB * S * 36;   // (head, slide, query, key) entries of this CTA
+    float* PRm = SCR;                 // saved probabilities   [NB][S][6][6]
+    float* DAm = SCR + NP;            // dctx . v
+    float* AMG = SCR + 2 * NP;        // a * dropout derivative
+    float* DSm = SCR + 3 * NP;        // gradient of the scaled scores
+    for (int i = d.t; i < NB * M * 96; i += NT) {
+      const int nb = i / (M * 96), j = i - nb * (M * 96), r = j / 96, c = j - r * 96, grow = d.grow0 + r;
+      QKVL[i] = grow < d.Rtot ? __ldcg(ws + w.qkv + static_cast<size_t>(grow) * 768 + (c >> 5) * 256 +
+                                       (d.rank * NB + nb) * 32 + (c & 31)) : 0.f;
     }
-    for (int p = d.t; p < S * 36; p += NT) {
-      const int sl = p / 36, slide = d.s0 + sl;
-      PRm[p] = slide < d.B ? __ldcg(ws + w.probs + (static_cast<size_t>(slide) * 8 + d.rank) * 36 + (p - sl * 36)) : 0.f;
+    for (int p = d.t; p < NP; p += NT) {
+      const int nb = p / (S * 36), j = p - nb * (S * 36), sl = j / 36, slide = d.s0 + sl;
+      PRm[p] = slide < d.B ? __ldcg(ws + w.probs + (static_cast<size_t>(slide) * 8 + d.rank * NB + nb) * 36 + (j - sl * 36)) : 0.f;
     }
     __syncthreads();
-    for (int p = d.warp; p < S * 36; p += NW) {
-      const int sl = p / 36, q6 = p - sl * 36, l1 = q6 / 6, l2 = q6 - l1 * 6;
-      const float v = warp_sum(DCTX[(sl * 6 + l1) * 32 + d.lane] * QKVL[(sl * 6 + l2) * 96 + 64 + d.lane]);
+    for (int p = d.warp; p < NP; p += NW) {
+      const int nb = p / (S * 36), j = p - nb * (S * 36), sl = j / 36, q6 = j - sl * 36, l1 = q6 / 6, l2 = q6 - l1 * 6;
+      const float v = warp_sum(DCTX[(nb * M + sl * 6 + l1) * 32 + d.lane] * QKVL[(nb * M + sl * 6 + l2) * 96 + 64 + d.lane]);
       if (d.lane == 0) DAm[p] = v;
     }
     __syncthreads();
-    if (d.t < M) {
-      const int sl = d.t / 6, l1 = d.t - sl * 6, p0 = sl * 36 + l1 * 6;
-      const uint32_t pw = ((static_cast<uint32_t>(d.s0 + sl) * 8 + d.rank) * 6 + l1) * 6;
+    if (d.t < NB * M) {
+      const int nb = d.t / M, r = d.t - nb * M, sl = r / 6, l1 = r - sl * 6, p0 = nb * S * 36 + sl * 36 + l1 * 6;
+      const uint32_t pw = ((static_cast<uint32_t>(d.s0 + sl) * 8 + d.rank * NB + nb) * 6 + l1) * 6;
       float a[6], dA[6];
       float dot = 0.f;
 #pragma unroll
@@ -579,28 +586,31 @@ __device__ __forceinline__ void enc_bwd(Dev& d, const EncP& p, const EncW& w, in
       for (int l2 = 0; l2 < 6; ++l2) DSm[p0 + l2] = a[l2] * (dA[l2] - dot) * scale;
     }
     __syncthreads();
-    for (int o = d.warp; o < 3 * M; o += NW) {
-      const int which = o / M, r = o - which * M, sl = r / 6, l = r - sl * 6;
+    for (int o = d.warp; o < NB * 3 * M; o += NW) {
+      const int nb = o / (3 * M), j = o - nb * (3 * M), which = j / M, r = j - which * M, sl = r / 6, l = r - sl * 6;
+      const float* Q = QKVL + nb * M * 96;
+      const float* DC = DCTX + nb * M * 32;
+      const int pb = nb * S * 36 + sl * 36;
       float acc = 0.f;
       if (which == 0) {
 #pragma unroll
-        for (int l2 = 0; l2 < 6; ++l2) acc = fmaf(DSm[sl * 36 + l * 6 + l2], QKVL[(sl * 6 + l2) * 96 + 32 + d.lane], acc);
+        for (int l2 = 0; l2 < 6; ++l2) acc = fmaf(DSm[pb + l * 6 + l2], Q[(sl * 6 + l2) * 96 + 32 + d.lane], acc);
       } else if (which == 1) {
 #pragma unroll
-        for (int l1 = 0; l1 < 6; ++l1) acc = fmaf(DSm[sl * 36 + l1 * 6 + l], QKVL[(sl * 6 + l1) * 96 + d.lane], acc);
+        for (int l1 = 0; l1 < 6; ++l1) acc = fmaf(DSm[pb + l1 * 6 + l], Q[(sl * 6 + l1) * 96 + d.lane], acc);
       } else {
 #pragma unroll
-        for (int l1 = 0; l1 < 6; ++l1) acc = fmaf(AMG[sl * 36 + l1 * 6 + l], DCTX[(sl * 6 + l1) * 32 + d.lane], acc);
+        for (int l1 = 0; l1 < 6; ++l1) acc = fmaf(AMG[pb + l1 * 6 + l], DC[(sl * 6 + l1) * 32 + d.lane], acc);
       }
-      const int col = d.rank * 32 + d.lane;
+      const int col = (d.rank * NB + nb) * 32 + d.lane;
       bcast(BIG + r * 768 + which * 256 + col, acc);
       if (d.grow0 + r < d.Rtot) ws[w.dqkv + static_cast<size_t>(d.grow0 + r) * 768 + which * 256 + col] = acc;
     }
   }
   cluster_sync();
   // in-projection data gradient + the residual branch: dx
-  {
-    const int col = d.rank * 32 + d.lane;
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     gemm_block<M, T_DGRAD, 768>(*d.pipe, smem_addr(d.red), BIG, 768);
     reduce_epi<M>(d, [&](int r, int, float v) {
       v += XB[r * E + col];
@@ -621,43 +631,42 @@ __device__ __forceinline__ void pool_fwd(Dev& d, const PoolP& p, const PoolW& w,
                                          float* PA, float* AW, float* HP, float* CAT) {
   constexpr int M = 6 * S;
   float* ws = d.ws;
-  const int col = d.rank * 32 + d.lane;
-  for (int br = 0; br < 2; ++br) {
-    const float bias = __ldg((br == 0 ? p.ba : p.bb) + col);
-    const DropSpec ds = site_of(dq, SITE_POOL + 2 * pidx + br);
-    float* dst = br == 0 ? AL : BL;
-    const int off = br == 0 ? w.a : w.b;
-    gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
-    reduce_epi<M>(d, [&](int r, int, float v) {
-      v += bias;
-      v = br == 0 ? tanhf(v) : 1.f / (1.f + expf(-v));
-      const int grow = d.grow0 + r;
-      if (ds.thr != 0) v = drop_fwd(v, ds, d.seedv, static_cast<uint32_t>(grow) * E + col);
-      dst[r * 32 + d.lane] = v;
-      if (grow < d.Rtot) ws[off + static_cast<size_t>(grow) * E + col] = v;
-    });
-  }
-  __syncthreads();
-  {
-    const float wc = __ldg(p.wc + col);
-    for (int r = d.warp; r < M; r += NW) {
-      const float v = warp_sum(AL[r * 32 + d.lane] * BL[r * 32 + d.lane] * wc);
-      if (d.lane == 0) bcast(PA + d.rank * M + r, v);
+  for (int nb = 0; nb < NB; ++nb)
+    for (int br = 0; br < 2; ++br) {
+      const int col = (d.rank * NB + nb) * 32 + d.lane;
+      const float bias = __ldg((br == 0 ? p.ba : p.bb) + col);
+      const DropSpec ds = site_of(dq, SITE_POOL + 2 * pidx + br);
+      float* dst = (br == 0 ? AL : BL) + nb * M * 32;
+      const int off = br == 0 ? w.a : w.b;
+      gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
+      reduce_epi<M>(d, [&](int r, int, float v) {
+        v += bias;
+        v = br == 0 ? tanhf(v) : 1.f / (1.f + expf(-v));
+        const int grow = d.grow0 + r;
+        if (ds.thr != 0) v = drop_fwd(v, ds, d.seedv, static_cast<uint32_t>(grow) * E + col);
+        dst[r * 32 + d.lane] = v;
+        if (grow < d.Rtot) ws[off + static_cast<size_t>(grow) * E + col] = v;
+      });
     }
+  __syncthreads();
+  for (int it = d.warp; it < NB * M; it += NW) {
+    const int nb = it / M, r = it - nb * M, vr = d.rank * NB + nb;
+    const float v = warp_sum(AL[(nb * M + r) * 32 + d.lane] * BL[(nb * M + r) * 32 + d.lane] * __ldg(p.wc + vr * 32 + d.lane));
+    if (d.lane == 0) bcast(PA + vr * M + r, v);
   }
   cluster_sync();
   if (d.t < M) {
     float a = 0.f;
 #pragma unroll
-    for (int k = 0; k < CL; ++k) a += PA[k * M + d.t];
+    for (int k = 0; k < NV; ++k) a += PA[k * M + d.t];
     a += __ldg(p.bc);
-    PA[CL * M + d.t] = a;                       // raw logits A
+    PA[NV * M + d.t] = a;                       // raw logits A
     const int grow = d.grow0 + d.t;
     if (d.rank == 0 && grow < d.Rtot) att_out[grow] = a;
   }
   __syncthreads();
   if (d.t < S) {
-    const float* A = PA + CL * M + d.t * 6;
+    const float* A = PA + NV * M + d.t * 6;
     float m = A[0];
 #pragma unroll
     for (int l = 1; l < 6; ++l) m = fmaxf(m, A[l]);
@@ -681,7 +690,8 @@ __device__ __forceinline__ void pool_fwd(Dev& d, const PoolP& p, const PoolW& w,
     if (d.rank == 0 && d.s0 + s < d.B) ws[w.hp + static_cast<size_t>(d.s0 + s) * E + d.t] = h;
   }
   __syncthreads();
-  {
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float bias = __ldg(p.br + col);
     const DropSpec dr = site_of(dm, SITE_RHO + pidx);
     gemm_block<S, T_FWD, E>(*d.pipe, smem_addr(d.red), HP, E);
@@ -703,20 +713,20 @@ __device__ __forceinline__ void pool_bwd(Dev& d, const PoolP& p, const PoolW& w,
                                          float* AW, float* DHP, const float* DZR) {
   constexpr int M = 6 * S;
   float* ws = d.ws;
-  const int col = d.rank * 32 + d.lane;
   // rho data gradient
-  {
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     gemm_block<S, T_DGRAD, 2 * E>(*d.pipe, smem_addr(d.red), DZR + pidx * E, E);
     reduce_epi<S>(d, [&](int s, int, float v) { bcast(DHP + s * E + col, v); });
   }
   // this pooling head's tokens, own columns of the two gate branches, pooling weights
   load_rows<M>(d, XA, tok_g, d.grow0, d.Rtot);
-  for (int i = d.t; i < M * 32; i += NT) {
-    const int r = i >> 5, n = i & 31;
+  for (int i = d.t; i < NB * M * 32; i += NT) {
+    const int nb = i / (M * 32), j = i - nb * (M * 32), r = j >> 5, n = j & 31;
     const int grow = d.grow0 + r;
     const bool valid = grow < d.Rtot;
-    AL[i] = valid ? __ldcg(ws + w.a + static_cast<size_t>(grow) * E + d.rank * 32 + n) : 0.f;
-    BL[i] = valid ? __ldcg(ws + w.b + static_cast<size_t>(grow) * E + d.rank * 32 + n) : 0.f;
+    AL[i] = valid ? __ldcg(ws + w.a + static_cast<size_t>(grow) * E + (d.rank * NB + nb) * 32 + n) : 0.f;
+    BL[i] = valid ? __ldcg(ws + w.b + static_cast<size_t>(grow) * E + (d.rank * NB + nb) * 32 + n) : 0.f;
   }
   if (d.t < M) AW[d.t] = (d.grow0 + d.t < d.Rtot) ? __ldcg(ws + w.w + d.grow0 + d.t) : 0.f;
   cluster_sync();
@@ -738,7 +748,8 @@ __device__ __forceinline__ void pool_bwd(Dev& d, const PoolP& p, const PoolW& w,
     for (int l = 0; l < 6; ++l) PA[M + d.t * 6 + l] = AW[d.t * 6 + l] * (PA[d.t * 6 + l] - dot);      // dA
   }
   __syncthreads();
-  {
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float wc = __ldg(p.wc + col);
     const DropSpec dsa = site_of(dq, SITE_POOL + 2 * pidx), dsb = site_of(dq, SITE_POOL + 2 * pidx + 1);
     float gw = 0.f;
@@ -749,7 +760,7 @@ __device__ __forceinline__ void pool_bwd(Dev& d, const PoolP& p, const PoolW& w,
         const int grow = d.grow0 + r;
         const uint32_t o = static_cast<uint32_t>(grow) * E + col;
         const float dA = PA[M + r];
-        const float av = AL[r * 32 + d.lane], bv = BL[r * 32 + d.lane];   // as stored: after their dropout layers
+        const float av = AL[(nb * M + r) * 32 + d.lane], bv = BL[(nb * M + r) * 32 + d.lane];   // after their dropout layers
         const float dab = dA * wc;
         float ga = 1.f, gb = 1.f, a0 = av, b0 = bv;
         if (dsa.thr != 0) { ga = drop_grad(dsa, d.seedv, o); a0 = drop_invert(av, dsa); }
@@ -766,6 +777,7 @@ __device__ __forceinline__ void pool_bwd(Dev& d, const PoolP& p, const PoolW& w,
       }
     }
     // attention_c parameter gradients: one atomic per (cluster, column)
+    __syncthreads();
     d.red[d.warp * 32 + d.lane] = gw;
     __syncthreads();
     if (d.warp == 0 && p.gwc != nullptr) {
@@ -774,15 +786,16 @@ __device__ __forceinline__ void pool_bwd(Dev& d, const PoolP& p, const PoolW& w,
       for (int k = 0; k < NW; ++k) v += d.red[k * 32 + d.lane];
       atomicAdd(p.gwc + col, v);
     }
-    if (d.rank == 0 && d.t == 0 && p.gbc != nullptr) {
-      float v = 0.f;
-      for (int r = 0; r < M; ++r) if (d.grow0 + r < d.Rtot) v += PA[M + r];
-      atomicAdd(p.gbc, v);
-    }
+  }
+  if (d.rank == 0 && d.t == 0 && p.gbc != nullptr) {
+    float v = 0.f;
+    for (int r = 0; r < M; ++r) if (d.grow0 + r < d.Rtot) v += PA[M + r];
+    atomicAdd(p.gbc, v);
   }
   cluster_sync();
   // gradient of the tokens: both gate branches' data gradients + the value path of the pooling
-  {
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     gemm_block<M, T_DGRAD, FF>(*d.pipe, smem_addr(d.red), BIG, FF);          // chunks: attention_a then attention_b
     reduce_epi<M>(d, [&](int r, int, float v) {
       v = fmaf(AW[r], DHP[(r / 6) * E + col], v);
@@ -803,10 +816,10 @@ struct PathSmem {
   static constexpr int BIG = XC + M * E;
   static constexpr int RED = BIG + M * 768;
   static constexpr int QKVL = RED + NW * M * 32;
-  static constexpr int AL = QKVL + M * 96;
-  static constexpr int BL = AL + M * 32;
-  static constexpr int PA = BL + M * 32;              // [CL + 1][M]
-  static constexpr int AW = PA + (CL + 1) * M + 4;
+  static constexpr int AL = QKVL + NB * M * 96;
+  static constexpr int BL = AL + NB * M * 32;
+  static constexpr int PA = BL + NB * M * 32;         // [NV + 1][M]
+  static constexpr int AW = PA + (NV + 1) * M + 4;
   static constexpr int HP = ((AW + M + 3) / 4) * 4;
   static constexpr int CAT = HP + S * E;
   static constexpr int Z1 = CAT + S * 2 * E;
@@ -849,7 +862,6 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
   float* DYv = DS + S * MAXK;             // d Y
   float* DLG = DYv + S * MAXK;            // d logits
   const int K = P.K;
-  const int col = d.rank * 32 + d.lane;
   const DropSpec& dm = P.d_model;
   const DropSpec& dq = P.d_quarter;
   cluster_sync();                         // every CTA of the cluster is running before any remote store
@@ -864,7 +876,8 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
         load_rows<M>(d, XA, ws + P.off_G, d.grow0, d.Rtot);
       } else {
         load_rows<M>(d, XA, P.pooled, d.grow0, d.Rtot);
-        {
+        for (int nb = 0; nb < NB; ++nb) {
+          const int col = (d.rank * NB + nb) * 32 + d.lane;
           const float bias = __ldg(P.bv + col);
           gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
           reduce_epi<M>(d, [&](int r, int, float v) {
@@ -874,7 +887,8 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
           });
         }
         cluster_sync();
-        {
+        for (int nb = 0; nb < NB; ++nb) {
+          const int col = (d.rank * NB + nb) * 32 + d.lane;
           const float bias = __ldg(P.bo + col);
           gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XB, E);
           reduce_epi<M>(d, [&](int r, int, float v) {
@@ -891,7 +905,8 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
                   HP, CAT);
     }
     // ---- concat fusion (fusion.py:17-19)
-    {
+    for (int nb = 0; nb < NB; ++nb) {
+      const int col = (d.rank * NB + nb) * 32 + d.lane;
       const float bias = __ldg(P.bf0 + col);
       gemm_block<S, T_FWD, 2 * E>(*d.pipe, smem_addr(d.red), CAT, 2 * E);
       reduce_epi<S>(d, [&](int s, int, float v) {
@@ -901,7 +916,8 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
       });
     }
     cluster_sync();
-    {
+    for (int nb = 0; nb < NB; ++nb) {
+      const int col = (d.rank * NB + nb) * 32 + d.lane;
       const float bias = __ldg(P.bf2 + col);
       gemm_block<S, T_FWD, E>(*d.pipe, smem_addr(d.red), Z1, E);
       reduce_epi<S>(d, [&](int s, int, float v) {
@@ -1038,7 +1054,8 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
       if (d.rank == 0 && d.s0 + s < d.B) ws[P.off_dz2 + static_cast<size_t>(d.s0 + s) * E + d.t] = g;
     }
     __syncthreads();
-    {
+    for (int nb = 0; nb < NB; ++nb) {
+      const int col = (d.rank * NB + nb) * 32 + d.lane;
       gemm_block<S, T_DGRAD, E>(*d.pipe, smem_addr(d.red), DZS, E);
       reduce_epi<S>(d, [&](int s, int, float v) {
         v = Z1[s * E + col] > 0.f ? v : 0.f;
@@ -1048,8 +1065,8 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
     }
     cluster_sync();
     // fusion layer 0 data gradient: the gradient of [h_path | h_omic], taken through rho's dropout and ReLU
-    for (int blk = 0; blk < 2; ++blk) {
-      const int c2 = d.rank * 64 + blk * 32 + d.lane;     // column of the [., 512] concat
+    for (int blk = 0; blk < 2 * NB; ++blk) {
+      const int c2 = d.rank * (64 * NB) + blk * 32 + d.lane;     // column of the [., 512] concat
       const int pidx = c2 >> 8, c = c2 & 255;
       const DropSpec dr = site_of(dm, SITE_RHO + pidx);
       gemm_block<S, T_DGRAD, E>(*d.pipe, smem_addr(d.red), DZ1, E);
@@ -1072,7 +1089,8 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
         enc_bwd<S>(d, P.enc[2 * br + l], P.encw[2 * br + l], 2 * br + l, dm, XA, XB, XC, BIG, AL, QKVL, BL,
                    l == 1 ? nullptr : ws + (br == 1 ? P.off_dG : P.off_dhc));
     }
-    {
+    for (int nb = 0; nb < NB; ++nb) {
+      const int col = (d.rank * NB + nb) * 32 + d.lane;
       gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XA, E);
       reduce_epi<M>(d, [&](int r, int, float v) {
         bcast(XB + r * E + col, v);
@@ -1080,7 +1098,8 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
       });
     }
     cluster_sync();
-    {
+    for (int nb = 0; nb < NB; ++nb) {
+      const int col = (d.rank * NB + nb) * 32 + d.lane;
       gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XB, E);
       reduce_epi<M>(d, [&](int r, int, float v) {
         if (d.grow0 + r < d.Rtot) P.dpooled[static_cast<size_t>(d.grow0 + r) * E + col] = v;
@@ -1141,7 +1160,6 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
   pipe_init(pipe, P.prog, sm + L::TBL, sm + L::ring, d.rank);
   float* ws = P.ws;
   float *XO = sm + L::XO, *H1 = sm + L::H1, *G = sm + L::G, *QP = sm + L::QP;
-  const int col = d.rank * 32 + d.lane;
   for (int i = 0; i < MPO_Q; ++i) {
     const int dim = P.omic_dims[i];
     for (int j = d.t; j < S * dim; j += NT) {
@@ -1150,7 +1168,9 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
     }
   }
   cluster_sync();
-  for (int i = 0; i < MPO_Q; ++i) {
+  for (int i = 0; i < MPO_Q; ++i)
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float bias = __ldg(P.b1[i] + col);
     const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * i);
     gemm_block<S, T_FWD, OMIC_LD>(*d.pipe, smem_addr(d.red), XO + i * S * OMIC_LD, P.omic_dims[i]);
@@ -1164,7 +1184,9 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
     });
   }
   cluster_sync();
-  for (int i = 0; i < MPO_Q; ++i) {
+  for (int i = 0; i < MPO_Q; ++i)
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float bias = __ldg(P.b2[i] + col);
     const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * i + 1);
     gemm_block<S, T_FWD, E>(*d.pipe, smem_addr(d.red), H1 + i * S * E, E);
@@ -1178,7 +1200,8 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
     });
   }
   cluster_sync();
-  {
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float bias = __ldg(P.bq + col);
     gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), G, E);
     reduce_epi<M>(d, [&](int r, int, float v) {
@@ -1188,7 +1211,8 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
     });
   }
   cluster_sync();
-  {
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), QP, E);
     reduce_epi<M>(d, [&](int r, int, float v) {
       if (d.grow0 + r < d.Rtot) P.qk[static_cast<size_t>(d.grow0 + r) * E + col] = v * (1.f / 16.f);
@@ -1217,11 +1241,11 @@ __global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ 
   pipe_init(pipe, P.prog, sm + L::TBL, sm + L::ring, d.rank);
   float* ws = P.ws;
   float *XA = sm + L::G, *XB = sm + L::QP, *DZ2 = sm + L::H1;     // DZ2: [M][256], row s*6+i
-  const int col = d.rank * 32 + d.lane;
   load_rows<M>(d, XA, P.dqk, d.grow0, d.Rtot);
   cluster_sync();
   // dq[r][e] = sum_d dqk[r][d] W_k[e][d] / 16
-  {
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
     reduce_epi<M>(d, [&](int r, int, float v) {
       v *= (1.f / 16.f);
@@ -1231,7 +1255,8 @@ __global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ 
   }
   cluster_sync();
   // dG = dq W_q + (omic branch), then through the second SNN layer's ELU + AlphaDropout
-  {
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     float dg0[(M + NW - 1) / NW], gv[(M + NW - 1) / NW];
 #pragma unroll
     for (int i = 0; i < (M + NW - 1) / NW; ++i) {
@@ -1253,7 +1278,9 @@ __global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ 
     });
   }
   cluster_sync();
-  for (int i = 0; i < MPO_Q; ++i) {
+  for (int i = 0; i < MPO_Q; ++i)
+  for (int nb = 0; nb < NB; ++nb) {
+    const int col = (d.rank * NB + nb) * 32 + d.lane;
     float hv[S];
 #pragma unroll
     for (int s = 0; s < S; ++s)
@@ -1428,8 +1455,8 @@ cudaError_t launch_cluster(K kern, const PT& prm, int nclusters, size_t smem_byt
   return e;
 }
 
-// two slides (12 token rows) per cluster; an odd batch leaves the last cluster's second slide empty.
-constexpr int kS = 2;
+// one slide (6 token rows) per cluster of 4 CTAs: the 32 slides of a step are 32 clusters = 128 CTAs, one wave
+constexpr int kS = 1;
 
 bool eligible(const mpo_model* m, const mpo_tail_io* io) {
   const char* env = getenv("MPO_TAIL_FUSED");        // read on every call: tests flip it to compare the two tails
@@ -1465,10 +1492,10 @@ int pre_fwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t
   static PreParams P;
   fill_pre(m, io, w, P);
   ProgBuilder pb{P.prog};
-  for (int i = 0; i < MPO_Q; ++i) pb.fwd(m->snn[i][0].w, m->omic_dims[i], m->omic_dims[i]);
-  for (int i = 0; i < MPO_Q; ++i) pb.fwd(m->snn[i][1].w, E, E);
-  pb.fwd(m->coattn_in.w, E, E);
-  pb.dgrad(m->coattn_in.w + static_cast<size_t>(E) * E, E, E);
+  for (int i = 0; i < MPO_Q; ++i) pb.fwd(m->snn[i][0].w, m->omic_dims[i], m->omic_dims[i], NB, 32 * NB);
+  for (int i = 0; i < MPO_Q; ++i) pb.fwd(m->snn[i][1].w, E, E, NB, 32 * NB);
+  pb.fwd(m->coattn_in.w, E, E, NB, 32 * NB);
+  pb.dgrad(m->coattn_in.w + static_cast<size_t>(E) * E, E, E, NB, 32 * NB);
   if (!pb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
   const int B = io->num_slides, ncl = (B + kS - 1) / kS;
   cudaError_t e = launch_cluster(pre_kernel<kS>, P, ncl, PreSmem<kS>::total * sizeof(float), st);
@@ -1486,9 +1513,9 @@ int pre_bwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t
   static PreParams P;
   fill_pre(m, io, w, P);
   ProgBuilder pb{P.prog};
-  pb.fwd(m->coattn_in.w + static_cast<size_t>(E) * E, E, E);
-  pb.dgrad(m->coattn_in.w, E, E);
-  for (int i = 0; i < MPO_Q; ++i) pb.dgrad(m->snn[i][1].w, E, E);
+  pb.fwd(m->coattn_in.w + static_cast<size_t>(E) * E, E, E, NB, 32 * NB);
+  pb.dgrad(m->coattn_in.w, E, E, NB, 32 * NB);
+  for (int i = 0; i < MPO_Q; ++i) pb.dgrad(m->snn[i][1].w, E, E, NB, 32 * NB);
   if (!pb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
   const int B = io->num_slides, R = 6 * B, ncl = (B + kS - 1) / kS;
   cudaError_t e = launch_cluster(pre_bwd_kernel<kS>, P, ncl, PreSmem<kS>::total * sizeof(float), st);
@@ -1556,32 +1583,45 @@ int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, cons
   P.B = B; P.K = K; P.flags = flags;
 
   ProgBuilder pb{P.prog};
+  // chunk order = consumption order of the device code; a CTA owns NB column blocks of every 256-wide layer
   auto enc_f = [&](const mpo_encoder_layer& L) {
-    pb.fwd(L.in_proj.w, E, E, 3, 32, E);
-    pb.fwd(L.out_proj.w, E, E);
-    pb.fwd(L.linear1.w, E, E, 2, 64, 32);
-    pb.fwd(L.linear2.w, FF, FF);
+    for (int nb = 0; nb < NB; ++nb) pb.fwd(L.in_proj.w, E, E, 3, 32 * NB, E, nb * 32);     // q, k, v of head rank * NB + nb
+    pb.fwd(L.out_proj.w, E, E, NB, 32 * NB);
+    pb.fwd(L.linear1.w, E, E, 2 * NB, 64 * NB, 32);
+    pb.fwd(L.linear2.w, FF, FF, NB, 32 * NB);
   };
   auto enc_b = [&](const mpo_encoder_layer& L) {
-    pb.dgrad(L.linear2.w, FF, E, 2, 64, 32);
-    pb.dgrad(L.linear1.w, E, FF);
-    pb.dgrad(L.out_proj.w, E, E);
-    pb.dgrad(L.in_proj.w, E, 3 * E);
+    pb.dgrad(L.linear2.w, FF, E, 2 * NB, 64 * NB, 32);
+    pb.dgrad(L.linear1.w, E, FF, NB, 32 * NB);
+    pb.dgrad(L.out_proj.w, E, E, NB, 32 * NB);
+    pb.dgrad(L.in_proj.w, E, 3 * E, NB, 32 * NB);
   };
-  auto pool_f = [&](const mpo_pool_head& H) { pb.fwd(H.att_a.w, E, E); pb.fwd(H.att_b.w, E, E); pb.fwd(H.rho.w, E, E); };
-  auto pool_b = [&](const mpo_pool_head& H) { pb.dgrad(H.rho.w, E, E); pb.dgrad(H.att_a.w, E, E); pb.dgrad(H.att_b.w, E, E); };
+  auto pool_f = [&](const mpo_pool_head& H) {
+    for (int nb = 0; nb < NB; ++nb) {
+      pb.fwd(H.att_a.w, E, E, 1, 32 * NB, 32, nb * 32);
+      pb.fwd(H.att_b.w, E, E, 1, 32 * NB, 32, nb * 32);
+    }
+    pb.fwd(H.rho.w, E, E, NB, 32 * NB);
+  };
+  auto pool_b = [&](const mpo_pool_head& H) {
+    pb.dgrad(H.rho.w, E, E, NB, 32 * NB);
+    for (int nb = 0; nb < NB; ++nb) {
+      pb.dgrad(H.att_a.w, E, E, 1, 32 * NB, 32, nb * 32);
+      pb.dgrad(H.att_b.w, E, E, 1, 32 * NB, 32, nb * 32);
+    }
+  };
   if (flags & F_FWD) {
     enc_f(m->omic_tr[0]); enc_f(m->omic_tr[1]); pool_f(m->omic_pool);
-    pb.fwd(Wv, E, E); pb.fwd(m->coattn_out.w, E, E);
+    pb.fwd(Wv, E, E, NB, 32 * NB); pb.fwd(m->coattn_out.w, E, E, NB, 32 * NB);
     enc_f(m->path_tr[0]); enc_f(m->path_tr[1]); pool_f(m->path_pool);
-    pb.fwd(m->fusion0.w, 2 * E, 2 * E); pb.fwd(m->fusion2.w, E, E);
+    pb.fwd(m->fusion0.w, 2 * E, 2 * E, NB, 32 * NB); pb.fwd(m->fusion2.w, E, E, NB, 32 * NB);
   }
   if (flags & F_BWD) {
-    pb.dgrad(m->fusion2.w, E, E);
-    pb.dgrad(m->fusion0.w, 2 * E, E, 2, 64, 32);
+    pb.dgrad(m->fusion2.w, E, E, NB, 32 * NB);
+    pb.dgrad(m->fusion0.w, 2 * E, E, 2 * NB, 64 * NB, 32);
     pool_b(m->omic_pool); enc_b(m->omic_tr[1]); enc_b(m->omic_tr[0]);
     pool_b(m->path_pool); enc_b(m->path_tr[1]); enc_b(m->path_tr[0]);
-    pb.dgrad(m->coattn_out.w, E, E); pb.dgrad(Wv, E, E);
+    pb.dgrad(m->coattn_out.w, E, E, NB, 32 * NB); pb.dgrad(Wv, E, E, NB, 32 * NB);
   }
   if (!pb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
   const int ncl = (B + kS - 1) / kS;
