@@ -833,6 +833,7 @@ struct PathSmem {
   static constexpr int total = TBL + MAX_CHUNKS * 4;
 };
 
+static_assert(PathSmem<2>::total * sizeof(float) <= 227 * 1024, "path kernel shared memory");
 template <int S>
 __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ PathParams P) {
   constexpr int M = 6 * S;
@@ -1455,8 +1456,14 @@ cudaError_t launch_cluster(K kern, const PT& prm, int nclusters, size_t smem_byt
   return e;
 }
 
-// one slide (6 token rows) per cluster of 4 CTAs: the 32 slides of a step are 32 clusters = 128 CTAs, one wave
-constexpr int kS = 1;
+// Slides per cluster.  One slide (6 token rows) per cluster of 4 CTAs makes the 32 slides of a step 32 clusters =
+// 128 CTAs, a single wave (33 such clusters fit); larger batches take two slides per cluster to halve the waves.
+int slides_per_cluster(int B) {
+  const char* env = getenv("MPO_TAIL_FUSED_S");
+  const int forced = env ? atoi(env) : 0;
+  if (forced == 1 || forced == 2) return forced;
+  return B <= 33 ? 1 : 2;
+}
 
 bool eligible(const mpo_model* m, const mpo_tail_io* io) {
   const char* env = getenv("MPO_TAIL_FUSED");        // read on every call: tests flip it to compare the two tails
@@ -1497,8 +1504,9 @@ int pre_fwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t
   pb.fwd(m->coattn_in.w, E, E, NB, 32 * NB);
   pb.dgrad(m->coattn_in.w + static_cast<size_t>(E) * E, E, E, NB, 32 * NB);
   if (!pb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
-  const int B = io->num_slides, ncl = (B + kS - 1) / kS;
-  cudaError_t e = launch_cluster(pre_kernel<kS>, P, ncl, PreSmem<kS>::total * sizeof(float), st);
+  const int B = io->num_slides, S = slides_per_cluster(B), ncl = (B + S - 1) / S;
+  cudaError_t e = S == 2 ? launch_cluster(pre_kernel<2>, P, ncl, PreSmem<2>::total * sizeof(float), st)
+                         : launch_cluster(pre_kernel<1>, P, ncl, PreSmem<1>::total * sizeof(float), st);
   return fin(e, "pre_kernel (fused tail)");
 }
 
@@ -1517,8 +1525,9 @@ int pre_bwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t
   pb.dgrad(m->coattn_in.w, E, E, NB, 32 * NB);
   for (int i = 0; i < MPO_Q; ++i) pb.dgrad(m->snn[i][1].w, E, E, NB, 32 * NB);
   if (!pb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
-  const int B = io->num_slides, R = 6 * B, ncl = (B + kS - 1) / kS;
-  cudaError_t e = launch_cluster(pre_bwd_kernel<kS>, P, ncl, PreSmem<kS>::total * sizeof(float), st);
+  const int B = io->num_slides, R = 6 * B, S = slides_per_cluster(B), ncl = (B + S - 1) / S;
+  cudaError_t e = S == 2 ? launch_cluster(pre_bwd_kernel<2>, P, ncl, PreSmem<2>::total * sizeof(float), st)
+                         : launch_cluster(pre_bwd_kernel<1>, P, ncl, PreSmem<1>::total * sizeof(float), st);
   int rc = fin(e, "pre_bwd_kernel (fused tail)");
   if (rc) return rc;
   static WParams W;
@@ -1624,8 +1633,9 @@ int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, cons
     pb.dgrad(m->coattn_out.w, E, E, NB, 32 * NB); pb.dgrad(Wv, E, E, NB, 32 * NB);
   }
   if (!pb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
-  const int ncl = (B + kS - 1) / kS;
-  cudaError_t e = launch_cluster(path_kernel<kS>, P, ncl, PathSmem<kS>::total * sizeof(float), st);
+  const int S = slides_per_cluster(B), ncl = (B + S - 1) / S;
+  cudaError_t e = S == 2 ? launch_cluster(path_kernel<2>, P, ncl, PathSmem<2>::total * sizeof(float), st)
+                         : launch_cluster(path_kernel<1>, P, ncl, PathSmem<1>::total * sizeof(float), st);
   int rc = fin(e, "path_kernel (fused tail)");
   if (rc || !(flags & F_BWD)) return rc;
 
