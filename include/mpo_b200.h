@@ -281,7 +281,10 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
 /* post_fwd + mpo_surv_loss + post_bwd as one call (the training step of models/mcat/main.py:39-70 between the bag
  * forward and the bag backward): for MCAT with concat fusion this is ONE cluster kernel (csrc/tail_fused.cu) plus the
  * grouped weight-gradient kernel; other configurations run the three stages back to back.  Arguments as in
- * mpo_surv_loss; io->dpooled is written, parameter gradients are accumulated. */
+ * mpo_surv_loss; io->dpooled is written, parameter gradients are accumulated.  On the fused path the post stage's
+ * weight gradients run on an internal side stream next to the bag backward pass and are joined back into `stream`
+ * by mpo_tail_pre_bwd: the step's gradients are complete (stream-ordered) after mpo_tail_pre_bwd, which a training
+ * step always calls (mpo_bag_bwd needs nothing but io->dpooled from this call). */
 int mpo_tail_post_step(const mpo_model* m, const mpo_tail_io* io, int32_t kind, const int64_t* label, const float* censor,
                        float alpha, float eps, float grad_scale, float* loss, float* dhaz, float* dS, void* stream);
 /* autograd of pre_fwd: consumes io->dqk and the workspace gradients, finishes co_attention.in_proj and SNN grads */

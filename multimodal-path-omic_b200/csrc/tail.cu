@@ -738,7 +738,7 @@ int mpo_tail_post_step(const mpo_model* m, const mpo_tail_io* io, int32_t kind, 
     Ws w; build_layout(m, io->num_slides, w);
     fused::LossArgs la{kind, label, censor, alpha, eps, grad_scale, loss, dhaz, dS};
     return fused::post(m, io, w, fused::F_FWD | fused::F_LOSS | fused::F_BWD, &la, nullptr, nullptr, nullptr,
-                       static_cast<cudaStream_t>(stream));
+                       static_cast<cudaStream_t>(stream), /*side_wgrad=*/true);
   }
   if ((rc = mpo_tail_post_fwd(m, io, stream))) return rc;
   if ((rc = mpo_surv_loss(kind, io->hazards, io->S, label, censor, alpha, eps, grad_scale, loss, dhaz, dS, io->num_slides,

@@ -153,14 +153,16 @@ __device__ __noinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int 
     const int ld = pk & 0xffff, kc = (pk >> 16) & 0x7fff, type = (pk >> 31) & 1;
     const float* src = reinterpret_cast<const float*>(base) + static_cast<size_t>(rank) * rs;
     const uint32_t dst = ring + (c % NSTAGE) * (CHUNK * 4);
+    // (1-D bulk copies by one warp were tried instead: 256 copies of 128 B per data-gradient chunk are far slower)
     if (type == T_FWD) {
       if (kc == KC) {
+        // thread t copies 16 B of rows (t >> 6) + 4 j: strength-reduced addresses, 8 copies in flight per thread
+        const float* s0 = src + static_cast<size_t>(t >> 6) * ld + (t & 63) * 4;
+        const uint32_t d0 = dst + ((t >> 6) * WLD + (t & 63) * 4) * 4;
+        const size_t sstep = static_cast<size_t>(4) * ld;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int p = t + j * NT, row = p >> 6, c4 = p & 63;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (row * WLD + c4 * 4) * 4),
-                       "l"(src + static_cast<size_t>(row) * ld + c4 * 4) : "memory");
-        }
+        for (int j = 0; j < 8; ++j)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * (4 * WLD * 4)), "l"(s0 + j * sstep) : "memory");
       } else {
         const int per_row = kc >> 2;
         for (int p = t; p < 32 * per_row; p += NT) {
@@ -170,10 +172,17 @@ __device__ __noinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int 
         }
       }
     } else {
-      for (int p = t; p < kc * 8; p += NT) {
-        const int row = p >> 3, c4 = p & 7;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (row * 32 + c4 * 4) * 4),
-                     "l"(src + static_cast<size_t>(row) * ld + c4 * 4) : "memory");
+      // rows (t >> 3) + 32 j of the chunk, 16 B at column 4 (t & 7)
+      const float* s0 = src + static_cast<size_t>(t >> 3) * ld + (t & 7) * 4;
+      const uint32_t d0 = dst + ((t >> 3) * 32 + (t & 7) * 4) * 4;
+      const size_t sstep = static_cast<size_t>(32) * ld;
+      if (kc == KC) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * (32 * 32 * 4)), "l"(s0 + j * sstep) : "memory");
+      } else {
+        for (int j = 0; j * 32 + (t >> 3) < kc; ++j)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * (32 * 32 * 4)), "l"(s0 + j * sstep) : "memory");
       }
     }
   }
@@ -1510,6 +1519,31 @@ int pre_fwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t
   return fin(e, "pre_kernel (fused tail)");
 }
 
+// Side stream for the post stage's weight gradients inside a training step: they depend only on the path kernel and
+// are first needed by the optimizer, so they run next to the bag backward pass instead of in front of it.  The fork
+// and the join (at the end of pre_bwd) are event edges, so the step stays capturable into one CUDA graph.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int state = 0;          // 0 not created, 1 ready, -1 unavailable
+  bool pending = false;   // a weight-gradient launch on `s` has not been joined yet
+};
+static SideStream& side_stream() {
+  static SideStream pool[32];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SideStream& p = pool[dev & 31];
+  if (p.state == 0) {
+    const char* env = getenv("MPO_TAIL_STREAMS");
+    bool ok = !(env && atoi(env) == 0);
+    ok = ok && cudaStreamCreateWithFlags(&p.s, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&p.ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&p.ev_join, cudaEventDisableTiming) == cudaSuccess;
+    p.state = ok ? 1 : -1;
+  }
+  return p;
+}
+
 static int launch_wgrad(const WParams& W, cudaStream_t st) {
   if (W.ntiles == 0) return MPO_OK;
   wgrad_kernel<<<W.ntiles, 256, 0, st>>>(W);
@@ -1544,11 +1578,18 @@ int pre_bwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t
   mpo_lin Lk = {nullptr, nullptr, m->coattn_in.gw ? m->coattn_in.gw + static_cast<size_t>(E) * E : nullptr, nullptr};
   jb.lin(io->qp, E, io->dqk, E, Lk, E, E, R, 1.f / 16.f);
   if (!jb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: job table overflow");
-  return launch_wgrad(W, st);
+  rc = launch_wgrad(W, st);
+  if (rc) return rc;
+  SideStream& side = side_stream();
+  if (side.pending) {          // the post stage's weight gradients of this step (launched by post() on the side stream)
+    side.pending = false;
+    return check_cuda(cudaStreamWaitEvent(st, side.ev_join, 0), "fused tail: join of the weight-gradient stream");
+  }
+  return MPO_OK;
 }
 
 int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, const LossArgs* loss, const float* dhaz,
-         const float* dS, const float* dY, cudaStream_t st) {
+         const float* dS, const float* dY, cudaStream_t st, bool side_wgrad) {
   static PathParams P;
   memset(&P, 0, sizeof(P));
   const int B = io->num_slides, R = 6 * B, K = m->n_classes;
@@ -1669,6 +1710,16 @@ int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, cons
                 m->coattn_in.gb ? m->coattn_in.gb + 2 * E : nullptr};
   jb.lin(ws + w.dv, E, io->pooled, E, Lv, E, E, R);
   if (!jb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: job table overflow");
+  SideStream& side = side_stream();
+  if (side_wgrad && side.state == 1) {
+    cudaError_t e2 = cudaEventRecord(side.ev_fork, st);
+    if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(side.s, side.ev_fork, 0);
+    if (e2 != cudaSuccess) return check_cuda(e2, "fused tail: fork of the weight-gradient stream");
+    rc = launch_wgrad(W, side.s);
+    if (rc) return rc;
+    side.pending = true;
+    return check_cuda(cudaEventRecord(side.ev_join, side.s), "fused tail: weight-gradient stream event");
+  }
   return launch_wgrad(W, st);
 }
 

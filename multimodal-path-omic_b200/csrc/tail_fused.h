@@ -25,8 +25,10 @@ bool eligible(const mpo_model* m, const mpo_tail_io* io);
 int pre_fwd(const mpo_model* m, const mpo_tail_io* io, const tailws::Ws& w, cudaStream_t st);
 // flags: F_FWD (mcat.py:97-138), F_LOSS (needs F_FWD; `loss` non-null), F_BWD (gradients from the in-kernel loss, or
 // from dhaz/dS/dY when F_LOSS is not set); F_BWD also launches the grouped weight-gradient kernel of the post stage
+// side_wgrad: launch that kernel on an internal side stream (joined into `st` at the end of pre_bwd) so that it
+// overlaps the bag backward pass; only for callers that always finish the step with pre_bwd (mpo_tail_post_step)
 int post(const mpo_model* m, const mpo_tail_io* io, const tailws::Ws& w, int flags, const LossArgs* loss,
-         const float* dhaz, const float* dS, const float* dY, cudaStream_t st);
+         const float* dhaz, const float* dS, const float* dY, cudaStream_t st, bool side_wgrad = false);
 int pre_bwd(const mpo_model* m, const mpo_tail_io* io, const tailws::Ws& w, cudaStream_t st);
 
 }  // namespace fused
