@@ -145,6 +145,46 @@ def test_batched_trainer_equals_per_slide_gradients():
         assert err < 2e-3, (k, err)
 
 
+@pytest.mark.parametrize("slides_per_cluster,train", [(1, True), (2, True), (2, False)])
+def test_fused_cluster_tail_equals_per_op_tail(slides_per_cluster, train, monkeypatch):
+    """The fused cluster tail (csrc/tail_fused.cu: three cluster kernels + one grouped weight-gradient kernel) and the
+    per-op tail (csrc/tail.cu) are two implementations of the same step: same dropout masks (stateless RNG keyed by
+    seed / site / element), so losses, hazards, d(pooled) and every parameter gradient must agree to fp32 rounding.
+    Ragged batch of 5 slides: the second slide slot of the last 2-slide cluster is empty."""
+    synth = _pkg("synth")
+    sp = _pkg("slidepath")
+    bpm = _pkg("bagpass")
+    case = load_case("mcat_concat_sharp_517")
+    lens = [300, 129, 1, 517, 64]
+    slides = [synth.make_slide(300 + i, n) for i, n in enumerate(lens)]
+    pb = bpm.PackedBag.from_slides([torch.from_numpy(s[0]).cuda() for s in slides])
+    om = [torch.stack([torch.from_numpy(s[1][i]) for s in slides]).cuda() for i in range(6)]
+    labels = torch.tensor([s[2] for s in slides], dtype=torch.int64, device="cuda")
+    cens = torch.tensor([s[3] for s in slides], dtype=torch.float32, device="cuda")
+    monkeypatch.setenv("MPO_TAIL_FUSED_S", str(slides_per_cluster))
+    out = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("MPO_TAIL_FUSED", fused)
+        net = build_model(case)
+        net.train() if train else net.eval()
+        tr = sp.BatchTrainer(net, loss="nll", grad_acc_step=len(lens))
+        tr.zero_grad()
+        loss, hz, S = tr.step(pb, om, labels, cens, train=train, seed=4242)
+        torch.cuda.synchronize()
+        st = tr.last_state
+        out[fused] = dict(loss=loss.clone(), hz=hz.clone(), S=S.clone(), dpooled=st.dpooled.clone(),
+                          att_path=st.att_path.clone(), att_omic=st.att_omic.clone(),
+                          grads={k: v.clone() for k, v in tr.grads.items()})
+    a, b = out["0"], out["1"]
+    for k in ("loss", "hz", "S", "att_path", "att_omic"):
+        assert torch.allclose(a[k], b[k], rtol=2e-5, atol=1e-6), k
+    assert float((a["dpooled"] - b["dpooled"]).norm() / a["dpooled"].norm()) < 1e-4
+    gmax = max(float(v.norm()) for v in a["grads"].values())
+    for k, g in a["grads"].items():
+        err = float((g - b["grads"][k]).norm()) / max(float(g.norm()), 1e-5 * gmax)
+        assert err < 5e-4, (k, err)
+
+
 def test_graph_replay_equals_eager_step():
     """A captured CUDA-graph step accumulates the same gradients as the eager step (eval mode, so no dropout)."""
     synth = _pkg("synth")
