@@ -284,9 +284,13 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
  * mpo_surv_loss; io->dpooled is written, parameter gradients are accumulated.  On the fused path the post stage's
  * weight gradients run on an internal side stream next to the bag backward pass and are joined back into `stream`
  * by mpo_tail_pre_bwd: the step's gradients are complete (stream-ordered) after mpo_tail_pre_bwd, which a training
- * step always calls (mpo_bag_bwd needs nothing but io->dpooled from this call). */
+ * step always calls (mpo_bag_bwd needs nothing but io->dpooled from this call).  With MPO_POST_STEP_INLINE_WGRAD in
+ * `flags` they stay on `stream` instead: a data-parallel trainer can then all-reduce the post stage's gradient bucket
+ * while the bag backward pass runs. */
+#define MPO_POST_STEP_INLINE_WGRAD 1   /* flags: keep the post stage's weight gradients on `stream` (complete on return order) */
 int mpo_tail_post_step(const mpo_model* m, const mpo_tail_io* io, int32_t kind, const int64_t* label, const float* censor,
-                       float alpha, float eps, float grad_scale, float* loss, float* dhaz, float* dS, void* stream);
+                       float alpha, float eps, float grad_scale, float* loss, float* dhaz, float* dS, int32_t flags,
+                       void* stream);
 /* autograd of pre_fwd: consumes io->dqk and the workspace gradients, finishes co_attention.in_proj and SNN grads */
 int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream);
 

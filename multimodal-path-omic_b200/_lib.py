@@ -143,7 +143,7 @@ SIGNATURES = {
     "mpo_tail_post_bwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p, c_void_p, c_void_p, c_void_p],
     "mpo_tail_pre_bwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],
     "mpo_tail_post_step": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_i32, c_void_p, c_void_p, c_float, c_float,
-                           c_float, c_void_p, c_void_p, c_void_p, c_void_p],
+                           c_float, c_void_p, c_void_p, c_void_p, c_i32, c_void_p],
 }
 # functions with a non-int return type
 OTHER_EXPORTS = ["mpo_tail_ws_floats", "mpo_tail_ws_lookup", "mpo_sizeof", "mpo_launch_count", "mpo_ge_ws_floats"]

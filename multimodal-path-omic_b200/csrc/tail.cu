@@ -727,7 +727,8 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
 }
 
 int mpo_tail_post_step(const mpo_model* m, const mpo_tail_io* io, int32_t kind, const int64_t* label, const float* censor,
-                       float alpha, float eps, float grad_scale, float* loss, float* dhaz, float* dS, void* stream) {
+                       float alpha, float eps, float grad_scale, float* loss, float* dhaz, float* dS, int32_t flags,
+                       void* stream) {
   int rc = check_model(m, io, "mpo_tail_post_step");
   if (rc) return rc;
   if (kind != MPO_LOSS_NLL && kind != MPO_LOSS_CES) return fail(MPO_E_UNSUPPORTED, "%s", "mpo_tail_post_step: unknown loss kind");
@@ -738,7 +739,7 @@ int mpo_tail_post_step(const mpo_model* m, const mpo_tail_io* io, int32_t kind, 
     Ws w; build_layout(m, io->num_slides, w);
     fused::LossArgs la{kind, label, censor, alpha, eps, grad_scale, loss, dhaz, dS};
     return fused::post(m, io, w, fused::F_FWD | fused::F_LOSS | fused::F_BWD, &la, nullptr, nullptr, nullptr,
-                       static_cast<cudaStream_t>(stream), /*side_wgrad=*/true);
+                       static_cast<cudaStream_t>(stream), /*side_wgrad=*/(flags & MPO_POST_STEP_INLINE_WGRAD) == 0);
   }
   if ((rc = mpo_tail_post_fwd(m, io, stream))) return rc;
   if ((rc = mpo_surv_loss(kind, io->hazards, io->S, label, censor, alpha, eps, grad_scale, loss, dhaz, dS, io->num_slides,

@@ -479,23 +479,44 @@ class BatchTrainer:
                   self.flat_grad.numel(), ctypes.c_float(lr), ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps),
                   ctypes.c_float(wd), _ptr(self.adam_step_dev), 1 if zero_grad else 0, _stream())
 
-    def _run(self, st, bag, omics, labels, censor, train, seed):
+    def _run_fwd(self, st, bag, omics, labels, censor, train, seed, inline_wgrad=False):
+        """pre -> bag forward -> post forward + loss + post backward (mpo_tail_post_step).  With inline_wgrad the
+        post stage's parameter gradients are complete when this part is (see post_bucket_offset)."""
         eng = self.engine
         if st is not None and st.seed_dev is not None and train:
             _lib.call("mpo_advance_seed", _ptr(st.seed_dev), _stream())
         if st is None:
             st = eng.alloc_state(self.model, bag, save_for_backward=True, reuse_ws=True, with_backward_buffers=True)
+        flags = 1 if inline_wgrad else 0          # MPO_POST_STEP_INLINE_WGRAD
 
         def post(st_, io, s):
             # post forward + loss (models/loss.py) + post backward in one call: one cluster kernel on the fused path
             _lib.call("mpo_tail_post_step", ctypes.byref(self.model), ctypes.byref(io), self.kind, _ptr(labels),
                       _ptr(censor), ctypes.c_float(self.alpha), ctypes.c_float(self.eps),
-                      ctypes.c_float(1.0 / self.grad_acc_step), _ptr(st_.loss), _ptr(st_.dhz), _ptr(st_.dS), s)
+                      ctypes.c_float(1.0 / self.grad_acc_step), _ptr(st_.loss), _ptr(st_.dhz), _ptr(st_.dS), flags, s)
 
-        st = eng.forward(self.model, bag, omics, train=train, save_for_backward=True, seed=seed, reuse_ws=True, st=st,
-                         post=post)
-        eng.backward(self.model, st, st.dhz, st.dS, None, post_done=True)
+        return eng.forward(self.model, bag, omics, train=train, save_for_backward=True, seed=seed, reuse_ws=True, st=st,
+                           post=post)
+
+    def _run_bwd(self, st):
+        """bag backward -> pre backward (the rest of the step's gradients)."""
+        self.engine.backward(self.model, st, st.dhz, st.dS, None, post_done=True)
         return st
+
+    def _run(self, st, bag, omics, labels, censor, train, seed):
+        return self._run_bwd(self._run_fwd(st, bag, omics, labels, censor, train, seed))
+
+    def post_bucket_offset(self):
+        """First element of the flat gradient buffer that belongs to the post-stage-only bucket: every parameter from
+        co_attention.out_proj on (out projection, encoders, pooling heads, rho, fusion, classifier) is registered after
+        H / G / co_attention.in_proj, and its gradient is final once mpo_tail_post_step has run -- a data-parallel
+        trainer all-reduces flat_grad[offset:] while the bag backward pass is still running."""
+        names = list(self.offsets.keys())
+        first = names.index("co_attention.out_proj.weight")
+        pre_only = ("H.", "G.", "co_attention.in_proj")
+        if any(n.startswith(pre_only) for n in names[first:]):
+            raise RuntimeError("unexpected parameter order: the post-stage gradient bucket is not a contiguous tail")
+        return self.offsets[names[first]]
 
     def step(self, bag, omics, labels, censor, train=True, seed=None):
         """Returns (loss [B], hazards [B,K], S [B,K]).  labels int64 [B], censor float32 [B], on the GPU."""
@@ -503,12 +524,14 @@ class BatchTrainer:
         self.last_state = st
         return st.loss, st.hazards, st.S
 
-    def capture(self, bag, omics, labels, censor, train=True, with_adam=False):
+    def capture(self, bag, omics, labels, censor, train=True, with_adam=False, split=False):
         """Record one step (forward + loss + backward) over these STATIC buffers into a CUDA graph.
 
         The caller refreshes the contents of bag.x / omics / labels / censor in place and calls replay(); the
-        ~250 small tail launches then cost one graph launch.  Dropout masks change on every replay
-        through a device-side seed."""
+        small tail launches then cost one graph launch.  Dropout masks change on every replay
+        through a device-side seed.  split=True records the step as TWO graphs -- everything up to and including the
+        post stage's gradients, then bag backward + pre backward -- so that a data-parallel caller can start the
+        all-reduce of flat_grad[post_bucket_offset():] between them (replay_first() / replay_second())."""
         eng = self.engine
         dev = bag.x.device
         st = eng.alloc_state(self.model, bag, save_for_backward=True, reuse_ws=False, with_backward_buffers=True)
@@ -518,32 +541,52 @@ class BatchTrainer:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):                         # warm-up outside the capture (lazy kernel attributes etc.)
-                self._run(st, bag, omics, labels, censor, train, 0)
+                self._run_bwd(self._run_fwd(st, bag, omics, labels, censor, train, 0, inline_wgrad=split))
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.flat_grad.zero_()
         graph = torch.cuda.CUDAGraph()
+        graph2 = torch.cuda.CUDAGraph() if split else None
         _lib.lib().mpo_launch_count(1)
-        with torch.cuda.graph(graph):
-            self._run(st, bag, omics, labels, censor, train, 0)
-            if with_adam:        # single-GPU: the optimizer step (and the gradient reset) ride in the same graph
-                self.adam_step(zero_grad=True)
-        launches = int(_lib.lib().mpo_launch_count(1))     # kernels recorded into the graph = launched per replay
+        if split:
+            with torch.cuda.graph(graph):
+                self._run_fwd(st, bag, omics, labels, censor, train, 0, inline_wgrad=True)
+            with torch.cuda.graph(graph2, pool=graph.pool()):
+                self._run_bwd(st)
+        else:
+            with torch.cuda.graph(graph):
+                self._run(st, bag, omics, labels, censor, train, 0)
+                if with_adam:        # single-GPU: the optimizer step (and the gradient reset) ride in the same graph
+                    self.adam_step(zero_grad=True)
+        launches = int(_lib.lib().mpo_launch_count(1))     # kernels recorded into the graph(s) = launched per replay
         self.flat_grad.zero_()
         self.last_state = st
-        return GraphedStep(graph, st, (bag, omics, labels, censor), launches)
+        return GraphedStep(graph, st, (bag, omics, labels, censor), launches, graph2)
 
 
 class GraphedStep:
     """A captured train step over static buffers: refresh the buffers in place, then replay()."""
 
-    def __init__(self, graph, state, static_inputs, launches=0):
-        self.graph, self.state, self.static_inputs = graph, state, static_inputs
+    def __init__(self, graph, state, static_inputs, launches=0, graph2=None):
+        self.graph, self.graph2, self.state, self.static_inputs = graph, graph2, state, static_inputs
         self.launches_per_replay = launches     # kernels of libmpo_b200.so inside the captured step
         self.replays = 0
 
+    def replay_first(self):
+        """split capture: pre, bag forward, post forward + loss + post backward (post-stage gradients complete)."""
+        self.graph.replay()
+
+    def replay_second(self):
+        """split capture: bag backward + pre backward."""
+        self.graph2.replay()
+        self.replays += 1
+        st = self.state
+        return st.loss, st.hazards, st.S
+
     def replay(self):
         self.graph.replay()
+        if self.graph2 is not None:
+            return self.replay_second()
         self.replays += 1
         st = self.state
         return st.loss, st.hazards, st.S
