@@ -409,11 +409,25 @@ __device__ __forceinline__ void enc_fwd(Dev& d, const EncP& p, const EncW& w, in
   constexpr int M = 6 * S;
   float* ws = d.ws;
   const uint32_t s0 = SITE_ENC + 4 * eidx;      // attention probabilities, dropout1, feed-forward dropout, dropout2
+  // every bias of the layer up front: one exposed global-load latency per layer instead of one in front of each GEMM
+  float bias_in[NB][3], bias_out[NB], bias_1[2 * NB], bias_2[NB];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    const int c = (d.rank * NB + nb) * 32 + d.lane;
+#pragma unroll
+    for (int blk = 0; blk < 3; ++blk) bias_in[nb][blk] = __ldg(p.b_in + blk * E + c);
+    bias_out[nb] = __ldg(p.b_out + c);
+    bias_2[nb] = __ldg(p.b2 + c);
+  }
+#pragma unroll
+  for (int blk = 0; blk < 2 * NB; ++blk) bias_1[blk] = __ldg(p.b1 + d.rank * (64 * NB) + blk * 32 + d.lane);
   // packed in-projection: this CTA computes q, k, v of its heads
+#pragma unroll
   for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
     for (int blk = 0; blk < 3; ++blk) {
       const int col = blk * E + (d.rank * NB + nb) * 32 + d.lane;
-      const float bias = __ldg(p.b_in + col);
+      const float bias = bias_in[nb][blk];
       gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
       reduce_epi<M>(d, [&](int r, int, float v) {
         v += bias;
@@ -460,9 +474,10 @@ __device__ __forceinline__ void enc_fwd(Dev& d, const EncP& p, const EncW& w, in
   }
   cluster_sync();
   // out-projection + dropout1 + residual
+#pragma unroll
   for (int nb = 0; nb < NB; ++nb) {
     const int col = (d.rank * NB + nb) * 32 + d.lane;
-    const float bias = __ldg(p.b_out + col);
+    const float bias = bias_out[nb];
     const DropSpec d1 = site_of(dm, s0 + 1);
     gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XB, E);
     reduce_epi<M>(d, [&](int r, int, float v) {
@@ -475,9 +490,10 @@ __device__ __forceinline__ void enc_fwd(Dev& d, const EncP& p, const EncW& w, in
   ln_fwd_rows<M>(row_ctx(d), XC, XA, p.g1, p.be1, ws + w.y1, ws + w.xh1, ws + w.rs1);
   __syncthreads();
   // feed-forward
+#pragma unroll
   for (int blk = 0; blk < 2 * NB; ++blk) {
     const int col = d.rank * (64 * NB) + blk * 32 + d.lane;
-    const float bias = __ldg(p.b1 + col);
+    const float bias = bias_1[blk];
     const DropSpec d2 = site_of(dm, s0 + 2);
     gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
     reduce_epi<M>(d, [&](int r, int, float v) {
@@ -489,9 +505,10 @@ __device__ __forceinline__ void enc_fwd(Dev& d, const EncP& p, const EncW& w, in
     });
   }
   cluster_sync();
+#pragma unroll
   for (int nb = 0; nb < NB; ++nb) {
     const int col = (d.rank * NB + nb) * 32 + d.lane;
-    const float bias = __ldg(p.b2 + col);
+    const float bias = bias_2[nb];
     const DropSpec d3 = site_of(dm, s0 + 3);
     gemm_block<M, T_FWD, FF>(*d.pipe, smem_addr(d.red), BIG, FF);
     reduce_epi<M>(d, [&](int r, int, float v) {
