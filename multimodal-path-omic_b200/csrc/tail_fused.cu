@@ -376,6 +376,12 @@ struct EncW { int x, qkv, probs, ctx, y1, xh1, rs1, f, y2, xh2, rs2, dy2, df2, d
 struct PoolP { const float *wa, *ba, *wb, *bb, *wc, *bc, *wr, *br; float *gwc, *gbc; };
 struct PoolW { int a, b, w, hp, dzr, da, db; };
 
+// ContextualAttentionGate of NaCAGaT (models/blocks.py:232-253)
+struct CagP { const float *w1, *b1, *w2, *b2, *w3, *b3, *wc, *bc, *gG, *bG, *gE, *bE; };
+struct CagW { int f1, f2, f3, u, w, Gg, Gxh, Grs, Ee, Exh, Ers, m, C, t0, dGg, dEe, df1, df2, df3; };
+__device__ __forceinline__ float elu_f(float v) { return v > 0.f ? v : expm1f(v); }
+__device__ __forceinline__ float elu_d(float y) { return y > 0.f ? 1.f : y + 1.f; }      // from the ELU output
+
 struct PathParams {
   Program prog;
   EncP enc[4];                 // path.0, path.1, omic.0, omic.1
@@ -397,6 +403,14 @@ struct PathParams {
   const float *dhaz_in, *dS_in, *dY_in;
   DropSpec d_model, d_quarter;
   int B, K, flags;
+  // NaCAGaT: CAG(G, q) added to the co-attention output (blocks.py:110-111); attention dropout leaves sum_n a' != 1
+  int nac;
+  CagP cag;
+  CagW cagw;
+  const float* qp;             // [B][6][256] projected queries (Q-hat of the CAG)
+  const float* suma;           // [B][6] or null
+  float* dsuma;                // [B][6] or null
+  int off_dqp;
 };
 static_assert(sizeof(PathParams) <= 8000, "kernel parameter space (large kernel parameters, CUDA 12.1+)");
 
@@ -906,9 +920,15 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
         for (int nb = 0; nb < NB; ++nb) {
           const int col = (d.rank * NB + nb) * 32 + d.lane;
           const float bias = __ldg(P.bv + col);
+          float sa[(M + NW - 1) / NW];        // v_i = W_v pooled_i + (sum_n a'_in) b_v   (blocks.py:189-192)
+#pragma unroll
+          for (int i = 0; i < (M + NW - 1) / NW; ++i) {
+            const int grow = d.grow0 + d.warp + NW * i;
+            sa[i] = (P.suma != nullptr && d.warp + NW * i < M && grow < d.Rtot) ? __ldcg(P.suma + grow) : 1.f;
+          }
           gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
-          reduce_epi<M>(d, [&](int r, int, float v) {
-            v += bias;
+          reduce_epi<M>(d, [&](int r, int i, float v) {
+            v = fmaf(bias, sa[i], v);
             bcast(XB + r * E + col, v);
             if (d.grow0 + r < d.Rtot) ws[P.off_v + static_cast<size_t>(d.grow0 + r) * E + col] = v;
           });
@@ -925,6 +945,71 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
           });
         }
         cluster_sync();
+        if (P.nac) {
+          // C = fc_c( LN_G(ELU(fc1 G + fc2 q)) * LN_E(ELU(fc3 q)) ), every fc = Linear + ELU; hc += C
+          const CagP& cp = P.cag;
+          const CagW& cw = P.cagw;
+          load_rows<M>(d, XB, ws + P.off_G, d.grow0, d.Rtot);
+          load_rows<M>(d, XC, P.qp, d.grow0, d.Rtot);
+          for (int nb = 0; nb < NB; ++nb) {
+            const int col = (d.rank * NB + nb) * 32 + d.lane;
+            const float b1 = __ldg(cp.b1 + col), b2 = __ldg(cp.b2 + col), b3 = __ldg(cp.b3 + col);
+            float f1v[(M + NW - 1) / NW];
+            gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XB, E);
+            reduce_epi<M>(d, [&](int r, int i, float v) {
+              v = elu_f(v + b1);
+              f1v[i] = v;
+              if (d.grow0 + r < d.Rtot) ws[cw.f1 + static_cast<size_t>(d.grow0 + r) * E + col] = v;
+            });
+            gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XC, E);
+            reduce_epi<M>(d, [&](int r, int i, float v) {
+              v = elu_f(v + b2);
+              const float u = elu_f(f1v[i] + v);
+              bcast(BIG + r * E + col, u);
+              if (d.grow0 + r < d.Rtot) {
+                ws[cw.f2 + static_cast<size_t>(d.grow0 + r) * E + col] = v;
+                ws[cw.u + static_cast<size_t>(d.grow0 + r) * E + col] = u;
+              }
+            });
+            gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XC, E);
+            reduce_epi<M>(d, [&](int r, int, float v) {
+              v = elu_f(v + b3);
+              const float wv = elu_f(v);
+              bcast(BIG + M * E + r * E + col, wv);
+              if (d.grow0 + r < d.Rtot) {
+                ws[cw.f3 + static_cast<size_t>(d.grow0 + r) * E + col] = v;
+                ws[cw.w + static_cast<size_t>(d.grow0 + r) * E + col] = wv;
+              }
+            });
+          }
+          cluster_sync();
+          ln_fwd_rows<M>(row_ctx(d), BIG, XB, cp.gG, cp.bG, ws + cw.Gg, ws + cw.Gxh, ws + cw.Grs);
+          ln_fwd_rows<M>(row_ctx(d), BIG + M * E, XC, cp.gE, cp.bE, ws + cw.Ee, ws + cw.Exh, ws + cw.Ers);
+          __syncthreads();
+          for (int i = d.t; i < M * E; i += NT) {
+            const int r = i / E, grow = d.grow0 + r;
+            const float mv = XB[i] * XC[i];
+            XB[i] = mv;
+            if (grow < d.Rtot && (r % CL) == d.rank) ws[cw.m + static_cast<size_t>(grow) * E + (i - r * E)] = mv;
+          }
+          for (int nb = 0; nb < NB; ++nb) {
+            const int col = (d.rank * NB + nb) * 32 + d.lane;
+            const float bc = __ldg(cp.bc + col);
+            gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XB, E);
+            reduce_epi<M>(d, [&](int r, int, float v) {
+              v = elu_f(v + bc);
+              const float hv = XA[r * E + col] + v;
+              bcast(BIG + 2 * M * E + r * E + col, hv);
+              if (d.grow0 + r < d.Rtot) {
+                ws[cw.C + static_cast<size_t>(d.grow0 + r) * E + col] = v;
+                ws[P.off_hc + static_cast<size_t>(d.grow0 + r) * E + col] = hv;
+              }
+            });
+          }
+          cluster_sync();
+          for (int i = d.t; i < M * E; i += NT) XA[i] = BIG[2 * M * E + i];
+          __syncthreads();
+        }
       }
 #pragma unroll 1
       for (int l = 0; l < 2; ++l) enc_fwd<S>(d, P.enc[2 * br + l], P.encw[2 * br + l], 2 * br + l, dm, XA, XB, XC, BIG, QKVL);
@@ -1125,12 +1210,92 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
       });
     }
     cluster_sync();
+    if (P.dsuma != nullptr) {       // d(sum_n a'_in) = dv_i . b_v
+      for (int r = d.warp; r < M; r += NW) {
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v = fmaf(XB[r * E + d.lane + 32 * j], __ldg(P.bv + d.lane + 32 * j), v);
+        v = warp_sum(v);
+        if (d.lane == 0 && d.rank == 0 && d.grow0 + r < d.Rtot) P.dsuma[d.grow0 + r] = v;
+      }
+    }
     for (int nb = 0; nb < NB; ++nb) {
       const int col = (d.rank * NB + nb) * 32 + d.lane;
       gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XB, E);
       reduce_epi<M>(d, [&](int r, int, float v) {
         if (d.grow0 + r < d.Rtot) P.dpooled[static_cast<size_t>(d.grow0 + r) * E + col] = v;
       });
+    }
+    if (P.nac) {
+      // CAG backward (autograd of blocks.py:247-253): dC = d(hc) -> dQ accumulated into dG, dQ-hat written to dqp
+      const CagP& cp = P.cag;
+      const CagW& cw = P.cagw;
+      cluster_sync();
+      load_rows<M>(d, XA, ws + P.off_dhc, d.grow0, d.Rtot);
+      __syncthreads();
+      for (int i = d.t; i < M * E; i += NT) {          // t0 = dC * ELU'(C): gradient at fc_c's pre-activation
+        const int r = i / E, c = i - r * E, grow = d.grow0 + r;
+        const bool valid = grow < d.Rtot;
+        const float Cv = valid ? __ldcg(ws + cw.C + static_cast<size_t>(grow) * E + c) : 0.f;
+        const float t0 = XA[i] * elu_d(Cv);
+        XB[i] = t0;
+        if (valid && (r % CL) == d.rank) ws[cw.t0 + static_cast<size_t>(grow) * E + c] = t0;
+      }
+      for (int nb = 0; nb < NB; ++nb) {                // dm = t0 W_c ; dGg = dm * Ee, dEe = dm * Gg
+        const int col = (d.rank * NB + nb) * 32 + d.lane;
+        float ee[(M + NW - 1) / NW], gg[(M + NW - 1) / NW];
+#pragma unroll
+        for (int i = 0; i < (M + NW - 1) / NW; ++i) {
+          const int r = d.warp + NW * i, grow = d.grow0 + r;
+          const bool valid = r < M && grow < d.Rtot;
+          ee[i] = valid ? __ldcg(ws + cw.Ee + static_cast<size_t>(grow) * E + col) : 0.f;
+          gg[i] = valid ? __ldcg(ws + cw.Gg + static_cast<size_t>(grow) * E + col) : 0.f;
+        }
+        gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XB, E);
+        reduce_epi<M>(d, [&](int r, int i, float v) {
+          bcast(BIG + r * E + col, v * ee[i]);
+          bcast(BIG + M * E + r * E + col, v * gg[i]);
+        });
+      }
+      cluster_sync();
+      // du -> XB, dw -> XC (XA is scratch for the unused dropout output; df1 is rewritten below)
+      ln_bwd_rows<M>(row_ctx(d), BIG, XB, XA, cp.gG, ws + cw.Gxh, ws + cw.Grs, ws + cw.dGg, ws + cw.df1, DropSpec{});
+      ln_bwd_rows<M>(row_ctx(d), BIG + M * E, XC, XA, cp.gE, ws + cw.Exh, ws + cw.Ers, ws + cw.dEe, ws + cw.df1, DropSpec{});
+      __syncthreads();
+      for (int i = d.t; i < M * E; i += NT) {          // gradients at the pre-activations of fc1, fc2, fc3 (all columns)
+        const int r = i / E, c = i - r * E, grow = d.grow0 + r;
+        const bool valid = grow < d.Rtot;
+        const size_t o = static_cast<size_t>(grow) * E + c;
+        const float u = valid ? __ldcg(ws + cw.u + o) : 0.f, f1 = valid ? __ldcg(ws + cw.f1 + o) : 0.f;
+        const float f2 = valid ? __ldcg(ws + cw.f2 + o) : 0.f, wv = valid ? __ldcg(ws + cw.w + o) : 0.f;
+        const float f3 = valid ? __ldcg(ws + cw.f3 + o) : 0.f;
+        const float dsum = XB[i] * elu_d(u);
+        const float d1 = dsum * elu_d(f1), d2 = dsum * elu_d(f2), d3 = XC[i] * elu_d(wv) * elu_d(f3);
+        BIG[r * FF + c] = d3;
+        BIG[r * FF + E + c] = d2;
+        XA[i] = d1;
+        if (valid && (r % CL) == d.rank) { ws[cw.df1 + o] = d1; ws[cw.df2 + o] = d2; ws[cw.df3 + o] = d3; }
+      }
+      for (int nb = 0; nb < NB; ++nb) {                // dQ-hat = df3 W_3 + df2 W_2
+        const int col = (d.rank * NB + nb) * 32 + d.lane;
+        gemm_block<M, T_DGRAD, FF>(*d.pipe, smem_addr(d.red), BIG, FF);
+        reduce_epi<M>(d, [&](int r, int, float v) {
+          if (d.grow0 + r < d.Rtot) ws[P.off_dqp + static_cast<size_t>(d.grow0 + r) * E + col] = v;
+        });
+      }
+      for (int nb = 0; nb < NB; ++nb) {                // dQ = df1 W_1, added to the omic branch's dG
+        const int col = (d.rank * NB + nb) * 32 + d.lane;
+        float dg0[(M + NW - 1) / NW];
+#pragma unroll
+        for (int i = 0; i < (M + NW - 1) / NW; ++i) {
+          const int r = d.warp + NW * i, grow = d.grow0 + r;
+          dg0[i] = (r < M && grow < d.Rtot) ? __ldcg(ws + P.off_dG + static_cast<size_t>(grow) * E + col) : 0.f;
+        }
+        gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XA, E);
+        reduce_epi<M>(d, [&](int r, int i, float v) {
+          if (d.grow0 + r < d.Rtot) ws[P.off_dG + static_cast<size_t>(d.grow0 + r) * E + col] = v + dg0[i];
+        });
+      }
     }
   }
   cp_async_wait<0>();
@@ -1151,6 +1316,12 @@ struct PreParams {
   int off_snn_h[MPO_Q], off_G, off_dqp, off_dG, off_snn_dz1[MPO_Q], off_snn_dz2[MPO_Q];
   DropSpec d_alpha;
   int B;
+  // NaCAGaT: key-bias score term kc = q . b_k / 16 (forward) and the extra gradient paths into q (backward)
+  int nac;
+  const float* bk;             // co_attention.in_proj_bias[256:512]
+  float* kc;                   // [B][6] out of pre_kernel
+  const float* dkc;            // [B][6]      from the bag backward
+  const float* dtq;            // [B][6][256] gradient w.r.t. tanh(q) from the bag backward
 };
 static_assert(sizeof(PreParams) <= 4000, "kernel parameter space");
 
@@ -1238,6 +1409,15 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
     });
   }
   cluster_sync();
+  if (P.nac && d.rank == 0) {
+    for (int r = d.warp; r < M; r += NW) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v = fmaf(QP[r * E + d.lane + 32 * j], __ldg(P.bk + d.lane + 32 * j), v);
+      v = warp_sum(v);
+      if (d.lane == 0 && d.grow0 + r < d.Rtot) P.kc[d.grow0 + r] = v * (1.f / 16.f);
+    }
+  }
   for (int nb = 0; nb < NB; ++nb) {
     const int col = (d.rank * NB + nb) * 32 + d.lane;
     gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), QP, E);
@@ -1273,9 +1453,22 @@ __global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ 
   // dq[r][e] = sum_d dqk[r][d] W_k[e][d] / 16
   for (int nb = 0; nb < NB; ++nb) {
     const int col = (d.rank * NB + nb) * 32 + d.lane;
+    // NaCAGaT: + the CAG's dQ-hat (left in dqp by the path kernel) + dkc b_k / 16 + dtq (1 - tanh(q)^2)
+    float extra[(M + NW - 1) / NW];
+#pragma unroll
+    for (int i = 0; i < (M + NW - 1) / NW; ++i) {
+      const int r = d.warp + NW * i, grow = d.grow0 + r;
+      extra[i] = 0.f;
+      if (P.nac && r < M && grow < d.Rtot) {
+        const size_t o = static_cast<size_t>(grow) * E + col;
+        const float tq = tanhf(__ldcg(P.qp + o));
+        extra[i] = __ldcg(ws + P.off_dqp + o) + __ldcg(P.dkc + grow) * __ldg(P.bk + col) * (1.f / 16.f) +
+                   __ldcg(P.dtq + o) * (1.f - tq * tq);
+      }
+    }
     gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
-    reduce_epi<M>(d, [&](int r, int, float v) {
-      v *= (1.f / 16.f);
+    reduce_epi<M>(d, [&](int r, int i, float v) {
+      v = fmaf(v, 1.f / 16.f, extra[i]);
       bcast(XB + r * E + col, v);
       if (d.grow0 + r < d.Rtot) ws[P.off_dqp + static_cast<size_t>(d.grow0 + r) * E + col] = v;
     });
@@ -1334,12 +1527,13 @@ struct WJob {
   const float* x;
   float* gw;
   float* gb;
+  const float* rw;       // optional per-row weights of the bias gradient (gb[o] += sum_r rw[r] dz[r][o]); null = 1
   int lddz, ldx, out, in, rows, tile0, kind;
   float alpha;
 };
 constexpr int MAX_JOBS = 60;
 struct WParams { WJob job[MAX_JOBS]; int njobs; int ntiles; };
-static_assert(sizeof(WParams) <= 4000, "kernel parameter space");
+static_assert(sizeof(WParams) <= 8000, "kernel parameter space (large kernel parameters, CUDA 12.1+)");
 
 __global__ void __launch_bounds__(256) wgrad_kernel(const __grid_constant__ WParams P) {
   __shared__ __align__(16) float As[2][32][64 + 4];
@@ -1408,8 +1602,12 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const __grid_constant__ WPar
         for (int bb = 0; bb < 4; ++bb) acc[aa][bb] = fmaf(av[aa], bv[bb], acc[aa][bb]);
     }
     if (J.gb != nullptr && i0 == 0 && t < 64) {
+      if (J.rw == nullptr) {
 #pragma unroll
-      for (int kk = 0; kk < 32; ++kk) bsum += As[buf][kk][t];
+        for (int kk = 0; kk < 32; ++kk) bsum += As[buf][kk][t];
+      } else {
+        for (int kk = 0; kk < 32 && s * 32 + kk < J.rows; ++kk) bsum = fmaf(__ldcg(J.rw + s * 32 + kk), As[buf][kk][t], bsum);
+      }
     }
     if (s + 1 < nsteps) store(buf ^ 1);
     __syncthreads();
@@ -1431,12 +1629,12 @@ struct JobBuilder {
   WParams& p;
   bool ok = true;
   void push(int kind, const float* dz, int lddz, const float* x, int ldx, float* gw, float* gb, int out, int in, int rows,
-            float alpha) {
+            float alpha, const float* rw = nullptr) {
     if (gw == nullptr) return;
     if (p.njobs >= MAX_JOBS) { ok = false; return; }
     WJob& j = p.job[p.njobs++];
     j.dz = dz; j.x = x; j.gw = gw; j.gb = gb; j.lddz = lddz; j.ldx = ldx; j.out = out; j.in = in; j.rows = rows;
-    j.kind = kind; j.alpha = alpha; j.tile0 = p.ntiles;
+    j.kind = kind; j.alpha = alpha; j.tile0 = p.ntiles; j.rw = rw;
     p.ntiles += kind == 1 ? (out + 63) / 64 : ((out + 63) / 64) * ((in + 63) / 64);
   }
   void lin(const float* dz, int lddz, const float* x, int ldx, const mpo_lin& L, int out, int in, int rows, float alpha = 1.f) {
@@ -1494,8 +1692,13 @@ int slides_per_cluster(int B) {
 bool eligible(const mpo_model* m, const mpo_tail_io* io) {
   const char* env = getenv("MPO_TAIL_FUSED");        // read on every call: tests flip it to compare the two tails
   if (env != nullptr && atoi(env) == 0) return false;
-  if (m->variant != MPO_VARIANT_MCAT || m->fusion != MPO_FUSION_CONCAT) return false;
-  if (m->n_classes > MAXK || io->suma != nullptr) return false;
+  if (m->fusion != MPO_FUSION_CONCAT) return false;                      // bilinear fusion: per-op tail
+  if (m->variant != MPO_VARIANT_MCAT && m->variant != MPO_VARIANT_NACAGAT) return false;
+  if (m->n_classes > MAXK) return false;
+  if (m->variant == MPO_VARIANT_NACAGAT) {
+    const char* e2 = getenv("MPO_TAIL_FUSED_NACAGAT");
+    if (e2 != nullptr && atoi(e2) == 0) return false;
+  }
   for (int i = 0; i < MPO_Q; ++i)
     if (m->omic_dims[i] % 4 != 0 || m->omic_dims[i] > OMIC_LD || m->omic_dims[i] < 4) return false;
   return true;
@@ -1519,11 +1722,15 @@ static void fill_pre(const mpo_model* m, const mpo_tail_io* io, const Ws& w, Pre
   P.off_G = static_cast<int>(w.G); P.off_dqp = static_cast<int>(w.dqp); P.off_dG = static_cast<int>(w.dG);
   P.d_alpha = host_drop(io, io->drop_p, true);
   P.B = io->num_slides;
+  P.nac = m->variant == MPO_VARIANT_NACAGAT ? 1 : 0;
+  P.bk = m->coattn_in.b + E;
+  P.kc = io->kc; P.dkc = io->dkc; P.dtq = io->dtq;
 }
 
 int pre_fwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t st) {
   static PreParams P;
   fill_pre(m, io, w, P);
+  if (P.nac && !io->kc) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_fwd: kc is NULL (NaCAGaT)");
   ProgBuilder pb{P.prog};
   for (int i = 0; i < MPO_Q; ++i) pb.fwd(m->snn[i][0].w, m->omic_dims[i], m->omic_dims[i], NB, 32 * NB);
   for (int i = 0; i < MPO_Q; ++i) pb.fwd(m->snn[i][1].w, E, E, NB, 32 * NB);
@@ -1571,6 +1778,7 @@ static int launch_wgrad(const WParams& W, cudaStream_t st) {
 int pre_bwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t st) {
   static PreParams P;
   fill_pre(m, io, w, P);
+  if (P.nac && (!io->dkc || !io->dtq)) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_bwd: dkc/dtq are NULL (NaCAGaT)");
   ProgBuilder pb{P.prog};
   pb.fwd(m->coattn_in.w + static_cast<size_t>(E) * E, E, E, NB, 32 * NB);
   pb.dgrad(m->coattn_in.w, E, E, NB, 32 * NB);
@@ -1594,6 +1802,8 @@ int pre_bwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t
   jb.lin(ws + w.dqp, E, ws + w.G, E, Lq, E, E, R);
   mpo_lin Lk = {nullptr, nullptr, m->coattn_in.gw ? m->coattn_in.gw + static_cast<size_t>(E) * E : nullptr, nullptr};
   jb.lin(io->qp, E, io->dqk, E, Lk, E, E, R, 1.f / 16.f);
+  if (P.nac && m->coattn_in.gb != nullptr)      // kc = q . b_k / 16 :  db_k[e] += sum_r dkc[r] q[r][e] / 16
+    jb.push(0, io->dkc, 1, io->qp, E, m->coattn_in.gb + E, nullptr, 1, E, R, 1.f / 16.f);
   if (!jb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: job table overflow");
   rc = launch_wgrad(W, st);
   if (rc) return rc;
@@ -1648,6 +1858,21 @@ int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, cons
   P.d_model = host_drop(io, io->drop_p, false);
   P.d_quarter = host_drop(io, 0.25f, false);        // AttentionNetGated hard-codes p = 0.25 (blocks.py:34-36)
   P.B = B; P.K = K; P.flags = flags;
+  const bool nac = m->variant == MPO_VARIANT_NACAGAT;
+  P.nac = nac ? 1 : 0;
+  if (nac) {
+    if (!io->qp) return fail(MPO_E_ARG, "%s", "fused tail: qp is NULL (NaCAGaT)");
+    if ((flags & F_BWD) && io->suma != nullptr && !io->dsuma) return fail(MPO_E_ARG, "%s", "fused tail: dsuma is NULL although suma is given");
+    const mpo_cag& C = m->cag;
+    P.cag = CagP{C.fc1.w, C.fc1.b, C.fc2.w, C.fc2.b, C.fc3.w, C.fc3.b, C.fc_c.w, C.fc_c.b, C.G.g, C.G.b, C.E.g, C.E.b};
+    P.cagw = CagW{(int)w.cag_f1, (int)w.cag_f2, (int)w.cag_f3, (int)w.cag_u, (int)w.cag_w, (int)w.cag_Gg, (int)w.cag_Gxh,
+                  (int)w.cag_Grs, (int)w.cag_Ee, (int)w.cag_Exh, (int)w.cag_Ers, (int)w.cag_m, (int)w.cag_C,
+                  (int)w.fz_cag[0], (int)w.fz_cag[1], (int)w.fz_cag[2], (int)w.fz_cag[3], (int)w.fz_cag[4], (int)w.fz_cag[5]};
+    P.qp = io->qp;
+    P.suma = io->suma;
+    P.dsuma = io->suma != nullptr ? io->dsuma : nullptr;
+  }
+  P.off_dqp = (int)w.dqp;
 
   ProgBuilder pb{P.prog};
   // chunk order = consumption order of the device code; a CTA owns NB column blocks of every 256-wide layer
@@ -1680,6 +1905,14 @@ int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, cons
   if (flags & F_FWD) {
     enc_f(m->omic_tr[0]); enc_f(m->omic_tr[1]); pool_f(m->omic_pool);
     pb.fwd(Wv, E, E, NB, 32 * NB); pb.fwd(m->coattn_out.w, E, E, NB, 32 * NB);
+    if (nac) {
+      for (int nb = 0; nb < NB; ++nb) {
+        pb.fwd(m->cag.fc1.w, E, E, 1, 32 * NB, 32, nb * 32);
+        pb.fwd(m->cag.fc2.w, E, E, 1, 32 * NB, 32, nb * 32);
+        pb.fwd(m->cag.fc3.w, E, E, 1, 32 * NB, 32, nb * 32);
+      }
+      pb.fwd(m->cag.fc_c.w, E, E, NB, 32 * NB);
+    }
     enc_f(m->path_tr[0]); enc_f(m->path_tr[1]); pool_f(m->path_pool);
     pb.fwd(m->fusion0.w, 2 * E, 2 * E, NB, 32 * NB); pb.fwd(m->fusion2.w, E, E, NB, 32 * NB);
   }
@@ -1689,6 +1922,14 @@ int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, cons
     pool_b(m->omic_pool); enc_b(m->omic_tr[1]); enc_b(m->omic_tr[0]);
     pool_b(m->path_pool); enc_b(m->path_tr[1]); enc_b(m->path_tr[0]);
     pb.dgrad(m->coattn_out.w, E, E, NB, 32 * NB); pb.dgrad(Wv, E, E, NB, 32 * NB);
+    if (nac) {
+      pb.dgrad(m->cag.fc_c.w, E, E, NB, 32 * NB);
+      for (int nb = 0; nb < NB; ++nb) {
+        pb.dgrad(m->cag.fc3.w, E, E, 1, 32 * NB, 32, nb * 32);
+        pb.dgrad(m->cag.fc2.w, E, E, 1, 32 * NB, 32, nb * 32);
+      }
+      pb.dgrad(m->cag.fc1.w, E, E, NB, 32 * NB);
+    }
   }
   if (!pb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
   const int S = slides_per_cluster(B), ncl = (B + S - 1) / S;
@@ -1725,7 +1966,17 @@ int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, cons
   jb.lin(ws + w.dhc, E, ws + w.v, E, m->coattn_out, E, E, R);
   mpo_lin Lv = {nullptr, nullptr, m->coattn_in.gw ? m->coattn_in.gw + static_cast<size_t>(2 * E) * E : nullptr,
                 m->coattn_in.gb ? m->coattn_in.gb + 2 * E : nullptr};
-  jb.lin(ws + w.dv, E, io->pooled, E, Lv, E, E, R);
+  // with attention dropout the value bias enters as (sum_n a'_in) b_v: its gradient is weighted by suma
+  jb.push(0, ws + w.dv, E, io->pooled, E, Lv.gw, Lv.gb, E, E, R, 1.f, nac ? io->suma : nullptr);
+  if (nac) {
+    const mpo_cag& C = m->cag;
+    jb.lin(ws + w.fz_cag[0], E, ws + w.cag_m, E, C.fc_c, E, E, R);
+    jb.lin(ws + w.fz_cag[5], E, io->qp, E, C.fc3, E, E, R);
+    jb.lin(ws + w.fz_cag[4], E, io->qp, E, C.fc2, E, E, R);
+    jb.lin(ws + w.fz_cag[3], E, ws + w.G, E, C.fc1, E, E, R);
+    jb.norm(ws + w.fz_cag[1], ws + w.cag_Gxh, C.G, R);
+    jb.norm(ws + w.fz_cag[2], ws + w.cag_Exh, C.E, R);
+  }
   if (!jb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: job table overflow");
   SideStream& side = side_stream();
   if (side_wgrad && side.state == 1) {

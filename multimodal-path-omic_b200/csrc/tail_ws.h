@@ -48,6 +48,7 @@ struct Ws {
   // output keeps its own buffer until the grouped weight-gradient kernel has consumed it
   struct FzEnc { long long dy2, df2, df, dy1, dsa, dqkv; } fz_enc[4];
   struct FzPool { long long dzr, da, db; } fz_pool[2];
+  long long fz_cag[6];     // NaCAGaT CAG: t0 (d fc_c pre-activation), dGg, dEe, df1, df2, df3
   Layout lay;
 };
 
@@ -122,6 +123,10 @@ inline void build_layout(const mpo_model* m, int B, Ws& w) {
     auto A = [&](const char* s, long long n) { snprintf(nm, sizeof nm, "fz_%s_%s", en[e], s); return L.add(nm, n); };
     w.fz_enc[e].dy2 = A("dy2", R * E); w.fz_enc[e].df2 = A("df2", R * E); w.fz_enc[e].df = A("df", R * FF);
     w.fz_enc[e].dy1 = A("dy1", R * E); w.fz_enc[e].dsa = A("dsa", R * E); w.fz_enc[e].dqkv = A("dqkv", R * 3 * E);
+  }
+  if (m->variant == MPO_VARIANT_NACAGAT) {
+    const char* cn[6] = {"t0", "dGg", "dEe", "df1", "df2", "df3"};
+    for (int i = 0; i < 6; ++i) { snprintf(nm, sizeof nm, "fz_cag_%s", cn[i]); w.fz_cag[i] = L.add(nm, R * E); }
   }
   for (int p = 0; p < 2; ++p) {
     auto A = [&](const char* s, long long n) { snprintf(nm, sizeof nm, "fz_%s_%s", pn[p], s); return L.add(nm, n); };

@@ -12,12 +12,15 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 train = (sys.argv[3] == "train") if len(sys.argv) > 3 else False
 dev = torch.device("cuda", 0)
-cls = import_module(pkg + "mcat").MultimodalCoAttentionTransformer
+model_name = sys.argv[4] if len(sys.argv) > 4 else "mcat"
+cls = (import_module(pkg + "mcat").MultimodalCoAttentionTransformer if model_name == "mcat"
+       else import_module(pkg + "nacagat").NarrowContextualAttentionGateTransformer)
 names = ["G", "v", "hc", "cat", "z1", "z2", "logits", "dlogits", "dz1", "dz2", "dhc", "dv", "dG", "dqp"]
 for e in ("path0", "path1", "omic0", "omic1"):
     names += ["%s_%s" % (e, s) for s in ("qkv", "probs", "ctx", "y1", "xh1", "rs1", "f", "y2", "xh2", "rs2")]
 for p in ("pathpool", "omicpool"):
     names += ["%s_%s" % (p, s) for s in ("a", "b", "w", "hp")]
+names += ["cag_" + n for n in ("f1", "f2", "f3", "u", "w", "Gg", "Gxh", "Ee", "Exh", "m", "C")]
 names += ["snn_h%d" % i for i in range(6)] + ["snn_dz1_%d" % i for i in range(6)] + ["snn_dz2_%d" % i for i in range(6)]
 
 def run(fused):
@@ -37,6 +40,10 @@ def run(fused):
     out = {"loss": loss.clone(), "hazards": hz.clone(), "S": S.clone(), "att_path": st.att_path.clone(),
            "att_omic": st.att_omic.clone(), "qp": st.qp.clone(), "qk": st.qk.clone(), "dpooled": st.dpooled.clone(),
            "dqk": st.dqk.clone(), "pooled": st.bag_ws.pooled.clone()}
+    if st.kc is not None:
+        out["kc"] = st.kc.clone()
+    if st.dsuma is not None and train:
+        out["dsuma"] = st.dsuma.clone()
     for n in names:
         try:
             out["ws." + n] = tr.engine.ws_view(tr.model, st, n).clone()

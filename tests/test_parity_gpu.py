@@ -145,16 +145,20 @@ def test_batched_trainer_equals_per_slide_gradients():
         assert err < 2e-3, (k, err)
 
 
-@pytest.mark.parametrize("slides_per_cluster,train", [(1, True), (2, True), (2, False)])
-def test_fused_cluster_tail_equals_per_op_tail(slides_per_cluster, train, monkeypatch):
-    """The fused cluster tail (csrc/tail_fused.cu: three cluster kernels + one grouped weight-gradient kernel) and the
-    per-op tail (csrc/tail.cu) are two implementations of the same step: same dropout masks (stateless RNG keyed by
+@pytest.mark.parametrize("case_name,slides_per_cluster,train,loss_kind",
+                         [("mcat_concat_sharp_517", 1, True, "nll"), ("mcat_concat_sharp_517", 2, True, "ces"),
+                          ("mcat_concat_sharp_517", 2, False, "nll"), ("nacagat_concat_sharp_517", 1, True, "nll"),
+                          ("nacagat_concat_sharp_517", 2, False, "ces")])
+def test_fused_cluster_tail_equals_per_op_tail(case_name, slides_per_cluster, train, loss_kind, monkeypatch):
+    """The fused cluster tail (csrc/tail_fused.cu: three cluster kernels + one grouped weight-gradient kernel; MCAT and
+    NaCAGaT with its CAG / attention-dropout terms) and the per-op tail (csrc/tail.cu) are two implementations of the
+    same step: same dropout masks (stateless RNG keyed by
     seed / site / element), so losses, hazards, d(pooled) and every parameter gradient must agree to fp32 rounding.
     Ragged batch of 5 slides: the second slide slot of the last 2-slide cluster is empty."""
     synth = _pkg("synth")
     sp = _pkg("slidepath")
     bpm = _pkg("bagpass")
-    case = load_case("mcat_concat_sharp_517")
+    case = load_case(case_name)
     lens = [300, 129, 1, 517, 64]
     slides = [synth.make_slide(300 + i, n) for i, n in enumerate(lens)]
     pb = bpm.PackedBag.from_slides([torch.from_numpy(s[0]).cuda() for s in slides])
@@ -167,7 +171,7 @@ def test_fused_cluster_tail_equals_per_op_tail(slides_per_cluster, train, monkey
         monkeypatch.setenv("MPO_TAIL_FUSED", fused)
         net = build_model(case)
         net.train() if train else net.eval()
-        tr = sp.BatchTrainer(net, loss="nll", grad_acc_step=len(lens))
+        tr = sp.BatchTrainer(net, loss=loss_kind, grad_acc_step=len(lens))
         tr.zero_grad()
         loss, hz, S = tr.step(pb, om, labels, cens, train=train, seed=4242)
         torch.cuda.synchronize()
