@@ -458,6 +458,28 @@ def run_ours(args, rank, world, local_rank):
             "note": "first functional version: fp32 CUDA-core GEMMs, N x N attention materialised (DESIGN.md 4.5)"}
         del gnet
         torch.cuda.empty_cache()
+        # BASELINE config 5: MCAT inference on one 200 000-patch bag.  One GPU streams the whole bag here; under the
+        # 8-way patch-range sharding of dp.sharded_inference each GPU streams 25 000 patches (second entry) and the
+        # combine adds one all-gather of 6 x 257 floats.
+        inet = import_module(pkg + "mcat").MultimodalCoAttentionTransformer(omic_sizes=list(synth.OMIC_SIZES)).to(dev).eval()
+        iom = [torch.randn(d, generator=gen, device=dev) for d in synth.OMIC_SIZES]
+        for tag, n_inf in (("mcat_inference_200000_patches_1gpu", 200000), ("mcat_inference_25000_patch_shard", 25000)):
+            n_inf = min(n_inf, B * N)
+            wsi = x[:n_inf]
+            with torch.no_grad():
+                for _ in range(2):
+                    inet(wsi, iom, inference=True)
+                torch.cuda.synchronize()
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(5):
+                    inet(wsi, iom, inference=True)
+                b_.record(); torch.cuda.synchronize()
+            msi = a.elapsed_time(b_) / 5
+            also[tag] = {"ms_per_bag": msi, "patches": n_inf, "bag_GBps": n_inf * 2048 / (msi * 1e-3) / 1e9,
+                         "note": "eager module call (forward + attention map), CUDA events"}
+        del inet
+        torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -270,13 +270,158 @@ inline void launch_gemm_fullk(const GemmArgs& g, cudaStream_t st) {
   else launch_k(gemm_fullk_kernel<false, false>, dim3(grid), dim3(256), smem, st, g);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Throughput variant for the bag-scale fp32 GEMMs of GE-NaCAGaT (N x N attention over the patches): 128 x 128 tiles
+// (or 256 x 32 when the output is only a head wide), 16-deep K steps, 8 x 8 (8 x 4) outputs per thread accumulated
+// with packed FFMA2 (fma.rn.f32x2: two fp32 FMAs per instruction), double-buffered shared memory, global loads of
+// step k + 1 in flight during the math of step k.  Same contract as gemm_kernel for the epilogues it supports
+// (alpha, bias, accumulate, activation).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long gb_pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long gb_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+template <int BN, bool A_KC, bool B_NC>
+__global__ void __launch_bounds__(256) gemm_big_kernel(const GemmArgs g) {
+  constexpr int BK = 16;
+  constexpr int TX = BN == 128 ? 16 : 8;        // thread columns
+  constexpr int TY = 256 / TX;                  // thread rows (16 or 32)
+  constexpr int BM = TY * 8;                    // 128 or 256
+  constexpr int CN = BN / TX;                   // output columns per thread: 8 (two float4 halves) or 4
+  constexpr int A_PER = BM * BK / 256, B_PER = BN * BK / 256;
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int t = threadIdx.x, tx = t % TX, ty = t / TX;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  unsigned long long acc[8][CN / 2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < CN / 2; ++j) acc[i][j] = 0ull;
+  float ra[A_PER], rb[B_PER];
+  auto a_pos = [&](int j, int& mm, int& kk) {
+    if (A_KC) { kk = t & 15; mm = (t >> 4) + 16 * j; } else { mm = t % BM; kk = t / BM + (256 / BM) * j; }
+  };
+  auto b_pos = [&](int j, int& nn, int& kk) {
+    if (B_NC) { nn = t % BN; kk = t / BN + (256 / BN) * j; } else { kk = t & 15; nn = (t >> 4) + 16 * j; }
+  };
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j) {
+      int mm, kk; a_pos(j, mm, kk);
+      const long long m = m0 + mm, k = k0 + kk;
+      ra[j] = (m < g.M && k < g.K) ? __ldg(g.A + m * g.sa_m + k * g.sa_k) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < B_PER; ++j) {
+      int nn, kk; b_pos(j, nn, kk);
+      const long long n = n0 + nn, k = k0 + kk;
+      rb[j] = (n < g.N && k < g.K) ? __ldg(g.B + k * g.sb_k + n * g.sb_n) : 0.f;
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j) { int mm, kk; a_pos(j, mm, kk); As[buf][kk][mm] = ra[j]; }
+#pragma unroll
+    for (int j = 0; j < B_PER; ++j) { int nn, kk; b_pos(j, nn, kk); Bs[buf][kk][nn] = rb[j]; }
+  };
+  pdl_enter();
+  const int nsteps = (g.K + BK - 1) / BK;
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (int s = 0; s < nsteps; ++s) {
+    const int buf = s & 1;
+    if (s + 1 < nsteps) load_tile((s + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      // rows ty*4 .. +3 and BM/2 + ty*4 .. +3; columns tx*4 .. +3 (and BN/2 + tx*4 .. +3): conflict-free float4 reads
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][BM / 2 + ty * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      unsigned long long bv[CN / 2];
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+        bv[0] = gb_pack2(b0.x, b0.y); bv[1] = gb_pack2(b0.z, b0.w);
+        if (CN == 8) {
+          const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][BN / 2 + tx * 4]);
+          bv[CN / 2 - 2] = gb_pack2(b1.x, b1.y); bv[CN / 2 - 1] = gb_pack2(b1.z, b1.w);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const unsigned long long aa = gb_pack2(av[i], av[i]);
+#pragma unroll
+        for (int j = 0; j < CN / 2; ++j) acc[i][j] = gb_fma2(aa, bv[j], acc[i][j]);
+      }
+    }
+    if (s + 1 < nsteps) store_tile(buf ^ 1);
+    __syncthreads();
+  }
+  // epilogue: each thread owns groups of 4 consecutive columns -> one 16-byte store per row and group when aligned
+  const bool vec_ok = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long m = m0 + (i < 4 ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int grp = 0; grp < CN / 4; ++grp) {
+      const long long nb = n0 + (grp == 0 ? tx * 4 : BN / 2 + tx * 4);
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i][grp * 2 + j]));
+        v[2 * j] = lo; v[2 * j + 1] = hi;
+      }
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        v[h] *= g.alpha;
+        if (g.bias != nullptr && nb + h < g.N) v[h] += g.bias[nb + h];
+        v[h] = act_fwd(v[h], g.act);
+      }
+      float* c = g.C + m * g.ldc + nb;
+      if (vec_ok && nb + 3 < g.N) {
+        float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        if (g.accumulate) { const float4 p = *reinterpret_cast<const float4*>(c); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+        *reinterpret_cast<float4*>(c) = o;
+      } else {
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+          if (nb + h < g.N) c[h] = g.accumulate ? (c[h] + v[h]) : v[h];
+      }
+    }
+  }
+}
+template <int BN>
+inline void launch_gemm_big(const GemmArgs& g, cudaStream_t st) {
+  constexpr int BM = BN == 128 ? 128 : 256;
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+  const bool akc = (g.sa_k == 1), bnc = (g.sb_n == 1);
+  if (akc && bnc) launch_k(gemm_big_kernel<BN, true, true>, dim3(grid), dim3(256), 0, st, g);
+  else if (akc && !bnc) launch_k(gemm_big_kernel<BN, true, false>, dim3(grid), dim3(256), 0, st, g);
+  else if (!akc && bnc) launch_k(gemm_big_kernel<BN, false, true>, dim3(grid), dim3(256), 0, st, g);
+  else launch_k(gemm_big_kernel<BN, false, false>, dim3(grid), dim3(256), 0, st, g);
+}
+
 inline cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
   static int mode = -1;
   if (mode < 0) { const char* e = getenv("MPO_TAIL_GEMM"); mode = e ? atoi(e) : 1; }
   const long long blocks32 = static_cast<long long>((g.N + 31) / 32) * ((g.M + 31) / 32);
   pdl_kind() = 1;
-  if (mode == 1 && blocks32 <= 1184 && g.K <= 4 * kFkBK) {
+  const bool plain = g.rowsum == nullptr && g.drop.thr == 0 && g.addend == nullptr && g.bwd_y == nullptr;
+  static int big = -1;
+  if (big < 0) { const char* e = getenv("MPO_GEMM_BIG"); big = e ? atoi(e) : 1; }
+  if (big && plain && g.M >= 256 && static_cast<long long>(g.M) * g.N * g.K >= (1LL << 24)) {
+    if (g.N >= 96) launch_gemm_big<128>(g, st); else launch_gemm_big<32>(g, st);      // bag-scale GEMMs (GE-NaCAGaT)
+  } else if (mode == 1 && blocks32 <= 1184 && g.K <= 4 * kFkBK) {
     pdl_kind() = 2;
     launch_gemm_fullk(g, st);                  // the latency-bound regime of the slide tail
   } else {

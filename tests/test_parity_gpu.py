@@ -186,9 +186,10 @@ def test_fused_cluster_tail_equals_per_op_tail(case_name, slides_per_cluster, tr
     gmax = max(float(v.norm()) for v in a["grads"].values())
     for k, g in a["grads"].items():
         err = float((g - b["grads"][k]).norm()) / max(float(g.norm()), 1e-5 * gmax)
-        # H.0.* (and NaCAGaT's key block) come out of the bag backward, which rounds dz to bf16 / dkg to fp16 with a
-        # batch-wide scale: fp32-rounding differences in d(pooled) move individual roundings (2^-9 per element)
-        bag_side = k.startswith("H.0.") or k.startswith("co_attention.in_proj")
+        # H.0.*, the co-attention in-projection and (through dqk) the SNN encoders sit behind the bag backward, which
+        # rounds dz to bf16 / dkg to fp16 with a batch-wide scale: fp32-rounding differences in d(pooled) move
+        # individual roundings (2^-9 per element)
+        bag_side = k.startswith("H.0.") or k.startswith("co_attention.in_proj") or k.startswith("G.")
         assert err < (3e-3 if bag_side else 5e-4), (k, err)
 
 
