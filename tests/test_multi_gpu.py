@@ -1,7 +1,8 @@
 """2-GPU checks (NCCL), run when the box has at least two devices (`gpurun --gpus 2 -- python -m pytest tests -m gpu`):
   * one bag sharded by patch range over two ranks + cross-GPU log-sum-exp combine == the reference outputs
     (golden fixture generated from the unmodified reference, BASELINE config 5);
-  * data-parallel gradients: two ranks x 2 slides, one all-reduce == one rank x 4 slides."""
+  * data-parallel gradients: two ranks x 2 slides, one all-reduce == one rank x 4 slides;
+  * the split-graph step with the bucketed, overlapped all-reduce == the eager step with one all-reduce."""
 import os
 import sys
 from importlib import import_module
@@ -71,6 +72,24 @@ def _worker(rank, world, port, q):
         cens = torch.tensor([s[3] for s in slides], dtype=torch.float32, device=dev)
         tr.step(pb, om, labels, cens, train=False)
         res["grad_one"] = tr.flat_grad.cpu().numpy()
+    # ---- 3) the step captured as two CUDA graphs with the post-stage gradient bucket all-reduced next to the bag
+    #         backward pass (bench.py at N > 1) == the eager step followed by one all-reduce
+    tr.zero_grad()
+    pb = bpm.PackedBag.from_slides([torch.from_numpy(slides[i][0]).to(dev) for i in mine])
+    om = [torch.stack([torch.from_numpy(slides[i][1][j]) for i in mine]).to(dev) for j in range(6)]
+    labels = torch.tensor([slides[i][2] for i in mine], dtype=torch.int64, device=dev)
+    cens = torch.tensor([slides[i][3] for i in mine], dtype=torch.float32, device=dev)
+    gstep = tr.capture(pb, om, labels, cens, train=False, split=True)
+    off = tr.post_bucket_offset()
+    tr.zero_grad()
+    gstep.replay_first()
+    w1 = dist.all_reduce(tr.flat_grad[off:], async_op=True)
+    gstep.replay_second()
+    w2 = dist.all_reduce(tr.flat_grad[:off], async_op=True)
+    w1.wait(); w2.wait()
+    torch.cuda.synchronize()
+    res["grad_split"] = tr.flat_grad.cpu().numpy()
+    res["bucket_offset"] = int(off)
     torch.cuda.synchronize()
     q.put(res)
     dist.barrier()
@@ -101,3 +120,7 @@ def test_two_gpu_sharded_inference_and_dp_gradients():
     g1, gd = got[0]["grad_one"].astype(np.float64), got[0]["grad_dp"].astype(np.float64)
     assert np.linalg.norm(gd - g1) / np.linalg.norm(g1) < 2e-3
     assert np.allclose(got[0]["grad_dp"], got[1]["grad_dp"])
+    gs = got[0]["grad_split"].astype(np.float64)
+    assert 0 < got[0]["bucket_offset"] < gs.size
+    assert np.linalg.norm(gs - gd) / np.linalg.norm(gd) < 1e-4
+    assert np.allclose(got[0]["grad_split"], got[1]["grad_split"])
