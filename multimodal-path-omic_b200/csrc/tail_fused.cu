@@ -31,7 +31,8 @@ constexpr int NV = 8;              // 32-column blocks of a 256-wide layer (= he
 constexpr int NB = NV / CL;        // column blocks (heads) owned by one CTA: "virtual ranks" rank * NB + nb
 constexpr int NT = 256;            // threads per CTA
 constexpr int NW = NT / 32;
-constexpr int KC = 256;            // reduction extent of one weight chunk
+constexpr int KC = 128;            // reduction extent of one weight chunk (128: the one-slide kernels fit twice per SM)
+constexpr int KW = KC / (NT / 32); // reduction elements of a chunk per warp
 constexpr int WLD = KC + 4;        // padded row pitch of a forward chunk [32][WLD]
 constexpr int CHUNK = 32 * WLD;    // floats per ring slot (a data-gradient chunk [256][32] fits as well)
 constexpr int NSTAGE = 3;
@@ -50,7 +51,7 @@ struct Chunk {
   short ld;              // row pitch of W (in_features)
   short kc_type;         // kc (reduction elements, multiple of 4, <= KC) | type << 15
 };
-constexpr int MAX_CHUNKS = 192;
+constexpr int MAX_CHUNKS = 160;    // per launch and role (path role of NaCAGaT: 100 forward, 124 backward)
 struct Program { Chunk c[MAX_CHUNKS]; int n; };
 
 struct ProgBuilder {
@@ -156,13 +157,14 @@ __device__ __noinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int 
     // (1-D bulk copies by one warp were tried instead: 256 copies of 128 B per data-gradient chunk are far slower)
     if (type == T_FWD) {
       if (kc == KC) {
-        // thread t copies 16 B of rows (t >> 6) + 4 j: strength-reduced addresses, 8 copies in flight per thread
-        const float* s0 = src + static_cast<size_t>(t >> 6) * ld + (t & 63) * 4;
-        const uint32_t d0 = dst + ((t >> 6) * WLD + (t & 63) * 4) * 4;
-        const size_t sstep = static_cast<size_t>(4) * ld;
+        // thread t copies 16 B of rows t / PR + RP j (PR pieces per row): strength-reduced addresses
+        constexpr int PR = KC / 4, RP = NT / PR;
+        const float* s0 = src + static_cast<size_t>(t / PR) * ld + (t % PR) * 4;
+        const uint32_t d0 = dst + ((t / PR) * WLD + (t % PR) * 4) * 4;
+        const size_t sstep = static_cast<size_t>(RP) * ld;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * (4 * WLD * 4)), "l"(s0 + j * sstep) : "memory");
+        for (int j = 0; j < 32 / RP; ++j)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * (RP * WLD * 4)), "l"(s0 + j * sstep) : "memory");
       } else {
         const int per_row = kc >> 2;
         for (int p = t; p < 32 * per_row; p += NT) {
@@ -178,7 +180,7 @@ __device__ __noinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int 
       const size_t sstep = static_cast<size_t>(32) * ld;
       if (kc == KC) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < KC / 32; ++j)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * (32 * 32 * 4)), "l"(s0 + j * sstep) : "memory");
       } else {
         for (int j = 0; j * 32 + (t >> 3) < kc; ++j)
@@ -243,16 +245,16 @@ __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __
     const uint32_t wsm = ring + (cons % NSTAGE) * (CHUNK * 4);
     ++cons;
     const int kc = min(KC, Ktot - kb);
-    const int kbeg = warp * 32;
-    // this warp's 32 reduction elements: k-step stride is 16 B in x and in a forward chunk row, 4 rows in a dgrad chunk
+    const int kbeg = warp * KW;
+    // this warp's KW reduction elements: k-step stride is 16 B in x and in a forward chunk row, 4 rows in a dgrad chunk
     const uint32_t xk = smem_addr(xs) + (kb + kbeg) * 4;
     const uint32_t wk = TYPE == T_FWD ? wsm + (lane * WLD + kbeg) * 4 : wsm + (kbeg * 32 + lane) * 4;
     constexpr int WSTEP = TYPE == T_FWD ? 16 : 4 * 128;
     if (kc == KC) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) gemm_step<M, TYPE, LDX>(wk + j * WSTEP, xk + j * 16, acc);
+      for (int j = 0; j < KW / 4; ++j) gemm_step<M, TYPE, LDX>(wk + j * WSTEP, xk + j * 16, acc);
     } else {
-      const int nst = (min(kbeg + 32, kc) - kbeg) >> 2;       // may be <= 0
+      const int nst = (min(kbeg + KW, kc) - kbeg) >> 2;       // may be <= 0
       for (int j = 0; j < nst; ++j) gemm_step<M, TYPE, LDX>(wk + j * WSTEP, xk + j * 16, acc);
     }
   }
@@ -383,7 +385,9 @@ __device__ __forceinline__ float elu_f(float v) { return v > 0.f ? v : expm1f(v)
 __device__ __forceinline__ float elu_d(float y) { return y > 0.f ? 1.f : y + 1.f; }      // from the ELU output
 
 struct PathParams {
-  Program prog;
+  Program prog[2];             // chunk streams of the path-role ([0]) and omic-role ([1]) clusters
+  int nroles;                  // 2: adjacent clusters 2g / 2g+1 run the path / omic branch of slide group g concurrently
+  int off_dG2;                 // NaCAGaT: the CAG's dQ (added to dG by pre_bwd_kernel; the omic role owns dG)
   EncP enc[4];                 // path.0, path.1, omic.0, omic.1
   EncW encw[4];
   PoolP pool[2];               // path, omic
@@ -412,7 +416,8 @@ struct PathParams {
   float* dsuma;                // [B][6] or null
   int off_dqp;
 };
-static_assert(sizeof(PathParams) <= 8000, "kernel parameter space (large kernel parameters, CUDA 12.1+)");
+static_assert(sizeof(PathParams) <= 12000, "kernel parameter space (large kernel parameters, CUDA 12.1+)");
+static_assert(sizeof(Program) <= 2600, "two chunk programs have to fit the kernel parameter space");
 
 // ------------------------------------------------------------------------------------------------ encoder layer
 // nn.TransformerEncoderLayer(256, nhead 8, ff 512, relu, post-norm) as built at models/mcat/mcat.py:51-53.
@@ -874,22 +879,27 @@ struct PathSmem {
 };
 
 static_assert(PathSmem<2>::total * sizeof(float) <= 227 * 1024, "path kernel shared memory");
+static_assert(PathSmem<1>::total * sizeof(float) <= 113 * 1024, "two one-slide path CTAs have to fit one SM");
 template <int S>
-__global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ PathParams P) {
+__global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_constant__ PathParams P) {
   constexpr int M = 6 * S;
   using L = PathSmem<S>;
   extern __shared__ __align__(16) float sm[];
   Dev d;
   d.rank = cluster_rank();
   d.t = threadIdx.x; d.lane = d.t & 31; d.warp = d.t >> 5;
-  d.s0 = (blockIdx.x / CL) * S;
+  const int cid = blockIdx.x / CL;
+  const int role = P.nroles == 2 ? (cid & 1) : 0;          // 0: path branch (and everything that is saved), 1: omic branch
+  const int br_hi = P.nroles == 2 ? role : 1, br_lo = P.nroles == 2 ? role : 0;
+  const bool saver = role == 0;
+  d.s0 = (cid / P.nroles) * S;
   d.B = P.B; d.grow0 = d.s0 * 6; d.Rtot = 6 * P.B;
   d.seedv = drop_seed(P.d_model);
   d.ws = P.ws;
   d.red = sm + L::RED;
   Pipe pipe;
   d.pipe = &pipe;
-  pipe_init(pipe, P.prog, sm + L::TBL, sm + L::ring, d.rank);
+  pipe_init(pipe, P.prog[role], sm + L::TBL, sm + L::ring, d.rank);
   float* ws = P.ws;
   float *XA = sm + L::XA, *XB = sm + L::XB, *XC = sm + L::XC, *BIG = sm + L::BIG, *QKVL = sm + L::QKVL;
   float *AL = sm + L::AL, *BL = sm + L::BL, *PA = sm + L::PA, *AW = sm + L::AW, *HP = sm + L::HP, *CAT = sm + L::CAT;
@@ -912,7 +922,7 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
     // output projections of the pooled vectors -- the folded form of mcat.py:97 -- encoders, pooling); one copy of the
     // code, run twice
 #pragma unroll 1
-    for (int br = 1; br >= 0; --br) {
+    for (int br = br_hi; br >= br_lo; --br) {
       if (br == 1) {
         load_rows<M>(d, XA, ws + P.off_G, d.grow0, d.Rtot);
       } else {
@@ -1016,6 +1026,16 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
       pool_fwd<S>(d, P.pool[br], P.poolw[br], br, dm, dq, br == 1 ? P.att_omic : P.att_path, P.off_cat, XA, AL, BL, PA, AW,
                   HP, CAT);
     }
+  }
+  if (P.flags & F_HEAD) {
+    if (!(P.flags & F_FWD) || P.nroles == 2) {
+      // [h_path | h_omic] was written by the two roles of the previous launch
+      for (int i = d.t; i < S * 2 * E; i += NT) {
+        const int s = i / (2 * E);
+        CAT[i] = (d.s0 + s < d.B) ? __ldcg(ws + P.off_cat + static_cast<size_t>(d.s0 + s) * 2 * E + (i - s * 2 * E)) : 0.f;
+      }
+      __syncthreads();
+    }
     // ---- concat fusion (fusion.py:17-19)
     for (int nb = 0; nb < NB; ++nb) {
       const int col = (d.rank * NB + nb) * 32 + d.lane;
@@ -1024,7 +1044,7 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
       reduce_epi<S>(d, [&](int s, int, float v) {
         v = fmaxf(v + bias, 0.f);
         bcast(Z1 + s * E + col, v);
-        if (d.s0 + s < d.B) ws[P.off_z1 + static_cast<size_t>(d.s0 + s) * E + col] = v;
+        if (saver && d.s0 + s < d.B) ws[P.off_z1 + static_cast<size_t>(d.s0 + s) * E + col] = v;
       });
     }
     cluster_sync();
@@ -1035,7 +1055,7 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
       reduce_epi<S>(d, [&](int s, int, float v) {
         v = fmaxf(v + bias, 0.f);
         bcast(Z2 + s * E + col, v);
-        if (d.s0 + s < d.B) ws[P.off_z2 + static_cast<size_t>(d.s0 + s) * E + col] = v;
+        if (saver && d.s0 + s < d.B) ws[P.off_z2 + static_cast<size_t>(d.s0 + s) * E + col] = v;
       });
     }
     cluster_sync();
@@ -1063,7 +1083,7 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
         sum += expf(z - m);
       }
       for (int j = 0; j < K; ++j) YV[s * MAXK + j] = expf(LG[s * MAXK + j] - m) / sum;
-      if (d.rank == 0 && slide < d.B) {
+      if (saver && d.rank == 0 && slide < d.B) {
         for (int j = 0; j < K; ++j) {
           P.hazards[slide * K + j] = HZ[s * MAXK + j];
           P.S[slide * K + j] = SV[s * MAXK + j];
@@ -1076,7 +1096,7 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
   }
 
   if (P.flags & F_BWD) {
-    if (!(P.flags & F_FWD)) {
+    if (!(P.flags & F_HEAD)) {
       // activations of the forward pass come back from the workspace
       for (int i = d.t; i < S * E; i += NT) {
         const int s = i / E, c = i - s * E;
@@ -1127,7 +1147,7 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
             if (y >= 1 && s_prev > eps) DS[s * MAXK + y - 1] += gs * w_unc * (-(1.f - c) / s_prev);
             if (h_y > eps) DH[s * MAXK + y] += gs * w_unc * (-(1.f - c) / h_y);
           }
-          if (d.rank == 0) {
+          if (saver && d.rank == 0) {
             P.loss[slide] = l;
             for (int j = 0; j < K; ++j) {
               if (P.dhaz_out) P.dhaz_out[slide * K + j] = DH[s * MAXK + j];
@@ -1152,7 +1172,7 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
         float dh = DH[s * MAXK + tt] - tail / (1.f - hz);
         float dl = dh * hz * (1.f - hz) + YV[s * MAXK + tt] * (DYv[s * MAXK + tt] - dotY);
         DLG[s * MAXK + tt] = dl;
-        if (d.rank == 0 && valid) ws[P.off_dlogits + slide * K + tt] = dl;
+        if (saver && d.rank == 0 && valid) ws[P.off_dlogits + slide * K + tt] = dl;
       }
     }
     __syncthreads();
@@ -1163,7 +1183,7 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
       for (int k = 0; k < K; ++k) g = fmaf(DLG[s * MAXK + k], __ldg(P.wcl + k * E + d.t), g);
       g = Z2[s * E + d.t] > 0.f ? g : 0.f;
       DZS[s * E + d.t] = g;
-      if (d.rank == 0 && d.s0 + s < d.B) ws[P.off_dz2 + static_cast<size_t>(d.s0 + s) * E + d.t] = g;
+      if (saver && d.rank == 0 && d.s0 + s < d.B) ws[P.off_dz2 + static_cast<size_t>(d.s0 + s) * E + d.t] = g;
     }
     __syncthreads();
     for (int nb = 0; nb < NB; ++nb) {
@@ -1172,7 +1192,7 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
       reduce_epi<S>(d, [&](int s, int, float v) {
         v = Z1[s * E + col] > 0.f ? v : 0.f;
         bcast(DZ1 + s * E + col, v);
-        if (d.s0 + s < d.B) ws[P.off_dz1 + static_cast<size_t>(d.s0 + s) * E + col] = v;
+        if (saver && d.s0 + s < d.B) ws[P.off_dz1 + static_cast<size_t>(d.s0 + s) * E + col] = v;
       });
     }
     cluster_sync();
@@ -1188,19 +1208,20 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
         if (dr.thr != 0) { v *= drop_grad(dr, d.seedv, static_cast<uint32_t>(slide) * E + c); hv = drop_invert(hv, dr); }
         v = hv > 0.f ? v : 0.f;
         bcast(DZR + s * 2 * E + c2, v);
-        if (slide < d.B) ws[P.poolw[pidx].dzr + static_cast<size_t>(slide) * E + c] = v;
+        if (saver && slide < d.B) ws[P.poolw[pidx].dzr + static_cast<size_t>(slide) * E + c] = v;
       });
     }
     cluster_sync();
     // omic branch backward -> dG (completed by pre_bwd_kernel), then the path branch backward -> d(pooled)
 #pragma unroll 1
-    for (int br = 1; br >= 0; --br) {
+    for (int br = br_hi; br >= br_lo; --br) {
       pool_bwd<S>(d, P.pool[br], P.poolw[br], br, dq, ws + P.encw[2 * br + 1].y2, XA, BIG, AL, BL, PA, AW, DHP, DZR);
 #pragma unroll 1
       for (int l = 1; l >= 0; --l)
         enc_bwd<S>(d, P.enc[2 * br + l], P.encw[2 * br + l], 2 * br + l, dm, XA, XB, XC, BIG, AL, QKVL, BL,
                    l == 1 ? nullptr : ws + (br == 1 ? P.off_dG : P.off_dhc));
     }
+    if (br_lo == 0) {            // the path branch goes on to d(pooled) (and through the CAG for NaCAGaT)
     for (int nb = 0; nb < NB; ++nb) {
       const int col = (d.rank * NB + nb) * 32 + d.lane;
       gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XA, E);
@@ -1283,19 +1304,14 @@ __global__ void __launch_bounds__(NT, 1) path_kernel(const __grid_constant__ Pat
           if (d.grow0 + r < d.Rtot) ws[P.off_dqp + static_cast<size_t>(d.grow0 + r) * E + col] = v;
         });
       }
-      for (int nb = 0; nb < NB; ++nb) {                // dQ = df1 W_1, added to the omic branch's dG
+      for (int nb = 0; nb < NB; ++nb) {                // dQ = df1 W_1 (pre_bwd_kernel adds it to the omic branch's dG)
         const int col = (d.rank * NB + nb) * 32 + d.lane;
-        float dg0[(M + NW - 1) / NW];
-#pragma unroll
-        for (int i = 0; i < (M + NW - 1) / NW; ++i) {
-          const int r = d.warp + NW * i, grow = d.grow0 + r;
-          dg0[i] = (r < M && grow < d.Rtot) ? __ldcg(ws + P.off_dG + static_cast<size_t>(grow) * E + col) : 0.f;
-        }
         gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XA, E);
-        reduce_epi<M>(d, [&](int r, int i, float v) {
-          if (d.grow0 + r < d.Rtot) ws[P.off_dG + static_cast<size_t>(d.grow0 + r) * E + col] = v + dg0[i];
+        reduce_epi<M>(d, [&](int r, int, float v) {
+          if (d.grow0 + r < d.Rtot) ws[P.off_dG2 + static_cast<size_t>(d.grow0 + r) * E + col] = v;
         });
       }
+    }
     }
   }
   cp_async_wait<0>();
@@ -1322,8 +1338,9 @@ struct PreParams {
   float* kc;                   // [B][6] out of pre_kernel
   const float* dkc;            // [B][6]      from the bag backward
   const float* dtq;            // [B][6][256] gradient w.r.t. tanh(q) from the bag backward
+  int off_dG2;                 // the CAG's dQ, left by the path kernel
 };
-static_assert(sizeof(PreParams) <= 4000, "kernel parameter space");
+static_assert(sizeof(PreParams) <= 12000, "kernel parameter space (large kernel parameters, CUDA 12.1+)");
 
 template <int S>
 struct PreSmem {
@@ -1483,6 +1500,7 @@ __global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ 
       const int r = d.warp + NW * i, grow = d.grow0 + r;
       const bool valid = r < M && grow < d.Rtot;
       dg0[i] = valid ? __ldcg(ws + P.off_dG + static_cast<size_t>(grow) * E + col) : 0.f;
+      if (valid && P.nac) dg0[i] += __ldcg(ws + P.off_dG2 + static_cast<size_t>(grow) * E + col);
       gv[i] = valid ? __ldcg(ws + P.off_G + static_cast<size_t>(grow) * E + col) : 0.f;
     }
     gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XB, E);
@@ -1686,7 +1704,7 @@ int slides_per_cluster(int B) {
   const char* env = getenv("MPO_TAIL_FUSED_S");
   const int forced = env ? atoi(env) : 0;
   if (forced == 1 || forced == 2) return forced;
-  return B <= 33 ? 1 : 2;
+  return B <= 35 ? 1 : 2;        // 2 x 35 one-slide clusters (path + omic role) are resident at once (71 fit)
 }
 
 bool eligible(const mpo_model* m, const mpo_tail_io* io) {
@@ -1725,6 +1743,7 @@ static void fill_pre(const mpo_model* m, const mpo_tail_io* io, const Ws& w, Pre
   P.nac = m->variant == MPO_VARIANT_NACAGAT ? 1 : 0;
   P.bk = m->coattn_in.b + E;
   P.kc = io->kc; P.dkc = io->dkc; P.dtq = io->dtq;
+  P.off_dG2 = static_cast<int>(w.fz_dG2);
 }
 
 int pre_fwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t st) {
@@ -1874,69 +1893,112 @@ int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, cons
   }
   P.off_dqp = (int)w.dqp;
 
-  ProgBuilder pb{P.prog};
   // chunk order = consumption order of the device code; a CTA owns NB column blocks of every 256-wide layer
-  auto enc_f = [&](const mpo_encoder_layer& L) {
-    for (int nb = 0; nb < NB; ++nb) pb.fwd(L.in_proj.w, E, E, 3, 32 * NB, E, nb * 32);     // q, k, v of head rank * NB + nb
-    pb.fwd(L.out_proj.w, E, E, NB, 32 * NB);
-    pb.fwd(L.linear1.w, E, E, 2 * NB, 64 * NB, 32);
-    pb.fwd(L.linear2.w, FF, FF, NB, 32 * NB);
-  };
-  auto enc_b = [&](const mpo_encoder_layer& L) {
-    pb.dgrad(L.linear2.w, FF, E, 2 * NB, 64 * NB, 32);
-    pb.dgrad(L.linear1.w, E, FF, NB, 32 * NB);
-    pb.dgrad(L.out_proj.w, E, E, NB, 32 * NB);
-    pb.dgrad(L.in_proj.w, E, 3 * E, NB, 32 * NB);
-  };
-  auto pool_f = [&](const mpo_pool_head& H) {
-    for (int nb = 0; nb < NB; ++nb) {
-      pb.fwd(H.att_a.w, E, E, 1, 32 * NB, 32, nb * 32);
-      pb.fwd(H.att_b.w, E, E, 1, 32 * NB, 32, nb * 32);
-    }
-    pb.fwd(H.rho.w, E, E, NB, 32 * NB);
-  };
-  auto pool_b = [&](const mpo_pool_head& H) {
-    pb.dgrad(H.rho.w, E, E, NB, 32 * NB);
-    for (int nb = 0; nb < NB; ++nb) {
-      pb.dgrad(H.att_a.w, E, E, 1, 32 * NB, 32, nb * 32);
-      pb.dgrad(H.att_b.w, E, E, 1, 32 * NB, 32, nb * 32);
-    }
-  };
-  if (flags & F_FWD) {
-    enc_f(m->omic_tr[0]); enc_f(m->omic_tr[1]); pool_f(m->omic_pool);
-    pb.fwd(Wv, E, E, NB, 32 * NB); pb.fwd(m->coattn_out.w, E, E, NB, 32 * NB);
-    if (nac) {
+  auto build_program = [&](Program& prog, int lflags, int br_hi, int br_lo) -> bool {
+    prog.n = 0;
+    ProgBuilder pb{prog};
+    auto enc_f = [&](const mpo_encoder_layer& L) {
+      for (int nb = 0; nb < NB; ++nb) pb.fwd(L.in_proj.w, E, E, 3, 32 * NB, E, nb * 32);     // q, k, v of head rank * NB + nb
+      pb.fwd(L.out_proj.w, E, E, NB, 32 * NB);
+      pb.fwd(L.linear1.w, E, E, 2 * NB, 64 * NB, 32);
+      pb.fwd(L.linear2.w, FF, FF, NB, 32 * NB);
+    };
+    auto enc_b = [&](const mpo_encoder_layer& L) {
+      pb.dgrad(L.linear2.w, FF, E, 2 * NB, 64 * NB, 32);
+      pb.dgrad(L.linear1.w, E, FF, NB, 32 * NB);
+      pb.dgrad(L.out_proj.w, E, E, NB, 32 * NB);
+      pb.dgrad(L.in_proj.w, E, 3 * E, NB, 32 * NB);
+    };
+    auto pool_f = [&](const mpo_pool_head& H) {
       for (int nb = 0; nb < NB; ++nb) {
-        pb.fwd(m->cag.fc1.w, E, E, 1, 32 * NB, 32, nb * 32);
-        pb.fwd(m->cag.fc2.w, E, E, 1, 32 * NB, 32, nb * 32);
-        pb.fwd(m->cag.fc3.w, E, E, 1, 32 * NB, 32, nb * 32);
+        pb.fwd(H.att_a.w, E, E, 1, 32 * NB, 32, nb * 32);
+        pb.fwd(H.att_b.w, E, E, 1, 32 * NB, 32, nb * 32);
       }
-      pb.fwd(m->cag.fc_c.w, E, E, NB, 32 * NB);
-    }
-    enc_f(m->path_tr[0]); enc_f(m->path_tr[1]); pool_f(m->path_pool);
-    pb.fwd(m->fusion0.w, 2 * E, 2 * E, NB, 32 * NB); pb.fwd(m->fusion2.w, E, E, NB, 32 * NB);
-  }
-  if (flags & F_BWD) {
-    pb.dgrad(m->fusion2.w, E, E, NB, 32 * NB);
-    pb.dgrad(m->fusion0.w, 2 * E, E, 2 * NB, 64 * NB, 32);
-    pool_b(m->omic_pool); enc_b(m->omic_tr[1]); enc_b(m->omic_tr[0]);
-    pool_b(m->path_pool); enc_b(m->path_tr[1]); enc_b(m->path_tr[0]);
-    pb.dgrad(m->coattn_out.w, E, E, NB, 32 * NB); pb.dgrad(Wv, E, E, NB, 32 * NB);
-    if (nac) {
-      pb.dgrad(m->cag.fc_c.w, E, E, NB, 32 * NB);
+      pb.fwd(H.rho.w, E, E, NB, 32 * NB);
+    };
+    auto pool_b = [&](const mpo_pool_head& H) {
+      pb.dgrad(H.rho.w, E, E, NB, 32 * NB);
       for (int nb = 0; nb < NB; ++nb) {
-        pb.dgrad(m->cag.fc3.w, E, E, 1, 32 * NB, 32, nb * 32);
-        pb.dgrad(m->cag.fc2.w, E, E, 1, 32 * NB, 32, nb * 32);
+        pb.dgrad(H.att_a.w, E, E, 1, 32 * NB, 32, nb * 32);
+        pb.dgrad(H.att_b.w, E, E, 1, 32 * NB, 32, nb * 32);
       }
-      pb.dgrad(m->cag.fc1.w, E, E, NB, 32 * NB);
+    };
+    if (lflags & F_FWD) {
+      for (int br = br_hi; br >= br_lo; --br) {
+        if (br == 1) {
+          enc_f(m->omic_tr[0]); enc_f(m->omic_tr[1]); pool_f(m->omic_pool);
+        } else {
+          pb.fwd(Wv, E, E, NB, 32 * NB); pb.fwd(m->coattn_out.w, E, E, NB, 32 * NB);
+          if (nac) {
+            for (int nb = 0; nb < NB; ++nb) {
+              pb.fwd(m->cag.fc1.w, E, E, 1, 32 * NB, 32, nb * 32);
+              pb.fwd(m->cag.fc2.w, E, E, 1, 32 * NB, 32, nb * 32);
+              pb.fwd(m->cag.fc3.w, E, E, 1, 32 * NB, 32, nb * 32);
+            }
+            pb.fwd(m->cag.fc_c.w, E, E, NB, 32 * NB);
+          }
+          enc_f(m->path_tr[0]); enc_f(m->path_tr[1]); pool_f(m->path_pool);
+        }
+      }
     }
-  }
-  if (!pb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
+    if (lflags & F_HEAD) { pb.fwd(m->fusion0.w, 2 * E, 2 * E, NB, 32 * NB); pb.fwd(m->fusion2.w, E, E, NB, 32 * NB); }
+    if (lflags & F_BWD) {
+      pb.dgrad(m->fusion2.w, E, E, NB, 32 * NB);
+      pb.dgrad(m->fusion0.w, 2 * E, E, 2 * NB, 64 * NB, 32);
+      for (int br = br_hi; br >= br_lo; --br) {
+        if (br == 1) { pool_b(m->omic_pool); enc_b(m->omic_tr[1]); enc_b(m->omic_tr[0]); }
+        else { pool_b(m->path_pool); enc_b(m->path_tr[1]); enc_b(m->path_tr[0]); }
+      }
+      if (br_lo == 0) {
+        pb.dgrad(m->coattn_out.w, E, E, NB, 32 * NB); pb.dgrad(Wv, E, E, NB, 32 * NB);
+        if (nac) {
+          pb.dgrad(m->cag.fc_c.w, E, E, NB, 32 * NB);
+          for (int nb = 0; nb < NB; ++nb) {
+            pb.dgrad(m->cag.fc3.w, E, E, 1, 32 * NB, 32, nb * 32);
+            pb.dgrad(m->cag.fc2.w, E, E, 1, 32 * NB, 32, nb * 32);
+          }
+          pb.dgrad(m->cag.fc1.w, E, E, NB, 32 * NB);
+        }
+      }
+    }
+    return pb.ok;
+  };
+  // Launch plan.  The omic and the path branch are independent, so two clusters per slide group (roles) run them
+  // concurrently -- at 113 KB of shared memory two CTAs share an SM and hide each other's barrier latencies.  The
+  // branches meet in the fusion layer: a kernel boundary, after which BOTH roles redo the (tiny) fusion + head + loss
+  // + fusion backward and continue with their own branch's backward pass.
   const int S = slides_per_cluster(B), ncl = (B + S - 1) / S;
-  cudaError_t e = S == 2 ? launch_cluster(path_kernel<2>, P, ncl, PathSmem<2>::total * sizeof(float), st)
-                         : launch_cluster(path_kernel<1>, P, ncl, PathSmem<1>::total * sizeof(float), st);
-  int rc = fin(e, "path_kernel (fused tail)");
-  if (rc || !(flags & F_BWD)) return rc;
+  const char* renv = getenv("MPO_TAIL_ROLES");
+  const bool roles = !(renv != nullptr && atoi(renv) == 0);
+  P.off_dG2 = static_cast<int>(w.fz_dG2);
+  int plan_flags[2] = {0, 0}, plan_roles[2] = {1, 1}, nlaunch = 1;
+  if (!roles) {                  // one cluster per slide group runs both branches back to back (comparison / debugging)
+    if ((flags & F_FWD) && (flags & F_BWD)) {
+      plan_flags[0] = F_FWD | F_HEAD; plan_flags[1] = flags & (F_LOSS | F_BWD); nlaunch = 2;
+    } else {
+      plan_flags[0] = flags | ((flags & F_FWD) ? F_HEAD : 0);
+    }
+  } else if (flags & F_FWD) {
+    plan_flags[0] = F_FWD; plan_roles[0] = 2;
+    plan_flags[1] = F_HEAD | (flags & (F_LOSS | F_BWD)); plan_roles[1] = (flags & F_BWD) ? 2 : 1;
+    nlaunch = 2;
+  } else {
+    plan_flags[0] = flags; plan_roles[0] = 2;
+  }
+  int rc = MPO_OK;
+  for (int l = 0; l < nlaunch; ++l) {
+    P.flags = plan_flags[l];
+    P.nroles = plan_roles[l];
+    bool ok = true;
+    if (P.nroles == 2) { ok = build_program(P.prog[0], P.flags, 0, 0) && build_program(P.prog[1], P.flags, 1, 1); }
+    else { ok = build_program(P.prog[0], P.flags, 1, 0); P.prog[1].n = 0; }
+    if (!ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
+    cudaError_t e = S == 2 ? launch_cluster(path_kernel<2>, P, ncl * P.nroles, PathSmem<2>::total * sizeof(float), st)
+                           : launch_cluster(path_kernel<1>, P, ncl * P.nroles, PathSmem<1>::total * sizeof(float), st);
+    rc = fin(e, "path_kernel (fused tail)");
+    if (rc) return rc;
+  }
+  if (!(flags & F_BWD)) return rc;
 
   static WParams W;
   memset(&W, 0, sizeof(W));

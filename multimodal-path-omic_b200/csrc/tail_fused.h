@@ -8,7 +8,7 @@
 namespace mpo {
 namespace fused {
 
-enum : int { F_FWD = 1, F_LOSS = 2, F_BWD = 4 };
+enum : int { F_FWD = 1, F_LOSS = 2, F_BWD = 4, F_HEAD = 8 };   // F_HEAD: fusion + survival head (internal)
 
 struct LossArgs {              // models/loss.py:5-43 through mpo_surv_loss's argument meaning
   int kind;                    // MPO_LOSS_NLL / MPO_LOSS_CES

@@ -49,6 +49,7 @@ struct Ws {
   struct FzEnc { long long dy2, df2, df, dy1, dsa, dqkv; } fz_enc[4];
   struct FzPool { long long dzr, da, db; } fz_pool[2];
   long long fz_cag[6];     // NaCAGaT CAG: t0 (d fc_c pre-activation), dGg, dEe, df1, df2, df3
+  long long fz_dG2 = 0;    // NaCAGaT CAG: dQ, added to dG by the pre-backward kernel
   Layout lay;
 };
 
@@ -127,6 +128,7 @@ inline void build_layout(const mpo_model* m, int B, Ws& w) {
   if (m->variant == MPO_VARIANT_NACAGAT) {
     const char* cn[6] = {"t0", "dGg", "dEe", "df1", "df2", "df3"};
     for (int i = 0; i < 6; ++i) { snprintf(nm, sizeof nm, "fz_cag_%s", cn[i]); w.fz_cag[i] = L.add(nm, R * E); }
+    w.fz_dG2 = L.add("fz_cag_dG2", R * E);
   }
   for (int p = 0; p < 2; ++p) {
     auto A = [&](const char* s, long long n) { snprintf(nm, sizeof nm, "fz_%s_%s", pn[p], s); return L.add(nm, n); };
