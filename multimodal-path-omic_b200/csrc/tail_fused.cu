@@ -1968,17 +1968,9 @@ int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, cons
   // branches meet in the fusion layer: a kernel boundary, after which BOTH roles redo the (tiny) fusion + head + loss
   // + fusion backward and continue with their own branch's backward pass.
   const int S = slides_per_cluster(B), ncl = (B + S - 1) / S;
-  const char* renv = getenv("MPO_TAIL_ROLES");
-  const bool roles = !(renv != nullptr && atoi(renv) == 0);
   P.off_dG2 = static_cast<int>(w.fz_dG2);
   int plan_flags[2] = {0, 0}, plan_roles[2] = {1, 1}, nlaunch = 1;
-  if (!roles) {                  // one cluster per slide group runs both branches back to back (comparison / debugging)
-    if ((flags & F_FWD) && (flags & F_BWD)) {
-      plan_flags[0] = F_FWD | F_HEAD; plan_flags[1] = flags & (F_LOSS | F_BWD); nlaunch = 2;
-    } else {
-      plan_flags[0] = flags | ((flags & F_FWD) ? F_HEAD : 0);
-    }
-  } else if (flags & F_FWD) {
+  if (flags & F_FWD) {
     plan_flags[0] = F_FWD; plan_roles[0] = 2;
     plan_flags[1] = F_HEAD | (flags & (F_LOSS | F_BWD)); plan_roles[1] = (flags & F_BWD) ? 2 : 1;
     nlaunch = 2;
