@@ -94,6 +94,16 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // store v at the same shared-memory offset in every CTA of the cluster
+template <int N>
+__device__ __forceinline__ void bcast_n(float* local, float v) {
+  const uint32_t a = smem_addr(local);
+#pragma unroll
+  for (int rk = 0; rk < N; ++rk) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rk));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+  }
+}
 __device__ __forceinline__ void bcast(float* local, float v) {
   const uint32_t a = smem_addr(local);
 #pragma unroll
@@ -191,12 +201,15 @@ __device__ __noinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int 
   cp_async_commit();
 }
 // copies the chunk table to shared memory and puts the first two chunks in flight
-__device__ __forceinline__ void pipe_init(Pipe& pp, const Program& prog, float* tbl_smem, float* ring_smem, int rank) {
-  for (int i = threadIdx.x; i < prog.n; i += NT) reinterpret_cast<Chunk*>(tbl_smem)[i] = prog.c[i];
+__device__ __forceinline__ void pipe_init(Pipe& pp, const Chunk* chunks, int n, float* tbl_smem, float* ring_smem, int rank) {
+  for (int i = threadIdx.x; i < n; i += NT) reinterpret_cast<Chunk*>(tbl_smem)[i] = chunks[i];
   __syncthreads();
-  pp.tbl = smem_addr(tbl_smem); pp.ring = smem_addr(ring_smem); pp.n = prog.n; pp.rank = rank; pp.cons = 0;
+  pp.tbl = smem_addr(tbl_smem); pp.ring = smem_addr(ring_smem); pp.n = n; pp.rank = rank; pp.cons = 0;
   pipe_issue(pp.tbl, pp.ring, pp.n, rank, 0);
   pipe_issue(pp.tbl, pp.ring, pp.n, rank, 1);
+}
+__device__ __forceinline__ void pipe_init(Pipe& pp, const Program& prog, float* tbl_smem, float* ring_smem, int rank) {
+  pipe_init(pp, prog.c, prog.n, tbl_smem, ring_smem, rank);
 }
 
 struct Dev {
@@ -1339,6 +1352,7 @@ struct PreParams {
   const float* dkc;            // [B][6]      from the bag backward
   const float* dtq;            // [B][6][256] gradient w.r.t. tanh(q) from the bag backward
   int off_dG2;                 // the CAG's dQ, left by the path kernel
+  int skip_snn;                // the SNN encoders run batched over the slides in snn_fwd_kernel / snn_bwd_kernel
 };
 static_assert(sizeof(PreParams) <= 12000, "kernel parameter space (large kernel parameters, CUDA 12.1+)");
 
@@ -1375,7 +1389,8 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
   pipe_init(pipe, P.prog, sm + L::TBL, sm + L::ring, d.rank);
   float* ws = P.ws;
   float *XO = sm + L::XO, *H1 = sm + L::H1, *G = sm + L::G, *QP = sm + L::QP;
-  for (int i = 0; i < MPO_Q; ++i) {
+  if (P.skip_snn) load_rows<M>(d, G, ws + P.off_G, d.grow0, d.Rtot);      // G_bag comes from snn_fwd_kernel
+  for (int i = 0; i < (P.skip_snn ? 0 : MPO_Q); ++i) {
     const int dim = P.omic_dims[i];
     for (int j = d.t; j < S * dim; j += NT) {
       const int s = j / dim, c = j - s * dim;
@@ -1383,7 +1398,7 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
     }
   }
   cluster_sync();
-  for (int i = 0; i < MPO_Q; ++i)
+  for (int i = 0; i < (P.skip_snn ? 0 : MPO_Q); ++i)
   for (int nb = 0; nb < NB; ++nb) {
     const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float bias = __ldg(P.b1[i] + col);
@@ -1399,7 +1414,7 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
     });
   }
   cluster_sync();
-  for (int i = 0; i < MPO_Q; ++i)
+  for (int i = 0; i < (P.skip_snn ? 0 : MPO_Q); ++i)
   for (int nb = 0; nb < NB; ++nb) {
     const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float bias = __ldg(P.b2[i] + col);
@@ -1506,6 +1521,10 @@ __global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ 
     gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XB, E);
     reduce_epi<M>(d, [&](int r, int i, float v) {
       v += dg0[i];
+      if (P.skip_snn) {                 // total gradient of G_bag, consumed by snn_bwd_kernel
+        if (d.grow0 + r < d.Rtot) ws[P.off_dG + static_cast<size_t>(d.grow0 + r) * E + col] = v;
+        return;
+      }
       const int s = r / 6, om = r - s * 6, slide = d.s0 + s;
       const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * om + 1);
       float y = gv[i];
@@ -1516,7 +1535,7 @@ __global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ 
     });
   }
   cluster_sync();
-  for (int i = 0; i < MPO_Q; ++i)
+  for (int i = 0; i < (P.skip_snn ? 0 : MPO_Q); ++i)
   for (int nb = 0; nb < NB; ++nb) {
     const int col = (d.rank * NB + nb) * 32 + d.lane;
     float hv[S];
@@ -1531,6 +1550,138 @@ __global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ 
       if (ds.thr != 0) { v *= drop_grad(ds, d.seedv, static_cast<uint32_t>(slide) * E + col); y = drop_invert(y, ds); }
       v *= (y > 0.f ? 1.f : y + 1.f);
       if (slide < d.B) ws[P.off_snn_dz1[i] + static_cast<size_t>(slide) * E + col] = v;
+    });
+  }
+  cp_async_wait<0>();
+  cluster_sync();
+}
+
+// ------------------------------------------------------------------------------------------------ SNN encoders
+// The six SNN encoders (mcat.py:32-45,90-92) see ONE row per slide, so inside a per-slide cluster they are 62 tiny
+// one-row GEMM chunks.  Batched over the slides instead: a cluster of 8 CTAs per omic group and 32 slides, CTA r owning
+// the 32 output columns 32 r .. 32 r + 31 of both layers; the hidden layer is exchanged through distributed shared
+// memory.  Same weight ring, FFMA2 blocks and dropout indices as the per-slide kernels.
+constexpr int SNN_CL = 8, SNN_ROWS = 32;
+struct SnnParams {
+  Chunk c[MPO_Q][8];           // per omic group: layer 1 (ceil(d / KC) chunks) then layer 2 (forward); layer-2 dgrad (backward)
+  int n[MPO_Q];
+  const float* omics[MPO_Q];
+  int omic_dims[MPO_Q];
+  const float* b1[MPO_Q];
+  const float* b2[MPO_Q];
+  float* ws;
+  int off_snn_h[MPO_Q], off_G, off_dG, off_snn_dz1[MPO_Q], off_snn_dz2[MPO_Q];
+  DropSpec d_alpha;
+  int B;
+};
+struct SnnSmem {
+  static constexpr int ring = 0;
+  static constexpr int XO = ring + NSTAGE * CHUNK;              // [32][OMIC_LD] inputs (backward: [32][256] dz2)
+  static constexpr int H1 = XO + SNN_ROWS * OMIC_LD;            // [32][256] hidden layer
+  static constexpr int RED = H1 + SNN_ROWS * E;
+  static constexpr int TBL = RED + NW * SNN_ROWS * 32;
+  static constexpr int total = TBL + 8 * 4 + 8;
+};
+static_assert(SnnSmem::total * sizeof(float) <= 227 * 1024, "SNN kernel shared memory");
+
+__global__ void __launch_bounds__(NT, 1) snn_fwd_kernel(const __grid_constant__ SnnParams P) {
+  extern __shared__ __align__(16) float sm[];
+  Dev d;
+  d.rank = cluster_rank();
+  d.t = threadIdx.x; d.lane = d.t & 31; d.warp = d.t >> 5;
+  const int cid = blockIdx.x / SNN_CL, om = cid % MPO_Q;
+  d.s0 = (cid / MPO_Q) * SNN_ROWS;
+  d.B = P.B; d.grow0 = 0; d.Rtot = 0;
+  d.seedv = drop_seed(P.d_alpha);
+  d.ws = P.ws;
+  d.red = sm + SnnSmem::RED;
+  Pipe pipe;
+  d.pipe = &pipe;
+  pipe_init(pipe, P.c[om], P.n[om], sm + SnnSmem::TBL, sm + SnnSmem::ring, d.rank);
+  float* ws = P.ws;
+  float *XO = sm + SnnSmem::XO, *H1 = sm + SnnSmem::H1;
+  const int dim = P.omic_dims[om];
+  for (int j = d.t; j < SNN_ROWS * dim; j += NT) {
+    const int s = j / dim, c = j - s * dim;
+    XO[s * OMIC_LD + c] = (d.s0 + s < d.B) ? __ldg(P.omics[om] + static_cast<size_t>(d.s0 + s) * dim + c) : 0.f;
+  }
+  cluster_sync();
+  const int col = d.rank * 32 + d.lane;
+  {
+    const float bias = __ldg(P.b1[om] + col);
+    const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * om);
+    gemm_block<SNN_ROWS, T_FWD, OMIC_LD>(*d.pipe, smem_addr(d.red), XO, dim);
+    reduce_epi<SNN_ROWS>(d, [&](int s, int, float v) {
+      v = elu_f(v + bias);
+      const int slide = d.s0 + s;
+      if (ds.thr != 0) v = drop_fwd(v, ds, d.seedv, static_cast<uint32_t>(slide) * E + col);
+      bcast_n<SNN_CL>(H1 + s * E + col, v);
+      if (slide < d.B) ws[P.off_snn_h[om] + static_cast<size_t>(slide) * E + col] = v;
+    });
+  }
+  cluster_sync();
+  {
+    const float bias = __ldg(P.b2[om] + col);
+    const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * om + 1);
+    gemm_block<SNN_ROWS, T_FWD, E>(*d.pipe, smem_addr(d.red), H1, E);
+    reduce_epi<SNN_ROWS>(d, [&](int s, int, float v) {
+      v = elu_f(v + bias);
+      const int slide = d.s0 + s;
+      if (ds.thr != 0) v = drop_fwd(v, ds, d.seedv, static_cast<uint32_t>(slide) * E + col);
+      if (slide < d.B) ws[P.off_G + static_cast<size_t>(slide * 6 + om) * E + col] = v;
+    });
+  }
+  cp_async_wait<0>();
+  cluster_sync();
+}
+
+// dG (total gradient of G_bag, from pre_bwd_kernel) -> gradients at the pre-activations of both SNN layers
+__global__ void __launch_bounds__(NT, 1) snn_bwd_kernel(const __grid_constant__ SnnParams P) {
+  extern __shared__ __align__(16) float sm[];
+  Dev d;
+  d.rank = cluster_rank();
+  d.t = threadIdx.x; d.lane = d.t & 31; d.warp = d.t >> 5;
+  const int cid = blockIdx.x / SNN_CL, om = cid % MPO_Q;
+  d.s0 = (cid / MPO_Q) * SNN_ROWS;
+  d.B = P.B; d.grow0 = 0; d.Rtot = 0;
+  d.seedv = drop_seed(P.d_alpha);
+  d.ws = P.ws;
+  d.red = sm + SnnSmem::RED;
+  Pipe pipe;
+  d.pipe = &pipe;
+  pipe_init(pipe, P.c[om], P.n[om], sm + SnnSmem::TBL, sm + SnnSmem::ring, d.rank);
+  float* ws = P.ws;
+  float* DZ = sm + SnnSmem::XO;                     // [32][256], every CTA computes all columns (elementwise)
+  const int col = d.rank * 32 + d.lane;
+  {
+    const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * om + 1);
+    for (int idx = d.t; idx < SNN_ROWS * E; idx += NT) {
+      const int s = idx / E, c = idx - s * E, slide = d.s0 + s;
+      const bool valid = slide < d.B;
+      const size_t o = static_cast<size_t>(slide * 6 + om) * E + c;
+      float g = valid ? __ldcg(ws + P.off_dG + o) : 0.f;
+      float y = valid ? __ldcg(ws + P.off_G + o) : 0.f;
+      if (ds.thr != 0) { g *= drop_grad(ds, d.seedv, static_cast<uint32_t>(slide) * E + c); y = drop_invert(y, ds); }
+      g *= elu_d(y);
+      DZ[idx] = g;
+      if (valid && (c >> 5) == d.rank) ws[P.off_snn_dz2[om] + static_cast<size_t>(slide) * E + c] = g;
+    }
+  }
+  {
+    float hv[SNN_ROWS / NW];
+#pragma unroll
+    for (int i = 0; i < SNN_ROWS / NW; ++i) {
+      const int slide = d.s0 + d.warp + NW * i;
+      hv[i] = slide < d.B ? __ldcg(ws + P.off_snn_h[om] + static_cast<size_t>(slide) * E + col) : 0.f;
+    }
+    const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * om);
+    gemm_block<SNN_ROWS, T_DGRAD, E>(*d.pipe, smem_addr(d.red), DZ, E);
+    reduce_epi<SNN_ROWS>(d, [&](int s, int i, float v) {
+      const int slide = d.s0 + s;
+      float y = hv[i];
+      if (ds.thr != 0) { v *= drop_grad(ds, d.seedv, static_cast<uint32_t>(slide) * E + col); y = drop_invert(y, ds); }
+      v *= elu_d(y);
+      if (slide < d.B) ws[P.off_snn_dz1[om] + static_cast<size_t>(slide) * E + col] = v;
     });
   }
   cp_async_wait<0>();
@@ -1680,17 +1831,17 @@ DropSpec host_drop(const mpo_tail_io* io, float p, bool alpha) {
 }
 
 template <typename K, typename PT>
-cudaError_t launch_cluster(K kern, const PT& prm, int nclusters, size_t smem_bytes, cudaStream_t st) {
+cudaError_t launch_cluster(K kern, const PT& prm, int nclusters, size_t smem_bytes, cudaStream_t st, int cluster_size = CL) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(nclusters * CL));
+  cfg.gridDim = dim3(static_cast<unsigned>(nclusters * cluster_size));
   cfg.blockDim = dim3(NT);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[0].val.clusterDim.x = cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   e = cudaLaunchKernelEx(&cfg, kern, prm);
@@ -1746,13 +1897,50 @@ static void fill_pre(const mpo_model* m, const mpo_tail_io* io, const Ws& w, Pre
   P.off_dG2 = static_cast<int>(w.fz_dG2);
 }
 
+static bool snn_batched() {
+  const char* env = getenv("MPO_TAIL_SNN_BATCH");
+  return !(env != nullptr && atoi(env) == 0);
+}
+static void fill_snn(const mpo_model* m, const mpo_tail_io* io, const Ws& w, SnnParams& P, bool backward) {
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < MPO_Q; ++i) {
+    P.omics[i] = io->omics[i]; P.omic_dims[i] = m->omic_dims[i];
+    P.b1[i] = m->snn[i][0].b; P.b2[i] = m->snn[i][1].b;
+    P.off_snn_h[i] = static_cast<int>(w.snn_h[i]);
+    P.off_snn_dz1[i] = static_cast<int>(w.snn_dz1[i]); P.off_snn_dz2[i] = static_cast<int>(w.snn_dz2[i]);
+    // one 32-column block per CTA of the 8-CTA cluster
+    Program tmp; tmp.n = 0;
+    ProgBuilder pb{tmp};
+    if (!backward) { pb.fwd(m->snn[i][0].w, m->omic_dims[i], m->omic_dims[i]); pb.fwd(m->snn[i][1].w, E, E); }
+    else pb.dgrad(m->snn[i][1].w, E, E);
+    P.n[i] = tmp.n < 8 ? tmp.n : 8;
+    for (int k = 0; k < P.n[i]; ++k) P.c[i][k] = tmp.c[k];
+  }
+  P.ws = io->ws;
+  P.off_G = static_cast<int>(w.G); P.off_dG = static_cast<int>(w.dG);
+  P.d_alpha = host_drop(io, io->drop_p, true);
+  P.B = io->num_slides;
+}
+
 int pre_fwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t st) {
   static PreParams P;
   fill_pre(m, io, w, P);
   if (P.nac && !io->kc) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_fwd: kc is NULL (NaCAGaT)");
+  const bool batched = snn_batched();
+  if (batched) {
+    static SnnParams SP;
+    fill_snn(m, io, w, SP, false);
+    const int ncl_snn = MPO_Q * ((io->num_slides + SNN_ROWS - 1) / SNN_ROWS);
+    cudaError_t e0 = launch_cluster(snn_fwd_kernel, SP, ncl_snn, SnnSmem::total * sizeof(float), st, SNN_CL);
+    const int rc0 = fin(e0, "snn_fwd_kernel (fused tail)");
+    if (rc0) return rc0;
+  }
+  P.skip_snn = batched ? 1 : 0;
   ProgBuilder pb{P.prog};
-  for (int i = 0; i < MPO_Q; ++i) pb.fwd(m->snn[i][0].w, m->omic_dims[i], m->omic_dims[i], NB, 32 * NB);
-  for (int i = 0; i < MPO_Q; ++i) pb.fwd(m->snn[i][1].w, E, E, NB, 32 * NB);
+  if (!batched) {
+    for (int i = 0; i < MPO_Q; ++i) pb.fwd(m->snn[i][0].w, m->omic_dims[i], m->omic_dims[i], NB, 32 * NB);
+    for (int i = 0; i < MPO_Q; ++i) pb.fwd(m->snn[i][1].w, E, E, NB, 32 * NB);
+  }
   pb.fwd(m->coattn_in.w, E, E, NB, 32 * NB);
   pb.dgrad(m->coattn_in.w + static_cast<size_t>(E) * E, E, E, NB, 32 * NB);
   if (!pb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
@@ -1801,13 +1989,24 @@ int pre_bwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t
   ProgBuilder pb{P.prog};
   pb.fwd(m->coattn_in.w + static_cast<size_t>(E) * E, E, E, NB, 32 * NB);
   pb.dgrad(m->coattn_in.w, E, E, NB, 32 * NB);
-  for (int i = 0; i < MPO_Q; ++i) pb.dgrad(m->snn[i][1].w, E, E, NB, 32 * NB);
+  const bool batched = snn_batched();
+  P.skip_snn = batched ? 1 : 0;
+  if (!batched)
+    for (int i = 0; i < MPO_Q; ++i) pb.dgrad(m->snn[i][1].w, E, E, NB, 32 * NB);
   if (!pb.ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
   const int B = io->num_slides, R = 6 * B, S = slides_per_cluster(B), ncl = (B + S - 1) / S;
   cudaError_t e = S == 2 ? launch_cluster(pre_bwd_kernel<2>, P, ncl, PreSmem<2>::total * sizeof(float), st)
                          : launch_cluster(pre_bwd_kernel<1>, P, ncl, PreSmem<1>::total * sizeof(float), st);
   int rc = fin(e, "pre_bwd_kernel (fused tail)");
   if (rc) return rc;
+  if (batched) {
+    static SnnParams SP;
+    fill_snn(m, io, w, SP, true);
+    const int ncl_snn = MPO_Q * ((io->num_slides + SNN_ROWS - 1) / SNN_ROWS);
+    cudaError_t e1 = launch_cluster(snn_bwd_kernel, SP, ncl_snn, SnnSmem::total * sizeof(float), st, SNN_CL);
+    rc = fin(e1, "snn_bwd_kernel (fused tail)");
+    if (rc) return rc;
+  }
   static WParams W;
   memset(&W, 0, sizeof(W));
   JobBuilder jb{W};
