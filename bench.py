@@ -478,6 +478,27 @@ def run_ours(args, rank, world, local_rank):
             msi = a.elapsed_time(b_) / 5
             also[tag] = {"ms_per_bag": msi, "patches": n_inf, "bag_GBps": n_inf * 2048 / (msi * 1e-3) / 1e9,
                          "note": "eager module call (forward + attention map), CUDA events"}
+        # the drop-in path itself: the reference's per-slide loop (models/mcat/main.py:39-70) calling the module and
+        # the loss one slide at a time through torch.autograd (host overhead included: wall clock around 20 calls)
+        inet.train()
+        lfn = import_module(pkg + "loss").NegativeLogLikelihoodSurvivalLoss()
+        wsi1 = x[:N]
+        lab1, cen1 = torch.tensor([[1]], device=dev), torch.tensor([0.0], device=dev)
+
+        def slide_step():
+            hz_, S_, _, _ = inet(wsi1, iom)
+            lfn(hz_, S_, lab1, cen1).backward()
+        for _ in range(3):
+            slide_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            slide_step()
+        torch.cuda.synchronize()
+        ms_slide = (time.perf_counter() - t0) / 20 * 1e3
+        also[f"mcat_module_api_per_slide_{N}_patches"] = {
+            "ms_per_slide_step": ms_slide, "slides_per_s": 1e3 / ms_slide,
+            "note": "model(wsi, omics) + NLL loss + loss.backward() per slide, as the reference's train() loop calls it"}
         del inet
         torch.cuda.empty_cache()
 

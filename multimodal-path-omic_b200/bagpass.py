@@ -94,6 +94,8 @@ class PackedBag:
             lengths.append(s.shape[0])
             parts.append(s)
         total = sum(lengths)
+        if len(parts) == 1 and parts[0].dtype == torch.bfloat16 and parts[0].is_contiguous():
+            return cls(parts[0], lengths)          # one bf16 slide: stream it where it lies
         x = torch.empty((total, D_IN), dtype=torch.bfloat16, device=parts[0].device)
         row = 0
         for s, n in zip(parts, lengths):

@@ -7,6 +7,7 @@ into nn.Parameter.grad through one torch.autograd.Function.
 """
 import ctypes
 import itertools
+import os
 
 import torch
 
@@ -46,8 +47,12 @@ class ModelBinding:
         self.n_classes = int(n_classes)
         self.names = [n for n, _ in module.named_parameters()]
 
-    def params(self):
-        return dict(self.module.named_parameters())
+    def params(self, refresh=False):
+        """name -> nn.Parameter.  One module traversal costs ~0.5 ms, so the per-slide entry refreshes the map once per
+        call (run_slide) and everything below reuses it."""
+        if refresh or getattr(self, "_P", None) is None:
+            self._P = dict(self.module.named_parameters())
+        return self._P
 
     def build(self, grads=None):
         P = self.params()
@@ -385,17 +390,36 @@ class _SlideFn(torch.autograd.Function):
                             save_for_backward=needs_bwd)
         ctx.engine, ctx.state, ctx.n_omics, ctx.n_params = engine, st, n_omics, len(params)
         coattn = engine.attention_map(st) if want_map else torch.empty(0, device=wsi.device)
-        outs = (st.hazards, st.S, st.Y, coattn, st.att_path, st.att_omic)
-        ctx.mark_non_differentiable(coattn, st.att_path, st.att_omic)
+        # the outputs are COPIES of the state's buffers: returning st.hazards itself would close a reference cycle
+        # (ctx -> state -> hazards -> grad_fn -> ctx) that only the cyclic GC breaks, and every slide's saved
+        # activations would stay allocated (fresh cudaMallocs per call) until it runs
+        a_path, a_omic = st.att_path.clone(), st.att_omic.clone()
+        outs = (st.hazards.clone(), st.S.clone(), st.Y.clone(), coattn, a_path, a_omic)
+        ctx.mark_non_differentiable(coattn, a_path, a_omic)
         return outs
 
     @staticmethod
     def backward(ctx, dhaz, dS, dY, *unused):
         engine, st = ctx.engine, ctx.state
+        ctx.state = None
         bnd = engine.binding
         P = bnd.params()
         if st.bag_ws.h_saved is None:
             raise RuntimeError("this forward pass did not keep activations (it ran under no_grad)")
+        none_in = (None, None, None, None, None, None) + (None,) * ctx.n_omics
+        if _ACCUMULATE_IN_PLACE and all(p.requires_grad for p in P.values()):
+            # The kernels accumulate (+=) like torch's AccumulateGrad, so they write straight into p.grad (created as
+            # zeros when absent) and autograd gets no per-parameter gradient back: 100 tensor adds per slide less.
+            grads = {}
+            for n, p in P.items():
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                elif not (p.grad.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.is_cuda):
+                    raise RuntimeError("parameter %s has a .grad the kernels cannot accumulate into" % n)
+                grads[n] = p.grad
+            model = bnd.build(grads=grads)
+            engine.backward(model, st, dhaz, dS, dY)
+            return none_in + (None,) * ctx.n_params
         total = sum(p.numel() for p in P.values())
         flat = torch.zeros(total, dtype=torch.float32, device=st.bag.x.device)
         grads, off = {}, 0
@@ -404,14 +428,20 @@ class _SlideFn(torch.autograd.Function):
             off += p.numel()
         model = bnd.build(grads=grads)
         engine.backward(model, st, dhaz, dS, dY)
-        return (None, None, None, None, None, None) + (None,) * ctx.n_omics + tuple(grads[n] for n in bnd.names)
+        return none_in + tuple(grads[n] for n in bnd.names)
+
+
+# MPO_AUTOGRAD_RETURN_GRADS=1: hand the parameter gradients back to autograd (hooks on parameters fire, one add per
+# parameter and slide) instead of accumulating into .grad in place
+_ACCUMULATE_IN_PLACE = os.environ.get("MPO_AUTOGRAD_RETURN_GRADS", "0") != "1"
 
 
 def run_slide(engine, wsi, omics, want_map, train):
     """Module-level entry used by the drop-in forward()s.  Returns hazards, S, Y [1,K], coattn or None, path, omic."""
     require_cuda(wsi, "wsi")
     bnd = engine.binding
-    params = [dict(bnd.module.named_parameters())[n] for n in bnd.names]
+    P = bnd.params(refresh=True)
+    params = [P[n] for n in bnd.names]
     needs_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     outs = _SlideFn.apply(engine, bool(want_map), bool(train), needs_bwd, wsi, len(omics), *omics, *params)
     hazards, S, Y, coattn, a_path, a_omic = outs
