@@ -299,7 +299,7 @@ def test_ge_nacagat_matches_reference(name):
     assert worst < GRAD_TOL, details[:5]
 
 
-@pytest.mark.parametrize("model,fusion", [("mcat", "concat"), ("nacagat", "bilinear")])
+@pytest.mark.parametrize("model,fusion", [("mcat", "concat"), ("nacagat", "bilinear"), ("nacagat", "concat")])
 def test_train_mode_gradients_match_finite_differences(model, fusion):
     """Train mode (every dropout layer of the path on, masks fixed by the seed) cannot be compared with the reference
     bit for bit (different RNG streams); instead the analytic gradients of the CUDA path are checked against
@@ -307,7 +307,8 @@ def test_train_mode_gradients_match_finite_differences(model, fusion):
     synth = _pkg("synth")
     sp = _pkg("slidepath")
     bpm = _pkg("bagpass")
-    name = "mcat_concat_300" if model == "mcat" else "nacagat_bilinear_200"
+    name = {("mcat", "concat"): "mcat_concat_300", ("nacagat", "bilinear"): "nacagat_bilinear_200",
+            ("nacagat", "concat"): "nacagat_concat_300"}[(model, fusion)]        # nacagat/concat: the fused cluster tail
     case = load_case(name)
     net = build_model(case).train()
     lens = [300, 200]
@@ -337,8 +338,10 @@ def test_train_mode_gradients_match_finite_differences(model, fusion):
               "omic_transformer.layers.1.linear2.weight", "path_transformer.layers.0.self_attn.out_proj.bias",
               "G.2.0.0.weight", "G.4.1.0.bias", "co_attention.out_proj.weight"]
     probes += ["fusion_layer.fusion_layer.0.weight"] if fusion == "concat" else \
-        ["fusion_layer.fc1.0.bias", "fusion_layer.linear_o1.0.weight", "fusion_layer.fc2.0.weight",
-         "co_attention.CAG.fc1.0.bias"]
+        ["fusion_layer.fc1.0.bias", "fusion_layer.linear_o1.0.weight", "fusion_layer.fc2.0.weight"]
+    if model == "nacagat":
+        probes += ["co_attention.CAG.fc1.0.bias", "co_attention.CAG.fc3.0.weight", "co_attention.CAG.G.1.weight",
+                   "co_attention.CAG.fc_c.0.weight", "co_attention.in_proj_bias"]
     P = dict(net.named_parameters())
     rng = np.random.default_rng(3)
     bad, checked = [], 0
