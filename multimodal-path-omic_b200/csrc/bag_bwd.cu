@@ -520,39 +520,39 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
 }
 
 // dqk[b][i][d] = sum over the slide's tiles;  db_H[d] += sum over all tiles (gradient accumulation)
-// 4 tile groups x 64 float4 columns per block so that many independent loads are in flight
+// 16 tile groups x 16 float4 columns per block (blockIdx.z = quarter of the columns): all loads of a thread in flight
 __global__ void __launch_bounds__(256)
 bag_bwd_reduce_kernel(const int* __restrict__ tile_prefix, const float* __restrict__ part_dqk,
                       const float* __restrict__ part_db, float* __restrict__ dqk, float* __restrict__ grad_bias,
                       int B, int num_tiles) {
-  __shared__ float4 acc_s[4][64];
-  const int tid = threadIdx.x, tg = tid >> 6, dq = tid & 63;
+  __shared__ float4 acc_s[16][16];
+  const int tid = threadIdx.x, tg = tid >> 4, dl = tid & 15, dq = dl + 16 * static_cast<int>(blockIdx.z);
   const bool is_bias = static_cast<int>(blockIdx.x) >= B;
   const int b = blockIdx.x, i = blockIdx.y;
   // bias blocks: (gridDim.x - B) * 6 chunks share the tiles round-robin and finish with atomics
   const int nchunk = (static_cast<int>(gridDim.x) - B) * kQ;
   const int chunk = (static_cast<int>(blockIdx.x) - B) * kQ + i;
-  const int t0 = is_bias ? chunk * 4 : tile_prefix[b];
+  const int t0 = is_bias ? chunk * 16 : tile_prefix[b];
   const int t1 = is_bias ? num_tiles : tile_prefix[b + 1];
-  const int tstep = is_bias ? nchunk * 4 : 4;
+  const int tstep = is_bias ? nchunk * 16 : 16;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+#pragma unroll 8
   for (int t = t0 + tg; t < t1; t += tstep) {
     const float* src = is_bias ? part_db + static_cast<size_t>(t) * kD : part_dqk + (static_cast<size_t>(t) * kQ + i) * kD;
     const float4 v = __ldg(reinterpret_cast<const float4*>(src) + dq);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  acc_s[tg][dq] = acc;
+  acc_s[tg][dl] = acc;
   __syncthreads();
-  if (tid < 64) {
+  if (tid < 16) {
     float4 r = acc_s[0][tid];
 #pragma unroll
-    for (int g = 1; g < 4; ++g) { r.x += acc_s[g][tid].x; r.y += acc_s[g][tid].y; r.z += acc_s[g][tid].z; r.w += acc_s[g][tid].w; }
+    for (int g = 1; g < 16; ++g) { r.x += acc_s[g][tid].x; r.y += acc_s[g][tid].y; r.z += acc_s[g][tid].z; r.w += acc_s[g][tid].w; }
     if (is_bias) {
-      float* g4 = grad_bias + tid * 4;
+      float* g4 = grad_bias + dq * 4;
       atomicAdd(g4 + 0, r.x); atomicAdd(g4 + 1, r.y); atomicAdd(g4 + 2, r.z); atomicAdd(g4 + 3, r.w);
     } else {
-      reinterpret_cast<float4*>(dqk + (static_cast<size_t>(b) * kQ + i) * kD)[tid] = r;
+      reinterpret_cast<float4*>(dqk + (static_cast<size_t>(b) * kQ + i) * kD)[dq] = r;
     }
   }
 }
@@ -723,7 +723,7 @@ cudaError_t launch_bag_bwd_dz(int mode, const CUtensorMap& tm_in, const CUtensor
 
 cudaError_t launch_bag_bwd_reduce(const int* tile_prefix, const float* part_dqk, const float* part_db, float* dqk,
                                   float* grad_bias, int B, int num_tiles, cudaStream_t stream) {
-  bag_bwd_reduce_kernel<<<dim3(B + (part_db != nullptr ? 16 : 0), kQ), 256, 0, stream>>>(tile_prefix, part_dqk, part_db,
+  bag_bwd_reduce_kernel<<<dim3(B + (part_db != nullptr ? 16 : 0), kQ, 4), 256, 0, stream>>>(tile_prefix, part_dqk, part_db,
                                                                                         dqk, grad_bias, B, num_tiles);
   count_launch();
   return cudaGetLastError();

@@ -422,9 +422,10 @@ bag_merge_kernel(const int* __restrict__ tile_prefix,   // [B+1] first tile of e
                  const float* __restrict__ part_ml, const int mls,   // per-tile stats, mls floats per tile (12 or 18)
                  const float* __restrict__ part_pool, float* __restrict__ pooled, float* __restrict__ lse,
                  float* __restrict__ suma) {   // suma (NaCAGaT, mls = 18): sum_n of the dropped-and-rescaled weights
-  // one block per (slide, query); 4 tile groups x 64 float4 feature columns, many independent loads in flight
+  // one block per (slide, query, quarter of the feature columns); 16 tile groups x 16 float4 columns: a 128-tile slide
+  // is 8 independent loads per thread, all in flight at once
   __shared__ float red[8];
-  __shared__ float4 acc_s[4][64];
+  __shared__ float4 acc_s[16][16];
   const int b = blockIdx.x, i = blockIdx.y, tid = threadIdx.x;
   const int t0 = tile_prefix[b], t1 = tile_prefix[b + 1];
   float m = -INFINITY;
@@ -447,26 +448,26 @@ bag_merge_kernel(const int* __restrict__ tile_prefix,   // [B+1] first tile of e
   float L = 0.f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) L += red[w];
-  const int tg = tid >> 6, dq = tid & 63;
+  const int tg = tid >> 4, dl = tid & 15, dq = dl + 16 * static_cast<int>(blockIdx.z);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-  for (int t = t0 + tg; t < t1; t += 4) {
+#pragma unroll 8
+  for (int t = t0 + tg; t < t1; t += 16) {
     const float w = __expf(__ldg(part_ml + static_cast<size_t>(t) * mls + i) - M);
     const float4 v = __ldg(reinterpret_cast<const float4*>(part_pool + (static_cast<size_t>(t) * kQ + i) * kD) + dq);
     acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
   }
-  acc_s[tg][dq] = acc;
+  acc_s[tg][dl] = acc;
   __syncthreads();
-  if (tid < 64) {
+  if (tid < 16) {
     const float inv = 1.f / L;
     float4 r = acc_s[0][tid];
 #pragma unroll
-    for (int g = 1; g < 4; ++g) { r.x += acc_s[g][tid].x; r.y += acc_s[g][tid].y; r.z += acc_s[g][tid].z; r.w += acc_s[g][tid].w; }
+    for (int g = 1; g < 16; ++g) { r.x += acc_s[g][tid].x; r.y += acc_s[g][tid].y; r.z += acc_s[g][tid].z; r.w += acc_s[g][tid].w; }
     r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
-    reinterpret_cast<float4*>(pooled + (static_cast<size_t>(b) * kQ + i) * kD)[tid] = r;
+    reinterpret_cast<float4*>(pooled + (static_cast<size_t>(b) * kQ + i) * kD)[dq] = r;
   }
-  if (tid == 0) lse[b * kQ + i] = M + __logf(L);
-  if (suma != nullptr) {       // block-uniform
+  if (tid == 0 && blockIdx.z == 0) lse[b * kQ + i] = M + __logf(L);
+  if (suma != nullptr && blockIdx.z == 0) {       // block-uniform
     __syncthreads();
     float ld = 0.f;
     for (int t = t0 + tid; t < t1; t += 256)
@@ -545,7 +546,7 @@ cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, con
 cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, int ml_stride, const float* part_pool,
                              float* pooled, float* lse, float* suma, int B, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
-  bag_merge_kernel<<<dim3(B, kQ), 256, 0, stream>>>(tile_prefix, part_ml, ml_stride, part_pool, pooled, lse, suma);
+  bag_merge_kernel<<<dim3(B, kQ, 4), 256, 0, stream>>>(tile_prefix, part_ml, ml_stride, part_pool, pooled, lse, suma);
   count_launch();
   return cudaGetLastError();
 }
