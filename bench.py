@@ -208,11 +208,24 @@ def run_ours(args, rank, world, local_rank):
     # gradient all-reduce sits between the graph and the (then eager, two-launch) Adam update
     # (N > 1: two graphs, so that the all-reduce of the post-stage gradient bucket -- ~70 % of the 16.6 MB, final once
     # the tail's path kernel and its weight-gradient kernel have run -- overlaps the bag backward pass)
-    graphed = trainer.capture(bag, omics, labels, censor, train=True, with_adam=(world == 1), split=(world > 1))
+    # opt-in (MPO_BENCH_NCCL_IN_GRAPH=1): measured 1.174 vs 1.191 ms per step at N = 2, but the process then hangs in
+    # the process-group teardown with the captured collectives alive, so the default keeps NCCL outside the graphs
+    one_graph = world > 1 and os.environ.get("MPO_BENCH_NCCL_IN_GRAPH", "0") == "1"
+    graphed = None
+    if one_graph:
+        # the bucketed all-reduce and the Adam update inside the captured step (NCCL collectives are graph-capturable)
+        try:
+            graphed = trainer.capture(bag, omics, labels, censor, train=True, with_adam=True, allreduce=True)
+        except Exception as exc:          # fall back to two graphs with the collectives between them
+            print("bench: NCCL-in-graph capture failed (%s); using the split-graph step" % (exc,), file=sys.stderr)
+            one_graph = False
+            torch.cuda.synchronize()
+    if graphed is None:
+        graphed = trainer.capture(bag, omics, labels, censor, train=True, with_adam=(world == 1), split=(world > 1))
     post_off = trainer.post_bucket_offset() if world > 1 else 0
 
     def one_step():
-        if world == 1:
+        if world == 1 or one_graph:
             loss, _, _ = graphed.replay()
             return loss
         graphed.replay_first()

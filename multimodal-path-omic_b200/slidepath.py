@@ -554,14 +554,17 @@ class BatchTrainer:
         self.last_state = st
         return st.loss, st.hazards, st.S
 
-    def capture(self, bag, omics, labels, censor, train=True, with_adam=False, split=False):
+    def capture(self, bag, omics, labels, censor, train=True, with_adam=False, split=False, allreduce=False):
         """Record one step (forward + loss + backward) over these STATIC buffers into a CUDA graph.
 
         The caller refreshes the contents of bag.x / omics / labels / censor in place and calls replay(); the
         small tail launches then cost one graph launch.  Dropout masks change on every replay
         through a device-side seed.  split=True records the step as TWO graphs -- everything up to and including the
         post stage's gradients, then bag backward + pre backward -- so that a data-parallel caller can start the
-        all-reduce of flat_grad[post_bucket_offset():] between them (replay_first() / replay_second())."""
+        all-reduce of flat_grad[post_bucket_offset():] between them (replay_first() / replay_second()).
+        allreduce=True (torch.distributed initialised, NCCL) records the whole data-parallel step as ONE graph instead:
+        forward part, all-reduce of the post-stage bucket on NCCL's stream next to the bag backward part, all-reduce
+        of the rest, then (with_adam) the optimizer step."""
         eng = self.engine
         dev = bag.x.device
         st = eng.alloc_state(self.model, bag, save_for_backward=True, reuse_ws=False, with_backward_buffers=True)
@@ -571,14 +574,31 @@ class BatchTrainer:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):                         # warm-up outside the capture (lazy kernel attributes etc.)
-                self._run_bwd(self._run_fwd(st, bag, omics, labels, censor, train, 0, inline_wgrad=split))
+                self._run_bwd(self._run_fwd(st, bag, omics, labels, censor, train, 0, inline_wgrad=split or allreduce))
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if allreduce:
+            import torch.distributed as dist
+            off = self.post_bucket_offset()
+            for _ in range(2):                         # communicator / channel set-up outside the capture
+                dist.all_reduce(self.flat_grad[off:])
+                dist.all_reduce(self.flat_grad[:off])
+            torch.cuda.synchronize()
         self.flat_grad.zero_()
         graph = torch.cuda.CUDAGraph()
         graph2 = torch.cuda.CUDAGraph() if split else None
         _lib.lib().mpo_launch_count(1)
-        if split:
+        if allreduce:
+            with torch.cuda.graph(graph):
+                self._run_fwd(st, bag, omics, labels, censor, train, 0, inline_wgrad=True)
+                w1 = dist.all_reduce(self.flat_grad[off:], async_op=True)
+                self._run_bwd(st)
+                w2 = dist.all_reduce(self.flat_grad[:off], async_op=True)
+                w1.wait()
+                w2.wait()
+                if with_adam:
+                    self.adam_step(zero_grad=True)
+        elif split:
             with torch.cuda.graph(graph):
                 self._run_fwd(st, bag, omics, labels, censor, train, 0, inline_wgrad=True)
             with torch.cuda.graph(graph2, pool=graph.pool()):
