@@ -332,13 +332,18 @@ __global__ void __launch_bounds__(256) gemm_big_kernel(const GemmArgs g) {
     for (int j = 0; j < B_PER; ++j) { int nn, kk; b_pos(j, nn, kk); Bs[buf][kk][nn] = rb[j]; }
   };
   pdl_enter();
-  const int nsteps = (g.K + BK - 1) / BK;
-  load_tile(0);
+  // split-K (gridDim.z > 1): this CTA reduces steps [s_begin, s_end) and adds its partial with atomics (C pre-zeroed)
+  const int nsteps_all = (g.K + BK - 1) / BK;
+  const int per_z = (nsteps_all + static_cast<int>(gridDim.z) - 1) / static_cast<int>(gridDim.z);
+  const int s_begin = static_cast<int>(blockIdx.z) * per_z, s_end = min(nsteps_all, s_begin + per_z);
+  if (s_begin >= s_end) return;
+  const int nsteps = s_end - s_begin, kbase = s_begin * BK;
+  load_tile(kbase);
   store_tile(0);
   __syncthreads();
   for (int s = 0; s < nsteps; ++s) {
     const int buf = s & 1;
-    if (s + 1 < nsteps) load_tile((s + 1) * BK);
+    if (s + 1 < nsteps) load_tile(kbase + (s + 1) * BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       // rows ty*4 .. +3 and BM/2 + ty*4 .. +3; columns tx*4 .. +3 (and BN/2 + tx*4 .. +3): conflict-free float4 reads
@@ -387,7 +392,11 @@ __global__ void __launch_bounds__(256) gemm_big_kernel(const GemmArgs g) {
         v[h] = act_fwd(v[h], g.act);
       }
       float* c = g.C + m * g.ldc + nb;
-      if (vec_ok && nb + 3 < g.N) {
+      if (gridDim.z > 1) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+          if (nb + h < g.N) atomicAdd(c + h, v[h]);
+      } else if (vec_ok && nb + 3 < g.N) {
         float4 o = make_float4(v[0], v[1], v[2], v[3]);
         if (g.accumulate) { const float4 p = *reinterpret_cast<const float4*>(c); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
         *reinterpret_cast<float4*>(c) = o;
@@ -399,10 +408,30 @@ __global__ void __launch_bounds__(256) gemm_big_kernel(const GemmArgs g) {
     }
   }
 }
+// C[m][n] = 0 over an [M, N] window of a strided matrix (split-K GEMMs accumulate into it with atomics)
+__global__ void zero_window_kernel(float* __restrict__ C, long long ldc, int M, int N) {
+  pdl_enter();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < static_cast<long long>(M) * N) C[(i / N) * ldc + (i % N)] = 0.f;
+}
 template <int BN>
 inline void launch_gemm_big(const GemmArgs& g, cudaStream_t st) {
   constexpr int BM = BN == 128 ? 128 : 256;
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+  // tall-skinny outputs with a bag-long reduction (P V, P^T dctx, dS K, dS^T Q of GE-NaCAGaT): too few tiles to fill
+  // the GPU and thousands of dependent K steps each -> split K
+  if (g.K >= 512 && g.bias == nullptr && g.act == ACT_NONE && grid.x * grid.y < 296) {
+    int splits = g.K / 256;
+    if (splits > 16) splits = 16;
+    if (splits > 1) {
+      grid.z = splits;
+      if (!g.accumulate) {
+        const long long n = static_cast<long long>(g.M) * g.N;
+        launch_k(zero_window_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, g.C, g.ldc, g.M, g.N);
+        count_launch();
+      }
+    }
+  }
   const bool akc = (g.sa_k == 1), bnc = (g.sb_n == 1);
   if (akc && bnc) launch_k(gemm_big_kernel<BN, true, true>, dim3(grid), dim3(256), 0, st, g);
   else if (akc && !bnc) launch_k(gemm_big_kernel<BN, true, false>, dim3(grid), dim3(256), 0, st, g);
