@@ -468,7 +468,7 @@ def run_ours(args, rank, world, local_rank):
         msg = a.elapsed_time(b_) / 3
         also[f"ge_nacagat_train_step_{N}_patches_B1"] = {
             "slides_per_s": 1e3 / msg, "ms_per_step": msg, "slides_per_step": 1,
-            "note": "first functional version: fp32 CUDA-core GEMMs, N x N attention materialised (DESIGN.md 4.5)"}
+            "note": "fp32 CUDA-core GEMMs (FFMA2, split-K), N x N attention materialised (DESIGN.md 4.5)"}
         del gnet
         torch.cuda.empty_cache()
         # BASELINE config 5: MCAT inference on one 200 000-patch bag.  One GPU streams the whole bag here; under the
