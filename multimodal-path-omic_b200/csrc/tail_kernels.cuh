@@ -422,7 +422,8 @@ inline void launch_gemm_big(const GemmArgs& g, cudaStream_t st) {
   // the GPU and thousands of dependent K steps each -> split K
   if (g.K >= 512 && g.bias == nullptr && g.act == ACT_NONE && grid.x * grid.y < 296) {
     int splits = g.K / 256;
-    if (splits > 16) splits = 16;
+    const int cap = static_cast<int>(296u / (grid.x * grid.y)) > 16 ? static_cast<int>(296u / (grid.x * grid.y)) : 16;
+    if (splits > cap) splits = cap;
     if (splits > 1) {
       grid.z = splits;
       if (!g.accumulate) {
