@@ -1,16 +1,21 @@
-// Fused cluster tail: the 6-token part of MCAT (reference models/mcat/mcat.py:90-138 and its autograd) as
-//   pre_kernel      SNN encoders, query projection, key fold                       (before the bag forward)
-//   path_kernel     omic + path encoders, pooling, fusion, survival head, loss, and the whole data-gradient chain
-//                   back to d(pooled)                                                (between bag forward and backward)
-//   pre_bwd_kernel  fold / query projection / SNN data gradients                    (after the bag backward)
-//   wgrad_kernel    every weight / bias / LayerNorm gradient of the tail as one grouped launch
-// One thread-block cluster of 8 CTAs owns S slides (M = 6 S token rows).  Activations are replicated in the shared
-// memory of the 8 CTAs; every linear layer is split by output columns (32 per CTA and block), its weight slice is
-// streamed L2 -> shared memory through a 3-stage cp.async ring that runs ahead across layer boundaries, results
-// are broadcast to the peers through distributed shared memory, and the per-row work (LayerNorm, the 6x6 attention
-// of one head per CTA, pooling soft-max, survival head, loss) happens in place.  Slides never mix inside these
-// kernels, so no grid-wide synchronisation is needed; only the weight gradients sum over slides, and they are
-// deferred to wgrad_kernel.  fp32 CUDA-core arithmetic throughout (the 1e-3 parity gate of SURVEY.md 8c).
+// Fused cluster tail: the 6-token part of MCAT / NaCAGaT with concat fusion (reference models/mcat/mcat.py:90-138,
+// models/nacagat/nacagat.py:80-138, models/blocks.py:51-111,232-253 and their autograd) as
+//   snn_fwd_kernel  the six SNN encoders, batched over the slides (cluster of 8 CTAs per omic group and 32 slides)
+//   pre_kernel      query projection, key fold (and NaCAGaT's key-bias term)              (before the bag forward)
+//   path_kernel x2  launch 1: omic and path encoders + pooling as two concurrent cluster roles; launch 2: fusion,
+//                   survival head, loss, and the whole data-gradient chain back to d(pooled) / dG, again by role
+//                                                                              (between bag forward and backward)
+//   pre_bwd_kernel  fold / query projection data gradients; snn_bwd_kernel: SNN data gradients (after the bag backward)
+//   wgrad_kernel    every weight / bias / LayerNorm gradient of the tail as one grouped launch (twice per step)
+// One thread-block cluster of 4 CTAs owns S slides (M = 6 S token rows; S = 1 up to 35 slides per step).  Activations
+// are replicated in the shared memory of the 4 CTAs; every linear layer is split by output columns (two 32-column
+// blocks = two attention heads per CTA), its weight slice is streamed L2 -> shared memory through a 3-stage cp.async
+// ring that runs ahead across layer boundaries, results are broadcast to the peers through distributed shared
+// memory, and the per-row work (LayerNorm, the 6x6 attention of the CTA's heads, pooling soft-max, survival head,
+// loss) happens in place.  The one-slide kernels fit twice per SM (113 KB, 128 registers), so the two roles hide each
+// other's latencies.  Slides never mix inside these kernels, so no grid-wide synchronisation is needed; only the
+// weight gradients sum over slides, and they are deferred to wgrad_kernel.  fp32 CUDA-core arithmetic throughout
+// (packed FFMA2), the 1e-3 parity gate of SURVEY.md 8c.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
