@@ -95,6 +95,9 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   constexpr uint16_t kMask = static_cast<uint16_t>((1u << kC) - 1);
   // every CTA of a cluster runs the same number of pipeline iterations; surplus ones are dummies without MMAs
   const int iters = (p.num_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  // a CTA owns `iters` CONSECUTIVE tiles: it stays inside one slide for up to `iters` tiles, so the folded queries are
+  // reloaded once or twice per CTA instead of once per tile (a stride of gridDim tiles lands in a new slide every time)
+  const int tile0 = static_cast<int>(blockIdx.x) * iters;
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -104,12 +107,13 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       constexpr int kWRows = kD / kC;                     // W_H rows this CTA fetches per K block
+      int row_pref = tile0 < p.num_tiles ? p.tile_info[tile0].row0 : -1;   // loaded one tile ahead of its use
       for (int it = 0; it < iters; ++it) {
-        const int t = blockIdx.x + it * gridDim.x;
-        int row0 = t < p.num_tiles ? p.tile_info[t].row0 : 0;
+        int row0 = row_pref >= 0 ? row_pref : 0;
         if (p.debug & 2) row0 = (blockIdx.x & 7) * kTileM;
-        const int tn = t + gridDim.x;
-        const int row_next = tn < p.num_tiles ? p.tile_info[tn].row0 : -1;
+        const int tn = tile0 + it + 1;
+        row_pref = (it + 1 < iters && tn < p.num_tiles) ? p.tile_info[tn].row0 : -1;
+        const int row_next = row_pref;
         for (int kb = 0; kb < kKBlocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + FwdSmem::stages + stage * kStageBytes;
@@ -140,7 +144,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
-        const bool real = blockIdx.x + it * gridDim.x < static_cast<unsigned>(p.num_tiles);
+        const bool real = tile0 + it < p.num_tiles;
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         if (real) {
@@ -211,8 +215,11 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[pas]);
     };
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-      const TileInfo ti = p.tile_info[t];
+    const int tile_end = min(tile0 + iters, p.num_tiles);
+    TileInfo ti_next = tile0 < tile_end ? p.tile_info[tile0] : TileInfo{};
+    for (int t = tile0; t < tile_end; ++t, ++it) {
+      const TileInfo ti = ti_next;
+      if (t + 1 < tile_end) ti_next = p.tile_info[t + 1];     // in flight during this tile's epilogue
       if (prev_t >= 0) read_pooled(prev_t, (it - 1) & 1, (it - 1) & 1);   // also: the staged tile / P operand are free again
       prev_t = -1;
       if (et == 32) tma_store_wait_read();      // the previous tile's H store no longer reads the staged tile
@@ -230,6 +237,12 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       const uint32_t acc_col = tmem_base + as * kD;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
+      if (p.debug & 32) {                       // timing experiment: loads + MMAs alone, no epilogue work
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        continue;
+      }
 
       // ---- (1)+(2) accumulator -> h = relu(acc + bias) (dropout); fp32 score partials; fp16 tile in shared memory
       float s[kQ];
@@ -322,10 +335,35 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         *reinterpret_cast<float2*>(spart_s + r * 8 + 4) = make_float2(s[4], s[5]);
       }
       named_bar_sync(1, kEpiThreads);
-      if (et == 32 && p.h_out != nullptr) {
+      if ((p.debug & 128) && p.h_out != nullptr) {
+        // timing experiment: the saved activations leave through the LSU instead of the TMA unit.  The 12 warps that
+        // do not run the tile soft-max copy the staged tile, one 512 B patch row per instruction (lane = 16 B chunk)
+        if (ch != 0) {
+          const int cbl = lane >> 3, jl = lane & 7;
+          uint4 hv[11];
+#pragma unroll
+          for (int k = 0; k < 11; ++k) {
+            const int row = (warp - 6) + 12 * k;
+            if (row < kTileM)
+              hv[k] = *reinterpret_cast<const uint4*>(staging + cbl * (kTileM * 128) + row * 128 + ((jl ^ (row & 7)) << 4));
+          }
+#pragma unroll
+          for (int k = 0; k < 11; ++k) {
+            const int row = (warp - 6) + 12 * k;
+            if (row < ti.nvalid)
+              __stcs(reinterpret_cast<uint4*>(p.h_out + static_cast<size_t>(ti.row0 + row) * kD + lane * 8), hv[k]);
+          }
+        }
+      } else if (et == 32 && p.h_out != nullptr) {
         // keep the activations for the backward pass: one TMA store per 64-feature block, straight from the tile
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) tma_store_2d(&tm_h, staging + cb * (kTileM * 128), cb * 64, ti.row0);
+        // evict-first: the tile is next read by the backward pass, a bag-pass (> L2) later; measured 4 % on the kernel
+        const uint64_t pol_store = policy_evict_first();
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          if (p.debug & 64) tma_store_2d(&tm_h, staging + cb * (kTileM * 128), cb * 64, ti.row0);
+          else tma_store_2d_hint(&tm_h, staging + cb * (kTileM * 128), cb * 64, ti.row0, pol_store);
+        }
         tma_store_commit();
       }
 

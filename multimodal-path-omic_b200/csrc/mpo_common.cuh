@@ -39,7 +39,8 @@ struct BagFwdParams {
   float drop_scale;            // 1 / keep probability
   int skip_pool;               // 1: write activations and raw scores only (NaCAGaT: softmax runs on gated scores)
   int debug;                   // timing experiments only (env MPO_FWD_DEBUG): bit0 skip W loads, bit1 X from L2,
-                               // bit2 L2-prefetch the next tile's X
+                               // bit2 L2-prefetch the next tile's X, bit3 no TMA loads, bit4 no main MMAs,
+                               // bit5 no epilogue work, bit6 h_saved store without the evict-first hint
 };
 
 // NaCAGaT gate pass (bag_gate.cu)

@@ -13,7 +13,8 @@ x = torch.randn(sum(lengths), 1024, device=dev).bfloat16()
 bag = bp.PackedBag(x, lengths)
 w = (torch.randn(256, 1024, device=dev) / 32).bfloat16()
 bias = torch.zeros(256, device=dev); qk = torch.randn(B, 6, 256, device=dev) * 0.05
-ws = bp.BagWorkspace(bag, save_h=True)
+save_h = os.environ.get("MPO_TIME_SAVE_H", "1") != "0"
+ws = bp.BagWorkspace(bag, save_h=save_h)
 dpooled = torch.randn(B, 6, 256, device=dev) * 0.1
 gw = torch.zeros(256, 1024, device=dev); gb = torch.zeros(256, device=dev)
 fns = {"fwd": lambda: bp.bag_forward(bag, w, bias, qk, ws), "bwd": lambda: bp.bag_backward(bag, ws, dpooled, qk, gw, gb)}
@@ -27,4 +28,4 @@ for name in which.split(","):
     for _ in range(10): fn()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    print(f"{name}: {ms*1e3/B:.2f} us/slide  ({sum(lengths)*2048/(ms*1e-3)/1e9:.0f} GB/s algorithmic)  env={os.environ.get('MPO_FWD_DEBUG','0')} cluster={os.environ.get('MPO_FWD_CLUSTER','2')}")
+    print(f"{name}: {ms*1e3/B:.2f} us/slide  ({sum(lengths)*2048/(ms*1e-3)/1e9:.0f} GB/s algorithmic)  env={os.environ.get('MPO_FWD_DEBUG','0')} cluster={os.environ.get('MPO_FWD_CLUSTER','2')} save_h={int(save_h)}")
