@@ -20,10 +20,13 @@ class _SurvLossFn(torch.autograd.Function):
         K = int(hazards.shape[-1])
         hz = hazards.detach().reshape(B, K).float().contiguous()
         Sv = S.detach().reshape(B, K).float().contiguous()
+        # labels that are still on the host are range-checked here for free; for device labels a check would cost
+        # two device->host syncs per slide (the host could no longer run ahead of the GPU), so the kernel guards
+        # instead: an out-of-range label reads nothing and poisons that slide's loss with NaN
+        if not Y.is_cuda and B > 0 and (int(Y.min()) < 0 or int(Y.max()) >= K):
+            raise IndexError("survival label out of range [0, %d)" % K)
         lab = Y.detach().reshape(B).to(device=hz.device, dtype=torch.int64).contiguous()
         cen = c.detach().reshape(B).to(device=hz.device, dtype=torch.float32).contiguous()
-        if int(lab.min()) < 0 or int(lab.max()) >= K:
-            raise IndexError("survival label out of range [0, %d)" % K)
         loss = torch.empty(B, dtype=torch.float32, device=hz.device)
         dhz = torch.empty_like(hz)
         dS = torch.empty_like(Sv)

@@ -47,11 +47,39 @@ class ModelBinding:
         self.n_classes = int(n_classes)
         self.names = [n for n, _ in module.named_parameters()]
 
+    def _build_index(self):
+        """(full name, owning module's _parameters dict, key) per parameter, in named_parameters() order, plus the
+        (parent _modules dict, key, child) links that prove the module tree is still the one that was indexed."""
+        index, links = [], []
+        for mod_name, mod in self.module.named_modules():
+            for key, p in mod._parameters.items():
+                if p is not None:
+                    index.append(((mod_name + "." if mod_name else "") + key, mod._parameters, key))
+            for key, child in mod._modules.items():
+                if child is not None:
+                    links.append((mod._modules, key, child))
+        if [e[0] for e in index] != self.names:      # shared / re-registered parameters: keep the plain traversal
+            return None, None
+        return index, links
+
     def params(self, refresh=False):
-        """name -> nn.Parameter.  One module traversal costs ~0.5 ms, so the per-slide entry refreshes the map once per
-        call (run_slide) and everything below reuses it."""
+        """name -> nn.Parameter.  module.named_parameters() costs ~0.3-0.5 ms per traversal, which was a quarter of the
+        per-slide call; the refresh (once per call, in run_slide) instead re-reads every parameter from its owning
+        module's _parameters dict through a cached index (~100 dict lookups).  The index is rebuilt when a submodule
+        has been replaced; a parameter re-assigned in place of an old one is picked up by the lookup itself."""
         if refresh or getattr(self, "_P", None) is None:
-            self._P = dict(self.module.named_parameters())
+            index = getattr(self, "_index", None)          # None: not built yet; False: do not use an index
+            if index and not all(d.get(k) is c for d, k, c in self._links):
+                index = None
+            if index is None:
+                index, self._links = self._build_index()
+                self._index = index = index if index else False
+            P = None
+            if index:
+                P = {name: d.get(k) for name, d, k in index}
+                if any(p is None for p in P.values()):      # a parameter was deleted or set to None: re-index next time
+                    self._index, P = None, None
+            self._P = P if P is not None else dict(self.module.named_parameters())
         return self._P
 
     def build(self, grads=None):

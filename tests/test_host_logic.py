@@ -135,3 +135,26 @@ def test_state_dict_and_initialisation_match_the_reference(fusion):
         assert all(torch.equal(sa[k], sb[k]) for k in sa)
         assert a.get_trainable_parameters() == b.get_trainable_parameters()
         b.load_state_dict(sa)      # checkpoints travel both ways
+
+
+def test_parameter_map_follows_reassigned_parameters_and_modules():
+    """ModelBinding.params(refresh=True) reads the parameters through a cached index instead of named_parameters();
+    it must still see a parameter or a submodule that was replaced after the index was built."""
+    synth = _pkg("synth")
+    net = _pkg("mcat").MultimodalCoAttentionTransformer(omic_sizes=list(synth.OMIC_SIZES))
+    bnd = net._engine.binding
+
+    def same(P):
+        ref = dict(net.named_parameters())
+        assert list(P) == list(ref)
+        assert all(P[n] is ref[n] for n in ref)
+
+    same(bnd.params(refresh=True))
+    same(bnd.params(refresh=True))                       # second call goes through the index
+    assert bnd._index                                    # and the index is in use
+    net.H[0].weight = torch.nn.Parameter(torch.zeros_like(net.H[0].weight))
+    same(bnd.params(refresh=True))
+    net.classifier = torch.nn.Linear(net.classifier.in_features, net.classifier.out_features)
+    same(bnd.params(refresh=True))
+    net.load_state_dict({k: v.clone() for k, v in net.state_dict().items()})
+    same(bnd.params(refresh=True))
