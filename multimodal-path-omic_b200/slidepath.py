@@ -83,7 +83,21 @@ class ModelBinding:
         return self._P
 
     def build(self, grads=None):
+        """struct mpo_model over the current parameter (and gradient) addresses.  The struct of the last call is kept
+        per mode (with / without gradients) and reused while every address is unchanged: filling ~200 pointers
+        through ctypes and re-validating 100 tensors was 0.17 ms per call, twice per slide step."""
         P = self.params()
+        key = (tuple([p.data_ptr() for p in P.values()]),
+               None if grads is None else tuple([g.data_ptr() for g in grads.values()]))
+        cache = self.__dict__.setdefault("_built", {})
+        hit = cache.get(grads is None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        m = self._build(P, grads)
+        cache[grads is None] = (key, m)
+        return m
+
+    def _build(self, P, grads):
         for n, p in P.items():
             if not p.is_cuda:
                 raise RuntimeError("parameter %s is on %s: move the model to a CUDA device (no CPU fallback)" % (n, p.device))

@@ -8,4 +8,4 @@ tail -2 gpurun_out/fin_smoke.log
 timeout 900 python bench.py > gpurun_out/fin_bench.json 2> gpurun_out/fin_bench.err; echo "bench rc=$?"
 cat gpurun_out/fin_bench.json | cut -c1-600
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/fin_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-also > gpurun_out/fin_ncu.log 2>&1; echo "ncu rc=$?"
-for d in 0 64; do MPO_FWD_DEBUG=$d timeout 120 python scripts/gpu_time_bag.py 32 fwd,bwd 2>&1 | tail -2; done | tee gpurun_out/fin_decomp.log
+timeout 300 python scripts/gpu_profile_module_call.py 16384 > gpurun_out/fin_modprof.log 2>&1; grep "ms per call" gpurun_out/fin_modprof.log
