@@ -40,7 +40,8 @@ struct BagFwdParams {
   int skip_pool;               // 1: write activations and raw scores only (NaCAGaT: softmax runs on gated scores)
   int debug;                   // timing experiments only (env MPO_FWD_DEBUG): bit0 skip W loads, bit1 X from L2,
                                // bit2 L2-prefetch the next tile's X, bit3 no TMA loads, bit4 no main MMAs,
-                               // bit5 no epilogue work, bit6 h_saved store without the evict-first hint
+                               // bit5 no epilogue work, bit6 h_saved store without the evict-first hint,
+                               // bit7 h_saved stored through the LSU (st.global.cs) instead of the TMA unit
 };
 
 // NaCAGaT gate pass (bag_gate.cu)
