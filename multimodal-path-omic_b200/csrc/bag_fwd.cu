@@ -1,9 +1,10 @@
 // Bag-pass forward for MCAT (reference: models/mcat/mcat.py:87 `H_bag = self.H(wsi)` and :97 co-attention).
 //
-// One persistent CTA per SM streams 128-patch tiles of the packed bf16 bag; everything GEMM-shaped runs on tcgen05:
+// One persistent CTA per SM streams a range of CONSECUTIVE 128-patch tiles of the packed bf16 bag (so the folded queries
+// of a slide are loaded once per CTA and slide, not once per tile); everything GEMM-shaped runs on tcgen05:
 //   TMA (warp 0)  : X tile [128 x 1024] and W_H [256 x 1024] in 64-wide K blocks, 128B-swizzled, 3-stage ring
 //   MMA (warp 1)  : H = X W_H^T, tcgen05.mma M=128 N=256 K=16, fp32 accumulators in TMEM, two accumulator stages
-//   epilogue (8 w): (1) TMEM -> registers; +bias, ReLU, (dropout); the H tile is written ONCE to shared memory as
+//   epilogue (16 w): (1) TMEM -> registers; +bias, ReLU, (dropout); the H tile is written ONCE to shared memory as
 //                       fp16 in the canonical 128B-swizzle layout (and TMA-stored to HBM when the backward needs it);
 //                   (2) the six folded-query dots per patch are taken in the same register pass, in fp32 (an fp16
 //                       tensor-core product would cost the attention map its 1e-3 parity on sharp softmaxes);
