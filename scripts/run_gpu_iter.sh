@@ -1,6 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/iter_pytest.log 2>&1; echo "pytest rc=$?"
-tail -2 gpurun_out/iter_pytest.log
-timeout 300 python scripts/gpu_profile_module_call.py 16384 > gpurun_out/modprof2.log 2>&1
-grep "ms per call" gpurun_out/modprof2.log
+for d in 0 256 512 768 0 256; do MPO_FWD_DEBUG=$d timeout 120 python scripts/gpu_time_bag.py 32 fwd 2>&1 | tail -1; done | tee gpurun_out/iter_decomp.log
