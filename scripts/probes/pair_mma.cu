@@ -166,11 +166,13 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 // PAIR = true : one CTA pair per tile pair, half of the W_H block per CTA (32 KB stages), cta_group::2 MMAs
 template <bool PAIR>
 __global__ void __launch_bounds__(192, 1)
-stream_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, int num_tiles, int stages) {
+stream_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+              const __grid_constant__ CUtensorMap tm_h, int num_tiles, int stages, int store) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int kStB = PAIR ? 2 * kAB : 3 * kAB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * kStB);
+  uint8_t* staging = smem + stages * kStB;       // 64 KB: stands in for the fp16 H tile the epilogue would have written
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 65536);
   uint64_t* full = bars;
   uint64_t* empty = bars + 8;
   uint64_t* done = bars + 16;
@@ -217,7 +219,14 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
         }
         if (++s == stages) { s = 0; ph ^= 1; }
       }
+      if (store) {       // the h_saved traffic of the product kernel: 64 KB per tile, TMA store, evict-first
+        tma_store_wait_read();
+        const uint64_t pol_s = policy_evict_first();
+        for (int cb = 0; cb < 4; ++cb) tma_store_2d_hint(&tm_h, staging + cb * 16384, cb * 64, row0, pol_s);
+        tma_store_commit();
+      }
     }
+    if (store) tma_store_wait_read();
   } else if (warp == 1 && lane == 0 && rank == 0) {
     const uint32_t idesc = PAIR ? umma_idesc_bf16(256, 256, 0, 0) : umma_idesc_bf16(128, 256, 0, 0);
     int s = 0; uint32_t ph = 0;
@@ -253,9 +262,9 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
 }
 
 template <bool PAIR>
-static int run_stream(const CUtensorMap& tx, const CUtensorMap& tw, int num_tiles, int stages, int sms) {
+static int run_stream(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& th, int num_tiles, int stages, int sms, int store) {
   const int stb = PAIR ? 2 * kAB : 3 * kAB;
-  const int smem = stages * stb + 256 + 1024;
+  const int smem = stages * stb + 65536 + 256 + 1024;
   auto kern = stream_kernel<PAIR>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { printf("smem %d too large\n", smem); return 1; }
   cudaLaunchConfig_t cfg = {};
@@ -264,13 +273,13 @@ static int run_stream(const CUtensorMap& tx, const CUtensorMap& tw, int num_tile
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = PAIR ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int w = 0; w < 2; ++w) if (cudaLaunchKernelEx(&cfg, kern, tx, tw, num_tiles, stages) != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
+  for (int w = 0; w < 2; ++w) if (cudaLaunchKernelEx(&cfg, kern, tx, tw, th, num_tiles, stages, store) != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
   cudaEventRecord(e0);
-  for (int r = 0; r < 5; ++r) cudaLaunchKernelEx(&cfg, kern, tx, tw, num_tiles, stages);
+  for (int r = 0; r < 5; ++r) cudaLaunchKernelEx(&cfg, kern, tx, tw, th, num_tiles, stages, store);
   cudaEventRecord(e1);
   if (cudaDeviceSynchronize() != cudaSuccess) { printf("stream kernel failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
-  printf("load+MMA loop, %s, %d stages of %d KB: %.2f us per 16384-patch slide (%.0f GB/s of X)\n", PAIR ? "pair tiles (cta_group::2, half W_H per CTA)" : "single tiles (cta_group::1, full W_H per CTA)",
+  printf("load+MMA loop%s, %s, %d stages of %d KB: %.2f us per 16384-patch slide (%.0f GB/s of X)\n", store ? " + 64 KB store per tile" : "", PAIR ? "pair tiles (cta_group::2, half W_H per CTA)" : "single tiles (cta_group::1, full W_H per CTA)",
          stages, stb / 1024, ms * 1e3 / (num_tiles / 128.0), num_tiles * 128.0 * 2048 / (ms * 1e-3) / 1e9);
   return 0;
 }
@@ -278,13 +287,13 @@ static int run_stream(const CUtensorMap& tx, const CUtensorMap& tw, int num_tile
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_map(CUtensorMap* out, void* base, uint64_t rows, uint64_t cols) {
+static int make_map(CUtensorMap* out, void* base, uint64_t rows, uint64_t cols, bool f16 = false) {
   void* p = nullptr;
   cudaDriverEntryPointQueryResult q;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return 1;
   cuuint64_t dims[2] = {cols, rows}, strides[1] = {cols * 2};
   cuuint32_t box[2] = {64, 128}, es[2] = {1, 1};
-  return reinterpret_cast<EncodeTiledFn>(p)(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es,
+  return reinterpret_cast<EncodeTiledFn>(p)(out, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es,
                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS;
 }
@@ -334,7 +343,13 @@ int main() {
   CUtensorMap tbx;
   if (make_map(&tbx, bx, static_cast<uint64_t>(num_tiles) * 128, kK)) { printf("tensor map failed\n"); return 1; }
   int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  for (int st = 3; st <= 4; ++st) if (run_stream<false>(tbx, tw, num_tiles, st, sms)) return 3;
-  for (int st = 3; st <= 6; ++st) if (run_stream<true>(tbx, tw, num_tiles, st, sms)) return 3;
+  __half* bh;
+  CK(cudaMalloc(&bh, static_cast<size_t>(num_tiles) * 128 * 256 * 2));
+  CUtensorMap tbh;
+  if (make_map(&tbh, bh, static_cast<uint64_t>(num_tiles) * 128, 256, true)) { printf("tensor map failed\n"); return 1; }
+  for (int store = 0; store <= 1; ++store) {
+    for (int st = 3; st <= 3; ++st) if (run_stream<false>(tbx, tw, tbh, num_tiles, st, sms, store)) return 3;
+    for (int st = 3; st <= 5; ++st) if (run_stream<true>(tbx, tw, tbh, num_tiles, st, sms, store)) return 3;
+  }
   return 0;
 }
