@@ -23,7 +23,7 @@ using namespace mpo;
 constexpr int kM = 256, kN = 256, kK = 1024, kBKp = 64, kKB = kK / kBKp, kSt = 2;
 constexpr int kAB = 128 * kBKp * 2;          // 16 KB: this CTA's X block, and its half of the W block
 constexpr int kStage = 2 * kAB;
-constexpr int kSmem = kSt * kStage + 256 + 1024;
+constexpr int kSmem = kSt * kStage + 4096 + 256 + 1024;   // + the 4 KB soft-max weight operand of mode 3
 
 __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity, int what) {
   for (long long i = 0; i < (1ll << 24); ++i)
@@ -62,15 +62,16 @@ __device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, ui
 
 // mode 0: correctness (TMA pipeline, H written out).  mode 1 / 2: `reps` x 64 MMAs on whatever is resident, cta_group 1 / 2
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
-pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, float* H, int mode, int reps,
-            long long* cycles) {
+pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+            const __grid_constant__ CUtensorMap tm_h, float* H, int mode, int reps, long long* cycles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSt * kStage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSt * kStage + 4096);
   uint64_t* full = bars;            // [kSt]
   uint64_t* empty = bars + kSt;     // [kSt]
   uint64_t* done = bars + 2 * kSt;
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2 * kSt + 1);
+  uint64_t* pready = bars + 2 * kSt + 1;   // rank 0: both CTAs' operands of the pooled pair MMA are in place (count 2)
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2 * kSt + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool pair = mode != 1;
@@ -78,6 +79,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kSt; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(done, 1);
+    mbar_init(pready, 2);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -125,6 +127,55 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(qd * 32) << 16) + c, v);
         tmem_ld_wait();
         for (int j = 0; j < 32; ++j) H[(static_cast<size_t>(rank) * 128 + row) * kN + c + j] = __uint_as_float(v[j]);
+      }
+    }
+  } else if (mode == 3) {
+    // The pooled product of the forward kernel as ONE pair MMA: D_r[feature, 16 r + i] = sum_patch H_r[patch, feature] P_r[i, patch].
+    // A = each CTA's staged fp16 tile read M-major (M = 256 over the pair = 128 features per CTA and pass), B = [P_0 ; P_1]
+    // (N = 32: 16 rows per CTA, K = the CTA's own 128 patches), hand-off through a count-2 barrier in rank 0 that rank 1
+    // reaches with a remote arrive (peer bit cleared).
+    uint8_t* staging = smem;
+    uint8_t* Pb = smem + kSt * kStage;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) reinterpret_cast<uint32_t*>(Pb)[i] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&full[0], 65536);
+      for (int cb = 0; cb < 4; ++cb) tma_load_2d(staging + cb * 16384, &tm_h, &full[0], cb * 64, static_cast<int>(rank) * 128, policy_evict_first());
+    }
+    if (threadIdx.x < 128) {
+      const int r = threadIdx.x;
+      for (int i = 0; i < 6; ++i) {
+        const float pv = static_cast<float>((r * 7 + i * 13 + static_cast<int>(rank) * 5) % 17 - 8) / 16.f;
+        uint8_t* pcol = Pb + (r >> 6) * 2048 + (r & 7) * 2;
+        *reinterpret_cast<__half*>(pcol + i * 128 + ((((r & 63) >> 3) ^ i) << 4)) = __float2half_rn(pv);
+      }
+    }
+    wait_or_trap(&full[0], 0, 21);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(pready) & 0xFEFFFFFFu) : "memory");
+    if (warp == 1 && lane == 0 && rank == 0) {
+      wait_or_trap(pready, 0, 22);
+      tc_fence_after();
+      const uint32_t idesc_d = umma_idesc(256, 32, 0, 0, 1, 0);
+      const uint32_t a0 = smem_u32(staging), b0 = smem_u32(Pb);
+      for (int mh = 0; mh < 2; ++mh)
+        for (int kk = 0; kk < 8; ++kk)
+          umma2_bf16(tmem + mh * 32, umma_desc_sw128(a0 + mh * 2 * 16384 + kk * 2048, 128 * 128, 1024),
+                     umma_desc_sw128(b0 + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), idesc_d, kk != 0 ? 1u : 0u);
+      umma2_commit_mcast(done, 3);
+    }
+    if (warp >= 2) {
+      wait_or_trap(done, 0, 23);
+      tc_fence_after();
+      const int qd = warp & 3;
+      for (int mh = 0; mh < 2; ++mh) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tmem + (static_cast<uint32_t>(qd * 32) << 16) + mh * 32 + 16 * rank, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 16; ++i) H[(static_cast<size_t>(rank) * 256 + mh * 128 + qd * 32 + lane) * 16 + i] = __uint_as_float(v[i]);
       }
     }
   } else {
@@ -313,7 +364,13 @@ int main() {
   CUtensorMap tx, tw;
   if (make_map(&tx, dx, kM, kK) || make_map(&tw, dw, kN, kK)) { printf("tensor map failed\n"); return 1; }
   CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-  pair_kernel<<<2, 192, kSmem>>>(tx, tw, dH, 0, 0, dc);
+  std::vector<__half> hh(256 * 256);
+  for (size_t i = 0; i < hh.size(); ++i) hh[i] = __float2half((rand() % 2001 - 1000) / 1000.f);
+  __half* dh;
+  CK(cudaMalloc(&dh, hh.size() * 2));
+  CK(cudaMemcpy(dh, hh.data(), hh.size() * 2, cudaMemcpyHostToDevice));
+  CUtensorMap th0;
+  pair_kernel<<<2, 192, kSmem>>>(tx, tw, tx, dH, 0, 0, dc);
   CK(cudaDeviceSynchronize());
   std::vector<float> H(kM * kN);
   CK(cudaMemcpy(H.data(), dH, H.size() * 4, cudaMemcpyDeviceToHost));
@@ -327,7 +384,7 @@ int main() {
   printf("pair MMA (cta_group::2, M256 N256, half of W per CTA): max |err| = %.3g  %s\n", worst, worst < 2e-3 ? "OK" : "MISMATCH");
   for (int mode = 1; mode <= 2; ++mode) {
     const int reps = 50;
-    pair_kernel<<<2, 192, kSmem>>>(tx, tw, dH, mode, reps, dc);
+    pair_kernel<<<2, 192, kSmem>>>(tx, tw, tx, dH, mode, reps, dc);
     CK(cudaDeviceSynchronize());
     long long c[2];
     CK(cudaMemcpy(c, dc, 16, cudaMemcpyDeviceToHost));
@@ -335,6 +392,27 @@ int main() {
            mode == 1 ? "M128 N256 K16" : "M256 N256 K16 over the pair = M128 N256 K16", 64 * reps);
   }
   if (worst >= 2e-3) return 2;
+  {
+    if (make_map(&th0, dh, 256, 256, true)) { printf("tensor map failed\n"); return 1; }
+    CK(cudaMemset(dH, 0, kM * kN * 4));
+    pair_kernel<<<2, 192, kSmem>>>(tx, tw, th0, dH, 3, 0, dc);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> D(2 * 256 * 16);
+    CK(cudaMemcpy(D.data(), dH, D.size() * 4, cudaMemcpyDeviceToHost));
+    double w3 = 0;
+    for (int r = 0; r < 2; ++r)
+      for (int f = 0; f < 256; ++f)
+        for (int i = 0; i < 16; ++i) {
+          double acc = 0;
+          if (i < 6)
+            for (int pt = 0; pt < 128; ++pt)
+              acc += static_cast<double>(__half2float(hh[(r * 128 + pt) * 256 + f])) * (static_cast<double>((pt * 7 + i * 13 + r * 5) % 17 - 8) / 16.0);
+          w3 = fmax(w3, fabs(acc - D[(r * 256 + f) * 16 + i]));
+        }
+    printf("pooled pair MMA (M-major A, N = 32 = 16 weight rows per CTA, count-2 barrier with a remote arrive): max |err| = %.3g  %s\n", w3,
+           w3 < 1e-3 ? "OK" : "MISMATCH");
+    if (w3 >= 1e-3) return 4;
+  }
   // the load + MMA loop over a bag-sized X (32 slides x 16384 patches), by pipeline depth
   const int num_tiles = 4096;
   __nv_bfloat16* bx;
