@@ -50,7 +50,10 @@ constexpr int kFwdSmemBytes = FwdSmem::total + 1024;  // + slack for manual 1024
 // kC = CTAs per cluster.  With kC > 1 every CTA still owns its own tiles, but the cluster walks the K blocks in
 // lock step and each CTA fetches only 1/kC of every W_H block, multicasting it to all kC shared memories: the L2 ->
 // SM traffic for the weights drops by kC (W_H re-reads, not the bag, are what saturates the L2 slices at kC = 1).
-template <int kC>
+// kPair (kC = 2): the two CTAs share every MMA (tcgen05 cta_group::2, M = 256 = two adjacent tiles): each CTA stages its own
+// X block and HALF of the W_H block (four 32 KB stages instead of three of 48 KB), rank 0 issues all MMAs; the pooled
+// product is one N = 32 pair MMA over both CTAs' weight operands (scripts/probes/pair_mma.cu).
+template <int kC, bool kPair = false>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                const __grid_constant__ CUtensorMap tm_h, const BagFwdParams p) {
@@ -59,11 +62,14 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::bars);
-  uint64_t* full_bar = bars;                 // [kStages]
-  uint64_t* empty_bar = bars + kStages;      // [kStages]
-  uint64_t* tfull_bar = bars + 2 * kStages;  // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+  constexpr int kNS = kPair ? 4 : kStages;                  // ring depth
+  constexpr int kSB = kPair ? 2 * kABytes : kStageBytes;    // bytes per stage in this CTA
+  uint64_t* full_bar = bars;                 // [kNS]   (pair: only rank 0's are used)
+  uint64_t* empty_bar = bars + kNS;          // [kNS]
+  uint64_t* tfull_bar = bars + 2 * kNS;      // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2]     (pair: only rank 0's are used, both CTAs' warps arrive)
   uint64_t* d_bar = tempty_bar + 2;          // pooled MMA done
+  uint64_t* pready_bar = d_bar + 1;          // pair, rank 0: both CTAs' pooled operands are in place
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FwdSmem::tmem_slot);
 
   const int warp = threadIdx.x >> 5;
@@ -72,20 +78,21 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kNS; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kC);     // one tcgen05.commit arrival from every CTA of the cluster
+      mbar_init(&empty_bar[s], kPair ? 1 : kC);     // one tcgen05.commit arrival from every MMA-issuing CTA
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiThreads / 32);
+      mbar_init(&tempty_bar[s], (kPair ? 2 : 1) * (kEpiThreads / 32));
     }
     mbar_init(d_bar, 1);
+    mbar_init(pready_bar, 2);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (kPair) { tmem_alloc2(tmem_slot, 512); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -95,10 +102,15 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   const uint32_t cta_rank = kC > 1 ? cluster_ctarank() : 0;
   constexpr uint16_t kMask = static_cast<uint16_t>((1u << kC) - 1);
   // every CTA of a cluster runs the same number of pipeline iterations; surplus ones are dummies without MMAs
-  const int iters = (p.num_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  // work units: tiles, or tile pairs (2u, 2u + 1 -> rank 0, 1) in pair mode
+  const int nunits = kPair ? p.num_tiles / 2 : p.num_tiles;
+  const int nworkers = kPair ? static_cast<int>(gridDim.x) / 2 : static_cast<int>(gridDim.x);
+  const int iters = (nunits + nworkers - 1) / nworkers;
   // a CTA owns `iters` CONSECUTIVE tiles: it stays inside one slide for up to `iters` tiles, so the folded queries are
   // reloaded once or twice per CTA instead of once per tile (a stride of gridDim tiles lands in a new slide every time)
-  const int tile0 = static_cast<int>(blockIdx.x) * iters;
+  const int unit0 = (kPair ? static_cast<int>(blockIdx.x) / 2 : static_cast<int>(blockIdx.x)) * iters;
+  const int nreal = max(0, min(iters, nunits - unit0));
+  auto tile_at = [&](int it) { return kPair ? 2 * (unit0 + it) + static_cast<int>(cta_rank) : unit0 + it; };
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -108,20 +120,26 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       constexpr int kWRows = kD / kC;                     // W_H rows this CTA fetches per K block
-      int row_pref = tile0 < p.num_tiles ? p.tile_info[tile0].row0 : -1;   // loaded one tile ahead of its use
+      int row_pref = nreal > 0 ? p.tile_info[tile_at(0)].row0 : -1;        // loaded one tile ahead of its use
       for (int it = 0; it < iters; ++it) {
         int row0 = row_pref >= 0 ? row_pref : 0;
         if (p.debug & 2) row0 = (blockIdx.x & 7) * kTileM;
-        const int tn = tile0 + it + 1;
-        row_pref = (it + 1 < iters && tn < p.num_tiles) ? p.tile_info[tn].row0 : -1;
+        row_pref = it + 1 < nreal ? p.tile_info[tile_at(it + 1)].row0 : -1;
         const int row_next = row_pref;
         for (int kb = 0; kb < kKBlocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + FwdSmem::stages + stage * kStageBytes;
+          uint8_t* sa = smem + FwdSmem::stages + stage * kSB;
+          if (kPair) {
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kSB);      // the bytes of both CTAs
+            tma2_load_2d(sa, &tm_x, &full_bar[stage], kb * kBK, row0, pol_stream);
+            tma2_load_2d(sa + kABytes, &tm_w, &full_bar[stage], kb * kBK, static_cast<int>(cta_rank) * (kD / 2), pol_keep);
+            if (++stage == kNS) { stage = 0; phase ^= 1; }
+            continue;
+          }
           const bool skip_w = (p.debug & 1) && it > 0;
           if ((p.debug & 8) && it > 0) {            // timing experiment: no TMA traffic at all
             mbar_arrive(&full_bar[stage]);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (++stage == kNS) { stage = 0; phase ^= 1; }
             continue;
           }
           mbar_expect_tx(&full_bar[stage], skip_w ? kABytes : kStageBytes);
@@ -134,18 +152,18 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             tma_load_2d_mcast(sa + kABytes + cta_rank * (kWRows * 128), &tm_w, &full_bar[stage], kb * kBK,
                               cta_rank * kWRows, kMask, pol_keep);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kNS) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, kD, 0, 0);
+    if (lane == 0 && (!kPair || cta_rank == 0)) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kPair ? 2 * kTileM : kTileM, kD, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
-        const bool real = tile0 + it < p.num_tiles;
+        const bool real = it < nreal;
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         if (real) {
@@ -157,21 +175,26 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (real && !(p.debug & 16)) {            // (debug bit 4: timing experiment without the main MMAs)
-            const uint32_t a_addr = smem_u32(smem + FwdSmem::stages + stage * kStageBytes);
+            const uint32_t a_addr = smem_u32(smem + FwdSmem::stages + stage * kSB);
             const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
               const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
               const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-              umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (kPair) umma2_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
           // frees this smem stage -- in every CTA of the cluster -- once these MMAs retire
-          if (kC == 1) umma_commit(&empty_bar[stage]);
+          if (kPair) umma2_commit_mcast(&empty_bar[stage], kMask);
+          else if (kC == 1) umma_commit(&empty_bar[stage]);
           else umma_commit_mcast(&empty_bar[stage], kMask);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kNS) { stage = 0; phase ^= 1; }
         }
-        if (real) umma_commit(&tfull_bar[as]);      // accumulator complete -> epilogue
+        if (real) {                                 // accumulator complete -> epilogue (of both CTAs in pair mode)
+          if (kPair) umma2_commit_mcast(&tfull_bar[as], kMask);
+          else umma_commit(&tfull_bar[as]);
+        }
       }
     }
   } else {
@@ -206,7 +229,8 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       tc_fence_after();
       if (ch < 2) {
         uint32_t dv[16];
-        tmem_ld_32x32b_x16(tmem_base + pas * kD + (static_cast<uint32_t>(qd * 32) << 16) + ch * 16, dv);
+        tmem_ld_32x32b_x16(tmem_base + pas * kD + (static_cast<uint32_t>(qd * 32) << 16) +
+                               (kPair ? ch * 32 + 16 * static_cast<int>(cta_rank) : ch * 16), dv);
         tmem_ld_wait();
         float* dst = p.part_pool + static_cast<size_t>(tt) * (kQ * kD) + ch * 128 + qd * 32 + lane;
 #pragma unroll
@@ -214,13 +238,13 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[pas]);
+      if (lane == 0) { if (kPair) mbar_arrive_pair0(&tempty_bar[pas]); else mbar_arrive(&tempty_bar[pas]); }
     };
-    const int tile_end = min(tile0 + iters, p.num_tiles);
-    TileInfo ti_next = tile0 < tile_end ? p.tile_info[tile0] : TileInfo{};
-    for (int t = tile0; t < tile_end; ++t, ++it) {
+    TileInfo ti_next = nreal > 0 ? p.tile_info[tile_at(0)] : TileInfo{};
+    for (; it < nreal; ++it) {
+      const int t = tile_at(it);
       const TileInfo ti = ti_next;
-      if (t + 1 < tile_end) ti_next = p.tile_info[t + 1];     // in flight during this tile's epilogue
+      if (it + 1 < nreal) ti_next = p.tile_info[tile_at(it + 1)];     // in flight during this tile's epilogue
       if (prev_t >= 0) read_pooled(prev_t, (it - 1) & 1, (it - 1) & 1);   // also: the staged tile / P operand are free again
       prev_t = -1;
       if (et == 32) tma_store_wait_read();      // the previous tile's H store no longer reads the staged tile
@@ -241,7 +265,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       if (p.debug & 32) {                       // timing experiment: loads + MMAs alone, no epilogue work
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) { if (kPair) mbar_arrive_pair0(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
         continue;
       }
 
@@ -382,7 +406,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         // NaCAGaT: the softmax runs on the gated scores in bag_gate_kernel; this pass only projects and scores
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) { if (kPair) mbar_arrive_pair0(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
         continue;
       }
       if (ch == 0) {
@@ -425,7 +449,26 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       }
 
       // ---- (4) pooled = p^T H on the tensor core: A = the same staged bytes read M-major (features), K = 128 patches
-      if (et == 0) {
+      if (kPair) {
+        // one pair MMA, N = 32: rank r's weight rows are B rows 16r..16r+15, so its product sits in columns 16r..16r+15
+        if (et == 0) {
+          mbar_arrive_pair0(pready_bar);
+          if (cta_rank == 0) {
+            mbar_wait(pready_bar, tphase);
+            tc_fence_after();
+            constexpr uint32_t idesc_p = umma_idesc(2 * kTileM, 32, 0, 0, 1, 0);
+            const uint32_t a0 = smem_u32(staging), b0 = smem_u32(Pb);
+#pragma unroll
+            for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)
+                umma2_f16(acc_col + mh * 32,
+                          umma_desc_sw128(a0 + mh * 2 * (kTileM * 128) + kk * 2048, kTileM * 128, 1024),
+                          umma_desc_sw128(b0 + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), idesc_p, kk != 0 ? 1u : 0u);
+            umma2_commit_mcast(d_bar, kMask);
+          }
+        }
+      } else if (et == 0) {
         tc_fence_after();
         const uint32_t a0 = smem_u32(staging), b0 = smem_u32(Pb);
 #pragma unroll
@@ -448,7 +491,8 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   if (kC > 1) cluster_sync_all();     // nobody leaves while a peer may still multicast into / arrive on its smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kPair) tmem_dealloc2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -527,13 +571,13 @@ bag_merge_kernel(const int* __restrict__ tile_prefix,   // [B+1] first tile of e
 // ------------------------------------------------------------------------------------------------
 // host launchers (C++ side; the extern "C" surface is in api.cu)
 // ------------------------------------------------------------------------------------------------
-template <int kC>
+template <int kC, bool kPair = false>
 static cudaError_t launch_fwd_cluster(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const CUtensorMap& tm_h,
                                       const BagFwdParams& prm,
                                       int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   static int max_clusters = 0;
-  auto kern = bag_fwd_kernel<kC>;
+  auto kern = bag_fwd_kernel<kC, kPair>;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kFwdThreads);
   cfg.dynamicSmemBytes = kFwdSmemBytes;
@@ -575,6 +619,10 @@ int fwd_cluster_size() {
 cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const CUtensorMap& tm_h,
                            const BagFwdParams& prm, int num_sms, cudaStream_t stream) {
   if (prm.num_tiles <= 0) return cudaSuccess;
+  static int pair = -1;
+  if (pair < 0) { const char* e = getenv("MPO_FWD_PAIR"); pair = (e && atoi(e) != 0) ? 1 : 0; }
+  if (pair && fwd_cluster_size() == 2 && prm.num_tiles % 2 == 0 && (prm.debug & ~(32 | 64 | 128)) == 0)
+    return launch_fwd_cluster<2, true>(tm_x, tm_w, tm_h, prm, num_sms, stream);
   switch (fwd_cluster_size()) {
     case 1: return launch_fwd_cluster<1>(tm_x, tm_w, tm_h, prm, num_sms, stream);
     case 4: return launch_fwd_cluster<4>(tm_x, tm_w, tm_h, prm, num_sms, stream);

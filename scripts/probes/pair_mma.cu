@@ -31,34 +31,7 @@ __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity, int
   printf("probe: wait %d timed out (block %d thread %d)\n", what, blockIdx.x, threadIdx.x);
   __trap();
 }
-__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish2() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma2_commit_mcast(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)), "h"(mask)
-               : "memory");
-}
-// this CTA's box lands in its own shared memory; the bytes complete on the barrier of the pair's rank-0 CTA
-__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint64_t pol) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)),
-      "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(pol)
-      : "memory");
-}
+// (the cta_group::2 instruction forms are in mpo_ptx.cuh: tmem_alloc2, umma2_f16, umma2_commit_mcast, tma2_load_2d, ...)
 
 // mode 0: correctness (TMA pipeline, H written out).  mode 1 / 2: `reps` x 64 MMAs on whatever is resident, cta_group 1 / 2
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
@@ -113,7 +86,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         const uint32_t a = smem_u32(smem + s * kStage), b = a + kAB;
 #pragma unroll
         for (int k = 0; k < kBKp / 16; ++k)
-          umma2_bf16(tmem, umma_desc_sw128(a + k * 32, 16, 1024), umma_desc_sw128(b + k * 32, 16, 1024), idesc,
+          umma2_f16(tmem, umma_desc_sw128(a + k * 32, 16, 1024), umma_desc_sw128(b + k * 32, 16, 1024), idesc,
                      (kb | k) != 0 ? 1u : 0u);
         umma2_commit_mcast(&empty[s], 3);
       }
@@ -155,7 +128,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0)
-      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(pready) & 0xFEFFFFFFu) : "memory");
+      mbar_arrive_pair0(pready);
     if (warp == 1 && lane == 0 && rank == 0) {
       wait_or_trap(pready, 0, 22);
       tc_fence_after();
@@ -163,7 +136,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       const uint32_t a0 = smem_u32(staging), b0 = smem_u32(Pb);
       for (int mh = 0; mh < 2; ++mh)
         for (int kk = 0; kk < 8; ++kk)
-          umma2_bf16(tmem + mh * 32, umma_desc_sw128(a0 + mh * 2 * 16384 + kk * 2048, 128 * 128, 1024),
+          umma2_f16(tmem + mh * 32, umma_desc_sw128(a0 + mh * 2 * 16384 + kk * 2048, 128 * 128, 1024),
                      umma_desc_sw128(b0 + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), idesc_d, kk != 0 ? 1u : 0u);
       umma2_commit_mcast(done, 3);
     }
@@ -189,7 +162,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 #pragma unroll 1
         for (int i = 0; i < 64; ++i) {
           const uint64_t da = umma_desc_sw128(a + (i & 3) * 32, 16, 1024), db = umma_desc_sw128(b + (i & 3) * 32, 16, 1024);
-          if (pair) umma2_bf16(tmem, da, db, idesc, 1u);
+          if (pair) umma2_f16(tmem, da, db, idesc, 1u);
           else umma_bf16(tmem, da, db, idesc, 1u);
         }
       if (pair) umma2_commit_mcast(done, 3);
@@ -289,7 +262,7 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < kBKp / 16; ++k) {
           const uint64_t da = umma_desc_sw128(a + k * 32, 16, 1024), db = umma_desc_sw128(b + k * 32, 16, 1024);
-          if (PAIR) umma2_bf16(tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (PAIR) umma2_f16(tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           else umma_bf16(tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         if (PAIR) umma2_commit_mcast(&empty[s], 3);

@@ -1,8 +1,3 @@
-# quick check of the in-tree build: parity tests, smoke, a short bench
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/iter_pytest.log 2>&1; echo "pytest rc=$?"
-tail -2 gpurun_out/iter_pytest.log
-timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 600 python bench.py --no-also > gpurun_out/iter_bench.json 2> gpurun_out/iter_bench.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/iter_bench.json
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | cut -c1-300
+for cfg in "1 0 1" "1 32 1" "1 0 0" "0 32 1" "0 0 0" "0 0 1"; do set -- $cfg; MPO_FWD_PAIR=$1 MPO_FWD_DEBUG=$2 MPO_TIME_SAVE_H=$3 timeout 100 python scripts/gpu_time_bag.py 32 fwd 2>&1 | tail -1 | sed "s/^/pair=$1 /"; done | tee gpurun_out/iter_pair.log

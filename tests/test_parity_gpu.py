@@ -364,3 +364,16 @@ def test_train_mode_gradients_match_finite_differences(model, fusion):
             bad.append((k, j, an, fd))
     print(model, fusion, "checked", checked, "bad", bad)
     assert len(bad) <= 1, bad       # one probe may straddle a ReLU kink
+
+
+def test_pair_tile_forward_kernel_matches_reference():
+    """The cta_group::2 variant of the forward bag kernel (MPO_FWD_PAIR=1: two adjacent tiles share every MMA, half of
+    the W_H block per CTA, pooled product as one N = 32 pair MMA) against the same reference fixtures
+    and the batched-trainer check.  The switch is read once per process, hence the subprocess."""
+    import subprocess
+    env = dict(os.environ, MPO_FWD_PAIR="1")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", "-k",
+                        "test_forward_backward_matches_reference or test_batched_trainer_equals_per_slide_gradients"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
