@@ -238,7 +238,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { if (kPair) mbar_arrive_pair0(&tempty_bar[pas]); else mbar_arrive(&tempty_bar[pas]); }
+      if (lane == 0 && !(p.debug & 256)) { if (kPair) mbar_arrive_pair0(&tempty_bar[pas]); else mbar_arrive(&tempty_bar[pas]); }
     };
     TileInfo ti_next = nreal > 0 ? p.tile_info[tile_at(0)] : TileInfo{};
     for (; it < nreal; ++it) {
@@ -347,6 +347,10 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       }
       fence_proxy_async_smem();      // generic-proxy writes of the tile -> visible to UMMA / TMA (async proxy)
       tc_fence_before();
+      if (p.debug & 256) {           // timing experiment (WRONG pooled vectors): the accumulator stage goes back to the MMA
+        __syncwarp();                // warp as soon as it has been drained, not after the pooled product has been read
+        if (lane == 0) { if (kPair) mbar_arrive_pair0(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
+      }
       named_bar_sync(1, kEpiThreads);
       if (ch == 0 || ch == 2) {
         const float* src = ch == 0 ? spart_s : reinterpret_cast<const float*>(Pb);
@@ -621,7 +625,7 @@ cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, con
   if (prm.num_tiles <= 0) return cudaSuccess;
   static int pair = -1;
   if (pair < 0) { const char* e = getenv("MPO_FWD_PAIR"); pair = (e && atoi(e) != 0) ? 1 : 0; }
-  if (pair && fwd_cluster_size() == 2 && prm.num_tiles % 2 == 0 && (prm.debug & ~(32 | 64 | 128)) == 0)
+  if (pair && fwd_cluster_size() == 2 && prm.num_tiles % 2 == 0 && (prm.debug & ~(32 | 64 | 128 | 256)) == 0)
     return launch_fwd_cluster<2, true>(tm_x, tm_w, tm_h, prm, num_sms, stream);
   switch (fwd_cluster_size()) {
     case 1: return launch_fwd_cluster<1>(tm_x, tm_w, tm_h, prm, num_sms, stream);
