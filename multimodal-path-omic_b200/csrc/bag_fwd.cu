@@ -278,8 +278,13 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       for (int c4 = 0; c4 < 8 / kCG; ++c4) {
         const int col0 = ch * (kD / kCG) + c4 * 32;
         uint32_t v[32];
-        tmem_ld_32x32b_x32(acc_col + (static_cast<uint32_t>(qd * 32) << 16) + col0, v);
-        tmem_ld_wait();
+        if (p.debug & 512) {          // timing experiment (wrong results): no accumulator reads
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0x3f000000u + static_cast<uint32_t>(j + lane);
+        } else {
+          tmem_ld_32x32b_x32(acc_col + (static_cast<uint32_t>(qd * 32) << 16) + col0, v);
+          tmem_ld_wait();
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           float h[8];
@@ -625,7 +630,7 @@ cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, con
   if (prm.num_tiles <= 0) return cudaSuccess;
   static int pair = -1;
   if (pair < 0) { const char* e = getenv("MPO_FWD_PAIR"); pair = (e && atoi(e) != 0) ? 1 : 0; }
-  if (pair && fwd_cluster_size() == 2 && prm.num_tiles % 2 == 0 && (prm.debug & ~(32 | 64 | 128 | 256)) == 0)
+  if (pair && fwd_cluster_size() == 2 && prm.num_tiles % 2 == 0 && (prm.debug & ~(32 | 64 | 128 | 256 | 512)) == 0)
     return launch_fwd_cluster<2, true>(tm_x, tm_w, tm_h, prm, num_sms, stream);
   switch (fwd_cluster_size()) {
     case 1: return launch_fwd_cluster<1>(tm_x, tm_w, tm_h, prm, num_sms, stream);

@@ -42,7 +42,8 @@ struct BagFwdParams {
                                // bit2 L2-prefetch the next tile's X, bit3 no TMA loads, bit4 no main MMAs,
                                // bit5 no epilogue work, bit6 h_saved store without the evict-first hint,
                                // bit7 h_saved stored through the LSU (st.global.cs) instead of the TMA unit,
-                               // bit8 accumulator stage released before the pooled product (wrong results)
+                               // bit8 accumulator stage released before the pooled product (wrong results),
+                               // bit9 epilogue without its accumulator reads (wrong results)
 };
 
 // NaCAGaT gate pass (bag_gate.cu)
