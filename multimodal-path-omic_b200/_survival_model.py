@@ -64,9 +64,17 @@ class SurvivalModelBase(nn.Module):
         self.classifier = nn.Linear(w1, n_classes)
         self._engine_obj = None
         self.model_size = model_size
+        # nn.DataParallel (models/mcat/main.py:267-268 wraps the model whenever the box has more than one GPU) calls
+        # forward() on replicas whose _parameters dicts are EMPTY (the weights are plain broadcast tensors there).  A
+        # replica shares this __dict__ entry, so it finds the module that owns the leaf parameters: the engine binds
+        # to that one, and gradients land in its .grad exactly where DataParallel's reduction would put them.
+        self._master_ref = (self,)
 
     @property
     def _engine(self):
+        master = self._master_ref[0]
+        if master is not self:
+            return master._engine
         if self._engine_obj is None:
             if self.model_sizes[0] != 256:
                 raise NotImplementedError(

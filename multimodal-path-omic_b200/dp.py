@@ -68,17 +68,27 @@ class DataParallelTrainer:
 def sharded_inference(module, wsi_local, omics, group=None):
     """MCAT / NaCAGaT inference on one bag whose patches are split over the ranks of `group`.
 
-    wsi_local: this rank's [n_local, 1024] slice (see patch_range); omics: the same 6 vectors on every rank.
-    Returns hazards, S, Y (identical on every rank) and this rank's [6, n_local] slice of the co-attention map."""
+    wsi_local: this rank's [n_local, 1024] slice (see patch_range; ranks at the tail of a short bag may hold ZERO
+    rows); omics: the same 6 vectors on every rank.  Returns hazards, S, Y (identical on every rank) and this rank's
+    [6, n_local] slice of the co-attention map.  Every rank takes part in the all-gather: an empty rank contributes
+    lse = -inf / pooled = 0, which the log-sum-exp combine weights with exactly zero."""
     from . import bagpass as bp
     eng = module._engine
-    if wsi_local.shape[0] == 0:
-        raise RuntimeError("every rank needs at least one patch of the sharded bag")
-    bag = bp.PackedBag.from_slides([wsi_local])
+    n_local = int(wsi_local.shape[-2])
+    if n_local == 0:
+        # the kernels need at least one row to launch on: one zero row whose statistics are discarded below
+        wsi_run = torch.zeros((1, wsi_local.shape[-1]), dtype=torch.bfloat16, device=wsi_local.device)
+    else:
+        wsi_run = wsi_local
+    bag = bp.PackedBag.from_slides([wsi_run])
     model = eng.binding.build(grads=None)
 
     def combine(st):
-        lse_all, pooled_all = gather_shard_stats(st.bag_ws.lse[0], st.bag_ws.pooled[0], group)
+        lse_l, pooled_l = st.bag_ws.lse[0], st.bag_ws.pooled[0]
+        if n_local == 0:
+            lse_l = torch.full_like(lse_l, float("-inf"))
+            pooled_l = torch.zeros_like(pooled_l)
+        lse_all, pooled_all = gather_shard_stats(lse_l, pooled_l, group)
         lse, pooled = bp.lse_combine(lse_all, pooled_all)
         st.bag_ws.lse.copy_(lse.reshape(1, 6))
         st.bag_ws.pooled.copy_(pooled.reshape(1, 6, -1))
@@ -87,4 +97,6 @@ def sharded_inference(module, wsi_local, omics, group=None):
         st = eng.forward(model, bag, [o.reshape(1, -1) for o in omics], train=False, save_for_backward=False,
                          after_bag=combine)
         amap = eng.attention_map(st)
+    if n_local == 0:
+        amap = amap[:, :0]
     return st.hazards, st.S, st.Y, amap

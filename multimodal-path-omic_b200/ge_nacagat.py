@@ -34,6 +34,7 @@ class GeneExprNarrowContextualAttentionGateTransformer(nn.Module):
         self.path_rho = nn.Sequential(*[nn.Linear(w1, w1), nn.ReLU(), nn.Dropout(dropout)])
         self.classifier = nn.Linear(w1, n_classes)
         self._w_bf16 = None
+        self._master_ref = (self,)      # nn.DataParallel replicas have empty _parameters: they run on this module's leaves
 
     def get_trainable_parameters(self):
         return sum(p.numel() for p in self.parameters() if p.requires_grad)
@@ -87,10 +88,11 @@ class GeneExprNarrowContextualAttentionGateTransformer(nn.Module):
 
     def forward(self, wsi):
         require_cuda(wsi, "wsi")
-        names = [n for n, _ in self.named_parameters()]
-        params = [p for _, p in self.named_parameters()]
+        master = self._master_ref[0]
+        names = [n for n, _ in master.named_parameters()]
+        params = [p for _, p in master.named_parameters()]
         needs_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        Y, attn, path = _GeFn.apply(self, needs_bwd, bool(self.training), wsi, len(names), *params)
+        Y, attn, path = _GeFn.apply(master, needs_bwd, bool(self.training), wsi, len(names), *params)
         return Y, {'attn': attn, 'path': path}
 
 

@@ -22,8 +22,20 @@ _FUSION_CODE = {"concat": FUSION_CONCAT, "bilinear": FUSION_BILINEAR}
 _seed_counter = itertools.count(1)
 
 
+def _rank_salt():
+    """ranks seeded identically (the usual torch.manual_seed(0) on every rank) must still draw different dropout
+    masks for their different slides (rank-distinct offsets)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank() + 1
+    except Exception:
+        pass
+    return 0
+
+
 def _next_seed():
-    return (torch.initial_seed() * 2654435761 + next(_seed_counter) * 40503) & 0xFFFFFFFF
+    return (torch.initial_seed() * 2654435761 + next(_seed_counter) * 40503 + _rank_salt() * 0x9E3779B1) & 0xFFFFFFFF
 
 
 def _lin_names(prefix):
@@ -193,7 +205,19 @@ class SlideState:
     pass
 
 
+def _no_engine():
+    return None
+
+
 class SlideEngine:
+    # an engine caches device buffers and ctypes structs over one module's parameter addresses: a copy.deepcopy() or
+    # pickle of the owning module drops it, and the copy builds its own on first use
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (_no_engine, ())
+
     def __init__(self, binding, bag_dropout=0.25, attn_dropout=0.25):
         self.binding = binding
         self.bag_dropout = float(bag_dropout)
@@ -491,6 +515,23 @@ def run_slide(engine, wsi, omics, want_map, train):
 
 
 # ------------------------------------------------------------------------------------------------ batched training
+def rebind_grad_views(params, grad_views):
+    """optimizer.zero_grad() / module.zero_grad() default to set_to_none=True (it is the call in the reference loop,
+    models/mcat/main.py:72-74) and drop the .grad views of the flat gradient buffer bound by BatchTrainer; the kernels
+    would keep accumulating into the flat buffer while a torch optimizer sees grad None and skips every parameter.
+    Re-bind: a parameter whose .grad was set to None gets its (zeroed) slice back, a foreign .grad tensor is copied
+    into the slice."""
+    for n, p in params.items():
+        g = grad_views[n]
+        if p.grad is g:
+            continue
+        if p.grad is None:
+            g.zero_()
+        elif p.grad.data_ptr() != g.data_ptr():
+            g.copy_(p.grad)
+        p.grad = g
+
+
 class BatchTrainer:
     """Forward + loss + backward for B slides per call with gradients accumulated straight into one flat fp32
     buffer whose slices are the parameters' .grad (so a single NCCL all-reduce covers the whole model).
@@ -524,8 +565,14 @@ class BatchTrainer:
         self.grad_acc_step = int(grad_acc_step)
         self.model = bnd.build(grads=self.grads)
 
-    def zero_grad(self):
+    def zero_grad(self, set_to_none=False):
+        """zeroes the flat gradient buffer; the parameters' .grad stay views of it (set_to_none is accepted for
+        signature compatibility and ignored: the kernels accumulate into this buffer by address)."""
         self.flat_grad.zero_()
+        self.check_grad_views()
+
+    def check_grad_views(self):
+        rebind_grad_views(self.engine.binding.params(), self.grads)
 
     # -- optimizer over the flat buffers (mpo_adam_step)
     def use_flat_adam(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5):
@@ -592,6 +639,7 @@ class BatchTrainer:
 
     def step(self, bag, omics, labels, censor, train=True, seed=None):
         """Returns (loss [B], hazards [B,K], S [B,K]).  labels int64 [B], censor float32 [B], on the GPU."""
+        self.check_grad_views()
         st = self._run(None, bag, omics, labels, censor, train, seed)
         self.last_state = st
         return st.loss, st.hazards, st.S
@@ -653,19 +701,22 @@ class BatchTrainer:
         launches = int(_lib.lib().mpo_launch_count(1))     # kernels recorded into the graph(s) = launched per replay
         self.flat_grad.zero_()
         self.last_state = st
-        return GraphedStep(graph, st, (bag, omics, labels, censor), launches, graph2)
+        return GraphedStep(graph, st, (bag, omics, labels, censor), launches, graph2, trainer=self)
 
 
 class GraphedStep:
     """A captured train step over static buffers: refresh the buffers in place, then replay()."""
 
-    def __init__(self, graph, state, static_inputs, launches=0, graph2=None):
+    def __init__(self, graph, state, static_inputs, launches=0, graph2=None, trainer=None):
         self.graph, self.graph2, self.state, self.static_inputs = graph, graph2, state, static_inputs
+        self.trainer = trainer
         self.launches_per_replay = launches     # kernels of libmpo_b200.so inside the captured step
         self.replays = 0
 
     def replay_first(self):
         """split capture: pre, bag forward, post forward + loss + post backward (post-stage gradients complete)."""
+        if self.trainer is not None and self.trainer.flat_param is None:
+            self.trainer.check_grad_views()       # a torch optimizer reads p.grad: keep the views bound (see BatchTrainer)
         self.graph.replay()
 
     def replay_second(self):
@@ -676,7 +727,7 @@ class GraphedStep:
         return st.loss, st.hazards, st.S
 
     def replay(self):
-        self.graph.replay()
+        self.replay_first()
         if self.graph2 is not None:
             return self.replay_second()
         self.replays += 1

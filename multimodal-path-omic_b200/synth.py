@@ -23,8 +23,9 @@ def _is_norm_weight(name):
     return name.endswith(("norm1.weight", "norm2.weight", ".G.1.weight", ".E.1.weight"))
 
 
-def make_state(shapes, seed, model="mcat", sharpen=1.0):
-    """shapes: ordered {state_dict key: shape}.  Returns {key: float32 ndarray}."""
+def make_state(shapes, seed, model="mcat", sharpen=1.0, round_bag_weights=True):
+    """shapes: ordered {state_dict key: shape}.  Returns {key: float32 ndarray}.  round_bag_weights=False leaves the
+    bag-facing weights un-rounded (the "unrounded" fixtures that measure what the kernels' own bf16 rounding costs)."""
     out = {}
     for idx, (name, shape) in enumerate(shapes.items()):
         shape = tuple(int(s) for s in shape)
@@ -39,9 +40,9 @@ def make_state(shapes, seed, model="mcat", sharpen=1.0):
         w = w.astype(np.float32)
         if name == "co_attention.in_proj_weight" or name == "self_attention.in_proj_weight":
             w = (w * np.float32(sharpen)).astype(np.float32)
-        if name == "H.0.weight":
+        if name == "H.0.weight" and round_bag_weights:
             w = bf16_round(w)
-        if name == "co_attention.in_proj_weight" and model == "nacagat":
+        if name == "co_attention.in_proj_weight" and model == "nacagat" and round_bag_weights:
             e = shape[1]
             w[e:2 * e] = bf16_round(w[e:2 * e])
         out[name] = w

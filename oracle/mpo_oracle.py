@@ -561,6 +561,7 @@ def model_forward_backward(P, wsi, omics, label=None, censor=None, model="mcat",
         dG2, dH = mcat_coattn_bwd(P, cco, dHc, grads)
     else:
         dG2, dH = nacagat_coattn_bwd(P, cco, dHc, grads)
+    out["_internals"] = dict(H=H, dHc=dHc, coattn_cache=cco, dH=dH)      # for bag-stage level comparisons in tests
     snn_bwd(P, csnn, dG + dG2, grads)
     bag_proj_bwd(P, X, H, dH, grads)
     out["grads"] = dict(grads)
@@ -633,3 +634,19 @@ def folded_bag_stage(W_h, b_h, qk, X):
     lse = m[:, 0] + np.log(np.exp(s - m).sum(axis=1))
     a = np.exp(s - lse[:, None])
     return H, s, lse, a @ H
+
+
+def folded_bag_stage_bwd(W_h, b_h, qk, X, dpooled):
+    """Autograd of folded_bag_stage w.r.t. the folded queries, H.0.weight and H.0.bias given d(pooled) [6,256]
+    (the chain mcat.py:87,97 leaves on the bag side once K/V are folded):
+    da = dpooled h, ds = a (da - sum a da), dqk = ds H, dH = a^T dpooled + ds^T qk, dz = dH [z > 0], dW = dz^T X."""
+    X = np.asarray(X, F64)
+    H, s, lse, pooled = folded_bag_stage(W_h, b_h, qk, X)
+    a = np.exp(s - lse[:, None])
+    dP = np.asarray(dpooled, F64)
+    da = dP @ H.T
+    ds = a * (da - (a * da).sum(axis=1, keepdims=True))
+    dqk = ds @ H
+    dH = a.T @ dP + ds.T @ np.asarray(qk, F64)
+    dz = dH * (H > 0)
+    return dict(dqk=dqk, dW=dz.T @ X, db=dz.sum(axis=0), pooled=pooled, lse=lse, scores=s)

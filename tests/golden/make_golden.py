@@ -29,6 +29,14 @@ CASES = [
     ("nacagat_concat_sharp_517", "nacagat", "concat", 517, 8, 8.0),
     ("nacagat_bilinear_200", "nacagat", "bilinear", 200, 9, 4.0),
     ("nacagat_concat_4096", "nacagat", "concat", 4096, 10, 4.0),
+    # the benchmarked shape (BASELINE configs 2/3: 16 384 patches = 128 tiles) and one 25 088-patch shard of config 5
+    ("mcat_concat_16384", "mcat", "concat", 16384, 11, 4.0),
+    ("nacagat_concat_16384", "nacagat", "concat", 16384, 12, 4.0),
+    ("mcat_concat_25088", "mcat", "concat", 25088, 13, 6.0),
+    # SURVEY H2 option (a), second half: the reference run on weights that are NOT bf16-representable (the CUDA path
+    # rounds H.0.weight / W_k itself): the delta is reported by tests/test_parity_gpu.py::test_unrounded_weights_delta
+    ("mcat_concat_unrounded_4096", "mcat", "concat", 4096, 14, 4.0),
+    ("nacagat_concat_unrounded_4096", "nacagat", "concat", 4096, 15, 4.0),
 ]
 
 
@@ -57,12 +65,15 @@ def main():
     MCAT, NACAGAT, NLL, CES = import_reference()
     torch.set_num_threads(8)
     outdir = os.path.dirname(os.path.abspath(__file__))
+    only = set(sys.argv[1:])          # optional: generate only the named cases (existing fixtures stay untouched)
     for name, model, fusion, n, seed, sharpen in CASES:
+        if only and name not in only:
+            continue
         cls = MCAT if model == "mcat" else NACAGAT
         torch.manual_seed(seed)
         net = cls(omic_sizes=list(synth.OMIC_SIZES), fusion=fusion)
         shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
-        state = synth.make_state(shapes, seed, model=model, sharpen=sharpen)
+        state = synth.make_state(shapes, seed, model=model, sharpen=sharpen, round_bag_weights="unrounded" not in name)
         net.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()})
         net.eval()
         bag, omics, label, censor = synth.make_slide(seed, n)
@@ -101,6 +112,8 @@ def main():
     # pooling logits, the driver's CrossEntropyLoss on Y (models/ge_nacagat/main.py:33) and its gradient digests
     from models.ge_nacagat.ge_nacagat import GeneExprNarrowContextualAttentionGateTransformer as GE
     for name, n, seed, sharpen in GE_CASES:
+        if only and name not in only:
+            continue
         torch.manual_seed(seed)
         net = GE()
         shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
@@ -130,6 +143,8 @@ def main():
         np.savez_compressed(os.path.join(outdir, name + ".npz"), **rec)
         print(f"{name}: Y={rec['Y'].round(5).tolist()} loss={rec['loss']:.6f} attn max={A.max():.3e}")
 
+    if only and "loss_known_answers" not in only:
+        return
     # loss known answers: the reference's own test vectors (models/loss.py:108-121) plus the SURVEY 8c probes
     hz = torch.tensor([0.51, 0.52, 0.49, 0.48]).reshape(1, 4)
     S = torch.tensor([0.5, 0.4, 0.2, 0.1]).reshape(1, 4)

@@ -10,9 +10,12 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 synth = import_module("multimodal-path-omic_b200.synth")
 
 
-def golden_cases():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not p.endswith("loss_known_answers.npz") and not os.path.basename(p).startswith("ge_"))
+def golden_cases(unrounded=False):
+    """MCAT / NaCAGaT fixtures.  The `unrounded` ones hold reference results for weights that are not
+    bf16-representable: the oracle must match them exactly, the CUDA path only within the reported rounding delta."""
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                   if not p.endswith("loss_known_answers.npz") and not os.path.basename(p).startswith("ge_"))
+    return [n for n in names if ("unrounded" in n) == unrounded]
 
 
 def ge_cases():
@@ -37,7 +40,8 @@ def load_case(name):
     model, fusion = parts[0], parts[1]
     names = [str(s) for s in z["param_names"]]
     shapes = {k: ast.literal_eval(str(s)) for k, s in zip(names, z["param_shapes"])}
-    state = synth.make_state(shapes, int(seed), model=model, sharpen=float(sharpen))
+    state = synth.make_state(shapes, int(seed), model=model, sharpen=float(sharpen),
+                             round_bag_weights="unrounded" not in name)
     bag, omics, lab, cen = synth.make_slide(int(seed), int(n))
     assert lab == int(label) and cen == float(censor)
     return dict(name=name, model=model, fusion=fusion, n=int(n), seed=int(seed), label=lab, censor=cen,

@@ -158,3 +158,72 @@ def test_parameter_map_follows_reassigned_parameters_and_modules():
     same(bnd.params(refresh=True))
     net.load_state_dict({k: v.clone() for k, v in net.state_dict().items()})
     same(bnd.params(refresh=True))
+
+
+def test_data_parallel_replica_binds_to_the_module_that_owns_the_parameters():
+    """models/mcat/main.py:267-268 wraps the model in nn.DataParallel whenever the box has several GPUs;
+    DataParallel.replicate() builds replicas whose _parameters dicts are empty.  A replica must resolve to the engine of
+    the module that owns the leaf parameters."""
+    synth = _pkg("synth")
+    for cls in (_pkg("mcat").MultimodalCoAttentionTransformer, _pkg("nacagat").NarrowContextualAttentionGateTransformer):
+        net = cls(omic_sizes=list(synth.OMIC_SIZES))
+        # what torch.nn.parallel.replicate() does on one device: every module is shallow-copied with an empty
+        # _parameters dict, children re-linked, the weights re-attached as plain (non-leaf) tensors
+        mods = list(net.modules())
+        idx = {m: i for i, m in enumerate(mods)}
+        reps = [m._replicate_for_data_parallel() for m in mods]
+        for m, r in zip(mods, reps):
+            for key, child in m._modules.items():
+                r._modules[key] = None if child is None else reps[idx[child]]
+            for key, p in m._parameters.items():
+                if p is not None:
+                    setattr(r, key, p.detach().clone().requires_grad_())     # nn.Module.__setattr__: a plain tensor
+        replica = reps[0]
+        assert not list(replica.named_parameters())
+        eng = replica._engine
+        assert eng is net._engine and eng.binding.module is net
+        assert eng.binding.names == [n for n, _ in net.named_parameters()]
+        P = eng.binding.params(refresh=True)
+        assert all(P[n] is p for n, p in net.named_parameters())
+    ge = _pkg("ge_nacagat").GeneExprNarrowContextualAttentionGateTransformer()
+    assert ge._replicate_for_data_parallel()._master_ref[0] is ge
+
+
+def test_deepcopy_and_pickle_drop_the_engine_and_rebind():
+    import copy
+    import pickle
+    synth = _pkg("synth")
+    net = _pkg("mcat").MultimodalCoAttentionTransformer(omic_sizes=list(synth.OMIC_SIZES))
+    eng = net._engine
+    eng.binding.params(refresh=True)
+    for clone in (copy.deepcopy(net), pickle.loads(pickle.dumps(net))):
+        assert clone._engine_obj is None and clone._master_ref[0] is clone
+        assert clone._engine is not eng and clone._engine.binding.module is clone
+
+
+def test_batch_trainer_rebinds_gradient_views_after_zero_grad_set_to_none():
+    """optimizer.zero_grad() (set_to_none=True by default, the call in models/mcat/main.py:72-74) drops the .grad views
+    of the flat gradient buffer; rebind_grad_views() -- run by BatchTrainer.step() / zero_grad() and GraphedStep.replay()
+    -- restores them."""
+    synth = _pkg("synth")
+    sp = _pkg("slidepath")
+    net = _pkg("mcat").MultimodalCoAttentionTransformer(omic_sizes=list(synth.OMIC_SIZES))
+    P = dict(net.named_parameters())
+    flat = torch.full((sum(p.numel() for p in P.values()),), 3.0)
+    views, off = {}, 0
+    for n, p in P.items():
+        views[n] = flat[off:off + p.numel()].view_as(p)
+        p.grad = views[n]
+        off += p.numel()
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    opt.zero_grad()                                      # set_to_none=True
+    assert all(p.grad is None for p in net.parameters())
+    net.classifier.bias.grad = torch.full_like(net.classifier.bias, 7.0)     # a foreign gradient tensor
+    sp.rebind_grad_views(P, views)
+    for n, p in P.items():
+        assert p.grad is views[n]
+        want = 7.0 if n == "classifier.bias" else 0.0
+        assert float(p.grad.max()) == want and float(p.grad.min()) == want
+    net.zero_grad(set_to_none=False)
+    sp.rebind_grad_views(P, views)
+    assert float(flat.abs().max()) == 0.0 and all(p.grad is views[n] for n, p in P.items())

@@ -15,7 +15,7 @@ OUT_TOL = 2e-4     # reference runs in fp32, the oracle in fp64
 GRAD_TOL = 1e-3    # norm-relative, with the noise floor of helpers.digest_errors
 
 
-@pytest.mark.parametrize("name", golden_cases())
+@pytest.mark.parametrize("name", golden_cases() + golden_cases(unrounded=True))
 def test_oracle_matches_reference_fixture(name):
     c = load_case(name)
     out = orc.model_forward_backward(c["state"], c["bag"], c["omics"], c["label"], c["censor"], model=c["model"],
@@ -110,3 +110,29 @@ def test_folded_bag_stage_equals_unfolded_attention():
     out2 = (pooled @ Win[2 * E:].T + b_in[2 * E:]) @ P["co_attention.out_proj.weight"].T + P["co_attention.out_proj.bias"]
     assert np.max(np.abs(A - A2)) < 1e-12
     assert np.max(np.abs(out - out2)) < 1e-10
+
+
+def test_folded_bag_stage_backward_finite_difference():
+    """oracle.folded_bag_stage_bwd (the checker of the large-shape GPU tests) against central differences of
+    sum(pooled * dpooled) in fp64."""
+    rng = np.random.default_rng(5)
+    n, din, d = 37, 24, 16
+    X = rng.standard_normal((n, din))
+    W = rng.standard_normal((d, din)) / np.sqrt(din)
+    b = rng.standard_normal(d) * 0.1
+    qk = rng.standard_normal((6, d)) * 0.7
+    dP = rng.standard_normal((6, d))
+    out = orc.folded_bag_stage_bwd(W, b, qk, X, dP)
+
+    def f(W_, b_, qk_):
+        return float((orc.folded_bag_stage(W_, b_, qk_, X)[3] * dP).sum())
+    eps = 1e-6
+    for name, arr, grad in (("W", W, out["dW"]), ("b", b, out["db"]), ("qk", qk, out["dqk"])):
+        for _ in range(6):
+            idx = tuple(int(rng.integers(0, s)) for s in arr.shape)
+            old = arr[idx]
+            arr[idx] = old + eps; fp = f(W, b, qk)
+            arr[idx] = old - eps; fm = f(W, b, qk)
+            arr[idx] = old
+            fd = (fp - fm) / (2 * eps)
+            assert abs(fd - grad[idx]) < 1e-6 * max(1.0, abs(fd)), (name, idx, fd, grad[idx])

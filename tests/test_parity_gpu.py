@@ -100,6 +100,37 @@ def test_forward_backward_matches_reference(name):
     assert worst < GRAD_TOL, details[:5]
 
 
+@pytest.mark.parametrize("name", golden_cases(unrounded=True))
+def test_unrounded_weights_delta(name):
+    """SURVEY H2 option (a), second half: the reference here ran on weights that are NOT bf16-representable, while the
+    CUDA path streams H.0.weight (and NaCAGaT's W_k) as bf16/fp16 copies.  Outputs stay inside the 1e-3 gate; the
+    rounding shows up in the gradients that pass through the rounded operands (SURVEY F7 measured 1.3e-2 L2-relative on
+    dW_H), so those are REPORTED and held to 5e-2; every other gradient keeps the 1e-2 gate."""
+    case = load_case(name)
+    net = build_model(case).eval()
+    wsi = torch.from_numpy(case["bag"]).cuda()
+    omics = [torch.from_numpy(o).cuda() for o in case["omics"]]
+    hazards, S, Y, att = net(wsi=wsi, omics=omics, inference=True) if case["model"] == "mcat" else net(wsi=wsi, omics=omics)
+    g = case["gold"]
+    A, Aref = att["coattn"].cpu().numpy().astype(np.float64), g["coattn"].astype(np.float64)
+    errs = dict(hazards=rel_err(hazards.detach().cpu(), g["hazards"]), S=rel_err(S.detach().cpu(), g["S"]),
+                coattn=float(np.max(np.abs(A - Aref) / (np.abs(Aref) + 1e-3 * Aref.max()))))
+    loss = _pkg("loss").NegativeLogLikelihoodSurvivalLoss()(
+        hazards, S, torch.tensor([[case["label"]]], device="cuda"), torch.tensor([case["censor"]], device="cuda"))
+    net.zero_grad()
+    loss.backward()
+    grads = {k: p.grad.detach().cpu().numpy() for k, p in net.named_parameters()}
+    _, details = digest_errors(case, grads)
+    rounded = ("H.0.", "co_attention.in_proj", "G.")        # behind the rounded operands
+    e_r = max(e for k, _, e in details if k.startswith(rounded))
+    e_o = max(e for k, _, e in details if not k.startswith(rounded))
+    print(name, "UNROUNDED-WEIGHT DELTA:", {k: "%.2e" % v for k, v in errs.items()},
+          "grads behind rounded operands %.2e, others %.2e" % (e_r, e_o))
+    assert errs["hazards"] < OUT_TOL and errs["S"] < OUT_TOL
+    assert errs["coattn"] < 5e-3          # SURVEY F7: 3e-4..8e-4 at 16k for MCAT; sharper gates move it further
+    assert e_o < GRAD_TOL and e_r < 5e-2
+
+
 def test_mcat_non_inference_returns_no_map_and_same_hazards():
     case = load_case("mcat_concat_300")
     net = build_model(case).eval()
