@@ -88,12 +88,15 @@ int mpo_cast_f16(const float* src, void* dst_f16, int64_t n, void* stream);
  *   pgate     fp32 [6][total_rows] and t_saved fp16 [total_rows][256] (tanh(k)): kept for mpo_bag_bwd_nacagat, or both NULL
  *   part_ml   fp32 [num_tiles][18], part_pool fp32 [num_tiles][6][256]   workspaces
  *   pooled    fp32 [B][6][256] sum_n a'_in h_n ; lse fp32 [B][6] of s' ; suma fp32 [B][6] sum_n a'_in (1 without dropout)
+ *   part_pool_lo fp32 [num_tiles][6][256] workspace and pooled_lo fp32 [B][6][256], or both NULL (inference): the part of
+ *             `pooled` contributed by the fp16 remainders h_lo -- the gated softmax is often sharp, so pooled is formed
+ *             from the ~22-bit pair (h_saved, h_lo); mpo_bag_bwd_nacagat works on h_saved alone and needs the split
  *   attn_drop_p  dropout on the attention weights in train mode (blocks.py:52,189-190: 0.25), 0 in eval; the mask
  *             stream is (seed ^ *seed_dev) as in mpo_bag_fwd, site 1 */
 int mpo_bag_gate_fwd(const mpo_bag* bag, const void* h_saved, const void* h_lo, const void* w_k_f16, const float* bias_k, const float* qp,
                      const float* kc, float* scores, float* scores_g, float* pgate, void* t_saved, float* part_ml,
-                     float* part_pool, float* pooled, float* lse, float* suma, uint32_t seed, const uint32_t* seed_dev,
-                     float attn_drop_p, void* stream);
+                     float* part_pool, float* pooled, float* lse, float* suma, float* part_pool_lo, float* pooled_lo,
+                     uint32_t seed, const uint32_t* seed_dev, float attn_drop_p, void* stream);
 /* NaCAGaT attention map: dropout(softmax(s')) -- the reference returns the post-dropout weights (blocks.py:189-199) */
 int mpo_attn_map_dropout(const mpo_bag* bag, const float* scores_g, const float* lse, float* amap, uint32_t seed,
                          const uint32_t* seed_dev, float attn_drop_p, void* stream);
@@ -109,10 +112,35 @@ int mpo_attn_map(const mpo_bag* bag, const float* scores, const float* lse, floa
  *   dz_ws     bf16 [total_rows][256]     workspace (gradient at the pre-activation, feeds the dW_H GEMM)
  *   part_dqk  fp32 [num_tiles][6][256], part_db fp32 [num_tiles][256]  workspaces
  *   dqk       fp32 [num_slides][6][256]  gradient of the folded queries (overwritten)
- *   grad_w_h  fp32 [256][1024], grad_b_h fp32 [256]   accumulated */
+ *   grad_w_h  fp32 [256][1024], grad_b_h fp32 [256]   accumulated
+ *   d_amap    fp32 [6][total_rows] or NULL: a gradient arriving on the returned co-attention map (attention_scores['coattn']
+ *             fed to a loss, e.g. models/loss.py:88-101) and amap_dot fp32 [num_slides][6] = sum_n A_in d_amap_in
+ *             (mpo_attn_map_dot); both or neither */
 int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, const float* lse, const float* pooled,
                 const float* dpooled, const float* qk, void* dz_ws, float* part_dqk, float* part_db, float* dqk,
-                float* grad_w_h, float* grad_b_h, float drop_p, void* stream);
+                float* grad_w_h, float* grad_b_h, const float* d_amap, const float* amap_dot, float drop_p, void* stream);
+
+/* dot[b][i] = sum over the patches n of slide b of amap[i][n] * other[i][n]   (both fp32 [6][total_rows]; dot is
+ * overwritten).  other = d_amap gives the softmax-Jacobian term of a map gradient; other = amap gives the squared
+ * Frobenius norm per query that the attention-norm regulariser needs. */
+int mpo_attn_map_dot(const mpo_bag* bag, const float* amap, const float* other, float* dot, void* stream);
+
+/* Attention-norm regulariser of CrossEntropySurvivalAttnRegLoss (models/loss.py:88-101): for every slide b
+ *   reg[b] = lambda_reg * ||A_b||_2 (Frobenius norm of the slide's [6, N_b] map) and
+ *   d_amap[i][n] = grad_scale * lambda_reg * A_in / ||A_b||_2        (overwritten; feeds mpo_bag_bwd*)
+ * sumsq fp32 [num_slides][6] = mpo_attn_map_dot(amap, amap). */
+int mpo_cesar_reg(const mpo_bag* bag, const float* amap, const float* sumsq, float lambda_reg, float grad_scale,
+                  float* reg, float* d_amap, void* stream);
+
+/* SurvivalClassificationTobitLoss (models/loss.py:62-85) on the soft-maxed class probabilities Y [B][n_classes]:
+ * uncensored: -log(Y[label] + eps); censored: -log(sum_{j >= label} Y[j] + eps).  dY is scaled by grad_scale. */
+int mpo_sct_loss(const float* Y, const int64_t* label, const float* censor, float eps, float grad_scale, float* loss,
+                 float* dY, int32_t B, int32_t n_classes, void* stream);
+
+/* l1_reg (models/utils.py:33-40) over a flat fp32 buffer: *sum_out += sum |p| (the caller zeroes it); and its autograd:
+ * grad[i] += scale * sign(p[i]). */
+int mpo_l1_sum(const float* p, int64_t n, float* sum_out, void* stream);
+int mpo_l1_grad(const float* p, float* grad, int64_t n, float scale, void* stream);
 
 /* NaCAGaT bag-pass backward (autograd of nacagat.py:83,93 / blocks.py:156-192 w.r.t. H.0.*, the key projection and the
  * query-side operands).  All pointers are device pointers; workspaces are caller-owned. */
@@ -125,9 +153,12 @@ typedef struct mpo_nacagat_bwd {
   const float* lse;           /* fp32 [B][6]             of s' = s P                        */
   const float* pooled;        /* fp32 [B][6][256]                                           */
   const float* suma;          /* fp32 [B][6] or NULL (no attention dropout)                 */
+  const float* pooled_lo;     /* fp32 [B][6][256] or NULL: remainder part of pooled (mpo_bag_gate_fwd) */
   /* upstream gradients (mpo_tail_post_bwd) */
   const float* dpooled;       /* fp32 [B][6][256]                                           */
   const float* dsuma;         /* fp32 [B][6] or NULL, together with suma                    */
+  const float* d_amap;        /* fp32 [6][total_rows] or NULL: gradient on the returned (post-dropout) map */
+  const float* amap_dot;      /* fp32 [B][6] = mpo_attn_map_dot(map, d_amap), together with d_amap */
   /* query-side operands (mpo_tail_pre_fwd) and the fp16 key projection */
   const float* qk;            /* fp32 [B][6][256]                                           */
   const float* qp;            /* fp32 [B][6][256]                                           */
@@ -210,6 +241,7 @@ typedef struct mpo_bilinear {           /* BilinearFusion(256,256, hidden 32, mm
 #define MPO_VARIANT_NACAGAT 1
 #define MPO_FUSION_CONCAT 0
 #define MPO_FUSION_BILINEAR 1
+#define MPO_FUSION_GATED_CONCAT 2
 #define MPO_LOSS_NLL 0
 #define MPO_LOSS_CES 1
 
@@ -225,7 +257,10 @@ typedef struct mpo_model {
   mpo_cag cag;                          /* NaCAGaT only */
   mpo_encoder_layer path_tr[2], omic_tr[2];
   mpo_pool_head path_pool, omic_pool;
-  mpo_lin fusion0, fusion2;             /* ConcatFusion [256,512], [256,256] (fusion.py:7-19) */
+  mpo_lin fusion0, fusion2;             /* ConcatFusion / GatedConcatFusion MLP [256,512], [256,256] (fusion.py:7-19, 28-33) */
+  mpo_lin gate[2];                      /* fusion == gated_concat: Linear(256,1) + Sigmoid per input (fusion.py:25-27,36-39).
+                                         * The reference keeps these in a plain Python list: not in the state_dict, never
+                                         * trained; gw / gb may be NULL (their gradients are then not formed) */
   mpo_bilinear bil;                     /* fusion == bilinear */
   mpo_lin classifier;                   /* [n_classes,256] */
 } mpo_model;

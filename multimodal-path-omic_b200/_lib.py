@@ -62,7 +62,7 @@ class MpoModel(ctypes.Structure):
         ("H", MpoLin), ("snn", (MpoLin * 2) * 6), ("coattn_in", MpoLin), ("coattn_out", MpoLin), ("cag", MpoCag),
         ("path_tr", MpoEncoderLayer * 2), ("omic_tr", MpoEncoderLayer * 2),
         ("path_pool", MpoPoolHead), ("omic_pool", MpoPoolHead),
-        ("fusion0", MpoLin), ("fusion2", MpoLin), ("bil", MpoBilinear), ("classifier", MpoLin),
+        ("fusion0", MpoLin), ("fusion2", MpoLin), ("gate", MpoLin * 2), ("bil", MpoBilinear), ("classifier", MpoLin),
     ]
 
 
@@ -87,7 +87,8 @@ class MpoGeModel(ctypes.Structure):
 class MpoNacagatBwd(ctypes.Structure):
     """struct mpo_nacagat_bwd (include/mpo_b200.h)."""
     _fields_ = [(n, c_void_p) for n in (
-        "h_saved", "t_saved", "scores", "pgate", "lse", "pooled", "suma", "dpooled", "dsuma", "qk", "qp", "w_k_f16",
+        "h_saved", "t_saved", "scores", "pgate", "lse", "pooled", "suma", "pooled_lo", "dpooled", "dsuma", "d_amap", "amap_dot",
+        "qk", "qp", "w_k_f16",
         "dz_ws", "dkg_ws", "dg_ws", "part_dqk", "part_dtq", "part_db", "part_dbk", "part_dkc", "dg_max",
         "dqk", "dkc", "dtq", "grad_w_h", "grad_b_h", "grad_w_k", "grad_b_k")] + [
         ("drop_p", c_float), ("attn_drop_p", c_float), ("seed", c_u32), ("seed_dev", c_void_p)]
@@ -122,12 +123,17 @@ SIGNATURES = {
     "mpo_bag_fwd": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                     c_void_p, c_void_p, c_void_p, c_u32, c_void_p, c_float, c_void_p],
     "mpo_cast_f16": [c_void_p, c_void_p, c_i64, c_void_p],
-    "mpo_bag_gate_fwd": [ctypes.POINTER(MpoBag)] + [c_void_p] * 15 + [c_u32, c_void_p, c_float, c_void_p],
+    "mpo_bag_gate_fwd": [ctypes.POINTER(MpoBag)] + [c_void_p] * 17 + [c_u32, c_void_p, c_float, c_void_p],
     "mpo_attn_map_dropout": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_u32, c_void_p, c_float, c_void_p],
     "mpo_advance_seed": [c_void_p, c_void_p],
     "mpo_attn_map": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p],
     "mpo_bag_bwd": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p],
+                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p],
+    "mpo_attn_map_dot": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p],
+    "mpo_cesar_reg": [ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p],
+    "mpo_sct_loss": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_i32, c_i32, c_void_p],
+    "mpo_l1_sum": [c_void_p, c_i64, c_void_p, c_void_p],
+    "mpo_l1_grad": [c_void_p, c_void_p, c_i64, c_float, c_void_p],
     "mpo_bag_bwd_nacagat": [ctypes.POINTER(MpoBag), ctypes.POINTER(MpoNacagatBwd), c_void_p],
     "mpo_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float,
                       c_void_p, c_i32, c_void_p],

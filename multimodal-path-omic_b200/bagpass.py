@@ -125,7 +125,7 @@ class BagWorkspace:
         f32 = dict(dtype=torch.float32, device=dev)
         self.scores = torch.empty((Q, R), **f32)
         self.nacagat = nacagat
-        self.scores_g = self.pgate = self.t_saved = self.suma = self.h_lo = None
+        self.scores_g = self.pgate = self.t_saved = self.suma = self.h_lo = self.part_pool_lo = self.pooled_lo = None
         if nacagat:
             self.h_lo = torch.empty((R, D), dtype=torch.float16, device=dev)        # gate pass (mpo_bag_gate_fwd): gated scores always; P and tanh(k) only for a backward pass
             self.scores_g = torch.empty((Q, R), **f32)
@@ -133,6 +133,8 @@ class BagWorkspace:
             if save_gate:
                 self.pgate = torch.empty((Q, R), **f32)
                 self.t_saved = torch.empty((R, D), dtype=torch.float16, device=dev)
+                self.part_pool_lo = torch.empty((T, Q, D), **f32)     # remainder part of pooled, for the backward's delta
+                self.pooled_lo = torch.empty((B, Q, D), **f32)
         self.part_ml = torch.empty((T, 18 if nacagat else 12), **f32)
         self.part_pool = torch.empty((T, Q, D), **f32)
         self.pooled = torch.empty((B, Q, D), **f32)
@@ -196,11 +198,19 @@ def bag_gate_forward(bag, w_k_f16, bias_k, qp, kc, ws, seed=0, attn_drop_p=0.0, 
     """mpo_bag_gate_fwd: fills ws.scores_g / ws.pooled / ws.lse / ws.suma (and ws.pgate, ws.t_saved when allocated)."""
     _lib.call("mpo_bag_gate_fwd", bag.c(), _ptr(ws.h_saved), _ptr(ws.h_lo), _ptr(w_k_f16), _ptr(bias_k), _ptr(qp), _ptr(kc),
               _ptr(ws.scores), _ptr(ws.scores_g), _ptr(ws.pgate), _ptr(ws.t_saved), _ptr(ws.part_ml), _ptr(ws.part_pool),
-              _ptr(ws.pooled), _ptr(ws.lse), _ptr(ws.suma), ctypes.c_uint32(seed & 0xFFFFFFFF), _ptr(seed_dev),
+              _ptr(ws.pooled), _ptr(ws.lse), _ptr(ws.suma), _ptr(ws.part_pool_lo), _ptr(ws.pooled_lo),
+              ctypes.c_uint32(seed & 0xFFFFFFFF), _ptr(seed_dev),
               ctypes.c_float(attn_drop_p), _stream())
 
 
-def bag_backward(bag, ws, dpooled, qk, grad_w_h, grad_b_h, drop_p=0.0):
+def attention_map_dot(bag, amap, other):
+    """mpo_attn_map_dot: [B, 6] per-slide, per-query sums of amap * other over the patches."""
+    out = torch.empty((bag.num_slides, Q), dtype=torch.float32, device=bag.x.device)
+    _lib.call("mpo_attn_map_dot", bag.c(), _ptr(amap), _ptr(other), _ptr(out), _stream())
+    return out
+
+
+def bag_backward(bag, ws, dpooled, qk, grad_w_h, grad_b_h, drop_p=0.0, d_amap=None, amap_dot=None):
     """mpo_bag_bwd: accumulates into grad_w_h [256,1024] / grad_b_h [256], returns dqk [B,6,256]."""
     if ws.h_saved is None:
         raise RuntimeError("bag_backward needs the activations saved by bag_forward (save_h=True)")
@@ -208,7 +218,7 @@ def bag_backward(bag, ws, dpooled, qk, grad_w_h, grad_b_h, drop_p=0.0):
     dqk = torch.empty((bag.num_slides, Q, D), dtype=torch.float32, device=bag.x.device)
     _lib.call("mpo_bag_bwd", bag.c(), _ptr(ws.h_saved), _ptr(ws.scores), _ptr(ws.lse), _ptr(ws.pooled),
               _ptr(dpooled), _ptr(qk), _ptr(ws.dz), _ptr(ws.part_dqk), _ptr(ws.part_db), _ptr(dqk),
-              _ptr(grad_w_h), _ptr(grad_b_h), ctypes.c_float(drop_p), _stream())
+              _ptr(grad_w_h), _ptr(grad_b_h), _ptr(d_amap), _ptr(amap_dot), ctypes.c_float(drop_p), _stream())
     return dqk
 
 

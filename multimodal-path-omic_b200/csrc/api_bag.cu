@@ -262,8 +262,8 @@ static void drop_params(float drop_p, uint32_t* thr, float* scale) {
 
 int mpo_bag_gate_fwd(const mpo_bag* bag, const void* h_saved, const void* h_lo, const void* w_k_f16, const float* bias_k, const float* qp,
                      const float* kc, float* scores, float* scores_g, float* pgate, void* t_saved, float* part_ml,
-                     float* part_pool, float* pooled, float* lse, float* suma, uint32_t seed, const uint32_t* seed_dev,
-                     float attn_drop_p, void* stream) {
+                     float* part_pool, float* pooled, float* lse, float* suma, float* part_pool_lo, float* pooled_lo,
+                     uint32_t seed, const uint32_t* seed_dev, float attn_drop_p, void* stream) {
   int rc = check_bag(bag, "mpo_bag_gate_fwd");
   if (rc) return rc;
   if (bag->total_rows == 0 || bag->num_tiles == 0) return MPO_OK;
@@ -272,6 +272,8 @@ int mpo_bag_gate_fwd(const mpo_bag* bag, const void* h_saved, const void* h_lo, 
     return fail(MPO_E_ARG, "%s", "mpo_bag_gate_fwd: null pointer");
   if ((pgate == nullptr) != (t_saved == nullptr))
     return fail(MPO_E_ARG, "%s", "mpo_bag_gate_fwd: pgate and t_saved are kept (or dropped) together");
+  if ((part_pool_lo == nullptr) != (pooled_lo == nullptr))
+    return fail(MPO_E_ARG, "%s", "mpo_bag_gate_fwd: part_pool_lo and pooled_lo are kept (or dropped) together");
   if (attn_drop_p < 0.f || attn_drop_p >= 1.f) return fail(MPO_E_ARG, "%s", "mpo_bag_gate_fwd: drop_p must be in [0,1)");
   CUtensorMap tm_h, tm_hlo, tm_w;
   rc = make_tmap_16b_2d(&tm_h, h_saved, static_cast<uint64_t>(bag->total_rows), kD, 64, kTileM, true);
@@ -287,13 +289,14 @@ int mpo_bag_gate_fwd(const mpo_bag* bag, const void* h_saved, const void* h_lo, 
   p.qp = qp; p.kc = kc; p.bias_k = bias_k;
   p.scores = scores; p.scores_g = scores_g; p.pgate = pgate;
   p.t_out = static_cast<__half*>(t_saved);
-  p.part_ml = part_ml; p.part_pool = part_pool;
+  p.part_ml = part_ml; p.part_pool = part_pool; p.part_pool_lo = part_pool_lo;
   p.seed = seed; p.seed_dev = seed_dev;
   drop_params(attn_drop_p, &p.drop_thr, &p.drop_scale);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   rc = check_cuda(launch_bag_gate(tm_h, tm_hlo, tm_w, p, num_sms(), st), "bag_gate_kernel");
   if (rc) return rc;
-  return check_cuda(launch_bag_merge(bag->tile_prefix, part_ml, 18, part_pool, pooled, lse, suma, bag->num_slides, st),
+  return check_cuda(launch_bag_merge(bag->tile_prefix, part_ml, 18, part_pool, pooled, lse, suma, bag->num_slides, st,
+                                     part_pool_lo, pooled_lo),
                     "bag_merge_kernel");
 }
 
@@ -314,15 +317,19 @@ int mpo_attn_map_dropout(const mpo_bag* bag, const float* scores_g, const float*
 
 int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, const float* lse, const float* pooled,
                 const float* dpooled, const float* qk, void* dz_ws, float* part_dqk, float* part_db, float* dqk,
-                float* grad_w_h, float* grad_b_h, float drop_p, void* stream) {
+                float* grad_w_h, float* grad_b_h, const float* d_amap, const float* amap_dot, float drop_p, void* stream) {
   int rc = check_bag(bag, "mpo_bag_bwd");
   if (rc) return rc;
   if (bag->total_rows == 0 || bag->num_tiles == 0) return MPO_OK;
   if (!h_saved || !scores || !lse || !pooled || !dpooled || !qk || !dz_ws || !part_dqk || !part_db || !dqk ||
       !grad_w_h || !grad_b_h)
     return fail(MPO_E_ARG, "%s", "mpo_bag_bwd: null pointer");
+  if ((d_amap == nullptr) != (amap_dot == nullptr))
+    return fail(MPO_E_ARG, "%s", "mpo_bag_bwd: d_amap and amap_dot go together");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BagBwdDzParams p = {};
+  p.d_amap = d_amap;
+  p.amap_dot = amap_dot;
   p.tile_info = reinterpret_cast<const TileInfo*>(bag->tile_info);
   p.num_tiles = bag->num_tiles;
   p.total_rows = static_cast<int>(bag->total_rows);
@@ -369,6 +376,8 @@ int mpo_bag_bwd_nacagat(const mpo_bag* bag, const mpo_nacagat_bwd* a, void* stre
     return fail(MPO_E_ARG, "%s", "mpo_bag_bwd_nacagat: null pointer");
   if ((a->suma == nullptr) != (a->dsuma == nullptr))
     return fail(MPO_E_ARG, "%s", "mpo_bag_bwd_nacagat: suma and dsuma go together");
+  if ((a->d_amap == nullptr) != (a->amap_dot == nullptr))
+    return fail(MPO_E_ARG, "%s", "mpo_bag_bwd_nacagat: d_amap and amap_dot go together");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint64_t R = static_cast<uint64_t>(bag->total_rows);
   const int ns = num_sms();
@@ -385,9 +394,10 @@ int mpo_bag_bwd_nacagat(const mpo_bag* bag, const mpo_nacagat_bwd* a, void* stre
   p.tile_info = reinterpret_cast<const TileInfo*>(bag->tile_info);
   p.num_tiles = bag->num_tiles;
   p.total_rows = static_cast<int>(bag->total_rows);
-  p.scores = a->scores; p.lse = a->lse; p.pooled = a->pooled; p.dpooled = a->dpooled; p.qk = a->qk;
+  p.scores = a->scores; p.lse = a->lse; p.pooled = a->pooled; p.pooled_lo = a->pooled_lo; p.dpooled = a->dpooled; p.qk = a->qk;
   p.pgate = a->pgate; p.suma = a->suma; p.dsuma = a->dsuma; p.qp = a->qp;
   p.dg = a->dg_ws; p.dg_max = a->dg_max; p.part_dkc = a->part_dkc;
+  p.d_amap = a->d_amap; p.amap_dot = a->amap_dot;
   p.seed = a->seed; p.seed_dev = a->seed_dev;
   drop_params(a->attn_drop_p, &p.attn_thr, &p.attn_scale);
   { uint32_t thr; drop_params(a->drop_p, &thr, &p.keep_scale); }

@@ -295,7 +295,8 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           for (int i = 0; i < kQ; ++i) {
             dp[i] = p.dpooled[sb + i * kD + et];
             qv[i] = p.qk[sb + i * kD + et];
-            red[i] = dp[i] * p.pooled[sb + i * kD + et];     // delta_i partial
+            // delta_i partial; consistent with g = dP . fp16(h): the hi-only pooled vector when a remainder part exists
+            red[i] = dp[i] * (p.pooled[sb + i * kD + et] - (p.pooled_lo != nullptr ? p.pooled_lo[sb + i * kD + et] : 0.f));
             red[6 + i] = fabsf(dp[i]);                       // max |dP_i|
           }
 #pragma unroll
@@ -326,6 +327,7 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
                 dsum = p.dsuma[ti.slide * kQ + i];
                 s += dsum * p.suma[ti.slide * kQ + i];
               }
+              if (p.d_amap != nullptr) s += p.amap_dot[ti.slide * kQ + i];   // softmax Jacobian of the map gradient
               scal[i] = s; scal[8 + i] = p.lse[ti.slide * kQ + i]; scal[16 + i] = inv; scal[160 + i] = dsum;
             }
           }
@@ -365,11 +367,12 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
             ds[i] = dg * gs;
           }
         } else {
-          float sc[kQ], pg[kQ];
+          float sc[kQ], pg[kQ], dmap[kQ];
 #pragma unroll
           for (int i = 0; i < kQ; ++i) {
             sc[i] = valid ? __ldg(p.scores + static_cast<size_t>(i) * p.total_rows + grow) : 0.f;
             pg[i] = (MODE == kDzNacDh && valid) ? __ldg(p.pgate + static_cast<size_t>(i) * p.total_rows + grow) : 1.f;
+            dmap[i] = (p.d_amap != nullptr && valid) ? __ldg(p.d_amap + static_cast<size_t>(i) * p.total_rows + grow) : 0.f;
           }
           mbar_wait(g_bar, tph);
           tc_fence_after();
@@ -378,7 +381,7 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < kQ; ++i) {
-            const float g = (__uint_as_float(gv[i]) + __uint_as_float(gv[i + 6])) * scal[16 + i];
+            const float g = (__uint_as_float(gv[i]) + __uint_as_float(gv[i + 6])) * scal[16 + i] + dmap[i];
             if (MODE == kDzMcat) {
               const float a = valid ? __expf(sc[i] - scal[8 + i]) : 0.f;
               ds[i] = a * (g - scal[i]);

@@ -513,7 +513,8 @@ __global__ void __launch_bounds__(256)
 bag_merge_kernel(const int* __restrict__ tile_prefix,   // [B+1] first tile of each slide
                  const float* __restrict__ part_ml, const int mls,   // per-tile stats, mls floats per tile (12 or 18)
                  const float* __restrict__ part_pool, float* __restrict__ pooled, float* __restrict__ lse,
-                 float* __restrict__ suma) {   // suma (NaCAGaT, mls = 18): sum_n of the dropped-and-rescaled weights
+                 float* __restrict__ suma,     // suma (NaCAGaT, mls = 18): sum_n of the dropped-and-rescaled weights
+                 const float* __restrict__ part_pool2, float* __restrict__ pooled2) {   // optional second partial set
   // one block per (slide, query, quarter of the feature columns); 16 tile groups x 16 float4 columns: a 128-tile slide
   // is 8 independent loads per thread, all in flight at once
   __shared__ float red[8];
@@ -541,22 +542,27 @@ bag_merge_kernel(const int* __restrict__ tile_prefix,   // [B+1] first tile of e
 #pragma unroll
   for (int w = 0; w < 8; ++w) L += red[w];
   const int tg = tid >> 4, dl = tid & 15, dq = dl + 16 * static_cast<int>(blockIdx.z);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int set = 0; set < (part_pool2 != nullptr ? 2 : 1); ++set) {      // block-uniform
+    const float* pp = set == 0 ? part_pool : part_pool2;
+    float* out = set == 0 ? pooled : pooled2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
-  for (int t = t0 + tg; t < t1; t += 16) {
-    const float w = __expf(__ldg(part_ml + static_cast<size_t>(t) * mls + i) - M);
-    const float4 v = __ldg(reinterpret_cast<const float4*>(part_pool + (static_cast<size_t>(t) * kQ + i) * kD) + dq);
-    acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
-  }
-  acc_s[tg][dl] = acc;
-  __syncthreads();
-  if (tid < 16) {
-    const float inv = 1.f / L;
-    float4 r = acc_s[0][tid];
+    for (int t = t0 + tg; t < t1; t += 16) {
+      const float w = __expf(__ldg(part_ml + static_cast<size_t>(t) * mls + i) - M);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(pp + (static_cast<size_t>(t) * kQ + i) * kD) + dq);
+      acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+    }
+    if (set) __syncthreads();
+    acc_s[tg][dl] = acc;
+    __syncthreads();
+    if (tid < 16) {
+      const float inv = 1.f / L;
+      float4 r = acc_s[0][tid];
 #pragma unroll
-    for (int g = 1; g < 16; ++g) { r.x += acc_s[g][tid].x; r.y += acc_s[g][tid].y; r.z += acc_s[g][tid].z; r.w += acc_s[g][tid].w; }
-    r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
-    reinterpret_cast<float4*>(pooled + (static_cast<size_t>(b) * kQ + i) * kD)[dq] = r;
+      for (int g = 1; g < 16; ++g) { r.x += acc_s[g][tid].x; r.y += acc_s[g][tid].y; r.z += acc_s[g][tid].z; r.w += acc_s[g][tid].w; }
+      r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
+      reinterpret_cast<float4*>(out + (static_cast<size_t>(b) * kQ + i) * kD)[dq] = r;
+    }
   }
   if (tid == 0 && blockIdx.z == 0) lse[b * kQ + i] = M + __logf(L);
   if (suma != nullptr && blockIdx.z == 0) {       // block-uniform
@@ -640,9 +646,11 @@ cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, con
 }
 
 cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, int ml_stride, const float* part_pool,
-                             float* pooled, float* lse, float* suma, int B, cudaStream_t stream) {
+                             float* pooled, float* lse, float* suma, int B, cudaStream_t stream,
+                             const float* part_pool2, float* pooled2) {
   if (B <= 0) return cudaSuccess;
-  bag_merge_kernel<<<dim3(B, kQ, 4), 256, 0, stream>>>(tile_prefix, part_ml, ml_stride, part_pool, pooled, lse, suma);
+  bag_merge_kernel<<<dim3(B, kQ, 4), 256, 0, stream>>>(tile_prefix, part_ml, ml_stride, part_pool, pooled, lse, suma,
+                                                       part_pool2, pooled2);
   count_launch();
   return cudaGetLastError();
 }

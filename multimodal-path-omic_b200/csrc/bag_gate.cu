@@ -88,7 +88,7 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t kColK = 0, kColP = 256;
+  constexpr uint32_t kColK = 0, kColP = 256, kColPlo = 288;
 
   if (warp == 0) {
     if (lane == 0 && t_begin < t_end) {
@@ -146,6 +146,20 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             umma_bf16(tmem_base + kColP + mh * 16, umma_desc_sw128(aA + mh * 2 * 16384 + kk * 2048, 16384, 1024),
+                      umma_desc_sw128(aP + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), id_p, kk != 0 ? 1u : 0u);
+        // + p^T H_lo: NaCAGaT's gated softmax is often sharp (one patch can carry > 0.9 of a query's weight), so the fp16
+        // rounding of that patch's activations (2^-11) does not average out of the pooled vector; measured on the GPU it
+        // flipped ReLU units of the slide tail against the reference (8-13 % gradient error on 2 of 13 slides).  The
+        // remainder tile is already staged for the key projection: 16 more N = 16 MMAs make pooled ~22-bit exact.
+        // The remainder part goes to its own accumulator columns and (when the backward pass follows) to its own
+        // partial buffer: the backward forms g = dP . fp16(h) from the saved hi tile alone, so its softmax-gradient
+        // offset delta = dP . pooled must use the hi-only pooled vector as well, or a (g - delta) cancels to the wrong
+        // value on a sharp softmax (measured: 2 % on the query gradients of the sharp fixture).
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16(tmem_base + kColPlo + mh * 16, umma_desc_sw128(aL + mh * 2 * 16384 + kk * 2048, 16384, 1024),
                       umma_desc_sw128(aP + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), id_p, kk != 0 ? 1u : 0u);
         umma_commit(d_bar);
         umma_commit(a_empty);
@@ -284,12 +298,17 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       mbar_wait(d_bar, ph);
       tc_fence_after();
       {
-        uint32_t dv[16];
+        uint32_t dv[16], dl[16];
         tmem_ld_32x32b_x16(tmem_base + kColP + ch * 16 + (static_cast<uint32_t>(qd * 32) << 16), dv);
+        tmem_ld_32x32b_x16(tmem_base + kColPlo + ch * 16 + (static_cast<uint32_t>(qd * 32) << 16), dl);
         tmem_ld_wait();
-        float* dst = p.part_pool + static_cast<size_t>(t) * (kQ * kD) + ch * 128 + qd * 32 + lane;
+        const size_t po = static_cast<size_t>(t) * (kQ * kD) + ch * 128 + qd * 32 + lane;
 #pragma unroll
-        for (int i = 0; i < kQ; ++i) dst[i * kD] = __uint_as_float(dv[i]) + __uint_as_float(dv[i + 6]);
+        for (int i = 0; i < kQ; ++i) {
+          const float lo = __uint_as_float(dl[i]) + __uint_as_float(dl[i + 6]);
+          p.part_pool[po + i * kD] = __uint_as_float(dv[i]) + __uint_as_float(dv[i + 6]) + lo;
+          if (p.part_pool_lo != nullptr) p.part_pool_lo[po + i * kD] = lo;
+        }
       }
       tc_fence_before();
     }

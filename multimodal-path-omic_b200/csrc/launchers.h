@@ -18,7 +18,8 @@ int fwd_cluster_size();   // CTAs per cluster of the forward bag kernel (1, 2 or
 cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const CUtensorMap& tm_h,
                            const BagFwdParams& prm, int num_sms, cudaStream_t stream);
 cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, int ml_stride, const float* part_pool,
-                             float* pooled, float* lse, float* suma, int B, cudaStream_t stream);
+                             float* pooled, float* lse, float* suma, int B, cudaStream_t stream,
+                             const float* part_pool2 = nullptr, float* pooled2 = nullptr);
 cudaError_t launch_bag_gate(const CUtensorMap& tm_h, const CUtensorMap& tm_hlo, const CUtensorMap& tm_w,
                             const BagGateParams& prm, int num_sms, cudaStream_t stream);
 cudaError_t launch_bag_dhk(const CUtensorMap& tm_dkg, const CUtensorMap& tm_w, const CUtensorMap& tm_dz,

@@ -59,7 +59,8 @@ struct BagGateParams {
   float* pgate;                // [6][total_rows] out: P (kept for the backward pass) or null
   __half* t_out;               // [total_rows][256] out: tanh(k) fp16 (kept for the backward pass) or null
   float* part_ml;              // [num_tiles][18]  tile max, sum of exp, sum of dropped-and-rescaled exp
-  float* part_pool;            // [num_tiles][6][256]
+  float* part_pool;            // [num_tiles][6][256]  sum_n p_n (fp16(h_n) + remainder)
+  float* part_pool_lo;         // [num_tiles][6][256]  the remainder part alone (for the backward pass) or null
   uint32_t seed;
   const uint32_t* seed_dev;
   uint32_t drop_thr;           // attention dropout (blocks.py:189-190): drop when 8 random bits < drop_thr
@@ -85,6 +86,7 @@ struct BagBwdDzParams {
   const float* scores;         // [6][total_rows]  raw scores s (NaCAGaT: including the key-bias term)
   const float* lse;            // [B][6]           log-sum-exp of the softmax argument (s, or s P for NaCAGaT)
   const float* pooled;         // [B][6][256]
+  const float* pooled_lo;      // [B][6][256] or null: part of `pooled` that came from the fp16 remainders of h (NaCAGaT)
   const float* dpooled;        // [B][6][256]
   const float* qk;             // [B][6][256]
   void* out;                   // [total_rows][256] 16-bit output tile rows (dz bf16 / dkg fp16), for ragged tiles
@@ -99,6 +101,9 @@ struct BagBwdDzParams {
   float* dg;                   // [6][total_rows]  mode 1 writes, mode 2 reads the gate-dot gradients
   uint32_t* dg_max;            // bits of max |dg| over the batch (mode 1: atomicMax; mode 2: scale source)
   float* part_dkc;             // [num_tiles][8]   per-tile sums of ds_i (mode 1)
+  // optional gradient arriving on the returned attention map (e.g. the CESAR regulariser, models/loss.py:88-101)
+  const float* d_amap;         // [6][total_rows]  dL/dA (A = the map as returned: post-dropout for NaCAGaT) or null
+  const float* amap_dot;       // [B][6]           sum_n A_in dL/dA_in   (with d_amap)
   uint32_t seed;
   const uint32_t* seed_dev;
   uint32_t attn_thr;           // attention dropout threshold (0 = off) and rescale factor

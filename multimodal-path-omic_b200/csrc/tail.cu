@@ -393,7 +393,10 @@ int finish(Ctx& c) {
 int check_model(const mpo_model* m, const mpo_tail_io* io, const char* who) {
   if (!m || !io) return fail(MPO_E_ARG, "%s: NULL model/io", who);
   if (m->variant != MPO_VARIANT_MCAT && m->variant != MPO_VARIANT_NACAGAT) return fail(MPO_E_UNSUPPORTED, "%s: unknown variant", who);
-  if (m->fusion != MPO_FUSION_CONCAT && m->fusion != MPO_FUSION_BILINEAR) return fail(MPO_E_UNSUPPORTED, "%s: unsupported fusion", who);
+  if (m->fusion != MPO_FUSION_CONCAT && m->fusion != MPO_FUSION_BILINEAR && m->fusion != MPO_FUSION_GATED_CONCAT)
+    return fail(MPO_E_UNSUPPORTED, "%s: unsupported fusion", who);
+  if (m->fusion == MPO_FUSION_GATED_CONCAT && (!m->gate[0].w || !m->gate[0].b || !m->gate[1].w || !m->gate[1].b))
+    return fail(MPO_E_ARG, "%s: gated_concat needs the two gate layers", who);
   if (m->n_classes < 1 || m->n_classes > 16) return fail(MPO_E_ARG, "%s: n_classes out of range", who);
   if (io->num_slides <= 0) return fail(MPO_E_ARG, "%s: num_slides must be positive", who);
   if (!io->ws) return fail(MPO_E_ARG, "%s: workspace is NULL", who);
@@ -608,8 +611,15 @@ int mpo_tail_post_fwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   const float* hpath = ws + w.pool[0].h;
   const float* homic = ws + w.pool[1].h;
   const float* hfin;
-  if (m->fusion == MPO_FUSION_CONCAT) {            // fusion.py:17-19
-    lin_fwd(c, ws + w.cat, 2 * E, m->fusion0, E, 2 * E, ws + w.z1, E, B, ACT_RELU);
+  if (m->fusion != MPO_FUSION_BILINEAR) {          // fusion.py:17-19 (concat), :35-41 (gated concat)
+    const float* cat = ws + w.cat;
+    if (m->fusion == MPO_FUSION_GATED_CONCAT) {    // item_p * sigmoid(w_p . item_p + b_p) per input, then the same MLP
+      launch_k(gate_concat_fwd_kernel, dim3(B), dim3(256), 0, c.st, ws + w.cat, m->gate[0].w, m->gate[0].b, m->gate[1].w,
+               m->gate[1].b, ws + w.catg, ws + w.gateg); count_launch();
+      c.chk(cudaGetLastError(), "gate_concat_fwd");
+      cat = ws + w.catg;
+    }
+    lin_fwd(c, cat, 2 * E, m->fusion0, E, 2 * E, ws + w.z1, E, B, ACT_RELU);
     lin_fwd(c, ws + w.z1, E, m->fusion2, E, E, ws + w.z2, E, B, ACT_RELU);
     hfin = ws + w.z2;
   } else {                                          // fusion.py:81-113
@@ -660,7 +670,7 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
   const float* homic = ws + w.pool[1].h;
   // gradients of the two rho outputs: [B,256] blocks of `dcat` (bilinear), or the two column halves of the [B,512]
   // concat gradient (row stride 512)
-  const bool concat = m->fusion == MPO_FUSION_CONCAT;
+  const bool concat = m->fusion != MPO_FUSION_BILINEAR;
   float* dhpath = ws + w.dcat;
   float* dhomic = concat ? ws + w.dcat + E : ws + w.dcat + (long long)B * E;
   const long long lddh = concat ? 2 * E : E;
@@ -670,7 +680,13 @@ int mpo_tail_post_bwd(const mpo_model* m, const mpo_tail_io* io, const float* dh
     lin_bwd(c, ws + w.dlogits, K, ws + w.z2, E, m->classifier, K, E, ws + w.dz2, E, B, false, e2);
     DgradEpi e1; e1.y = ws + w.z1; e1.ld_y = E; e1.act = ACT_RELU;
     lin_bwd(c, ws + w.dz2, E, ws + w.z1, E, m->fusion2, E, E, ws + w.dz1, E, B, false, e1);
-    lin_bwd(c, ws + w.dz1, E, ws + w.cat, 2 * E, m->fusion0, E, 2 * E, ws + w.dcat, 2 * E, B, false);
+    const bool gated = m->fusion == MPO_FUSION_GATED_CONCAT;
+    lin_bwd(c, ws + w.dz1, E, ws + (gated ? w.catg : w.cat), 2 * E, m->fusion0, E, 2 * E, ws + w.dcat, 2 * E, B, false);
+    if (gated) {     // gradient at the gated items -> gradient at the rho outputs (in place), gate gradients when asked for
+      launch_k(gate_concat_bwd_kernel, dim3(B), dim3(256), 0, c.st, ws + w.cat, ws + w.gateg, m->gate[0].w, m->gate[1].w,
+               ws + w.dcat, m->gate[0].gw, m->gate[0].gb, m->gate[1].gw, m->gate[1].gb); count_launch();
+      c.chk(cudaGetLastError(), "gate_concat_bwd");
+    }
   } else {
     lin_bwd(c, ws + w.dlogits, K, ws + w.bf2, E, m->classifier, K, E, ws + w.dh, E, B, false);
     act_bwd(c, ws + w.dh, E, ws + w.bf2, E, ws + w.dz2, E, B, E, ACT_RELU, mk_drop(c, 0.25f, SITE_BIL + 4));

@@ -877,6 +877,45 @@ __global__ void surv_loss_kernel(int kind, const float* __restrict__ hazards, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// GatedConcatFusion gates (models/fusion.py:25-27, 35-40): item_p * sigmoid(w_p . item_p + b_p), p = path / omic.
+// One block per slide, 256 threads (one feature of both halves each); cat / catg / dcat are [B][512].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gate_concat_fwd_kernel(const float* __restrict__ cat, const float* __restrict__ w0, const float* __restrict__ b0,
+                       const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ catg,
+                       float* __restrict__ gateg) {
+  pdl_enter();
+  __shared__ float red[8];
+  const int b = blockIdx.x, f = threadIdx.x;
+  const float x0 = cat[b * 512 + f], x1 = cat[b * 512 + 256 + f];
+  const float g0 = 1.f / (1.f + __expf(-(block_sum_256(x0 * w0[f], red) + b0[0])));
+  const float g1 = 1.f / (1.f + __expf(-(block_sum_256(x1 * w1[f], red) + b1[0])));
+  catg[b * 512 + f] = x0 * g0;
+  catg[b * 512 + 256 + f] = x1 * g1;
+  if (f == 0) { gateg[b * 2] = g0; gateg[b * 2 + 1] = g1; }
+}
+// dcat: in = gradient at the gated items, out = gradient at the items (in place); gw / gb (may be null) accumulate the
+// gradients of the gate layers themselves
+__global__ void __launch_bounds__(256)
+gate_concat_bwd_kernel(const float* __restrict__ cat, const float* __restrict__ gateg, const float* __restrict__ w0,
+                       const float* __restrict__ w1, float* __restrict__ dcat, float* __restrict__ gw0,
+                       float* __restrict__ gb0, float* __restrict__ gw1, float* __restrict__ gb1) {
+  pdl_enter();
+  __shared__ float red[8];
+  const int b = blockIdx.x, f = threadIdx.x;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const float x = cat[b * 512 + p * 256 + f], d = dcat[b * 512 + p * 256 + f], g = gateg[b * 2 + p];
+    const float ds = block_sum_256(d * x, red) * g * (1.f - g);      // gradient at the gate's pre-activation
+    dcat[b * 512 + p * 256 + f] = d * g + ds * (p == 0 ? w0[f] : w1[f]);
+    float* gw = p == 0 ? gw0 : gw1;
+    float* gb = p == 0 ? gb0 : gb1;
+    if (gw != nullptr) atomicAdd(gw + f, ds * x);
+    if (gb != nullptr && f == 0) atomicAdd(gb, ds);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // bilinear-fusion helpers (models/fusion.py:81-113)
 // ------------------------------------------------------------------------------------------------
 // z[b][k] = sum_i x1[b][i] U[b][k*256+i] + bias[k];  g = sigmoid(z);  gh = g * h          (U = x2 W_z^T, by GEMM)

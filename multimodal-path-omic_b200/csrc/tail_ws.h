@@ -36,6 +36,7 @@ struct Ws {
   EncBuf enc[4];      // path.0, path.1, omic.0, omic.1
   PoolBuf pool[2];    // path, omic
   long long cat, z1, z2;                                   // concat fusion
+  long long catg = 0, gateg = 0;                            // gated concat: gated copy of `cat` [B][512], gate values [B][2]
   long long bh[2], bU[2], bg[2], bgh[2], bo[2], kp, cat130, bf2;   // bilinear fusion
   long long logits;
   // gradients / scratch
@@ -78,16 +79,19 @@ inline void build_layout(const mpo_model* m, int B, Ws& w) {
   }
   const char* pn[2] = {"pathpool", "omicpool"};
   // concat fusion reads [h_path | h_omic] as one [B, 512] row block: the two rho outputs are written straight into it
-  if (m->fusion == MPO_FUSION_CONCAT) w.cat = L.add("cat", (long long)B * 2 * E);
+  if (m->fusion != MPO_FUSION_BILINEAR) w.cat = L.add("cat", (long long)B * 2 * E);
   for (int p = 0; p < 2; ++p) {
     PoolBuf& b = w.pool[p];
     auto A = [&](const char* s, long long n) { snprintf(nm, sizeof nm, "%s_%s", pn[p], s); return L.add(nm, n); };
     b.a = A("a", R * E); b.b = A("b", R * E); b.w = A("w", (long long)B * 6); b.hp = A("hp", (long long)B * E);
-    if (m->fusion == MPO_FUSION_CONCAT) { b.h = w.cat + p * E; b.hld = 2 * E; }
+    if (m->fusion != MPO_FUSION_BILINEAR) { b.h = w.cat + p * E; b.hld = 2 * E; }
     else { b.h = A("h", (long long)B * E); b.hld = E; }
   }
-  if (m->fusion == MPO_FUSION_CONCAT) {
+  if (m->fusion != MPO_FUSION_BILINEAR) {
     w.z1 = L.add("z1", (long long)B * E); w.z2 = L.add("z2", (long long)B * E);
+    if (m->fusion == MPO_FUSION_GATED_CONCAT) {
+      w.catg = L.add("catg", (long long)B * 2 * E); w.gateg = L.add("gateg", (long long)B * 2);
+    }
   } else {
     for (int s = 0; s < 2; ++s) {
       auto A = [&](const char* t, long long n) { snprintf(nm, sizeof nm, "bil%d_%s", s + 1, t); return L.add(nm, n); };

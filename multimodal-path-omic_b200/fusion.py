@@ -23,8 +23,8 @@ class ConcatFusion(nn.Module):
 class GatedConcatFusion(nn.Module):
     """reference: models/fusion.py:22-41.  Its per-input gates live in a plain Python list there, so they are not
     parameters, never trained and never moved to the device; the state_dict only has fusion_layer.{0,2}.*.
-    The gates are kept here the same way for construction parity; the B200 engine does not implement this
-    variant yet and says so when asked to run it."""
+    The gates are kept here the same way; the slide tail applies them from device copies (csrc/tail_kernels.cuh,
+    gate_concat_*_kernel)."""
 
     def __init__(self, dims: list, hidden_size: int = 256, output_size: int = 256):
         super().__init__()

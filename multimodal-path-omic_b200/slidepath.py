@@ -16,8 +16,8 @@ from . import bagpass as bp
 from .bagpass import D, Q, _ptr, _stream, require_cuda
 
 VARIANT_MCAT, VARIANT_NACAGAT = 0, 1
-FUSION_CONCAT, FUSION_BILINEAR = 0, 1
-_FUSION_CODE = {"concat": FUSION_CONCAT, "bilinear": FUSION_BILINEAR}
+FUSION_CONCAT, FUSION_BILINEAR, FUSION_GATED_CONCAT = 0, 1, 2
+_FUSION_CODE = {"concat": FUSION_CONCAT, "bilinear": FUSION_BILINEAR, "gated_concat": FUSION_GATED_CONCAT}
 
 _seed_counter = itertools.count(1)
 
@@ -47,9 +47,7 @@ class ModelBinding:
 
     def __init__(self, module, variant, fusion, omic_sizes, n_classes):
         if fusion not in _FUSION_CODE:
-            raise NotImplementedError(
-                "fusion=%r is not implemented on the B200 path (concat and bilinear are; gated_concat is listed "
-                "as a next step in SURVEY.md 8f)" % fusion)
+            raise NotImplementedError("fusion=%r is not implemented on the B200 path" % fusion)
         if len(omic_sizes) != Q:
             raise NotImplementedError("the B200 kernels are built for 6 omic signature groups, got %d" % len(omic_sizes))
         self.module = module
@@ -179,9 +177,18 @@ class ModelBinding:
             m.omic_tr[l] = enc_layer("omic_transformer.layers.%d" % l)
         m.path_pool = pool("path_attention_head", "path_rho")
         m.omic_pool = pool("omic_attention_head", "omic_rho")
-        if self.fusion == FUSION_CONCAT:
+        if self.fusion in (FUSION_CONCAT, FUSION_GATED_CONCAT):
             m.fusion0 = lin("fusion_layer.fusion_layer.0")
             m.fusion2 = lin("fusion_layer.fusion_layer.2")
+            if self.fusion == FUSION_GATED_CONCAT:
+                # the reference keeps the two gate layers in a plain Python list (fusion.py:25-27): they are not
+                # parameters of the module, are never trained and do not follow .to(device); device copies are made here
+                dev = next(iter(P.values())).device
+                for i, gate in enumerate(self.module.fusion_layer.gates):
+                    gw = gate[0].weight.detach().to(device=dev, dtype=torch.float32).contiguous()
+                    gb = gate[0].bias.detach().to(device=dev, dtype=torch.float32).contiguous()
+                    keep.append((gw, gb))
+                    m.gate[i].w, m.gate[i].b = gw.data_ptr(), gb.data_ptr()
         else:
             b = _lib.MpoBilinear()
             b.h1 = lin("fusion_layer.linear_h1.0")
@@ -395,7 +402,10 @@ class SlideEngine:
             a = _lib.MpoNacagatBwd()
             for name, t in (("h_saved", ws.h_saved), ("t_saved", ws.t_saved), ("scores", ws.scores), ("pgate", ws.pgate),
                             ("lse", ws.lse), ("pooled", ws.pooled), ("suma", ws.suma if use_suma else None),
-                            ("dpooled", st.dpooled), ("dsuma", st.dsuma if use_suma else None), ("qk", st.qk),
+                            ("pooled_lo", ws.pooled_lo),
+                            ("dpooled", st.dpooled), ("dsuma", st.dsuma if use_suma else None),
+                            ("d_amap", getattr(st, "d_amap", None)), ("amap_dot", getattr(st, "amap_dot", None)),
+                            ("qk", st.qk),
                             ("qp", st.qp), ("w_k_f16", self._wk_f16), ("dz_ws", ws.dz), ("dkg_ws", ws.dkg),
                             ("dg_ws", ws.dg), ("part_dqk", ws.part_dqk), ("part_dtq", ws.part_dtq),
                             ("part_db", ws.part_db), ("part_dbk", ws.part_dbk), ("part_dkc", ws.part_dkc),
@@ -411,7 +421,8 @@ class SlideEngine:
         else:
             _lib.call("mpo_bag_bwd", st.bag.c(), _ptr(ws.h_saved), _ptr(ws.scores), _ptr(ws.lse), _ptr(ws.pooled),
                       _ptr(st.dpooled), _ptr(st.qk), _ptr(ws.dz), _ptr(ws.part_dqk), _ptr(ws.part_db), _ptr(st.dqk),
-                      gw, gb, ctypes.c_float(st.drop_p), s)
+                      gw, gb, _ptr(getattr(st, "d_amap", None)), _ptr(getattr(st, "amap_dot", None)),
+                      ctypes.c_float(st.drop_p), s)
 
     # -- backward
     def backward(self, model, st, dhaz, dS, dY, post_done=False):
@@ -456,18 +467,29 @@ class _SlideFn(torch.autograd.Function):
                             save_for_backward=needs_bwd)
         ctx.engine, ctx.state, ctx.n_omics, ctx.n_params = engine, st, n_omics, len(params)
         coattn = engine.attention_map(st) if want_map else torch.empty(0, device=wsi.device)
+        st.amap = coattn if want_map else None
         # the outputs are COPIES of the state's buffers: returning st.hazards itself would close a reference cycle
         # (ctx -> state -> hazards -> grad_fn -> ctx) that only the cyclic GC breaks, and every slide's saved
         # activations would stay allocated (fresh cudaMallocs per call) until it runs
         a_path, a_omic = st.att_path.clone(), st.att_omic.clone()
         outs = (st.hazards.clone(), st.S.clone(), st.Y.clone(), coattn, a_path, a_omic)
-        ctx.mark_non_differentiable(coattn, a_path, a_omic)
+        # the map is differentiable (CrossEntropySurvivalAttnRegLoss feeds attention_scores['coattn'] to the loss,
+        # models/loss.py:88-101 / models/nacagat/main.py:49-50); the pooling logits are not consumed by any loss
+        if want_map and needs_bwd:
+            ctx.mark_non_differentiable(a_path, a_omic)
+        else:
+            ctx.mark_non_differentiable(coattn, a_path, a_omic)
+        ctx.set_materialize_grads(False)
         return outs
 
     @staticmethod
-    def backward(ctx, dhaz, dS, dY, *unused):
+    def backward(ctx, dhaz, dS, dY, dA=None, *unused):
         engine, st = ctx.engine, ctx.state
         ctx.state = None
+        if dA is not None and st.amap is not None:
+            # a gradient arrived on the returned map: dense [6, N] upstream gradient + its softmax-Jacobian dot
+            st.d_amap = dA.detach().to(torch.float32).reshape(Q, -1).contiguous()
+            st.amap_dot = bp.attention_map_dot(st.bag, st.amap.detach(), st.d_amap)
         bnd = engine.binding
         P = bnd.params()
         if st.bag_ws.h_saved is None:

@@ -136,7 +136,8 @@ def mcat_coattn_fwd(P, G, H, pre="co_attention."):
     return out, a, (G, H, q, k, v, a, ctx)
 
 
-def mcat_coattn_bwd(P, cache, dout, grads, pre="co_attention."):
+def mcat_coattn_bwd(P, cache, dout, grads, pre="co_attention.", dA=None):
+    """dA: optional gradient arriving on the returned map (CrossEntropySurvivalAttnRegLoss, loss.py:88-101)."""
     G, H, q, k, v, a, ctx = cache
     E = G.shape[1]
     Win = P[pre + "in_proj_weight"]
@@ -144,6 +145,8 @@ def mcat_coattn_bwd(P, cache, dout, grads, pre="co_attention."):
     grads.add(pre + "out_proj.weight", dWo)
     grads.add(pre + "out_proj.bias", dbo)
     da = dctx @ v.T
+    if dA is not None:
+        da = da + dA
     dv = a.T @ dctx
     ds = softmax_bwd(da, a, axis=1)
     dq = (ds @ k) / np.sqrt(E)
@@ -211,7 +214,7 @@ def nacagat_coattn_fwd(P, G, H, pre="co_attention."):
     return out + C, a, (G, H, q, k, v, s, tq, tk, Pm, a, ctx, ccag)
 
 
-def nacagat_coattn_bwd(P, cache, dout, grads, pre="co_attention."):
+def nacagat_coattn_bwd(P, cache, dout, grads, pre="co_attention.", dA=None):
     G, H, q, k, v, s, tq, tk, Pm, a, ctx, ccag = cache
     E = G.shape[1]
     Win = P[pre + "in_proj_weight"]
@@ -220,6 +223,8 @@ def nacagat_coattn_bwd(P, cache, dout, grads, pre="co_attention."):
     grads.add(pre + "out_proj.weight", dWo)
     grads.add(pre + "out_proj.bias", dbo)
     da = dctx @ v.T
+    if dA is not None:
+        da = da + dA
     dv = a.T @ dctx
     ds2 = softmax_bwd(da, a, axis=1)
     ds = ds2 * Pm
@@ -450,6 +455,49 @@ def surv_head_bwd(P, h, logits, hazards, S, Y, dhaz, dS, dY, grads):
     return dlogits[0] @ P["classifier.weight"]
 
 
+def fusion_gated_concat_fwd(P, hp, ho, gates, pre="fusion_layer."):
+    """reference: models/fusion.py:22-41 (GatedConcatFusion).  gates = [(w [1,256], b [1])] * 2: the reference keeps
+    them in a plain Python list, so they are unregistered, untrained and absent from the state_dict (fusion.py:25-27)."""
+    items, gcache = [], []
+    for (w, b), x in zip(gates, (hp, ho)):
+        g = sigmoid(float(np.asarray(w, F64).reshape(-1) @ x + np.asarray(b, F64).reshape(-1)[0]))
+        items.append(x * g)
+        gcache.append((np.asarray(w, F64).reshape(-1), x, g))
+    out, c = fusion_concat_fwd(P, items[0], items[1], pre)
+    return out, (c, gcache)
+
+
+def fusion_gated_concat_bwd(P, cache, dh, grads, pre="fusion_layer."):
+    c, gcache = cache
+    d_items = fusion_concat_bwd(P, c, dh, grads, pre)
+    outs = []
+    for (w, x, g), di in zip(gcache, d_items):
+        outs.append(di * g + (di @ x) * g * (1.0 - g) * w)        # item = x * sigmoid(w.x + b)
+    return outs[0], outs[1]
+
+
+def sct_loss(Y, label, c, eps=1e-7):
+    """reference: models/loss.py:62-85 (SurvivalClassificationTobitLoss).  Returns loss and d/dY."""
+    Yv = np.asarray(Y, F64).reshape(-1)
+    y = int(np.asarray(label).reshape(-1)[0])
+    dY = np.zeros_like(Yv)
+    if float(np.asarray(c).reshape(-1)[0]) == 0:
+        loss = -np.log(Yv[y] + eps)
+        dY[y] = -1.0 / (Yv[y] + eps)
+    else:
+        cum = Yv[y:].sum() + eps
+        loss = -np.log(cum)
+        dY[y:] = -1.0 / cum
+    return float(loss), dY.reshape(np.asarray(Y).shape)
+
+
+def attn_norm_reg(A, lambda_reg):
+    """reference: models/loss.py:97  lambda_reg * torch.norm(attention, p=2).  Returns the term and d/dA."""
+    A = np.asarray(A, F64)
+    nrm = np.sqrt((A * A).sum())
+    return float(lambda_reg * nrm), (lambda_reg * A / nrm if nrm > 0 else np.zeros_like(A))
+
+
 def nll_surv_loss(hazards, S, Y, c, alpha=0.15, eps=1e-7):
     """reference: models/loss.py:31-43.  Returns loss, d/dhazards, d/dS (batch of 1)."""
     y = int(np.asarray(Y).reshape(-1)[0])
@@ -507,7 +555,7 @@ def _to64(P):
 
 
 def model_forward_backward(P, wsi, omics, label=None, censor=None, model="mcat", fusion="concat", loss="nll",
-                           want_grads=True):
+                           want_grads=True, gates=None, lambda_reg=0.01):
     """One slide through MCAT (models/mcat/mcat.py:84-142) or NaCAGaT (models/nacagat/nacagat.py:80-138), eval mode.
 
     Returns a dict with hazards, S, Y, risk, coattn [6,N], path [1,6], omic [1,6], loss and (optionally) grads."""
@@ -531,6 +579,8 @@ def model_forward_backward(P, wsi, omics, label=None, censor=None, model="mcat",
         h, cf = fusion_concat_fwd(P, h_path, h_omic)
     elif fusion == "bilinear":
         h, cf = fusion_bilinear_fwd(P, h_path, h_omic)
+    elif fusion == "gated_concat":
+        h, cf = fusion_gated_concat_fwd(P, h_path, h_omic, gates)
     else:
         raise ValueError(fusion)
     logits, hazards, S, Y = surv_head_fwd(P, h)
@@ -538,19 +588,29 @@ def model_forward_backward(P, wsi, omics, label=None, censor=None, model="mcat",
                H_coattn=Hc, G_bag=G)
     if label is None:
         return out
+    dY, dA = np.zeros_like(Y), None
     if loss == "nll":
         L, dhz, dS = nll_surv_loss(hazards, S, label, censor)
     elif loss == "ces":
         L, dhz, dS = ces_surv_loss(hazards, S, label, censor)
+    elif loss == "sct":
+        L, dY = sct_loss(Y, label, censor)
+        dhz, dS = np.zeros_like(hazards), np.zeros_like(S)
+    elif loss == "cesar":
+        L, dhz, dS = ces_surv_loss(hazards, S, label, censor)
+        reg, dA = attn_norm_reg(A, lambda_reg)
+        L = L + reg
     else:
         raise ValueError(loss)
     out["loss"] = L
     if not want_grads:
         return out
     grads = Grads()
-    dh = surv_head_bwd(P, h, logits, hazards, S, Y, dhz, dS, np.zeros_like(Y), grads)
+    dh = surv_head_bwd(P, h, logits, hazards, S, Y, dhz, dS, dY, grads)
     if fusion == "concat":
         dhp, dho = fusion_concat_bwd(P, cf, dh, grads)
+    elif fusion == "gated_concat":
+        dhp, dho = fusion_gated_concat_bwd(P, cf, dh, grads)
     else:
         dhp, dho = fusion_bilinear_bwd(P, cf, dh, grads)
     dpt = pool_bwd(P, "path_attention_head", "path_rho", cpp, dhp, grads)
@@ -558,9 +618,9 @@ def model_forward_backward(P, wsi, omics, label=None, censor=None, model="mcat",
     dHc = encoder_bwd(P, "path_transformer", cpt, dpt, grads)
     dG = encoder_bwd(P, "omic_transformer", cot, dot, grads)
     if model == "mcat":
-        dG2, dH = mcat_coattn_bwd(P, cco, dHc, grads)
+        dG2, dH = mcat_coattn_bwd(P, cco, dHc, grads, dA=dA)
     else:
-        dG2, dH = nacagat_coattn_bwd(P, cco, dHc, grads)
+        dG2, dH = nacagat_coattn_bwd(P, cco, dHc, grads, dA=dA)
     out["_internals"] = dict(H=H, dHc=dHc, coattn_cache=cco, dH=dH)      # for bag-stage level comparisons in tests
     snn_bwd(P, csnn, dG + dG2, grads)
     bag_proj_bwd(P, X, H, dH, grads)

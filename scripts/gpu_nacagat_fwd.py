@@ -23,7 +23,7 @@ for name in golden_cases():
             hazards, S, Y, att = net(wsi=wsi, omics=omics)
         g = case["gold"]
         eh = float(np.max(np.abs(hazards.detach().cpu().numpy() - g["hazards"]) / np.abs(g["hazards"])))
-        A, Aref = att["coattn"].cpu().numpy().astype(np.float64), g["coattn"].astype(np.float64)
+        A, Aref = att["coattn"].detach().cpu().numpy().astype(np.float64), g["coattn"].astype(np.float64)
         ea = float(np.max(np.abs(A - Aref) / (np.abs(Aref) + 1e-3 * Aref.max())))
         ep = float(np.max(np.abs(att["path"].cpu().numpy() - g["path"])) / np.max(np.abs(g["path"])))
         print(f"{name} [{mode}]: hazards {eh:.2e}  coattn {ea:.2e}  path {ep:.2e}")

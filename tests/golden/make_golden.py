@@ -35,8 +35,22 @@ CASES = [
     ("mcat_concat_25088", "mcat", "concat", 25088, 13, 6.0),
     # SURVEY H2 option (a), second half: the reference run on weights that are NOT bf16-representable (the CUDA path
     # rounds H.0.weight / W_k itself): the delta is reported by tests/test_parity_gpu.py::test_unrounded_weights_delta
-    ("mcat_concat_unrounded_4096", "mcat", "concat", 4096, 14, 4.0),
-    ("nacagat_concat_unrounded_4096", "nacagat", "concat", 4096, 15, 4.0),
+    # (sharpen 1.0 = the statistics of the reference's own initialisation; the `sharp` one scales the in-projection by 4)
+    ("mcat_concat_unrounded_4096", "mcat", "concat", 4096, 14, 1.0),
+    ("nacagat_concat_unrounded_4096", "nacagat", "concat", 4096, 15, 1.0),
+    ("nacagat_concat_unrounded_sharp_4096", "nacagat", "concat", 4096, 15, 4.0),
+]
+
+
+# other loss branches of the reference drivers (models/nacagat/main.py:41-50): gradient digests of `loss_kind`
+# name,  model, fusion, N, seed, sharpen, loss kind, lambda_reg
+ALT_CASES = [
+    ("alt_mcat_concat_sct_300", "mcat", "concat", 300, 17, 2.0, "sct", 0.0),          # label 1, censored
+    ("alt_mcat_concat_sct_517", "mcat", "concat", 517, 18, 2.0, "sct", 0.0),          # label 2, uncensored
+    ("alt_nacagat_concat_cesar_300", "nacagat", "concat", 300, 19, 2.0, "cesar", 5.0),
+    ("alt_mcat_concat_cesar_517", "mcat", "concat", 517, 20, 4.0, "cesar", 5.0),
+    ("alt_mcat_gated_concat_300", "mcat", "gated_concat", 300, 24, 2.0, "nll", 0.0),
+    ("alt_nacagat_gated_concat_517", "nacagat", "gated_concat", 517, 25, 2.0, "ces", 0.0),
 ]
 
 
@@ -107,6 +121,54 @@ def main():
         np.savez_compressed(os.path.join(outdir, name + ".npz"), **rec)
         print(f"{name}: hazards={rec['hazards'].round(5).tolist()} loss_nll={rec['loss_nll']:.6f} "
               f"coattn max={rec['coattn'].max():.3e} min={rec['coattn'].min():.3e}")
+
+    from models.loss import SurvivalClassificationTobitLoss, CrossEntropySurvivalAttnRegLoss
+    for name, model, fusion, n, seed, sharpen, kind, lam in ALT_CASES:
+        if only and name not in only:
+            continue
+        cls = MCAT if model == "mcat" else NACAGAT
+        torch.manual_seed(seed)
+        net = cls(omic_sizes=list(synth.OMIC_SIZES), fusion=fusion)
+        shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        state = synth.make_state(shapes, seed, model=model, sharpen=sharpen)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()})
+        net.eval()
+        rec = {}
+        if fusion == "gated_concat":
+            # the reference keeps the gates in a plain Python list (fusion.py:25-27): unregistered, absent from the
+            # state_dict; their torch-default initial values are stored with the fixture
+            for gi, gate in enumerate(net.fusion_layer.gates):
+                rec["gate%d_w" % gi] = gate[0].weight.detach().numpy().copy()
+                rec["gate%d_b" % gi] = gate[0].bias.detach().numpy().copy()
+        bag, omics, label, censor = synth.make_slide(seed, n)
+        wsi = torch.from_numpy(bag)
+        om = [torch.from_numpy(o) for o in omics]
+        Y_t = torch.tensor([[label]], dtype=torch.int64)
+        c_t = torch.tensor([censor])
+        hazards, S, Y, att = net(wsi=wsi, omics=om, inference=True) if model == "mcat" else net(wsi=wsi, omics=om)
+        if kind == "sct":
+            loss = SurvivalClassificationTobitLoss()(Y, Y_t.reshape(1), c=c_t)
+        elif kind == "cesar":
+            loss, _ = CrossEntropySurvivalAttnRegLoss(lambda_reg=lam)(hazards, S, Y_t, c=c_t, attention=att["coattn"])
+        elif kind == "nll":
+            loss = NLL()(hazards, S, Y_t, c_t)
+        else:
+            loss = CES()(hazards, S, Y_t, c=c_t)
+        net.zero_grad()
+        loss.backward()
+        rec.update(hazards=hazards.detach().numpy(), S=S.detach().numpy(), Y=Y.detach().numpy(),
+                   coattn=att["coattn"].detach().numpy(), loss=np.float64(loss.item()),
+                   meta=np.array([n, seed, label, censor, sharpen], dtype=np.float64), lambda_reg=np.float64(lam),
+                   loss_kind=np.array(kind))
+        names = []
+        for k, p_ in net.named_parameters():
+            g = p_.grad.detach().numpy() if p_.grad is not None else np.zeros(tuple(p_.shape), np.float32)
+            rec["gd/" + k] = synth.grad_digest(k, g)
+            names.append(k)
+        rec["param_names"] = np.array(names)
+        rec["param_shapes"] = np.array([str(shapes[k]) for k in names])
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), **rec)
+        print(f"{name}: loss[{kind}]={rec['loss']:.6f} hazards={rec['hazards'].round(5).tolist()}")
 
     # GE-NaCAGaT (models/ge_nacagat/ge_nacagat.py): Y, the N x N self-attention map (digest + corner block), the
     # pooling logits, the driver's CrossEntropyLoss on Y (models/ge_nacagat/main.py:33) and its gradient digests

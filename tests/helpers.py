@@ -14,7 +14,7 @@ def golden_cases(unrounded=False):
     """MCAT / NaCAGaT fixtures.  The `unrounded` ones hold reference results for weights that are not
     bf16-representable: the oracle must match them exactly, the CUDA path only within the reported rounding delta."""
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                   if not p.endswith("loss_known_answers.npz") and not os.path.basename(p).startswith("ge_"))
+                   if not p.endswith("loss_known_answers.npz") and not os.path.basename(p).startswith(("ge_", "alt_")))
     return [n for n in names if ("unrounded" in n) == unrounded]
 
 
@@ -33,11 +33,18 @@ def load_ge_case(name):
                 param_names=names)
 
 
+def alt_cases():
+    """fixtures of the other loss / fusion branches (sct, cesar, gated_concat): gradient digests of `loss_kind`."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "alt_*.npz")))
+
+
 def load_case(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     n, seed, label, censor, sharpen = z["meta"]
-    parts = name.split("_")
+    parts = name[4:].split("_") if name.startswith("alt_") else name.split("_")
     model, fusion = parts[0], parts[1]
+    if fusion == "gated":
+        fusion = "gated_concat"
     names = [str(s) for s in z["param_names"]]
     shapes = {k: ast.literal_eval(str(s)) for k, s in zip(names, z["param_shapes"])}
     state = synth.make_state(shapes, int(seed), model=model, sharpen=float(sharpen),
