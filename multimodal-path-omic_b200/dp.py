@@ -100,3 +100,22 @@ def sharded_inference(module, wsi_local, omics, group=None):
     if n_local == 0:
         amap = amap[:, :0]
     return st.hazards, st.S, st.Y, amap
+
+
+def gather_attention_map(amap_local, num_patches, group=None, dst=0):
+    """Patch-range sharded inference leaves every rank with its [6, n_local] slice of the co-attention map; this gathers
+    the full [6, num_patches] map on rank `dst` (4.8 MB at 200 000 patches), None elsewhere.
+    Slices follow patch_range(): rank r owns columns [r * per, (r + 1) * per)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    per = patch_range(num_patches, 0, world)[1] if world > 0 else num_patches
+    per = max(per, 1)
+    a, b = patch_range(num_patches, rank, world)
+    pad = torch.zeros((amap_local.shape[0], per), dtype=amap_local.dtype, device=amap_local.device)
+    pad[:, :b - a] = amap_local
+    parts = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    full = torch.cat(parts, dim=1)[:, :num_patches]
+    return full.contiguous()

@@ -666,6 +666,21 @@ class BatchTrainer:
         self.last_state = st
         return st.loss, st.hazards, st.S
 
+    def evaluate(self, bag, omics, labels, censor, want_map=False):
+        """Forward + loss for B slides, no backward (models/mcat/main.py:115-148 `validate`, :159-183 `test`):
+        returns (loss [B], hazards [B,K], S [B,K], Y [B,K], map [6, rows] or None).  Eval mode (no dropout)."""
+        eng = self.engine
+        model = eng.binding.build(grads=None)
+        st = eng.forward(model, bag, omics, train=False, save_for_backward=False)
+        B, K = st.B, st.hazards.shape[1]
+        loss = torch.empty(B, dtype=torch.float32, device=bag.x.device)
+        scratch = torch.empty((2, B, K), dtype=torch.float32, device=bag.x.device)
+        _lib.call("mpo_surv_loss", self.kind, _ptr(st.hazards), _ptr(st.S), _ptr(labels), _ptr(censor),
+                  ctypes.c_float(self.alpha), ctypes.c_float(self.eps), ctypes.c_float(1.0), _ptr(loss), _ptr(scratch[0]),
+                  _ptr(scratch[1]), B, K, _stream())
+        amap = eng.attention_map(st) if want_map else None
+        return loss, st.hazards, st.S, st.Y, amap
+
     def capture(self, bag, omics, labels, censor, train=True, with_adam=False, split=False, allreduce=False):
         """Record one step (forward + loss + backward) over these STATIC buffers into a CUDA graph.
 

@@ -37,7 +37,19 @@ def _worker(rank, world, port, out):
     lse = m[:, 0] + np.log(np.exp(s_loc - m).sum(axis=1))
     pooled = np.exp(s_loc - lse[:, None]) @ h_loc
     lse_all, pooled_all = dp.gather_shard_stats(torch.from_numpy(lse), torch.from_numpy(pooled))
+    # 3) map export: every rank's [6, n_local] slice gathered on rank 0
+    Nm = 1000
+    full_map = torch.arange(6 * Nm, dtype=torch.float32).reshape(6, Nm)
+    a, b = dp.patch_range(Nm, rank, world)
+    gathered = dp.gather_attention_map(full_map[:, a:b].contiguous(), Nm)
+    assert (gathered is None) == (rank != 0)
     if rank == 0:
+        assert torch.equal(gathered, full_map)
+    # ... and with an empty last rank (a 100-patch bag is one tile: rank 1 owns nothing)
+    a, b = dp.patch_range(100, rank, world)
+    small = dp.gather_attention_map(full_map[:, a:b].contiguous(), 100)
+    if rank == 0:
+        assert torch.equal(small, full_map[:, :100])
         out.put((g.numpy(), lse_all.numpy(), pooled_all.numpy(), s_full, h_full))
     dist.barrier()
     dist.destroy_process_group()

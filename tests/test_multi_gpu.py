@@ -51,6 +51,15 @@ def _worker(rank, world, port, q):
     omics = [torch.from_numpy(o).to(dev) for o in case["omics"]]
     hz, S, Y, amap = dp.sharded_inference(net, wsi, omics)
     res = dict(rank=rank, hazards=hz.cpu().numpy(), amap=amap.cpu().numpy(), rows=(a, b))
+    full = dp.gather_attention_map(amap, case["n"])                      # the map export path
+    res["amap_full"] = None if full is None else full.cpu().numpy()
+    # a bag shorter than one tile per rank: rank 1 holds ZERO rows and still takes part in the combine
+    small = load_case("mcat_concat_128")
+    net_s = _build(small, dev)
+    a2, b2 = dp.patch_range(small["n"], rank, world)
+    hz2, _, _, amap2 = dp.sharded_inference(net_s, torch.from_numpy(small["bag"][a2:b2]).to(dev).reshape(-1, 1024),
+                                            [torch.from_numpy(o).to(dev) for o in small["omics"]])
+    res["small"] = dict(hazards=hz2.cpu().numpy(), cols=int(amap2.shape[1]), rows=(a2, b2))
     # ---- 2) data-parallel gradients
     lens = [300, 517, 129, 1000]
     slides = [synth.make_slide(300 + i, n) for i, n in enumerate(lens)]
@@ -117,6 +126,11 @@ def test_two_gpu_sharded_inference_and_dp_gradients():
     ref = g["coattn"].astype(np.float64)
     assert amap.shape == ref.shape
     assert np.max(np.abs(amap - ref) / (np.abs(ref) + 1e-3 * ref.max())) < 1e-3
+    assert got[1]["amap_full"] is None and np.array_equal(got[0]["amap_full"], np.concatenate([r["amap"] for r in got], axis=1))
+    gs_ = load_case("mcat_concat_128")["gold"]
+    assert got[1]["small"]["rows"] == (128, 128) and got[1]["small"]["cols"] == 0 and got[0]["small"]["cols"] == 128
+    for r in got:
+        assert np.max(np.abs(r["small"]["hazards"] - gs_["hazards"]) / np.abs(gs_["hazards"])) < 1e-3
     g1, gd = got[0]["grad_one"].astype(np.float64), got[0]["grad_dp"].astype(np.float64)
     assert np.linalg.norm(gd - g1) / np.linalg.norm(g1) < 2e-3
     assert np.allclose(got[0]["grad_dp"], got[1]["grad_dp"])
