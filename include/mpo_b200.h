@@ -202,6 +202,53 @@ int mpo_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
 int mpo_lse_combine(const float* lse_in, const float* pooled_in, int32_t nshards, float* lse_out, float* pooled_out,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Peer-memory collectives over NVLink / NVSwitch (one process per GPU).  The reference has no distributed
+ * code at all (its nn.DataParallel wrapper is a no-op at batch 1, models/mcat/main.py:267-268); these entry points carry
+ * the two exchanges of the B200 design -- the gradient reduction of data-parallel training over slides and the soft-max
+ * state combine of one bag sharded by patch range -- as plain kernels over CUDA-IPC mapped peer memory, so that a whole
+ * step replays as one CUDA graph (csrc/peer.cu).
+ *
+ * Set-up (once): every rank allocates an exchange buffer of mpo_peer_exchange_bytes() with mpo_peer_alloc, exports it
+ * (mpo_peer_export -> 64 opaque bytes, sent to the other ranks by any means, e.g. torch.distributed.all_gather_object),
+ * opens the others' (mpo_peer_open) and fills struct mpo_peer_group: data[p] = rank p's exchange buffer as mapped here,
+ * flags[p] = data[p] + mpo_peer_flags_offset(); for mpo_peer_adam_step also the flat gradient / parameter buffers of
+ * every rank (allocated with mpo_peer_alloc, exported and opened the same way).  epochs: local device memory,
+ * 8 zero-initialised uint32 counters.  All ranks must issue the same sequence of calls per slot.
+ * ------------------------------------------------------------------------------------------------ */
+#define MPO_PEER_MAX 8
+#define MPO_PEER_HANDLE_BYTES 64
+typedef struct mpo_peer_group {
+  int32_t world, rank;
+  void* data[MPO_PEER_MAX];             /* exchange buffers (peer-mapped; data[rank] is the local one)   */
+  uint32_t* flags[MPO_PEER_MAX];        /* flags[p][slot * 8 + r]: written by rank r, polled by rank p   */
+  void* grad[MPO_PEER_MAX];             /* flat fp32 gradient buffer of every rank  (mpo_peer_adam_step) */
+  void* param[MPO_PEER_MAX];            /* flat fp32 parameter buffer of every rank (mpo_peer_adam_step) */
+  uint32_t* epochs;                     /* local: one call counter per slot                              */
+} mpo_peer_group;
+int64_t mpo_peer_exchange_bytes(void);
+int64_t mpo_peer_flags_offset(void);
+int mpo_peer_alloc(int64_t bytes, void** ptr);           /* cudaMalloc'd (IPC-exportable), zero-filled */
+int mpo_peer_free(void* ptr);
+int mpo_peer_export(const void* ptr, void* handle_out);  /* handle_out: MPO_PEER_HANDLE_BYTES */
+int mpo_peer_open(const void* handle, void** ptr_out);
+int mpo_peer_close(void* ptr);
+/* all ranks' earlier work on `stream` is complete and visible to every rank's later work (signal + wait kernel) */
+int mpo_peer_barrier(const mpo_peer_group* g, int32_t slot, void* stream);
+/* Patch-range sharded bag: publish this rank's (lse [6], pooled [6][256]) to every peer, wait for theirs, merge:
+ * lse_out [6], pooled_out [6][256] are identical on every rank.  An empty shard passes lse = -inf, pooled = 0.
+ * Replaces all-gather + mpo_lse_combine by one launch. */
+int mpo_peer_lse_combine(const mpo_peer_group* g, int32_t slot, const float* lse_local, const float* pooled_local,
+                         float* lse_out, float* pooled_out, void* stream);
+/* Data-parallel optimizer step over elements [lo, hi) of the flat buffers (multiples of 4): barrier(slot) ->
+ * rank r sums slice r (mpo_peer_slice) of all ranks' gradients, scaled by grad_scale, applies Adam with L2 weight decay
+ * (models/mcat/main.py:298-299; arithmetic of mpo_adam_step) using exp_avg / exp_avg_sq [i - state_offset], and stores the
+ * new parameters into every rank's parameter buffer -> barrier(slot + 1) -> this rank's gradients [lo, hi) are zeroed.
+ * bump_step: increment *step_dev afterwards (pass 1 on the last bucket of an optimizer step). */
+int mpo_peer_adam_step(const mpo_peer_group* g, int32_t slot, int64_t lo, int64_t hi, float* exp_avg, float* exp_avg_sq,
+                       int64_t state_offset, float lr, float beta1, float beta2, float eps, float weight_decay,
+                       float grad_scale, int32_t* step_dev, int32_t bump_step, void* stream);
+void mpo_peer_slice(int64_t lo, int64_t hi, int32_t world, int32_t rank, int64_t* s0, int64_t* s1);
 
 /* ------------------------------------------------------------------------------------------------
  * Slide tail: everything that runs on the 6 omic tokens per slide, batched over the B slides of a step.
@@ -294,7 +341,7 @@ typedef struct mpo_tail_io {
 } mpo_tail_io;
 
 /* ABI self-check for bindings: sizeof(mpo_bag) (which = 0), sizeof(mpo_model) (1), sizeof(mpo_tail_io) (2),
- * sizeof(mpo_nacagat_bwd) (3) */
+ * sizeof(mpo_nacagat_bwd) (3), sizeof(mpo_ge_model) (4), sizeof(mpo_peer_group) (5) */
 int64_t mpo_sizeof(int32_t which);
 /* workspace size in floats for a batch of B slides */
 int64_t mpo_tail_ws_floats(const mpo_model* m, int32_t B);

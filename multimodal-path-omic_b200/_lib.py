@@ -94,6 +94,12 @@ class MpoNacagatBwd(ctypes.Structure):
         ("drop_p", c_float), ("attn_drop_p", c_float), ("seed", c_u32), ("seed_dev", c_void_p)]
 
 
+class MpoPeerGroup(ctypes.Structure):
+    """struct mpo_peer_group (include/mpo_b200.h)."""
+    _fields_ = [("world", c_i32), ("rank", c_i32), ("data", c_void_p * 8), ("flags", c_void_p * 8),
+                ("grad", c_void_p * 8), ("param", c_void_p * 8), ("epochs", c_void_p)]
+
+
 _lib = None
 
 
@@ -134,6 +140,15 @@ SIGNATURES = {
     "mpo_sct_loss": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_i32, c_i32, c_void_p],
     "mpo_l1_sum": [c_void_p, c_i64, c_void_p, c_void_p],
     "mpo_l1_grad": [c_void_p, c_void_p, c_i64, c_float, c_void_p],
+    "mpo_peer_alloc": [c_i64, ctypes.POINTER(c_void_p)],
+    "mpo_peer_free": [c_void_p],
+    "mpo_peer_export": [c_void_p, c_void_p],
+    "mpo_peer_open": [c_void_p, ctypes.POINTER(c_void_p)],
+    "mpo_peer_close": [c_void_p],
+    "mpo_peer_barrier": [ctypes.POINTER(MpoPeerGroup), c_i32, c_void_p],
+    "mpo_peer_lse_combine": [ctypes.POINTER(MpoPeerGroup), c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "mpo_peer_adam_step": [ctypes.POINTER(MpoPeerGroup), c_i32, c_i64, c_i64, c_void_p, c_void_p, c_i64, c_float, c_float,
+                           c_float, c_float, c_float, c_float, c_void_p, c_i32, c_void_p],
     "mpo_bag_bwd_nacagat": [ctypes.POINTER(MpoBag), ctypes.POINTER(MpoNacagatBwd), c_void_p],
     "mpo_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float,
                       c_void_p, c_i32, c_void_p],
@@ -152,7 +167,8 @@ SIGNATURES = {
                            c_float, c_void_p, c_void_p, c_void_p, c_i32, c_void_p],
 }
 # functions with a non-int return type
-OTHER_EXPORTS = ["mpo_tail_ws_floats", "mpo_tail_ws_lookup", "mpo_sizeof", "mpo_launch_count", "mpo_ge_ws_floats"]
+OTHER_EXPORTS = ["mpo_tail_ws_floats", "mpo_tail_ws_lookup", "mpo_sizeof", "mpo_launch_count", "mpo_ge_ws_floats",
+                 "mpo_peer_exchange_bytes", "mpo_peer_flags_offset", "mpo_peer_slice"]
 
 
 def _declare(L):
@@ -168,7 +184,13 @@ def _declare(L):
     L.mpo_launch_count.argtypes = [c_i32]
     L.mpo_sizeof.restype = c_i64
     L.mpo_sizeof.argtypes = [c_i32]
-    for which, st in enumerate((MpoBag, MpoModel, MpoTailIo, MpoNacagatBwd, MpoGeModel)):
+    L.mpo_peer_exchange_bytes.restype = c_i64
+    L.mpo_peer_exchange_bytes.argtypes = []
+    L.mpo_peer_flags_offset.restype = c_i64
+    L.mpo_peer_flags_offset.argtypes = []
+    L.mpo_peer_slice.restype = None
+    L.mpo_peer_slice.argtypes = [c_i64, c_i64, c_i32, c_i32, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
+    for which, st in enumerate((MpoBag, MpoModel, MpoTailIo, MpoNacagatBwd, MpoGeModel, MpoPeerGroup)):
         if L.mpo_sizeof(which) != ctypes.sizeof(st):
             raise RuntimeError("ABI mismatch: %s is %d bytes in libmpo_b200.so but %d in the ctypes binding"
                                % (st.__name__, L.mpo_sizeof(which), ctypes.sizeof(st)))

@@ -503,6 +503,7 @@ int64_t mpo_sizeof(int32_t which) {
     case 2: return sizeof(mpo_tail_io);
     case 3: return sizeof(mpo_nacagat_bwd);
     case 4: return sizeof(mpo_ge_model);
+    case 5: return sizeof(mpo_peer_group);
     default: return -1;
   }
 }

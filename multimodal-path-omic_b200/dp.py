@@ -65,13 +65,15 @@ class DataParallelTrainer:
         return loss, hazards, S
 
 
-def sharded_inference(module, wsi_local, omics, group=None):
+def sharded_inference(module, wsi_local, omics, group=None, peer=None):
     """MCAT / NaCAGaT inference on one bag whose patches are split over the ranks of `group`.
 
     wsi_local: this rank's [n_local, 1024] slice (see patch_range; ranks at the tail of a short bag may hold ZERO
     rows); omics: the same 6 vectors on every rank.  Returns hazards, S, Y (identical on every rank) and this rank's
     [6, n_local] slice of the co-attention map.  Every rank takes part in the all-gather: an empty rank contributes
-    lse = -inf / pooled = 0, which the log-sum-exp combine weights with exactly zero."""
+    lse = -inf / pooled = 0, which the log-sum-exp combine weights with exactly zero.
+    peer (peer.PeerGroup): the exchange + merge run as ONE kernel over NVLink peer memory (mpo_peer_lse_combine) instead of
+    an NCCL all-gather followed by mpo_lse_combine."""
     from . import bagpass as bp
     eng = module._engine
     n_local = int(wsi_local.shape[-2])
@@ -88,6 +90,9 @@ def sharded_inference(module, wsi_local, omics, group=None):
         if n_local == 0:
             lse_l = torch.full_like(lse_l, float("-inf"))
             pooled_l = torch.zeros_like(pooled_l)
+        if peer is not None:
+            peer.lse_combine(lse_l.contiguous(), pooled_l.contiguous(), st.bag_ws.lse[0], st.bag_ws.pooled[0])
+            return
         lse_all, pooled_all = gather_shard_stats(lse_l, pooled_l, group)
         lse, pooled = bp.lse_combine(lse_all, pooled_all)
         st.bag_ws.lse.copy_(lse.reshape(1, 6))
@@ -100,6 +105,63 @@ def sharded_inference(module, wsi_local, omics, group=None):
     if n_local == 0:
         amap = amap[:, :0]
     return st.hazards, st.S, st.Y, amap
+
+
+class ShardedInference:
+    """A patch-range sharded inference call captured as ONE CUDA graph per rank (BASELINE config 5): SNN / query fold ->
+    bag forward over this rank's patches -> mpo_peer_lse_combine over NVLink -> replicated tail -> this rank's slice of
+    the co-attention map.  The caller refreshes `wsi_local` / `omics` in place and calls replay().
+
+    wsi_local: static bf16 [n_local, 1024] device tensor (n_local may be 0); omics: 6 static fp32 device vectors."""
+
+    def __init__(self, module, wsi_local, omics, peer):
+        from . import bagpass as bp
+        self.eng = module._engine
+        self.peer = peer
+        self.n_local = int(wsi_local.shape[0])
+        dev = wsi_local.device
+        if self.n_local == 0:
+            wsi_local = torch.zeros((1, wsi_local.shape[-1]), dtype=torch.bfloat16, device=dev)
+        if wsi_local.dtype != torch.bfloat16:
+            raise RuntimeError("ShardedInference streams the shard where it lies: pass a bf16 tensor")
+        self.bag = bp.PackedBag.from_slides([wsi_local])
+        self.omics = [o.reshape(1, -1) for o in omics]
+        self.model = self.eng.binding.build(grads=None)
+        self.st = self.eng.alloc_state(self.model, self.bag, save_for_backward=False)
+        self.amap = torch.empty((6, self.bag.total_rows), dtype=torch.float32, device=dev)
+        self._neg_inf = torch.full((6,), float("-inf"), dtype=torch.float32, device=dev)
+        self._zeros = torch.zeros((6, 256), dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):                       # warm-up outside the capture (same call count on every rank)
+                self._run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        _lib_mod = __import__("importlib").import_module(__package__ + "._lib")
+        _lib_mod.lib().mpo_launch_count(1)
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self._run()
+        self.launches_per_replay = int(_lib_mod.lib().mpo_launch_count(1))
+
+    def _combine(self, st):
+        lse_l, pooled_l = st.bag_ws.lse[0], st.bag_ws.pooled[0]
+        if self.n_local == 0:
+            lse_l, pooled_l = self._neg_inf, self._zeros
+        self.peer.lse_combine(lse_l, pooled_l, st.bag_ws.lse[0], st.bag_ws.pooled[0])
+
+    def _run(self):
+        from . import bagpass as bp
+        self.eng.forward(self.model, self.bag, self.omics, train=False, save_for_backward=False, st=self.st,
+                         after_bag=self._combine)
+        bp.attention_map(self.bag, self.st.bag_ws, out=self.amap)
+
+    def replay(self):
+        """-> hazards, S, Y [1, K] (identical on every rank) and this rank's [6, n_local] slice of the map."""
+        self.graph.replay()
+        st = self.st
+        return st.hazards, st.S, st.Y, (self.amap if self.n_local else self.amap[:, :0])
 
 
 def gather_attention_map(amap_local, num_patches, group=None, dst=0):

@@ -597,13 +597,32 @@ class BatchTrainer:
         rebind_grad_views(self.engine.binding.params(), self.grads)
 
     # -- optimizer over the flat buffers (mpo_adam_step)
-    def use_flat_adam(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5):
+    def use_flat_adam(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, peer=None):
         """Moves the parameters into one flat buffer (their nn.Parameter objects stay, .data becomes a view) and
         sets up Adam state; adam_step() then updates the whole model with one kernel (reference optimizer:
-        torch.optim.Adam(lr=2e-4, weight_decay=1e-5), models/mcat/main.py:298-299, config.yaml:60-62)."""
+        torch.optim.Adam(lr=2e-4, weight_decay=1e-5), models/mcat/main.py:298-299, config.yaml:60-62).
+
+        peer (a peer.PeerGroup): data-parallel training -- the flat gradient and parameter buffers move into
+        IPC-exported memory that every rank maps, and peer_adam_step() replaces all-reduce + adam_step() by the sharded
+        reduce-scatter / Adam / all-gather kernels of csrc/peer.cu."""
         P = self.engine.binding.params()
         dev = self.flat_grad.device
-        self.flat_param = torch.zeros_like(self.flat_grad)
+        self.peer = peer
+        if peer is not None:
+            from .peer import PeerBuffer
+            n = self.flat_grad.numel()
+            self._peer_grad, self._peer_param = PeerBuffer(4 * n, dev), PeerBuffer(4 * n, dev)
+            new_grad = self._peer_grad.tensor(torch.float32)
+            new_grad.copy_(self.flat_grad)
+            self.flat_grad = new_grad
+            for nme, p in P.items():
+                g = self.flat_grad[self.offsets[nme]:self.offsets[nme] + p.numel()].view_as(p)
+                p.grad = g
+                self.grads[nme] = g
+            self.flat_param = self._peer_param.tensor(torch.float32)
+            peer.register_flat_buffers(self._peer_grad, self._peer_param)
+        else:
+            self.flat_param = torch.zeros_like(self.flat_grad)
         for n, p in P.items():
             view = self.flat_param[self.offsets[n]:self.offsets[n] + p.numel()].view_as(p)
             view.copy_(p.data)
@@ -619,6 +638,17 @@ class BatchTrainer:
         _lib.call("mpo_adam_step", _ptr(self.flat_param), _ptr(self.flat_grad), _ptr(self.adam_m), _ptr(self.adam_v),
                   self.flat_grad.numel(), ctypes.c_float(lr), ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps),
                   ctypes.c_float(wd), _ptr(self.adam_step_dev), 1 if zero_grad else 0, _stream())
+
+    def peer_adam_step(self, lo=0, hi=None, bump=True, slot=2):
+        """mpo_peer_adam_step over elements [lo, hi) of the flat buffers (the whole model by default): needs
+        use_flat_adam(peer=...).  The gradients must already carry the 1 / global-window scale (grad_acc_step)."""
+        if getattr(self, "peer", None) is None:
+            raise RuntimeError("peer_adam_step needs use_flat_adam(peer=PeerGroup)")
+        lr, b1, b2, eps, wd = self.adam_hp
+        hi = self.flat_grad.numel() if hi is None else hi
+        _lib.call("mpo_peer_adam_step", self.peer.ref(), slot, lo, hi, _ptr(self.adam_m), _ptr(self.adam_v), 0,
+                  ctypes.c_float(lr), ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps), ctypes.c_float(wd),
+                  ctypes.c_float(1.0), _ptr(self.adam_step_dev), 1 if bump else 0, _stream())
 
     def _run_fwd(self, st, bag, omics, labels, censor, train, seed, inline_wgrad=False):
         """pre -> bag forward -> post forward + loss + post backward (mpo_tail_post_step).  With inline_wgrad the
