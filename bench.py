@@ -44,6 +44,15 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary configurations (NaCAGaT, scaled window)")
     ap.add_argument("--no-parity", action="store_true", help="skip the reference-fixture parity gate in front of the timing")
+    ap.add_argument("--workload", default="train", choices=["train", "shard200k"],
+                    help="train: the headline train step; shard200k: BASELINE config 5, one 200 000-patch bag sharded by "
+                         "patch range over the GPUs (inference)")
+    ap.add_argument("--window", default="scaled", choices=["scaled", "strict"],
+                    help="accumulation window at N > 1: scaled = --batch slides per GPU per optimizer step (global window "
+                         "batch x N), strict = the reference's global window of --batch slides split over the GPUs")
+    ap.add_argument("--comm", default=os.environ.get("MPO_BENCH_COMM", "peer"), choices=["peer", "nccl"],
+                    help="N > 1: peer = reduce-scatter / Adam / all-gather kernels over NVLink peer memory inside the step "
+                         "graph (csrc/peer.cu); nccl = bucketed NCCL all-reduce between two graphs + flat Adam")
     return ap.parse_args()
 
 
@@ -249,6 +258,87 @@ def parity_gate(args, dev, pkg):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ config 5
+def run_shard200k(args, rank, world, dev, pkg, peer_group, n_total=200000, steps=None, quick=False):
+    """BASELINE config 5: MCAT inference on ONE 200 000-patch bag sharded by patch range over the GPUs.
+    Every rank streams its tile-aligned share of the bag, the partial soft-max states are exchanged and merged by
+    mpo_peer_lse_combine (one kernel over NVLink peer memory), the tail is replicated; the whole call is one CUDA-graph
+    replay per rank.  Checked in the same run against the unsharded call on rank 0 (hazards and the gathered [6, N] map).
+    At N = 1 the same graph runs with a group of one (no exchange partner): the single-GPU reference point."""
+    import torch
+    import torch.distributed as dist
+    from importlib import import_module
+    synth = import_module(pkg + "synth")
+    dp = import_module(pkg + "dp")
+    torch.manual_seed(0)
+    net = import_module(pkg + "mcat").MultimodalCoAttentionTransformer(omic_sizes=list(synth.OMIC_SIZES)).to(dev).eval()
+    a, b = dp.patch_range(n_total, rank, world)
+    # every rank draws the same bag (same generator seed, chunks of 25 000 rows) and keeps its own patch range
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4321)
+    wsi = torch.empty((b - a, 1024), dtype=torch.bfloat16, device=dev)
+    full = torch.empty((n_total, 1024), dtype=torch.bfloat16, device=dev) if rank == 0 else None
+    for c0 in range(0, n_total, 25000):
+        c1 = min(n_total, c0 + 25000)
+        chunk = torch.randn((c1 - c0, 1024), generator=gen, device=dev).to(torch.bfloat16)
+        lo, hi = max(a, c0), min(b, c1)
+        if hi > lo:
+            wsi[lo - a:hi - a] = chunk[lo - c0:hi - c0]
+        if full is not None:
+            full[c0:c1] = chunk
+    omics = [torch.randn(d, generator=gen, device=dev) for d in synth.OMIC_SIZES]
+    if world > 1 and peer_group is None:
+        raise RuntimeError("the sharded-inference benchmark runs over the peer-memory kernels: use --comm peer")
+
+    class _Solo:                       # world 1: the "merge" is the identity
+        def lse_combine(self, lse_l, pooled_l, lse_out, pooled_out, slot=0):
+            return lse_out, pooled_out
+    sh = dp.ShardedInference(net, wsi, omics, peer_group if world > 1 else _Solo())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    steps = steps or max(20, args.steps)
+    for _ in range(max(3, args.warmup)):
+        sh.replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        hz, S, Y, amap = sh.replay()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_bag = float(ms.item()) / steps
+    # parity inside the run: the unsharded module call on rank 0
+    check = None
+    full_map = dp.gather_attention_map(amap, n_total) if world > 1 else amap
+    if rank == 0:
+        with torch.no_grad():
+            hz1, _, _, att1 = net(full, omics, inference=True)
+        ref_map = att1["coattn"]
+        check = {"hazards_rel_err": float(((hz - hz1).abs() / hz1.abs()).max().item()),
+                 "map_rel_err": float(((full_map - ref_map).abs() / (ref_map.abs() + 1e-3 * ref_map.max())).max().item())}
+        check["ok"] = bool(check["hazards_rel_err"] < 1e-3 and check["map_rel_err"] < 1e-3)
+    out = {"ms_per_bag": ms_bag, "bags_per_s": 1e3 / ms_bag, "patches": n_total, "patches_per_gpu": b - a,
+           "per_gpu_bag_GBps": (b - a) * 2048 / (ms_bag * 1e-3) / 1e9, "aggregate_bag_GBps": n_total * 2048 / (ms_bag * 1e-3) / 1e9,
+           "gpu_launches_per_call": sh.launches_per_replay, "parity_vs_unsharded": check,
+           "note": "one CUDA-graph replay per rank: SNN + query fold, bag forward over the rank's patch range, "
+                   "mpo_peer_lse_combine over NVLink peer memory, replicated tail, map slice; CUDA events, max over ranks"}
+    if quick:
+        return out
+    return {"metric": "bags/sec (MCAT inference, 200k patches sharded by patch range)", "value": 1e3 / ms_bag, "unit": "bags/s",
+            "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": ms_bag, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "mcat_inference_200000_patches_sharded", "parallelism": f"patch-range x{world}",
+                       "l2": "every call streams the shard from HBM (51 MB per GPU at 8 GPUs < 126 MB L2: the bag of the "
+                             "previous call may still be L2-resident; the 1-GPU line streams 410 MB)"},
+            "gpu_launches": sh.launches_per_replay * steps, "shard200k": out}
+
+
 # ------------------------------------------------------------------------------------------------ ours
 def run_ours(args, rank, world, local_rank):
     import numpy as np
@@ -270,6 +360,18 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
 
     parity = None if args.no_parity else parity_gate(args, dev, pkg)
+    peer_group = None
+    if world > 1 and args.comm == "peer":
+        peer_group = import_module(pkg + "peer").PeerGroup(dev)
+    if args.workload == "shard200k":
+        line = run_shard200k(args, rank, world, dev, pkg, peer_group)
+        if rank == 0:
+            emit(line)
+        if peer_group is not None:
+            peer_group.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     if args.model == "mcat":
         cls = import_module(pkg + "mcat").MultimodalCoAttentionTransformer
@@ -279,8 +381,11 @@ def run_ours(args, rank, world, local_rank):
     net = cls(omic_sizes=list(synth.OMIC_SIZES)).to(dev)
     net.train()
     B, N = args.batch, args.patches
+    if world > 1 and args.window == "strict":
+        B = max(1, args.batch // world)          # the reference's global window (grad_acc_step slides) split over the GPUs
     trainer = sp.BatchTrainer(net, loss="nll", grad_acc_step=B * world)
-    trainer.use_flat_adam(lr=2e-4, weight_decay=1e-5)      # Adam(lr 2e-4, wd 1e-5): reference mcat/main.py:298, config.yaml
+    # Adam(lr 2e-4, wd 1e-5): reference mcat/main.py:298, config.yaml
+    trainer.use_flat_adam(lr=2e-4, weight_decay=1e-5, peer=peer_group)
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -301,7 +406,12 @@ def run_ours(args, rank, world, local_rank):
     # the process-group teardown with the captured collectives alive, so the default keeps NCCL outside the graphs
     one_graph = world > 1 and os.environ.get("MPO_BENCH_NCCL_IN_GRAPH", "0") == "1"
     graphed = None
-    if one_graph:
+    if peer_group is not None:
+        # the whole data-parallel step -- communication and optimizer included -- is ONE graph of plain kernels
+        graphed = trainer.capture(bag, omics, labels, censor, train=True, peer_step=True,
+                                  peer_overlap=os.environ.get("MPO_BENCH_PEER_OVERLAP", "1") == "1")
+        one_graph = True
+    elif one_graph:
         # the bucketed all-reduce and the Adam update inside the captured step (NCCL collectives are graph-capturable)
         try:
             graphed = trainer.capture(bag, omics, labels, censor, train=True, with_adam=True, allreduce=True)
@@ -443,8 +553,8 @@ def run_ours(args, rank, world, local_rank):
         dev_cen = [censor.clone() for _ in range(2)]
         for dx in dev_x:
             dx.copy_(x)
-        steps_g = [trainer.capture(dev_bags[i], dev_om[i], dev_lab[i], dev_cen[i], train=True, with_adam=(world == 1))
-                   for i in range(2)]
+        steps_g = [trainer.capture(dev_bags[i], dev_om[i], dev_lab[i], dev_cen[i], train=True, with_adam=(world == 1),
+                                   peer_step=peer_group is not None) for i in range(2)]
         copy_stream = torch.cuda.Stream(device=dev)
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
@@ -471,7 +581,7 @@ def run_ours(args, rank, world, local_rank):
                 torch.cuda.current_stream().wait_event(ready[slot])
                 loss, _, _ = steps_g[slot].replay()
                 freed[slot].record(torch.cuda.current_stream())
-                if world > 1:
+                if world > 1 and peer_group is None:
                     dist.all_reduce(trainer.flat_grad)
                     trainer.adam_step(zero_grad=True)
                 loss_host.copy_(loss, non_blocking=True)
@@ -580,6 +690,10 @@ def run_ours(args, rank, world, local_rank):
             msi = a.elapsed_time(b_) / 5
             also[tag] = {"ms_per_bag": msi, "patches": n_inf, "bag_GBps": n_inf * 2048 / (msi * 1e-3) / 1e9,
                          "note": "eager module call (forward + attention map), CUDA events"}
+        del inet
+        torch.cuda.empty_cache()
+        also["mcat_inference_200000_patches_graphed_1gpu"] = run_shard200k(args, 0, 1, dev, pkg, None, quick=True)
+        inet = import_module(pkg + "mcat").MultimodalCoAttentionTransformer(omic_sizes=list(synth.OMIC_SIZES)).to(dev)
         # the drop-in path itself: the reference's per-slide loop (models/mcat/main.py:39-70) calling the module and
         # the loss one slide at a time through torch.autograd (host overhead included: wall clock around 20 calls)
         inet.train()
@@ -604,6 +718,42 @@ def run_ours(args, rank, world, local_rank):
         del inet
         torch.cuda.empty_cache()
 
+    if world > 1 and not args.no_also:
+        # the other regime of SURVEY 8e and BASELINE config 5, measured in the same multi-GPU run (every rank takes part)
+        also = {}
+        other = "strict" if args.window == "scaled" else "scaled"
+        Bo = max(1, args.batch // world) if other == "strict" else args.batch
+        if peer_group is not None and Bo <= B:
+            torch.manual_seed(0)
+            onet = cls(omic_sizes=list(synth.OMIC_SIZES)).to(dev).train()
+            otr = sp.BatchTrainer(onet, loss="nll", grad_acc_step=Bo * world)
+            otr.use_flat_adam(lr=2e-4, weight_decay=1e-5, peer=peer_group)
+            obag = bpm.PackedBag(x[:Bo * N], (N,) * Bo)
+            og = otr.capture(obag, [o[:Bo].contiguous() for o in omics], labels[:Bo].contiguous(), censor[:Bo].contiguous(),
+                             train=True, peer_step=True)
+            for _ in range(5):
+                og.replay()
+            barrier()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            nst = max(20, args.steps)
+            for _ in range(nst):
+                og.replay()
+            b_.record()
+            barrier()
+            mso = torch.tensor([a_.elapsed_time(b_)], device=dev)
+            dist.all_reduce(mso, op=dist.ReduceOp.MAX)
+            mso = float(mso.item()) / nst
+            also[f"{other}_window"] = {
+                "slides_per_s": world * Bo / (mso * 1e-3), "ms_per_step": mso, "slides_per_gpu_per_step": Bo,
+                "global_slides_per_step": Bo * world,
+                "note": ("the reference's global accumulation window of %d slides split over the GPUs (SURVEY 8e 'strict')"
+                         % (Bo * world)) if other == "strict" else "scaled window: --batch slides per GPU per optimizer step"}
+            del og, otr, onet
+            torch.cuda.empty_cache()
+        if peer_group is not None:
+            also["mcat_inference_200000_patches_sharded"] = run_shard200k(args, rank, world, dev, pkg, peer_group, quick=True)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         rate, n, med, kind, threads, what = cpu_reference_rate(args.model, N, budget_s=12.0)
@@ -619,15 +769,23 @@ def run_ours(args, rank, world, local_rank):
                        "global_slides_per_step": B * world, "patches_per_slide": N, "features": 1024,
                        "parallelism": f"dp{world}", "mode": "train (every dropout layer of the path on: bag embedding, "
                        + ("attention weights, " if args.model != "mcat" else "") + "SNN, encoder layers, pooling heads, rho), "
-                       "NLL loss, Adam(lr 2e-4, wd 1e-5) step per batch (mpo_adam_step, in the graph at N=1), "
-                       "when N>1 the fp32 gradient all-reduce runs in two buckets per step, the post-stage bucket (~70 % of "
-                       "16.6 MB) next to the bag backward pass",
+                       "NLL loss, Adam(lr 2e-4, wd 1e-5) step per batch (mpo_adam_step, in the graph at N=1)",
+                       "window": args.window if world > 1 else "single GPU: --batch slides per optimizer step",
+                       "comm": None if world == 1 else (
+                           "peer: reduce-scatter + Adam + all-gather kernels over NVLink peer memory inside the step graph, the "
+                           "post-stage bucket (~2/3 of 16.6 MB) on a graph branch next to the bag backward pass (csrc/peer.cu)"
+                           if peer_group is not None else
+                           "nccl: fp32 all-reduce in two buckets between two graphs, the post-stage bucket next to the bag "
+                           "backward pass, then the flat Adam kernel"),
                        "l2": f"each step streams {B * N * 2048 / 1e9:.2f} GB of bag per GPU (> 126 MB L2), no flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
             "parity": parity,
             "stages": stages, "also": also,
         }
         emit(line)
+    if peer_group is not None:
+        barrier()
+        peer_group.close()
     if world > 1:
         dist.destroy_process_group()
 

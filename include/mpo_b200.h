@@ -233,6 +233,7 @@ int mpo_peer_free(void* ptr);
 int mpo_peer_export(const void* ptr, void* handle_out);  /* handle_out: MPO_PEER_HANDLE_BYTES */
 int mpo_peer_open(const void* handle, void** ptr_out);
 int mpo_peer_close(void* ptr);
+int mpo_peer_warmup(void);                               /* load the kernels ahead of a CUDA-graph capture */
 /* all ranks' earlier work on `stream` is complete and visible to every rank's later work (signal + wait kernel) */
 int mpo_peer_barrier(const mpo_peer_group* g, int32_t slot, void* stream);
 /* Patch-range sharded bag: publish this rank's (lse [6], pooled [6][256]) to every peer, wait for theirs, merge:

@@ -145,6 +145,7 @@ SIGNATURES = {
     "mpo_peer_export": [c_void_p, c_void_p],
     "mpo_peer_open": [c_void_p, ctypes.POINTER(c_void_p)],
     "mpo_peer_close": [c_void_p],
+    "mpo_peer_warmup": [],
     "mpo_peer_barrier": [ctypes.POINTER(MpoPeerGroup), c_i32, c_void_p],
     "mpo_peer_lse_combine": [ctypes.POINTER(MpoPeerGroup), c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "mpo_peer_adam_step": [ctypes.POINTER(MpoPeerGroup), c_i32, c_i64, c_i64, c_void_p, c_void_p, c_i64, c_float, c_float,

@@ -187,6 +187,17 @@ int mpo_peer_open(const void* handle, void** ptr_out) {
 }
 int mpo_peer_close(void* ptr) { return ptr ? check_cuda(cudaIpcCloseMemHandle(ptr), "cudaIpcCloseMemHandle") : MPO_OK; }
 
+int mpo_peer_warmup(void) {
+  // loads the kernels of this file (lazy module loading must not happen for the first time inside a stream capture)
+  if (num_sms() <= 0) return fail(MPO_E_CUDA, "%s", "mpo_peer_warmup: no CUDA device (this library has no CPU fallback)");
+  cudaFuncAttributes a;
+  cudaError_t e = cudaFuncGetAttributes(&a, peer_barrier_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_lse_combine_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_adam_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, peer_bump_step_kernel);
+  return check_cuda(e, "mpo_peer_warmup");
+}
+
 int mpo_peer_barrier(const mpo_peer_group* g, int32_t slot, void* stream) {
   int rc = check_group(g, "mpo_peer_barrier");
   if (rc) return rc;

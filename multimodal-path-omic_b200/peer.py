@@ -62,7 +62,8 @@ class PeerGroup:
         for p, ptr in enumerate(self.share(self.exchange)):
             self.c.data[p] = ptr
             self.c.flags[p] = ptr + off
-        self._stat = None
+        with torch.cuda.device(self.device):
+            _lib.call("mpo_peer_warmup")
 
     def share(self, buf):
         """exports `buf`, gathers every rank's handle and maps the others: -> list of W device pointers valid HERE."""

@@ -711,7 +711,8 @@ class BatchTrainer:
         amap = eng.attention_map(st) if want_map else None
         return loss, st.hazards, st.S, st.Y, amap
 
-    def capture(self, bag, omics, labels, censor, train=True, with_adam=False, split=False, allreduce=False):
+    def capture(self, bag, omics, labels, censor, train=True, with_adam=False, split=False, allreduce=False,
+                peer_step=False, peer_overlap=True):
         """Record one step (forward + loss + backward) over these STATIC buffers into a CUDA graph.
 
         The caller refreshes the contents of bag.x / omics / labels / censor in place and calls replay(); the
@@ -721,7 +722,10 @@ class BatchTrainer:
         all-reduce of flat_grad[post_bucket_offset():] between them (replay_first() / replay_second()).
         allreduce=True (torch.distributed initialised, NCCL) records the whole data-parallel step as ONE graph instead:
         forward part, all-reduce of the post-stage bucket on NCCL's stream next to the bag backward part, all-reduce
-        of the rest, then (with_adam) the optimizer step."""
+        of the rest, then (with_adam) the optimizer step.
+        peer_step=True (use_flat_adam(peer=...)): the whole data-parallel step INCLUDING its communication is one graph
+        of plain kernels: forward part -> [side branch: mpo_peer_adam_step over the post-stage bucket] next to the bag
+        backward part -> mpo_peer_adam_step over the rest.  Every rank must replay the same number of times."""
         eng = self.engine
         dev = bag.x.device
         st = eng.alloc_state(self.model, bag, save_for_backward=True, reuse_ws=False, with_backward_buffers=True)
@@ -731,7 +735,8 @@ class BatchTrainer:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):                         # warm-up outside the capture (lazy kernel attributes etc.)
-                self._run_bwd(self._run_fwd(st, bag, omics, labels, censor, train, 0, inline_wgrad=split or allreduce))
+                self._run_bwd(self._run_fwd(st, bag, omics, labels, censor, train, 0,
+                                            inline_wgrad=split or allreduce or peer_step))
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         if allreduce:
@@ -745,7 +750,24 @@ class BatchTrainer:
         graph = torch.cuda.CUDAGraph()
         graph2 = torch.cuda.CUDAGraph() if split else None
         _lib.lib().mpo_launch_count(1)
-        if allreduce:
+        if peer_step:
+            off = self.post_bucket_offset()
+            branch = torch.cuda.Stream(device=dev)
+            with torch.cuda.graph(graph):
+                self._run_fwd(st, bag, omics, labels, censor, train, 0, inline_wgrad=True)
+                if peer_overlap:
+                    # the post-stage bucket (~2/3 of the model) is final here: its sharded optimizer step runs on a
+                    # branch of the graph next to the bag backward pass, which only produces pre-stage gradients
+                    branch.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(branch):
+                        self.peer_adam_step(off, None, bump=False, slot=2)
+                    self._run_bwd(st)
+                    torch.cuda.current_stream().wait_stream(branch)
+                    self.peer_adam_step(0, off, bump=True, slot=4)
+                else:
+                    self._run_bwd(st)
+                    self.peer_adam_step(0, None, bump=True, slot=2)
+        elif allreduce:
             with torch.cuda.graph(graph):
                 self._run_fwd(st, bag, omics, labels, censor, train, 0, inline_wgrad=True)
                 w1 = dist.all_reduce(self.flat_grad[off:], async_op=True)
