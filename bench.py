@@ -356,6 +356,10 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one process per GPU: run on the cores (and first-touch the pinned staging memory on the NUMA node) next to this GPU
+    numa_cpus = None
+    if world > 1 and os.environ.get("MPO_BENCH_NUMA_BIND", "1") == "1":
+        numa_cpus = import_module(pkg + "ingest").bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -601,7 +605,8 @@ def run_ours(args, rank, world, local_rank):
         h2d = B * N * 1024 * 2 + sum(B * d * 4 for d in synth.OMIC_SIZES) + B * 8 + B * 4
         e2e = {"value": world * B * e2e_steps / float(dt.item()), "unit": "slides/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": B * 4, "steps": e2e_steps,
-               "note": "pinned host bf16 bags, double-buffered H2D on a copy stream, loss read back every step"}
+               "note": "pinned host bf16 bags, double-buffered H2D on a copy stream, loss read back every step",
+               "cpu_affinity_rank0": (None if numa_cpus is None else "%d cores next to GPU %d" % (len(numa_cpus), local_rank))}
 
     # ---- secondary configurations measured in the same run (N = 1 only): BASELINE config 2 (NaCAGaT train step) and
     # the scaled accumulation window of SURVEY 8e (128 slides per optimizer step instead of the reference's 32)
