@@ -346,6 +346,46 @@ int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, co
   CUtensorMap tm_h, tm_dzs;
   rc = make_tmap_16b_2d(&tm_h, h_saved, static_cast<uint64_t>(bag->total_rows), kD, 64, kTileM, true);
   if (rc) return rc;
+  // MPO_BWD_REGEN=1: dz never exists in HBM.  The row-scalar kernel leaves 80 B per patch (12 fp32 coefficients + 256
+  // mask bits, inside the dz workspace the caller provides) and the weight-gradient kernel regenerates the dz operand,
+  // once per 4-CTA cluster (bag_bwd_dwz_kernel).  Parity-green and 0.54 GB less HBM traffic per 32 x 16k step, but
+  // measured SLOWER than the two-kernel path with a materialised bf16 dz (0.414 vs 0.375 ms): the exchange of
+  // the regenerated boxes inside the cluster is latency-bound.  Off by default.
+  static int regen = -1;
+  if (regen < 0) { const char* e = getenv("MPO_BWD_REGEN"); regen = e ? atoi(e) : 0; }
+  // the regenerating kernel needs a 24 KB scratch ring per CTA behind the 80 B per patch: both live in the caller's dz
+  // workspace (512 B per patch), which is large enough from ~8 k patches on; smaller batches take the two-kernel path
+  int clusters = bag_bwd_dwz_max_clusters(num_sms());
+  if (clusters > bag->num_tiles) clusters = bag->num_tiles;
+  const size_t scr_off = (static_cast<size_t>(bag->total_rows) * 80 + 1023) / 1024 * 1024;
+  bool use_regen = regen != 0;
+  if (scr_off + bag_bwd_dwz_scratch_bytes(clusters) > static_cast<size_t>(bag->total_rows) * kD * 2) use_regen = false;
+  if ((reinterpret_cast<uintptr_t>(dz_ws) & 127) != 0) use_regen = false;        // TMA global addresses: 16 B, keep 128
+  if (use_regen) {
+    float* c12 = static_cast<float*>(dz_ws);
+    uint32_t* mask = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(dz_ws) + static_cast<size_t>(bag->total_rows) * 48);
+    p.c12_out = c12;
+    p.mask_out = mask;
+    p.out = nullptr;
+    p.part_db = nullptr;
+    rc = check_cuda(launch_bag_bwd_dz(3, tm_h, tm_h, p, num_sms(), st), "bag_bwd_dz_kernel<lite>");
+    if (rc) return rc;
+    rc = check_cuda(launch_bag_bwd_reduce(bag->tile_prefix, part_dqk, nullptr, dqk, nullptr, bag->num_slides,
+                                          bag->num_tiles, st), "bag_bwd_reduce_kernel");
+    if (rc) return rc;
+    CUtensorMap tm_x64;
+    rc = make_tmap_bf16_2d(&tm_x64, bag->x, static_cast<uint64_t>(bag->total_rows), kDIn, 64, 64);
+    if (rc) return rc;
+    BagBwdDwzParams z = {};
+    z.tile_info = p.tile_info; z.num_tiles = p.num_tiles; z.total_rows = p.total_rows;
+    z.c12 = c12; z.mask = mask; z.dpooled = dpooled; z.qk = qk;
+    z.grad_w = grad_w_h; z.grad_b = grad_b_h; z.keep_scale = p.keep_scale;
+    z.scratch = static_cast<uint8_t*>(dz_ws) + scr_off;
+    CUtensorMap tm_scr;
+    rc = make_tmap_bf16_2d(&tm_scr, z.scratch, static_cast<uint64_t>(clusters) * 4 * 3 * 64, 64, 64, 64);
+    if (rc) return rc;
+    return check_cuda(launch_bag_bwd_dwz(tm_x64, tm_scr, z, num_sms(), st), "bag_bwd_dwz_kernel");
+  }
   rc = make_tmap_bf16_2d(&tm_dzs, dz_ws, static_cast<uint64_t>(bag->total_rows), kD, 64, kTileM);
   if (rc) return rc;
   rc = check_cuda(launch_bag_bwd_dz(0, tm_h, tm_dzs, p, num_sms(), st), "bag_bwd_dz_kernel");

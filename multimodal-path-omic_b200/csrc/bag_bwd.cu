@@ -33,7 +33,11 @@ namespace mpo {
 // kDzNacDkg  (NaCAGaT gate path, blocks.py:185-186): tile = tanh(k); Z = dg tq; out = dkg = (1 - t^2) Z gs (fp16,
 //            gs a batch-wide power of two); Q = dtq = sum_n dg_n tanh(k_n); b = gate part of db_k
 // ------------------------------------------------------------------------------------------------
-constexpr int kDzMcat = 0, kDzNacDh = 1, kDzNacDkg = 2;
+// kDzMcatLite (MCAT, default): the row-scalar half of kDzMcat only -- per patch the 12 coefficients [a_i | ds_i] (fp32)
+//            and the 256 ReLU/dropout mask bits of h are written out (80 B per patch instead of a 512 B dz row), Q = dqk;
+//            the dz tile itself is regenerated inside the weight-gradient kernel (bag_bwd_dwz_kernel below), so dz never
+//            makes the round trip through HBM
+constexpr int kDzMcat = 0, kDzNacDh = 1, kDzNacDkg = 2, kDzMcatLite = 3;
 constexpr int kDzThreads = 64 + 256;
 struct DzSmem {
   static constexpr int tile = 0;                       // 2 x 64 KB  fp16 tile [4][128][64] SW128 (later: the 16-bit output tile)
@@ -99,8 +103,9 @@ template <int MODE>
 __global__ void __launch_bounds__(kDzThreads, 1)
 bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                   const BagBwdDzParams p) {
+  constexpr bool kLite = MODE == kDzMcatLite;    // no dz tile: coefficients + mask bits out, dz regenerated by the dW kernel
   constexpr bool kHasG = MODE != kDzNacDkg;      // MMA-G (dots of the tile rows with dP)
-  constexpr bool kHasB = MODE != kDzNacDh;       // MMA-db (column sums of the output tile)
+  constexpr bool kHasB = MODE != kDzNacDh && !kLite;   // MMA-db (column sums of the output tile)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DzSmem::bars);
@@ -199,10 +204,12 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         mbar_wait(c_bar, tph);
         if (!kHasG) mbar_wait(&full_bar[buf], ph);
         tc_fence_after();
+        if (!kLite) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-          umma_bf16(tmem_base + kColZ, umma_desc_sw128(aC + k * 32, 16, 1024), umma_desc_sw128(aD + k * 32, 16, 1024),
-                    id_z, k != 0 ? 1u : 0u);
+          for (int k = 0; k < 3; ++k)
+            umma_bf16(tmem_base + kColZ, umma_desc_sw128(aC + k * 32, 16, 1024), umma_desc_sw128(aD + k * 32, 16, 1024),
+                      id_z, k != 0 ? 1u : 0u);
+        }
 #pragma unroll
         for (int mh = 0; mh < 2; ++mh)
 #pragma unroll
@@ -224,7 +231,7 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         mbar_wait(w_bar, tph);
         tc_fence_after();
         const TileInfo ti = p.tile_info[t];
-        const bool full_tile = ti.nvalid == kTileM;
+        const bool full_tile = !kLite && ti.nvalid == kTileM;
         if (full_tile) {
 #pragma unroll
           for (int cb = 0; cb < 4; ++cb) tma_store_2d(&tm_out, smem + DzSmem::tile + buf * 65536 + cb * 16384, cb * 64, ti.row0);
@@ -382,7 +389,7 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
 #pragma unroll
           for (int i = 0; i < kQ; ++i) {
             const float g = (__uint_as_float(gv[i]) + __uint_as_float(gv[i + 6])) * scal[16 + i] + dmap[i];
-            if (MODE == kDzMcat) {
+            if (MODE == kDzMcat || kLite) {
               const float a = valid ? __expf(sc[i] - scal[8 + i]) : 0.f;
               ds[i] = a * (g - scal[i]);
               c12[i] = a;
@@ -430,7 +437,15 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
 #pragma unroll
           for (int i = 0; i < kQ; ++i) scal[128 + qd * 8 + i] = amax[i];
         }
-        {
+        if (kLite) {
+          // the coefficients of dz_n = mask_n * keep_scale * sum_j c12[j] D[j] leave as fp32 (48 B per patch)
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(p.c12_out + grow * 12);
+            dst[0] = make_float4(c12[0], c12[1], c12[2], c12[3]);
+            dst[1] = make_float4(c12[4], c12[5], c12[6], c12[7]);
+            dst[2] = make_float4(c12[8], c12[9], c12[10], c12[11]);
+          }
+        } else {
           uint32_t hi[6], lo[6];
           split_bf16x12(c12, hi, lo);
           store_row48(Cs + r * 128, r & 7, hi, lo, hi);     // k 16..27 lo (x D hi), 32..43 hi (x D lo)
@@ -465,8 +480,28 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       tc_fence_after();
       uint16_t* grow_out = static_cast<uint16_t*>(p.out) + grow * kD;
       const bool direct = ti.nvalid != kTileM;     // ragged tile: rows are stored by the threads, not by TMA
+      if (kLite) {
+        // mask bits of this row's 128 features of column half ch: bit = h > 0 (ReLU and dropout zero the same way)
+        uint32_t w4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int j16 = 0; j16 < 16; ++j16) {
+          const int g16 = ch * 16 + j16;             // 16-byte chunk (8 features) of the 512 B row
+          const int cb = g16 >> 3, jj = g16 & 7;
+          const uint4 hv = *reinterpret_cast<const uint4*>(tile + cb * 16384 + r * 128 + ((jj ^ (r & 7)) << 4));
+          const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+          uint32_t bits = 0u;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            // fp16 pair: positive <=> sign bit clear and magnitude non-zero
+            bits |= ((hw[e] & 0x8000u) == 0u && (hw[e] & 0x7FFFu) != 0u) ? (1u << (2 * e)) : 0u;
+            bits |= ((hw[e] & 0x80000000u) == 0u && (hw[e] & 0x7FFF0000u) != 0u) ? (1u << (2 * e + 1)) : 0u;
+          }
+          w4[j16 >> 2] |= bits << ((j16 & 3) * 8);
+        }
+        if (valid) *reinterpret_cast<uint4*>(p.mask_out + grow * 8 + ch * 4) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
 #pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
+      for (int c4 = 0; c4 < (kLite ? 0 : 4); ++c4) {
         const int col0 = ch * 128 + c4 * 32;
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + kColZ + (static_cast<uint32_t>(qd * 32) << 16) + col0, v);
@@ -682,6 +717,348 @@ bag_bwd_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+// dW_H += dz^T X with dz REGENERATED on the fly (MCAT): no dz buffer in HBM.
+//
+// A cluster of 4 CTAs owns a contiguous range of 128-patch tiles; CTA cb of the cluster owns the gradient block
+// dW_H[:, 256 cb : 256 cb + 256] (all 512 TMEM columns, as in bag_bwd_dw_kernel) and streams the matching X columns.
+// The dz operand of a 64-patch chunk is [64 patches x 256 features] bf16, needed in full by all four CTAs: CTA cb
+// regenerates ITS feature block 64 cb .. 64 cb + 63 from the per-patch coefficients c12 = [a | ds] (bag_bwd_dz_kernel
+// <kDzMcatLite>), the per-slide operand D = [dP ; qk] and the saved mask bits,
+//     dz[n][f] = mask[n][f] keep_scale sum_j c12[n][j] D[j][f]            (fp32 FFMA2, then one rounding to bf16)
+// and hands the 8 KB box to all four CTAs through the L2: the threads write it (plain row-major, coalesced) into a
+// per-CTA scratch ring in global memory, and ONE multicast TMA load issued by the same CTA lands it, swizzled, at the same
+// dz-slot offset of every CTA of the cluster and completes on every CTA's dz_full barrier.  Each element is computed once
+// per cluster; the scratch (24 KB per CTA) never leaves the L2.
+// (Measured dead ends: per-thread st.shared::cluster stores of the box into the four shared memories -- 5x slower than
+// the whole old backward, DSMEM takes the stores packet by packet; bulk DSMEM copies shared::cta -> shared::cluster --
+// 387 us for the kernel whatever the slot count: 24 KB out + 24 KB in per 64-patch chunk at the ~17 B/clk the SM-to-SM
+// network sustains is 2.9 k cycles against 1.44 k cycles of MMA.)  Per CTA: warp 0 TMA (X, 3 stages of 32 KB), warp 1 MMA issuer, warps 2..9 regenerate (and, at the end, warps
+// 2..5 flush the accumulators with red.global.add).  db_H[f] = sum_n dz[n][f] falls out of the regenerating threads.
+// ------------------------------------------------------------------------------------------------
+constexpr int kZStages = 3;
+constexpr int kZSlots = 3;                            // dz slots: regenerate + ship (DSMEM) + MMA are three overlapping phases
+constexpr int kZXBytes = 4 * kDwBox;                    // X chunk [64 patches x 256 columns]     32 KB
+constexpr int kZDzBytes = 4 * kDwBox;                   // dz chunk [64 patches x 256 features]   32 KB
+constexpr int kZThreads = 64 + 256;
+constexpr int kZC12Bytes = 64 * 48;                     // coefficients of the chunk's 64 patches (fp32 [64][12])
+constexpr int kZMaskBytes = 64 * 32;                    // mask bits of the chunk's 64 patches (uint32 [64][8])
+constexpr int kZStageBytes = kZXBytes;                  // X chunk
+constexpr int kZCStages = 6;                            // coefficient / mask ring: its own, deeper, so that regenerating
+constexpr int kZCBytes = kZC12Bytes + kZMaskBytes;      // runs up to kZSlots chunks ahead of the MMAs (5 KB per chunk)
+struct DwzSmem {
+  static constexpr int x = 0;                           // 3 x 32 KB
+  static constexpr int dz = kZStages * kZStageBytes;    // 3 x 32 KB
+  static constexpr int cring = dz + kZSlots * kZDzBytes;      // 6 x 5 KB
+  static constexpr int red = cring + kZCStages * kZCBytes;    // fp32 [8][64] column-sum partials
+  static constexpr int bars = red + 8 * 64 * 4;
+  static constexpr int tmem_slot = bars + 256;
+  static constexpr int total = tmem_slot + 16;
+};
+constexpr int kDwzSmemBytes = DwzSmem::total + 1024;
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  return ra;
+}
+// bulk copy local shared memory -> shared memory of another CTA of the cluster; its bytes complete on that CTA's mbarrier
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(remote_dst), "r"(local_src), "r"(bytes), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+// 1-D bulk copy global -> shared memory of this CTA, completing on an mbarrier (size and addresses multiples of 16 B)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kZThreads, 1)
+bag_bwd_dwz_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_scr,
+                   const BagBwdDwzParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DwzSmem::bars);
+  uint64_t* x_full = bars;             // [3] TMA -> MMA
+  uint64_t* x_empty = bars + 3;        // [3] MMA -> TMA
+  uint64_t* dz_full = bars + 6;        // [3] 1 arrival (expect 4 x 8 KB) + the bytes of the four multicast box loads
+  uint64_t* dz_empty = bars + 9;       // [3] 4 arrivals: the MMA issuers of the 4 CTAs (multicast commit)
+  uint64_t* done_bar = bars + 12;
+  uint64_t* c_full = bars + 13;        // [6] coefficient rows landed
+  uint64_t* c_empty = bars + 19;       // [6] 4 arrivals: the regenerating warps of the chunk's group have read them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DwzSmem::tmem_slot);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cb = cluster_ctarank();                       // column block of dW_H / feature block regenerated here
+  const int cluster_id = static_cast<int>(blockIdx.x) >> 2;
+  const int nclusters = static_cast<int>(gridDim.x) >> 2;
+  const int per = (p.num_tiles + nclusters - 1) / nclusters;
+  const int t_begin = min(p.num_tiles, cluster_id * per);
+  const int t_end = min(p.num_tiles, t_begin + per);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_scr);
+    for (int s = 0; s < kZStages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
+    for (int s = 0; s < kZCStages; ++s) { mbar_init(&c_full[s], 1); mbar_init(&c_empty[s], 4); }
+    for (int s = 0; s < kZSlots; ++s) { mbar_init(&dz_full[s], 1); mbar_init(&dz_empty[s], 4); }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // every CTA's barriers exist before a peer arrives on them or writes its dz slots
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol_stream = policy_evict_first();
+      int c = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const TileInfo ti = p.tile_info[t];
+        for (int half = 0; half < 2; ++half) {
+          if (half == 1 && ti.nvalid <= 64) break;
+          const int stage = c % kZStages;
+          const uint32_t ph = (c / kZStages) & 1;
+          mbar_wait(&x_empty[stage], ph ^ 1);
+          uint8_t* sx = smem + DwzSmem::x + stage * kZStageBytes;
+          mbar_expect_tx(&x_full[stage], kZXBytes);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            tma_load_2d(sx + j * kDwBox, &tm_x, &x_full[stage], static_cast<int>(cb) * 256 + j * 64, ti.row0 + half * 64, pol_stream);
+          ++c;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 1, 1);      // A (dz^T) and B (X) both MN-major
+      int c = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int nvalid = p.tile_info[t].nvalid;
+        for (int half = 0; half < 2; ++half) {
+          if (half == 1 && nvalid <= 64) break;
+          const int stage = c % kZStages, slot = c % kZSlots;
+          mbar_wait(&x_full[stage], (c / kZStages) & 1);
+          mbar_wait_cluster(&dz_full[slot], (c / kZSlots) & 1);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(smem + DwzSmem::x + stage * kZStageBytes);
+          const uint32_t a_addr = smem_u32(smem + DwzSmem::dz + slot * kZDzBytes);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t db = umma_desc_sw128(b_addr + kk * 2048, kDwBox, 1024);
+#pragma unroll
+            for (int mh = 0; mh < 2; ++mh)
+              umma_bf16(tmem_base + mh * 256, umma_desc_sw128(a_addr + mh * 2 * kDwBox + kk * 2048, kDwBox, 1024), db, idesc,
+                        (c | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&x_empty[stage]);
+          umma_commit_mcast(&dz_empty[slot], 0xF);        // this CTA no longer reads the slot: tell all four producers
+          ++c;
+        }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    // ---------------------------------------------------------------- regenerating warps 2..9
+    const int rw = warp - 2;                 // 0..7: rows 8 rw .. 8 rw + 7 of the chunk
+    const int f0 = static_cast<int>(cb) * 64 + 2 * lane;       // the two features this thread regenerates
+    const int wsel = lane >> 4;              // which of the CTA's two mask words holds them
+    const uint32_t bit0 = 1u << ((2 * lane) & 31);
+    // byte offset of the pair inside a k-row of the CTA's box: 16-byte chunk lane >> 2 (swizzled per row), 4 (lane & 3) within
+    // this CTA's scratch ring in global memory: kZSlots boxes of [64 patches][64 features] bf16, row-major
+    const int scr_row0 = static_cast<int>(blockIdx.x) * (kZSlots * 64);
+    uint8_t* scr = reinterpret_cast<uint8_t*>(p.scratch) + static_cast<size_t>(scr_row0) * 128;
+    float2 D[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) D[j] = make_float2(0.f, 0.f);
+    float bsum0 = 0.f, bsum1 = 0.f;
+    int cur_slide = -1;
+    int c = 0;
+    // coefficient / mask prefetch (thread 0 of the regenerating warps): a second walk over the chunk sequence that stays
+    // kZCStages - 1 chunks ahead; the rows of a chunk are contiguous, two 1-D bulk copies per chunk
+    int pf_c = 0, pf_t = t_begin, pf_half = 0;
+    auto prefetch_one = [&]() {
+      if (pf_t >= t_end) return;
+      const TileInfo pt = p.tile_info[pf_t];
+      const int st = pf_c % kZCStages;
+      mbar_wait(&c_empty[st], ((pf_c / kZCStages) & 1) ^ 1);
+      const size_t r0 = static_cast<size_t>(pt.row0 + pf_half * 64);
+      const uint32_t nrows = static_cast<uint32_t>(min(64, p.total_rows - static_cast<int>(r0)));   // rows that exist
+      uint8_t* dst = smem + DwzSmem::cring + st * kZCBytes;
+      mbar_expect_tx(&c_full[st], nrows * 80u);
+      bulk_load_1d(dst, p.c12 + r0 * 12, nrows * 48u, &c_full[st]);
+      bulk_load_1d(dst + kZC12Bytes, p.mask + r0 * 8, nrows * 32u, &c_full[st]);
+      ++pf_c;
+      if (pf_half == 0 && pt.nvalid > 64) pf_half = 1; else { pf_half = 0; ++pf_t; }
+    };
+    // Two groups of four warps alternate over the chunks (group g takes the chunks with c % 2 == g, 16 rows per warp): the
+    // publication of a chunk -- global stores, proxy fence (waits for the stores' acknowledgement from the L2, ~1.5 k
+    // cycles), multicast load -- of one group overlaps the arithmetic of the other.  One group alone was regenerate-bound
+    // (2.8 k cycles per chunk against 1.44 k cycles of MMA).
+    const int grp = rw >> 2, gw = rw & 3;
+    const bool is_pf = rw == 0 && lane == 0;
+    if (is_pf) for (int i = 0; i < kZCStages - 2; ++i) prefetch_one();
+    for (int t = t_begin; t < t_end; ++t) {
+      const TileInfo ti = p.tile_info[t];
+      if (ti.slide != cur_slide) {
+        cur_slide = ti.slide;
+        const size_t sb = static_cast<size_t>(ti.slide) * kQ * kD + f0;
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
+          D[i] = *reinterpret_cast<const float2*>(p.dpooled + sb + i * kD);
+          D[6 + i] = *reinterpret_cast<const float2*>(p.qk + sb + i * kD);
+          D[i].x *= p.keep_scale; D[i].y *= p.keep_scale; D[6 + i].x *= p.keep_scale; D[6 + i].y *= p.keep_scale;
+        }
+      }
+      for (int half = 0; half < 2; ++half) {
+        if (half == 1 && ti.nvalid <= 64) break;
+        if ((c & 1) != grp) { ++c; continue; }
+        const int slot = c % kZSlots, stage = c % kZCStages;
+        const int nv = min(64, ti.nvalid - half * 64);
+        if (is_pf) { prefetch_one(); prefetch_one(); }
+        // coefficients and mask words of this warp's 16 rows from the prefetch ring (warp-uniform shared-memory
+        // addresses: broadcast reads).  Rows past the tile's end are another slide's: masked to zero.
+        mbar_wait(&c_full[stage], (c / kZCStages) & 1);
+        const uint8_t* sc = smem + DwzSmem::cring + stage * kZCBytes;
+        uint32_t zv[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int kr = gw * 16 + q;
+          const float4* src = reinterpret_cast<const float4*>(sc + kr * 48);
+          const float4 c0 = src[0], c1 = src[1], c2 = src[2];
+          const uint32_t mk = kr < nv ? *reinterpret_cast<const uint32_t*>(sc + kZC12Bytes + kr * 32 + (cb * 2 + wsel) * 4) : 0u;
+          const float cv[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+          float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 12; ++j) { z0 = fmaf(cv[j], D[j].x, z0); z1 = fmaf(cv[j], D[j].y, z1); }
+          z0 = (mk & bit0) ? z0 : 0.f;
+          z1 = (mk & (bit0 << 1)) ? z1 : 0.f;
+          bsum0 += z0; bsum1 += z1;
+          zv[q] = pack_bf16x2(z0, z1);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&c_empty[stage]);           // this warp is done with the stage's coefficient rows
+        mbar_wait(&dz_empty[slot], ((c / kZSlots) & 1) ^ 1);   // all four CTAs have consumed this slot's previous chunk
+        // a warp writes one 128-byte row of the box (64 features) per instruction
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          *reinterpret_cast<uint32_t*>(scr + (slot * 64 + gw * 16 + q) * 128 + lane * 4) = zv[q];
+        // generic-proxy global stores -> visible to the async proxy (the multicast TMA load below reads them back)
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        named_bar_sync(1 + grp, 128);
+        if (gw == 0 && lane == 0) {
+          // one arrival that announces the four boxes (this CTA's and the three peers') landing in this slot
+          mbar_expect_tx(&dz_full[slot], 4 * kDwBox);
+          tma_load_2d_mcast(smem + DwzSmem::dz + slot * kZDzBytes + cb * kDwBox, &tm_scr, &dz_full[slot], 0,
+                            scr_row0 + slot * 64, static_cast<uint16_t>(0xF), policy_evict_last());
+        }
+        ++c;
+      }
+    }
+    // db_H: column sums of the features regenerated here (each dz element exists exactly once per cluster)
+    float* red = reinterpret_cast<float*>(smem + DwzSmem::red);
+    red[rw * 64 + 2 * lane] = bsum0;
+    red[rw * 64 + 2 * lane + 1] = bsum1;
+    named_bar_sync(3, 256);
+    if (rw == 0) {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { s0 += red[w * 64 + 2 * lane]; s1 += red[w * 64 + 2 * lane + 1]; }
+      if (t_begin < t_end) { atomicAdd(p.grad_b + f0, s0); atomicAdd(p.grad_b + f0 + 1, s1); }
+    }
+    // accumulators -> gradient (warps 2..5 cover the four TMEM lane quadrants)
+    if (rw < 4 && t_begin < t_end) {
+      const int qd = warp & 3;
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mh = 0; mh < 2; ++mh) {
+        const int f = mh * 128 + qd * 32 + lane;
+        float* dst = p.grad_w + static_cast<size_t>(f) * kDIn + cb * 256;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + mh * 256 + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(__uint_as_float(v[j])),
+                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                         : "memory");
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // nobody leaves while a peer may still store into its dz slots / arrive on its barriers
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+int bag_bwd_dwz_max_clusters(int num_sms);
+
+cudaError_t launch_bag_bwd_dwz(const CUtensorMap& tm_x, const CUtensorMap& tm_scr, const BagBwdDwzParams& prm, int num_sms,
+                               cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(bag_bwd_dwz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwzSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (prm.num_tiles <= 0) return cudaSuccess;
+  // clusters of 4 only fit 33 at a time on a B200 (GPC sizes are not multiples of 4: 132 of the 148 SMs); a 34th cluster
+  // would run as a second wave and double the kernel (measured), so the grid is what is resident at once
+  int clusters = bag_bwd_dwz_max_clusters(num_sms);
+  if (clusters > prm.num_tiles) clusters = prm.num_tiles;
+  if (clusters < 1) clusters = 1;
+  bag_bwd_dwz_kernel<<<clusters * 4, kZThreads, kDwzSmemBytes, stream>>>(tm_x, tm_scr, prm);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// bytes of global scratch the kernel needs for `clusters` clusters (one ring of kZSlots boxes per CTA)
+size_t bag_bwd_dwz_scratch_bytes(int clusters) { return static_cast<size_t>(clusters) * 4 * kZSlots * kDwBox; }
+
+int bag_bwd_dwz_max_clusters(int num_sms) {
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cudaFuncSetAttribute(bag_bwd_dwz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwzSmemBytes);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms / 4 * 4);
+    cfg.blockDim = dim3(kZThreads);
+    cfg.dynamicSmemBytes = kDwzSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, bag_bwd_dwz_kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = num_sms / 4 - 4; }
+    max_clusters = n < 1 ? 1 : n;
+  }
+  return max_clusters;
+}
+
+// ------------------------------------------------------------------------------------------------
 // dkc[b][i] = sum over the slide's tiles of the per-tile sums of ds_i (one warp per slide and query)
 __global__ void bag_bwd_dkc_kernel(const int* __restrict__ tile_prefix, const float* __restrict__ part_dkc,
                                    float* __restrict__ dkc) {
@@ -720,6 +1097,7 @@ cudaError_t launch_bag_bwd_dz(int mode, const CUtensorMap& tm_in, const CUtensor
     case kDzMcat: return launch_dz_mode<kDzMcat>(tm_in, tm_out, prm, num_sms, stream);
     case kDzNacDh: return launch_dz_mode<kDzNacDh>(tm_in, tm_out, prm, num_sms, stream);
     case kDzNacDkg: return launch_dz_mode<kDzNacDkg>(tm_in, tm_out, prm, num_sms, stream);
+    case kDzMcatLite: return launch_dz_mode<kDzMcatLite>(tm_in, tm_out, prm, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -30,6 +30,10 @@ cudaError_t launch_bag_bwd_reduce(const int* tile_prefix, const float* part_dqk,
                                   float* grad_bias, int B, int num_tiles, cudaStream_t stream);
 cudaError_t launch_bag_bwd_dw(const CUtensorMap& tm_dz, const CUtensorMap& tm_x, float* grad_w, int total_rows,
                               int ncols, int ld, bool f16, const uint32_t* dg_max, int num_sms, cudaStream_t stream);
+cudaError_t launch_bag_bwd_dwz(const CUtensorMap& tm_x, const CUtensorMap& tm_scr, const BagBwdDwzParams& prm, int num_sms,
+                               cudaStream_t stream);
+int bag_bwd_dwz_max_clusters(int num_sms);
+size_t bag_bwd_dwz_scratch_bytes(int clusters);
 cudaError_t launch_bag_bwd_dkc(const int* tile_prefix, const float* part_dkc, float* dkc, int B, cudaStream_t stream);
 
 }  // namespace mpo

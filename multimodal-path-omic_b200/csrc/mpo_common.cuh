@@ -79,6 +79,21 @@ struct BagDhkParams {
   float keep_scale;
 };
 
+// weight gradient with regenerated dz (bag_bwd.cu: bag_bwd_dwz_kernel)
+struct BagBwdDwzParams {
+  const TileInfo* tile_info;
+  int num_tiles;
+  int total_rows;
+  const float* c12;            // [total_rows][12]  from bag_bwd_dz_kernel<kDzMcatLite>
+  const uint32_t* mask;        // [total_rows][8]
+  const float* dpooled;        // [B][6][256]
+  const float* qk;             // [B][6][256]
+  float* grad_w;               // [256][1024]  accumulated
+  float* grad_b;               // [256]        accumulated
+  void* scratch;               // bf16 [CTAs x 3 x 64][64]: the regenerated boxes on their way through the L2
+  float keep_scale;
+};
+
 struct BagBwdDzParams {
   const TileInfo* tile_info;
   int num_tiles;
@@ -101,6 +116,9 @@ struct BagBwdDzParams {
   float* dg;                   // [6][total_rows]  mode 1 writes, mode 2 reads the gate-dot gradients
   uint32_t* dg_max;            // bits of max |dg| over the batch (mode 1: atomicMax; mode 2: scale source)
   float* part_dkc;             // [num_tiles][8]   per-tile sums of ds_i (mode 1)
+  // lite mode (MCAT): coefficients and mask bits instead of a dz tile
+  float* c12_out;              // [total_rows][12] fp32  a_0..a_5, ds_0..ds_5
+  uint32_t* mask_out;          // [total_rows][8]        bit f of a row: h[row][f] > 0
   // optional gradient arriving on the returned attention map (e.g. the CESAR regulariser, models/loss.py:88-101)
   const float* d_amap;         // [6][total_rows]  dL/dA (A = the map as returned: post-dropout for NaCAGaT) or null
   const float* amap_dot;       // [B][6]           sum_n A_in dL/dA_in   (with d_amap)

@@ -153,11 +153,13 @@ def test_large_batch_graph_replay_matches_eager():
     assert float((tr.flat_grad - g_e).norm() / g_e.norm()) < 1e-5
 
 
-@pytest.mark.parametrize("env", [{"MPO_FWD_CLUSTER": "1"}, {"MPO_FWD_CLUSTER": "4"}, {"MPO_FWD_PAIR": "1"}],
-                         ids=["cluster1", "cluster4", "pair"])
+@pytest.mark.parametrize("env", [{"MPO_FWD_CLUSTER": "1"}, {"MPO_FWD_CLUSTER": "4"}, {"MPO_FWD_PAIR": "1"},
+                                 {"MPO_BWD_REGEN": "1"}],
+                         ids=["cluster1", "cluster4", "pair", "bwd_regen"])
 def test_forward_kernel_variants_at_large_shapes(env):
-    """every selectable build of the forward bag kernel through the large ragged batch and the 16 384 / 25 088-patch
-    reference fixtures (the switches are read once per process, hence the subprocess)."""
+    """every selectable build of the forward bag kernel -- and the opt-in backward that regenerates dz inside the
+    weight-gradient kernel (MPO_BWD_REGEN=1) -- through the large ragged batch and the 16 384 / 25 088-patch reference
+    fixtures (the switches are read once per process, hence the subprocess)."""
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_parity_large_gpu.py"),
                         os.path.join(here, "test_parity_gpu.py"), "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", "-k",
