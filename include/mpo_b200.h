@@ -339,6 +339,9 @@ typedef struct mpo_tail_io {
   float drop_p;
   uint32_t seed;
   const uint32_t* seed_dev;
+  /* 1 = train mode.  Separate from drop_p because the pooling heads (blocks.py:34-36) and the bilinear fusion
+   * (fusion.py:58-76) hard-code p = 0.25: a model built with dropout = 0 still drops there while training. */
+  int32_t train;
 } mpo_tail_io;
 
 /* ABI self-check for bindings: sizeof(mpo_bag) (which = 0), sizeof(mpo_model) (1), sizeof(mpo_tail_io) (2),
@@ -393,17 +396,22 @@ typedef struct mpo_ge_model {
   mpo_pool_head pool;                   /* path_attention_head + path_rho                                     */
   mpo_lin classifier;                   /* [n_classes,256]                                                    */
 } mpo_ge_model;
-/* workspace size in floats for a slide of N patches (dominated by 17 N x N attention matrices) */
+/* workspace size in floats for a slide of N patches (dominated by 18 N x N attention matrices) */
 int64_t mpo_ge_ws_floats(int64_t N);
 /* attn fp32 [N][N] (attention_scores['attn']), path fp32 [N] raw pooling logits (attention_scores['path']), Y [n_classes] */
+/* train != 0: the dropout layers of the path draw masks from the stateless RNG keyed by (seed, site, element): the four
+ * sites of each encoder layer at rate drop_p (attention probabilities, dropout1, feed-forward, dropout2:
+ * ge_nacagat.py:30-32), the pooling head at its hard-coded 0.25 (blocks.py:34-36) and rho at drop_p (ge_nacagat.py:36).
+ * mpo_ge_bwd regenerates them from the same (drop_p, seed, train). */
 int mpo_ge_fwd(const mpo_ge_model* m, int64_t N, const void* h_hi, const void* h_lo, float* ws, float* attn, float* path,
-               float* Y, void* stream);
+               float* Y, float drop_p, uint32_t seed, int32_t train, void* stream);
 /* the reference driver's loss: nn.CrossEntropyLoss on the soft-maxed Y (models/ge_nacagat/main.py:29,33); dY scaled by grad_scale */
 int mpo_ge_ce_loss(const float* Y, const int64_t* label, int32_t n_classes, float grad_scale, float* loss, float* dY,
                    void* stream);
 /* autograd of mpo_ge_fwd (+ the projection) given dY; gradients accumulated into m->*.gw/gb; dz_ws bf16 [N][256] */
 int mpo_ge_bwd(const mpo_ge_model* m, const mpo_bag* bag, const void* h_hi, float* ws, const float* attn, const float* path,
-               const float* Y, const float* dY, void* dz_ws, float keep_scale, void* stream);
+               const float* Y, const float* dY, void* dz_ws, float keep_scale, float drop_p, uint32_t seed, int32_t train,
+               void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,7 +74,7 @@ class MpoTailIo(ctypes.Structure):
         ("dpooled", c_void_p),
         ("dqk", c_void_p), ("dkc", c_void_p), ("dtq", c_void_p),
         ("hazards", c_void_p), ("S", c_void_p), ("Y", c_void_p), ("att_path", c_void_p), ("att_omic", c_void_p),
-        ("drop_p", c_float), ("seed", c_u32), ("seed_dev", c_void_p),
+        ("drop_p", c_float), ("seed", c_u32), ("seed_dev", c_void_p), ("train", c_i32),
     ]
 
 
@@ -153,10 +153,11 @@ SIGNATURES = {
     "mpo_bag_bwd_nacagat": [ctypes.POINTER(MpoBag), ctypes.POINTER(MpoNacagatBwd), c_void_p],
     "mpo_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float,
                       c_void_p, c_i32, c_void_p],
-    "mpo_ge_fwd": [ctypes.POINTER(MpoGeModel), c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "mpo_ge_fwd": [ctypes.POINTER(MpoGeModel), c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                   c_u32, c_i32, c_void_p],
     "mpo_ge_ce_loss": [c_void_p, c_void_p, c_i32, c_float, c_void_p, c_void_p, c_void_p],
     "mpo_ge_bwd": [ctypes.POINTER(MpoGeModel), ctypes.POINTER(MpoBag), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                   c_void_p, c_void_p, c_float, c_void_p],
+                   c_void_p, c_void_p, c_float, c_float, c_u32, c_i32, c_void_p],
     "mpo_lse_combine": [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p],
     "mpo_tail_pre_fwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],
     "mpo_tail_post_fwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],

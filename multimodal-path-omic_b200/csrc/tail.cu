@@ -48,7 +48,8 @@ struct Ctx {
   cudaStream_t wst = nullptr;  // weight-gradient stream of this branch, valid when async_w
   bool async_w = false;        // (a null stream handle is the legacy default stream, so it cannot double as "none")
   int sb = 0;                  // scratch set of this branch
-  float drop_p = 0.f;          // train-mode dropout of the tail (0 = eval); seed of the mask streams
+  bool train = false;          // train mode: dropout sites draw masks (the rate of a site may still be 0)
+  float drop_p = 0.f;          // the model's `dropout` rate; seed of the mask streams
   uint32_t seed = 0;
   const uint32_t* seed_dev = nullptr;
   cudaError_t err = cudaSuccess;
@@ -71,7 +72,8 @@ void join_w(Ctx& c) { if (c.async_w) dep(c, c.wst, c.st); }
 DropSpec no_drop() { DropSpec d = {}; return d; }
 DropSpec mk_drop(const Ctx& c, float p, uint32_t site, bool alpha = false) {
   DropSpec d = {};
-  if (c.drop_p <= 0.f || p <= 0.f) return d;       // eval, or a model built with dropout = 0
+  if (!c.train || p <= 0.f) return d;              // eval, or a site whose rate is 0 (a model built with dropout = 0
+                                                   // still drops at the hard-coded p = 0.25 sites, as in the reference)
   d.thr = static_cast<uint32_t>(p * 256.f + 0.5f);
   if (d.thr == 0) return d;
   const float pe = static_cast<float>(d.thr) / 256.f;     // the probability actually drawn
@@ -184,7 +186,7 @@ void enc_bwd(Ctx& c, const mpo_encoder_layer& P, const EncBuf& b, const Ws& w, f
              const float* dy2, float* dx_out, int B, int eidx) {
   const int R = 6 * B;
   const uint32_t s0 = SITE_ENC + 4 * eidx;
-  const bool train = c.drop_p > 0.f;
+  const bool train = c.train && c.drop_p > 0.f;
   join_w(c);
   float* dr2 = ws + w.s256a[c.sb];     // gradient of (y1 + dropout2(f2))
   const float* df2 = dr2;              // gradient of f2: through dropout2 in train mode (second output of the LN backward)
@@ -341,7 +343,8 @@ Branches make_branches(cudaStream_t stream, bool async_wgrad, const mpo_tail_io*
   } else {
     b.second.st = stream;     // everything in program order on the caller's stream
   }
-  if (io != nullptr && io->drop_p > 0.f) {
+  if (io != nullptr && io->train != 0) {
+    b.main.train = b.second.train = true;
     b.main.drop_p = b.second.drop_p = io->drop_p;
     b.main.seed = b.second.seed = io->seed;
     b.main.seed_dev = b.second.seed_dev = io->seed_dev;
@@ -414,6 +417,7 @@ struct GeWs {
   GeEnc enc[2];
   long long pa, pb, pab, pw, hp, h, logits;
   long long dlogits, dh, dzr, dhp, dw, dA, dab, t0, dx, dr2, df, dy1, dr1, dctx, dqkv, dP, dmid, dH, dzf;
+  long long dP2, dmk1, dmk2;      // train mode: dropped probabilities of one head; gradients behind dropout1 / dropout2
   long long total;
 };
 void ge_layout(long long N, GeWs& w) {
@@ -429,10 +433,14 @@ void ge_layout(long long N, GeWs& w) {
   w.dlogits = A(16); w.dh = A(E); w.dzr = A(E); w.dhp = A(E); w.dw = A(N); w.dA = A(N); w.dab = A(N * E); w.t0 = A(N * E);
   w.dx = A(N * E); w.dr2 = A(N * E); w.df = A(N * FF); w.dy1 = A(N * E); w.dr1 = A(N * E); w.dctx = A(N * E);
   w.dqkv = A(N * 3 * E); w.dP = A(N * N); w.dmid = A(N * E); w.dH = A(N * E); w.dzf = A(N * E);
+  w.dP2 = A(N * N); w.dmk1 = A(N * E); w.dmk2 = A(N * E);
   w.total = off;
 }
 // multi-head attention over N tokens from a packed [N, 3E] projection: probs [nh][N][N], ctx [N, E]
-void ge_attn_fwd(Ctx& c, const float* qkv, float* probs, float* ctx, int N, int nh) {
+// drop / pdrop: attention-probability dropout (train mode); the stored probabilities stay un-dropped (the soft-max
+// backward needs them), the dropped copy of one head lives in the scratch `pdrop` while its context GEMM runs
+void ge_attn_fwd(Ctx& c, const float* qkv, float* probs, float* ctx, int N, int nh, const DropSpec drop = DropSpec{},
+                 float* pdrop = nullptr) {
   const int hd = E / nh;
   const float scale = 1.f / sqrtf(static_cast<float>(hd));
   for (int h = 0; h < nh; ++h) {
@@ -440,23 +448,41 @@ void ge_attn_fwd(Ctx& c, const float* qkv, float* probs, float* ctx, int N, int 
     GemmArgs s{qkv + h * hd, 3 * E, 1, qkv + E + h * hd, 1, 3 * E, P, N, nullptr, N, N, hd, scale, 0, ACT_NONE, nullptr};
     c.chk(launch_gemm(s, c.st), "ge.scores");
     launch_k(row_softmax_kernel, dim3(N), dim3(256), 0, c.st, P, (long long)N, N); count_launch();
+    if (drop.thr != 0) {
+      launch_k(probs_dropout_kernel, dim3(nblk((long long)N * N, 1024)), dim3(256), 0, c.st, (const float*)P, pdrop,
+               (long long)N * N, static_cast<uint32_t>(h) * static_cast<uint32_t>(N) * static_cast<uint32_t>(N), drop); count_launch();
+      P = pdrop;
+    }
     GemmArgs o{P, N, 1, qkv + 2 * E + h * hd, 3 * E, 1, ctx + h * hd, E, nullptr, N, hd, N, 1.f, 0, ACT_NONE, nullptr};
     c.chk(launch_gemm(o, c.st), "ge.ctx");
   }
   c.chk(cudaGetLastError(), "ge_attn_fwd");
 }
 // dctx [N, E] -> dqkv [N, 3E]; dP is an [N, N] scratch
-void ge_attn_bwd(Ctx& c, const float* qkv, const float* probs, const float* dctx, float* dP, float* dqkv, int N, int nh) {
+void ge_attn_bwd(Ctx& c, const float* qkv, const float* probs, const float* dctx, float* dP, float* dqkv, int N, int nh,
+                 const DropSpec drop = DropSpec{}, float* pdrop = nullptr) {
   const int hd = E / nh;
   const float scale = 1.f / sqrtf(static_cast<float>(hd));
   for (int h = 0; h < nh; ++h) {
     const float* P = probs + (long long)h * N * N;
-    // dP = dctx_h V_h^T ; dV_h = P^T dctx_h
+    const uint32_t base = static_cast<uint32_t>(h) * static_cast<uint32_t>(N) * static_cast<uint32_t>(N);
+    // dP = dctx_h V_h^T ; dV_h = P'^T dctx_h  (P' = the dropped probabilities in train mode, regenerated)
     GemmArgs g1{dctx + h * hd, E, 1, qkv + 2 * E + h * hd, 1, 3 * E, dP, N, nullptr, N, N, hd, 1.f, 0, ACT_NONE, nullptr};
     c.chk(launch_gemm(g1, c.st), "ge.dP");
-    GemmArgs g2{P, 1, N, dctx + h * hd, E, 1, dqkv + 2 * E + h * hd, 3 * E, nullptr, N, hd, N, 1.f, 0, ACT_NONE, nullptr};
+    const float* Pv = P;
+    if (drop.thr != 0) {
+      launch_k(probs_dropout_kernel, dim3(nblk((long long)N * N, 1024)), dim3(256), 0, c.st, P, pdrop, (long long)N * N, base,
+               drop); count_launch();
+      Pv = pdrop;
+    }
+    GemmArgs g2{Pv, 1, N, dctx + h * hd, E, 1, dqkv + 2 * E + h * hd, 3 * E, nullptr, N, hd, N, 1.f, 0, ACT_NONE, nullptr};
     c.chk(launch_gemm(g2, c.st), "ge.dV");
-    launch_k(row_softmax_bwd_kernel, dim3(N), dim3(256), 0, c.st, P, (long long)N, dP, (long long)N, N, scale); count_launch();
+    if (drop.thr != 0) {
+      launch_k(row_softmax_bwd_drop_kernel, dim3(N), dim3(256), 0, c.st, P, (long long)N, dP, (long long)N, N, scale, base,
+               drop); count_launch();
+    } else {
+      launch_k(row_softmax_bwd_kernel, dim3(N), dim3(256), 0, c.st, P, (long long)N, dP, (long long)N, N, scale); count_launch();
+    }
     // dQ_h = dS K_h ; dK_h = dS^T Q_h
     GemmArgs g3{dP, N, 1, qkv + E + h * hd, 3 * E, 1, dqkv + h * hd, 3 * E, nullptr, N, hd, N, 1.f, 0, ACT_NONE, nullptr};
     c.chk(launch_gemm(g3, c.st), "ge.dQ");
@@ -465,26 +491,44 @@ void ge_attn_bwd(Ctx& c, const float* qkv, const float* probs, const float* dctx
   }
   c.chk(cudaGetLastError(), "ge_attn_bwd");
 }
-void ge_enc_fwd(Ctx& c, const mpo_encoder_layer& P, const GeEnc& b, float* ws, const float* x, int N) {
+// dropout sites of layer l as in enc_fwd: attention probabilities, dropout1, feed-forward dropout, dropout2
+// (models/ge_nacagat/ge_nacagat.py:30-32: TransformerEncoderLayer(..., dropout=dropout))
+void ge_enc_fwd(Ctx& c, const mpo_encoder_layer& P, const GeEnc& b, const GeWs& w, float* ws, const float* x, int N, int l) {
+  const uint32_t s0 = SITE_ENC + 4 * l;
   lin_fwd(c, x, E, P.in_proj, 3 * E, E, ws + b.qkv, 3 * E, N, ACT_NONE);
-  ge_attn_fwd(c, ws + b.qkv, ws + b.probs, ws + b.ctx, N, 8);
-  lin_fwd(c, ws + b.ctx, E, P.out_proj, E, E, ws + b.sa, E, N, ACT_NONE);
+  ge_attn_fwd(c, ws + b.qkv, ws + b.probs, ws + b.ctx, N, 8, mk_drop(c, c.drop_p, s0), ws + w.dP2);
+  lin_fwd(c, ws + b.ctx, E, P.out_proj, E, E, ws + b.sa, E, N, ACT_NONE, mk_drop(c, c.drop_p, s0 + 1));
   ln_fwd(c, x, ws + b.sa, P.norm1, ws + b.y1, ws + b.xh1, ws + b.rs1, N);
-  lin_fwd(c, ws + b.y1, E, P.linear1, FF, E, ws + b.f, FF, N, ACT_RELU);
-  lin_fwd(c, ws + b.f, FF, P.linear2, E, FF, ws + b.f2, E, N, ACT_NONE);
+  lin_fwd(c, ws + b.y1, E, P.linear1, FF, E, ws + b.f, FF, N, ACT_RELU, mk_drop(c, c.drop_p, s0 + 2));
+  lin_fwd(c, ws + b.f, FF, P.linear2, E, FF, ws + b.f2, E, N, ACT_NONE, mk_drop(c, c.drop_p, s0 + 3));
   ln_fwd(c, ws + b.y1, ws + b.f2, P.norm2, ws + b.y2, ws + b.xh2, ws + b.rs2, N);
 }
 void ge_enc_bwd(Ctx& c, const mpo_encoder_layer& P, const GeEnc& b, const GeWs& w, float* ws, const float* x,
-                const float* dy2, float* dx_out, int N) {
+                const float* dy2, float* dx_out, int N, int l) {
   const long long n = (long long)N * E;
-  ln_bwd(c, dy2, P.norm2, ws + b.xh2, ws + b.rs2, ws + w.dr2, N);
-  lin_bwd(c, ws + w.dr2, E, ws + b.f, FF, P.linear2, E, FF, ws + w.df, FF, N, false);
-  act_bwd(c, ws + w.df, FF, ws + b.f, FF, ws + w.df, FF, N, FF, ACT_RELU);
+  const uint32_t s0 = SITE_ENC + 4 * l;
+  const bool train = c.train && c.drop_p > 0.f;
+  // dr2 = gradient of (y1 + dropout2(f2)); df2 = gradient of f2 (through dropout2 in train mode)
+  const float* df2 = ws + w.dr2;
+  if (train) {
+    ln_bwd(c, dy2, P.norm2, ws + b.xh2, ws + b.rs2, ws + w.dr2, N, ws + w.dmk2, mk_drop(c, c.drop_p, s0 + 3));
+    df2 = ws + w.dmk2;
+  } else {
+    ln_bwd(c, dy2, P.norm2, ws + b.xh2, ws + b.rs2, ws + w.dr2, N);
+  }
+  lin_bwd(c, df2, E, ws + b.f, FF, P.linear2, E, FF, ws + w.df, FF, N, false);
+  act_bwd(c, ws + w.df, FF, ws + b.f, FF, ws + w.df, FF, N, FF, ACT_RELU, mk_drop(c, c.drop_p, s0 + 2));
   lin_bwd(c, ws + w.df, FF, ws + b.y1, E, P.linear1, FF, E, ws + w.dy1, E, N, false);
   add(c, ws + w.dy1, ws + w.dr2, ws + w.dy1, n);
-  ln_bwd(c, ws + w.dy1, P.norm1, ws + b.xh1, ws + b.rs1, ws + w.dr1, N);
-  lin_bwd(c, ws + w.dr1, E, ws + b.ctx, E, P.out_proj, E, E, ws + w.dctx, E, N, false);
-  ge_attn_bwd(c, ws + b.qkv, ws + b.probs, ws + w.dctx, ws + w.dP, ws + w.dqkv, N, 8);
+  const float* dsa = ws + w.dr1;
+  if (train) {
+    ln_bwd(c, ws + w.dy1, P.norm1, ws + b.xh1, ws + b.rs1, ws + w.dr1, N, ws + w.dmk1, mk_drop(c, c.drop_p, s0 + 1));
+    dsa = ws + w.dmk1;
+  } else {
+    ln_bwd(c, ws + w.dy1, P.norm1, ws + b.xh1, ws + b.rs1, ws + w.dr1, N);
+  }
+  lin_bwd(c, dsa, E, ws + b.ctx, E, P.out_proj, E, E, ws + w.dctx, E, N, false);
+  ge_attn_bwd(c, ws + b.qkv, ws + b.probs, ws + w.dctx, ws + w.dP, ws + w.dqkv, N, 8, mk_drop(c, c.drop_p, s0), ws + w.dP2);
   lin_bwd(c, ws + w.dqkv, 3 * E, x, E, P.in_proj, 3 * E, E, dx_out, E, N, false);
   add(c, dx_out, ws + w.dr1, dx_out, n);
 }
@@ -845,13 +889,14 @@ static int check_ge(const mpo_ge_model* m, int64_t N, const char* who) {
 }
 
 int mpo_ge_fwd(const mpo_ge_model* m, int64_t N64, const void* h_hi, const void* h_lo, float* ws, float* attn,
-               float* path, float* Y, void* stream) {
+               float* path, float* Y, float drop_p, uint32_t seed, int32_t train, void* stream) {
   int rc = check_ge(m, N64, "mpo_ge_fwd");
   if (rc) return rc;
   if (!h_hi || !h_lo || !ws || !attn || !path || !Y) return fail(MPO_E_ARG, "%s", "mpo_ge_fwd: NULL pointer");
   const int N = static_cast<int>(N64);
   GeWs w; ge_layout(N, w);
   Ctx c; c.st = static_cast<cudaStream_t>(stream);
+  c.train = train != 0; c.drop_p = drop_p; c.seed = seed;
   const long long n = (long long)N * E;
   launch_k(ge_h_kernel, dim3(nblk(n)), dim3(256), 0, c.st, static_cast<const __half*>(h_hi), static_cast<const __half*>(h_lo),
            ws + w.H, n); count_launch();
@@ -860,19 +905,19 @@ int mpo_ge_fwd(const mpo_ge_model* m, int64_t N64, const void* h_hi, const void*
   ge_attn_fwd(c, ws + w.sa_qkv, attn, ws + w.sa_ctx, N, 1);
   lin_fwd(c, ws + w.sa_ctx, E, m->sa_out, E, E, ws + w.sa_out, E, N, ACT_NONE);
   // encoder over the N tokens (ge_nacagat.py:30-32,53)
-  ge_enc_fwd(c, m->tr[0], w.enc[0], ws, ws + w.sa_out, N);
-  ge_enc_fwd(c, m->tr[1], w.enc[1], ws, ws + w.enc[0].y2, N);
+  ge_enc_fwd(c, m->tr[0], w.enc[0], w, ws, ws + w.sa_out, N, 0);
+  ge_enc_fwd(c, m->tr[1], w.enc[1], w, ws, ws + w.enc[0].y2, N, 1);
   const float* x = ws + w.enc[1].y2;
-  // gated attention pooling over N (blocks.py:42-48, ge_nacagat.py:56-60)
-  lin_fwd(c, x, E, m->pool.att_a, E, E, ws + w.pa, E, N, ACT_TANH);
-  lin_fwd(c, x, E, m->pool.att_b, E, E, ws + w.pb, E, N, ACT_SIGMOID);
+  // gated attention pooling over N (blocks.py:42-48, ge_nacagat.py:56-60); p = 0.25 hard-coded in the head (blocks.py:34-36)
+  lin_fwd(c, x, E, m->pool.att_a, E, E, ws + w.pa, E, N, ACT_TANH, mk_drop(c, 0.25f, SITE_POOL));
+  lin_fwd(c, x, E, m->pool.att_b, E, E, ws + w.pb, E, N, ACT_SIGMOID, mk_drop(c, 0.25f, SITE_POOL + 1));
   mul(c, ws + w.pa, ws + w.pb, ws + w.pab, n);
   lin_fwd(c, ws + w.pab, E, m->pool.att_c, 1, E, path, 1, N, ACT_NONE);                 // raw logits A [N] (returned)
   c.chk(cudaMemcpyAsync(ws + w.pw, path, (size_t)N * 4, cudaMemcpyDeviceToDevice, c.st), "ge.copy");
   launch_k(row_softmax_kernel, dim3(1), dim3(256), 0, c.st, ws + w.pw, (long long)N, N); count_launch();
   { GemmArgs g{ws + w.pw, N, 1, x, E, 1, ws + w.hp, E, nullptr, 1, E, N, 1.f, 0, ACT_NONE, nullptr};
     c.chk(launch_gemm(g, c.st), "ge.pool"); }
-  lin_fwd(c, ws + w.hp, E, m->pool.rho, E, E, ws + w.h, E, 1, ACT_RELU);
+  lin_fwd(c, ws + w.hp, E, m->pool.rho, E, E, ws + w.h, E, 1, ACT_RELU, mk_drop(c, c.drop_p, SITE_RHO));
   lin_fwd(c, ws + w.h, E, m->classifier, m->n_classes, E, ws + w.logits, m->n_classes, 1, ACT_NONE);
   c.chk(cudaMemcpyAsync(Y, ws + w.logits, (size_t)m->n_classes * 4, cudaMemcpyDeviceToDevice, c.st), "ge.copyY");
   launch_k(row_softmax_kernel, dim3(1), dim3(256), 0, c.st, Y, (long long)m->n_classes, m->n_classes); count_launch();
@@ -890,7 +935,8 @@ int mpo_ge_ce_loss(const float* Y, const int64_t* label, int32_t n_classes, floa
 }
 
 int mpo_ge_bwd(const mpo_ge_model* m, const mpo_bag* bag, const void* h_hi, float* ws, const float* attn, const float* path,
-               const float* Y, const float* dY, void* dz_ws, float keep_scale, void* stream) {
+               const float* Y, const float* dY, void* dz_ws, float keep_scale, float drop_p, uint32_t seed, int32_t train,
+               void* stream) {
   if (!bag) return fail(MPO_E_ARG, "%s", "mpo_ge_bwd: bag is NULL");
   int rc = check_ge(m, bag->total_rows, "mpo_ge_bwd");
   if (rc) return rc;
@@ -900,6 +946,7 @@ int mpo_ge_bwd(const mpo_ge_model* m, const mpo_bag* bag, const void* h_hi, floa
   const int N = static_cast<int>(bag->total_rows);
   GeWs w; ge_layout(N, w);
   Ctx c; c.st = static_cast<cudaStream_t>(stream);
+  c.train = train != 0; c.drop_p = drop_p; c.seed = seed;
   const long long n = (long long)N * E;
   const int K = m->n_classes;
   const float* x = ws + w.enc[1].y2;
@@ -907,7 +954,7 @@ int mpo_ge_bwd(const mpo_ge_model* m, const mpo_bag* bag, const void* h_hi, floa
   c.chk(cudaMemcpyAsync(ws + w.dlogits, dY, (size_t)K * 4, cudaMemcpyDeviceToDevice, c.st), "ge.copy");
   launch_k(row_softmax_bwd_kernel, dim3(1), dim3(256), 0, c.st, Y, (long long)K, ws + w.dlogits, (long long)K, K, 1.f); count_launch();
   lin_bwd(c, ws + w.dlogits, K, ws + w.h, E, m->classifier, K, E, ws + w.dh, E, 1, false);
-  act_bwd(c, ws + w.dh, E, ws + w.h, E, ws + w.dzr, E, 1, E, ACT_RELU);
+  act_bwd(c, ws + w.dh, E, ws + w.h, E, ws + w.dzr, E, 1, E, ACT_RELU, mk_drop(c, c.drop_p, SITE_RHO));
   lin_bwd(c, ws + w.dzr, E, ws + w.hp, E, m->pool.rho, E, E, ws + w.dhp, E, 1, false);
   // pooled = softmax(A)^T x : dw = dhp x^T [N], dx = w dhp [N,E]
   { GemmArgs g{ws + w.dhp, E, 1, x, 1, E, ws + w.dw, N, nullptr, 1, N, E, 1.f, 0, ACT_NONE, nullptr};
@@ -918,14 +965,14 @@ int mpo_ge_bwd(const mpo_ge_model* m, const mpo_bag* bag, const void* h_hi, floa
   // A = (a * b) w_c + b_c
   lin_bwd(c, ws + w.dw, 1, ws + w.pab, E, m->pool.att_c, 1, E, ws + w.dab, E, N, false);
   mul(c, ws + w.dab, ws + w.pb, ws + w.t0, n);
-  act_bwd(c, ws + w.t0, E, ws + w.pa, E, ws + w.t0, E, N, E, ACT_TANH);
+  act_bwd(c, ws + w.t0, E, ws + w.pa, E, ws + w.t0, E, N, E, ACT_TANH, mk_drop(c, 0.25f, SITE_POOL));
   lin_bwd(c, ws + w.t0, E, x, E, m->pool.att_a, E, E, ws + w.dx, E, N, true);
   mul(c, ws + w.dab, ws + w.pa, ws + w.t0, n);
-  act_bwd(c, ws + w.t0, E, ws + w.pb, E, ws + w.t0, E, N, E, ACT_SIGMOID);
+  act_bwd(c, ws + w.t0, E, ws + w.pb, E, ws + w.t0, E, N, E, ACT_SIGMOID, mk_drop(c, 0.25f, SITE_POOL + 1));
   lin_bwd(c, ws + w.t0, E, x, E, m->pool.att_b, E, E, ws + w.dx, E, N, true);
   // encoder
-  ge_enc_bwd(c, m->tr[1], w.enc[1], w, ws, ws + w.enc[0].y2, ws + w.dx, ws + w.dmid, N);
-  ge_enc_bwd(c, m->tr[0], w.enc[0], w, ws, ws + w.sa_out, ws + w.dmid, ws + w.dx, N);
+  ge_enc_bwd(c, m->tr[1], w.enc[1], w, ws, ws + w.enc[0].y2, ws + w.dx, ws + w.dmid, N, 1);
+  ge_enc_bwd(c, m->tr[0], w.enc[0], w, ws, ws + w.sa_out, ws + w.dmid, ws + w.dx, N, 0);
   // self-attention
   lin_bwd(c, ws + w.dx, E, ws + w.sa_ctx, E, m->sa_out, E, E, ws + w.dctx, E, N, false);
   ge_attn_bwd(c, ws + w.sa_qkv, attn, ws + w.dctx, ws + w.dP, ws + w.dqkv, N, 1);

@@ -1820,7 +1820,7 @@ struct JobBuilder {
 // ------------------------------------------------------------------------------------------------ host side
 DropSpec host_drop(const mpo_tail_io* io, float p, bool alpha) {
   DropSpec d = {};
-  if (io->drop_p <= 0.f || p <= 0.f) return d;
+  if (io->train == 0 || p <= 0.f) return d;            // eval, or a site whose rate is 0
   d.thr = static_cast<uint32_t>(p * 256.f + 0.5f);
   if (d.thr == 0) return d;
   const float pe = static_cast<float>(d.thr) / 256.f;

@@ -1048,6 +1048,35 @@ row_softmax_bwd_kernel(const float* __restrict__ a, long long lda, float* __rest
   s = block_reduce_256(s, false, red);
   for (int c = threadIdx.x; c < cols; c += 256) dr[c] = ar[c] * (dr[c] - s) * scale;
 }
+// GE-NaCAGaT train mode: attention-probability dropout of the N-token encoder layers (nn.TransformerEncoderLayer's
+// self_attn carries the layer's dropout rate).  out = dropout(p), element index = base + row * cols + col.
+__global__ void __launch_bounds__(256)
+probs_dropout_kernel(const float* __restrict__ p, float* __restrict__ out, long long n, uint32_t base, DropSpec drop) {
+  pdl_enter();
+  const uint32_t seedv = drop_seed(drop);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = drop_fwd(p[i], drop, seedv, base + static_cast<uint32_t>(i));
+}
+// ds = a (m da - sum_c a m da) * scale with m the regenerated dropout factor of the probabilities, in place over da
+__global__ void __launch_bounds__(256)
+row_softmax_bwd_drop_kernel(const float* __restrict__ a, long long lda, float* __restrict__ da, long long ldd, int cols,
+                            float scale, uint32_t base, DropSpec drop) {
+  pdl_enter();
+  __shared__ float red[8];
+  const uint32_t seedv = drop_seed(drop);
+  const float* ar = a + static_cast<long long>(blockIdx.x) * lda;
+  float* dr = da + static_cast<long long>(blockIdx.x) * ldd;
+  const uint32_t rb = base + static_cast<uint32_t>(blockIdx.x) * static_cast<uint32_t>(cols);
+  float s = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) {
+    const float d = dr[c] * drop_grad(drop, seedv, rb + c);
+    dr[c] = d;
+    s = fmaf(ar[c], d, s);
+  }
+  s = block_reduce_256(s, false, red);
+  for (int c = threadIdx.x; c < cols; c += 256) dr[c] = ar[c] * (dr[c] - s) * scale;
+}
 // H = fp16 hi + fp16 lo (the projection pass keeps both: bag_fwd.cu)
 __global__ void ge_h_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ H, long long n) {
   pdl_enter();

@@ -110,7 +110,7 @@ class _GeFn(torch.autograd.Function):
         ws_bag = bp.BagWorkspace(bag, save_h=True, nacagat=True, save_gate=False)
         qk0 = torch.zeros((1, Q, D), dtype=torch.float32, device=dev)
         drop_p = float(module.dropout) if train else 0.0
-        seed = _next_seed() if train else 0
+        seed = (getattr(module, "_fixed_seed", None) or _next_seed()) if train else 0
         bp.bag_project(bag, module._w_bf16, dict(module.named_parameters())["H.0.bias"].detach(), qk0, ws_bag,
                        seed=seed, drop_p=drop_p)
         nfl = _lib.lib().mpo_ge_ws_floats(N)
@@ -121,9 +121,9 @@ class _GeFn(torch.autograd.Function):
         path = torch.empty((1, N), dtype=torch.float32, device=dev)
         Y = torch.empty(module.n_classes, dtype=torch.float32, device=dev)
         _lib.call("mpo_ge_fwd", ctypes.byref(model), N, _ptr(ws_bag.h_saved), _ptr(ws_bag.h_lo), _ptr(ws), _ptr(attn),
-                  _ptr(path), _ptr(Y), _stream())
+                  _ptr(path), _ptr(Y), ctypes.c_float(drop_p), ctypes.c_uint32(seed & 0xFFFFFFFF), 1 if train else 0, _stream())
         if needs_bwd:
-            ctx.saved = (module, bag, ws_bag, ws, attn, path, Y, drop_p)
+            ctx.saved = (module, bag, ws_bag, ws, attn, path, Y, drop_p, seed, train)
         else:
             ctx.saved = None
             del ws
@@ -135,7 +135,7 @@ class _GeFn(torch.autograd.Function):
     def backward(ctx, dY, *unused):
         if ctx.saved is None:
             raise RuntimeError("this forward pass did not keep activations (it ran under no_grad)")
-        module, bag, ws_bag, ws, attn, path, Y, drop_p = ctx.saved
+        module, bag, ws_bag, ws, attn, path, Y, drop_p, seed, train = ctx.saved
         dev = bag.x.device
         P = dict(module.named_parameters())
         offs, off = {}, 0
@@ -149,7 +149,8 @@ class _GeFn(torch.autograd.Function):
         keep = 1.0 / (1.0 - drop_p) if drop_p > 0 else 1.0
         dYc = dY.detach().to(torch.float32).contiguous()
         _lib.call("mpo_ge_bwd", ctypes.byref(model), bag.c(), _ptr(ws_bag.h_saved), _ptr(ws), _ptr(attn), _ptr(path),
-                  _ptr(Y), _ptr(dYc), _ptr(dz), ctypes.c_float(keep), _stream())
+                  _ptr(Y), _ptr(dYc), _ptr(dz), ctypes.c_float(keep), ctypes.c_float(drop_p),
+                  ctypes.c_uint32(seed & 0xFFFFFFFF), 1 if train else 0, _stream())
         return (None, None, None, None, None) + tuple(grads[n] for n in P.keys())
 
 

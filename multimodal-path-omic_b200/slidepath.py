@@ -283,6 +283,7 @@ class SlideEngine:
         io.drop_p = self.tail_dropout if getattr(st, "train", False) else 0.0
         io.seed = getattr(st, "seed", 0) & 0xFFFFFFFF
         io.seed_dev = st.seed_dev.data_ptr() if (getattr(st, "train", False) and st.seed_dev is not None) else None
+        io.train = 1 if getattr(st, "train", False) else 0
         return io
 
     # -- buffers

@@ -486,3 +486,64 @@ def test_pair_tile_forward_kernel_matches_reference():
                         "test_forward_backward_matches_reference or test_batched_trainer_equals_per_slide_gradients"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_ge_nacagat_train_mode_dropouts_finite_differences():
+    """GE-NaCAGaT in train mode: the dropout layers of its N-token encoder (attention probabilities, dropout1,
+    feed-forward, dropout2: ge_nacagat.py:30-32), of the pooling head (p = 0.25, blocks.py:34-36) and of rho
+    (ge_nacagat.py:36) draw masks from the stateless RNG and the backward pass regenerates them: with a fixed seed the
+    loss is reproducible, another seed changes it, and directional finite differences of the loss along the analytic
+    gradient (two steps, extrapolated to 0: the loss is piecewise smooth) agree with the analytic norm."""
+    ge = _pkg("ge_nacagat")
+    case = load_ge_case("ge_300")
+    net = ge.GeneExprNarrowContextualAttentionGateTransformer()
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in case["state"].items()})
+    net = net.cuda().train()
+    wsi = torch.from_numpy(case["bag"]).cuda()
+    label = torch.tensor([case["label"]], device="cuda")
+
+    def loss_value(seed=777):
+        net._fixed_seed = seed
+        with torch.no_grad():
+            Y, _ = net(wsi=wsi)
+        return float(ge.ge_cross_entropy(Y, label).double().item())
+
+    base = loss_value()
+    assert loss_value() == base and abs(loss_value(778) - base) > 1e-7
+    net.eval()
+    with torch.no_grad():
+        Ye, _ = net(wsi=wsi)
+    assert abs(float(ge.ge_cross_entropy(Ye, label).item()) - base) > 1e-7          # dropout really is on in train mode
+    net.train()
+    net._fixed_seed = 777
+    net.zero_grad()
+    Y, _ = net(wsi=wsi)
+    ge.ge_cross_entropy(Y, label).backward()
+    grads = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    P = dict(net.named_parameters())
+    bad, report = [], []
+    for k in ("classifier.weight", "path_rho.0.weight", "path_attention_head.attention_a.0.weight",
+              "path_attention_head.attention_b.0.bias", "path_transformer.layers.1.linear2.weight",
+              "path_transformer.layers.0.linear1.weight", "path_transformer.layers.1.self_attn.in_proj_weight",
+              "path_transformer.layers.0.self_attn.out_proj.weight", "path_transformer.layers.0.norm1.weight",
+              "self_attention.in_proj_weight", "H.0.bias"):
+        g = grads[k]
+        gn = float(g.double().norm().item())
+        if gn < 1e-7:
+            continue
+        d = g / g.norm()
+        steps = (0.02 / max(gn, 1e-3) * 1e-2, 0.005 / max(gn, 1e-3) * 1e-2)
+        steps = (min(steps[0], 0.2), min(steps[1], 0.05))
+        fds = []
+        for st in steps:
+            old = P[k].data.clone()
+            P[k].data.copy_(old + st * d); lp = loss_value()
+            P[k].data.copy_(old - st * d); lm = loss_value()
+            P[k].data.copy_(old)
+            fds.append((lp - lm) / (2 * st))
+        fd0 = fds[1] + (fds[1] - fds[0]) / 3.0
+        report.append((k, "%.3e" % gn, "%.3e %.3e -> %.3e" % (fds[0], fds[1], fd0)))
+        if abs(fd0 - gn) > 8e-2 * max(gn, abs(fd0)) + 2e-6:
+            bad.append((k, gn, fds, fd0))
+    print(report)
+    assert len(bad) <= 1, bad
