@@ -48,9 +48,12 @@ def test_train_epoch_equals_the_reference_style_per_slide_loop(model):
     slides = _slides([300, 129, 517, 64, 200], 500)
     net_a = _net(case)
     net_b = copy.deepcopy(net_a)
-    # (a) reference-style loop
+    start = {n: p.detach().clone() for n, p in net_a.named_parameters()}
+    # (a) reference-style loop.  SGD, not Adam: the update is linear in the gradient, so the comparison measures the
+    # gradients of the two loops (Adam's normalisation turns rounding-level differences of near-zero gradients --
+    # atomics order, NaCAGaT's batch-wide fp16 scale of dkg -- into full-size steps)
     net_a.eval()
-    opt_a = torch.optim.Adam(net_a.parameters(), lr=2e-4, weight_decay=1e-5)
+    opt_a = torch.optim.SGD(net_a.parameters(), lr=0.05)
     ces = loss_mod.CrossEntropySurvivalLoss(alpha=0.75)
     ref_loss, ref_risk = [], []
     count = 0
@@ -68,15 +71,18 @@ def test_train_epoch_equals_the_reference_style_per_slide_loop(model):
                 opt_a.zero_grad()
         ref_loss.append(ep_loss / len(slides))
     # (b) windowed epochs
-    opt_b = torch.optim.Adam(net_b.parameters(), lr=2e-4, weight_decay=1e-5)
+    opt_b = torch.optim.SGD(net_b.parameters(), lr=0.05)
     runner = tr.EpochRunner(net_b, optimizer=opt_b, loss="ces", grad_acc_step=2)
     got = [runner.train_epoch(slides, train_mode=False) for _ in range(2)]
     assert [g["optimizer_steps"] for g in got] == [2, 3] and runner.pending == 0
     assert np.allclose([g["loss"] for g in got], ref_loss, rtol=2e-5)
     assert np.allclose(np.concatenate([g["risk"] for g in got]), ref_risk, rtol=2e-5)
     assert 0.0 <= got[0]["c_index"] <= 1.0
+    umax = max(float((p.detach() - start[n]).norm()) for n, p in net_a.named_parameters())
     for (n, p), (_, q) in zip(net_a.named_parameters(), net_b.named_parameters()):
-        assert torch.allclose(p, q, rtol=1e-4, atol=2e-6), n
+        da, db = p.detach() - start[n], q.detach() - start[n]
+        err = float((da - db).norm()) / max(float(da.norm()), 1e-5 * umax)
+        assert err < 5e-3, (n, err)
 
 
 def test_validate_and_test_match_per_slide_calls(tmp_path):
