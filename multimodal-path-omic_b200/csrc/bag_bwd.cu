@@ -278,8 +278,30 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       p.part_db[static_cast<size_t>(tt) * kD + ch * 128 + qd * 32 + lane] = __uint_as_float(bv[0]) * inv_gs;
       tc_fence_before();
     };
+    // The per-row scalars of a tile (scores / gate / map gradient, or dg) are plain global loads feeding the head of the
+    // tile's dependency chain: they are issued one tile ahead (while the previous tile's output is being written), and the
+    // tile table is read one tile ahead as well, so no DRAM latency sits between the tiles.
+    float nsc[kQ], npg[kQ], ndm[kQ];
+    auto prefetch_rows = [&](const TileInfo& tn) {
+      const bool v = r < tn.nvalid;
+      const size_t g0 = static_cast<size_t>(tn.row0 + r);
+#pragma unroll
+      for (int i = 0; i < kQ; ++i) {
+        const size_t o = static_cast<size_t>(i) * p.total_rows + g0;
+        if (MODE == kDzNacDkg) {
+          nsc[i] = v ? __ldg(p.dg + o) : 0.f;
+        } else {
+          nsc[i] = v ? __ldg(p.scores + o) : 0.f;
+          npg[i] = (MODE == kDzNacDh && v) ? __ldg(p.pgate + o) : 1.f;
+          ndm[i] = (p.d_amap != nullptr && v) ? __ldg(p.d_amap + o) : 0.f;
+        }
+      }
+    };
+    TileInfo ti_next = t_begin < t_end ? p.tile_info[t_begin] : TileInfo{};
+    if (ch == 0 && t_begin < t_end) prefetch_rows(ti_next);
     for (int t = t_begin; t < t_end; ++t, ++it) {
-      const TileInfo ti = p.tile_info[t];
+      const TileInfo ti = ti_next;
+      if (t + 1 < t_end) ti_next = p.tile_info[t + 1];
       const int buf = it & 1;
       const uint32_t tph = it & 1;
       uint8_t* tile = smem + DzSmem::tile + buf * 65536;
@@ -369,18 +391,14 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         if (MODE == kDzNacDkg) {
 #pragma unroll
           for (int i = 0; i < kQ; ++i) {
-            const float dg = valid ? __ldg(p.dg + static_cast<size_t>(i) * p.total_rows + grow) : 0.f;
+            const float dg = nsc[i];
             c12[i] = dg; c12[6 + i] = 0.f;
             ds[i] = dg * gs;
           }
         } else {
           float sc[kQ], pg[kQ], dmap[kQ];
 #pragma unroll
-          for (int i = 0; i < kQ; ++i) {
-            sc[i] = valid ? __ldg(p.scores + static_cast<size_t>(i) * p.total_rows + grow) : 0.f;
-            pg[i] = (MODE == kDzNacDh && valid) ? __ldg(p.pgate + static_cast<size_t>(i) * p.total_rows + grow) : 1.f;
-            dmap[i] = (p.d_amap != nullptr && valid) ? __ldg(p.d_amap + static_cast<size_t>(i) * p.total_rows + grow) : 0.f;
-          }
+          for (int i = 0; i < kQ; ++i) { sc[i] = nsc[i]; pg[i] = npg[i]; dmap[i] = ndm[i]; }
           mbar_wait(g_bar, tph);
           tc_fence_after();
           uint32_t gv[16];
@@ -473,6 +491,7 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(c_bar);
+      if (ch == 0 && t + 1 < t_end) prefetch_rows(ti_next);     // in flight while this tile's output is written
 
       // ---- output tile, in place over the input tile (row r, column half ch)
       if (kHasB && prev_t >= 0) read_db(prev_t, tph ^ 1);     // before this tile's w_bar arrival lets MMA-db overwrite it
@@ -519,6 +538,9 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           for (int e = 0; e < 8; ++e) {
             const float z = __uint_as_float(v[j + e]);
             if (MODE == kDzNacDkg) o8[e] = (1.f - hh[e] * hh[e]) * z * gs;
+            // NaCAGaT: -0.0 marks a unit masked by ReLU / dropout (bag_dhk_kernel reads the mask from this tile instead
+            // of re-reading the saved activations, 0.27 GB); the +0 addend turns a live unit's exact -0 product into +0
+            else if (MODE == kDzNacDh) o8[e] = hh[e] > 0.f ? fmaf(z, p.keep_scale, 0.f) : -0.f;
             else o8[e] = hh[e] > 0.f ? z * p.keep_scale : 0.f;
           }
           uint4 o;

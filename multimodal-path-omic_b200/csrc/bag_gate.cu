@@ -21,7 +21,8 @@
 
 namespace mpo {
 
-constexpr int kGateThreads = 64 + 256;
+constexpr int kGateThreads = 64 + 256;        // bag_dhk_kernel
+constexpr int kGateFwdThreads = 64 + 512;     // bag_gate_kernel: 16 epilogue warps (a patch row is shared by four threads)
 struct GateSmem {
   static constexpr int A = 0;                          // fp16 tile hi [4 blocks][128 rows][64] SW128   64 KB
   static constexpr int Alo = 65536;                    // fp16 tile lo (h - fp16(h)), same layout        64 KB
@@ -29,8 +30,8 @@ struct GateSmem {
   static constexpr int Pb = W + 65536;                 // fp16 [2][16][64] softmax weights (B operand)  4 KB
   static constexpr int tq = Pb + 4096;                 // fp32 [6][256] tanh(q_i) of the slide          6 KB
   static constexpr int bk = tq + 6144;                 // fp32 [256] key bias                           1 KB
-  static constexpr int spart = bk + 1024;              // fp32 [128][8] gate partials of column half 1  4 KB
-  static constexpr int wred = spart + 4096;            // fp32 [3][4][8] warp partials (max, sum, dropped sum)
+  static constexpr int spart = bk + 1024;              // fp32 [3][128][8] gate partials of column quarters 1..3  12 KB
+  static constexpr int wred = spart + 3 * 4096;        // fp32 [3][4][8] warp partials (max, sum, dropped sum)
   static constexpr int misc = wred + 384;              // fp32 [8] kc_i
   static constexpr int bars = misc + 64;
   static constexpr int tmem_slot = bars + 128;
@@ -53,19 +54,20 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return 1.f - __fdividef(2.f, e + 1.f);
 }
 
-__global__ void __launch_bounds__(kGateThreads, 1)
+__global__ void __launch_bounds__(kGateFwdThreads, 1)
 bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_hlo,
                 const __grid_constant__ CUtensorMap tm_w, const BagGateParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GateSmem::bars);
-  uint64_t* a_full = bars + 1;        // tile (hi and lo) landed
+  uint64_t* a_full = bars + 12;       // [4] K block kb of the tile (hi and lo, 32 KB) landed: the key MMAs of block 0
+                                      //     start while blocks 1..3 are still in flight
   uint64_t* w_full = bars + 8;        // [2] W_k block landed
   uint64_t* w_empty = bars + 10;      // [2] W_k block consumed
   uint64_t* a_empty = bars + 2;       // tile buffer free (pooled MMA retired)
   uint64_t* acc_full = bars + 3;      // K accumulators complete
-  uint64_t* acc_empty = bars + 4;     // epilogue has drained TMEM (8 warp arrivals)
-  uint64_t* p_ready = bars + 5;       // softmax weights written (8 warp arrivals)
+  uint64_t* acc_empty = bars + 4;     // epilogue has drained TMEM (16 warp arrivals)
+  uint64_t* p_ready = bars + 5;       // softmax weights written (16 warp arrivals)
   uint64_t* d_bar = bars + 6;         // pooled MMA retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + GateSmem::tmem_slot);
 
@@ -79,8 +81,9 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_hlo);
     for (int s = 0; s < 2; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    mbar_init(a_full, 1); mbar_init(a_empty, 1); mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 8); mbar_init(p_ready, 8); mbar_init(d_bar, 1);
+    for (int kb = 0; kb < 4; ++kb) mbar_init(&a_full[kb], 1);
+    mbar_init(a_empty, 1); mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 16); mbar_init(p_ready, 16); mbar_init(d_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -97,12 +100,12 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       uint32_t wph = 0;
       for (int t = t_begin; t < t_end; ++t, ++it) {
         mbar_wait(a_empty, (it & 1) ^ 1);
-        mbar_expect_tx(a_full, 131072);
         const int row0 = p.tile_info[t].row0;
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
-          tma_load_2d(smem + GateSmem::A + cb * 16384, &tm_h, a_full, cb * 64, row0, pol_stream);
-          tma_load_2d(smem + GateSmem::Alo + cb * 16384, &tm_hlo, a_full, cb * 64, row0, pol_stream);
+          mbar_expect_tx(&a_full[cb], 32768);
+          tma_load_2d(smem + GateSmem::A + cb * 16384, &tm_h, &a_full[cb], cb * 64, row0, pol_stream);
+          tma_load_2d(smem + GateSmem::Alo + cb * 16384, &tm_hlo, &a_full[cb], cb * 64, row0, pol_stream);
         }
         for (int kb = 0; kb < 4; ++kb) {          // W_k is re-streamed from L2 for every tile, one 64-wide K block at a time
           mbar_wait(&w_empty[ws], wph ^ 1);
@@ -124,8 +127,8 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       for (int t = t_begin; t < t_end; ++t, ++it) {
         const uint32_t ph = it & 1;
         mbar_wait(acc_empty, ph ^ 1);
-        mbar_wait(a_full, ph);
         for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(&a_full[kb], ph);
           mbar_wait(&w_full[ws], wph);
           tc_fence_after();
           const uint32_t wb = aW + ws * 32768;
@@ -166,10 +169,10 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       }
     }
   } else {
-    const int et = threadIdx.x - 64;
-    const int qd = warp & 3;
-    const int ch = (warp - 2) >> 2;
-    const int r = qd * 32 + lane;
+    const int et = threadIdx.x - 64;           // 0..511
+    const int qd = warp & 3;                    // TMEM lane quadrant
+    const int ch = (warp - 2) >> 2;             // column quarter 0..3 (64 key features each)
+    const int r = qd * 32 + lane;               // patch row of the tile
     float* tq_s = reinterpret_cast<float*>(smem + GateSmem::tq);
     float* bk_s = reinterpret_cast<float*>(smem + GateSmem::bk);
     float* spart_s = reinterpret_cast<float*>(smem + GateSmem::spart);
@@ -178,23 +181,34 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
     float* wdrp_s = wmax_s + 64;
     float* kc_s = reinterpret_cast<float*>(smem + GateSmem::misc);
     uint8_t* Pb = smem + GateSmem::Pb;
-    bk_s[et] = p.bias_k[et];
-    for (int o = et * 16; o < 4096; o += 256 * 16) *reinterpret_cast<uint4*>(Pb + o) = make_uint4(0, 0, 0, 0);
+    if (et < kD) bk_s[et] = p.bias_k[et];
+    for (int o = et * 16; o < 4096; o += 512 * 16) *reinterpret_cast<uint4*>(Pb + o) = make_uint4(0, 0, 0, 0);
     const uint32_t seed = p.seed_dev != nullptr ? (p.seed ^ __ldg(p.seed_dev)) : p.seed;
     int cur_slide = -1;
     int it = 0;
+    TileInfo ti_next = t_begin < t_end ? p.tile_info[t_begin] : TileInfo{};
     for (int t = t_begin; t < t_end; ++t, ++it) {
-      const TileInfo ti = p.tile_info[t];
+      const TileInfo ti = ti_next;                 // the tile table is read one tile ahead
+      if (t + 1 < t_end) ti_next = p.tile_info[t + 1];
       const uint32_t ph = it & 1;
+      // raw scores of this tile's rows (written by the projection pass): loaded before the wait for the K accumulators,
+      // so their DRAM latency overlaps the tile load and the key MMAs instead of sitting in front of the soft-max
+      float sraw_pre[kQ];
+      if (ch == 0) {
+        const bool v = r < ti.nvalid;
+#pragma unroll
+        for (int i = 0; i < kQ; ++i)
+          sraw_pre[i] = v ? p.scores[static_cast<size_t>(i) * p.total_rows + static_cast<size_t>(ti.row0 + r)] : 0.f;
+      }
       if (ti.slide != cur_slide) {
         cur_slide = ti.slide;
-        named_bar_sync(1, 256);     // nobody still reads the previous slide's operands
+        named_bar_sync(1, 512);     // nobody still reads the previous slide's operands
         const float* q = p.qp + static_cast<size_t>(ti.slide) * kQ * kD;
 #pragma unroll
-        for (int j = 0; j < kQ; ++j) tq_s[et + j * 256] = tanhf(q[et + j * 256]);
+        for (int j = 0; j < kQ * kD / 512; ++j) tq_s[et + j * 512] = tanhf(q[et + j * 512]);
         if (et < kQ) kc_s[et] = p.kc[ti.slide * kQ + et];
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 512);
 
       mbar_wait(acc_full, ph);
       tc_fence_after();
@@ -204,8 +218,8 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       const size_t grow = static_cast<size_t>(ti.row0 + r);
       const bool valid = r < ti.nvalid;
 #pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const int col0 = ch * 128 + c4 * 32;
+      for (int c4 = 0; c4 < 2; ++c4) {
+        const int col0 = ch * 64 + c4 * 32;
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + kColK + (static_cast<uint32_t>(qd * 32) << 16) + col0, v);
         tmem_ld_wait();
@@ -235,20 +249,24 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
-      if (ch == 1) {
-        *reinterpret_cast<float4*>(spart_s + r * 8) = make_float4(g[0], g[1], g[2], g[3]);
-        *reinterpret_cast<float2*>(spart_s + r * 8 + 4) = make_float2(g[4], g[5]);
+      if (ch != 0) {
+        float* sp = spart_s + (ch - 1) * 1024 + r * 8;
+        *reinterpret_cast<float4*>(sp) = make_float4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<float2*>(sp + 4) = make_float2(g[4], g[5]);
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 512);
       if (ch == 0) {
-        const float4 o0 = *reinterpret_cast<const float4*>(spart_s + r * 8);
-        const float2 o1 = *reinterpret_cast<const float2*>(spart_s + r * 8 + 4);
-        g[0] += o0.x; g[1] += o0.y; g[2] += o0.z; g[3] += o0.w; g[4] += o1.x; g[5] += o1.y;
+#pragma unroll
+        for (int qq = 0; qq < 3; ++qq) {
+          const float4 o0 = *reinterpret_cast<const float4*>(spart_s + qq * 1024 + r * 8);
+          const float2 o1 = *reinterpret_cast<const float2*>(spart_s + qq * 1024 + r * 8 + 4);
+          g[0] += o0.x; g[1] += o0.y; g[2] += o0.z; g[3] += o0.w; g[4] += o1.x; g[5] += o1.y;
+        }
         float sg[kQ];
 #pragma unroll
         for (int i = 0; i < kQ; ++i) {
           const size_t o = static_cast<size_t>(i) * p.total_rows + grow;
-          const float sraw = valid ? p.scores[o] + kc_s[i] : 0.f;
+          const float sraw = valid ? sraw_pre[i] + kc_s[i] : 0.f;
           const float P = 0.5f * (g[i] + 1.f);
           sg[i] = sraw * P;
           if (valid) {
@@ -290,14 +308,14 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 512);
       if (et < kQ) {
         p.part_ml[static_cast<size_t>(t) * 18 + 6 + et] = wsum_s[et] + wsum_s[8 + et] + wsum_s[16 + et] + wsum_s[24 + et];
         p.part_ml[static_cast<size_t>(t) * 18 + 12 + et] = wdrp_s[et] + wdrp_s[8 + et] + wdrp_s[16 + et] + wdrp_s[24 + et];
       }
       mbar_wait(d_bar, ph);
       tc_fence_after();
-      {
+      if (ch < 2) {                  // pooled read-back: feature half ch, 128 features x 12 (hi | lo) query columns
         uint32_t dv[16], dl[16];
         tmem_ld_32x32b_x16(tmem_base + kColP + ch * 16 + (static_cast<uint32_t>(qd * 32) << 16), dv);
         tmem_ld_32x32b_x16(tmem_base + kColPlo + ch * 16 + (static_cast<uint32_t>(qd * 32) << 16), dl);
@@ -325,8 +343,8 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 // dkg arrives as fp16 scaled by the batch-wide power of two gs (bag_bwd.cu); un-scaled here.
 // ------------------------------------------------------------------------------------------------
 struct DhkSmem {
-  static constexpr int A = 0;                          // fp16 dkg tile [4][128][64] SW128; later the bf16 dz tile   64 KB
-  static constexpr int W = 65536;                      // fp16 W_k ring: 2 x ([4 N blocks][64 k rows][64]) SW128     64 KB
+  static constexpr int A = 0;                          // 2 x fp16 dkg tile [4][128][64] SW128; later the bf16 dz tile  128 KB
+  static constexpr int W = 2 * 65536;                  // fp16 W_k ring: 2 x ([4 N blocks][64 k rows][64]) SW128     64 KB
   static constexpr int ones = W + 65536;               // bf16 [2][16][64] row 0 = 1                                 4 KB
   static constexpr int bars = ones + 4096;
   static constexpr int tmem_slot = bars + 128;
@@ -334,20 +352,23 @@ struct DhkSmem {
 };
 constexpr int kDhkSmemBytes = DhkSmem::total + 1024;
 
+// Round 2: the dkg / output tile is double-buffered (the load of tile t + 1 no longer waits for the store of tile t) and
+// every epilogue thread issues ALL of its dz / h loads of a tile before it waits for the accumulators, so their DRAM
+// latency overlaps the tile load and the MMAs (before: plain loads issued at use, long-scoreboard 77 %, 3.45 TB/s).
 __global__ void __launch_bounds__(kGateThreads, 1)
 bag_dhk_kernel(const __grid_constant__ CUtensorMap tm_dkg, const __grid_constant__ CUtensorMap tm_w,
                const __grid_constant__ CUtensorMap tm_dz, const BagDhkParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DhkSmem::bars);
-  uint64_t* a_full = bars;            // dkg tile landed
-  uint64_t* a_empty = bars + 1;       // tile buffer free (2 arrivals: MMA-db retired, store has read it)
-  uint64_t* acc_full = bars + 2;      // dkg W_k complete
-  uint64_t* acc_empty = bars + 3;     // accumulators drained (8 warp arrivals)
-  uint64_t* w_ready = bars + 4;       // dz tile written in place (8 warp arrivals)
-  uint64_t* b_bar = bars + 5;         // MMA-db retired
-  uint64_t* w_full = bars + 6;        // [2]
-  uint64_t* w_empty = bars + 8;       // [2]
+  uint64_t* a_full = bars;            // [2] dkg tile landed
+  uint64_t* a_empty = bars + 2;       // [2] tile buffer free (2 arrivals: MMA-db retired, store has read it)
+  uint64_t* acc_full = bars + 4;      // dkg W_k complete
+  uint64_t* acc_empty = bars + 5;     // accumulators drained (8 warp arrivals)
+  uint64_t* w_ready = bars + 6;       // dz tile written in place (8 warp arrivals)
+  uint64_t* b_bar = bars + 7;         // MMA-db retired
+  uint64_t* w_full = bars + 8;        // [2]
+  uint64_t* w_empty = bars + 10;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DhkSmem::tmem_slot);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = (p.num_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -356,9 +377,11 @@ bag_dhk_kernel(const __grid_constant__ CUtensorMap tm_dkg, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_dkg); tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_dz);
-    mbar_init(a_full, 1); mbar_init(a_empty, 2); mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
-    mbar_init(w_ready, 8); mbar_init(b_bar, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 8); mbar_init(w_ready, 8); mbar_init(b_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 2);
+      mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -382,11 +405,13 @@ bag_dhk_kernel(const __grid_constant__ CUtensorMap tm_dkg, const __grid_constant
       int it = 0, ws = 0;
       uint32_t wph = 0;
       for (int t = t_begin; t < t_end; ++t, ++it) {
-        mbar_wait(a_empty, (it & 1) ^ 1);
-        mbar_expect_tx(a_full, 65536);
+        const int buf = it & 1;
+        mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&a_full[buf], 65536);
         const int row0 = p.tile_info[t].row0;
+        uint8_t* dst = smem + DhkSmem::A + buf * 65536;
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) tma_load_2d(smem + DhkSmem::A + cb * 16384, &tm_dkg, a_full, cb * 64, row0, pol_stream);
+        for (int cb = 0; cb < 4; ++cb) tma_load_2d(dst + cb * 16384, &tm_dkg, &a_full[buf], cb * 64, row0, pol_stream);
         // W_k is read N-major: a ring slot holds the key features e in [64 kb, 64 kb + 64) (the K slice matching
         // A's block kb) for all 256 columns d, as four 64-column N blocks of [64 k rows][128 B]
         for (int kb = 0; kb < 4; ++kb) {
@@ -403,14 +428,17 @@ bag_dhk_kernel(const __grid_constant__ CUtensorMap tm_dkg, const __grid_constant
     if (lane == 0) {
       constexpr uint32_t id_k = umma_idesc(128, 256, 0, 0, 0, 1);     // fp16: A K-major (dkg), B N-major (W_k)
       constexpr uint32_t id_b = umma_idesc(128, 16, 1, 1, 1, 0);      // bf16: A M-major (dz^T), B K-major (ones)
-      const uint32_t aW = smem_u32(smem + DhkSmem::W), aA = smem_u32(smem + DhkSmem::A);
+      const uint32_t aW = smem_u32(smem + DhkSmem::W);
       const uint32_t aOne = smem_u32(smem + DhkSmem::ones);
       int it = 0, ws = 0;
       uint32_t wph = 0;
+      int pending_buf = -1;            // buffer whose TMA store has been issued but not yet waited for
       for (int t = t_begin; t < t_end; ++t, ++it) {
         const uint32_t ph = it & 1;
+        const int buf = it & 1;
+        const uint32_t aA = smem_u32(smem + DhkSmem::A + buf * 65536);
         mbar_wait(acc_empty, ph ^ 1);
-        mbar_wait(a_full, ph);
+        mbar_wait(&a_full[buf], (it >> 1) & 1);
         for (int kb = 0; kb < 4; ++kb) {
           mbar_wait(&w_full[ws], wph);
           tc_fence_after();
@@ -423,13 +451,16 @@ bag_dhk_kernel(const __grid_constant__ CUtensorMap tm_dkg, const __grid_constant
           if (++ws == 2) { ws = 0; wph ^= 1; }
         }
         umma_commit(acc_full);
+        // the previous tile's store has had a whole MMA phase to read its buffer: release it for the tile after this one
+        if (pending_buf >= 0) { tma_store_wait_read(); mbar_arrive(&a_empty[pending_buf]); pending_buf = -1; }
         mbar_wait(w_ready, ph);
         tc_fence_after();
         const TileInfo ti = p.tile_info[t];
         const bool full_tile = ti.nvalid == kTileM;
         if (full_tile) {
 #pragma unroll
-          for (int cb = 0; cb < 4; ++cb) tma_store_2d(&tm_dz, smem + DhkSmem::A + cb * 16384, cb * 64, ti.row0);
+          for (int cb = 0; cb < 4; ++cb)
+            tma_store_2d(&tm_dz, smem + DhkSmem::A + buf * 65536 + cb * 16384, cb * 64, ti.row0);
           tma_store_commit();
         }
 #pragma unroll
@@ -439,10 +470,10 @@ bag_dhk_kernel(const __grid_constant__ CUtensorMap tm_dkg, const __grid_constant
             umma_bf16(tmem_base + kColB + mh * 16, umma_desc_sw128(aA + mh * 2 * 16384 + kk * 2048, 16384, 1024),
                       umma_desc_sw128(aOne + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), id_b, kk != 0 ? 1u : 0u);
         umma_commit(b_bar);
-        umma_commit(a_empty);
-        if (full_tile) tma_store_wait_read();
-        mbar_arrive(a_empty);
+        umma_commit(&a_empty[buf]);
+        if (full_tile) pending_buf = buf; else mbar_arrive(&a_empty[buf]);
       }
+      if (pending_buf >= 0) { tma_store_wait_read(); mbar_arrive(&a_empty[pending_buf]); }
     }
   } else {
     const int qd = warp & 3;
@@ -461,39 +492,50 @@ bag_dhk_kernel(const __grid_constant__ CUtensorMap tm_dkg, const __grid_constant
       p.part_db[static_cast<size_t>(tt) * kD + ch * 128 + qd * 32 + lane] = __uint_as_float(bv[0]);
       tc_fence_before();
     };
+    // This thread's 256 B of the incoming dz tile (value path of the gradient; a unit masked by ReLU / dropout arrives as
+    // -0.0, see bag_bwd_dz_kernel<kDzNacDh>) live in registers one tile AHEAD: each 64 B group is re-loaded for the next tile
+    // as soon as the current tile has consumed it, so the loads are in flight during a whole tile's MMAs and epilogue.
+    auto row_ptr = [&](const TileInfo& tn) {
+      // rows past the end of the packed bag do not exist in the global buffers: clamp the address, mask the value
+      return reinterpret_cast<const uint4*>(p.dz + static_cast<size_t>(min(tn.row0 + r, p.total_rows - 1)) * kD + ch * 128);
+    };
+    TileInfo ti_next = t_begin < t_end ? p.tile_info[t_begin] : TileInfo{};
+    uint4 zin[16];
+    if (t_begin < t_end) {
+      const uint4* zp0 = row_ptr(ti_next);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) zin[q] = zp0[q];
+    }
     for (int t = t_begin; t < t_end; ++t, ++it) {
-      const TileInfo ti = p.tile_info[t];
+      const TileInfo ti = ti_next;
+      const bool has_next = t + 1 < t_end;
+      if (has_next) ti_next = p.tile_info[t + 1];
       const uint32_t ph = it & 1;
       const bool valid = r < ti.nvalid;
       const bool direct = ti.nvalid != kTileM;
-      // rows past the end of the packed bag do not exist in the global buffers: clamp the address, mask the value
       const size_t grow = static_cast<size_t>(min(ti.row0 + r, p.total_rows - 1));
-      const uint4* zp = reinterpret_cast<const uint4*>(p.dz + grow * kD + ch * 128);
-      const uint4* hp = reinterpret_cast<const uint4*>(p.h + grow * kD + ch * 128);
       if (prev_t >= 0) read_db(prev_t, ph ^ 1);
       mbar_wait(acc_full, ph);
       tc_fence_after();
-      uint8_t* tile = smem + DhkSmem::A;
-#pragma unroll 1
+      const uint4* zn = row_ptr(ti_next);
+      uint8_t* tile = smem + DhkSmem::A + (it & 1) * 65536;
+#pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
         const int col0 = ch * 128 + c4 * 32;
-        uint4 zin[4], hin[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { zin[q] = zp[c4 * 4 + q]; hin[q] = hp[c4 * 4 + q]; }
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + kColZ + (static_cast<uint32_t>(qd * 32) << 16) + col0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j = q * 8;
-          const uint32_t zi[4] = {zin[q].x, zin[q].y, zin[q].z, zin[q].w};
-          const uint32_t hi_[4] = {hin[q].x, hin[q].y, hin[q].z, hin[q].w};
+          const uint4 zq = zin[c4 * 4 + q];
+          const uint32_t zi[4] = {zq.x, zq.y, zq.z, zq.w};
           uint32_t ow[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 hh = unpack_f16x2(hi_[e]);
-            const float z0 = bf16lo_to_f32(zi[e]) + (hh.x > 0.f ? __uint_as_float(v[j + 2 * e]) * ks : 0.f);
-            const float z1 = bf16hi_to_f32(zi[e]) + (hh.y > 0.f ? __uint_as_float(v[j + 2 * e + 1]) * ks : 0.f);
+            const bool live0 = (zi[e] & 0xFFFFu) != 0x8000u, live1 = (zi[e] >> 16) != 0x8000u;
+            const float z0 = live0 ? bf16lo_to_f32(zi[e]) + __uint_as_float(v[j + 2 * e]) * ks : 0.f;
+            const float z1 = live1 ? bf16hi_to_f32(zi[e]) + __uint_as_float(v[j + 2 * e + 1]) * ks : 0.f;
             ow[e] = valid ? pack_bf16x2(z0, z1) : 0u;
           }
           const uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
@@ -501,6 +543,10 @@ bag_dhk_kernel(const __grid_constant__ CUtensorMap tm_dkg, const __grid_constant
           const int cb = j16 >> 3, jj = j16 & 7;
           *reinterpret_cast<uint4*>(tile + cb * 16384 + r * 128 + ((jj ^ (r & 7)) << 4)) = o;
           if (direct && valid) *reinterpret_cast<uint4*>(p.dz + grow * kD + col0 + j) = o;
+        }
+        if (has_next) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) zin[c4 * 4 + q] = zn[c4 * 4 + q];
         }
       }
       tc_fence_before();
@@ -541,7 +587,7 @@ cudaError_t launch_bag_gate(const CUtensorMap& tm_h, const CUtensorMap& tm_hlo, 
   }
   if (prm.num_tiles <= 0) return cudaSuccess;
   const int grid = prm.num_tiles < num_sms ? prm.num_tiles : num_sms;
-  bag_gate_kernel<<<grid, kGateThreads, kGateSmemBytes, stream>>>(tm_h, tm_hlo, tm_w, prm);
+  bag_gate_kernel<<<grid, kGateFwdThreads, kGateSmemBytes, stream>>>(tm_h, tm_hlo, tm_w, prm);
   count_launch();
   return cudaGetLastError();
 }

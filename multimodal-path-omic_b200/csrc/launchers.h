@@ -14,6 +14,7 @@ extern unsigned long long g_launches;   // kernels launched by this library sinc
 inline void count_launch(int n = 1) { g_launches += n; }
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows);
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows);
 int fwd_cluster_size();   // CTAs per cluster of the forward bag kernel (1, 2 or 4; env MPO_FWD_CLUSTER)
 cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const CUtensorMap& tm_h,
                            const BagFwdParams& prm, int num_sms, cudaStream_t stream);
@@ -34,6 +35,13 @@ cudaError_t launch_bag_bwd_dwz(const CUtensorMap& tm_x, const CUtensorMap& tm_sc
                                cudaStream_t stream);
 int bag_bwd_dwz_max_clusters(int num_sms);
 size_t bag_bwd_dwz_scratch_bytes(int clusters);
+// fp32-accurate tcgen05 GEMM on bf16 (hi, lo) operand pairs (tc_gemm.cu)
+struct DropSpec;      // tail_dev.cuh
+cudaError_t launch_split_bf16(const float* src, long long ld, int rows, int cols, void* hi, void* lo, int pitch,
+                              cudaStream_t stream, const DropSpec* drop = nullptr, uint32_t base = 0);
+int launch_tc_gemm(const void* a_hi, const void* a_lo, int a_rows, int a_pitch, bool a_mn, const void* b_hi, const void* b_lo,
+                   int b_rows, int b_pitch, bool b_mn, float* C, long long ldc, int M, int N, int K, float alpha, bool accumulate,
+                   cudaStream_t stream);
 cudaError_t launch_bag_bwd_dkc(const int* tile_prefix, const float* part_dkc, float* dkc, int B, cudaStream_t stream);
 
 }  // namespace mpo

@@ -259,6 +259,8 @@ __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, const vo
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores of this thread have finished READING their shared-memory source
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// at most one committed bulk store of this thread may still be reading its shared-memory source
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
 // UMMA descriptors (sm_100 SmemDescriptor v1 / InstrDescriptor; field positions per the PTX ISA

@@ -418,6 +418,7 @@ struct GeWs {
   long long pa, pb, pab, pw, hp, h, logits;
   long long dlogits, dh, dzr, dhp, dw, dA, dab, t0, dx, dr2, df, dy1, dr1, dctx, dqkv, dP, dmid, dH, dzf;
   long long dP2, dmk1, dmk2;      // train mode: dropped probabilities of one head; gradients behind dropout1 / dropout2
+  long long tcA, tcS[4];          // bf16 (hi, lo) operand pairs of the tensor-core GEMMs: one N x N operand, four N x 256 ones
   long long total;
 };
 void ge_layout(long long N, GeWs& w) {
@@ -434,15 +435,60 @@ void ge_layout(long long N, GeWs& w) {
   w.dx = A(N * E); w.dr2 = A(N * E); w.df = A(N * FF); w.dy1 = A(N * E); w.dr1 = A(N * E); w.dctx = A(N * E);
   w.dqkv = A(N * 3 * E); w.dP = A(N * N); w.dmid = A(N * E); w.dH = A(N * E); w.dzf = A(N * E);
   w.dP2 = A(N * N); w.dmk1 = A(N * E); w.dmk2 = A(N * E);
+  const long long Np = (N + 63) / 64 * 64;
+  w.tcA = A(N * Np);                                   // 2 x [N][Np] bf16 = N * Np floats
+  for (int i = 0; i < 4; ++i) w.tcS[i] = A(N * E);     // 2 x [N][256] bf16 = N * 256 floats
   w.total = off;
 }
 // multi-head attention over N tokens from a packed [N, 3E] projection: probs [nh][N][N], ctx [N, E]
+// The bag-scale products of the attention run on tcgen05 (tc_gemm.cu: bf16 hi/lo operand pairs, three MMAs per K step,
+// fp32 accumulation); MPO_GE_TC=0 keeps the fp32 CUDA-core GEMMs (gemm_big_kernel) for comparison.
+bool ge_use_tc() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MPO_GE_TC"); on = e ? atoi(e) : 1; }
+  return on != 0;
+}
+struct TcOp { void* hi; void* lo; int rows, pitch; };
+// splits a strided fp32 matrix [rows x cols] into the bf16 pair living at float offset `off` of the workspace
+// drop / base: the split applies the attention-probability dropout on the fly (element index base + row * cols + col)
+TcOp tc_split(Ctx& c, float* ws, long long off, const float* src, long long ld, int rows, int cols,
+              const DropSpec* drop = nullptr, uint32_t base = 0) {
+  TcOp o;
+  o.rows = rows; o.pitch = (cols + 63) / 64 * 64;
+  o.hi = ws + off;
+  o.lo = reinterpret_cast<__nv_bfloat16*>(ws + off) + static_cast<long long>(rows) * o.pitch;
+  c.chk(launch_split_bf16(src, ld, rows, cols, o.hi, o.lo, o.pitch, c.st, drop, base), "ge.split");
+  return o;
+}
+void tc_gemm(Ctx& c, const TcOp& a, bool a_mn, const TcOp& b, bool b_mn, float* C, long long ldc, int M, int Nn, int K,
+             float alpha) {
+  if (c.err != cudaSuccess) return;
+  if (launch_tc_gemm(a.hi, a.lo, a.rows, a.pitch, a_mn, b.hi, b.lo, b.rows, b.pitch, b_mn, C, ldc, M, Nn, K, alpha, false, c.st) != 0)
+    c.chk(cudaErrorUnknown, "ge.tc_gemm");
+}
+
 // drop / pdrop: attention-probability dropout (train mode); the stored probabilities stay un-dropped (the soft-max
 // backward needs them), the dropped copy of one head lives in the scratch `pdrop` while its context GEMM runs
-void ge_attn_fwd(Ctx& c, const float* qkv, float* probs, float* ctx, int N, int nh, const DropSpec drop = DropSpec{},
-                 float* pdrop = nullptr) {
+void ge_attn_fwd(Ctx& c, const GeWs& w, float* ws, const float* qkv, float* probs, float* ctx, int N, int nh,
+                 const DropSpec drop = DropSpec{}, float* pdrop = nullptr) {
   const int hd = E / nh;
   const float scale = 1.f / sqrtf(static_cast<float>(hd));
+  if (ge_use_tc()) {
+    for (int h = 0; h < nh; ++h) {
+      float* P = probs + (long long)h * N * N;
+      const TcOp sQ = tc_split(c, ws, w.tcS[0], qkv + h * hd, 3 * E, N, hd);
+      const TcOp sK = tc_split(c, ws, w.tcS[1], qkv + E + h * hd, 3 * E, N, hd);
+      tc_gemm(c, sQ, false, sK, false, P, N, N, N, hd, scale);                      // S = Q K^T / sqrt(hd)
+      launch_k(row_softmax_kernel, dim3(N), dim3(256), 0, c.st, P, (long long)N, N); count_launch();
+      // train mode: the dropped probabilities exist only as the bf16 operand pair (mask regenerated inside the split)
+      const TcOp sP = tc_split(c, ws, w.tcA, P, N, N, N, &drop,
+                               static_cast<uint32_t>(h) * static_cast<uint32_t>(N) * static_cast<uint32_t>(N));
+      const TcOp sV = tc_split(c, ws, w.tcS[2], qkv + 2 * E + h * hd, 3 * E, N, hd);   // [tokens][hd]: N-major B
+      tc_gemm(c, sP, false, sV, true, ctx + h * hd, E, N, hd, N, 1.f);              // ctx_h = P V_h
+    }
+    c.chk(cudaGetLastError(), "ge_attn_fwd (tc)");
+    return;
+  }
   for (int h = 0; h < nh; ++h) {
     float* P = probs + (long long)h * N * N;
     GemmArgs s{qkv + h * hd, 3 * E, 1, qkv + E + h * hd, 1, 3 * E, P, N, nullptr, N, N, hd, scale, 0, ACT_NONE, nullptr};
@@ -459,10 +505,34 @@ void ge_attn_fwd(Ctx& c, const float* qkv, float* probs, float* ctx, int N, int 
   c.chk(cudaGetLastError(), "ge_attn_fwd");
 }
 // dctx [N, E] -> dqkv [N, 3E]; dP is an [N, N] scratch
-void ge_attn_bwd(Ctx& c, const float* qkv, const float* probs, const float* dctx, float* dP, float* dqkv, int N, int nh,
-                 const DropSpec drop = DropSpec{}, float* pdrop = nullptr) {
+void ge_attn_bwd(Ctx& c, const GeWs& w, float* ws, const float* qkv, const float* probs, const float* dctx, float* dP,
+                 float* dqkv, int N, int nh, const DropSpec drop = DropSpec{}, float* pdrop = nullptr) {
   const int hd = E / nh;
   const float scale = 1.f / sqrtf(static_cast<float>(hd));
+  if (ge_use_tc()) {
+    for (int h = 0; h < nh; ++h) {
+      const float* P = probs + (long long)h * N * N;
+      const uint32_t base = static_cast<uint32_t>(h) * static_cast<uint32_t>(N) * static_cast<uint32_t>(N);
+      const TcOp sD = tc_split(c, ws, w.tcS[3], dctx + h * hd, E, N, hd);
+      const TcOp sV = tc_split(c, ws, w.tcS[2], qkv + 2 * E + h * hd, 3 * E, N, hd);
+      tc_gemm(c, sD, false, sV, false, dP, N, N, N, hd, 1.f);                       // dP' = dctx_h V_h^T
+      const TcOp sP = tc_split(c, ws, w.tcA, P, N, N, N, &drop, base);              // P' = dropout(P), regenerated
+      tc_gemm(c, sP, true, sD, true, dqkv + 2 * E + h * hd, 3 * E, N, hd, N, 1.f);  // dV_h = P'^T dctx_h (P' read M-major)
+      if (drop.thr != 0) {
+        launch_k(row_softmax_bwd_drop_kernel, dim3(N), dim3(256), 0, c.st, P, (long long)N, dP, (long long)N, N, scale, base,
+                 drop); count_launch();
+      } else {
+        launch_k(row_softmax_bwd_kernel, dim3(N), dim3(256), 0, c.st, P, (long long)N, dP, (long long)N, N, scale); count_launch();
+      }
+      const TcOp sS = tc_split(c, ws, w.tcA, dP, N, N, N);                          // dS (reuses the N x N operand slot)
+      const TcOp sK = tc_split(c, ws, w.tcS[1], qkv + E + h * hd, 3 * E, N, hd);
+      const TcOp sQ = tc_split(c, ws, w.tcS[0], qkv + h * hd, 3 * E, N, hd);
+      tc_gemm(c, sS, false, sK, true, dqkv + h * hd, 3 * E, N, hd, N, 1.f);         // dQ_h = dS K_h
+      tc_gemm(c, sS, true, sQ, true, dqkv + E + h * hd, 3 * E, N, hd, N, 1.f);      // dK_h = dS^T Q_h (dS read M-major)
+    }
+    c.chk(cudaGetLastError(), "ge_attn_bwd (tc)");
+    return;
+  }
   for (int h = 0; h < nh; ++h) {
     const float* P = probs + (long long)h * N * N;
     const uint32_t base = static_cast<uint32_t>(h) * static_cast<uint32_t>(N) * static_cast<uint32_t>(N);
@@ -496,7 +566,7 @@ void ge_attn_bwd(Ctx& c, const float* qkv, const float* probs, const float* dctx
 void ge_enc_fwd(Ctx& c, const mpo_encoder_layer& P, const GeEnc& b, const GeWs& w, float* ws, const float* x, int N, int l) {
   const uint32_t s0 = SITE_ENC + 4 * l;
   lin_fwd(c, x, E, P.in_proj, 3 * E, E, ws + b.qkv, 3 * E, N, ACT_NONE);
-  ge_attn_fwd(c, ws + b.qkv, ws + b.probs, ws + b.ctx, N, 8, mk_drop(c, c.drop_p, s0), ws + w.dP2);
+  ge_attn_fwd(c, w, ws, ws + b.qkv, ws + b.probs, ws + b.ctx, N, 8, mk_drop(c, c.drop_p, s0), ws + w.dP2);
   lin_fwd(c, ws + b.ctx, E, P.out_proj, E, E, ws + b.sa, E, N, ACT_NONE, mk_drop(c, c.drop_p, s0 + 1));
   ln_fwd(c, x, ws + b.sa, P.norm1, ws + b.y1, ws + b.xh1, ws + b.rs1, N);
   lin_fwd(c, ws + b.y1, E, P.linear1, FF, E, ws + b.f, FF, N, ACT_RELU, mk_drop(c, c.drop_p, s0 + 2));
@@ -528,7 +598,7 @@ void ge_enc_bwd(Ctx& c, const mpo_encoder_layer& P, const GeEnc& b, const GeWs& 
     ln_bwd(c, ws + w.dy1, P.norm1, ws + b.xh1, ws + b.rs1, ws + w.dr1, N);
   }
   lin_bwd(c, dsa, E, ws + b.ctx, E, P.out_proj, E, E, ws + w.dctx, E, N, false);
-  ge_attn_bwd(c, ws + b.qkv, ws + b.probs, ws + w.dctx, ws + w.dP, ws + w.dqkv, N, 8, mk_drop(c, c.drop_p, s0), ws + w.dP2);
+  ge_attn_bwd(c, w, ws, ws + b.qkv, ws + b.probs, ws + w.dctx, ws + w.dP, ws + w.dqkv, N, 8, mk_drop(c, c.drop_p, s0), ws + w.dP2);
   lin_bwd(c, ws + w.dqkv, 3 * E, x, E, P.in_proj, 3 * E, E, dx_out, E, N, false);
   add(c, dx_out, ws + w.dr1, dx_out, n);
 }
@@ -902,7 +972,7 @@ int mpo_ge_fwd(const mpo_ge_model* m, int64_t N64, const void* h_hi, const void*
            ws + w.H, n); count_launch();
   // self-attention over the patches, one head (ge_nacagat.py:27,49); the averaged map IS the head's map
   lin_fwd(c, ws + w.H, E, m->sa_in, 3 * E, E, ws + w.sa_qkv, 3 * E, N, ACT_NONE);
-  ge_attn_fwd(c, ws + w.sa_qkv, attn, ws + w.sa_ctx, N, 1);
+  ge_attn_fwd(c, w, ws, ws + w.sa_qkv, attn, ws + w.sa_ctx, N, 1);
   lin_fwd(c, ws + w.sa_ctx, E, m->sa_out, E, E, ws + w.sa_out, E, N, ACT_NONE);
   // encoder over the N tokens (ge_nacagat.py:30-32,53)
   ge_enc_fwd(c, m->tr[0], w.enc[0], w, ws, ws + w.sa_out, N, 0);
@@ -975,7 +1045,7 @@ int mpo_ge_bwd(const mpo_ge_model* m, const mpo_bag* bag, const void* h_hi, floa
   ge_enc_bwd(c, m->tr[0], w.enc[0], w, ws, ws + w.sa_out, ws + w.dmid, ws + w.dx, N, 0);
   // self-attention
   lin_bwd(c, ws + w.dx, E, ws + w.sa_ctx, E, m->sa_out, E, E, ws + w.dctx, E, N, false);
-  ge_attn_bwd(c, ws + w.sa_qkv, attn, ws + w.dctx, ws + w.dP, ws + w.dqkv, N, 1);
+  ge_attn_bwd(c, w, ws, ws + w.sa_qkv, attn, ws + w.dctx, ws + w.dP, ws + w.dqkv, N, 1);
   lin_bwd(c, ws + w.dqkv, 3 * E, ws + w.H, E, m->sa_in, 3 * E, E, ws + w.dH, E, N, false);
   // H projection: dz = dH * mask; db_H += colsum(dz); dW_H += dz^T X on the tensor cores
   launch_k(ge_dz_kernel, dim3(nblk(n)), dim3(256), 0, c.st, ws + w.dH, static_cast<const __half*>(h_hi), keep_scale,

@@ -1693,6 +1693,181 @@ __global__ void __launch_bounds__(NT, 1) snn_bwd_kernel(const __grid_constant__ 
   cluster_sync();
 }
 
+// ------------------------------------------------------------------------------------------------ SNN encoders, wide form
+// Round 2.  The cluster form above runs 48 CTAs through a 3-deep ring of 16 KB weight chunks and three cluster barriers:
+// 35 + 28 us per step for 3.6 MB of weights (latency-bound, 5 % of the issue slots).  Here one layer of the six encoders is
+// ONE plain launch of 16 x 6 CTAs per 32 slides: a CTA owns 16 output columns of one omic group, fetches its whole weight
+// slice and the 32 input rows with one burst of 16-byte cp.async (everything in flight at once, one wait), splits the
+// reduction over its 8 warps (lane = slide row, float4 along the reduction, weights as broadcast LDS.128) and finishes
+// with a cross-warp sum and the fused epilogue (bias, ELU, AlphaDropout with the same (site, element) indices as the
+// cluster form, so both forms produce identical masks).  Forward = two launches, backward = one.
+constexpr int SNN2_COLS = 16;
+constexpr int SNN2_RP = 20;                 // padded pitch of one row's 16 partial sums (conflict-free float4 stores)
+struct Snn2Params {
+  const float* x[MPO_Q];                    // forward: input rows [B][ldx].  backward: unused
+  const float* w[MPO_Q];                    // forward: layer weight [256][K].  backward: layer-2 weight [256][256]
+  const float* bias[MPO_Q];
+  int K[MPO_Q], ldx[MPO_Q];
+  float* ws;
+  int off_out[MPO_Q];                       // forward: first output element of the group; backward: snn_dz1
+  int out_ld;                               // floats between two slides of the output (E, or 6 E for G_bag)
+  int off_snn_h[MPO_Q], off_snn_dz2[MPO_Q], off_G, off_dG;
+  int site_add;                             // 0: layer 1, 1: layer 2
+  DropSpec d_alpha;
+  int B;
+};
+__host__ __device__ constexpr int snn2_kp(int K) { return ((K + 31) / 32) * 32 + 4; }       // row pitch = 4 (mod 32) floats
+constexpr int SNN2_SMEM_FLOATS = (SNN_ROWS + SNN2_COLS) * snn2_kp(OMIC_LD) + NW * SNN_ROWS * SNN2_RP;
+static_assert(SNN2_SMEM_FLOATS * sizeof(float) <= 227 * 1024, "SNN (wide form) shared memory");
+
+// acc[j] += sum over this warp's share of the reduction of X[lane][r] * W[j][r]
+__device__ __forceinline__ void snn2_dot(const float* Xs, const float* Wsm, int kp, int K, int warp, int lane, float (&acc)[SNN2_COLS]) {
+  const int groups = K >> 2;                               // float4 groups of the reduction
+  const float4* xr = reinterpret_cast<const float4*>(Xs + lane * kp);
+  for (int g = warp; g < groups; g += NW) {
+    const float4 xv = xr[g];
+#pragma unroll
+    for (int j = 0; j < SNN2_COLS; ++j) {
+      const float4 wv = *reinterpret_cast<const float4*>(Wsm + j * kp + 4 * g);
+      acc[j] = fmaf(xv.x, wv.x, acc[j]); acc[j] = fmaf(xv.y, wv.y, acc[j]);
+      acc[j] = fmaf(xv.z, wv.z, acc[j]); acc[j] = fmaf(xv.w, wv.w, acc[j]);
+    }
+  }
+}
+__device__ __forceinline__ void snn2_store_partials(float* red, int warp, int lane, const float (&acc)[SNN2_COLS]) {
+  float4* dst = reinterpret_cast<float4*>(red + (warp * SNN_ROWS + lane) * SNN2_RP);
+#pragma unroll
+  for (int q = 0; q < SNN2_COLS / 4; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+}
+__device__ __forceinline__ float snn2_sum_partials(const float* red, int s, int j) {
+  float v = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) v += red[(w * SNN_ROWS + s) * SNN2_RP + j];
+  return v;
+}
+
+__global__ void __launch_bounds__(NT, 1) snn2_fwd_kernel(const __grid_constant__ Snn2Params P) {
+  extern __shared__ __align__(16) float sm[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int om = blockIdx.y, col0 = blockIdx.x * SNN2_COLS, s0 = blockIdx.z * SNN_ROWS;
+  const int K = P.K[om], kp = snn2_kp(K), ldx = P.ldx[om];
+  float* Xs = sm;                              // [32][kp]
+  float* Wsm = Xs + SNN_ROWS * kp;             // [16][kp]
+  float* red = Wsm + SNN2_COLS * kp;           // [8][32][SNN2_RP]
+  const int g4 = K >> 2;
+  const float* xg = P.x[om];
+  const float* wg = P.w[om] + static_cast<size_t>(col0) * K;
+  for (int i = t; i < SNN_ROWS * g4; i += NT) {
+    const int s = i / g4, g = i - s * g4;
+    if (s0 + s < P.B) cp_async16(Xs + s * kp + 4 * g, xg + static_cast<size_t>(s0 + s) * ldx + 4 * g);
+    else *reinterpret_cast<float4*>(Xs + s * kp + 4 * g) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int i = t; i < SNN2_COLS * g4; i += NT) {
+    const int j = i / g4, g = i - j * g4;
+    cp_async16(Wsm + j * kp + 4 * g, wg + static_cast<size_t>(j) * K + 4 * g);
+  }
+  cp_async_commit();
+  const uint32_t seedv = drop_seed(P.d_alpha);
+  const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * om + P.site_add);
+  cp_async_wait<0>();
+  __syncthreads();
+  float acc[SNN2_COLS];
+#pragma unroll
+  for (int j = 0; j < SNN2_COLS; ++j) acc[j] = 0.f;
+  snn2_dot(Xs, Wsm, kp, K, warp, lane, acc);
+  snn2_store_partials(red, warp, lane, acc);
+  __syncthreads();
+  float* out = P.ws + P.off_out[om];
+#pragma unroll
+  for (int i = 0; i < SNN_ROWS * SNN2_COLS / NT; ++i) {
+    const int idx = t + i * NT, s = idx / SNN2_COLS, j = idx % SNN2_COLS, col = col0 + j, slide = s0 + s;
+    if (slide >= P.B) continue;
+    float v = elu_f(snn2_sum_partials(red, s, j) + __ldg(P.bias[om] + col));
+    if (ds.thr != 0) v = drop_fwd(v, ds, seedv, static_cast<uint32_t>(slide) * E + col);
+    out[static_cast<size_t>(slide) * P.out_ld + col] = v;
+  }
+}
+
+// dG -> dz2 (stored) -> dh1 = dz2 W2 -> dz1 (stored); a CTA owns 16 columns of dz2 (store) and of dz1
+__global__ void __launch_bounds__(NT, 1) snn2_bwd_kernel(const __grid_constant__ Snn2Params P) {
+  extern __shared__ __align__(16) float sm[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int om = blockIdx.y, col0 = blockIdx.x * SNN2_COLS, s0 = blockIdx.z * SNN_ROWS;
+  constexpr int kp = snn2_kp(E);
+  float* Xs = sm;                              // [32][kp]  dG, then dz2
+  float* Wsm = Xs + SNN_ROWS * kp;             // [16][kp]  Wsm[j][c] = W2[c][col0 + j]
+  float* red = Wsm + SNN2_COLS * kp;           // [8][32][SNN2_RP]; first holds the raw G_bag rows [32][kp]
+  float* Gs = red;
+  static_assert(NW * SNN_ROWS * SNN2_RP <= SNN_ROWS * snn2_kp(E), "the partial sums alias the staged G rows");
+  static_assert((2 * SNN_ROWS + SNN2_COLS) * snn2_kp(E) <= SNN2_SMEM_FLOATS, "SNN backward shared memory");
+  float* ws = P.ws;
+  constexpr int g4 = E / 4;
+  for (int i = t; i < SNN_ROWS * g4; i += NT) {
+    const int s = i / g4, g = i - s * g4, slide = s0 + s;
+    if (slide < P.B) {
+      const size_t o = static_cast<size_t>(slide * 6 + om) * E + 4 * g;
+      cp_async16(Xs + s * kp + 4 * g, ws + P.off_dG + o);
+      cp_async16(Gs + s * kp + 4 * g, ws + P.off_G + o);
+    } else {
+      *reinterpret_cast<float4*>(Xs + s * kp + 4 * g) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(Gs + s * kp + 4 * g) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  cp_async_commit();
+  // transposed slice of W2: 64-byte row pieces, scattered into the [j][c] layout
+  const float* w2 = P.w[om];
+  float wreg[SNN2_COLS * E / NT];
+#pragma unroll
+  for (int i = 0; i < SNN2_COLS * E / NT; ++i) {
+    const int idx = t + i * NT, c = idx / SNN2_COLS, j = idx % SNN2_COLS;
+    wreg[i] = __ldg(w2 + static_cast<size_t>(c) * E + col0 + j);
+  }
+  // hidden-layer outputs of this CTA's 16 columns (for the ELU / dropout derivative of dz1)
+  float hv[SNN_ROWS * SNN2_COLS / NT];
+#pragma unroll
+  for (int i = 0; i < SNN_ROWS * SNN2_COLS / NT; ++i) {
+    const int idx = t + i * NT, s = idx / SNN2_COLS, j = idx % SNN2_COLS, slide = s0 + s;
+    hv[i] = slide < P.B ? __ldcg(ws + P.off_snn_h[om] + static_cast<size_t>(slide) * E + col0 + j) : 0.f;
+  }
+  const uint32_t seedv = drop_seed(P.d_alpha);
+  const DropSpec ds2 = site_of(P.d_alpha, SITE_SNN + 2 * om + 1), ds1 = site_of(P.d_alpha, SITE_SNN + 2 * om);
+#pragma unroll
+  for (int i = 0; i < SNN2_COLS * E / NT; ++i) {
+    const int idx = t + i * NT, c = idx / SNN2_COLS, j = idx % SNN2_COLS;
+    Wsm[j * kp + c] = wreg[i];
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  for (int idx = t; idx < SNN_ROWS * E; idx += NT) {
+    const int s = idx / E, c = idx - s * E, slide = s0 + s;
+    float g = Xs[s * kp + c], y = Gs[s * kp + c];
+    if (ds2.thr != 0) { g *= drop_grad(ds2, seedv, static_cast<uint32_t>(slide) * E + c); y = drop_invert(y, ds2); }
+    g *= elu_d(y);
+    if (slide >= P.B) g = 0.f;
+    Xs[s * kp + c] = g;
+    if (slide < P.B && (c / SNN2_COLS) == static_cast<int>(blockIdx.x))
+      ws[P.off_snn_dz2[om] + static_cast<size_t>(slide) * E + c] = g;
+  }
+  __syncthreads();                             // dz2 complete, G rows no longer needed (red aliases them)
+  float acc[SNN2_COLS];
+#pragma unroll
+  for (int j = 0; j < SNN2_COLS; ++j) acc[j] = 0.f;
+  snn2_dot(Xs, Wsm, kp, E, warp, lane, acc);
+  __syncthreads();
+  snn2_store_partials(red, warp, lane, acc);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < SNN_ROWS * SNN2_COLS / NT; ++i) {
+    const int idx = t + i * NT, s = idx / SNN2_COLS, j = idx % SNN2_COLS, col = col0 + j, slide = s0 + s;
+    if (slide >= P.B) continue;
+    float v = snn2_sum_partials(red, s, j);
+    float y = hv[i];
+    if (ds1.thr != 0) { v *= drop_grad(ds1, seedv, static_cast<uint32_t>(slide) * E + col); y = drop_invert(y, ds1); }
+    v *= elu_d(y);
+    ws[P.off_out[om] + static_cast<size_t>(slide) * E + col] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ weight gradients
 // kind 0: gw[o][i] += alpha * sum_r dz[r][o] x[r][i]  and  gb[o] += sum_r dz[r][o]     (64 x 64 tiles)
 // kind 1: LayerNorm: gw[c] += sum_r dz[r][c] x[r][c]  and  gb[c] += sum_r dz[r][c]     (64-column tiles)
@@ -1927,12 +2102,66 @@ static void fill_snn(const mpo_model* m, const mpo_tail_io* io, const Ws& w, Snn
   P.B = io->num_slides;
 }
 
+// wide form of the SNN kernels (default); MPO_TAIL_SNN_FORM=cluster keeps the 8-CTA cluster kernels
+static bool snn_wide() {
+  const char* env = getenv("MPO_TAIL_SNN_FORM");
+  return !(env != nullptr && strcmp(env, "cluster") == 0);
+}
+static void fill_snn2(const mpo_model* m, const mpo_tail_io* io, const Ws& w, Snn2Params& P, int layer, bool backward) {
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < MPO_Q; ++i) {
+    P.off_snn_h[i] = static_cast<int>(w.snn_h[i]);
+    P.off_snn_dz2[i] = static_cast<int>(w.snn_dz2[i]);
+    if (backward) {
+      P.w[i] = m->snn[i][1].w; P.K[i] = E; P.ldx[i] = E;
+      P.off_out[i] = static_cast<int>(w.snn_dz1[i]);
+    } else if (layer == 0) {
+      P.x[i] = io->omics[i]; P.K[i] = m->omic_dims[i]; P.ldx[i] = m->omic_dims[i];
+      P.w[i] = m->snn[i][0].w; P.bias[i] = m->snn[i][0].b;
+      P.off_out[i] = static_cast<int>(w.snn_h[i]);
+    } else {
+      P.x[i] = io->ws + w.snn_h[i]; P.K[i] = E; P.ldx[i] = E;
+      P.w[i] = m->snn[i][1].w; P.bias[i] = m->snn[i][1].b;
+      P.off_out[i] = static_cast<int>(w.G) + i * E;
+    }
+  }
+  P.out_ld = (!backward && layer == 1) ? 6 * E : E;
+  P.site_add = layer;
+  P.ws = io->ws;
+  P.off_G = static_cast<int>(w.G); P.off_dG = static_cast<int>(w.dG);
+  P.d_alpha = host_drop(io, io->drop_p, true);
+  P.B = io->num_slides;
+}
+template <typename K>
+static cudaError_t launch_snn2(K kern, const Snn2Params& P, int maxK, cudaStream_t st, bool backward = false) {
+  // backward: dG rows + W2 slice + G rows (the partial sums alias the G rows)
+  const size_t smem = backward ? static_cast<size_t>(2 * SNN_ROWS + SNN2_COLS) * snn2_kp(E) * sizeof(float)
+                               : (static_cast<size_t>(SNN_ROWS + SNN2_COLS) * snn2_kp(maxK) + NW * SNN_ROWS * SNN2_RP) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(SNN2_SMEM_FLOATS * sizeof(float)));
+  if (e != cudaSuccess) return e;
+  const dim3 grid(E / SNN2_COLS, MPO_Q, (P.B + SNN_ROWS - 1) / SNN_ROWS);
+  kern<<<grid, NT, smem, st>>>(P);
+  count_launch();
+  return cudaGetLastError();
+}
+
 int pre_fwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t st) {
   static PreParams P;
   fill_pre(m, io, w, P);
   if (P.nac && !io->kc) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_fwd: kc is NULL (NaCAGaT)");
   const bool batched = snn_batched();
-  if (batched) {
+  if (batched && snn_wide()) {
+    static Snn2Params S2;
+    int maxK = 0;
+    for (int i = 0; i < MPO_Q; ++i) maxK = m->omic_dims[i] > maxK ? m->omic_dims[i] : maxK;
+    fill_snn2(m, io, w, S2, 0, false);
+    int rc0 = fin(launch_snn2(snn2_fwd_kernel, S2, maxK, st), "snn2_fwd_kernel layer 1 (fused tail)");
+    if (rc0) return rc0;
+    fill_snn2(m, io, w, S2, 1, false);
+    rc0 = fin(launch_snn2(snn2_fwd_kernel, S2, E, st), "snn2_fwd_kernel layer 2 (fused tail)");
+    if (rc0) return rc0;
+  } else if (batched) {
     static SnnParams SP;
     fill_snn(m, io, w, SP, false);
     const int ncl_snn = MPO_Q * ((io->num_slides + SNN_ROWS - 1) / SNN_ROWS);
@@ -2004,7 +2233,12 @@ int pre_bwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t
                          : launch_cluster(pre_bwd_kernel<1>, P, ncl, PreSmem<1>::total * sizeof(float), st);
   int rc = fin(e, "pre_bwd_kernel (fused tail)");
   if (rc) return rc;
-  if (batched) {
+  if (batched && snn_wide()) {
+    static Snn2Params S2;
+    fill_snn2(m, io, w, S2, 0, true);
+    rc = fin(launch_snn2(snn2_bwd_kernel, S2, E, st, true), "snn2_bwd_kernel (fused tail)");
+    if (rc) return rc;
+  } else if (batched) {
     static SnnParams SP;
     fill_snn(m, io, w, SP, true);
     const int ncl_snn = MPO_Q * ((io->num_slides + SNN_ROWS - 1) / SNN_ROWS);
