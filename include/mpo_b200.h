@@ -193,8 +193,16 @@ int mpo_bag_bwd_nacagat(const mpo_bag* bag, const mpo_nacagat_bwd* args, void* s
  * backward entry points accumulate into), fused with zeroing the gradients of the next accumulation window.
  * *step_dev is the number of steps taken so far (bias correction); the call increments it on the device, so the
  * step can sit inside a captured CUDA graph.  n must be a multiple of 4 and the buffers 16-byte aligned. */
+#define MPO_ADAM_NO_BUMP 2   /* zero_grad flag bit: leave *step_dev alone (an earlier call of the same step reads it too) */
 int mpo_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int32_t* step_dev, int32_t zero_grad, void* stream);
+/* The same update for a bucket whose gradients the post stage completes (co_attention.out_proj and everything behind
+ * it, models/mcat/mcat.py:97-138): queued BEHIND the side-stream weight-gradient kernel of mpo_tail_post_step, so it
+ * runs next to the bag backward pass; mpo_tail_pre_bwd joins it back into the step's stream.  *step_dev is read, not
+ * incremented (the step's last mpo_adam_step does that).  When no side-stream work is pending (per-op tail, or
+ * MPO_POST_STEP_INLINE_WGRAD) the update simply runs on `stream`. */
+int mpo_tail_side_adam(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int32_t* step_dev, int32_t zero_grad, void* stream);
 
 /* Cross-shard log-sum-exp combine for one bag split by patch range over `nshards` ranks:
  * lse_in fp32 [nshards][6], pooled_in fp32 [nshards][6][256] (each shard's normalised result, e.g. after an

@@ -153,6 +153,8 @@ SIGNATURES = {
     "mpo_bag_bwd_nacagat": [ctypes.POINTER(MpoBag), ctypes.POINTER(MpoNacagatBwd), c_void_p],
     "mpo_adam_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float,
                       c_void_p, c_i32, c_void_p],
+    "mpo_tail_side_adam": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float,
+                           c_void_p, c_i32, c_void_p],
     "mpo_ge_fwd": [ctypes.POINTER(MpoGeModel), c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                    c_u32, c_i32, c_void_p],
     "mpo_ge_ce_loss": [c_void_p, c_void_p, c_i32, c_float, c_void_p, c_void_p, c_void_p],

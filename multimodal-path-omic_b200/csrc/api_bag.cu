@@ -334,6 +334,51 @@ int mpo_attn_map_dropout(const mpo_bag* bag, const float* scores_g, const float*
   return check_cuda(cudaGetLastError(), "attn_map_drop_kernel");
 }
 
+}  // extern "C"
+namespace {
+// The per-tile partial sums of the backward kernels (dqk, dkc, dtq, bias gradients) are folded by small reduction
+// kernels whose results nothing inside the bag backward pass reads.  They run on an internal side stream, forked behind
+// the kernel that wrote the partials and joined at the end of the call (event edges: capturable), so that they overlap
+// the next bag kernel instead of sitting between two of them.  MPO_BAG_SIDE=0 keeps everything on the caller's stream.
+struct BagSide {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t join = nullptr;
+  int state = 0;     // 0 not created, 1 ready, -1 unavailable
+};
+BagSide& bag_side() {
+  static BagSide pool[32];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  BagSide& b = pool[dev & 31];
+  if (b.state == 0) {
+    const char* env = getenv("MPO_BAG_SIDE");
+    bool ok = !(env && atoi(env) == 0);
+    ok = ok && cudaStreamCreateWithFlags(&b.s, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&b.fork[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&b.join, cudaEventDisableTiming) == cudaSuccess;
+    b.state = ok ? 1 : -1;
+  }
+  return b;
+}
+// the stream for a reduction that depends on everything queued on `st` so far (fork number `i` of this call)
+cudaStream_t side_fork(BagSide& b, int i, cudaStream_t st, cudaError_t* err) {
+  if (b.state != 1) return st;
+  cudaError_t e = cudaEventRecord(b.fork[i & 3], st);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(b.s, b.fork[i & 3], 0);
+  if (e != cudaSuccess) { *err = e; return st; }
+  return b.s;
+}
+// `st` waits for everything queued on the side stream
+cudaError_t side_join(BagSide& b, cudaStream_t st) {
+  if (b.state != 1) return cudaSuccess;
+  cudaError_t e = cudaEventRecord(b.join, b.s);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, b.join, 0);
+  return e;
+}
+}  // namespace
+extern "C" {
+
 int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, const float* lse, const float* pooled,
                 const float* dpooled, const float* qk, void* dz_ws, float* part_dqk, float* part_db, float* dqk,
                 float* grad_w_h, float* grad_b_h, const float* d_amap, const float* amap_dot, float drop_p, void* stream) {
@@ -409,8 +454,12 @@ int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, co
   if (rc) return rc;
   rc = check_cuda(launch_bag_bwd_dz(0, tm_h, tm_dzs, p, num_sms(), st), "bag_bwd_dz_kernel");
   if (rc) return rc;
+  BagSide& side = bag_side();
+  cudaError_t ferr = cudaSuccess;
+  cudaStream_t rs = side_fork(side, 0, st, &ferr);        // the reduction overlaps the weight-gradient kernel
+  if (ferr != cudaSuccess) return check_cuda(ferr, "mpo_bag_bwd: side-stream fork");
   rc = check_cuda(launch_bag_bwd_reduce(bag->tile_prefix, part_dqk, part_db, dqk, grad_b_h, bag->num_slides,
-                                        bag->num_tiles, st),
+                                        bag->num_tiles, rs),
                   "bag_bwd_reduce_kernel");
   if (rc) return rc;
   CUtensorMap tm_dz, tm_x;
@@ -418,9 +467,11 @@ int mpo_bag_bwd(const mpo_bag* bag, const void* h_saved, const float* scores, co
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_x, bag->x, static_cast<uint64_t>(bag->total_rows), kDIn, 64, 64);
   if (rc) return rc;
-  return check_cuda(launch_bag_bwd_dw(tm_dz, tm_x, grad_w_h, static_cast<int>(bag->total_rows), kDIn, kDIn, false, nullptr,
-                                          num_sms(), st),
-                    "bag_bwd_dw_kernel");
+  rc = check_cuda(launch_bag_bwd_dw(tm_dz, tm_x, grad_w_h, static_cast<int>(bag->total_rows), kDIn, kDIn, false, nullptr,
+                                    num_sms(), st),
+                  "bag_bwd_dw_kernel");
+  if (rc) return rc;
+  return rs != st ? check_cuda(side_join(side, st), "mpo_bag_bwd: side-stream join") : MPO_OK;
 }
 
 int mpo_bag_bwd_nacagat(const mpo_bag* bag, const mpo_nacagat_bwd* a, void* stream) {
@@ -463,15 +514,21 @@ int mpo_bag_bwd_nacagat(const mpo_bag* bag, const mpo_nacagat_bwd* a, void* stre
   // value / fold path: dz_part, dqk, dkc, dg
   p.out = a->dz_ws; p.part_dqk = a->part_dqk; p.part_db = nullptr;
   if ((rc = check_cuda(launch_bag_bwd_dz(1, tm_h, tm_dz, p, ns, st), "bag_bwd_dz_kernel<nacagat dh>"))) return rc;
+  BagSide& side = bag_side();
+  cudaError_t ferr = cudaSuccess;
+  cudaStream_t rs = side_fork(side, 0, st, &ferr);        // the reductions overlap the next bag kernel
+  if (ferr != cudaSuccess) return check_cuda(ferr, "mpo_bag_bwd_nacagat: side-stream fork");
   if ((rc = check_cuda(launch_bag_bwd_reduce(bag->tile_prefix, a->part_dqk, nullptr, a->dqk, nullptr, bag->num_slides,
-                                             bag->num_tiles, st), "bag_bwd_reduce_kernel"))) return rc;
-  if ((rc = check_cuda(launch_bag_bwd_dkc(bag->tile_prefix, a->part_dkc, a->dkc, bag->num_slides, st),
+                                             bag->num_tiles, rs), "bag_bwd_reduce_kernel"))) return rc;
+  if ((rc = check_cuda(launch_bag_bwd_dkc(bag->tile_prefix, a->part_dkc, a->dkc, bag->num_slides, rs),
                        "bag_bwd_dkc_kernel"))) return rc;
   // gate path: dkg = (1 - tanh(k)^2) (dg tq) gs, dtq, gate part of db_k
   p.out = a->dkg_ws; p.part_dqk = a->part_dtq; p.part_db = a->part_dbk;
   if ((rc = check_cuda(launch_bag_bwd_dz(2, tm_t, tm_dkg, p, ns, st), "bag_bwd_dz_kernel<nacagat dkg>"))) return rc;
+  rs = side_fork(side, 1, st, &ferr);
+  if (ferr != cudaSuccess) return check_cuda(ferr, "mpo_bag_bwd_nacagat: side-stream fork");
   if ((rc = check_cuda(launch_bag_bwd_reduce(bag->tile_prefix, a->part_dtq, a->part_dbk, a->dtq, a->grad_b_k,
-                                             bag->num_slides, bag->num_tiles, st), "bag_bwd_reduce_kernel"))) return rc;
+                                             bag->num_slides, bag->num_tiles, rs), "bag_bwd_reduce_kernel"))) return rc;
   // key-projection path into dz, db_H
   BagDhkParams d = {};
   d.tile_info = p.tile_info; d.num_tiles = p.num_tiles; d.total_rows = p.total_rows;
@@ -480,8 +537,10 @@ int mpo_bag_bwd_nacagat(const mpo_bag* bag, const mpo_nacagat_bwd* a, void* stre
   d.part_db = a->part_db; d.dg_max = a->dg_max; d.keep_scale = p.keep_scale;
   CUtensorMap tm_dkg_a = tm_dkg;
   if ((rc = check_cuda(launch_bag_dhk(tm_dkg_a, tm_wk, tm_dz, d, ns, st), "bag_dhk_kernel"))) return rc;
+  rs = side_fork(side, 2, st, &ferr);
+  if (ferr != cudaSuccess) return check_cuda(ferr, "mpo_bag_bwd_nacagat: side-stream fork");
   if ((rc = check_cuda(launch_bag_bwd_reduce(bag->tile_prefix, a->part_dqk, a->part_db, a->dqk, a->grad_b_h, 0,
-                                             bag->num_tiles, st), "bag_bwd_reduce_kernel (bias)"))) return rc;
+                                             bag->num_tiles, rs), "bag_bwd_reduce_kernel (bias)"))) return rc;
   // weight gradients: dW_H += dz^T X (bf16), dW_k += dkg^T H / gs (fp16)
   CUtensorMap tm_dz64, tm_x64, tm_dkg64, tm_h64;
   if ((rc = make_tmap_bf16_2d(&tm_dz64, a->dz_ws, R, kD, 64, 64))) return rc;
@@ -490,8 +549,9 @@ int mpo_bag_bwd_nacagat(const mpo_bag* bag, const mpo_nacagat_bwd* a, void* stre
   if ((rc = make_tmap_16b_2d(&tm_h64, a->h_saved, R, kD, 64, 64, true))) return rc;
   if ((rc = check_cuda(launch_bag_bwd_dw(tm_dz64, tm_x64, a->grad_w_h, p.total_rows, kDIn, kDIn, false, nullptr, ns, st),
                        "bag_bwd_dw_kernel"))) return rc;
-  return check_cuda(launch_bag_bwd_dw(tm_dkg64, tm_h64, a->grad_w_k, p.total_rows, kD, kD, true, a->dg_max, ns, st),
-                    "bag_bwd_dw_kernel (W_k)");
+  if ((rc = check_cuda(launch_bag_bwd_dw(tm_dkg64, tm_h64, a->grad_w_k, p.total_rows, kD, kD, true, a->dg_max, ns, st),
+                       "bag_bwd_dw_kernel (W_k)"))) return rc;
+  return rs != st ? check_cuda(side_join(side, st), "mpo_bag_bwd_nacagat: side-stream join") : MPO_OK;
 }
 
 // Adam with L2 weight decay over one flat fp32 parameter buffer (torch.optim.Adam semantics, the optimizer of the
@@ -523,21 +583,33 @@ adam_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
 }
 __global__ void bump_step_kernel(int32_t* s) { *s += 1; }
 
-int mpo_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-                  float beta2, float eps, float weight_decay, int32_t* step_dev, int32_t zero_grad, void* stream) {
+}  // extern "C"
+namespace mpo {
+// Adam kernel over [0, n) on `st`; bump: increment *step_dev afterwards (one more 1-thread launch)
+int launch_adam(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                float eps, float weight_decay, int32_t* step_dev, bool zero_grad, bool bump, cudaStream_t st) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || !step_dev || n < 0 || (n & 3))
     return fail(MPO_E_ARG, "%s", "mpo_adam_step: null pointer or n not a multiple of 4");
   if (num_sms() <= 0) return fail(MPO_E_CUDA, "%s", "mpo_adam_step: no CUDA device (this library has no CPU fallback)");
-  if (n == 0) return MPO_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t groups = n / 4;
-  int blocks = static_cast<int>((groups + 255) / 256);
-  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-  adam_step_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
-                                           step_dev, zero_grad);
-  bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
-  count_launch(2);
+  if (n > 0) {
+    const int64_t groups = n / 4;
+    int blocks = static_cast<int>((groups + 255) / 256);
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    adam_step_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                             step_dev, zero_grad ? 1 : 0);
+    count_launch();
+  }
+  if (bump) { bump_step_kernel<<<1, 1, 0, st>>>(step_dev); count_launch(); }
   return check_cuda(cudaGetLastError(), "adam_step_kernel");
+}
+}  // namespace mpo
+extern "C" {
+
+int mpo_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t* step_dev, int32_t zero_grad, void* stream) {
+  if (n == 0 && !(zero_grad & MPO_ADAM_NO_BUMP)) return MPO_OK;
+  return mpo::launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step_dev,
+                          (zero_grad & 1) != 0, (zero_grad & MPO_ADAM_NO_BUMP) == 0, static_cast<cudaStream_t>(stream));
 }
 
 int mpo_lse_combine(const float* lse_in, const float* pooled_in, int32_t nshards, float* lse_out, float* pooled_out,

@@ -52,6 +52,10 @@ struct Ctx {
   float drop_p = 0.f;          // the model's `dropout` rate; seed of the mask streams
   uint32_t seed = 0;
   const uint32_t* seed_dev = nullptr;
+  // GE-NaCAGaT: scratch for the bf16 (hi, lo) operand pairs of the tensor-core weight-gradient GEMMs over tc_rows tokens
+  float* tc_dz = nullptr;      // [2][tc_rows][768] bf16
+  float* tc_x = nullptr;       // [2][tc_rows][512] bf16
+  int tc_rows = 0;
   cudaError_t err = cudaSuccess;
   const char* where = "";
   void chk(cudaError_t e, const char* w) { if (err == cudaSuccess && e != cudaSuccess) { err = e; where = w; } }
@@ -89,6 +93,14 @@ DropSpec mk_drop(const Ctx& c, float p, uint32_t site, bool alpha = false) {
 }
 
 inline unsigned nblk(long long n, int t = 256) { return static_cast<unsigned>((n + t - 1) / t); }
+// g[c] += column sums of x (optionally of x * y); bag-long reductions are split over row blocks
+void colsum(cudaStream_t st, const float* x, long long ldx, const float* y, long long ldy, float* g, int rows, int cols) {
+  int ry = rows / 512;
+  if (ry < 1) ry = 1;
+  if (ry > 64) ry = 64;
+  launch_k(colsum_kernel, dim3(nblk(cols, 32), ry), dim3(256), 0, st, x, ldx, y, ldy, g, rows, cols); count_launch();
+}
+
 
 mpo_lin sub(const mpo_lin& L, int row0, int in) {   // rows [row0, ...) of a packed projection
   mpo_lin s;
@@ -120,13 +132,27 @@ void lin_bwd(Ctx& c, const float* dz, long long lddz, const float* x, long long 
     g.bwd_y = epi.y; g.ld_bwd = epi.ld_y; g.bwd_act = epi.act; g.bwd_drop = epi.drop;
     c.chk(launch_gemm(g, c.st), "lin_bwd.dgrad");
   }
-  if (L.gw != nullptr) {     // gw += dz^T x, with gb += rowsum(dz^T) fused into the same kernel
+  if (L.gw != nullptr && c.tc_dz != nullptr && rows == c.tc_rows && out <= 768 && in <= 512) {
+    // bag-long reduction (GE-NaCAGaT's N-token layers): gw += dz^T x on tcgen05 -- both operands read MN-major out of
+    // their bf16 (hi, lo) pairs, split-K over the tokens, partial products added atomically; gb by the column-sum kernel
+    const int po = (out + 63) / 64 * 64, pi = (in + 63) / 64 * 64;
+    __nv_bfloat16* dzh = reinterpret_cast<__nv_bfloat16*>(c.tc_dz);
+    __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(c.tc_x);
+    __nv_bfloat16* dzl = dzh + static_cast<long long>(rows) * po;
+    __nv_bfloat16* xl = xh + static_cast<long long>(rows) * pi;
+    c.chk(launch_split_bf16(dz, lddz, rows, out, dzh, dzl, po, c.st), "lin_bwd.split dz");
+    c.chk(launch_split_bf16(x, ldx, rows, in, xh, xl, pi, c.st), "lin_bwd.split x");
+    if (c.err == cudaSuccess &&
+        launch_tc_gemm(dzh, dzl, rows, po, true, xh, xl, rows, pi, true, L.gw, in, out, in, rows, 1.f, true, c.st) != 0)
+      c.chk(cudaErrorUnknown, "lin_bwd.wgrad (tc)");
+    if (L.gb != nullptr) colsum(c.st, dz, lddz, nullptr, 0, L.gb, rows, out);
+  } else if (L.gw != nullptr) {     // gw += dz^T x, with gb += rowsum(dz^T) fused into the same kernel
     GemmArgs g{dz, 1, lddz, x, ldx, 1, L.gw, in, nullptr, out, in, rows, 1.f, 1, ACT_NONE, L.gb};
     cudaStream_t ws_ = c.async_w ? c.wst : c.st;
     if (c.async_w) dep(c, c.st, c.wst);      // dz is complete on the compute stream
     c.chk(launch_gemm(g, ws_), "lin_bwd.wgrad");
   } else if (L.gb != nullptr) {
-    launch_k(colsum_kernel, dim3(nblk(out, 32)), dim3(256), 0, c.st, dz, lddz, nullptr, 0, L.gb, rows, out); count_launch();
+    colsum(c.st, dz, lddz, nullptr, 0, L.gb, rows, out);
     c.chk(cudaGetLastError(), "lin_bwd.bgrad");
   }
 }
@@ -159,8 +185,8 @@ void ln_bwd(Ctx& c, const float* dy, const mpo_norm& N, const float* xh, const f
   if (N.gg != nullptr) {
     cudaStream_t ws_ = c.async_w ? c.wst : c.st;
     if (c.async_w) dep(c, c.st, c.wst);
-    launch_k(colsum_kernel, dim3(nblk(E, 32)), dim3(256), 0, ws_, dy, E, xh, E, N.gg, rows, E); count_launch();
-    launch_k(colsum_kernel, dim3(nblk(E, 32)), dim3(256), 0, ws_, dy, E, nullptr, 0, N.gb, rows, E); count_launch();
+    colsum(ws_, dy, E, xh, E, N.gg, rows, E);
+    colsum(ws_, dy, E, nullptr, 0, N.gb, rows, E);
     c.chk(cudaGetLastError(), "ln_bwd.params");
   }
 }
@@ -419,6 +445,7 @@ struct GeWs {
   long long dlogits, dh, dzr, dhp, dw, dA, dab, t0, dx, dr2, df, dy1, dr1, dctx, dqkv, dP, dmid, dH, dzf;
   long long dP2, dmk1, dmk2;      // train mode: dropped probabilities of one head; gradients behind dropout1 / dropout2
   long long tcA, tcS[4];          // bf16 (hi, lo) operand pairs of the tensor-core GEMMs: one N x N operand, four N x 256 ones
+  long long tcWdz, tcWx;          // operand pairs of the weight-gradient GEMMs: dz (<= 768 columns), x (<= 512 columns)
   long long total;
 };
 void ge_layout(long long N, GeWs& w) {
@@ -438,6 +465,7 @@ void ge_layout(long long N, GeWs& w) {
   const long long Np = (N + 63) / 64 * 64;
   w.tcA = A(N * Np);                                   // 2 x [N][Np] bf16 = N * Np floats
   for (int i = 0; i < 4; ++i) w.tcS[i] = A(N * E);     // 2 x [N][256] bf16 = N * 256 floats
+  w.tcWdz = A(N * 768); w.tcWx = A(N * 512);
   w.total = off;
 }
 // multi-head attention over N tokens from a packed [N, 3E] projection: probs [nh][N][N], ctx [N, E]
@@ -518,13 +546,19 @@ void ge_attn_bwd(Ctx& c, const GeWs& w, float* ws, const float* qkv, const float
       tc_gemm(c, sD, false, sV, false, dP, N, N, N, hd, 1.f);                       // dP' = dctx_h V_h^T
       const TcOp sP = tc_split(c, ws, w.tcA, P, N, N, N, &drop, base);              // P' = dropout(P), regenerated
       tc_gemm(c, sP, true, sD, true, dqkv + 2 * E + h * hd, 3 * E, N, hd, N, 1.f);  // dV_h = P'^T dctx_h (P' read M-major)
+      // dS as the operand pair of the two products below, written by the soft-max backward itself (no fp32 dS, no split
+      // pass); it reuses the N x N operand slot of P'
+      TcOp sS;
+      sS.rows = N; sS.pitch = (N + 63) / 64 * 64;
+      sS.hi = ws + w.tcA;
+      sS.lo = reinterpret_cast<__nv_bfloat16*>(ws + w.tcA) + static_cast<long long>(N) * sS.pitch;
       if (drop.thr != 0) {
-        launch_k(row_softmax_bwd_drop_kernel, dim3(N), dim3(256), 0, c.st, P, (long long)N, dP, (long long)N, N, scale, base,
-                 drop); count_launch();
+        launch_k(row_softmax_bwd_pair_kernel<true>, dim3(N), dim3(256), 0, c.st, P, (long long)N, (const float*)dP, (long long)N, N,
+                 scale, static_cast<__nv_bfloat16*>(sS.hi), static_cast<__nv_bfloat16*>(sS.lo), sS.pitch, base, drop); count_launch();
       } else {
-        launch_k(row_softmax_bwd_kernel, dim3(N), dim3(256), 0, c.st, P, (long long)N, dP, (long long)N, N, scale); count_launch();
+        launch_k(row_softmax_bwd_pair_kernel<false>, dim3(N), dim3(256), 0, c.st, P, (long long)N, (const float*)dP, (long long)N, N,
+                 scale, static_cast<__nv_bfloat16*>(sS.hi), static_cast<__nv_bfloat16*>(sS.lo), sS.pitch, base, DropSpec{}); count_launch();
       }
-      const TcOp sS = tc_split(c, ws, w.tcA, dP, N, N, N);                          // dS (reuses the N x N operand slot)
       const TcOp sK = tc_split(c, ws, w.tcS[1], qkv + E + h * hd, 3 * E, N, hd);
       const TcOp sQ = tc_split(c, ws, w.tcS[0], qkv + h * hd, 3 * E, N, hd);
       tc_gemm(c, sS, false, sK, true, dqkv + h * hd, 3 * E, N, hd, N, 1.f);         // dQ_h = dS K_h
@@ -879,6 +913,12 @@ int mpo_tail_post_step(const mpo_model* m, const mpo_tail_io* io, int32_t kind, 
   return mpo_tail_post_bwd(m, io, dhaz, dS, nullptr, stream);
 }
 
+int mpo_tail_side_adam(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int32_t* step_dev, int32_t zero_grad, void* stream) {
+  return fused::side_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step_dev,
+                          (zero_grad & 1) != 0, static_cast<cudaStream_t>(stream));
+}
+
 int mpo_tail_pre_bwd(const mpo_model* m, const mpo_tail_io* io, void* stream) {
   int rc = check_model(m, io, "mpo_tail_pre_bwd");
   if (rc) return rc;
@@ -1017,6 +1057,7 @@ int mpo_ge_bwd(const mpo_ge_model* m, const mpo_bag* bag, const void* h_hi, floa
   GeWs w; ge_layout(N, w);
   Ctx c; c.st = static_cast<cudaStream_t>(stream);
   c.train = train != 0; c.drop_p = drop_p; c.seed = seed;
+  if (ge_use_tc() && N >= 1024) { c.tc_dz = ws + w.tcWdz; c.tc_x = ws + w.tcWx; c.tc_rows = static_cast<int>(N); }
   const long long n = (long long)N * E;
   const int K = m->n_classes;
   const float* x = ws + w.enc[1].y2;
@@ -1050,7 +1091,7 @@ int mpo_ge_bwd(const mpo_ge_model* m, const mpo_bag* bag, const void* h_hi, floa
   // H projection: dz = dH * mask; db_H += colsum(dz); dW_H += dz^T X on the tensor cores
   launch_k(ge_dz_kernel, dim3(nblk(n)), dim3(256), 0, c.st, ws + w.dH, static_cast<const __half*>(h_hi), keep_scale,
            ws + w.dzf, static_cast<__nv_bfloat16*>(dz_ws), n); count_launch();
-  launch_k(colsum_kernel, dim3(nblk(E, 32)), dim3(256), 0, c.st, ws + w.dzf, (long long)E, nullptr, (long long)0, m->H.gb, N, E); count_launch();
+  colsum(c.st, ws + w.dzf, (long long)E, nullptr, (long long)0, m->H.gb, N, E);
   c.chk(cudaGetLastError(), "mpo_ge_bwd");
   rc = finish(c);
   if (rc) return rc;

@@ -30,6 +30,9 @@ int pre_fwd(const mpo_model* m, const mpo_tail_io* io, const tailws::Ws& w, cuda
 int post(const mpo_model* m, const mpo_tail_io* io, const tailws::Ws& w, int flags, const LossArgs* loss,
          const float* dhaz, const float* dS, const float* dY, cudaStream_t st, bool side_wgrad = false);
 int pre_bwd(const mpo_model* m, const mpo_tail_io* io, const tailws::Ws& w, cudaStream_t st);
+// Adam over a bucket completed by the pending side-stream weight gradients (see mpo_tail_side_adam)
+int side_adam(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+              float eps, float weight_decay, int32_t* step_dev, bool zero_grad, cudaStream_t st);
 
 }  // namespace fused
 }  // namespace mpo

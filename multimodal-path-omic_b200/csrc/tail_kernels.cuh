@@ -520,13 +520,15 @@ colsum_kernel(const float* __restrict__ x, long long ldx, const float* __restric
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   float s = 0.f;
+  // gridDim.y > 1: the rows are split over blockIdx.y as well (bag-long reductions) and the sums are added atomically
+  const int rstep = 8 * static_cast<int>(gridDim.y);
   if (c < cols) {
     if (y == nullptr) {
 #pragma unroll 4
-      for (int r = ry; r < rows; r += 8) s += x[r * ldx + c];
+      for (int r = ry + 8 * static_cast<int>(blockIdx.y); r < rows; r += rstep) s += x[r * ldx + c];
     } else {
 #pragma unroll 4
-      for (int r = ry; r < rows; r += 8) s = fmaf(x[r * ldx + c], y[r * ldy + c], s);
+      for (int r = ry + 8 * static_cast<int>(blockIdx.y); r < rows; r += rstep) s = fmaf(x[r * ldx + c], y[r * ldy + c], s);
     }
   }
   part[ry][cx] = s;
@@ -535,7 +537,8 @@ colsum_kernel(const float* __restrict__ x, long long ldx, const float* __restric
     float v = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v += part[i][cx];
-    g[c] += v;
+    if (gridDim.y > 1) atomicAdd(&g[c], v);
+    else g[c] += v;
   }
 }
 
@@ -1047,6 +1050,79 @@ row_softmax_bwd_kernel(const float* __restrict__ a, long long lda, float* __rest
   for (int c = threadIdx.x; c < cols; c += 256) s = fmaf(ar[c], dr[c], s);
   s = block_reduce_256(s, false, red);
   for (int c = threadIdx.x; c < cols; c += 256) dr[c] = ar[c] * (dr[c] - s) * scale;
+}
+// Tensor-core path of GE-NaCAGaT: the soft-max backward of one attention row written straight as the bf16 (hi, lo)
+// operand pair of the dQ / dK products (tc_gemm.cu) -- ds itself is never stored in fp32 and never re-read by a split
+// pass.  DROP: da is first multiplied by the regenerated dropout factor of the probabilities (element base + row * cols + c).
+template <bool DROP>
+__global__ void __launch_bounds__(256)
+row_softmax_bwd_pair_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ da, long long ldd, int cols,
+                            float scale, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int pitch,
+                            uint32_t base, DropSpec drop) {
+  pdl_enter();
+  __shared__ float red[8];
+  uint32_t seedv = 0;
+  if (DROP) seedv = drop_seed(drop);
+  const float* ar = a + static_cast<long long>(blockIdx.x) * lda;
+  const float* dr = da + static_cast<long long>(blockIdx.x) * ldd;
+  const uint32_t rb = base + static_cast<uint32_t>(blockIdx.x) * static_cast<uint32_t>(cols);
+  const bool vec = ((lda | ldd) & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(da)) & 15u) == 0;
+  float s = 0.f;
+  for (int c0 = threadIdx.x * 8; c0 < cols; c0 += 256 * 8) {
+    float av[8], dv[8];
+    if (vec && c0 + 8 <= cols) {
+      const float4 a0 = *reinterpret_cast<const float4*>(ar + c0), a1 = *reinterpret_cast<const float4*>(ar + c0 + 4);
+      const float4 d0 = *reinterpret_cast<const float4*>(dr + c0), d1 = *reinterpret_cast<const float4*>(dr + c0 + 4);
+      av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+      dv[0] = d0.x; dv[1] = d0.y; dv[2] = d0.z; dv[3] = d0.w; dv[4] = d1.x; dv[5] = d1.y; dv[6] = d1.z; dv[7] = d1.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { av[e] = c0 + e < cols ? ar[c0 + e] : 0.f; dv[e] = c0 + e < cols ? dr[c0 + e] : 0.f; }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (DROP) dv[e] *= drop_grad(drop, seedv, rb + c0 + e);
+      s = fmaf(av[e], dv[e], s);
+    }
+  }
+  s = block_reduce_256(s, false, red);
+  __nv_bfloat16* hr = hi + static_cast<long long>(blockIdx.x) * pitch;
+  __nv_bfloat16* lr = lo + static_cast<long long>(blockIdx.x) * pitch;
+  for (int c0 = threadIdx.x * 8; c0 < pitch; c0 += 256 * 8) {
+    float v[8];
+    if (vec && c0 + 8 <= cols) {
+      const float4 a0 = *reinterpret_cast<const float4*>(ar + c0), a1 = *reinterpret_cast<const float4*>(ar + c0 + 4);
+      const float4 d0 = *reinterpret_cast<const float4*>(dr + c0), d1 = *reinterpret_cast<const float4*>(dr + c0 + 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (DROP) dv[e] *= drop_grad(drop, seedv, rb + c0 + e);
+        v[e] = av[e] * (dv[e] - s) * scale;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[e] = 0.f;
+        if (c0 + e < cols) {
+          float d = dr[c0 + e];
+          if (DROP) d *= drop_grad(drop, seedv, rb + c0 + e);
+          v[e] = ar[c0 + e] * (d - s) * scale;
+        }
+      }
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * e] - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * e + 1] - __bfloat162float(h1));
+      h[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+      l[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+    }
+    *reinterpret_cast<uint4*>(hr + c0) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lr + c0) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
 }
 // GE-NaCAGaT train mode: attention-probability dropout of the N-token encoder layers (nn.TransformerEncoderLayer's
 // self_attn carries the layer's dropout rate).  out = dropout(p), element index = base + row * cols + col.

@@ -43,7 +43,19 @@ struct TcGemmParams {
   int a_mn, b_mn;    // 1: the operand is MN-major (its array has the GEMM's K dimension as rows)
   int tiles_m, num_tiles;
   int tma_store;     // 1: the epilogue stores through tm_c
+  int ksplit;        // > 1: split-K work items (tile, split); partial products are added with red.global.add
 };
+// work item -> output tile and K-block range (every split owns at least one K block: ksplit <= nkb)
+struct TcItem { int m0, n0, kb0, kb1; };
+__device__ __forceinline__ TcItem tc_item(const TcGemmParams& p, int item, int nkb) {
+  const int tile = item % p.num_tiles, split = item / p.num_tiles;
+  TcItem w;
+  w.m0 = (tile % p.tiles_m) * kTcBM;
+  w.n0 = (tile / p.tiles_m) * p.bn;
+  w.kb0 = static_cast<int>(static_cast<long long>(split) * nkb / p.ksplit);
+  w.kb1 = static_cast<int>(static_cast<long long>(split + 1) * nkb / p.ksplit);
+  return w;
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -61,6 +73,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.K + kTcBK - 1) / kTcBK;
   const int b_bytes = p.bn * kTcBK * 2;
+  const int num_items = p.num_tiles * p.ksplit;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
@@ -79,9 +92,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (lane == 0) {
       const uint64_t pol = policy_evict_last();          // operand panels are re-read by the other tiles of the row / column
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % p.tiles_m) * kTcBM, n0 = (tile / p.tiles_m) * p.bn;
-        for (int kb = 0; kb < nkb; ++kb) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const TcItem w = tc_item(p, item, nkb);
+        const int m0 = w.m0, n0 = w.n0;
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kTcStageBytes;
           uint8_t* sb = sa + 2 * kTcABytes;
@@ -116,12 +130,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                                              static_cast<uint32_t>(p.b_mn));
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const TcItem w = tc_item(p, item, nkb);
         const int acc = it & 1;
         const uint32_t tacc = tmem_base + static_cast<uint32_t>(acc * 128);
         mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + stage * kTcStageBytes), a_lo = a_hi + kTcABytes;
@@ -134,7 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const uint32_t albo = p.a_mn ? 8192 : 16, blbo = p.b_mn ? 8192 : 16;
             const uint64_t dah = umma_desc_sw128(a_hi + ao, albo, 1024), dal = umma_desc_sw128(a_lo + ao, albo, 1024);
             const uint64_t dbh = umma_desc_sw128(b_hi + bo, blbo, 1024), dbl = umma_desc_sw128(b_lo + bo, blbo, 1024);
-            umma_bf16(tacc, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(tacc, dah, dbh, idesc, (kb != w.kb0 || k != 0) ? 1u : 0u);
             umma_bf16(tacc, dah, dbl, idesc, 1u);
             umma_bf16(tacc, dal, dbh, idesc, 1u);
           }
@@ -151,9 +166,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const bool elected = threadIdx.x == 64;        // first epilogue thread issues the slab stores
     int it = 0;
     uint32_t nslab = 0;                            // slabs written so far by this CTA (staging buffer = nslab & 1)
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const TcItem w = tc_item(p, item, nkb);
       const int acc = it & 1;
-      const int m0 = (tile % p.tiles_m) * kTcBM, n0 = (tile / p.tiles_m) * p.bn;
+      const int m0 = w.m0, n0 = w.n0;
       const int row = m0 + r;
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
@@ -191,7 +207,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const int col = n0 + c0 + j;
             if (col < p.N) {
               const float rr = __uint_as_float(v[j]) * p.alpha;
-              crow[c0 + j] = p.accumulate ? crow[c0 + j] + rr : rr;
+              if (p.ksplit > 1) atomicAdd(crow + c0 + j, rr);
+              else crow[c0 + j] = p.accumulate ? crow[c0 + j] + rr : rr;
             }
           }
         }
@@ -300,7 +317,17 @@ int launch_tc_gemm(const void* a_hi, const void* a_lo, int a_rows, int a_pitch, 
   p.num_tiles = p.tiles_m * ((N + bn - 1) / bn);
   p.tma_store = tma_store ? 1 : 0;
   const int sms = num_sms();
-  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  // accumulating products with few output tiles and a bag-long reduction (the weight gradients of the N-token layers):
+  // split K so that every SM has a work item; the partial products are added atomically
+  p.ksplit = 1;
+  const int nkb = (K + kTcBK - 1) / kTcBK;
+  if (accumulate && p.num_tiles < sms && nkb >= 8) {
+    int ks = sms / p.num_tiles;
+    if (ks > nkb / 4) ks = nkb / 4;
+    if (ks > 1) p.ksplit = ks;
+  }
+  const int items = p.num_tiles * p.ksplit;
+  const int grid = items < sms ? items : sms;
   gemm_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc, p);
   count_launch();
   return check_cuda(cudaGetLastError(), "gemm_tc_kernel");

@@ -634,11 +634,18 @@ class BatchTrainer:
         self.adam_hp = (float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay))
         self.model = self.engine.binding.build(grads=self.grads)      # parameter addresses changed
 
-    def adam_step(self, zero_grad=True):
+    def adam_step(self, zero_grad=True, lo=0, hi=None, bump=True, side=False):
+        """mpo_adam_step over elements [lo, hi) of the flat buffers (the whole model by default).  side=True
+        (mpo_tail_side_adam): the bucket is one the post stage completes (see post_bucket_offset) -- the update is queued
+        behind the post stage's side-stream weight gradients, next to the bag backward pass, and never bumps the step
+        counter (the step's last adam_step does)."""
         lr, b1, b2, eps, wd = self.adam_hp
-        _lib.call("mpo_adam_step", _ptr(self.flat_param), _ptr(self.flat_grad), _ptr(self.adam_m), _ptr(self.adam_v),
-                  self.flat_grad.numel(), ctypes.c_float(lr), ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps),
-                  ctypes.c_float(wd), _ptr(self.adam_step_dev), 1 if zero_grad else 0, _stream())
+        hi = self.flat_grad.numel() if hi is None else hi
+        flags = (1 if zero_grad else 0) | (0 if (bump and not side) else 2)       # MPO_ADAM_NO_BUMP = 2
+        _lib.call("mpo_tail_side_adam" if side else "mpo_adam_step", _ptr(self.flat_param[lo:hi]),
+                  _ptr(self.flat_grad[lo:hi]), _ptr(self.adam_m[lo:hi]), _ptr(self.adam_v[lo:hi]), hi - lo,
+                  ctypes.c_float(lr), ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps), ctypes.c_float(wd),
+                  _ptr(self.adam_step_dev), flags, _stream())
 
     def peer_adam_step(self, lo=0, hi=None, bump=True, slot=2):
         """mpo_peer_adam_step over elements [lo, hi) of the flat buffers (the whole model by default): needs
@@ -785,9 +792,17 @@ class BatchTrainer:
                 self._run_bwd(st)
         else:
             with torch.cuda.graph(graph):
-                self._run(st, bag, omics, labels, censor, train, 0)
-                if with_adam:        # single-GPU: the optimizer step (and the gradient reset) ride in the same graph
-                    self.adam_step(zero_grad=True)
+                if with_adam:
+                    # single GPU: the optimizer step (and the gradient reset) ride in the same graph; the post-stage
+                    # bucket (~2/3 of the model) is updated behind its side-stream weight gradients, next to the bag
+                    # backward pass, the rest after the pre-stage backward
+                    off = self.post_bucket_offset()
+                    self._run_fwd(st, bag, omics, labels, censor, train, 0)
+                    self.adam_step(zero_grad=True, lo=off, side=True)
+                    self._run_bwd(st)
+                    self.adam_step(zero_grad=True, lo=0, hi=off)
+                else:
+                    self._run(st, bag, omics, labels, censor, train, 0)
         launches = int(_lib.lib().mpo_launch_count(1))     # kernels recorded into the graph(s) = launched per replay
         self.flat_grad.zero_()
         self.last_state = st

@@ -20,7 +20,7 @@ for _ in range(2):
     step(); net.zero_grad()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-reps = 3
+reps = 3 if N > 8192 else 10
 e0.record()
 for _ in range(reps):
     l = step(); net.zero_grad()

@@ -59,6 +59,7 @@ GE_CASES = [
     ("ge_300", 300, 21, 1.0),
     ("ge_sharp_517", 517, 22, 4.0),
     ("ge_1000", 1000, 23, 2.0),
+    ("ge_4096", 4096, 26, 2.0),       # 32 x 32 output tiles per attention product: the persistent tensor-core GEMM loops
 ]
 
 

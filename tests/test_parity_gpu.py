@@ -397,6 +397,46 @@ def test_flat_adam_matches_torch_adam():
         assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), n
 
 
+def test_captured_step_with_split_adam_equals_eager_step_plus_adam():
+    """capture(with_adam=True) updates the post-stage bucket behind the side-stream weight gradients
+    (mpo_tail_side_adam, next to the bag backward pass) and the rest after the pre-stage backward: three replays must
+    leave the same parameters, Adam moments and step count as three eager steps each followed by ONE whole-model
+    mpo_adam_step (eval mode: no dropout, so the two runs see identical gradients)."""
+    import copy
+    synth = _pkg("synth")
+    sp = _pkg("slidepath")
+    bpm = _pkg("bagpass")
+    case = load_case("mcat_concat_300")
+    lens = [300, 200, 129, 64]
+    slides = [synth.make_slide(700 + i, n) for i, n in enumerate(lens)]
+    pb = bpm.PackedBag.from_slides([torch.from_numpy(s[0]).cuda() for s in slides])
+    om = [torch.stack([torch.from_numpy(s[1][i]) for s in slides]).cuda() for i in range(6)]
+    labels = torch.tensor([s[2] for s in slides], dtype=torch.int64, device="cuda")
+    cens = torch.tensor([s[3] for s in slides], dtype=torch.float32, device="cuda")
+    out = {}
+    for mode in ("eager", "graph"):
+        net = build_model(case).eval()
+        tr = sp.BatchTrainer(net, loss="nll", grad_acc_step=len(lens))
+        tr.use_flat_adam(lr=2e-4, weight_decay=1e-5)
+        tr.zero_grad()
+        if mode == "eager":
+            for _ in range(3):
+                tr.step(pb, om, labels, cens, train=False)
+                tr.adam_step(zero_grad=True)
+        else:
+            g = tr.capture(pb, om, labels, cens, train=False, with_adam=True)
+            for _ in range(3):
+                g.replay()
+        torch.cuda.synchronize()
+        out[mode] = (tr.flat_param.clone(), tr.adam_m.clone(), tr.adam_v.clone(), int(tr.adam_step_dev.item()),
+                     float(tr.flat_grad.abs().max()))
+    a, b = out["eager"], out["graph"]
+    assert a[3] == b[3] == 3 and a[4] == b[4] == 0.0
+    for x, y, tol in ((a[0], b[0], 2e-5), (a[1], b[1], 2e-3), (a[2], b[2], 4e-3)):
+        # dW_H is accumulated with atomics (order-dependent fp32 sums): compare in norm
+        assert float((x - y).norm() / x.norm()) < tol
+
+
 from helpers import ge_cases, load_ge_case  # noqa: E402
 
 
