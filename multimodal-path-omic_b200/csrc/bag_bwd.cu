@@ -633,8 +633,7 @@ __global__ void __launch_bounds__(kDwThreads, 1)
 bag_bwd_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_x,
                   float* __restrict__ grad_w,   // [256][ld] fp32, accumulated
                   int total_rows, int num_splits, int ncb, int ld, uint32_t idesc,
-                  const uint32_t* __restrict__ dg_max,     // non-null: the A operand carries the batch-wide gate scale
-                  int dz_normal) {                         // 1: dz loads at normal L2 priority (evict-last otherwise)
+                  const uint32_t* __restrict__ dg_max) {   // non-null: the A operand carries the batch-wide gate scale
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms, by pointer arithmetic so the compiler keeps the shared state space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -669,9 +668,7 @@ bag_bwd_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       const uint64_t pol_stream = policy_evict_first();
-      // dz is re-read by the four column-block CTAs within a few microseconds; evict-last keeps it across them, but
-      // 0.27 GB of evict-last lines per pass also sweep the tail's (evict-last) weights out of the L2
-      const uint64_t pol_keep = dz_normal ? policy_evict_normal() : policy_evict_last();
+      const uint64_t pol_keep = policy_evict_last();     // dz is re-read by the four column-block CTAs
       int stage = 0; uint32_t phase = 0;
       for (int c = 0; c < n_chunks; ++c) {
         const int row = (c_begin + c) * kDwBK;
@@ -1150,10 +1147,8 @@ cudaError_t launch_bag_bwd_dw(const CUtensorMap& tm_dz, const CUtensorMap& tm_x,
   if (splits > chunks) splits = chunks;
   if (splits < 1) splits = 1;
   const uint32_t idesc = f16 ? umma_idesc(128, 256, 0, 0, 1, 1) : umma_idesc_bf16(128, 256, 1, 1);
-  static int dz_normal = -1;
-  if (dz_normal < 0) { const char* e = getenv("MPO_DW_DZ_NORMAL"); dz_normal = e ? atoi(e) : 0; }
   bag_bwd_dw_kernel<<<ncb * splits, kDwThreads, kDwSmemBytes, stream>>>(tm_dz, tm_x, grad_w, total_rows, splits, ncb, ld,
-                                                                       idesc, dg_max, dz_normal);
+                                                                       idesc, dg_max);
   count_launch();
   return cudaGetLastError();
 }

@@ -87,16 +87,6 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cas
 __device__ __forceinline__ void cp_async16(float* dst, const float* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
-// L2 evict-last policy for the weight stream: the ~10 MB of tail weights are re-read by every cluster of every launch of
-// every step, between bag passes that move > 1 GB through the L2 (those are loaded evict-first)
-__device__ __forceinline__ unsigned long long l2_keep_policy() {
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void cp_async16_keep(uint32_t dst, const float* src, unsigned long long pol) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -179,7 +169,6 @@ __device__ __noinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int 
     const int ld = pk & 0xffff, kc = (pk >> 16) & 0x7fff, type = (pk >> 31) & 1;
     const float* src = reinterpret_cast<const float*>(base) + static_cast<size_t>(rank) * rs;
     const uint32_t dst = ring + (c % NSTAGE) * (CHUNK * 4);
-    const unsigned long long pol = l2_keep_policy();
     // (1-D bulk copies by one warp were tried instead: 256 copies of 128 B per data-gradient chunk are far slower)
     if (type == T_FWD) {
       if (kc == KC) {
@@ -190,12 +179,13 @@ __device__ __noinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int 
         const size_t sstep = static_cast<size_t>(RP) * ld;
 #pragma unroll
         for (int j = 0; j < 32 / RP; ++j)
-          cp_async16_keep(d0 + j * (RP * WLD * 4), s0 + j * sstep, pol);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * (RP * WLD * 4)), "l"(s0 + j * sstep) : "memory");
       } else {
         const int per_row = kc >> 2;
         for (int p = t; p < 32 * per_row; p += NT) {
           const int row = p / per_row, c4 = p - row * per_row;
-          cp_async16_keep(dst + (row * WLD + c4 * 4) * 4, src + static_cast<size_t>(row) * ld + c4 * 4, pol);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (row * WLD + c4 * 4) * 4),
+                       "l"(src + static_cast<size_t>(row) * ld + c4 * 4) : "memory");
         }
       }
     } else {
@@ -206,10 +196,10 @@ __device__ __noinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int 
       if (kc == KC) {
 #pragma unroll
         for (int j = 0; j < KC / 32; ++j)
-          cp_async16_keep(d0 + j * (32 * 32 * 4), s0 + j * sstep, pol);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * (32 * 32 * 4)), "l"(s0 + j * sstep) : "memory");
       } else {
         for (int j = 0; j * 32 + (t >> 3) < kc; ++j)
-          cp_async16_keep(d0 + j * (32 * 32 * 4), s0 + j * sstep, pol);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * (32 * 32 * 4)), "l"(s0 + j * sstep) : "memory");
       }
     }
   }
@@ -1772,10 +1762,9 @@ __global__ void __launch_bounds__(NT, 1) snn2_fwd_kernel(const __grid_constant__
     if (s0 + s < P.B) cp_async16(Xs + s * kp + 4 * g, xg + static_cast<size_t>(s0 + s) * ldx + 4 * g);
     else *reinterpret_cast<float4*>(Xs + s * kp + 4 * g) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const unsigned long long wpol = l2_keep_policy();
   for (int i = t; i < SNN2_COLS * g4; i += NT) {
     const int j = i / g4, g = i - j * g4;
-    cp_async16_keep(smem_addr(Wsm + j * kp + 4 * g), wg + static_cast<size_t>(j) * K + 4 * g, wpol);
+    cp_async16(Wsm + j * kp + 4 * g, wg + static_cast<size_t>(j) * K + 4 * g);
   }
   cp_async_commit();
   const uint32_t seedv = drop_seed(P.d_alpha);
