@@ -672,7 +672,8 @@ def run_ours(args, rank, world, local_rank):
         msg = a.elapsed_time(b_) / 3
         also[f"ge_nacagat_train_step_{N}_patches_B1"] = {
             "slides_per_s": 1e3 / msg, "ms_per_step": msg, "slides_per_step": 1,
-            "note": "fp32 CUDA-core GEMMs (FFMA2, split-K), N x N attention materialised (DESIGN.md 4.5)"}
+            "note": "attention products and N-token weight gradients on tcgen05 (bf16 hi/lo operand pairs, fp32 "
+                    "accumulation; csrc/tc_gemm.cu), N x N attention materialised (DESIGN.md 4.5)"}
         del gnet
         torch.cuda.empty_cache()
         # BASELINE config 5: MCAT inference on one 200 000-patch bag.  One GPU streams the whole bag here; under the

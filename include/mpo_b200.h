@@ -421,6 +421,36 @@ int mpo_ge_bwd(const mpo_ge_model* m, const mpo_bag* bag, const void* h_hi, floa
                const float* Y, const float* dY, void* dz_ws, float keep_scale, float drop_p, uint32_t seed, int32_t train,
                void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone operators.  The reference's building blocks (models/blocks.py:13-48 AttentionNetGated, :232-253
+ * ContextualAttentionGate; models/fusion.py:7-113 ConcatFusion / GatedConcatFusion / BilinearFusion) are nn.Modules that
+ * can be called on their own -- its unit tests do (models/blocks.py:304-325, models/fusion.py:116-170).  On this path they
+ * run fused inside a slide pass; these entry points expose the same device kernels one operator at a time for the
+ * stand-alone `forward` of those classes (inference: no gradients).  All pointers are fp32 device memory.
+ *   mpo_op_linear    y[r][o] = dropout(act(sum_i x[r][i] w[o][i] + b[o]))   act: 0 none, 1 ReLU, 2 ELU, 3 tanh, 4 sigmoid
+ *   mpo_op_layernorm y = LayerNorm(x) over rows of `cols` features (biased variance)
+ *   mpo_op_ewise     y = a + b | a * b | act(a)                              op: MPO_OP_ADD, MPO_OP_MUL, MPO_OP_ACT + act
+ *   mpo_op_rowscale  y[r][c] = x[r][c] g[r]
+ *   mpo_op_dropout   y = dropout_p(x) from the stateless (seed, site, element) mask stream
+ *   mpo_op_bil_gate  nn.Bilinear(256, 256, 32) gate of BilinearFusion (fusion.py:86-89): z = x1^T W x2 + b through
+ *                    U = x2 W^T [rows][32 * 256] (by mpo_op_linear), g = sigmoid(z), gh = g * h
+ *   mpo_op_bil_kron  kp [rows][33 * 33] = dropout([o1, 1] x [o2, 1]) (fusion.py:100-107); cat [rows][130]: columns 64..129
+ *                    receive [o1, 1, o2, 1] (the skip connection, fusion.py:110-111) */
+#define MPO_OP_ADD 0
+#define MPO_OP_MUL 1
+#define MPO_OP_ACT 16
+int mpo_op_linear(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int32_t rows,
+                  int32_t in, int32_t out, int32_t act, float drop_p, uint32_t seed, uint32_t site, void* stream);
+int mpo_op_layernorm(const float* x, const float* gamma, const float* beta, float* y, int32_t rows, int32_t cols, float eps,
+                     void* stream);
+int mpo_op_ewise(int32_t op, const float* a, const float* b, float* y, int64_t n, void* stream);
+int mpo_op_rowscale(const float* x, const float* g, float* y, int32_t rows, int32_t cols, void* stream);
+int mpo_op_dropout(const float* x, float* y, int64_t n, float p, uint32_t seed, uint32_t site, void* stream);
+int mpo_op_bil_gate(const float* x1, const float* U, const float* bias, const float* h, float* g, float* gh, int32_t rows,
+                    void* stream);
+int mpo_op_bil_kron(const float* o1, const float* o2, float* kp, float* cat, int32_t rows, float drop_p, uint32_t seed,
+                    uint32_t site, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -169,6 +169,15 @@ SIGNATURES = {
     "mpo_tail_pre_bwd": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_void_p],
     "mpo_tail_post_step": [ctypes.POINTER(MpoModel), ctypes.POINTER(MpoTailIo), c_i32, c_void_p, c_void_p, c_float, c_float,
                            c_float, c_void_p, c_void_p, c_void_p, c_i32, c_void_p],
+    # stand-alone operators (the block / fusion classes called on their own)
+    "mpo_op_linear": [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_float, c_u32, c_u32,
+                      c_void_p],
+    "mpo_op_layernorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_float, c_void_p],
+    "mpo_op_ewise": [c_i32, c_void_p, c_void_p, c_void_p, c_i64, c_void_p],
+    "mpo_op_rowscale": [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p],
+    "mpo_op_dropout": [c_void_p, c_void_p, c_i64, c_float, c_u32, c_u32, c_void_p],
+    "mpo_op_bil_gate": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p],
+    "mpo_op_bil_kron": [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_float, c_u32, c_u32, c_void_p],
 }
 # functions with a non-int return type
 OTHER_EXPORTS = ["mpo_tail_ws_floats", "mpo_tail_ws_lookup", "mpo_sizeof", "mpo_launch_count", "mpo_ge_ws_floats",

@@ -2,8 +2,11 @@
 
 These classes own the nn.Parameters under the reference's state_dict names and reproduce its initialisation
 (same torch initialisers called in the same order, so a reference checkpoint -- or the same torch seed -- gives
-identical weights).  They carry no PyTorch arithmetic: the slide engine reads the parameter storage through the
-C ABI.  Calling one of them on its own raises, because on the B200 path they only exist fused into a slide pass.
+identical weights).  They carry no PyTorch arithmetic: inside MCAT / NaCAGaT the slide engine reads the parameter
+storage through the C ABI and runs them fused into the slide pass.  Called on their own (as the reference's unit tests
+do, models/blocks.py:288-345), AttentionNetGated and ContextualAttentionGate run operator by operator on the same
+CUDA kernels (ops.py: inference only, no autograd graph); PreGatingContextualAttention exists only fused into the bag
+pass and raises.
 """
 import torch
 import torch.nn as nn
@@ -37,7 +40,15 @@ class AttentionNetGated(nn.Module):
         self.branch_dropout = 0.25 if dropout_p else 0.0
 
     def forward(self, x):
-        _standalone("AttentionNetGated")
+        """(A, x) as models/blocks.py:42-48: A = attention_c(tanh-branch * sigmoid-branch), both branches with p = 0.25
+        dropout in train mode."""
+        from . import ops
+        p = self.branch_dropout if self.training else 0.0
+        la, lb = self.attention_a[0], self.attention_b[0]
+        a = ops.linear(x, la.weight, la.bias, act="tanh", drop_p=p)
+        b = ops.linear(x, lb.weight, lb.bias, act="sigmoid", drop_p=p)
+        A = ops.linear(ops.mul(a, b), self.attention_c.weight, self.attention_c.bias)
+        return A, x
 
 
 class ContextualAttentionGate(nn.Module):
@@ -53,7 +64,14 @@ class ContextualAttentionGate(nn.Module):
         self.fc_c = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nn.ELU())
 
     def forward(self, Q, Q_hat):
-        _standalone("ContextualAttentionGate")
+        """C = fc_c(G(fc1(Q) + fc2(Q_hat)) * E(fc3(Q_hat))) -- models/blocks.py:247-253."""
+        from . import ops
+        f1 = ops.linear(Q, self.fc1[0].weight, self.fc1[0].bias, act="elu")
+        f2 = ops.linear(Q_hat, self.fc2[0].weight, self.fc2[0].bias, act="elu")
+        f3 = ops.linear(Q_hat, self.fc3[0].weight, self.fc3[0].bias, act="elu")
+        G = ops.layernorm(ops.act(ops.add(f1, f2), "elu"), self.G[1].weight, self.G[1].bias, self.G[1].eps)
+        Eg = ops.layernorm(ops.act(f3, "elu"), self.E[1].weight, self.E[1].bias, self.E[1].eps)
+        return ops.linear(ops.mul(G, Eg), self.fc_c[0].weight, self.fc_c[0].bias, act="elu")
 
 
 class PreGatingContextualAttention(nn.Module):

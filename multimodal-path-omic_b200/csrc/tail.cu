@@ -1102,4 +1102,72 @@ int mpo_ge_bwd(const mpo_ge_model* m, const mpo_bag* bag, const void* h_hi, floa
                     "bag_bwd_dw_kernel (GE)");
 }
 
+
+// ------------------------------------------------------------------------------------------------ stand-alone operators
+// The reference's building blocks can also be called on their own (its unit tests do: models/blocks.py:304-325,
+// models/fusion.py:116-170).  On this path they run fused inside a slide pass; these entry points expose the same device
+// kernels one operator at a time, so that the stand-alone `forward` of the block / fusion classes is CUDA as well
+// (inference: no gradients are produced).
+static DropSpec op_drop(float p, uint32_t seed, uint32_t site) {
+  Ctx c; c.train = p > 0.f; c.seed = seed;
+  return mk_drop(c, p, site);
+}
+int mpo_op_linear(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int32_t rows,
+                  int32_t in, int32_t out, int32_t act, float drop_p, uint32_t seed, uint32_t site, void* stream) {
+  if (!x || !w || !y || rows < 0 || in <= 0 || out <= 0 || act < ACT_NONE || act > ACT_SIGMOID)
+    return fail(MPO_E_ARG, "%s", "mpo_op_linear: bad arguments");
+  if (num_sms() <= 0) return fail(MPO_E_CUDA, "%s", "mpo_op_linear: no CUDA device (this library has no CPU fallback)");
+  GemmArgs g{x, ldx, 1, w, 1, in, y, ldy, b, rows, out, in, 1.f, 0, act, nullptr, 1, op_drop(drop_p, seed, site)};
+  return check_cuda(launch_gemm(g, static_cast<cudaStream_t>(stream)), "mpo_op_linear");
+}
+int mpo_op_layernorm(const float* x, const float* gamma, const float* beta, float* y, int32_t rows, int32_t cols, float eps,
+                     void* stream) {
+  if (!x || !gamma || !beta || !y || rows < 0 || cols <= 0) return fail(MPO_E_ARG, "%s", "mpo_op_layernorm: bad arguments");
+  if (rows == 0) return MPO_OK;
+  op_layernorm_kernel<<<nblk(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, y, rows, cols, eps);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "mpo_op_layernorm");
+}
+int mpo_op_ewise(int32_t op, const float* a, const float* b, float* y, int64_t n, void* stream) {
+  if (!a || !y || n < 0 || ((op == MPO_OP_ADD || op == MPO_OP_MUL) && !b)) return fail(MPO_E_ARG, "%s", "mpo_op_ewise: bad arguments");
+  if (n == 0) return MPO_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (op == MPO_OP_ADD) add_kernel<<<nblk(n), 256, 0, st>>>(a, b, y, n);
+  else if (op == MPO_OP_MUL) mul_kernel<<<nblk(n), 256, 0, st>>>(a, b, y, n);
+  else if (op >= MPO_OP_ACT && op <= MPO_OP_ACT + ACT_SIGMOID) act_kernel<<<nblk(n), 256, 0, st>>>(a, y, n, op - MPO_OP_ACT);
+  else return fail(MPO_E_ARG, "%s", "mpo_op_ewise: unknown operator");
+  count_launch();
+  return check_cuda(cudaGetLastError(), "mpo_op_ewise");
+}
+int mpo_op_rowscale(const float* x, const float* g, float* y, int32_t rows, int32_t cols, void* stream) {
+  if (!x || !g || !y || rows < 0 || cols <= 0) return fail(MPO_E_ARG, "%s", "mpo_op_rowscale: bad arguments");
+  if (rows == 0) return MPO_OK;
+  op_rowscale_kernel<<<nblk(static_cast<long long>(rows) * cols), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, g, y, rows, cols);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "mpo_op_rowscale");
+}
+int mpo_op_dropout(const float* x, float* y, int64_t n, float p, uint32_t seed, uint32_t site, void* stream) {
+  if (!x || !y || n < 0) return fail(MPO_E_ARG, "%s", "mpo_op_dropout: bad arguments");
+  if (n == 0) return MPO_OK;
+  probs_dropout_kernel<<<nblk(n, 1024), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, 0u, op_drop(p, seed, site));
+  count_launch();
+  return check_cuda(cudaGetLastError(), "mpo_op_dropout");
+}
+int mpo_op_bil_gate(const float* x1, const float* U, const float* bias, const float* h, float* g, float* gh, int32_t rows,
+                    void* stream) {
+  if (!x1 || !U || !bias || !h || !g || !gh || rows < 0) return fail(MPO_E_ARG, "%s", "mpo_op_bil_gate: bad arguments");
+  if (rows == 0) return MPO_OK;
+  bil_gate_fwd_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(x1, U, bias, h, g, gh);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "mpo_op_bil_gate");
+}
+int mpo_op_bil_kron(const float* o1, const float* o2, float* kp, float* cat, int32_t rows, float drop_p, uint32_t seed,
+                    uint32_t site, void* stream) {
+  if (!o1 || !o2 || !kp || !cat || rows < 0) return fail(MPO_E_ARG, "%s", "mpo_op_bil_kron: bad arguments");
+  if (rows == 0) return MPO_OK;
+  bil_kron_fwd_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(o1, o2, kp, cat, op_drop(drop_p, seed, site));
+  count_launch();
+  return check_cuda(cudaGetLastError(), "mpo_op_bil_kron");
+}
+
 }  // extern "C"

@@ -1124,6 +1124,34 @@ row_softmax_bwd_pair_kernel(const float* __restrict__ a, long long lda, const fl
     *reinterpret_cast<uint4*>(lr + c0) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
+// Stand-alone operators (mpo_op_*): LayerNorm over rows of any width (one warp per row, biased variance), and the
+// product of every row with its own scalar (the gates of GatedConcatFusion, models/fusion.py:34-38)
+__global__ void __launch_bounds__(256)
+op_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float* __restrict__ y, int rows, int cols, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + static_cast<long long>(row) * cols;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += xr[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / static_cast<float>(cols);
+  float v = 0.f;
+  for (int c = lane; c < cols; c += 32) { const float d = xr[c] - mean; v = fmaf(d, d, v); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = rsqrtf(v / static_cast<float>(cols) + eps);
+  for (int c = lane; c < cols; c += 32)
+    y[static_cast<long long>(row) * cols + c] = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+}
+__global__ void __launch_bounds__(256)
+op_rowscale_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ y, int rows, int cols) {
+  const long long n = static_cast<long long>(rows) * cols;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = x[i] * g[i / cols];
+}
 // GE-NaCAGaT train mode: attention-probability dropout of the N-token encoder layers (nn.TransformerEncoderLayer's
 // self_attn carries the layer's dropout rate).  out = dropout(p), element index = base + row * cols + col.
 __global__ void __launch_bounds__(256)
