@@ -183,6 +183,7 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       int it = 0;
       bool g_early = false;
       auto issue_g = [&](uint32_t a_tile) {
+        if (p.debug & 32) return;
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
@@ -204,12 +205,13 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         mbar_wait(c_bar, tph);
         if (!kHasG) mbar_wait(&full_bar[buf], ph);
         tc_fence_after();
-        if (!kLite) {
+        if (!kLite && !(p.debug & 4)) {
 #pragma unroll
           for (int k = 0; k < 3; ++k)
             umma_bf16(tmem_base + kColZ, umma_desc_sw128(aC + k * 32, 16, 1024), umma_desc_sw128(aD + k * 32, 16, 1024),
                       id_z, k != 0 ? 1u : 0u);
         }
+        if (!(p.debug & 1))
 #pragma unroll
         for (int mh = 0; mh < 2; ++mh)
 #pragma unroll
@@ -232,12 +234,13 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         tc_fence_after();
         const TileInfo ti = p.tile_info[t];
         const bool full_tile = !kLite && ti.nvalid == kTileM;
-        if (full_tile) {
+        if (full_tile && !(p.debug & 16)) {
 #pragma unroll
           for (int cb = 0; cb < 4; ++cb) tma_store_2d(&tm_out, smem + DzSmem::tile + buf * 65536 + cb * 16384, cb * 64, ti.row0);
           tma_store_commit();
         }
         if (kHasB) {
+          if (!(p.debug & 2))
 #pragma unroll
           for (int mh = 0; mh < 2; ++mh)
 #pragma unroll
@@ -520,7 +523,7 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         if (valid) *reinterpret_cast<uint4*>(p.mask_out + grow * 8 + ch * 4) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
       }
 #pragma unroll 1
-      for (int c4 = 0; c4 < (kLite ? 0 : 4); ++c4) {
+      for (int c4 = 0; c4 < ((kLite || (p.debug & 8)) ? 0 : 4); ++c4) {
         const int col0 = ch * 128 + c4 * 32;
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + kColZ + (static_cast<uint32_t>(qd * 32) << 16) + col0, v);
@@ -1109,7 +1112,11 @@ static cudaError_t launch_dz_mode(const CUtensorMap& tm_in, const CUtensorMap& t
   }
   if (prm.num_tiles <= 0) return cudaSuccess;
   const int grid = prm.num_tiles < num_sms ? prm.num_tiles : num_sms;
-  bag_bwd_dz_kernel<MODE><<<grid, kDzThreads, kDzSmemBytes, stream>>>(tm_in, tm_out, prm);
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("MPO_DZ_DEBUG"); dbg = e ? atoi(e) : 0; }
+  BagBwdDzParams prm_d = prm;
+  prm_d.debug = dbg;
+  bag_bwd_dz_kernel<MODE><<<grid, kDzThreads, kDzSmemBytes, stream>>>(tm_in, tm_out, prm_d);
   count_launch();
   return cudaGetLastError();
 }

@@ -126,6 +126,8 @@ struct BagBwdDzParams {
   const uint32_t* seed_dev;
   uint32_t attn_thr;           // attention dropout threshold (0 = off) and rescale factor
   float attn_scale;
+  int debug;                   // timing switches (MPO_DZ_DEBUG; results are wrong when set): 1 no MMA-dqk, 2 no MMA-db,
+                               // 4 no MMA-dZ, 8 no output-tile epilogue, 16 no TMA store, 32 no MMA-G
 };
 
 }  // namespace mpo

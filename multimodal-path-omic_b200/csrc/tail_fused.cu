@@ -41,6 +41,9 @@ constexpr int KW = KC / (NT / 32); // reduction elements of a chunk per warp
 constexpr int WLD = KC + 4;        // padded row pitch of a forward chunk [32][WLD]
 constexpr int CHUNK = 32 * WLD;    // floats per ring slot (a data-gradient chunk [256][32] fits as well)
 constexpr int NSTAGE = 3;
+// Depth of the weight ring by slides per cluster S of the kernel: the one-slide kernels (M = 6) sit twice on an SM and have room
+// for 3 slots; the two-slide kernels (S = 2, M = 12) own the SM and take 6, i.e. 5 chunks (80 KB) in flight per CTA
+template <int S> struct RingDepth { static constexpr int n = S == 2 ? 6 : NSTAGE; };
 constexpr int MAXK = 8;            // survival bins supported by the fused kernels
 constexpr int OMIC_LD = 608;       // shared-memory pitch of one omic input row (d_i <= 608)
 
@@ -158,8 +161,9 @@ struct Pipe {
   uint32_t ring;       // shared-memory address of the ring
   int n, rank;
   int cons;
+  int nst;             // ring slots: chunks cons .. cons + nst - 2 are in flight or landed
 };
-__device__ __noinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int rank, int c) {
+__device__ __noinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int rank, int c, int nst) {
   if (c < n) {
     const int t = threadIdx.x;
     unsigned long long base;
@@ -168,7 +172,7 @@ __device__ __noinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int 
     asm volatile("ld.shared.u64 %0, [%1];" : "=l"(base) : "r"(tbl + c * 16));
     const int ld = pk & 0xffff, kc = (pk >> 16) & 0x7fff, type = (pk >> 31) & 1;
     const float* src = reinterpret_cast<const float*>(base) + static_cast<size_t>(rank) * rs;
-    const uint32_t dst = ring + (c % NSTAGE) * (CHUNK * 4);
+    const uint32_t dst = ring + (c % nst) * (CHUNK * 4);
     // (1-D bulk copies by one warp were tried instead: 256 copies of 128 B per data-gradient chunk are far slower)
     if (type == T_FWD) {
       if (kc == KC) {
@@ -206,15 +210,16 @@ __device__ __noinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int 
   cp_async_commit();
 }
 // copies the chunk table to shared memory and puts the first two chunks in flight
-__device__ __forceinline__ void pipe_init(Pipe& pp, const Chunk* chunks, int n, float* tbl_smem, float* ring_smem, int rank) {
+__device__ __forceinline__ void pipe_init(Pipe& pp, const Chunk* chunks, int n, float* tbl_smem, float* ring_smem, int rank,
+                                          int nst = NSTAGE) {
   for (int i = threadIdx.x; i < n; i += NT) reinterpret_cast<Chunk*>(tbl_smem)[i] = chunks[i];
   __syncthreads();
-  pp.tbl = smem_addr(tbl_smem); pp.ring = smem_addr(ring_smem); pp.n = n; pp.rank = rank; pp.cons = 0;
-  pipe_issue(pp.tbl, pp.ring, pp.n, rank, 0);
-  pipe_issue(pp.tbl, pp.ring, pp.n, rank, 1);
+  pp.tbl = smem_addr(tbl_smem); pp.ring = smem_addr(ring_smem); pp.n = n; pp.rank = rank; pp.cons = 0; pp.nst = nst;
+  for (int c = 0; c < nst - 1; ++c) pipe_issue(pp.tbl, pp.ring, pp.n, rank, c, nst);
 }
-__device__ __forceinline__ void pipe_init(Pipe& pp, const Program& prog, float* tbl_smem, float* ring_smem, int rank) {
-  pipe_init(pp, prog.c, prog.n, tbl_smem, ring_smem, rank);
+__device__ __forceinline__ void pipe_init(Pipe& pp, const Program& prog, float* tbl_smem, float* ring_smem, int rank,
+                                          int nst = NSTAGE) {
+  pipe_init(pp, prog.c, prog.n, tbl_smem, ring_smem, rank, nst);
 }
 
 struct Dev {
@@ -247,7 +252,7 @@ __device__ __forceinline__ void gemm_step(uint32_t wk, uint32_t xk, unsigned lon
     acc[r] = fma2(w1, x1, fma2(w0, x0, acc[r]));
   }
 }
-template <int M, int TYPE, int LDX>
+template <int M, int TYPE, int LDX, int NST = NSTAGE>
 __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __restrict__ xs, int Ktot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t tbl = pp.tbl, ring = pp.ring;
@@ -257,10 +262,10 @@ __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __
 #pragma unroll
   for (int r = 0; r < M; ++r) acc[r] = 0ull;
   for (int kb = 0; kb < Ktot; kb += KC) {
-    cp_async_wait<NSTAGE - 2>();
+    cp_async_wait<NST - 2>();
     __syncthreads();
-    pipe_issue(tbl, ring, nchunks, rank, cons + 2);     // refills the slot freed by chunk cons - 1
-    const uint32_t wsm = ring + (cons % NSTAGE) * (CHUNK * 4);
+    pipe_issue(tbl, ring, nchunks, rank, cons + NST - 1, NST);     // refills the slot freed by chunk cons - 1
+    const uint32_t wsm = ring + (cons % NST) * (CHUNK * 4);
     ++cons;
     const int kc = min(KC, Ktot - kb);
     const int kbeg = warp * KW;
@@ -465,7 +470,7 @@ __device__ __forceinline__ void enc_fwd(Dev& d, const EncP& p, const EncW& w, in
     for (int blk = 0; blk < 3; ++blk) {
       const int col = blk * E + (d.rank * NB + nb) * 32 + d.lane;
       const float bias = bias_in[nb][blk];
-      gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
+      gemm_block<M, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XA, E);
       reduce_epi<M>(d, [&](int r, int, float v) {
         v += bias;
         QKVL[(nb * M + r) * 96 + blk * 32 + d.lane] = v;
@@ -516,7 +521,7 @@ __device__ __forceinline__ void enc_fwd(Dev& d, const EncP& p, const EncW& w, in
     const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float bias = bias_out[nb];
     const DropSpec d1 = site_of(dm, s0 + 1);
-    gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XB, E);
+    gemm_block<M, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XB, E);
     reduce_epi<M>(d, [&](int r, int, float v) {
       v += bias;
       if (d1.thr != 0) v = drop_fwd(v, d1, d.seedv, static_cast<uint32_t>(d.grow0 + r) * E + col);
@@ -532,7 +537,7 @@ __device__ __forceinline__ void enc_fwd(Dev& d, const EncP& p, const EncW& w, in
     const int col = d.rank * (64 * NB) + blk * 32 + d.lane;
     const float bias = bias_1[blk];
     const DropSpec d2 = site_of(dm, s0 + 2);
-    gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
+    gemm_block<M, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XA, E);
     reduce_epi<M>(d, [&](int r, int, float v) {
       v = fmaxf(v + bias, 0.f);
       const int grow = d.grow0 + r;
@@ -547,7 +552,7 @@ __device__ __forceinline__ void enc_fwd(Dev& d, const EncP& p, const EncW& w, in
     const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float bias = bias_2[nb];
     const DropSpec d3 = site_of(dm, s0 + 3);
-    gemm_block<M, T_FWD, FF>(*d.pipe, smem_addr(d.red), BIG, FF);
+    gemm_block<M, T_FWD, FF, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), BIG, FF);
     reduce_epi<M>(d, [&](int r, int, float v) {
       v += bias;
       if (d3.thr != 0) v = drop_fwd(v, d3, d.seedv, static_cast<uint32_t>(d.grow0 + r) * E + col);
@@ -580,7 +585,7 @@ __device__ __forceinline__ void enc_bwd(Dev& d, const EncP& p, const EncW& w, in
       const int grow = d.grow0 + d.warp + NW * i;
       fv[i] = (d.warp + NW * i < M && grow < d.Rtot) ? __ldcg(ws + w.f + static_cast<size_t>(grow) * FF + col) : 0.f;
     }
-    gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XC, E);
+    gemm_block<M, T_DGRAD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XC, E);
     reduce_epi<M>(d, [&](int r, int i, float v) {
       const int grow = d.grow0 + r;
       if (d2.thr != 0) v *= drop_grad(d2, d.seedv, static_cast<uint32_t>(grow) * FF + col);
@@ -593,7 +598,7 @@ __device__ __forceinline__ void enc_bwd(Dev& d, const EncP& p, const EncW& w, in
   // linear1 data gradient + the residual branch: dy1
   for (int nb = 0; nb < NB; ++nb) {
     const int col = (d.rank * NB + nb) * 32 + d.lane;
-    gemm_block<M, T_DGRAD, FF>(*d.pipe, smem_addr(d.red), BIG, FF);
+    gemm_block<M, T_DGRAD, FF, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), BIG, FF);
     reduce_epi<M>(d, [&](int r, int, float v) { bcast(XA + r * E + col, v + XB[r * E + col]); });
   }
   cluster_sync();
@@ -602,7 +607,7 @@ __device__ __forceinline__ void enc_bwd(Dev& d, const EncP& p, const EncW& w, in
   __syncthreads();
   // out-projection data gradient: this CTA's column blocks are its own heads
   for (int nb = 0; nb < NB; ++nb) {
-    gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XC, E);
+    gemm_block<M, T_DGRAD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XC, E);
     reduce_epi<M>(d, [&](int r, int, float v) { DCTX[(nb * M + r) * 32 + d.lane] = v; });
   }
   __syncthreads();
@@ -674,7 +679,7 @@ __device__ __forceinline__ void enc_bwd(Dev& d, const EncP& p, const EncW& w, in
   // in-projection data gradient + the residual branch: dx
   for (int nb = 0; nb < NB; ++nb) {
     const int col = (d.rank * NB + nb) * 32 + d.lane;
-    gemm_block<M, T_DGRAD, 768>(*d.pipe, smem_addr(d.red), BIG, 768);
+    gemm_block<M, T_DGRAD, 768, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), BIG, 768);
     reduce_epi<M>(d, [&](int r, int, float v) {
       v += XB[r * E + col];
       bcast(XA + r * E + col, v);
@@ -701,7 +706,7 @@ __device__ __forceinline__ void pool_fwd(Dev& d, const PoolP& p, const PoolW& w,
       const DropSpec ds = site_of(dq, SITE_POOL + 2 * pidx + br);
       float* dst = (br == 0 ? AL : BL) + nb * M * 32;
       const int off = br == 0 ? w.a : w.b;
-      gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
+      gemm_block<M, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XA, E);
       reduce_epi<M>(d, [&](int r, int, float v) {
         v += bias;
         v = br == 0 ? tanhf(v) : 1.f / (1.f + expf(-v));
@@ -757,7 +762,7 @@ __device__ __forceinline__ void pool_fwd(Dev& d, const PoolP& p, const PoolW& w,
     const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float bias = __ldg(p.br + col);
     const DropSpec dr = site_of(dm, SITE_RHO + pidx);
-    gemm_block<S, T_FWD, E>(*d.pipe, smem_addr(d.red), HP, E);
+    gemm_block<S, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), HP, E);
     reduce_epi<S>(d, [&](int s, int, float v) {
       v = fmaxf(v + bias, 0.f);
       const int slide = d.s0 + s;
@@ -779,7 +784,7 @@ __device__ __forceinline__ void pool_bwd(Dev& d, const PoolP& p, const PoolW& w,
   // rho data gradient
   for (int nb = 0; nb < NB; ++nb) {
     const int col = (d.rank * NB + nb) * 32 + d.lane;
-    gemm_block<S, T_DGRAD, 2 * E>(*d.pipe, smem_addr(d.red), DZR + pidx * E, E);
+    gemm_block<S, T_DGRAD, 2 * E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), DZR + pidx * E, E);
     reduce_epi<S>(d, [&](int s, int, float v) { bcast(DHP + s * E + col, v); });
   }
   // this pooling head's tokens, own columns of the two gate branches, pooling weights
@@ -859,7 +864,7 @@ __device__ __forceinline__ void pool_bwd(Dev& d, const PoolP& p, const PoolW& w,
   // gradient of the tokens: both gate branches' data gradients + the value path of the pooling
   for (int nb = 0; nb < NB; ++nb) {
     const int col = (d.rank * NB + nb) * 32 + d.lane;
-    gemm_block<M, T_DGRAD, FF>(*d.pipe, smem_addr(d.red), BIG, FF);          // chunks: attention_a then attention_b
+    gemm_block<M, T_DGRAD, FF, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), BIG, FF);          // chunks: attention_a then attention_b
     reduce_epi<M>(d, [&](int r, int, float v) {
       v = fmaf(AW[r], DHP[(r / 6) * E + col], v);
       bcast(XA + r * E + col, v);
@@ -873,7 +878,7 @@ template <int S>
 struct PathSmem {
   static constexpr int M = 6 * S;
   static constexpr int ring = 0;
-  static constexpr int XA = ring + NSTAGE * CHUNK;
+  static constexpr int XA = ring + RingDepth<S>::n * CHUNK;
   static constexpr int XB = XA + M * E;
   static constexpr int XC = XB + M * E;
   static constexpr int BIG = XC + M * E;
@@ -917,7 +922,7 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
   d.red = sm + L::RED;
   Pipe pipe;
   d.pipe = &pipe;
-  pipe_init(pipe, P.prog[role], sm + L::TBL, sm + L::ring, d.rank);
+  pipe_init(pipe, P.prog[role], sm + L::TBL, sm + L::ring, d.rank, RingDepth<S>::n);
   float* ws = P.ws;
   float *XA = sm + L::XA, *XB = sm + L::XB, *XC = sm + L::XC, *BIG = sm + L::BIG, *QKVL = sm + L::QKVL;
   float *AL = sm + L::AL, *BL = sm + L::BL, *PA = sm + L::PA, *AW = sm + L::AW, *HP = sm + L::HP, *CAT = sm + L::CAT;
@@ -954,7 +959,7 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
             const int grow = d.grow0 + d.warp + NW * i;
             sa[i] = (P.suma != nullptr && d.warp + NW * i < M && grow < d.Rtot) ? __ldcg(P.suma + grow) : 1.f;
           }
-          gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
+          gemm_block<M, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XA, E);
           reduce_epi<M>(d, [&](int r, int i, float v) {
             v = fmaf(bias, sa[i], v);
             bcast(XB + r * E + col, v);
@@ -965,7 +970,7 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
         for (int nb = 0; nb < NB; ++nb) {
           const int col = (d.rank * NB + nb) * 32 + d.lane;
           const float bias = __ldg(P.bo + col);
-          gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XB, E);
+          gemm_block<M, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XB, E);
           reduce_epi<M>(d, [&](int r, int, float v) {
             v += bias;
             bcast(XA + r * E + col, v);
@@ -983,13 +988,13 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
             const int col = (d.rank * NB + nb) * 32 + d.lane;
             const float b1 = __ldg(cp.b1 + col), b2 = __ldg(cp.b2 + col), b3 = __ldg(cp.b3 + col);
             float f1v[(M + NW - 1) / NW];
-            gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XB, E);
+            gemm_block<M, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XB, E);
             reduce_epi<M>(d, [&](int r, int i, float v) {
               v = elu_f(v + b1);
               f1v[i] = v;
               if (d.grow0 + r < d.Rtot) ws[cw.f1 + static_cast<size_t>(d.grow0 + r) * E + col] = v;
             });
-            gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XC, E);
+            gemm_block<M, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XC, E);
             reduce_epi<M>(d, [&](int r, int i, float v) {
               v = elu_f(v + b2);
               const float u = elu_f(f1v[i] + v);
@@ -999,7 +1004,7 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
                 ws[cw.u + static_cast<size_t>(d.grow0 + r) * E + col] = u;
               }
             });
-            gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XC, E);
+            gemm_block<M, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XC, E);
             reduce_epi<M>(d, [&](int r, int, float v) {
               v = elu_f(v + b3);
               const float wv = elu_f(v);
@@ -1023,7 +1028,7 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
           for (int nb = 0; nb < NB; ++nb) {
             const int col = (d.rank * NB + nb) * 32 + d.lane;
             const float bc = __ldg(cp.bc + col);
-            gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XB, E);
+            gemm_block<M, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XB, E);
             reduce_epi<M>(d, [&](int r, int, float v) {
               v = elu_f(v + bc);
               const float hv = XA[r * E + col] + v;
@@ -1058,7 +1063,7 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
     for (int nb = 0; nb < NB; ++nb) {
       const int col = (d.rank * NB + nb) * 32 + d.lane;
       const float bias = __ldg(P.bf0 + col);
-      gemm_block<S, T_FWD, 2 * E>(*d.pipe, smem_addr(d.red), CAT, 2 * E);
+      gemm_block<S, T_FWD, 2 * E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), CAT, 2 * E);
       reduce_epi<S>(d, [&](int s, int, float v) {
         v = fmaxf(v + bias, 0.f);
         bcast(Z1 + s * E + col, v);
@@ -1069,7 +1074,7 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
     for (int nb = 0; nb < NB; ++nb) {
       const int col = (d.rank * NB + nb) * 32 + d.lane;
       const float bias = __ldg(P.bf2 + col);
-      gemm_block<S, T_FWD, E>(*d.pipe, smem_addr(d.red), Z1, E);
+      gemm_block<S, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), Z1, E);
       reduce_epi<S>(d, [&](int s, int, float v) {
         v = fmaxf(v + bias, 0.f);
         bcast(Z2 + s * E + col, v);
@@ -1206,7 +1211,7 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
     __syncthreads();
     for (int nb = 0; nb < NB; ++nb) {
       const int col = (d.rank * NB + nb) * 32 + d.lane;
-      gemm_block<S, T_DGRAD, E>(*d.pipe, smem_addr(d.red), DZS, E);
+      gemm_block<S, T_DGRAD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), DZS, E);
       reduce_epi<S>(d, [&](int s, int, float v) {
         v = Z1[s * E + col] > 0.f ? v : 0.f;
         bcast(DZ1 + s * E + col, v);
@@ -1219,7 +1224,7 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
       const int c2 = d.rank * (64 * NB) + blk * 32 + d.lane;     // column of the [., 512] concat
       const int pidx = c2 >> 8, c = c2 & 255;
       const DropSpec dr = site_of(dm, SITE_RHO + pidx);
-      gemm_block<S, T_DGRAD, E>(*d.pipe, smem_addr(d.red), DZ1, E);
+      gemm_block<S, T_DGRAD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), DZ1, E);
       reduce_epi<S>(d, [&](int s, int, float v) {
         const int slide = d.s0 + s;
         float hv = CAT[s * 2 * E + c2];
@@ -1242,7 +1247,7 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
     if (br_lo == 0) {            // the path branch goes on to d(pooled) (and through the CAG for NaCAGaT)
     for (int nb = 0; nb < NB; ++nb) {
       const int col = (d.rank * NB + nb) * 32 + d.lane;
-      gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XA, E);
+      gemm_block<M, T_DGRAD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XA, E);
       reduce_epi<M>(d, [&](int r, int, float v) {
         bcast(XB + r * E + col, v);
         if (d.grow0 + r < d.Rtot) ws[P.off_dv + static_cast<size_t>(d.grow0 + r) * E + col] = v;
@@ -1260,7 +1265,7 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
     }
     for (int nb = 0; nb < NB; ++nb) {
       const int col = (d.rank * NB + nb) * 32 + d.lane;
-      gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XB, E);
+      gemm_block<M, T_DGRAD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XB, E);
       reduce_epi<M>(d, [&](int r, int, float v) {
         if (d.grow0 + r < d.Rtot) P.dpooled[static_cast<size_t>(d.grow0 + r) * E + col] = v;
       });
@@ -1290,7 +1295,7 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
           ee[i] = valid ? __ldcg(ws + cw.Ee + static_cast<size_t>(grow) * E + col) : 0.f;
           gg[i] = valid ? __ldcg(ws + cw.Gg + static_cast<size_t>(grow) * E + col) : 0.f;
         }
-        gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XB, E);
+        gemm_block<M, T_DGRAD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XB, E);
         reduce_epi<M>(d, [&](int r, int i, float v) {
           bcast(BIG + r * E + col, v * ee[i]);
           bcast(BIG + M * E + r * E + col, v * gg[i]);
@@ -1317,14 +1322,14 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
       }
       for (int nb = 0; nb < NB; ++nb) {                // dQ-hat = df3 W_3 + df2 W_2
         const int col = (d.rank * NB + nb) * 32 + d.lane;
-        gemm_block<M, T_DGRAD, FF>(*d.pipe, smem_addr(d.red), BIG, FF);
+        gemm_block<M, T_DGRAD, FF, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), BIG, FF);
         reduce_epi<M>(d, [&](int r, int, float v) {
           if (d.grow0 + r < d.Rtot) ws[P.off_dqp + static_cast<size_t>(d.grow0 + r) * E + col] = v;
         });
       }
       for (int nb = 0; nb < NB; ++nb) {                // dQ = df1 W_1 (pre_bwd_kernel adds it to the omic branch's dG)
         const int col = (d.rank * NB + nb) * 32 + d.lane;
-        gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XA, E);
+        gemm_block<M, T_DGRAD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XA, E);
         reduce_epi<M>(d, [&](int r, int, float v) {
           if (d.grow0 + r < d.Rtot) ws[P.off_dG2 + static_cast<size_t>(d.grow0 + r) * E + col] = v;
         });
@@ -1365,7 +1370,7 @@ template <int S>
 struct PreSmem {
   static constexpr int M = 6 * S;
   static constexpr int ring = 0;
-  static constexpr int XO = ring + NSTAGE * CHUNK;       // [6][S][OMIC_LD] omic inputs
+  static constexpr int XO = ring + RingDepth<S>::n * CHUNK;       // [6][S][OMIC_LD] omic inputs
   static constexpr int H1 = XO + MPO_Q * S * OMIC_LD;    // [6][S][256]
   static constexpr int G = H1 + MPO_Q * S * E;           // [M][256]
   static constexpr int QP = G + M * E;                   // [M][256]
@@ -1391,7 +1396,7 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
   d.red = sm + L::RED;
   Pipe pipe;
   d.pipe = &pipe;
-  pipe_init(pipe, P.prog, sm + L::TBL, sm + L::ring, d.rank);
+  pipe_init(pipe, P.prog, sm + L::TBL, sm + L::ring, d.rank, RingDepth<S>::n);
   float* ws = P.ws;
   float *XO = sm + L::XO, *H1 = sm + L::H1, *G = sm + L::G, *QP = sm + L::QP;
   if (P.skip_snn) load_rows<M>(d, G, ws + P.off_G, d.grow0, d.Rtot);      // G_bag comes from snn_fwd_kernel
@@ -1408,7 +1413,7 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
     const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float bias = __ldg(P.b1[i] + col);
     const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * i);
-    gemm_block<S, T_FWD, OMIC_LD>(*d.pipe, smem_addr(d.red), XO + i * S * OMIC_LD, P.omic_dims[i]);
+    gemm_block<S, T_FWD, OMIC_LD, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XO + i * S * OMIC_LD, P.omic_dims[i]);
     reduce_epi<S>(d, [&](int s, int, float v) {
       v += bias;
       v = v > 0.f ? v : expm1f(v);
@@ -1424,7 +1429,7 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
     const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float bias = __ldg(P.b2[i] + col);
     const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * i + 1);
-    gemm_block<S, T_FWD, E>(*d.pipe, smem_addr(d.red), H1 + i * S * E, E);
+    gemm_block<S, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), H1 + i * S * E, E);
     reduce_epi<S>(d, [&](int s, int, float v) {
       v += bias;
       v = v > 0.f ? v : expm1f(v);
@@ -1438,7 +1443,7 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
   for (int nb = 0; nb < NB; ++nb) {
     const int col = (d.rank * NB + nb) * 32 + d.lane;
     const float bias = __ldg(P.bq + col);
-    gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), G, E);
+    gemm_block<M, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), G, E);
     reduce_epi<M>(d, [&](int r, int, float v) {
       v += bias;
       bcast(QP + r * E + col, v);
@@ -1457,7 +1462,7 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
   }
   for (int nb = 0; nb < NB; ++nb) {
     const int col = (d.rank * NB + nb) * 32 + d.lane;
-    gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), QP, E);
+    gemm_block<M, T_DGRAD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), QP, E);
     reduce_epi<M>(d, [&](int r, int, float v) {
       if (d.grow0 + r < d.Rtot) P.qk[static_cast<size_t>(d.grow0 + r) * E + col] = v * (1.f / 16.f);
     });
@@ -1482,7 +1487,7 @@ __global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ 
   d.red = sm + L::RED;
   Pipe pipe;
   d.pipe = &pipe;
-  pipe_init(pipe, P.prog, sm + L::TBL, sm + L::ring, d.rank);
+  pipe_init(pipe, P.prog, sm + L::TBL, sm + L::ring, d.rank, RingDepth<S>::n);
   float* ws = P.ws;
   float *XA = sm + L::G, *XB = sm + L::QP, *DZ2 = sm + L::H1;     // DZ2: [M][256], row s*6+i
   load_rows<M>(d, XA, P.dqk, d.grow0, d.Rtot);
@@ -1503,7 +1508,7 @@ __global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ 
                    __ldcg(P.dtq + o) * (1.f - tq * tq);
       }
     }
-    gemm_block<M, T_FWD, E>(*d.pipe, smem_addr(d.red), XA, E);
+    gemm_block<M, T_FWD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XA, E);
     reduce_epi<M>(d, [&](int r, int i, float v) {
       v = fmaf(v, 1.f / 16.f, extra[i]);
       bcast(XB + r * E + col, v);
@@ -1523,7 +1528,7 @@ __global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ 
       if (valid && P.nac) dg0[i] += __ldcg(ws + P.off_dG2 + static_cast<size_t>(grow) * E + col);
       gv[i] = valid ? __ldcg(ws + P.off_G + static_cast<size_t>(grow) * E + col) : 0.f;
     }
-    gemm_block<M, T_DGRAD, E>(*d.pipe, smem_addr(d.red), XB, E);
+    gemm_block<M, T_DGRAD, E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), XB, E);
     reduce_epi<M>(d, [&](int r, int i, float v) {
       v += dg0[i];
       if (P.skip_snn) {                 // total gradient of G_bag, consumed by snn_bwd_kernel
@@ -1548,7 +1553,7 @@ __global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ 
     for (int s = 0; s < S; ++s)
       hv[s] = (d.s0 + s < d.B) ? __ldcg(ws + P.off_snn_h[i] + static_cast<size_t>(d.s0 + s) * E + col) : 0.f;
     const DropSpec ds = site_of(P.d_alpha, SITE_SNN + 2 * i);
-    gemm_block<S, T_DGRAD, 6 * E>(*d.pipe, smem_addr(d.red), DZ2 + i * E, E);
+    gemm_block<S, T_DGRAD, 6 * E, RingDepth<S>::n>(*d.pipe, smem_addr(d.red), DZ2 + i * E, E);
     reduce_epi<S>(d, [&](int s, int, float v) {
       const int slide = d.s0 + s;
       float y = hv[s];
