@@ -93,13 +93,28 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// Phase timing of the path kernels (-DMPO_TAIL_PROF builds only; scripts/gpu_tail_prof.py): thread 0 of CTA 0 adds clock64
+// intervals to g_prof[8 * pass + phase]; phase 0 whole kernel, 1 gemm_block total, 2 ring wait + CTA barrier, 3 chunk
+// issue, 4 FFMA2 block, 5 partial store + CTA barrier, 6 cluster barriers, 7 gemm_block calls
+#ifdef MPO_TAIL_PROF
+__device__ unsigned long long g_prof[32];
+__device__ int g_prof_pass;
+#define PROF_ON (blockIdx.x == 0 && threadIdx.x == 0)
+#define PROF_T() (PROF_ON ? clock64() : 0ll)
+#define PROF_ADD(i, v) do { if (PROF_ON) g_prof[8 * g_prof_pass + (i)] += static_cast<unsigned long long>(v); } while (0)
+#else
+#define PROF_T() 0ll
+#define PROF_ADD(i, v) do { } while (0)
+#endif
 __device__ __forceinline__ int cluster_rank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return static_cast<int>(r);
 }
 __device__ __forceinline__ void cluster_sync() {
+  const long long pt0 = PROF_T();
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  PROF_ADD(6, PROF_T() - pt0);
 }
 // store v at the same shared-memory offset in every CTA of the cluster
 template <int N>
@@ -157,69 +172,81 @@ __device__ __forceinline__ float warp_sum(float v) {
 // cp.async ring over the chunk sequence of a Program (copied to shared memory at kernel start); chunk c lives in
 // slot c % NSTAGE and chunks cons and cons+1 are always in flight or landed
 struct Pipe {
-  uint32_t tbl;        // shared-memory address of the chunk table
+  uint32_t tbl;        // shared-memory address of the chunk table (bases already offset by the cluster rank)
   uint32_t ring;       // shared-memory address of the ring
   int n, rank;
-  int cons;
-  int nst;             // ring slots: chunks cons .. cons + nst - 2 are in flight or landed
+  int cons;            // next chunk to consume; chunks cons .. cons + NST - 2 are in flight or landed
+  int slot;            // ring slot of chunk `cons` (kept incrementally: no modulo in the loop)
 };
-__device__ __noinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int rank, int c, int nst) {
+// partial chunks (kc < KC: the omic input layers and ragged reduction tails) -- rare, kept out of line
+__device__ __noinline__ void pipe_issue_partial(const float* src, int ld, int kc, int type, uint32_t dst) {
+  const int t = threadIdx.x;
+  if (type == T_FWD) {
+    const int per_row = kc >> 2;
+    for (int p = t; p < 32 * per_row; p += NT) {
+      const int row = p / per_row, c4 = p - row * per_row;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (row * WLD + c4 * 4) * 4),
+                   "l"(src + static_cast<size_t>(row) * ld + c4 * 4) : "memory");
+    }
+  } else {
+    // rows (t >> 3) + 32 j of the chunk, 16 B at column 4 (t & 7)
+    const float* s0 = src + static_cast<size_t>(t >> 3) * ld + (t & 7) * 4;
+    const uint32_t d0 = dst + ((t >> 3) * 32 + (t & 7) * 4) * 4;
+    const size_t sstep = static_cast<size_t>(32) * ld;
+    for (int j = 0; j * 32 + (t >> 3) < kc; ++j)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * (32 * 32 * 4)), "l"(s0 + j * sstep) : "memory");
+  }
+}
+// Puts chunk c into ring slot `slot`: every thread copies 4 x 16 B.  Inlined into the GEMM blocks with one code path for
+// both chunk types (selects, no branches): as an out-of-line call that decoded the table entry, took a modulo and
+// converted the global-memory descriptor for every copy it cost ~680 cycles per chunk, 22 % of the path kernels
+// (phase timing of the -DMPO_TAIL_PROF build, profiles/r2d_tail_phase_timing.txt).
+// (1-D bulk copies by one warp were tried instead: 256 copies of 128 B per data-gradient chunk are far slower)
+__device__ __forceinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int c, int slot) {
   if (c < n) {
     const int t = threadIdx.x;
-    unsigned long long base;
-    int rs, pk;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rs), "=r"(pk) : "r"(tbl + c * 16 + 8));
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(base) : "r"(tbl + c * 16));
-    const int ld = pk & 0xffff, kc = (pk >> 16) & 0x7fff, type = (pk >> 31) & 1;
-    const float* src = reinterpret_cast<const float*>(base) + static_cast<size_t>(rank) * rs;
-    const uint32_t dst = ring + (c % nst) * (CHUNK * 4);
-    // (1-D bulk copies by one warp were tried instead: 256 copies of 128 B per data-gradient chunk are far slower)
-    if (type == T_FWD) {
-      if (kc == KC) {
-        // thread t copies 16 B of rows t / PR + RP j (PR pieces per row): strength-reduced addresses
-        constexpr int PR = KC / 4, RP = NT / PR;
-        const float* s0 = src + static_cast<size_t>(t / PR) * ld + (t % PR) * 4;
-        const uint32_t d0 = dst + ((t / PR) * WLD + (t % PR) * 4) * 4;
-        const size_t sstep = static_cast<size_t>(RP) * ld;
+    uint32_t b_lo, b_hi, rs, pk;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b_lo), "=r"(b_hi), "=r"(rs), "=r"(pk) : "r"(tbl + c * 16));
+    const float* src = reinterpret_cast<const float*>(static_cast<unsigned long long>(b_lo) |
+                                                      (static_cast<unsigned long long>(b_hi) << 32));
+    const int ld = pk & 0xffff, kc = (pk >> 16) & 0x7fff;
+    const bool dg = (pk >> 31) != 0u;
+    const uint32_t dst = ring + slot * (CHUNK * 4);
+    if (kc == KC) {
+      // forward chunk [32 rows][KC]: rows t / 32 + 8 j, 16 B at column 4 (t % 32), row pitch WLD in shared memory;
+      // data-gradient chunk [KC rows][32]: rows t / 8 + 32 j, 16 B at column 4 (t % 8), dense
+      const int row = dg ? (t >> 3) : (t >> 5);
+      const int seg = dg ? (t & 7) : (t & 31);
+      const uint32_t d0 = dst + (row * (dg ? 32 : WLD) + seg * 4) * 4;
+      const uint32_t dstep = dg ? 32 * 32 * 4 : 8 * WLD * 4;
+      const float* s0 = src + (row * ld + seg * 4);
+      const size_t sstep = static_cast<size_t>((dg ? 32 : 8) * ld);
 #pragma unroll
-        for (int j = 0; j < 32 / RP; ++j)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * (RP * WLD * 4)), "l"(s0 + j * sstep) : "memory");
-      } else {
-        const int per_row = kc >> 2;
-        for (int p = t; p < 32 * per_row; p += NT) {
-          const int row = p / per_row, c4 = p - row * per_row;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (row * WLD + c4 * 4) * 4),
-                       "l"(src + static_cast<size_t>(row) * ld + c4 * 4) : "memory");
-        }
-      }
+      for (int j = 0; j < 4; ++j)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * dstep), "l"(s0 + j * sstep) : "memory");
     } else {
-      // rows (t >> 3) + 32 j of the chunk, 16 B at column 4 (t & 7)
-      const float* s0 = src + static_cast<size_t>(t >> 3) * ld + (t & 7) * 4;
-      const uint32_t d0 = dst + ((t >> 3) * 32 + (t & 7) * 4) * 4;
-      const size_t sstep = static_cast<size_t>(32) * ld;
-      if (kc == KC) {
-#pragma unroll
-        for (int j = 0; j < KC / 32; ++j)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * (32 * 32 * 4)), "l"(s0 + j * sstep) : "memory");
-      } else {
-        for (int j = 0; j * 32 + (t >> 3) < kc; ++j)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * (32 * 32 * 4)), "l"(s0 + j * sstep) : "memory");
-      }
+      pipe_issue_partial(src, ld, kc, dg ? T_DGRAD : T_FWD, dst);
     }
   }
   cp_async_commit();
 }
-// copies the chunk table to shared memory and puts the first two chunks in flight
-__device__ __forceinline__ void pipe_init(Pipe& pp, const Chunk* chunks, int n, float* tbl_smem, float* ring_smem, int rank,
-                                          int nst = NSTAGE) {
-  for (int i = threadIdx.x; i < n; i += NT) reinterpret_cast<Chunk*>(tbl_smem)[i] = chunks[i];
+// copies the chunk table to shared memory (folding the cluster rank into the chunk bases) and puts the first NST - 1
+// chunks in flight
+template <int NST = NSTAGE>
+__device__ __forceinline__ void pipe_init(Pipe& pp, const Chunk* chunks, int n, float* tbl_smem, float* ring_smem, int rank) {
+  for (int i = threadIdx.x; i < n; i += NT) {
+    Chunk c = chunks[i];
+    c.base += static_cast<size_t>(rank) * c.rank_stride;
+    reinterpret_cast<Chunk*>(tbl_smem)[i] = c;
+  }
   __syncthreads();
-  pp.tbl = smem_addr(tbl_smem); pp.ring = smem_addr(ring_smem); pp.n = n; pp.rank = rank; pp.cons = 0; pp.nst = nst;
-  for (int c = 0; c < nst - 1; ++c) pipe_issue(pp.tbl, pp.ring, pp.n, rank, c, nst);
+  pp.tbl = smem_addr(tbl_smem); pp.ring = smem_addr(ring_smem); pp.n = n; pp.rank = rank; pp.cons = 0; pp.slot = 0;
+#pragma unroll
+  for (int c = 0; c < NST - 1; ++c) pipe_issue(pp.tbl, pp.ring, pp.n, c, c);
 }
-__device__ __forceinline__ void pipe_init(Pipe& pp, const Program& prog, float* tbl_smem, float* ring_smem, int rank,
-                                          int nst = NSTAGE) {
-  pipe_init(pp, prog.c, prog.n, tbl_smem, ring_smem, rank, nst);
+template <int NST = NSTAGE>
+__device__ __forceinline__ void pipe_init(Pipe& pp, const Program& prog, float* tbl_smem, float* ring_smem, int rank) {
+  pipe_init<NST>(pp, prog.c, prog.n, tbl_smem, ring_smem, rank);
 }
 
 struct Dev {
@@ -256,17 +283,24 @@ template <int M, int TYPE, int LDX, int NST = NSTAGE>
 __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __restrict__ xs, int Ktot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t tbl = pp.tbl, ring = pp.ring;
-  const int nchunks = pp.n, rank = pp.rank;
-  int cons = pp.cons;
+  const int nchunks = pp.n;
+  int cons = pp.cons, slot = pp.slot;
+  const long long pt_in = PROF_T();
+  long long pt_d = pt_in;
   unsigned long long acc[M];
 #pragma unroll
   for (int r = 0; r < M; ++r) acc[r] = 0ull;
   for (int kb = 0; kb < Ktot; kb += KC) {
+    const long long pt_a = PROF_T();
     cp_async_wait<NST - 2>();
     __syncthreads();
-    pipe_issue(tbl, ring, nchunks, rank, cons + NST - 1, NST);     // refills the slot freed by chunk cons - 1
-    const uint32_t wsm = ring + (cons % NST) * (CHUNK * 4);
+    const long long pt_b = PROF_T();
+    pipe_issue(tbl, ring, nchunks, cons + NST - 1, slot == 0 ? NST - 1 : slot - 1);     // the slot freed by chunk cons - 1
+    const long long pt_c = PROF_T();
+    PROF_ADD(2, pt_b - pt_a); PROF_ADD(3, pt_c - pt_b);
+    const uint32_t wsm = ring + slot * (CHUNK * 4);
     ++cons;
+    slot = slot + 1 == NST ? 0 : slot + 1;
     const int kc = min(KC, Ktot - kb);
     const int kbeg = warp * KW;
     // this warp's KW reduction elements: k-step stride is 16 B in x and in a forward chunk row, 4 rows in a dgrad chunk
@@ -280,8 +314,18 @@ __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __
       const int nst = (min(kbeg + KW, kc) - kbeg) >> 2;       // may be <= 0
       for (int j = 0; j < nst; ++j) gemm_step<M, TYPE, LDX>(wk + j * WSTEP, xk + j * 16, acc);
     }
+#ifdef MPO_TAIL_PROF
+    {   // (the accumulators have to be complete for the interval to mean anything)
+      unsigned long long sink = 0;
+#pragma unroll
+      for (int r = 0; r < M; ++r) sink ^= acc[r];
+      if (sink == 0x123456789abcdefull) g_prof[31] = 1;
+    }
+#endif
+    pt_d = PROF_T();
+    PROF_ADD(4, pt_d - pt_c);
   }
-  pp.cons = cons;
+  pp.cons = cons; pp.slot = slot;
   // this warp's k-slice partials; reduce_epi() sums the 8 slices
   const uint32_t red = red0 + ((warp * M) * 32 + lane) * 4;
 #pragma unroll
@@ -291,6 +335,8 @@ __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + r * 128), "f"(lo + hi) : "memory");
   }
   __syncthreads();
+  const long long pt_e = PROF_T();
+  PROF_ADD(5, pt_e - pt_d); PROF_ADD(1, pt_e - pt_in); PROF_ADD(7, 1);
 }
 // sums the 8 k-slices; thread (warp, lane) finishes outputs (row warp + 8 i, column lane): epi(row, i, value)
 template <int M, class Epi>
@@ -908,6 +954,10 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
   constexpr int M = 6 * S;
   using L = PathSmem<S>;
   extern __shared__ __align__(16) float sm[];
+#ifdef MPO_TAIL_PROF
+  if (PROF_ON) g_prof_pass = (P.flags & F_FWD) ? 0 : 1;
+  const long long pt_k0 = PROF_T();
+#endif
   Dev d;
   d.rank = cluster_rank();
   d.t = threadIdx.x; d.lane = d.t & 31; d.warp = d.t >> 5;
@@ -922,7 +972,7 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
   d.red = sm + L::RED;
   Pipe pipe;
   d.pipe = &pipe;
-  pipe_init(pipe, P.prog[role], sm + L::TBL, sm + L::ring, d.rank, RingDepth<S>::n);
+  pipe_init<RingDepth<S>::n>(pipe, P.prog[role], sm + L::TBL, sm + L::ring, d.rank);
   float* ws = P.ws;
   float *XA = sm + L::XA, *XB = sm + L::XB, *XC = sm + L::XC, *BIG = sm + L::BIG, *QKVL = sm + L::QKVL;
   float *AL = sm + L::AL, *BL = sm + L::BL, *PA = sm + L::PA, *AW = sm + L::AW, *HP = sm + L::HP, *CAT = sm + L::CAT;
@@ -1339,6 +1389,10 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
   }
   cp_async_wait<0>();
   cluster_sync();                         // no CTA exits while a peer may still store into its shared memory
+#ifdef MPO_TAIL_PROF
+  PROF_ADD(0, PROF_T() - pt_k0);
+  if (PROF_ON) g_prof_pass = 2;           // the pre / SNN kernels in between land in a scratch bucket
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ pre kernels
@@ -1396,7 +1450,7 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
   d.red = sm + L::RED;
   Pipe pipe;
   d.pipe = &pipe;
-  pipe_init(pipe, P.prog, sm + L::TBL, sm + L::ring, d.rank, RingDepth<S>::n);
+  pipe_init<RingDepth<S>::n>(pipe, P.prog, sm + L::TBL, sm + L::ring, d.rank);
   float* ws = P.ws;
   float *XO = sm + L::XO, *H1 = sm + L::H1, *G = sm + L::G, *QP = sm + L::QP;
   if (P.skip_snn) load_rows<M>(d, G, ws + P.off_G, d.grow0, d.Rtot);      // G_bag comes from snn_fwd_kernel
@@ -1487,7 +1541,7 @@ __global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ 
   d.red = sm + L::RED;
   Pipe pipe;
   d.pipe = &pipe;
-  pipe_init(pipe, P.prog, sm + L::TBL, sm + L::ring, d.rank, RingDepth<S>::n);
+  pipe_init<RingDepth<S>::n>(pipe, P.prog, sm + L::TBL, sm + L::ring, d.rank);
   float* ws = P.ws;
   float *XA = sm + L::G, *XB = sm + L::QP, *DZ2 = sm + L::H1;     // DZ2: [M][256], row s*6+i
   load_rows<M>(d, XA, P.dqk, d.grow0, d.Rtot);
@@ -2502,3 +2556,17 @@ int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, cons
 
 }  // namespace fused
 }  // namespace mpo
+
+#ifdef MPO_TAIL_PROF
+extern "C" int mpo_tail_prof_read(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, mpo::fused::g_prof, 32 * sizeof(unsigned long long));
+  if (reset) {
+    unsigned long long z[32] = {};
+    int two = 2;
+    cudaMemcpyToSymbol(mpo::fused::g_prof, z, sizeof(z));
+    cudaMemcpyToSymbol(mpo::fused::g_prof_pass, &two, sizeof(int));
+  }
+  return 0;
+}
+#endif
