@@ -279,17 +279,47 @@ __device__ __forceinline__ void gemm_step(uint32_t wk, uint32_t xk, unsigned lon
     acc[r] = fma2(w1, x1, fma2(w0, x0, acc[r]));
   }
 }
+// Half-warp form (M <= 12): lanes 0..15 take reduction quad 2 j, lanes 16..31 quad 2 j + 1, each for 16 columns at a time
+// (group A = the lane's own half of the 32 columns, group B = the other half, so that the two halves of the warp never
+// meet in a bank).  An activation load then fetches TWO distinct quads per instruction for the same two wavefronts a
+// full broadcast costs: 20 shared-memory wavefronts per 8 reduction elements instead of 32 (the path kernels are paced by
+// the shared-memory pipe, profiles/r2d_tail_phase_timing.txt), and 8 loads instead of 14 per 24 FFMA2.
+template <int M, int TYPE, int LDX>
+__device__ __forceinline__ void gemm_step2(uint32_t wa, uint32_t wb, uint32_t xk, unsigned long long (&acc)[M][2]) {
+  unsigned long long a0, a1, b0, b1;
+  if (TYPE == T_FWD) {
+    lds2x64(wa, a0, a1);
+    lds2x64(wb, b0, b1);
+  } else {
+    a0 = pack2(lds32(wa), lds32(wa + 128));
+    a1 = pack2(lds32(wa + 256), lds32(wa + 384));
+    b0 = pack2(lds32(wb), lds32(wb + 128));
+    b1 = pack2(lds32(wb + 256), lds32(wb + 384));
+  }
+#pragma unroll
+  for (int r = 0; r < M; ++r) {
+    unsigned long long x0, x1;
+    lds2x64(xk + r * LDX * 4, x0, x1);
+    acc[r][0] = fma2(a1, x1, fma2(a0, x0, acc[r][0]));
+    acc[r][1] = fma2(b1, x1, fma2(b0, x0, acc[r][1]));
+  }
+}
 template <int M, int TYPE, int LDX, int NST = NSTAGE>
 __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __restrict__ xs, int Ktot) {
+  constexpr bool kHalf = M <= 12;        // half-warp form (gemm_step2); the 32-row SNN blocks keep one column per lane
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hc = lane & 15, hh = lane >> 4;
   const uint32_t tbl = pp.tbl, ring = pp.ring;
   const int nchunks = pp.n;
   int cons = pp.cons, slot = pp.slot;
   const long long pt_in = PROF_T();
   long long pt_d = pt_in;
-  unsigned long long acc[M];
+  unsigned long long acc[kHalf ? 1 : M];
+  unsigned long long acc2[kHalf ? M : 1][2];
 #pragma unroll
-  for (int r = 0; r < M; ++r) acc[r] = 0ull;
+  for (int r = 0; r < (kHalf ? 1 : M); ++r) acc[r] = 0ull;
+#pragma unroll
+  for (int r = 0; r < (kHalf ? M : 1); ++r) acc2[r][0] = acc2[r][1] = 0ull;
   for (int kb = 0; kb < Ktot; kb += KC) {
     const long long pt_a = PROF_T();
     cp_async_wait<NST - 2>();
@@ -303,22 +333,42 @@ __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __
     slot = slot + 1 == NST ? 0 : slot + 1;
     const int kc = min(KC, Ktot - kb);
     const int kbeg = warp * KW;
-    // this warp's KW reduction elements: k-step stride is 16 B in x and in a forward chunk row, 4 rows in a dgrad chunk
-    const uint32_t xk = smem_addr(xs) + (kb + kbeg) * 4;
-    const uint32_t wk = TYPE == T_FWD ? wsm + (lane * WLD + kbeg) * 4 : wsm + (kbeg * 32 + lane) * 4;
-    constexpr int WSTEP = TYPE == T_FWD ? 16 : 4 * 128;
-    if (kc == KC) {
+    if constexpr (kHalf) {
+      // this warp's KW reduction elements as KW / 8 pairs of quads; quad 2 j + hh is this lane's
+      const int k0 = kbeg + 4 * hh;
+      const uint32_t xk = smem_addr(xs) + (kb + k0) * 4;
+      const int ca = 16 * hh + hc, cb = 16 * (1 - hh) + hc;
+      const uint32_t wa = TYPE == T_FWD ? wsm + (ca * WLD + k0) * 4 : wsm + (k0 * 32 + ca) * 4;
+      const uint32_t wb = TYPE == T_FWD ? wsm + (cb * WLD + k0) * 4 : wsm + (k0 * 32 + cb) * 4;
+      constexpr int WSTEP = TYPE == T_FWD ? 32 : 8 * 128;
+      if (kc == KC) {
 #pragma unroll
-      for (int j = 0; j < KW / 4; ++j) gemm_step<M, TYPE, LDX>(wk + j * WSTEP, xk + j * 16, acc);
+        for (int j = 0; j < KW / 8; ++j) gemm_step2<M, TYPE, LDX>(wa + j * WSTEP, wb + j * WSTEP, xk + j * 32, acc2);
+      } else {
+        const int nq = (min(kbeg + KW, kc) - kbeg) >> 2;       // valid quads of this warp's slice, may be <= 0
+        for (int j = 0; j < KW / 8; ++j)
+          if (2 * j + hh < nq) gemm_step2<M, TYPE, LDX>(wa + j * WSTEP, wb + j * WSTEP, xk + j * 32, acc2);
+      }
     } else {
-      const int nst = (min(kbeg + KW, kc) - kbeg) >> 2;       // may be <= 0
-      for (int j = 0; j < nst; ++j) gemm_step<M, TYPE, LDX>(wk + j * WSTEP, xk + j * 16, acc);
+      // this warp's KW reduction elements: k-step stride is 16 B in x and in a forward chunk row, 4 rows in a dgrad chunk
+      const uint32_t xk = smem_addr(xs) + (kb + kbeg) * 4;
+      const uint32_t wk = TYPE == T_FWD ? wsm + (lane * WLD + kbeg) * 4 : wsm + (kbeg * 32 + lane) * 4;
+      constexpr int WSTEP = TYPE == T_FWD ? 16 : 4 * 128;
+      if (kc == KC) {
+#pragma unroll
+        for (int j = 0; j < KW / 4; ++j) gemm_step<M, TYPE, LDX>(wk + j * WSTEP, xk + j * 16, acc);
+      } else {
+        const int nst = (min(kbeg + KW, kc) - kbeg) >> 2;       // may be <= 0
+        for (int j = 0; j < nst; ++j) gemm_step<M, TYPE, LDX>(wk + j * WSTEP, xk + j * 16, acc);
+      }
     }
 #ifdef MPO_TAIL_PROF
     {   // (the accumulators have to be complete for the interval to mean anything)
       unsigned long long sink = 0;
 #pragma unroll
-      for (int r = 0; r < M; ++r) sink ^= acc[r];
+      for (int r = 0; r < (kHalf ? 1 : M); ++r) sink ^= acc[r];
+#pragma unroll
+      for (int r = 0; r < (kHalf ? M : 1); ++r) sink ^= acc2[r][0] ^ acc2[r][1];
       if (sink == 0x123456789abcdefull) g_prof[31] = 1;
     }
 #endif
@@ -330,9 +380,19 @@ __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __
   const uint32_t red = red0 + ((warp * M) * 32 + lane) * 4;
 #pragma unroll
   for (int r = 0; r < M; ++r) {
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[r]));
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + r * 128), "f"(lo + hi) : "memory");
+    float v;
+    if constexpr (kHalf) {
+      // column `lane` = group A of this lane + group B of the lane in the other half
+      float alo, ahi, blo, bhi;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(alo), "=f"(ahi) : "l"(acc2[r][0]));
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(blo), "=f"(bhi) : "l"(acc2[r][1]));
+      v = (alo + ahi) + __shfl_xor_sync(0xffffffffu, blo + bhi, 16);
+    } else {
+      float lo, hi;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[r]));
+      v = lo + hi;
+    }
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + r * 128), "f"(v) : "memory");
   }
   __syncthreads();
   const long long pt_e = PROF_T();
