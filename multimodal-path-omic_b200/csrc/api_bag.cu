@@ -77,6 +77,11 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 // 2-D row-major fp32 tensor [rows][cols] with a row pitch of `pitch` elements (pitch * 4 B a multiple of 16 B);
 // box = 32 x box_rows (128 B wide), 128-byte swizzle: the store target of the tensor-core GEMM's epilogue
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows) {
+  return make_tmap_f32_2d_sw(out, base, rows, cols, pitch, box_rows, true);
+}
+// same with the swizzle selectable (false: the box lands dense, rows of 128 B): the weight ring of the fused tail
+int make_tmap_f32_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows,
+                        bool swizzle128) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(MPO_E_CUDA, "%s", "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t dims[2] = {cols, rows};
@@ -84,10 +89,30 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   cuuint32_t box[2] = {32, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", static_cast<int>(r));
+    return MPO_E_CUDA;
+  }
+  return MPO_OK;
+}
+
+// fp32 matrix [rows][ld] (ld a multiple of 32) seen as [ld / 32][rows][32]: one box {32, 32 rows, kblocks} delivers a
+// [32 rows][32 * kblocks] block of the matrix as `kblocks` consecutive 128-byte-swizzled [32][32] tiles with ONE copy
+// (the forward chunks of the fused tail's weight ring)
+int make_tmap_f32_rows32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t ld, uint32_t kblocks) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(MPO_E_CUDA, "%s", "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t dims[3] = {32, rows, ld / 32};
+  cuuint64_t strides[2] = {ld * 4, 128};
+  cuuint32_t box[3] = {32, 32, kblocks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", static_cast<int>(r));
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled (fp32, 3-D row view) failed with CUresult %d", static_cast<int>(r));
     return MPO_E_CUDA;
   }
   return MPO_OK;

@@ -17,6 +17,9 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int launch_adam(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
                 float eps, float weight_decay, int32_t* step_dev, bool zero_grad, bool bump, cudaStream_t st);
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows);
+int make_tmap_f32_rows32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t ld, uint32_t kblocks);
+int make_tmap_f32_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows,
+                        bool swizzle128);
 int fwd_cluster_size();   // CTAs per cluster of the forward bag kernel (1, 2 or 4; env MPO_FWD_CLUSTER)
 cudaError_t launch_bag_fwd(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const CUtensorMap& tm_h,
                            const BagFwdParams& prm, int num_sms, cudaStream_t stream);

@@ -60,18 +60,71 @@ struct Chunk {
   short kc_type;         // kc (reduction elements, multiple of 4, <= KC) | type << 15
 };
 constexpr int MAX_CHUNKS = 160;    // per launch and role (path role of NaCAGaT: 100 forward, 124 backward)
-struct Program { Chunk c[MAX_CHUNKS]; int n; };
+// TMA form of a chunk (same 16 bytes; Program::tma != 0): the chunk is ONE box of tensor map `map` -- data gradient:
+// 32 columns x KC rows of the 2-D matrix, dense; forward: 32 rows x KC reduction elements of the matrix seen as
+// [ld / 32][rows][32], i.e. KC / 32 tiles [32 rows][32 floats] with the 128-byte swizzle
+struct ChunkT {
+  int c0, c1;            // inner (column) and outer (row) coordinate of the chunk for rank 0
+  int map_rmul;          // tensor-map index | elements to add per cluster rank << 8 (to c1 forward, to c0 data gradient)
+  short ld;
+  short kc_type;
+};
+static_assert(sizeof(ChunkT) == sizeof(Chunk), "one table format for both forms");
+constexpr int NMAP = 24;           // distinct (weight matrix, chunk type) pairs per launch and role
+struct Program { Chunk c[MAX_CHUNKS]; int n; int tma; };
+
+// tensor maps of the weight matrices, cached by (base, pitch, chunk type): parameters keep their storage between steps
+struct MapKey { const float* w; int ld, type; };
+struct MapCache {
+  static constexpr int N = 256;
+  MapKey key[N]; CUtensorMap map[N]; int n = 0;
+  const CUtensorMap* get(const float* w, int ld, int type) {
+    for (int i = 0; i < n; ++i) if (key[i].w == w && key[i].ld == ld && key[i].type == type) return &map[i];
+    if (n >= N) n = 0;                   // (a process that cycles through > 256 weight matrices simply re-encodes)
+    // rows: an upper bound (full chunks never leave the matrix; the extent only has to cover every row that is read)
+    const int rc = type == T_FWD ? make_tmap_f32_rows32(&map[n], w, 1u << 20, static_cast<uint64_t>(ld), KC / 32)
+                                 : make_tmap_f32_2d_sw(&map[n], w, 1u << 20, static_cast<uint64_t>(ld),
+                                                       static_cast<uint64_t>(ld), KC, false);
+    if (rc != MPO_OK) return nullptr;
+    key[n] = MapKey{w, ld, type};
+    return &map[n++];
+  }
+};
+inline MapCache& map_cache() { static MapCache c; return c; }
 
 struct ProgBuilder {
   Program& p;
   bool ok = true;
+  // TMA form: the tensor maps of this program (kernel parameter space) and the matrices they stand for
+  CUtensorMap* maps = nullptr;
+  int nmaps = 0;
+  MapKey mkey[NMAP];
+  int map_index(const float* w, int ld, int type) {
+    for (int i = 0; i < nmaps; ++i) if (mkey[i].w == w && mkey[i].ld == ld && mkey[i].type == type) return i;
+    if (nmaps >= NMAP) return -1;
+    const CUtensorMap* m = map_cache().get(w, ld, type);
+    if (m == nullptr) return -1;
+    maps[nmaps] = *m; mkey[nmaps] = MapKey{w, ld, type};
+    return nmaps++;
+  }
   void add(int type, const float* w, int ld, int K, int nblk, int rank_mul, int blk_stride, int n_off) {
+    int mi = -1;
+    if (p.tma) {
+      // full chunks of 16-byte aligned, 16-byte pitched matrices only; anything else turns the whole program back
+      // into the cp.async form (the caller rebuilds it)
+      if (K % KC != 0 || (ld & 31) != 0 || (reinterpret_cast<uintptr_t>(w) & 15u) != 0 || rank_mul > 255 ||
+          (mi = map_index(w, ld, type)) < 0) { ok = false; return; }
+    }
     for (int blk = 0; blk < nblk; ++blk)
       for (int k0 = 0; k0 < K; k0 += KC) {
         if (p.n >= MAX_CHUNKS) { ok = false; return; }
         Chunk& c = p.c[p.n++];
         const int n0 = n_off + blk * blk_stride, kc = K - k0 < KC ? K - k0 : KC;
-        if (type == T_FWD) { c.base = w + static_cast<size_t>(n0) * ld + k0; c.rank_stride = rank_mul * ld; }
+        if (p.tma) {
+          ChunkT& t = reinterpret_cast<ChunkT&>(c);
+          if (type == T_FWD) { t.c0 = k0; t.c1 = n0; } else { t.c0 = n0; t.c1 = k0; }
+          t.map_rmul = mi | (rank_mul << 8);
+        } else if (type == T_FWD) { c.base = w + static_cast<size_t>(n0) * ld + k0; c.rank_stride = rank_mul * ld; }
         else { c.base = w + static_cast<size_t>(k0) * ld + n0; c.rank_stride = rank_mul; }
         c.ld = static_cast<short>(ld);
         c.kc_type = static_cast<short>(kc | (type << 15));
@@ -177,7 +230,23 @@ struct Pipe {
   int n, rank;
   int cons;            // next chunk to consume; chunks cons .. cons + NST - 2 are in flight or landed
   int slot;            // ring slot of chunk `cons` (kept incrementally: no modulo in the loop)
+  // TMA form (maps != nullptr; the path kernels): a chunk arrives as one or four 2-D tensor copies issued by thread 0
+  // behind the slot's mbarrier -- whole 128 B lines into shared memory (4 wavefronts per 512 B against ~10 for the
+  // sector-wise cp.async fill) and no per-thread address work.  (32 row-wise 1-D bulk copies per chunk were tried first:
+  // right for the shared-memory pipe, but their issue alone took ~2 200 cycles per chunk.)
+  const CUtensorMap* maps;
+  uint32_t bars;       // shared-memory address of one mbarrier per slot
+  uint32_t phase;      // bit s: parity the next wait on slot s's mbarrier expects
+  uint32_t stride;     // bytes per ring slot (dense 16 KB slots in the TMA form: 1024-byte aligned swizzle atoms)
 };
+constexpr uint32_t TMA_SLOT = 32 * KC * 4;
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (ok == 0u);
+}
 // partial chunks (kc < KC: the omic input layers and ragged reduction tails) -- rare, kept out of line
 __device__ __noinline__ void pipe_issue_partial(const float* src, int ld, int kc, int type, uint32_t dst) {
   const int t = threadIdx.x;
@@ -202,7 +271,27 @@ __device__ __noinline__ void pipe_issue_partial(const float* src, int ld, int kc
 // converted the global-memory descriptor for every copy it cost ~680 cycles per chunk, 22 % of the path kernels
 // (phase timing of the -DMPO_TAIL_PROF build, profiles/r2d_tail_phase_timing.txt).
 // (1-D bulk copies by one warp were tried instead: 256 copies of 128 B per data-gradient chunk are far slower)
-__device__ __forceinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int c, int slot) {
+__device__ __forceinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, int c, int slot, uint32_t bars,
+                                           const CUtensorMap* maps) {
+  if (maps != nullptr) {
+    if (c < n && threadIdx.x == 0) {
+      uint32_t c0, c1, mi, pk;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c0), "=r"(c1), "=r"(mi), "=r"(pk) : "r"(tbl + c * 16));
+      const uint32_t dst = ring + slot * TMA_SLOT, bar = bars + slot * 8;
+      const unsigned long long mp = reinterpret_cast<unsigned long long>(maps + (mi & 0xffu));
+      // (the slot was last READ, with generic loads that every warp finished before the CTA barrier in front of this
+      // call: a write-after-read across proxies needs no proxy fence)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TMA_SLOT) : "memory");
+      if ((pk >> 31) != 0u) {
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(dst), "l"(mp), "r"(bar), "r"(c0), "r"(c1) : "memory");
+      } else {
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(dst), "l"(mp), "r"(bar), "r"(0), "r"(c1), "r"(c0 >> 5) : "memory");
+      }
+    }
+    return;
+  }
   if (c < n) {
     const int t = threadIdx.x;
     uint32_t b_lo, b_hi, rs, pk;
@@ -233,20 +322,38 @@ __device__ __forceinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, i
 // copies the chunk table to shared memory (folding the cluster rank into the chunk bases) and puts the first NST - 1
 // chunks in flight
 template <int NST = NSTAGE>
-__device__ __forceinline__ void pipe_init(Pipe& pp, const Chunk* chunks, int n, float* tbl_smem, float* ring_smem, int rank) {
+__device__ __forceinline__ void pipe_init(Pipe& pp, const Chunk* chunks, int n, float* tbl_smem, float* ring_smem, int rank,
+                                          const CUtensorMap* maps = nullptr, float* bars_smem = nullptr) {
   for (int i = threadIdx.x; i < n; i += NT) {
     Chunk c = chunks[i];
-    c.base += static_cast<size_t>(rank) * c.rank_stride;
+    if (maps != nullptr) {
+      ChunkT& t = reinterpret_cast<ChunkT&>(c);
+      const int add = rank * (t.map_rmul >> 8);
+      if (((t.kc_type >> 15) & 1) == T_FWD) t.c1 += add; else t.c0 += add;
+    } else {
+      c.base += static_cast<size_t>(rank) * c.rank_stride;
+    }
     reinterpret_cast<Chunk*>(tbl_smem)[i] = c;
+  }
+  pp.maps = maps;
+  pp.bars = maps != nullptr ? smem_addr(bars_smem) : 0u;
+  pp.phase = 0u;
+  pp.stride = maps != nullptr ? TMA_SLOT : static_cast<uint32_t>(CHUNK * 4);
+  if (maps != nullptr && threadIdx.x == 0) {
+    for (int sl = 0; sl < NST; ++sl) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pp.bars + sl * 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   pp.tbl = smem_addr(tbl_smem); pp.ring = smem_addr(ring_smem); pp.n = n; pp.rank = rank; pp.cons = 0; pp.slot = 0;
+  // swizzle atoms want 1024-byte aligned slots: the dense TMA slots leave NST * 512 B of the ring region to align with
+  if (maps != nullptr) pp.ring = (pp.ring + 1023u) & ~1023u;
 #pragma unroll
-  for (int c = 0; c < NST - 1; ++c) pipe_issue(pp.tbl, pp.ring, pp.n, c, c);
+  for (int c = 0; c < NST - 1; ++c) pipe_issue(pp.tbl, pp.ring, pp.n, c, c, pp.bars, pp.maps);
 }
 template <int NST = NSTAGE>
-__device__ __forceinline__ void pipe_init(Pipe& pp, const Program& prog, float* tbl_smem, float* ring_smem, int rank) {
-  pipe_init<NST>(pp, prog.c, prog.n, tbl_smem, ring_smem, rank);
+__device__ __forceinline__ void pipe_init(Pipe& pp, const Program& prog, float* tbl_smem, float* ring_smem, int rank,
+                                          const CUtensorMap* maps = nullptr, float* bars_smem = nullptr) {
+  pipe_init<NST>(pp, prog.c, prog.n, tbl_smem, ring_smem, rank, maps, bars_smem);
 }
 
 struct Dev {
@@ -311,6 +418,10 @@ __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __
   const int hc = lane & 15, hh = lane >> 4;
   const uint32_t tbl = pp.tbl, ring = pp.ring;
   const int nchunks = pp.n;
+  const uint32_t bars = pp.bars, stride = pp.stride;
+  const CUtensorMap* const maps = pp.maps;
+  const bool tma = maps != nullptr;
+  uint32_t phase = pp.phase;
   int cons = pp.cons, slot = pp.slot;
   const long long pt_in = PROF_T();
   long long pt_d = pt_in;
@@ -322,16 +433,21 @@ __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __
   for (int r = 0; r < (kHalf ? M : 1); ++r) acc2[r][0] = acc2[r][1] = 0ull;
   for (int kb = 0; kb < Ktot; kb += KC) {
     const long long pt_a = PROF_T();
-    cp_async_wait<NST - 2>();
+    const int kc = min(KC, Ktot - kb);
+    if (tma) {
+      mbar_wait_u32(bars + slot * 8, (phase >> slot) & 1u);
+      phase ^= 1u << slot;
+    } else {
+      cp_async_wait<NST - 2>();
+    }
     __syncthreads();
     const long long pt_b = PROF_T();
-    pipe_issue(tbl, ring, nchunks, cons + NST - 1, slot == 0 ? NST - 1 : slot - 1);     // the slot freed by chunk cons - 1
+    pipe_issue(tbl, ring, nchunks, cons + NST - 1, slot == 0 ? NST - 1 : slot - 1, bars, maps);     // the slot freed by chunk cons - 1
     const long long pt_c = PROF_T();
     PROF_ADD(2, pt_b - pt_a); PROF_ADD(3, pt_c - pt_b);
-    const uint32_t wsm = ring + slot * (CHUNK * 4);
+    const uint32_t wsm = ring + slot * stride;
     ++cons;
     slot = slot + 1 == NST ? 0 : slot + 1;
-    const int kc = min(KC, Ktot - kb);
     const int kbeg = warp * KW;
     if constexpr (kHalf) {
       // this warp's KW reduction elements as KW / 8 pairs of quads; quad 2 j + hh is this lane's
@@ -341,7 +457,15 @@ __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __
       const uint32_t wa = TYPE == T_FWD ? wsm + (ca * WLD + k0) * 4 : wsm + (k0 * 32 + ca) * 4;
       const uint32_t wb = TYPE == T_FWD ? wsm + (cb * WLD + k0) * 4 : wsm + (k0 * 32 + cb) * 4;
       constexpr int WSTEP = TYPE == T_FWD ? 32 : 8 * 128;
-      if (kc == KC) {
+      if (TYPE == T_FWD && tma) {
+        // four boxes [32 rows][32 floats] with the 128-byte swizzle: the 16-byte quad q of row c sits at q ^ (c & 7);
+        // this warp's 16 reduction elements are quads 4 (warp & 1) .. + 3 of box warp / 2 (full chunks only)
+        const uint32_t ba = wsm + (warp >> 1) * 4096 + ca * 128, bb = wsm + (warp >> 1) * 4096 + cb * 128;
+        const int q0 = (warp & 1) * 4 + hh, sw = hc & 7;
+#pragma unroll
+        for (int j = 0; j < KW / 8; ++j)
+          gemm_step2<M, TYPE, LDX>(ba + (((q0 + 2 * j) ^ sw) << 4), bb + (((q0 + 2 * j) ^ sw) << 4), xk + j * 32, acc2);
+      } else if (kc == KC) {
 #pragma unroll
         for (int j = 0; j < KW / 8; ++j) gemm_step2<M, TYPE, LDX>(wa + j * WSTEP, wb + j * WSTEP, xk + j * 32, acc2);
       } else {
@@ -375,7 +499,7 @@ __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __
     pt_d = PROF_T();
     PROF_ADD(4, pt_d - pt_c);
   }
-  pp.cons = cons; pp.slot = slot;
+  pp.cons = cons; pp.slot = slot; pp.phase = phase;
   // this warp's k-slice partials; reduce_epi() sums the 8 slices
   const uint32_t red = red0 + ((warp * M) * 32 + lane) * 4;
 #pragma unroll
@@ -514,6 +638,7 @@ __device__ __forceinline__ float elu_f(float v) { return v > 0.f ? v : expm1f(v)
 __device__ __forceinline__ float elu_d(float y) { return y > 0.f ? 1.f : y + 1.f; }      // from the ELU output
 
 struct PathParams {
+  CUtensorMap maps[2][NMAP];   // TMA form of the weight ring: the tensor maps the chunks of prog[role] index
   Program prog[2];             // chunk streams of the path-role ([0]) and omic-role ([1]) clusters
   int nroles;                  // 2: adjacent clusters 2g / 2g+1 run the path / omic branch of slide group g concurrently
   int off_dG2;                 // NaCAGaT: the CAG's dQ (added to dG by pre_bwd_kernel; the omic role owns dG)
@@ -545,8 +670,8 @@ struct PathParams {
   float* dsuma;                // [B][6] or null
   int off_dqp;
 };
-static_assert(sizeof(PathParams) <= 12000, "kernel parameter space (large kernel parameters, CUDA 12.1+)");
-static_assert(sizeof(Program) <= 2600, "two chunk programs have to fit the kernel parameter space");
+static_assert(sizeof(PathParams) <= 20000, "kernel parameter space (large kernel parameters, CUDA 12.1+)");
+static_assert(sizeof(Program) <= 2608, "two chunk programs have to fit the kernel parameter space");
 
 // ------------------------------------------------------------------------------------------------ encoder layer
 // nn.TransformerEncoderLayer(256, nhead 8, ff 512, relu, post-norm) as built at models/mcat/mcat.py:51-53.
@@ -1004,7 +1129,8 @@ struct PathSmem {
   static constexpr int DHP = DZR + S * 2 * E;
   static constexpr int SM = DHP + S * E;              // small per-slide vectors: 8 x [S][MAXK]
   static constexpr int TBL = ((SM + 8 * S * MAXK + 3) / 4) * 4;     // chunk table
-  static constexpr int total = TBL + MAX_CHUNKS * 4;
+  static constexpr int BARS = TBL + MAX_CHUNKS * 4;                 // one mbarrier per ring slot (bulk forward chunks)
+  static constexpr int total = BARS + 16;
 };
 
 static_assert(PathSmem<2>::total * sizeof(float) <= 227 * 1024, "path kernel shared memory");
@@ -1032,7 +1158,8 @@ __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_c
   d.red = sm + L::RED;
   Pipe pipe;
   d.pipe = &pipe;
-  pipe_init<RingDepth<S>::n>(pipe, P.prog[role], sm + L::TBL, sm + L::ring, d.rank);
+  pipe_init<RingDepth<S>::n>(pipe, P.prog[role], sm + L::TBL, sm + L::ring, d.rank,
+                             P.prog[role].tma != 0 ? &P.maps[role][0] : nullptr, sm + L::BARS);
   float* ws = P.ws;
   float *XA = sm + L::XA, *XB = sm + L::XB, *XC = sm + L::XC, *BIG = sm + L::BIG, *QKVL = sm + L::QKVL;
   float *AL = sm + L::AL, *BL = sm + L::BL, *PA = sm + L::PA, *AW = sm + L::AW, *HP = sm + L::HP, *CAT = sm + L::CAT;
@@ -2208,7 +2335,7 @@ static void fill_snn(const mpo_model* m, const mpo_tail_io* io, const Ws& w, Snn
     P.off_snn_h[i] = static_cast<int>(w.snn_h[i]);
     P.off_snn_dz1[i] = static_cast<int>(w.snn_dz1[i]); P.off_snn_dz2[i] = static_cast<int>(w.snn_dz2[i]);
     // one 32-column block per CTA of the 8-CTA cluster
-    Program tmp; tmp.n = 0;
+    Program tmp; tmp.n = 0; tmp.tma = 0;
     ProgBuilder pb{tmp};
     if (!backward) { pb.fwd(m->snn[i][0].w, m->omic_dims[i], m->omic_dims[i]); pb.fwd(m->snn[i][1].w, E, E); }
     else pb.dgrad(m->snn[i][1].w, E, E);
@@ -2289,6 +2416,7 @@ int pre_fwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t
     if (rc0) return rc0;
   }
   P.skip_snn = batched ? 1 : 0;
+  P.prog.tma = 0;                  // (the pre / SNN kernels keep the cp.async ring)
   ProgBuilder pb{P.prog};
   if (!batched) {
     for (int i = 0; i < MPO_Q; ++i) pb.fwd(m->snn[i][0].w, m->omic_dims[i], m->omic_dims[i], NB, 32 * NB);
@@ -2351,6 +2479,7 @@ int pre_bwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t
   static PreParams P;
   fill_pre(m, io, w, P);
   if (P.nac && (!io->dkc || !io->dtq)) return fail(MPO_E_ARG, "%s", "mpo_tail_pre_bwd: dkc/dtq are NULL (NaCAGaT)");
+  P.prog.tma = 0;                  // (the pre / SNN kernels keep the cp.async ring)
   ProgBuilder pb{P.prog};
   pb.fwd(m->coattn_in.w + static_cast<size_t>(E) * E, E, E, NB, 32 * NB);
   pb.dgrad(m->coattn_in.w, E, E, NB, 32 * NB);
@@ -2463,9 +2592,11 @@ int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, cons
   P.off_dqp = (int)w.dqp;
 
   // chunk order = consumption order of the device code; a CTA owns NB column blocks of every 256-wide layer
-  auto build_program = [&](Program& prog, int lflags, int br_hi, int br_lo) -> bool {
+  auto build_program = [&](Program& prog, int lflags, int br_hi, int br_lo, CUtensorMap* maps) -> bool {
     prog.n = 0;
+    prog.tma = maps != nullptr ? 1 : 0;
     ProgBuilder pb{prog};
+    pb.maps = maps;
     auto enc_f = [&](const mpo_encoder_layer& L) {
       for (int nb = 0; nb < NB; ++nb) pb.fwd(L.in_proj.w, E, E, 3, 32 * NB, E, nb * 32);     // q, k, v of head rank * NB + nb
       pb.fwd(L.out_proj.w, E, E, NB, 32 * NB);
@@ -2547,12 +2678,27 @@ int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, cons
     plan_flags[0] = flags; plan_roles[0] = 2;
   }
   int rc = MPO_OK;
+  // weight ring through 2-D tensor copies (default) or per-thread cp.async (MPO_TAIL_TMA=0, and whenever a program has a
+  // chunk the TMA form does not cover)
+  static int use_tma = -1;
+  if (use_tma < 0) { const char* e = getenv("MPO_TAIL_TMA"); use_tma = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
   for (int l = 0; l < nlaunch; ++l) {
     P.flags = plan_flags[l];
     P.nroles = plan_roles[l];
-    bool ok = true;
-    if (P.nroles == 2) { ok = build_program(P.prog[0], P.flags, 0, 0) && build_program(P.prog[1], P.flags, 1, 1); }
-    else { ok = build_program(P.prog[0], P.flags, 1, 0); P.prog[1].n = 0; }
+    bool ok = false;
+    for (int form = use_tma ? 1 : 0; form >= 0 && !ok; --form) {
+      CUtensorMap* m0 = form ? &P.maps[0][0] : nullptr;
+      CUtensorMap* m1 = form ? &P.maps[1][0] : nullptr;
+      if (P.nroles == 2) { ok = build_program(P.prog[0], P.flags, 0, 0, m0) && build_program(P.prog[1], P.flags, 1, 1, m1); }
+      else { ok = build_program(P.prog[0], P.flags, 1, 0, m0); P.prog[1].n = 0; P.prog[1].tma = 0; }
+      if (form == 1 && !ok) {
+        static bool told = false;
+        if (!told && getenv("MPO_TAIL_VERBOSE") != nullptr) {
+          told = true;
+          fprintf(stderr, "[mpo] fused tail: a weight stream does not fit the TMA form, cp.async ring used (%s)\n", mpo_last_error());
+        }
+      }
+    }
     if (!ok) return fail(MPO_E_CUDA, "%s", "fused tail: program table overflow");
     cudaError_t e = S == 2 ? launch_cluster(path_kernel<2>, P, ncl * P.nroles, PathSmem<2>::total * sizeof(float), st)
                            : launch_cluster(path_kernel<1>, P, ncl * P.nroles, PathSmem<1>::total * sizeof(float), st);

@@ -254,11 +254,14 @@ def test_batched_trainer_equals_per_slide_gradients():
         assert err < 2e-3, (k, err)
 
 
-@pytest.mark.parametrize("case_name,slides_per_cluster,train,loss_kind",
-                         [("mcat_concat_sharp_517", 1, True, "nll"), ("mcat_concat_sharp_517", 2, True, "ces"),
-                          ("mcat_concat_sharp_517", 2, False, "nll"), ("nacagat_concat_sharp_517", 1, True, "nll"),
-                          ("nacagat_concat_sharp_517", 2, False, "ces")])
-def test_fused_cluster_tail_equals_per_op_tail(case_name, slides_per_cluster, train, loss_kind, monkeypatch):
+@pytest.mark.parametrize("case_name,slides_per_cluster,train,loss_kind,snn_batch",
+                         [("mcat_concat_sharp_517", 1, True, "nll", "1"), ("mcat_concat_sharp_517", 2, True, "ces", "1"),
+                          ("mcat_concat_sharp_517", 2, False, "nll", "1"), ("nacagat_concat_sharp_517", 1, True, "nll", "1"),
+                          ("nacagat_concat_sharp_517", 2, False, "ces", "1"),
+                          # SNN encoders inside the per-slide clusters: one-row GEMM blocks over ragged (partial) weight
+                          # chunks of the omic input layers, both ring depths
+                          ("mcat_concat_sharp_517", 1, False, "nll", "0"), ("nacagat_concat_sharp_517", 2, False, "nll", "0")])
+def test_fused_cluster_tail_equals_per_op_tail(case_name, slides_per_cluster, train, loss_kind, snn_batch, monkeypatch):
     """The fused cluster tail (csrc/tail_fused.cu: three cluster kernels + one grouped weight-gradient kernel; MCAT and
     NaCAGaT with its CAG / attention-dropout terms) and the per-op tail (csrc/tail.cu) are two implementations of the
     same step: same dropout masks (stateless RNG keyed by
@@ -275,6 +278,7 @@ def test_fused_cluster_tail_equals_per_op_tail(case_name, slides_per_cluster, tr
     labels = torch.tensor([s[2] for s in slides], dtype=torch.int64, device="cuda")
     cens = torch.tensor([s[3] for s in slides], dtype=torch.float32, device="cuda")
     monkeypatch.setenv("MPO_TAIL_FUSED_S", str(slides_per_cluster))
+    monkeypatch.setenv("MPO_TAIL_SNN_BATCH", snn_batch)
     out = {}
     for fused in ("0", "1"):
         monkeypatch.setenv("MPO_TAIL_FUSED", fused)
