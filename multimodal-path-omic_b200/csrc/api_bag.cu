@@ -7,6 +7,7 @@
 #include "mpo_ptx.cuh"
 #include "mpo_common.cuh"
 #include "launchers.h"
+#include "tail_dev.cuh"
 
 namespace mpo {
 
@@ -120,6 +121,7 @@ int make_tmap_f32_rows32(CUtensorMap* out, const void* base, uint64_t rows, uint
 
 // ------------------------------------------------------------------------------------------------
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  pdl_enter();
   const int64_t i4 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i4 + 8 <= n) {
     const float4 a = *reinterpret_cast<const float4*>(src + i4);
@@ -208,7 +210,7 @@ int mpo_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
   const int64_t groups = (n + 7) / 8;
   const int threads = 256;
   const int64_t blocks = (groups + threads - 1) / threads;
-  cast_bf16_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  mpo::launch_step(cast_bf16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, static_cast<cudaStream_t>(stream),
       src, static_cast<__nv_bfloat16*>(dst), n);
   count_launch();
   return check_cuda(cudaGetLastError(), "mpo_cast_bf16");
@@ -270,11 +272,11 @@ int mpo_bag_fwd(const mpo_bag* bag, const void* w_h_bf16, const float* bias_h, c
                     "bag_merge_kernel");
 }
 
-__global__ void advance_seed_kernel(uint32_t* s) { *s = mpo::hash_u32(*s + 0x9E3779B9u); }
+__global__ void advance_seed_kernel(uint32_t* s) { mpo::pdl_enter(); *s = mpo::hash_u32(*s + 0x9E3779B9u); }
 
 int mpo_advance_seed(uint32_t* seed_dev, void* stream) {
   if (!seed_dev) return fail(MPO_E_ARG, "%s", "mpo_advance_seed: NULL pointer");
-  advance_seed_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(seed_dev);
+  mpo::launch_step(advance_seed_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), seed_dev);
   count_launch();
   return check_cuda(cudaGetLastError(), "advance_seed_kernel");
 }
@@ -399,6 +401,7 @@ cudaError_t side_join(BagSide& b, cudaStream_t st) {
   if (b.state != 1) return cudaSuccess;
   cudaError_t e = cudaEventRecord(b.join, b.s);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(st, b.join, 0);
+  mpo::pdl_bar_next(st);        // the next kernel of the step waits for the side stream: launched fully serialized
   return e;
 }
 }  // namespace
@@ -584,6 +587,7 @@ int mpo_bag_bwd_nacagat(const mpo_bag* bag, const mpo_nacagat_bwd* a, void* stre
 __global__ void __launch_bounds__(256)
 adam_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
                  float lr, float b1, float b2, float eps, float wd, const int32_t* __restrict__ step_dev, int zero_grad) {
+  mpo::pdl_enter();
   const float t = static_cast<float>(*step_dev + 1);
   const float bc1 = 1.f - powf(b1, t);
   const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
@@ -606,7 +610,7 @@ adam_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
     if (zero_grad) *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
-__global__ void bump_step_kernel(int32_t* s) { *s += 1; }
+__global__ void bump_step_kernel(int32_t* s) { mpo::pdl_enter(); *s += 1; }
 
 }  // extern "C"
 namespace mpo {
@@ -620,11 +624,11 @@ int launch_adam(float* param, float* grad, float* exp_avg, float* exp_avg_sq, in
     const int64_t groups = n / 4;
     int blocks = static_cast<int>((groups + 255) / 256);
     if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-    adam_step_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+    mpo::launch_step(adam_step_kernel, dim3(blocks), dim3(256), 0, st, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                                              step_dev, zero_grad ? 1 : 0);
     count_launch();
   }
-  if (bump) { bump_step_kernel<<<1, 1, 0, st>>>(step_dev); count_launch(); }
+  if (bump) { mpo::launch_step(bump_step_kernel, dim3(1), dim3(1), 0, st, step_dev); count_launch(); }
   return check_cuda(cudaGetLastError(), "adam_step_kernel");
 }
 }  // namespace mpo

@@ -13,6 +13,7 @@
 #include "mpo_ptx.cuh"
 #include "mpo_common.cuh"
 #include "launchers.h"
+#include "tail_dev.cuh"
 
 namespace mpo {
 
@@ -103,6 +104,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kDzThreads, 1)
 bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                   const BagBwdDzParams p) {
+  pdl_enter();
   constexpr bool kLite = MODE == kDzMcatLite;    // no dz tile: coefficients + mask bits out, dz regenerated by the dW kernel
   constexpr bool kHasG = MODE != kDzNacDkg;      // MMA-G (dots of the tile rows with dP)
   constexpr bool kHasB = MODE != kDzNacDh && !kLite;   // MMA-db (column sums of the output tile)
@@ -588,6 +590,7 @@ __global__ void __launch_bounds__(256)
 bag_bwd_reduce_kernel(const int* __restrict__ tile_prefix, const float* __restrict__ part_dqk,
                       const float* __restrict__ part_db, float* __restrict__ dqk, float* __restrict__ grad_bias,
                       int B, int num_tiles) {
+  pdl_enter();
   __shared__ float4 acc_s[16][16];
   const int tid = threadIdx.x, tg = tid >> 4, dl = tid & 15, dq = dl + 16 * static_cast<int>(blockIdx.z);
   const bool is_bias = static_cast<int>(blockIdx.x) >= B;
@@ -637,6 +640,7 @@ bag_bwd_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_consta
                   float* __restrict__ grad_w,   // [256][ld] fp32, accumulated
                   int total_rows, int num_splits, int ncb, int ld, uint32_t idesc,
                   const uint32_t* __restrict__ dg_max) {   // non-null: the A operand carries the batch-wide gate scale
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms, by pointer arithmetic so the compiler keeps the shared state space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -1116,9 +1120,9 @@ static cudaError_t launch_dz_mode(const CUtensorMap& tm_in, const CUtensorMap& t
   if (dbg < 0) { const char* e = getenv("MPO_DZ_DEBUG"); dbg = e ? atoi(e) : 0; }
   BagBwdDzParams prm_d = prm;
   prm_d.debug = dbg;
-  bag_bwd_dz_kernel<MODE><<<grid, kDzThreads, kDzSmemBytes, stream>>>(tm_in, tm_out, prm_d);
+  cudaError_t e = launch_step(bag_bwd_dz_kernel<MODE>, dim3(grid), dim3(kDzThreads), kDzSmemBytes, stream, tm_in, tm_out, prm_d);
   count_launch();
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 cudaError_t launch_bag_bwd_dz(int mode, const CUtensorMap& tm_in, const CUtensorMap& tm_out, const BagBwdDzParams& prm,
                               int num_sms, cudaStream_t stream) {
@@ -1154,10 +1158,10 @@ cudaError_t launch_bag_bwd_dw(const CUtensorMap& tm_dz, const CUtensorMap& tm_x,
   if (splits > chunks) splits = chunks;
   if (splits < 1) splits = 1;
   const uint32_t idesc = f16 ? umma_idesc(128, 256, 0, 0, 1, 1) : umma_idesc_bf16(128, 256, 1, 1);
-  bag_bwd_dw_kernel<<<ncb * splits, kDwThreads, kDwSmemBytes, stream>>>(tm_dz, tm_x, grad_w, total_rows, splits, ncb, ld,
-                                                                       idesc, dg_max);
+  cudaError_t e = launch_step(bag_bwd_dw_kernel, dim3(ncb * splits), dim3(kDwThreads), kDwSmemBytes, stream, tm_dz, tm_x, grad_w,
+                              total_rows, splits, ncb, ld, idesc, dg_max);
   count_launch();
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace mpo

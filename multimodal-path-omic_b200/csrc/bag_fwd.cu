@@ -18,6 +18,7 @@
 #include "mpo_ptx.cuh"
 #include "mpo_common.cuh"
 #include "launchers.h"
+#include "tail_dev.cuh"
 #include <cstdlib>
 
 namespace mpo {
@@ -57,6 +58,7 @@ template <int kC, bool kPair = false>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                const __grid_constant__ CUtensorMap tm_h, const BagFwdParams p) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms, by pointer arithmetic so the compiler keeps the shared state space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -515,6 +517,7 @@ bag_merge_kernel(const int* __restrict__ tile_prefix,   // [B+1] first tile of e
                  const float* __restrict__ part_pool, float* __restrict__ pooled, float* __restrict__ lse,
                  float* __restrict__ suma,     // suma (NaCAGaT, mls = 18): sum_n of the dropped-and-rescaled weights
                  const float* __restrict__ part_pool2, float* __restrict__ pooled2) {   // optional second partial set
+  pdl_enter();
   // one block per (slide, query, quarter of the feature columns); 16 tile groups x 16 float4 columns: a 128-tile slide
   // is 8 independent loads per thread, all in flight at once
   __shared__ float red[8];
@@ -597,7 +600,7 @@ static cudaError_t launch_fwd_cluster(const CUtensorMap& tm_x, const CUtensorMap
   cfg.blockDim = dim3(kFwdThreads);
   cfg.dynamicSmemBytes = kFwdSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kC;
   attr[0].val.clusterDim.y = 1;
@@ -616,6 +619,7 @@ static cudaError_t launch_fwd_cluster(const CUtensorMap& tm_x, const CUtensorMap
   int clusters = (prm.num_tiles + kC - 1) / kC;
   if (clusters > max_clusters) clusters = max_clusters;
   cfg.gridDim = dim3(clusters * kC);
+  cfg.numAttrs = step_pdl_attr(attr, 1, stream);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x, tm_w, tm_h, prm);
   count_launch();
   return e;
@@ -649,10 +653,10 @@ cudaError_t launch_bag_merge(const int* tile_prefix, const float* part_ml, int m
                              float* pooled, float* lse, float* suma, int B, cudaStream_t stream,
                              const float* part_pool2, float* pooled2) {
   if (B <= 0) return cudaSuccess;
-  bag_merge_kernel<<<dim3(B, kQ, 4), 256, 0, stream>>>(tile_prefix, part_ml, ml_stride, part_pool, pooled, lse, suma,
-                                                       part_pool2, pooled2);
+  cudaError_t e = launch_step(bag_merge_kernel, dim3(B, kQ, 4), dim3(256), 0, stream, tile_prefix, part_ml, ml_stride, part_pool,
+                              pooled, lse, suma, part_pool2, pooled2);
   count_launch();
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace mpo

@@ -1137,6 +1137,7 @@ static_assert(PathSmem<2>::total * sizeof(float) <= 227 * 1024, "path kernel sha
 static_assert(PathSmem<1>::total * sizeof(float) <= 113 * 1024, "two one-slide path CTAs have to fit one SM");
 template <int S>
 __global__ void __launch_bounds__(NT, S == 1 ? 2 : 1) path_kernel(const __grid_constant__ PathParams P) {
+  pdl_enter();
   constexpr int M = 6 * S;
   using L = PathSmem<S>;
   extern __shared__ __align__(16) float sm[];
@@ -1624,6 +1625,7 @@ struct PreSmem {
 // qk = W_k^T q / 16
 template <int S>
 __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreParams P) {
+  pdl_enter();
   constexpr int M = 6 * S;
   using L = PreSmem<S>;
   extern __shared__ __align__(16) float sm[];
@@ -1715,6 +1717,7 @@ __global__ void __launch_bounds__(NT, 1) pre_kernel(const __grid_constant__ PreP
 // autograd of pre_kernel: fold, query projection (+ the omic branch's dG), SNN data gradients
 template <int S>
 __global__ void __launch_bounds__(NT, 1) pre_bwd_kernel(const __grid_constant__ PreParams P) {
+  pdl_enter();
   constexpr int M = 6 * S;
   using L = PreSmem<S>;
   extern __shared__ __align__(16) float sm[];
@@ -1836,6 +1839,7 @@ struct SnnSmem {
 static_assert(SnnSmem::total * sizeof(float) <= 227 * 1024, "SNN kernel shared memory");
 
 __global__ void __launch_bounds__(NT, 1) snn_fwd_kernel(const __grid_constant__ SnnParams P) {
+  pdl_enter();
   extern __shared__ __align__(16) float sm[];
   Dev d;
   d.rank = cluster_rank();
@@ -1888,6 +1892,7 @@ __global__ void __launch_bounds__(NT, 1) snn_fwd_kernel(const __grid_constant__ 
 
 // dG (total gradient of G_bag, from pre_bwd_kernel) -> gradients at the pre-activations of both SNN layers
 __global__ void __launch_bounds__(NT, 1) snn_bwd_kernel(const __grid_constant__ SnnParams P) {
+  pdl_enter();
   extern __shared__ __align__(16) float sm[];
   Dev d;
   d.rank = cluster_rank();
@@ -1993,6 +1998,7 @@ __device__ __forceinline__ float snn2_sum_partials(const float* red, int s, int 
 }
 
 __global__ void __launch_bounds__(NT, 1) snn2_fwd_kernel(const __grid_constant__ Snn2Params P) {
+  pdl_enter();
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int om = blockIdx.y, col0 = blockIdx.x * SNN2_COLS, s0 = blockIdx.z * SNN_ROWS;
@@ -2036,6 +2042,7 @@ __global__ void __launch_bounds__(NT, 1) snn2_fwd_kernel(const __grid_constant__
 
 // dG -> dz2 (stored) -> dh1 = dz2 W2 -> dz1 (stored); a CTA owns 16 columns of dz2 (store) and of dz1
 __global__ void __launch_bounds__(NT, 1) snn2_bwd_kernel(const __grid_constant__ Snn2Params P) {
+  pdl_enter();
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int om = blockIdx.y, col0 = blockIdx.x * SNN2_COLS, s0 = blockIdx.z * SNN_ROWS;
@@ -2131,6 +2138,7 @@ struct WParams { WJob job[MAX_JOBS]; int njobs; int ntiles; };
 static_assert(sizeof(WParams) <= 8000, "kernel parameter space (large kernel parameters, CUDA 12.1+)");
 
 __global__ void __launch_bounds__(256) wgrad_kernel(const __grid_constant__ WParams P) {
+  pdl_enter();
   __shared__ __align__(16) float As[2][32][64 + 4];
   __shared__ __align__(16) float Bs[2][32][64 + 4];
   const int t = threadIdx.x;
@@ -2265,11 +2273,11 @@ cudaError_t launch_cluster(K kern, const PT& prm, int nclusters, size_t smem_byt
   cfg.blockDim = dim3(NT);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = step_pdl_attr(at, 1, st);
   e = cudaLaunchKernelEx(&cfg, kern, prm);
   count_launch();
   return e;
@@ -2387,9 +2395,9 @@ static cudaError_t launch_snn2(K kern, const Snn2Params& P, int maxK, cudaStream
                                        static_cast<int>(SNN2_SMEM_FLOATS * sizeof(float)));
   if (e != cudaSuccess) return e;
   const dim3 grid(E / SNN2_COLS, MPO_Q, (P.B + SNN_ROWS - 1) / SNN_ROWS);
-  kern<<<grid, NT, smem, st>>>(P);
+  e = launch_step(kern, grid, dim3(NT), smem, st, P);
   count_launch();
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 int pre_fwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t st) {
@@ -2458,9 +2466,9 @@ static SideStream& side_stream() {
 
 static int launch_wgrad(const WParams& W, cudaStream_t st) {
   if (W.ntiles == 0) return MPO_OK;
-  wgrad_kernel<<<W.ntiles, 256, 0, st>>>(W);
+  const cudaError_t e = launch_step(wgrad_kernel, dim3(W.ntiles), dim3(256), 0, st, W);
   count_launch();
-  return fin(cudaSuccess, "wgrad_kernel (fused tail)");
+  return fin(e, "wgrad_kernel (fused tail)");
 }
 
 // Adam over a gradient bucket that the pending side-stream weight gradients complete: queued behind them (next to the bag
@@ -2527,6 +2535,7 @@ int pre_bwd(const mpo_model* m, const mpo_tail_io* io, const Ws& w, cudaStream_t
   SideStream& side = side_stream();
   if (side.pending) {          // the post stage's weight gradients of this step (launched by post() on the side stream)
     side.pending = false;
+    pdl_bar_next(st);          // the next kernel on st waits for the side stream: launched fully serialized
     return check_cuda(cudaStreamWaitEvent(st, side.ev_join, 0), "fused tail: join of the weight-gradient stream");
   }
   return MPO_OK;
@@ -2751,6 +2760,7 @@ int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, cons
   if (side_wgrad && side.state == 1) {
     cudaError_t e2 = cudaEventRecord(side.ev_fork, st);
     if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(side.s, side.ev_fork, 0);
+    pdl_bar_next(side.s);      // first kernel behind the fork: fully serialized
     if (e2 != cudaSuccess) return check_cuda(e2, "fused tail: fork of the weight-gradient stream");
     rc = launch_wgrad(W, side.s);
     if (rc) return rc;
