@@ -5,6 +5,7 @@ there is no PyTorch or CPU fallback behind any of these functions.
 """
 import ctypes
 import os
+import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmpo_b200.so")
@@ -216,9 +217,16 @@ def exported_symbols():
     return ["mpo_last_error", "mpo_version"] + list(SIGNATURES.keys()) + OTHER_EXPORTS
 
 
+_CALL_LOCK = threading.Lock()
+
+
 def call(name, *args):
+    """One C-ABI call; non-zero return codes become RuntimeError.  The library keeps per-process launch state (parameter
+    blocks, tensor-map cache, last error), and ctypes drops the GIL for the duration of a call, so calls from several
+    Python threads (e.g. nn.DataParallel's replica threads) are serialised here; they only enqueue work on streams."""
     L = lib()
-    rc = getattr(L, name)(*args)
-    if rc != 0:
-        msg = L.mpo_last_error().decode("utf-8", "replace")
-        raise RuntimeError("%s failed (%d): %s" % (name, rc, msg))
+    with _CALL_LOCK:
+        rc = getattr(L, name)(*args)
+        if rc != 0:
+            msg = L.mpo_last_error().decode("utf-8", "replace")
+            raise RuntimeError("%s failed (%d): %s" % (name, rc, msg))
