@@ -2689,8 +2689,8 @@ int post(const mpo_model* m, const mpo_tail_io* io, const Ws& w, int flags, cons
   int rc = MPO_OK;
   // weight ring through 2-D tensor copies (default) or per-thread cp.async (MPO_TAIL_TMA=0, and whenever a program has a
   // chunk the TMA form does not cover)
-  static int use_tma = -1;
-  if (use_tma < 0) { const char* e = getenv("MPO_TAIL_TMA"); use_tma = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
+  const char* tma_env = getenv("MPO_TAIL_TMA");       // read on every call: tests flip it to compare the two forms
+  const int use_tma = (tma_env == nullptr || atoi(tma_env) != 0) ? 1 : 0;
   for (int l = 0; l < nlaunch; ++l) {
     P.flags = plan_flags[l];
     P.nroles = plan_roles[l];

@@ -306,6 +306,44 @@ def test_fused_cluster_tail_equals_per_op_tail(case_name, slides_per_cluster, tr
         assert err < (3e-3 if bag_side else 5e-4), (k, err)
 
 
+@pytest.mark.parametrize("case_name,slides_per_cluster", [("mcat_concat_sharp_517", 1), ("nacagat_concat_sharp_517", 2)])
+def test_tma_weight_ring_equals_cp_async_ring(case_name, slides_per_cluster, monkeypatch):
+    """The path kernels stream their weights through 2-D / 3-D tensor copies behind per-slot mbarriers (default) or through
+    per-thread cp.async (MPO_TAIL_TMA=0, also the fallback for weight streams the TMA form does not cover).  Same
+    arithmetic in the same order, so a train step (same dropout seed) must agree bit for bit."""
+    synth = _pkg("synth")
+    sp = _pkg("slidepath")
+    bpm = _pkg("bagpass")
+    case = load_case(case_name)
+    lens = [257, 300, 64, 1000, 129, 31, 517]
+    slides = [synth.make_slide(700 + i, n) for i, n in enumerate(lens)]
+    pb = bpm.PackedBag.from_slides([torch.from_numpy(s[0]).cuda() for s in slides])
+    om = [torch.stack([torch.from_numpy(s[1][i]) for s in slides]).cuda() for i in range(6)]
+    labels = torch.tensor([s[2] for s in slides], dtype=torch.int64, device="cuda")
+    cens = torch.tensor([s[3] for s in slides], dtype=torch.float32, device="cuda")
+    monkeypatch.setenv("MPO_TAIL_FUSED_S", str(slides_per_cluster))
+    out = {}
+    for form in ("0", "1"):
+        monkeypatch.setenv("MPO_TAIL_TMA", form)
+        net = build_model(case)
+        net.train()
+        tr = sp.BatchTrainer(net, loss="nll", grad_acc_step=len(lens))
+        tr.zero_grad()
+        loss, hz, S = tr.step(pb, om, labels, cens, train=True, seed=99)
+        torch.cuda.synchronize()
+        st = tr.last_state
+        out[form] = dict(loss=loss.clone(), hz=hz.clone(), dpooled=st.dpooled.clone(),
+                         grads={k: v.clone() for k, v in tr.grads.items()})
+    a, b = out["0"], out["1"]
+    assert torch.equal(a["loss"], b["loss"]) and torch.equal(a["hz"], b["hz"])
+    assert torch.equal(a["dpooled"], b["dpooled"])
+    # the weight gradients behind the bag backward go through atomically accumulated split-K sums: compare to rounding
+    gmax = max(float(v.norm()) for v in a["grads"].values())
+    for k, g in a["grads"].items():
+        err = float((g - b["grads"][k]).norm()) / max(float(g.norm()), 1e-5 * gmax)
+        assert err < 1e-5, (k, err)
+
+
 @pytest.mark.parametrize("train", [True, False])
 def test_wide_snn_kernels_equal_cluster_form(train, monkeypatch):
     """The wide SNN kernels (snn2_fwd_kernel x 2 + snn2_bwd_kernel, the default) and the 8-CTA cluster kernels they
