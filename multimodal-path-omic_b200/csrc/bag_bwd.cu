@@ -39,12 +39,13 @@ namespace mpo {
 //            the dz tile itself is regenerated inside the weight-gradient kernel (bag_bwd_dwz_kernel below), so dz never
 //            makes the round trip through HBM
 constexpr int kDzMcat = 0, kDzNacDh = 1, kDzNacDkg = 2, kDzMcatLite = 3;
-constexpr int kDzThreads = 64 + 256;
+constexpr int kDzThreads = 64 + 128 + 256;      // producer + issuer warps, 4 row-scalar warps, 8 output warps
+constexpr int kDzBufs = 3;          // tile buffers: two loads in flight while a third tile is being worked on
 struct DzSmem {
-  static constexpr int tile = 0;                       // 2 x 64 KB  fp16 tile [4][128][64] SW128 (later: the 16-bit output tile)
-  static constexpr int C = 2 * 65536;                  // bf16 [128][64] K-major (48 used)   16 KB
-  static constexpr int Dm = C + 16384;                 // bf16 [256][64] K-major (48 used)   32 KB
-  static constexpr int DP = Dm + 32768;                // fp16 [4][16][64] K-major            8 KB
+  static constexpr int tile = 0;                       // 3 x 64 KB  fp16 tile [4][128][64] SW128 (later: the 16-bit output tile)
+  static constexpr int C = kDzBufs * 65536;            // fp16 [2 M blocks][16 k][64] M-major (12 k used)     4 KB
+  static constexpr int Dm = C + 4096;                  // fp16 [4 N blocks][16 k][64] N-major (12 k used)     8 KB
+  static constexpr int DP = Dm + 8192;                 // fp16 [4][16][64] K-major            8 KB
   static constexpr int DS = DP + 8192;                 // fp16 [2][16][64] K-major (K = rows) 4 KB
   static constexpr int ones = DS + 4096;               // 16-bit [2][16][64] row 0 = 1        4 KB
   static constexpr int scal = ones + 4096;             // fp32 scratch (see below)            1 KB
@@ -87,6 +88,12 @@ __device__ __forceinline__ void store_row48(uint8_t* row, int sw, const uint32_t
   *reinterpret_cast<uint4*>(row + ((4 ^ sw) << 4)) = make_uint4(c[0], c[1], c[2], c[3]);
   *reinterpret_cast<uint4*>(row + ((5 ^ sw) << 4)) = make_uint4(c[4], c[5], 0u, 0u);
 }
+// element (k, m) of an M- or N-major fp16 operand of one K = 16 step: 64-element atoms of [16 k][64] (2048 B, 128-byte
+// swizzle: the 16-byte group (m & 63) / 8 of k-row k sits at group ^ (k & 7))
+__device__ __forceinline__ void store_mn_f16(uint8_t* base, int k, int m, float v) {
+  *reinterpret_cast<__half*>(base + (m >> 6) * 2048 + k * 128 + ((((m & 63) >> 3) ^ (k & 7)) << 4) + (m & 7) * 2) =
+      __float2half_rn(v);
+}
 // 6 values -> fp16 hi/lo entries of a [16 x 128] K-major operand column (rows 0..5 hi, 6..11 lo)
 __device__ __forceinline__ void store_col_f16(uint8_t* base, int k, const float (&v)[kQ]) {
   uint8_t* pcol = base + (k >> 6) * 2048 + (k & 7) * 2;
@@ -111,18 +118,19 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DzSmem::bars);
-  uint64_t* full_bar = bars;          // [2] TMA -> issuer
-  uint64_t* empty_bar = bars + 2;     // [2] tile buffer free again (store has read it + last MMA reading it retired)
-  uint64_t* op_bar = bars + 4;        // per-slide operands in place (8 warp arrivals)
+  uint64_t* full_bar = bars;          // [3] TMA -> MMA issuers
+  uint64_t* empty_bar = bars + 10;    // [3] tile buffer free again (store has read it + last MMA reading it retired)
   uint64_t* g_bar = bars + 5;         // MMA-G retired
-  uint64_t* c_bar = bars + 6;         // C / DS operands written (8 warp arrivals)
+  uint64_t* c_bar = bars + 6;         // C / DS (and, after a slide change, D / DP) operands written (4 warp arrivals)
   uint64_t* z_bar = bars + 7;         // MMA-dZ + MMA-dqk retired
-  uint64_t* w_bar = bars + 8;         // output tile written in place (8 warp arrivals)
+  uint64_t* w_bar = bars + 8;         // output tile written in place, Q read back (8 warp arrivals)
   uint64_t* b_bar = bars + 9;         // MMA-db retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DzSmem::tmem_slot);
   float* scal = reinterpret_cast<float*>(smem + DzSmem::scal);
-  // scal: [0..7] delta_i, [8..15] lse_i, [16..23] 1/dp_scale_i, [24..31] ds un-scale, [32..127] warp partials [8][12],
-  //       [128..159] row-warp max [4][8], [160..167] dsuma_i, [168..175] row-warp sums of ds [4][8] at 168..199
+  // scal: [0..7] delta_i, [8..15] lse_i, [16..23] 1/dp_scale_i, [24..31] 1/qk_scale_i, [32..79] warp partials [4][12],
+  //       [80..103] warp maxima of |qk_i| [4][6], [128..159] row-warp max [4][8] (entry 6: max of the row warp's scaled
+  //       C entries), [160..167] dsuma_i, [168..199] row-warp sums of ds [4][8],
+  //       [208..223] ds un-scale of the Q read-back, by tile parity [2][8], [224..225] un-scale of Z, by tile parity
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // contiguous tile range of this CTA (consecutive tiles mostly share a slide -> per-slide operands are rebuilt rarely)
@@ -133,8 +141,8 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_in);
     tma_prefetch_desc(&tm_out);
-    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
-    mbar_init(op_bar, 8); mbar_init(g_bar, 1); mbar_init(c_bar, 8); mbar_init(z_bar, 1); mbar_init(w_bar, 8);
+    for (int s = 0; s < kDzBufs; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
+    mbar_init(g_bar, 1); mbar_init(c_bar, 4); mbar_init(z_bar, 1); mbar_init(w_bar, 8);
     mbar_init(b_bar, 1);
     fence_mbar_init();
   }
@@ -155,14 +163,23 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The tile loop is software-pipelined over three groups of warps and three tile buffers (round 2, third session; before
+  // it the eight compute warps did the row scalars and the output tile of one tile back to back, with the two MMA round
+  // trips in between -- scalars + MMA + output + hand-offs in series, 4.8 us per tile -- over two buffers.  Measured one
+  // at a time neither change moves the kernel: the pipeline alone is then bound by how long a buffer stays occupied, 5.1 us
+  // per tile; the third buffer alone by the serial chain, 4.8 us; profiles/r2d_probe_dz_timing_switches.txt):
+  //   row-scalar warps (2..5)  tile t:   wait z(t-1) -> [slide change: D / DP] -> MMA-G(t) -> [a | ds] -> C / DS -> c(t)
+  //   issuer (warp 1)          tile t:   wait w(t-1), store(t-1) -> wait c(t) -> MMA-dZ(t), MMA-dqk(t) -> z(t) -> MMA-db(t-1)
+  //   output warps (6..13)     tile t:   wait z(t) -> out(t) in place, Q(t), b(t-1) -> w(t)
+  // so the row scalars of tile t + 1 run while the output tile of tile t is being written.
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer: input tiles
     if (lane == 0) {
       const uint64_t pol = policy_evict_first();
       int it = 0;
       for (int t = t_begin; t < t_end; ++t, ++it) {
-        const int buf = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
+        const int buf = it % kDzBufs;
+        const uint32_t ph = (it / kDzBufs) & 1;
         mbar_wait(&empty_bar[buf], ph ^ 1);
         uint8_t* dst = smem + DzSmem::tile + buf * 65536;
         mbar_expect_tx(&full_bar[buf], 65536);
@@ -172,96 +189,84 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA / TMA-store issuer
+    // ---------------------------------------------------------------- MMA-dZ / dqk / db and TMA-store issuer
     if (lane == 0) {
-      constexpr uint32_t id_g = umma_idesc(128, 16, 0, 0, 0, 0);       // fp16 x fp16, both K-major
-      constexpr uint32_t id_z = umma_idesc_bf16(128, 256, 0, 0);       // bf16 x bf16, both K-major
+      constexpr uint32_t id_z = umma_idesc(128, 256, 0, 0, 1, 1);      // fp16 x fp16, A M-major, B N-major, K = 16
       constexpr uint32_t id_q = umma_idesc(128, 16, 0, 0, 1, 0);       // fp16, A M-major (tile^T)
       constexpr uint32_t id_b = MODE == kDzNacDkg ? umma_idesc(128, 16, 0, 0, 1, 0)    // fp16 output tile
                                                   : umma_idesc(128, 16, 1, 1, 1, 0);   // bf16 output tile
       const uint32_t aC = smem_u32(smem + DzSmem::C), aD = smem_u32(smem + DzSmem::Dm);
-      const uint32_t aDP = smem_u32(smem + DzSmem::DP), aDS = smem_u32(smem + DzSmem::DS);
+      const uint32_t aDS = smem_u32(smem + DzSmem::DS);
       const uint32_t aOne = smem_u32(smem + DzSmem::ones);
-      int it = 0;
-      bool g_early = false;
-      auto issue_g = [&](uint32_t a_tile) {
-        if (p.debug & 32) return;
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + kColG, umma_desc_sw128(a_tile + kb * 16384 + k * 32, 16, 1024),
-                      umma_desc_sw128(aDP + kb * 2048 + k * 32, 16, 1024), id_g, (kb | k) != 0 ? 1u : 0u);
-      };
-      for (int t = t_begin; t < t_end; ++t, ++it) {
-        const int buf = it & 1;
-        const uint32_t ph = (it >> 1) & 1, tph = it & 1;
-        const uint32_t aT = smem_u32(smem + DzSmem::tile + buf * 65536);
-        mbar_wait(op_bar, tph);
-        if (kHasG && !g_early) {
-          mbar_wait(&full_bar[buf], ph);
-          tc_fence_after();
-          issue_g(aT);
-          umma_commit(g_bar);
-        }
-        mbar_wait(c_bar, tph);
-        if (!kHasG) mbar_wait(&full_bar[buf], ph);
+      // output tile `tt` (pipeline index `ip`) has been written: store it ...
+      auto store_tile = [&](int tt, int ip) -> bool {
+        mbar_wait(w_bar, ip & 1);
         tc_fence_after();
-        if (!kLite && !(p.debug & 4)) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-            umma_bf16(tmem_base + kColZ, umma_desc_sw128(aC + k * 32, 16, 1024), umma_desc_sw128(aD + k * 32, 16, 1024),
-                      id_z, k != 0 ? 1u : 0u);
-        }
-        if (!(p.debug & 1))
-#pragma unroll
-        for (int mh = 0; mh < 2; ++mh)
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_bf16(tmem_base + kColQ + mh * 16, umma_desc_sw128(aT + mh * 2 * 16384 + kk * 2048, 16384, 1024),
-                      umma_desc_sw128(aDS + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), id_q, kk != 0 ? 1u : 0u);
-        umma_commit(z_bar);
-        // MMA-G of the next tile already now (same slide: same dP operand), so that it overlaps this tile's epilogue;
-        // every row thread has consumed this tile's G by the time c_bar completed
-        g_early = false;
-        if (kHasG && t + 1 < t_end && p.tile_info[t + 1].slide == p.tile_info[t].slide) {
-          const int nb = (it + 1) & 1;
-          mbar_wait(&full_bar[nb], ((it + 1) >> 1) & 1);
-          tc_fence_after();
-          issue_g(smem_u32(smem + DzSmem::tile + nb * 65536));
-          umma_commit(g_bar);
-          g_early = true;
-        }
-        mbar_wait(w_bar, tph);
-        tc_fence_after();
-        const TileInfo ti = p.tile_info[t];
+        const TileInfo ti = p.tile_info[tt];
         const bool full_tile = !kLite && ti.nvalid == kTileM;
         if (full_tile && !(p.debug & 16)) {
+          uint8_t* src = smem + DzSmem::tile + (ip % kDzBufs) * 65536;
 #pragma unroll
-          for (int cb = 0; cb < 4; ++cb) tma_store_2d(&tm_out, smem + DzSmem::tile + buf * 65536 + cb * 16384, cb * 64, ti.row0);
+          for (int cb = 0; cb < 4; ++cb) tma_store_2d(&tm_out, src + cb * 16384, cb * 64, ti.row0);
           tma_store_commit();
         }
+        return full_tile;
+      };
+      // ... and take its column sums; after that (and the store's read) the buffer goes back to the producer
+      auto release_tile = [&](int ip, bool stored) {
+        const int buf = ip % kDzBufs;
+        const uint32_t aT = smem_u32(smem + DzSmem::tile + buf * 65536);
         if (kHasB) {
-          if (!(p.debug & 2))
+          if (!(p.debug & 2)) {
+#pragma unroll
+            for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)
+                umma_bf16(tmem_base + kColB + mh * 16, umma_desc_sw128(aT + mh * 2 * 16384 + kk * 2048, 16384, 1024),
+                          umma_desc_sw128(aOne + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), id_b, kk != 0 ? 1u : 0u);
+          }
+          umma_commit(b_bar);
+        }
+        umma_commit(&empty_bar[buf]);            // arrival 1 of 2: no MMA reads the tile any more
+        if (stored) tma_store_wait_read();
+        mbar_arrive(&empty_bar[buf]);            // arrival 2 of 2: the store has read it
+      };
+      int it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int buf = it % kDzBufs;
+        const uint32_t ph = (it / kDzBufs) & 1, tph = it & 1;
+        const uint32_t aT = smem_u32(smem + DzSmem::tile + buf * 65536);
+        // the Z / Q accumulators are free once the previous output tile is written
+        const bool stored = it > 0 ? store_tile(t - 1, it - 1) : false;
+        mbar_wait(c_bar, tph);
+        mbar_wait(&full_bar[buf], ph);
+        tc_fence_after();
+        if (!kLite && !(p.debug & 4)) {
+          // one K = 16 step: 64-element M / N atoms 2048 B apart, the two 8-k-row swizzle atoms of an atom 1024 B apart
+          umma_bf16(tmem_base + kColZ, umma_desc_sw128(aC, 2048, 1024), umma_desc_sw128(aD, 2048, 1024), id_z, 0u);
+        }
+        if (!(p.debug & 1)) {
 #pragma unroll
           for (int mh = 0; mh < 2; ++mh)
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
-              umma_bf16(tmem_base + kColB + mh * 16, umma_desc_sw128(aT + mh * 2 * 16384 + kk * 2048, 16384, 1024),
-                        umma_desc_sw128(aOne + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), id_b, kk != 0 ? 1u : 0u);
-          umma_commit(b_bar);
+              umma_bf16(tmem_base + kColQ + mh * 16, umma_desc_sw128(aT + mh * 2 * 16384 + kk * 2048, 16384, 1024),
+                        umma_desc_sw128(aDS + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024), id_q, kk != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[buf]);            // arrival 1 of 2: no MMA reads the tile any more
-        if (full_tile) tma_store_wait_read();
-        mbar_arrive(&empty_bar[buf]);            // arrival 2 of 2: the store has read it
+        umma_commit(z_bar);
+        if (it > 0) release_tile(it - 1, stored);
+      }
+      if (it > 0) {
+        const bool stored = store_tile(t_end - 1, it - 1);
+        release_tile(it - 1, stored);
       }
     }
-  } else {
-    // ---------------------------------------------------------------- 8 compute warps
-    const int et = threadIdx.x - 64;           // 0..255 : feature owned when building per-slide operands / reading Q, b
+  } else if (warp < 6) {
+    // ---------------------------------------------------------------- 4 row-scalar warps (one patch row per thread)
+    const int st = threadIdx.x - 64;           // 0..127 : features st, st + 128 when building per-slide operands
     const int qd = warp & 3;                   // TMEM lane quadrant
-    const int ch = (warp - 2) >> 2;            // column half (epilogue) / feature half (Q, b read-back)
     const int r = qd * 32 + lane;              // patch row of the tile
+    const bool leader = warp == 2 && lane == 0;     // issues MMA-G
     uint8_t* Cs = smem + DzSmem::C;
     uint8_t* Ds = smem + DzSmem::Dm;
     uint8_t* DPs = smem + DzSmem::DP;
@@ -269,23 +274,28 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     float gs = 1.f, inv_gs = 1.f;
     if (MODE == kDzNacDkg) gs = gate_scale(p.dg_max, &inv_gs);
     const uint32_t seed = p.seed_dev != nullptr ? (p.seed ^ __ldg(p.seed_dev)) : p.seed;
+    constexpr uint32_t id_g = umma_idesc(128, 16, 0, 0, 0, 0);       // fp16 x fp16, both K-major
+    const uint32_t aDP = smem_u32(smem + DzSmem::DP);
+    auto issue_g = [&](int ip) {               // MMA-G of the tile in pipeline slot ip (leader only)
+      mbar_wait(&full_bar[ip % kDzBufs], (ip / kDzBufs) & 1);
+      tc_fence_after();
+      if (!(p.debug & 32)) {
+        const uint32_t a_tile = smem_u32(smem + DzSmem::tile + (ip % kDzBufs) * 65536);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + kColG, umma_desc_sw128(a_tile + kb * 16384 + k * 32, 16, 1024),
+                      umma_desc_sw128(aDP + kb * 2048 + k * 32, 16, 1024), id_g, (kb | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(g_bar);
+    };
     int cur_slide = -1;
     int it = 0;
-    int prev_t = -1;
-    // b partial of tile `tt` (its MMA-db was issued after the tile was written): read one tile late, so nobody
-    // waits for that MMA -- by then it has long retired
-    auto read_db = [&](int tt, uint32_t parity) {
-      mbar_wait(b_bar, parity);
-      tc_fence_after();
-      uint32_t bv[16];
-      tmem_ld_32x32b_x16(tmem_base + kColB + ch * 16 + (static_cast<uint32_t>(qd * 32) << 16), bv);
-      tmem_ld_wait();
-      p.part_db[static_cast<size_t>(tt) * kD + ch * 128 + qd * 32 + lane] = __uint_as_float(bv[0]) * inv_gs;
-      tc_fence_before();
-    };
+    bool g_early = false;
     // The per-row scalars of a tile (scores / gate / map gradient, or dg) are plain global loads feeding the head of the
-    // tile's dependency chain: they are issued one tile ahead (while the previous tile's output is being written), and the
-    // tile table is read one tile ahead as well, so no DRAM latency sits between the tiles.
+    // tile's dependency chain: they are issued one tile ahead, and the tile table is read one tile ahead as well, so no
+    // DRAM latency sits between the tiles.
     float nsc[kQ], npg[kQ], ndm[kQ];
     auto prefetch_rows = [&](const TileInfo& tn) {
       const bool v = r < tn.nvalid;
@@ -303,35 +313,44 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       }
     };
     TileInfo ti_next = t_begin < t_end ? p.tile_info[t_begin] : TileInfo{};
-    if (ch == 0 && t_begin < t_end) prefetch_rows(ti_next);
+    // mode 2 reads dg, written by the mode-1 launch before it: nothing of this launch produces it, so one tile ahead is safe
+    if (t_begin < t_end) prefetch_rows(ti_next);
     for (int t = t_begin; t < t_end; ++t, ++it) {
       const TileInfo ti = ti_next;
       if (t + 1 < t_end) ti_next = p.tile_info[t + 1];
-      const int buf = it & 1;
       const uint32_t tph = it & 1;
-      uint8_t* tile = smem + DzSmem::tile + buf * 65536;
+      // C / DS (and D across a slide change) are free again once MMA-dZ / MMA-dqk of the previous tile have retired
+      if (it > 0) mbar_wait(z_bar, tph ^ 1);
       // ---- per-slide operands
       if (ti.slide != cur_slide) {
         cur_slide = ti.slide;
         const size_t sb = static_cast<size_t>(ti.slide) * kQ * kD;
         if (MODE == kDzNacDkg) {
-          // D row `et` = tanh(q_i)[et] in the dP slots (hi | hi | lo), zeros in the qk slots
-          named_bar_sync(1, 256);
-          float v[12];
+          // D[k = i][n = et] = tanh(q_i)[et] (|.| <= 1: no scale); the qk rows 6..11 stay zero
 #pragma unroll
-          for (int i = 0; i < kQ; ++i) { v[i] = tanhf(p.qp[sb + i * kD + et]); v[6 + i] = 0.f; }
-          uint32_t hi[6], lo[6];
-          split_bf16x12(v, hi, lo);
-          store_row48(Ds + et * 128, et & 7, hi, hi, lo);
+          for (int h = 0; h < 2; ++h) {
+            const int et = st + h * 128;
+#pragma unroll
+            for (int i = 0; i < kQ; ++i) store_mn_f16(Ds, i, et, tanhf(p.qp[sb + i * kD + et]));
+          }
         } else {
-          float dp[kQ], qv[kQ], red[12];
+          float dp[2][kQ], qv[2][kQ], red[12], qmax[kQ];
 #pragma unroll
-          for (int i = 0; i < kQ; ++i) {
-            dp[i] = p.dpooled[sb + i * kD + et];
-            qv[i] = p.qk[sb + i * kD + et];
-            // delta_i partial; consistent with g = dP . fp16(h): the hi-only pooled vector when a remainder part exists
-            red[i] = dp[i] * (p.pooled[sb + i * kD + et] - (p.pooled_lo != nullptr ? p.pooled_lo[sb + i * kD + et] : 0.f));
-            red[6 + i] = fabsf(dp[i]);                       // max |dP_i|
+          for (int j = 0; j < 12; ++j) red[j] = 0.f;
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) qmax[i] = 0.f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int et = st + h * 128;
+#pragma unroll
+            for (int i = 0; i < kQ; ++i) {
+              dp[h][i] = p.dpooled[sb + i * kD + et];
+              qv[h][i] = p.qk[sb + i * kD + et];
+              // delta_i partial; consistent with g = dP . fp16(h): the hi-only pooled vector when a remainder part exists
+              red[i] += dp[h][i] * (p.pooled[sb + i * kD + et] - (p.pooled_lo != nullptr ? p.pooled_lo[sb + i * kD + et] : 0.f));
+              red[6 + i] = fmaxf(red[6 + i], fabsf(dp[h][i]));       // max |dP_i|
+              qmax[i] = fmaxf(qmax[i], fabsf(qv[h][i]));             // max |qk_i|
+            }
           }
 #pragma unroll
           for (int i = 0; i < kQ; ++i) {
@@ -339,23 +358,30 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
             for (int o = 16; o > 0; o >>= 1) {
               red[i] += __shfl_xor_sync(0xffffffffu, red[i], o);
               red[6 + i] = fmaxf(red[6 + i], __shfl_xor_sync(0xffffffffu, red[6 + i], o));
+              qmax[i] = fmaxf(qmax[i], __shfl_xor_sync(0xffffffffu, qmax[i], o));
             }
           }
-          named_bar_sync(1, 256);                            // previous tile no longer reads scal
+          named_bar_sync(1, 128);                            // previous tile no longer reads scal
           if (lane == 0) {
 #pragma unroll
             for (int j = 0; j < 12; ++j) scal[32 + (warp - 2) * 12 + j] = red[j];
+#pragma unroll
+            for (int i = 0; i < kQ; ++i) scal[80 + (warp - 2) * 6 + i] = qmax[i];
           }
-          named_bar_sync(1, 256);
-          float dscale[kQ];
+          named_bar_sync(1, 128);
+          float dscale[kQ], qscale[kQ];
 #pragma unroll
           for (int i = 0; i < kQ; ++i) {
-            float s = 0.f, m = 0.f;
+            float s = 0.f, m = 0.f, mq = 0.f;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) { s += scal[32 + w * 12 + i]; m = fmaxf(m, scal[32 + w * 12 + 6 + i]); }
-            float inv;
+            for (int w = 0; w < 4; ++w) {
+              s += scal[32 + w * 12 + i]; m = fmaxf(m, scal[32 + w * 12 + 6 + i]); mq = fmaxf(mq, scal[80 + w * 6 + i]);
+            }
+            float inv, invq;
             dscale[i] = pow2_scale(m, &inv);
-            if (et == 0) {
+            qscale[i] = pow2_scale(mq, &invq);
+            if (st == 0) scal[24 + i] = invq;
+            if (st == 0) {
               float dsum = 0.f;
               if (MODE == kDzNacDh && p.dsuma != nullptr) {   // delta_i = dP_i . pooled_i + dsuma_i suma_i
                 dsum = p.dsuma[ti.slide * kQ + i];
@@ -365,31 +391,33 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
               scal[i] = s; scal[8 + i] = p.lse[ti.slide * kQ + i]; scal[16 + i] = inv; scal[160 + i] = dsum;
             }
           }
-          // D row `et`: k 0..5 dP hi, 6..11 qk hi, 16..27 the same hi values, 32..43 the lo parts
-          {
-            float v[12];
 #pragma unroll
-            for (int i = 0; i < kQ; ++i) { v[i] = dp[i]; v[6 + i] = qv[i]; }
-            uint32_t hi[6], lo[6];
-            split_bf16x12(v, hi, lo);
-            store_row48(Ds + et * 128, et & 7, hi, hi, lo);
+          for (int h = 0; h < 2; ++h) {
+            const int et = st + h * 128;
+            // D[k][n = et]: k 0..5 dP_i * scale_i, k 6..11 qk_i * qk_scale_i (power-of-two scales bring every row's
+            // maximum into [1, 2); the C rows carry the reciprocals)
+#pragma unroll
+            for (int i = 0; i < kQ; ++i) {
+              store_mn_f16(Ds, i, et, dp[h][i] * dscale[i]);
+              store_mn_f16(Ds, 6 + i, et, qv[h][i] * qscale[i]);
+            }
+            // DP[n][k = et]: rows 0..5 hi, 6..11 lo of dP_i * scale_i (fp16), K-major in 4 blocks of 64 k
+            float v6[kQ];
+#pragma unroll
+            for (int i = 0; i < kQ; ++i) v6[i] = dp[h][i] * dscale[i];
+            store_col_f16(DPs, et, v6);
           }
-          // DP[n][k = et]: rows 0..5 hi, 6..11 lo of dP_i * scale_i (fp16), K-major in 4 blocks of 64 k
-          float v6[kQ];
-#pragma unroll
-          for (int i = 0; i < kQ; ++i) v6[i] = dp[i] * dscale[i];
-          store_col_f16(DPs, et, v6);
         }
         fence_proxy_async_smem();
+        g_early = false;                         // (never set across a slide change)
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(op_bar);
-      named_bar_sync(1, 256);                  // scal[0..23] visible to everyone
+      named_bar_sync(1, 128);                  // scal[0..23] visible to everyone, D / DP complete
+      if (kHasG && leader && !g_early) issue_g(it);
 
-      // ---- per-row scalars (one patch row per thread of warps 2..5)
+      // ---- per-row scalars
       const bool valid = r < ti.nvalid;
       const size_t grow = static_cast<size_t>(ti.row0 + r);
-      if (ch == 0) {
+      {
         float c12[12];                         // C row: [a'_i | ds_i]  (mode 2: [dg_i | 0])
         float ds[kQ];                          // DS column (mode 2: dg_i gs)
         float dgmax = 0.f;                     // mode 1: max_i |dg_i| of this row
@@ -456,9 +484,21 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           for (int o = 16; o > 0; o >>= 1) dgmax = fmaxf(dgmax, __shfl_xor_sync(0xffffffffu, dgmax, o));
           if (lane == 0 && dgmax > 0.f) atomicMax(p.dg_max, __float_as_uint(dgmax));   // non-negative floats order like uints
         }
+        // C entries before the per-tile scale: [a'_i / dp_scale_i | ds_i / qk_scale_i]  (mode 2: [dg_i | -])
+        float cu[12];
+        float cmax = 0.f;
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
+          if (MODE == kDzNacDkg) { cu[i] = c12[i]; cu[6 + i] = 0.f; }
+          else { cu[i] = c12[i] * scal[16 + i]; cu[6 + i] = c12[6 + i] * scal[24 + i]; }
+          cmax = fmaxf(cmax, fmaxf(fabsf(cu[i]), fabsf(cu[6 + i])));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
         if (lane == 0) {
 #pragma unroll
           for (int i = 0; i < kQ; ++i) scal[128 + qd * 8 + i] = amax[i];
+          scal[128 + qd * 8 + 6] = cmax;
         }
         if (kLite) {
           // the coefficients of dz_n = mask_n * keep_scale * sum_j c12[j] D[j] leave as fp32 (48 B per patch)
@@ -468,24 +508,29 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
             dst[1] = make_float4(c12[4], c12[5], c12[6], c12[7]);
             dst[2] = make_float4(c12[8], c12[9], c12[10], c12[11]);
           }
-        } else {
-          uint32_t hi[6], lo[6];
-          split_bf16x12(c12, hi, lo);
-          store_row48(Cs + r * 128, r & 7, hi, lo, hi);     // k 16..27 lo (x D hi), 32..43 hi (x D lo)
         }
-        named_bar_sync(2, 128);                // tile maxima of |ds_i| from the four row warps
+        tc_fence_before();                     // every warp has read G before the leader may issue the next MMA-G
+        named_bar_sync(2, 128);                // tile maxima of |ds_i| and of the C entries from the four row warps
+        if (!kLite) {
+          // C[k][m = r] as fp16 with one power-of-two scale per tile (un-done on the accumulators by the output warps)
+          float inv_c;
+          const float sc_t = pow2_scale(fmaxf(fmaxf(scal[128 + 6], scal[136 + 6]), fmaxf(scal[144 + 6], scal[152 + 6])), &inv_c);
+          if (r == 0) scal[224 + tph] = inv_c;
+#pragma unroll
+          for (int j = 0; j < (MODE == kDzNacDkg ? 6 : 12); ++j) store_mn_f16(Cs, j, r, cu[j] * sc_t);
+        }
         float v6[kQ];
 #pragma unroll
         for (int i = 0; i < kQ; ++i) {
           if (MODE == kDzNacDkg) {
             v6[i] = ds[i];                     // already scaled by the batch-wide gs
-            if (r == 0) scal[24 + i] = inv_gs;
+            if (r == 0) scal[208 + tph * 8 + i] = inv_gs;
           } else {
             const float m = fmaxf(fmaxf(scal[128 + i], scal[136 + i]), fmaxf(scal[144 + i], scal[152 + i]));
             float inv;
             const float s = pow2_scale(m, &inv);
             v6[i] = ds[i] * s;
-            if (r == 0) scal[24 + i] = inv;    // un-scale factor for the Q read-back
+            if (r == 0) scal[208 + tph * 8 + i] = inv;    // un-scale factor for the Q read-back
           }
         }
         store_col_f16(DSs, r, v6);
@@ -496,14 +541,49 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(c_bar);
-      if (ch == 0 && t + 1 < t_end) prefetch_rows(ti_next);     // in flight while this tile's output is written
-
-      // ---- output tile, in place over the input tile (row r, column half ch)
-      if (kHasB && prev_t >= 0) read_db(prev_t, tph ^ 1);     // before this tile's w_bar arrival lets MMA-db overwrite it
+      if (t + 1 < t_end) prefetch_rows(ti_next);
+      // MMA-G of the next tile already now (same slide: same dP operand), so that it has retired when that tile's scalars
+      // start; every row warp has consumed this tile's G (named barrier 2 above)
+      g_early = false;
+      if (kHasG && t + 1 < t_end && ti_next.slide == ti.slide) {
+        if (leader) { tc_fence_after(); issue_g(it + 1); }
+        g_early = true;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- 8 output warps (row r, column half ch)
+    const int qd = warp & 3;                   // TMEM lane quadrant
+    const int ch = (warp - 6) >> 2;            // column half (output tile) / feature half (Q, b read-back)
+    const int r = qd * 32 + lane;              // patch row of the tile
+    float gs = 1.f, inv_gs = 1.f;
+    if (MODE == kDzNacDkg) gs = gate_scale(p.dg_max, &inv_gs);
+    int it = 0;
+    int prev_t = -1;
+    // b partial of tile `tt` (its MMA-db is issued behind the NEXT tile's MMA-dZ): read at the end of the next tile, so
+    // nobody waits for that MMA -- by then it has long retired
+    auto read_db = [&](int tt, uint32_t parity) {
+      mbar_wait(b_bar, parity);
+      tc_fence_after();
+      uint32_t bv[16];
+      tmem_ld_32x32b_x16(tmem_base + kColB + ch * 16 + (static_cast<uint32_t>(qd * 32) << 16), bv);
+      tmem_ld_wait();
+      p.part_db[static_cast<size_t>(tt) * kD + ch * 128 + qd * 32 + lane] = __uint_as_float(bv[0]) * inv_gs;
+      tc_fence_before();
+    };
+    TileInfo ti_next = t_begin < t_end ? p.tile_info[t_begin] : TileInfo{};
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const TileInfo ti = ti_next;
+      if (t + 1 < t_end) ti_next = p.tile_info[t + 1];
+      const int buf = it % kDzBufs;
+      const uint32_t tph = it & 1;
+      uint8_t* tile = smem + DzSmem::tile + buf * 65536;
+      const bool valid = r < ti.nvalid;
+      const size_t grow = static_cast<size_t>(ti.row0 + r);
       mbar_wait(z_bar, tph);
       tc_fence_after();
       uint16_t* grow_out = static_cast<uint16_t*>(p.out) + grow * kD;
       const bool direct = ti.nvalid != kTileM;     // ragged tile: rows are stored by the threads, not by TMA
+      const float zs = scal[224 + tph] * (MODE == kDzNacDkg ? gs : p.keep_scale);   // un-scale of Z x the mode's output factor
       if (kLite) {
         // mask bits of this row's 128 features of column half ch: bit = h > 0 (ReLU and dropout zero the same way)
         uint32_t w4[4] = {0u, 0u, 0u, 0u};
@@ -542,11 +622,11 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float z = __uint_as_float(v[j + e]);
-            if (MODE == kDzNacDkg) o8[e] = (1.f - hh[e] * hh[e]) * z * gs;
+            if (MODE == kDzNacDkg) o8[e] = (1.f - hh[e] * hh[e]) * z * zs;
             // NaCAGaT: -0.0 marks a unit masked by ReLU / dropout (bag_dhk_kernel reads the mask from this tile instead
             // of re-reading the saved activations, 0.27 GB); the +0 addend turns a live unit's exact -0 product into +0
-            else if (MODE == kDzNacDh) o8[e] = hh[e] > 0.f ? fmaf(z, p.keep_scale, 0.f) : -0.f;
-            else o8[e] = hh[e] > 0.f ? z * p.keep_scale : 0.f;
+            else if (MODE == kDzNacDh) o8[e] = hh[e] > 0.f ? fmaf(z, zs, 0.f) : -0.f;
+            else o8[e] = hh[e] > 0.f ? z * zs : 0.f;
           }
           uint4 o;
           if (MODE == kDzNacDkg) {
@@ -567,13 +647,15 @@ bag_bwd_dz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         tmem_ld_wait();
         float* dst = p.part_dqk + static_cast<size_t>(t) * (kQ * kD) + ch * 128 + qd * 32 + lane;
 #pragma unroll
-        for (int i = 0; i < kQ; ++i) dst[i * kD] = (__uint_as_float(qv[i]) + __uint_as_float(qv[i + 6])) * scal[24 + i];
+        for (int i = 0; i < kQ; ++i)
+          dst[i * kD] = (__uint_as_float(qv[i]) + __uint_as_float(qv[i + 6])) * scal[208 + tph * 8 + i];
       }
+      // column sums of the previous output tile, before this tile's w_bar arrival lets the next MMA-db overwrite them
+      if (kHasB && prev_t >= 0) read_db(prev_t, tph ^ 1);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(w_bar);
-
       prev_t = t;
     }
     if (kHasB && prev_t >= 0) read_db(prev_t, (it - 1) & 1);
