@@ -21,10 +21,14 @@ namespace mpo {
 // ------------------------------------------------------------------------------------------------
 // Row-expand stage on tcgen05, three modes sharing one pipeline.  Per 128-patch tile (one persistent CTA per SM,
 // contiguous tile ranges per CTA):
-//   TMA      : a saved fp16 tile [128 x 256] (H, or tanh(k) in mode 2) -> shared memory (two buffers, one tile ahead)
+//   TMA      : a saved fp16 tile [128 x 256] (H, or tanh(k) in mode 2) -> shared memory (three buffers, two tiles ahead)
 //   MMA-G    : G[128 x 16]    = H dP^T            (dP of the slide as fp16 hi/lo rows, scaled per query to ~1)
-//   threads  : per-patch scalars (softmax weights and their gradients), written as tiny bf16 / fp16 operands
-//   MMA-dZ   : Z[128 x 256]   = [a | ds] [dP ; qk]   (bf16 hi/lo, K = 48)       -> TMEM
+//   threads  : per-patch scalars (softmax weights and their gradients), written as tiny fp16 operands
+//   MMA-dZ   : Z[128 x 256]   = [a | ds] [dP ; qk]   (fp16, ONE K = 16 step; both operands M / N-major so that they take
+//              4 + 8 KB instead of the 16 + 32 KB of 128-byte-swizzled K-major rows -- the room for the third tile buffer.
+//              Power-of-two scales keep fp16's range: every row of [dP ; qk] is brought to a maximum in [1, 2) per slide,
+//              [a | ds] carries the reciprocals and one more scale per tile that the output warps take off the
+//              accumulators; two fp16 roundings per product are a quarter of the bf16 rounding of the stored dz)
 //   MMA-dqk  : Q^T[256 x 16]  = tile^T ds            (tile read M-major, power-of-two scale on ds)
 //   threads  : out = f(Z, tile) -> 16-bit, written IN PLACE over the tile; TMA store to HBM
 //   MMA-db   : b[256] = out^T 1                      (out tile read M-major against a ones operand)
