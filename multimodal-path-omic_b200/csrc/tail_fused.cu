@@ -9,10 +9,12 @@
 //   wgrad_kernel    every weight / bias / LayerNorm gradient of the tail as one grouped launch (twice per step)
 // One thread-block cluster of 4 CTAs owns S slides (M = 6 S token rows; S = 1 up to 35 slides per step).  Activations
 // are replicated in the shared memory of the 4 CTAs; every linear layer is split by output columns (two 32-column
-// blocks = two attention heads per CTA), its weight slice is streamed L2 -> shared memory through a 3-stage cp.async
-// ring that runs ahead across layer boundaries, results are broadcast to the peers through distributed shared
-// memory, and the per-row work (LayerNorm, the 6x6 attention of the CTA's heads, pooling soft-max, survival head,
-// loss) happens in place.  The one-slide kernels fit twice per SM (113 KB, 128 registers), so the two roles hide each
+// blocks = two attention heads per CTA), its weight slice is streamed L2 -> shared memory through a 3-slot ring of 16 KB
+// chunks that runs ahead across layer boundaries (path kernels: one TMA tensor copy per chunk behind a per-slot
+// mbarrier; pre / SNN kernels and odd shapes: per-thread cp.async), results are broadcast to the peers through
+// distributed shared memory, and the per-row work (LayerNorm, the 6x6 attention of the CTA's heads, pooling soft-max,
+// survival head, loss) happens in place.  The GEMM blocks are paced by the shared-memory pipe, not by latency or
+// arithmetic (profiles/r2d_tail_phase_timing.txt): hence the half-warp step (gemm_step2) and the TMA ring.  The one-slide kernels fit twice per SM (113 KB, 128 registers), so the two roles hide each
 // other's latencies.  Slides never mix inside these kernels, so no grid-wide synchronisation is needed; only the
 // weight gradients sum over slides, and they are deferred to wgrad_kernel.  fp32 CUDA-core arithmetic throughout
 // (packed FFMA2), the 1e-3 parity gate of SURVEY.md 8c.
