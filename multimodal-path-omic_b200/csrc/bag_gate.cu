@@ -18,6 +18,7 @@
 #include "mpo_ptx.cuh"
 #include "mpo_common.cuh"
 #include "launchers.h"
+#include <cstdlib>
 
 namespace mpo {
 
@@ -106,6 +107,18 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           mbar_expect_tx(&a_full[cb], 32768);
           tma_load_2d(smem + GateSmem::A + cb * 16384, &tm_h, &a_full[cb], cb * 64, row0, pol_stream);
           tma_load_2d(smem + GateSmem::Alo + cb * 16384, &tm_hlo, &a_full[cb], cb * 64, row0, pol_stream);
+        }
+        // The one tile buffer (128 KB of (hi, lo)) is busy until this tile's pooled MMAs have retired, so the next tile's
+        // load cannot overlap anything on the SM.  Its DRAM half can: MPO_GATE_L2PF=1 prefetches the next tile into L2
+        // here (19 MB for the whole GPU).  Measured neutral (NaCAGaT step 1.996 / 1.998 ms with, 1.985 / 1.992 ms without):
+        // the tile load is not what the serial tile chain (32 key MMAs -> tanh epilogue -> 32 pooled MMAs) waits for.
+        if (p.l2_prefetch && t + 1 < t_end) {
+          const int row1 = p.tile_info[t + 1].row0;
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) {
+            tma_prefetch_l2_2d(&tm_h, cb * 64, row1);
+            tma_prefetch_l2_2d(&tm_hlo, cb * 64, row1);
+          }
         }
         for (int kb = 0; kb < 4; ++kb) {          // W_k is re-streamed from L2 for every tile, one 64-wide K block at a time
           mbar_wait(&w_empty[ws], wph ^ 1);
@@ -587,7 +600,11 @@ cudaError_t launch_bag_gate(const CUtensorMap& tm_h, const CUtensorMap& tm_hlo, 
   }
   if (prm.num_tiles <= 0) return cudaSuccess;
   const int grid = prm.num_tiles < num_sms ? prm.num_tiles : num_sms;
-  bag_gate_kernel<<<grid, kGateFwdThreads, kGateSmemBytes, stream>>>(tm_h, tm_hlo, tm_w, prm);
+  static int l2pf = -1;
+  if (l2pf < 0) { const char* e = getenv("MPO_GATE_L2PF"); l2pf = (e != nullptr && atoi(e) != 0) ? 1 : 0; }
+  BagGateParams prm_l = prm;
+  prm_l.l2_prefetch = l2pf;
+  bag_gate_kernel<<<grid, kGateFwdThreads, kGateSmemBytes, stream>>>(tm_h, tm_hlo, tm_w, prm_l);
   count_launch();
   return cudaGetLastError();
 }

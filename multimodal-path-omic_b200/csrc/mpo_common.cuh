@@ -65,6 +65,7 @@ struct BagGateParams {
   const uint32_t* seed_dev;
   uint32_t drop_thr;           // attention dropout (blocks.py:189-190): drop when 8 random bits < drop_thr
   float drop_scale;
+  int l2_prefetch;             // prefetch the next tile into L2 while this one occupies the tile buffer (MPO_GATE_L2PF)
 };
 
 // NaCAGaT backward, key-projection path (bag_gate.cu: bag_dhk_kernel)
