@@ -167,7 +167,7 @@ __device__ __forceinline__ int cluster_rank() {
   return static_cast<int>(r);
 }
 __device__ __forceinline__ void cluster_sync() {
-  const long long pt0 = PROF_T();
+  [[maybe_unused]] const long long pt0 = PROF_T();
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   PROF_ADD(6, PROF_T() - pt0);
 }
@@ -296,7 +296,8 @@ __device__ __forceinline__ void pipe_issue(uint32_t tbl, uint32_t ring, int n, i
   }
   if (c < n) {
     const int t = threadIdx.x;
-    uint32_t b_lo, b_hi, rs, pk;
+    uint32_t b_lo, b_hi, pk;
+    [[maybe_unused]] uint32_t rs;      // (the per-rank stride: folded into the base by pipe_init)
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b_lo), "=r"(b_hi), "=r"(rs), "=r"(pk) : "r"(tbl + c * 16));
     const float* src = reinterpret_cast<const float*>(static_cast<unsigned long long>(b_lo) |
                                                       (static_cast<unsigned long long>(b_hi) << 32));
@@ -425,8 +426,8 @@ __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __
   const bool tma = maps != nullptr;
   uint32_t phase = pp.phase;
   int cons = pp.cons, slot = pp.slot;
-  const long long pt_in = PROF_T();
-  long long pt_d = pt_in;
+  [[maybe_unused]] const long long pt_in = PROF_T();
+  [[maybe_unused]] long long pt_d = pt_in;
   unsigned long long acc[kHalf ? 1 : M];
   unsigned long long acc2[kHalf ? M : 1][2];
 #pragma unroll
@@ -434,7 +435,7 @@ __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __
 #pragma unroll
   for (int r = 0; r < (kHalf ? M : 1); ++r) acc2[r][0] = acc2[r][1] = 0ull;
   for (int kb = 0; kb < Ktot; kb += KC) {
-    const long long pt_a = PROF_T();
+    [[maybe_unused]] const long long pt_a = PROF_T();
     const int kc = min(KC, Ktot - kb);
     if (tma) {
       mbar_wait_u32(bars + slot * 8, (phase >> slot) & 1u);
@@ -443,9 +444,9 @@ __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __
       cp_async_wait<NST - 2>();
     }
     __syncthreads();
-    const long long pt_b = PROF_T();
+    [[maybe_unused]] const long long pt_b = PROF_T();
     pipe_issue(tbl, ring, nchunks, cons + NST - 1, slot == 0 ? NST - 1 : slot - 1, bars, maps);     // the slot freed by chunk cons - 1
-    const long long pt_c = PROF_T();
+    [[maybe_unused]] const long long pt_c = PROF_T();
     PROF_ADD(2, pt_b - pt_a); PROF_ADD(3, pt_c - pt_b);
     const uint32_t wsm = ring + slot * stride;
     ++cons;
@@ -521,7 +522,7 @@ __device__ __noinline__ void gemm_block(Pipe& pp, uint32_t red0, const float* __
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + r * 128), "f"(v) : "memory");
   }
   __syncthreads();
-  const long long pt_e = PROF_T();
+  [[maybe_unused]] const long long pt_e = PROF_T();
   PROF_ADD(5, pt_e - pt_d); PROF_ADD(1, pt_e - pt_in); PROF_ADD(7, 1);
 }
 // sums the 8 k-slices; thread (warp, lane) finishes outputs (row warp + 8 i, column lane): epi(row, i, value)
