@@ -287,6 +287,7 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           tmem_ld_32x32b_x32(acc_col + (static_cast<uint32_t>(qd * 32) << 16) + col0, v);
           tmem_ld_wait();
         }
+        uint4 lo_even = make_uint4(0u, 0u, 0u, 0u);     // remainder chunk of the even 8-column group, stored with the odd one
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           float h[8];
@@ -338,7 +339,9 @@ bag_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             lo.y = pack_f16x2(h[2] - a1.x, h[3] - a1.y);
             lo.z = pack_f16x2(h[4] - a2.x, h[5] - a2.y);
             lo.w = pack_f16x2(h[6] - a3.x, h[7] - a3.y);
-            *reinterpret_cast<uint4*>(p.h_lo_out + static_cast<size_t>(grow) * kD + col0 + j) = lo;
+            // the thread owns the row: two chunks = one full 32-byte sector per store instead of two half-filled ones
+            if ((j & 8) == 0) lo_even = lo;
+            else st_global_256(p.h_lo_out + static_cast<size_t>(grow) * kD + col0 + j - 8, lo_even, lo);
           }
           const int j16 = (col0 + j) >> 3;           // 16-byte chunk index within the 512 B row
           const int cb = j16 >> 3, jj = j16 & 7;     // 64-feature block, chunk within the 128 B swizzle row

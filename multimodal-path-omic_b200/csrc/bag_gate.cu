@@ -236,6 +236,7 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + kColK + (static_cast<uint32_t>(qd * 32) << 16) + col0, v);
         tmem_ld_wait();
+        uint4 pk_even = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           float tt[8];
@@ -254,7 +255,9 @@ bag_gate_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
             uint4 pk;
             pk.x = pack_f16x2(tt[0], tt[1]); pk.y = pack_f16x2(tt[2], tt[3]);
             pk.z = pack_f16x2(tt[4], tt[5]); pk.w = pack_f16x2(tt[6], tt[7]);
-            *reinterpret_cast<uint4*>(p.t_out + grow * kD + col0 + j) = pk;
+            // the thread owns the row: two chunks = one full 32-byte sector per store
+            if ((j & 8) == 0) pk_even = pk;
+            else st_global_256(p.t_out + grow * kD + col0 + j - 8, pk_even, pk);
           }
         }
       }
