@@ -520,7 +520,7 @@ bag_dhk_kernel(const __grid_constant__ CUtensorMap tm_dkg, const __grid_constant
     if (t_begin < t_end) {
       const uint4* zp0 = row_ptr(ti_next);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) zin[q] = zp0[q];
+      for (int q = 0; q < 16; q += 2) ld_global_256(zp0 + q, zin[q], zin[q + 1]);
     }
     for (int t = t_begin; t < t_end; ++t, ++it) {
       const TileInfo ti = ti_next;
@@ -561,8 +561,9 @@ bag_dhk_kernel(const __grid_constant__ CUtensorMap tm_dkg, const __grid_constant
           if (direct && valid) *reinterpret_cast<uint4*>(p.dz + grow * kD + col0 + j) = o;
         }
         if (has_next) {
+          // (one full 32-byte sector per load: the thread owns the row)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) zin[c4 * 4 + q] = zn[c4 * 4 + q];
+          for (int q = 0; q < 4; q += 2) ld_global_256(zn + c4 * 4 + q, zin[c4 * 4 + q], zin[c4 * 4 + q + 1]);
         }
       }
       tc_fence_before();
